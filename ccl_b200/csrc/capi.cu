@@ -1,0 +1,1109 @@
+// C ABI of the B200 Limber path (include/ccl_b200.h).  Host-side bookkeeping only: flat input
+// arrays are staged into one arena, uploaded with a single copy, and every derived table
+// (Akima / natural-cspline coefficients, bicubic derivative planes, index LUTs) is built by
+// device kernels.  No numerical work of the hot path happens on the CPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ccl_b200.h"
+#include "tables.h"
+
+using namespace cclb;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_device = -1;
+
+void set_err(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+bool cuda_ok(cudaError_t e, const char* what, int* status) {
+  if (e == cudaSuccess) return true;
+  set_err("ccl_b200: CUDA failure in %s: %s", what, cudaGetErrorString(e));
+  if (status) *status = CCL_B200_ERROR_CUDA;
+  return false;
+}
+
+bool use_device(int* status) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_err("ccl_b200: no CUDA device available (%s); this library has no CPU fallback",
+            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (status) *status = CCL_B200_ERROR_CUDA;
+    return false;
+  }
+  if (g_device >= 0) return cuda_ok(cudaSetDevice(g_device), "cudaSetDevice", status);
+  return true;
+}
+
+constexpr size_t ALIGN_D = 4;  // raw region alignment in doubles (32 B)
+
+// ---- plans: offsets into the arena, turned into device descriptors at commit ----
+struct S1Plan {
+  bool present = false;
+  int kind = 0;  // 0 akima, 1 natural cspline, 2 grid only (nodes + LUT)
+  int n = 0, nlut = 0;
+  size_t x_off = 0, y_off = 0;               // raw region, in doubles
+  size_t co_off = 0, lut_off = 0, scr_off = 0;  // derived region, in bytes
+  double x0 = 0, xn = 0;
+};
+
+struct F2DPlan {
+  F2D flags;  // pointer members unused
+  S1Plan fk, fa, gk, ga;
+  size_t z_off = 0, tab_off = 0, scr_off = 0;
+  int nk = 0, na = 0;
+};
+
+struct TracerPlan {
+  int der_bessel = 0, der_angles = 0;
+  double chi_min = 0, chi_max = 1e15;
+  S1Plan kernel;
+  bool has_transfer = false;
+  F2DPlan transfer;
+};
+
+struct CosmoPlan {
+  S1Plan achi, growth;
+  double chi_max_nokernel = 1e15;
+  bool has_psp = false;
+  F2DPlan psp;
+  std::vector<TracerPlan> tracers;
+};
+
+struct HostBuf {  // growable host staging; pinned once it is large
+  double* p = nullptr;
+  size_t size = 0, cap = 0;
+  bool pinned = false;
+  ~HostBuf() { release(); }
+  void release() {
+    if (p) {
+      if (pinned) cudaFreeHost(p); else free(p);
+    }
+    p = nullptr; size = cap = 0;
+  }
+  bool reserve(size_t n) {
+    if (n <= cap) return true;
+    size_t ncap = std::max(n, cap * 2);
+    bool want_pinned = ncap * sizeof(double) >= (size_t(1) << 20);
+    double* q = nullptr;
+    if (want_pinned) {
+      if (cudaHostAlloc((void**)&q, ncap * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        want_pinned = false;
+      }
+    }
+    if (!want_pinned) q = (double*)malloc(ncap * sizeof(double));
+    if (!q) return false;
+    if (p) memcpy(q, p, size * sizeof(double));
+    if (p) { if (pinned) cudaFreeHost(p); else free(p); }
+    p = q; cap = ncap; pinned = want_pinned;
+    return true;
+  }
+  size_t put(const double* src, size_t n) {
+    size_t off = (size + ALIGN_D - 1) / ALIGN_D * ALIGN_D;
+    if (!reserve(off + n)) return (size_t)-1;
+    if (off > size) memset(p + size, 0, (off - size) * sizeof(double));
+    memcpy(p + off, src, n * sizeof(double));
+    size = off + n;
+    return off;
+  }
+};
+
+struct DevBuf {
+  char* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  bool reserve(size_t n, int* status) {
+    if (n <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    if (!cuda_ok(cudaMalloc((void**)&p, n), "cudaMalloc(arena)", status)) return false;
+    cap = n;
+    return true;
+  }
+};
+
+// One arena with the table packs of `cosmos.size()` cosmologies.
+struct TableSet {
+  int device = 0;
+  HostBuf raw;
+  size_t derived = 0;  // bytes planned in the derived region
+  std::vector<CosmoPlan> cosmos;
+  DevBuf dev;          // [raw | derived | descriptors]
+  DevBuf jobs;         // prep job arrays
+  size_t raw_bytes = 0, desc_off = 0;
+  Cosmo* d_cosmos = nullptr;
+  F2D* d_psp = nullptr;
+  Tracer* d_tracers = nullptr;
+  std::vector<Cosmo> h_cosmos;
+  std::vector<F2D> h_psp;
+  std::vector<Tracer> h_tracers;
+  std::vector<size_t> tracer_base;  // first tracer of cosmology i in h_tracers
+  bool committed = false;
+  unsigned long long last_h2d = 0;
+
+  size_t derive(size_t bytes) {
+    size_t off = (derived + 31) / 32 * 32;
+    derived = off + bytes;
+    return off;
+  }
+
+  static int lut_size(int n) { return std::min(std::max(n > 1000 ? 2 * n : 4 * n, 64), 1 << 15); }
+
+  bool plan_s1(S1Plan& s, int kind, int n, const double* x, const double* y, int* status) {
+    s.present = true; s.kind = kind; s.n = n;
+    s.x_off = raw.put(x, n);
+    if (y) s.y_off = raw.put(y, n);
+    if (s.x_off == (size_t)-1 || s.y_off == (size_t)-1) { *status = CCL_B200_ERROR_MEMORY; return false; }
+    s.x0 = x[0]; s.xn = x[n - 1];
+    for (int i = 1; i < n; ++i)
+      if (!(x[i] > x[i - 1])) {  // gsl_spline_init requires strictly increasing x
+        set_err("ccl_b200: spline nodes must be strictly increasing");
+        *status = CCL_B200_ERROR_SPLINE;
+        return false;
+      }
+    s.nlut = lut_size(n);
+    s.lut_off = derive(sizeof(int) * s.nlut);
+    if (kind != 2) s.co_off = derive(sizeof(double4) * (n - 1));
+    if (kind == 1) s.scr_off = derive(sizeof(double) * 3 * n);
+    return true;
+  }
+
+  // ccl_f2d_t_new (src/ccl_f2d.c:92-201)
+  bool plan_f2d(F2DPlan& f, int na, const double* a_arr, int nk, const double* lk_arr,
+                const double* fka_arr, const double* fk_arr, const double* fa_arr, int is_factorizable,
+                int extrap_order_lok, int extrap_order_hik, int extrap_linear_growth, int is_fka_log,
+                double growth_factor_0, int growth_exponent, int* status) {
+    memset(&f.flags, 0, sizeof(F2D));
+    F2D& g = f.flags;
+    is_factorizable = is_factorizable || (a_arr == nullptr) || (lk_arr == nullptr) || (fka_arr == nullptr);
+    g.is_factorizable = is_factorizable;
+    g.is_k_constant = ((lk_arr == nullptr) || ((fka_arr == nullptr) && (fk_arr == nullptr)));
+    g.is_a_constant = ((a_arr == nullptr) || ((fka_arr == nullptr) && (fa_arr == nullptr)));
+    g.extrap_order_lok = extrap_order_lok;
+    g.extrap_order_hik = extrap_order_hik;
+    g.extrap_linear_growth = extrap_linear_growth;
+    g.is_log = is_fka_log;
+    g.growth_factor_0 = growth_factor_0;
+    g.growth_exponent = growth_exponent;
+    if (!g.is_k_constant) { g.lkmin = lk_arr[0]; g.lkmax = lk_arr[nk - 1]; }
+    if (!g.is_a_constant) { g.amin = a_arr[0]; g.amax = a_arr[na - 1]; }
+    if ((extrap_order_lok > 2) || (extrap_order_lok < 0) || (extrap_order_hik > 2) || (extrap_order_hik < 0))
+      *status = CCL_B200_ERROR_INCONSISTENT;
+    if ((extrap_linear_growth != GROWTH_CCL) && (extrap_linear_growth != GROWTH_CONST) &&
+        (extrap_linear_growth != GROWTH_NONE))
+      *status = CCL_B200_ERROR_INCONSISTENT;
+    if (*status) { set_err("ccl_b200: ccl_f2d_t_new(): inconsistent extrapolation settings"); return false; }
+    if (g.is_factorizable) {
+      if (!g.is_k_constant) {
+        if (nk < 3) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: cspline needs >= 3 nodes"); return false; }
+        if (!plan_s1(f.fk, 1, nk, lk_arr, fk_arr, status)) return false;
+        g.has_fk = 1;
+      }
+      if (!g.is_a_constant) {
+        if (na < 3) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: cspline needs >= 3 nodes"); return false; }
+        if (!plan_s1(f.fa, 1, na, a_arr, fa_arr, status)) return false;
+        g.has_fa = 1;
+      }
+    } else if (!(g.is_k_constant || g.is_a_constant)) {
+      if (nk < 4 || na < 4) {  // gsl_interp2d_bicubic min_size
+        *status = CCL_B200_ERROR_MEMORY;
+        set_err("ccl_b200: bicubic interpolation needs >= 4 nodes per axis");
+        return false;
+      }
+      if (!plan_s1(f.gk, 2, nk, lk_arr, nullptr, status)) return false;
+      if (!plan_s1(f.ga, 2, na, a_arr, nullptr, status)) return false;
+      f.nk = nk; f.na = na;
+      f.z_off = raw.put(fka_arr, (size_t)nk * na);
+      if (f.z_off == (size_t)-1) { *status = CCL_B200_ERROR_MEMORY; return false; }
+      f.tab_off = derive(sizeof(double4) * (size_t)nk * na);
+      f.scr_off = derive(sizeof(double) * 2 * (size_t)(nk + na));
+      g.has_fka = 1;
+    }
+    return true;
+  }
+
+  // ccl_cl_tracer_t_new (src/ccl_tracers.c:569-691)
+  bool plan_tracer(TracerPlan& t, double chi_max_nokernel, int der_bessel, int der_angles, int n_w,
+                   const double* chi_w, const double* w_w, int na_ka, const double* a_ka, int nk_ka,
+                   const double* lk_ka, const double* fka_arr, const double* fk_arr, const double* fa_arr,
+                   int is_fka_log, int is_factorizable, int extrap_order_lok, int extrap_order_hik,
+                   int* status) {
+    if ((der_angles < 0) || (der_angles > 2)) {
+      *status = CCL_B200_ERROR_INCONSISTENT;
+      set_err("ccl_tracers.c: ccl_cl_tracer_new(): der_angles must be between 0 and 2\n");
+    }
+    if ((der_bessel < -1) || (der_bessel > 2)) {
+      *status = CCL_B200_ERROR_INCONSISTENT;
+      set_err("ccl_tracers.c: ccl_cl_tracer_new(): der_bessel must be between -1 and 2\n");
+    }
+    if (*status) return false;
+    t.der_angles = der_angles;
+    t.der_bessel = der_bessel;
+    t.chi_min = 0;
+    t.chi_max = 1E15;
+    const bool has_kernel = (n_w > 0) && (chi_w != nullptr) && (w_w != nullptr);
+    if (has_kernel) {
+      if (n_w < 5) {  // gsl_spline_alloc(akima) fails below 5 points -> CCL_ERROR_MEMORY
+        *status = CCL_B200_ERROR_MEMORY;
+        set_err("ccl_b200: tracer kernel needs >= 5 nodes (akima)");
+        return false;
+      }
+      if (!plan_s1(t.kernel, 0, n_w, chi_w, w_w, status)) return false;
+      double w_max = fabs(w_w[0]);
+      for (int i = 0; i < n_w; ++i)
+        if (fabs(w_w[i]) >= w_max) w_max = fabs(w_w[i]);
+      w_max *= 5E-4;  // CCL_FRAC_RELEVANT, include/ccl_tracers.h:13
+      t.chi_min = chi_w[0];
+      t.chi_max = chi_w[n_w - 1];
+      for (int i = 0; i < n_w - 1; ++i)
+        if (fabs(w_w[i + 1]) >= w_max) { t.chi_min = chi_w[i]; break; }
+      for (int i = n_w - 1; i >= 1; --i)
+        if (fabs(w_w[i - 1]) >= w_max) { t.chi_max = chi_w[i]; break; }
+    } else {
+      t.chi_min = 0;
+      t.chi_max = chi_max_nokernel;
+    }
+    if ((fka_arr != nullptr) || (fk_arr != nullptr) || (fa_arr != nullptr)) {
+      t.has_transfer = true;
+      if (!plan_f2d(t.transfer, na_ka, a_ka, nk_ka, lk_ka, fka_arr, fk_arr, fa_arr, is_factorizable,
+                    extrap_order_lok, extrap_order_hik, GROWTH_CONST, is_fka_log, 1.0, 0, status))
+        return false;
+    }
+    return true;
+  }
+
+  void reset() {
+    raw.size = 0;
+    derived = 0;
+    for (auto& c : cosmos) c = CosmoPlan();
+    committed = false;
+  }
+
+  // ---- commit: upload + device preparation ----
+  Spline1D mk_s1(const S1Plan& s, char* base_raw, char* base_der) const {
+    Spline1D d;
+    memset(&d, 0, sizeof(d));
+    if (!s.present) return d;
+    d.x = reinterpret_cast<const double*>(base_raw) + s.x_off;
+    d.co = reinterpret_cast<const double4*>(base_der + s.co_off);
+    d.lut = reinterpret_cast<const int*>(base_der + s.lut_off);
+    d.n = s.n; d.nlut = s.nlut; d.x0 = s.x0; d.xn = s.xn;
+    d.inv_bin = s.nlut / (s.xn - s.x0);
+    return d;
+  }
+
+  F2D mk_f2d(const F2DPlan& f, char* br, char* bd) const {
+    F2D d = f.flags;
+    d.fk = mk_s1(f.fk, br, bd);
+    d.fa = mk_s1(f.fa, br, bd);
+    d.gk = mk_s1(f.gk, br, bd);
+    d.ga = mk_s1(f.ga, br, bd);
+    d.tab = d.has_fka ? reinterpret_cast<const double4*>(bd + f.tab_off) : nullptr;
+    return d;
+  }
+
+  void jobs_s1(const S1Plan& s, char* br, char* bd, std::vector<AkimaJob>& ak, std::vector<CsplineJob>& cs,
+               std::vector<LutJob>& lu) const {
+    if (!s.present) return;
+    const double* x = reinterpret_cast<const double*>(br) + s.x_off;
+    const double* y = reinterpret_cast<const double*>(br) + s.y_off;
+    lu.push_back(LutJob{x, reinterpret_cast<int*>(bd + s.lut_off), s.n, s.nlut});
+    if (s.kind == 0) ak.push_back(AkimaJob{x, y, reinterpret_cast<double4*>(bd + s.co_off), s.n});
+    else if (s.kind == 1)
+      cs.push_back(CsplineJob{x, y, reinterpret_cast<double4*>(bd + s.co_off),
+                              reinterpret_cast<double*>(bd + s.scr_off), s.n});
+  }
+
+  void jobs_f2d(const F2DPlan& f, char* br, char* bd, std::vector<AkimaJob>& ak, std::vector<CsplineJob>& cs,
+                std::vector<LutJob>& lu, std::vector<BicubicJob>& bc, int& max_nk, int& max_na) const {
+    jobs_s1(f.fk, br, bd, ak, cs, lu);
+    jobs_s1(f.fa, br, bd, ak, cs, lu);
+    jobs_s1(f.gk, br, bd, ak, cs, lu);
+    jobs_s1(f.ga, br, bd, ak, cs, lu);
+    if (f.flags.has_fka) {
+      bc.push_back(BicubicJob{reinterpret_cast<const double*>(br) + f.gk.x_off,
+                              reinterpret_cast<const double*>(br) + f.ga.x_off,
+                              reinterpret_cast<const double*>(br) + f.z_off,
+                              reinterpret_cast<double4*>(bd + f.tab_off),
+                              reinterpret_cast<double*>(bd + f.scr_off), f.nk, f.na});
+      max_nk = std::max(max_nk, f.nk);
+      max_na = std::max(max_na, f.na);
+    }
+  }
+
+  bool commit(cudaStream_t stream, int* status) {
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice", status)) return false;
+    raw_bytes = (raw.size * sizeof(double) + 255) / 256 * 256;
+    const size_t der_bytes = (derived + 255) / 256 * 256;
+    size_t ntr = 0;
+    for (auto& c : cosmos) ntr += c.tracers.size();
+    const size_t nc = cosmos.size();
+    const size_t desc_bytes = nc * sizeof(Cosmo) + nc * sizeof(F2D) + ntr * sizeof(Tracer) + 256;
+    desc_off = raw_bytes + der_bytes;
+    if (!dev.reserve(desc_off + desc_bytes, status)) return false;
+    char* br = dev.p;
+    char* bd = dev.p + raw_bytes;
+    d_cosmos = reinterpret_cast<Cosmo*>(dev.p + desc_off);
+    d_psp = reinterpret_cast<F2D*>(d_cosmos + nc);
+    d_tracers = reinterpret_cast<Tracer*>(d_psp + nc);
+    if (raw.size &&
+        !cuda_ok(cudaMemcpyAsync(br, raw.p, raw.size * sizeof(double), cudaMemcpyHostToDevice, stream),
+                 "H2D(raw tables)", status))
+      return false;
+    last_h2d = raw.size * sizeof(double);
+    // descriptors + jobs
+    h_cosmos.assign(nc, Cosmo());
+    h_psp.assign(nc, F2D());
+    h_tracers.clear();
+    h_tracers.reserve(ntr);
+    tracer_base.assign(nc, 0);
+    std::vector<AkimaJob> ak;
+    std::vector<CsplineJob> cs;
+    std::vector<LutJob> lu;
+    std::vector<BicubicJob> bc;
+    int max_nk = 0, max_na = 0;
+    for (size_t i = 0; i < nc; ++i) {
+      const CosmoPlan& c = cosmos[i];
+      Cosmo& d = h_cosmos[i];
+      memset(&d, 0, sizeof(d));
+      d.achi = mk_s1(c.achi, br, bd);
+      d.growth = mk_s1(c.growth, br, bd);
+      d.has_achi = c.achi.present;
+      d.has_growth = c.growth.present;
+      jobs_s1(c.achi, br, bd, ak, cs, lu);
+      jobs_s1(c.growth, br, bd, ak, cs, lu);
+      if (c.has_psp) {
+        h_psp[i] = mk_f2d(c.psp, br, bd);
+        jobs_f2d(c.psp, br, bd, ak, cs, lu, bc, max_nk, max_na);
+      } else
+        memset(&h_psp[i], 0, sizeof(F2D));
+      d.psp = c.has_psp ? d_psp + i : nullptr;
+      tracer_base[i] = h_tracers.size();
+      d.tracers = d_tracers + h_tracers.size();
+      d.ntracers = (int)c.tracers.size();
+      for (const TracerPlan& t : c.tracers) {
+        Tracer td;
+        memset(&td, 0, sizeof(td));
+        td.der_bessel = t.der_bessel; td.der_angles = t.der_angles;
+        td.has_kernel = t.kernel.present; td.has_transfer = t.has_transfer;
+        td.chi_min = t.chi_min; td.chi_max = t.chi_max;
+        td.kernel = mk_s1(t.kernel, br, bd);
+        jobs_s1(t.kernel, br, bd, ak, cs, lu);
+        if (t.has_transfer) {
+          td.transfer = mk_f2d(t.transfer, br, bd);
+          jobs_f2d(t.transfer, br, bd, ak, cs, lu, bc, max_nk, max_na);
+        }
+        h_tracers.push_back(td);
+      }
+    }
+    // upload descriptors
+    if (!cuda_ok(cudaMemcpyAsync(d_cosmos, h_cosmos.data(), nc * sizeof(Cosmo), cudaMemcpyHostToDevice, stream),
+                 "H2D(cosmo desc)", status)) return false;
+    if (!cuda_ok(cudaMemcpyAsync(d_psp, h_psp.data(), nc * sizeof(F2D), cudaMemcpyHostToDevice, stream),
+                 "H2D(psp desc)", status)) return false;
+    if (ntr && !cuda_ok(cudaMemcpyAsync(d_tracers, h_tracers.data(), ntr * sizeof(Tracer),
+                                        cudaMemcpyHostToDevice, stream), "H2D(tracer desc)", status))
+      return false;
+    last_h2d += nc * (sizeof(Cosmo) + sizeof(F2D)) + ntr * sizeof(Tracer);
+    // upload jobs
+    const size_t jb = ak.size() * sizeof(AkimaJob) + cs.size() * sizeof(CsplineJob) +
+                      lu.size() * sizeof(LutJob) + bc.size() * sizeof(BicubicJob) + 1024;
+    if (!jobs.reserve(jb, status)) return false;
+    char* q = jobs.p;
+    auto up = [&](const void* src, size_t bytes) -> char* {
+      char* at = q;
+      if (bytes) cudaMemcpyAsync(at, src, bytes, cudaMemcpyHostToDevice, stream);
+      q += (bytes + 255) / 256 * 256;
+      return at;
+    };
+    // (job arrays are pageable vectors: the async copies complete before returning to the host
+    //  only for pageable memory staged by the driver, which is the documented behaviour)
+    AkimaJob* d_ak = (AkimaJob*)up(ak.data(), ak.size() * sizeof(AkimaJob));
+    CsplineJob* d_cs = (CsplineJob*)up(cs.data(), cs.size() * sizeof(CsplineJob));
+    LutJob* d_lu = (LutJob*)up(lu.data(), lu.size() * sizeof(LutJob));
+    BicubicJob* d_bc = (BicubicJob*)up(bc.data(), bc.size() * sizeof(BicubicJob));
+    last_h2d += jb - 1024;
+    launch_prep(d_ak, (int)ak.size(), d_cs, (int)cs.size(), d_lu, (int)lu.size(), d_bc, (int)bc.size(),
+                max_nk, max_na, stream);
+    if (!cuda_ok(cudaGetLastError(), "table preparation launch", status)) return false;
+    if (!cuda_ok(cudaStreamSynchronize(stream), "table preparation", status)) return false;
+    committed = true;
+    return true;
+  }
+};
+
+// grow-only device scratch shared per device (qag workspace, call temporaries)
+struct DeviceScratch {
+  std::mutex mu;
+  DevBuf qag;
+  DevBuf call;
+  HostBuf pinned;
+};
+DeviceScratch g_scratch[16];
+
+DeviceScratch& scratch_for(int device) { return g_scratch[device & 15]; }
+
+LimberParams to_limber_params(const ccl_b200_params& p) {
+  LimberParams lp;
+  lp.K_MAX = p.K_MAX; lp.K_MIN = p.K_MIN; lp.DLOGK_INTEGRATION = p.DLOGK_INTEGRATION;
+  lp.LIMBER_EPSREL = p.INTEGRATION_LIMBER_EPSREL; lp.N_ITERATION = p.N_ITERATION;
+  lp.nk_cap = limber_nk_cap(lp);
+  return lp;
+}
+
+int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+struct ccl_b200_cosmology {
+  ccl_b200_params params;
+  TableSet ts;
+  std::mutex mu;
+  bool dirty = true;
+};
+struct ccl_b200_f2d { TableSet ts; };
+struct ccl_b200_tracer { TableSet ts; double chi_min, chi_max; int der_bessel, der_angles; };
+struct ccl_b200_collection { std::vector<ccl_b200_tracer*> ts; };
+struct ccl_b200_batch {
+  ccl_b200_params params;
+  TableSet ts;
+  unsigned long long last_qag_evals = 0;
+  DevBuf call;  // per-batch call buffers (colls, pairs, ells, counters, outputs)
+};
+
+static void cosmology_rebuild(ccl_b200_cosmology* c, const double* chi, const double* a, int n,
+                              const double* ag, const double* g, int ng, int* status) {
+  // re-plan from scratch keeping whichever table is not being replaced
+  std::vector<double> kx, ky;
+  CosmoPlan old = c->ts.cosmos[0];
+  auto grab = [&](const S1Plan& s, std::vector<double>& x, std::vector<double>& y) {
+    if (!s.present) return;
+    x.assign(c->ts.raw.p + s.x_off, c->ts.raw.p + s.x_off + s.n);
+    y.assign(c->ts.raw.p + s.y_off, c->ts.raw.p + s.y_off + s.n);
+  };
+  std::vector<double> ax, ay, gx, gy;
+  if (!chi) grab(old.achi, ax, ay);
+  if (!ag) grab(old.growth, gx, gy);
+  c->ts.reset();
+  CosmoPlan& p = c->ts.cosmos[0];
+  p.chi_max_nokernel = old.chi_max_nokernel;
+  if (chi) { ax.assign(chi, chi + n); ay.assign(a, a + n); }
+  if (ag) { gx.assign(ag, ag + ng); gy.assign(g, g + ng); }
+  if (!ax.empty()) {
+    if (ax.size() < 5) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: a(chi) spline needs >= 5 nodes"); return; }
+    if (!c->ts.plan_s1(p.achi, 0, (int)ax.size(), ax.data(), ay.data(), status)) return;
+  }
+  if (!gx.empty()) {
+    if (gx.size() < 5) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: growth spline needs >= 5 nodes"); return; }
+    if (!c->ts.plan_s1(p.growth, 0, (int)gx.size(), gx.data(), gy.data(), status)) return;
+  }
+  c->ts.commit(0, status);
+}
+
+// helper: run a vectorised accessor with host in/out arrays
+template <class F>
+static void run_vec(int device, int nin_arrays, const double* const* in, const size_t* in_n, size_t nout,
+                    double* out, int* status, F&& launch) {
+  if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice", status)) return;
+  size_t tot = 0;
+  for (int i = 0; i < nin_arrays; ++i) tot += in_n[i];
+  DevBuf buf;
+  if (!buf.reserve((tot + nout) * sizeof(double) + 64, status)) return;
+  double* d = reinterpret_cast<double*>(buf.p);
+  const double* dins[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t off = 0;
+  for (int i = 0; i < nin_arrays; ++i) {
+    if (in_n[i]) cudaMemcpy(d + off, in[i], in_n[i] * sizeof(double), cudaMemcpyHostToDevice);
+    dins[i] = d + off;
+    off += in_n[i];
+  }
+  double* dout = d + off;
+  int* dst = reinterpret_cast<int*>(dout + nout);
+  cudaMemset(dst, 0, sizeof(int));
+  launch(dins, dout, dst);
+  if (!cuda_ok(cudaGetLastError(), "accessor launch", status)) return;
+  if (!cuda_ok(cudaDeviceSynchronize(), "accessor kernel", status)) return;
+  cudaMemcpy(out, dout, nout * sizeof(double), cudaMemcpyDeviceToHost);
+  int st = 0;
+  cudaMemcpy(&st, dst, sizeof(int), cudaMemcpyDeviceToHost);
+  if (st) *status = st;
+}
+
+static bool batch_check(ccl_b200_batch* b, int ncoll, const int* coll_start, const int* coll_count,
+                        int npair, const int* pair1, const int* pair2, int* status) {
+  if (!b->ts.committed) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200: batch not committed");
+    return false;
+  }
+  for (size_t i = 0; i < b->ts.cosmos.size(); ++i) {
+    const CosmoPlan& c = b->ts.cosmos[i];
+    if (!c.achi.present) {
+      *status = CCL_B200_ERROR_DISTANCES_INIT;
+      set_err("ccl_cls.c: ccl_angular_cls_limber(): distance splines have not been precomputed!");
+      return false;
+    }
+    if (!c.has_psp) { *status = CCL_B200_ERROR_INCONSISTENT; set_err("ccl_b200: cosmology %zu has no P(k)", i); return false; }
+    for (int k = 0; k < ncoll; ++k)
+      if (coll_start[k] < 0 || coll_count[k] < 0 || coll_start[k] + coll_count[k] > (int)c.tracers.size()) {
+        *status = CCL_B200_ERROR_INCONSISTENT;
+        set_err("ccl_b200: collection %d exceeds the tracers of cosmology %zu", k, i);
+        return false;
+      }
+  }
+  for (int p = 0; p < npair; ++p)
+    if (pair1[p] < 0 || pair1[p] >= ncoll || pair2[p] < 0 || pair2[p] >= ncoll) {
+      *status = CCL_B200_ERROR_INCONSISTENT;
+      set_err("ccl_b200: pair %d names an unknown collection", p);
+      return false;
+    }
+  return true;
+}
+
+extern "C" {
+
+void ccl_b200_set_device(int device, int* status) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    set_err("ccl_b200_set_device: device %d not available (%d visible)", device, n);
+    if (status) *status = CCL_B200_ERROR_CUDA;
+    return;
+  }
+  g_device = device;
+  cuda_ok(cudaSetDevice(device), "cudaSetDevice", status);
+}
+
+int ccl_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* ccl_b200_last_error(void) { return g_err.c_str(); }
+const char* ccl_b200_version(void) { return "ccl_b200 0.1 (sm_100a)"; }
+
+void ccl_b200_default_params(ccl_b200_params* p) {
+  p->K_MAX = 1e3; p->K_MIN = 5e-5; p->DLOGK_INTEGRATION = 0.025;
+  p->INTEGRATION_LIMBER_EPSREL = 1e-4; p->N_ITERATION = 1000; p->A_SPLINE_MIN = 0.1;
+}
+
+// ---- cosmology ----
+ccl_b200_cosmology* ccl_b200_cosmology_new(const ccl_b200_params* params, int* status) {
+  if (*status) return nullptr;
+  if (!use_device(status)) return nullptr;
+  auto* c = new ccl_b200_cosmology();
+  if (params) c->params = *params; else ccl_b200_default_params(&c->params);
+  c->ts.device = current_device();
+  c->ts.cosmos.resize(1);
+  return c;
+}
+
+void ccl_b200_cosmology_free(ccl_b200_cosmology* cosmo) {
+  if (!cosmo) return;
+  cudaSetDevice(cosmo->ts.device);
+  delete cosmo;
+}
+
+void ccl_b200_cosmology_set_achi(ccl_b200_cosmology* cosmo, int n, const double* chi, const double* a,
+                                 int* status) {
+  if (*status || !cosmo) return;
+  std::lock_guard<std::mutex> lk(cosmo->mu);
+  cosmology_rebuild(cosmo, chi, a, n, nullptr, nullptr, 0, status);
+}
+
+void ccl_b200_cosmology_distances_from_input(ccl_b200_cosmology* cosmo, int na, const double* a,
+                                             const double* chi_a, int* status) {
+  if (*status || !cosmo) return;
+  std::vector<double> cr(na), ar(na);
+  for (int i = 0; i < na; ++i) { cr[i] = chi_a[na - 1 - i]; ar[i] = a[na - 1 - i]; }
+  cosmo->params.A_SPLINE_MIN = a[0];  // src/ccl_background.c:617
+  std::lock_guard<std::mutex> lk(cosmo->mu);
+  cosmology_rebuild(cosmo, cr.data(), ar.data(), na, nullptr, nullptr, 0, status);
+}
+
+void ccl_b200_cosmology_set_growth(ccl_b200_cosmology* cosmo, int n, const double* a, const double* growth,
+                                   int* status) {
+  if (*status || !cosmo) return;
+  std::lock_guard<std::mutex> lk(cosmo->mu);
+  cosmology_rebuild(cosmo, nullptr, nullptr, 0, a, growth, n, status);
+}
+
+void ccl_b200_cosmology_set_chi_max_nokernel(ccl_b200_cosmology* cosmo, double chi) {
+  if (cosmo) cosmo->ts.cosmos[0].chi_max_nokernel = chi;
+}
+
+void ccl_b200_scale_factor_of_chis(ccl_b200_cosmology* cosmo, int n, const double* chi, double* a_out,
+                                   int* status) {
+  if (*status || !cosmo) return;
+  if (!cosmo->ts.committed || !cosmo->ts.cosmos[0].achi.present) {
+    *status = CCL_B200_ERROR_DISTANCES_INIT;
+    set_err("ccl_background.c: ccl_scale_factor_of_chi(): distance splines have not been precomputed!");
+    return;
+  }
+  const double* in[1] = {chi};
+  const size_t nn[1] = {(size_t)n};
+  run_vec(cosmo->ts.device, 1, in, nn, n, a_out, status, [&](const double* const* di, double* dout, int* dst) {
+    launch_eval_achi(cosmo->ts.d_cosmos, n, di[0], dout, dst, 0);
+  });
+}
+
+// ---- f2d ----
+ccl_b200_f2d* ccl_b200_f2d_new(int na, const double* a_arr, int nk, const double* lk_arr,
+                               const double* fka_arr, const double* fk_arr, const double* fa_arr,
+                               int is_factorizable, int extrap_order_lok, int extrap_order_hik,
+                               int extrap_linear_growth, int is_fka_log, double growth_factor_0,
+                               int growth_exponent, int* status) {
+  if (*status) return nullptr;
+  if (!use_device(status)) return nullptr;
+  auto* f = new ccl_b200_f2d();
+  f->ts.device = current_device();
+  f->ts.cosmos.resize(1);
+  CosmoPlan& p = f->ts.cosmos[0];
+  p.has_psp = true;
+  if (!f->ts.plan_f2d(p.psp, na, a_arr, nk, lk_arr, fka_arr, fk_arr, fa_arr, is_factorizable,
+                      extrap_order_lok, extrap_order_hik, extrap_linear_growth, is_fka_log,
+                      growth_factor_0, growth_exponent, status) ||
+      !f->ts.commit(0, status)) {
+    delete f;
+    return nullptr;
+  }
+  return f;
+}
+
+ccl_b200_f2d* ccl_b200_pk2d_new_from_arrays(const double* lk_arr, int nk, const double* a_arr, int na,
+                                            const double* pk_arr, int order_lok, int order_hik,
+                                            int is_logp, int* status) {
+  return ccl_b200_f2d_new(na, a_arr, nk, lk_arr, pk_arr, nullptr, nullptr, 0, order_lok, order_hik,
+                          GROWTH_CCL, is_logp, 0, 2, status);
+}
+
+void ccl_b200_f2d_free(ccl_b200_f2d* f2d) {
+  if (!f2d) return;
+  cudaSetDevice(f2d->ts.device);
+  delete f2d;
+}
+
+void ccl_b200_f2d_eval_multi(ccl_b200_f2d* f2d, const double* lk, int nk, double a, ccl_b200_cosmology* cosmo,
+                             double* out, int* status) {
+  if (*status || !f2d) return;
+  std::vector<double> av(nk, a);
+  const double* in[2] = {lk, av.data()};
+  const size_t nn[2] = {(size_t)nk, (size_t)nk};
+  const Cosmo* dcs = (cosmo && cosmo->ts.committed) ? cosmo->ts.d_cosmos : nullptr;
+  run_vec(f2d->ts.device, 2, in, nn, nk, out, status, [&](const double* const* di, double* dout, int* dst) {
+    launch_eval_f2d(f2d->ts.d_psp, dcs, nk, di[0], di[1], dout, dst, 0);
+  });
+  if (*status == CCL_B200_ERROR_GROWTH_INIT)
+    set_err("ccl_f2d.c: ccl_f2d_t_eval(): growth factor splines have not been precomputed!");
+}
+
+// ---- tracers ----
+ccl_b200_tracer* ccl_b200_cl_tracer_t_new(ccl_b200_cosmology* cosmo, int der_bessel, int der_angles,
+                                          int n_w, const double* chi_w, const double* w_w, int na_ka,
+                                          const double* a_ka, int nk_ka, const double* lk_ka,
+                                          const double* fka_arr, const double* fk_arr,
+                                          const double* fa_arr, int is_fka_log, int is_factorizable,
+                                          int extrap_order_lok, int extrap_order_hik, int* status) {
+  if (*status) return nullptr;
+  if (!use_device(status)) return nullptr;
+  auto* t = new ccl_b200_tracer();
+  t->ts.device = current_device();
+  t->ts.cosmos.resize(1);
+  CosmoPlan& p = t->ts.cosmos[0];
+  p.tracers.resize(1);
+  const double cmax = cosmo ? cosmo->ts.cosmos[0].chi_max_nokernel : 1e15;
+  if (!t->ts.plan_tracer(p.tracers[0], cmax, der_bessel, der_angles, n_w, chi_w, w_w, na_ka, a_ka, nk_ka,
+                         lk_ka, fka_arr, fk_arr, fa_arr, is_fka_log, is_factorizable, extrap_order_lok,
+                         extrap_order_hik, status) ||
+      !t->ts.commit(0, status)) {
+    delete t;
+    return nullptr;
+  }
+  t->chi_min = p.tracers[0].chi_min;
+  t->chi_max = p.tracers[0].chi_max;
+  t->der_bessel = der_bessel;
+  t->der_angles = der_angles;
+  return t;
+}
+
+void ccl_b200_cl_tracer_t_free(ccl_b200_tracer* tr) {
+  if (!tr) return;
+  cudaSetDevice(tr->ts.device);
+  delete tr;
+}
+
+double ccl_b200_cl_tracer_t_chi_min(const ccl_b200_tracer* tr) { return tr->chi_min; }
+double ccl_b200_cl_tracer_t_chi_max(const ccl_b200_tracer* tr) { return tr->chi_max; }
+
+void ccl_b200_cl_tracer_get_f_ell(const ccl_b200_tracer* tr, int n, const double* ell, double* out,
+                                  int* status) {
+  if (*status) return;
+  // closed form, src/ccl_tracers.c:703-726 (host arithmetic of a per-ell constant, not table work)
+  for (int i = 0; i < n; ++i) {
+    const double l = ell[i];
+    double f = 1;
+    if (tr->der_angles == 1) f = l * (l + 1.);
+    else if (tr->der_angles == 2) {
+      if (l <= 1) f = 0;
+      else if (l <= 10) f = sqrt((l + 2) * (l + 1) * l * (l - 1));
+      else {
+        const double lp1h = l + 0.5, lp1h2 = lp1h * lp1h;
+        f = (l <= 1000) ? lp1h2 * (1 - 1.25 / lp1h2) : lp1h2;
+      }
+    }
+    out[i] = f;
+  }
+}
+
+void ccl_b200_cl_tracer_get_kernel(ccl_b200_tracer* tr, int n, const double* chi, double* out, int* status) {
+  if (*status || !tr) return;
+  const double* in[1] = {chi};
+  const size_t nn[1] = {(size_t)n};
+  run_vec(tr->ts.device, 1, in, nn, n, out, status, [&](const double* const* di, double* dout, int*) {
+    launch_eval_tracer_kernel(tr->ts.d_tracers, n, di[0], dout, 0);
+  });
+}
+
+void ccl_b200_cl_tracer_get_transfer(ccl_b200_tracer* tr, int nk, const double* lk, int na, const double* a,
+                                     double* out, int* status) {
+  if (*status || !tr) return;
+  const size_t n = (size_t)nk * na;
+  std::vector<double> lkv(n), av(n);
+  for (int i = 0; i < nk; ++i)
+    for (int j = 0; j < na; ++j) { lkv[(size_t)i * na + j] = lk[i]; av[(size_t)i * na + j] = a[j]; }
+  const double* in[2] = {lkv.data(), av.data()};
+  const size_t nn[2] = {n, n};
+  run_vec(tr->ts.device, 2, in, nn, n, out, status, [&](const double* const* di, double* dout, int* dst) {
+    launch_eval_tracer_transfer(tr->ts.d_tracers, (int)n, di[0], di[1], dout, dst, 0);
+  });
+}
+
+// ---- collections ----
+ccl_b200_collection* ccl_b200_cl_tracer_collection_t_new(int* status) {
+  if (*status) return nullptr;
+  return new ccl_b200_collection();
+}
+void ccl_b200_cl_tracer_collection_t_free(ccl_b200_collection* trc) { delete trc; }
+void ccl_b200_add_cl_tracer_to_collection(ccl_b200_collection* trc, ccl_b200_tracer* tr, int* status) {
+  if (*status) return;
+  if (trc->ts.size() >= 100) {  // CCL_MAX_TRACERS_PER_COLLECTION, include/ccl_tracers.h:167
+    *status = CCL_B200_ERROR_MEMORY;
+    set_err("ccl_tracers.c: ccl_add_cl_tracer_to_collection(): already reached maximum number of tracers\n");
+    return;
+  }
+  trc->ts.push_back(tr);
+}
+
+// ---- the hot path, single pair ----
+void ccl_b200_angular_cls_limber(ccl_b200_cosmology* cosmo, ccl_b200_collection* trc1,
+                                 ccl_b200_collection* trc2, ccl_b200_f2d* psp, int nl_out,
+                                 const double* l_out, double* cl_out, int integration_method,
+                                 int* status) {
+  if (!cosmo || !trc1 || !trc2 || !psp) { *status = CCL_B200_ERROR_INCONSISTENT; return; }
+  std::lock_guard<std::mutex> lk(cosmo->mu);
+  if (!cosmo->ts.committed || !cosmo->ts.cosmos[0].achi.present) {
+    *status = CCL_B200_ERROR_DISTANCES_INIT;
+    set_err("ccl_cls.c: ccl_angular_cls_limber(): distance splines have not been precomputed!");
+    return;
+  }
+  // The reference proceeds into the OpenMP region with local_status = *status and skips all work
+  // if it is non-zero (src/ccl_cls.c:289-319).
+  if (*status) return;
+  if (integration_method != INTEG_QAG && integration_method != INTEG_SPLINE) {
+    for (int i = 0; i < nl_out; ++i) cl_out[i] = NAN;
+    *status = CCL_B200_ERROR_INTEG;  // CCL_ERROR_NOT_IMPLEMENTED is overwritten at :343-345
+    set_err("ccl_cls.c: ccl_angular_cls_limber(); integration error\n");
+    return;
+  }
+  const int device = cosmo->ts.device;
+  if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice", status)) return;
+  DeviceScratch& sc = scratch_for(device);
+  std::lock_guard<std::mutex> lk2(sc.mu);
+  const int n1 = (int)trc1->ts.size(), n2 = (int)trc2->ts.size();
+  const bool same = (trc1 == trc2);
+  // layout of the call buffer: Tracer[n1+n2] | Cosmo | int2 colls[2] | int2 pair | ells | cl | status[2]
+  std::vector<Tracer> trs;
+  for (auto* t : trc1->ts) trs.push_back(t->ts.h_tracers[0]);
+  for (auto* t : trc2->ts) trs.push_back(t->ts.h_tracers[0]);
+  Cosmo cd = cosmo->ts.h_cosmos[0];
+  const size_t o_tr = 0;
+  const size_t o_cs = (o_tr + trs.size() * sizeof(Tracer) + 255) / 256 * 256;
+  const size_t o_co = o_cs + 256 * ((sizeof(Cosmo) + 255) / 256);
+  const size_t o_pr = o_co + 256;
+  const size_t o_el = o_pr + 256;
+  const size_t o_cl = o_el + ((size_t)nl_out * 8 + 255) / 256 * 256;
+  const size_t o_st = o_cl + ((size_t)nl_out * 8 + 255) / 256 * 256;
+  const size_t total = o_st + 256;
+  if (!sc.call.reserve(total, status)) return;
+  char* base = sc.call.p;
+  cd.psp = psp->ts.d_psp;
+  cd.tracers = reinterpret_cast<const Tracer*>(base + o_tr);
+  cd.ntracers = n1 + n2;
+  const int2 colls[2] = {make_int2(0, n1), make_int2(n1, n2)};
+  const int2 pair = same ? make_int2(0, 0) : make_int2(0, 1);
+  cudaMemcpyAsync(base + o_tr, trs.data(), trs.size() * sizeof(Tracer), cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_cs, &cd, sizeof(Cosmo), cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_co, colls, sizeof(colls), cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_pr, &pair, sizeof(pair), cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_el, l_out, (size_t)nl_out * 8, cudaMemcpyHostToDevice, 0);
+  cudaMemsetAsync(base + o_st, 0, 256, 0);
+  LimberProblem P;
+  P.cosmos = reinterpret_cast<const Cosmo*>(base + o_cs);
+  P.colls = reinterpret_cast<const int2*>(base + o_co);
+  P.pairs = reinterpret_cast<const int2*>(base + o_pr);
+  P.ells = reinterpret_cast<const double*>(base + o_el);
+  P.ncosmo = 1; P.npair = 1; P.nl = nl_out; P.ncoll = 2;
+  P.par = to_limber_params(cosmo->params);
+  P.cl = reinterpret_cast<double*>(base + o_cl);
+  P.status = reinterpret_cast<int*>(base + o_st);
+  P.status_detail = P.status + 1;
+  P.counters = nullptr;
+  double* ws = nullptr;
+  size_t wsb = 0;
+  if (integration_method == INTEG_QAG) {
+    wsb = limber_qag_workspace_bytes(P.par.N_ITERATION);
+    if (!sc.qag.reserve(wsb, status)) return;
+    ws = reinterpret_cast<double*>(sc.qag.p);
+  }
+  if (!cuda_ok(launch_limber(P, integration_method, ws, wsb, 0), "limber launch", status)) return;
+  if (!cuda_ok(cudaMemcpy(cl_out, P.cl, (size_t)nl_out * 8, cudaMemcpyDeviceToHost), "limber kernel", status))
+    return;
+  int st[2] = {0, 0};
+  cudaMemcpy(st, P.status, sizeof(st), cudaMemcpyDeviceToHost);
+  if (st[0]) {
+    *status = st[0];
+    set_err("ccl_cls.c: ccl_angular_cls_limber(); integration error (first underlying code %d)\n", st[1]);
+  }
+}
+
+// ---- batch ----
+ccl_b200_batch* ccl_b200_batch_new(int ncosmo, const ccl_b200_params* params, int* status) {
+  if (*status) return nullptr;
+  if (!use_device(status)) return nullptr;
+  auto* b = new ccl_b200_batch();
+  if (params) b->params = *params; else ccl_b200_default_params(&b->params);
+  b->ts.device = current_device();
+  b->ts.cosmos.resize(ncosmo);
+  return b;
+}
+
+void ccl_b200_batch_free(ccl_b200_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ts.device);
+  delete b;
+}
+
+#define BATCH_SLOT(b, ic)                                                      \
+  if (*status) return;                                                         \
+  if (!(b) || (ic) < 0 || (ic) >= (int)(b)->ts.cosmos.size()) {               \
+    *status = CCL_B200_ERROR_INCONSISTENT;                                     \
+    set_err("ccl_b200: batch slot %d out of range", (ic));                    \
+    return;                                                                    \
+  }
+
+void ccl_b200_batch_set_achi(ccl_b200_batch* b, int icosmo, int n, const double* chi, const double* a,
+                             int* status) {
+  BATCH_SLOT(b, icosmo);
+  if (n < 5) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: a(chi) spline needs >= 5 nodes"); return; }
+  b->ts.plan_s1(b->ts.cosmos[icosmo].achi, 0, n, chi, a, status);
+  b->ts.committed = false;
+}
+
+void ccl_b200_batch_set_growth(ccl_b200_batch* b, int icosmo, int n, const double* a, const double* growth,
+                               int* status) {
+  BATCH_SLOT(b, icosmo);
+  if (n < 5) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: growth spline needs >= 5 nodes"); return; }
+  b->ts.plan_s1(b->ts.cosmos[icosmo].growth, 0, n, a, growth, status);
+  b->ts.committed = false;
+}
+
+void ccl_b200_batch_set_chi_max_nokernel(ccl_b200_batch* b, int icosmo, double chi) {
+  if (b && icosmo >= 0 && icosmo < (int)b->ts.cosmos.size()) b->ts.cosmos[icosmo].chi_max_nokernel = chi;
+}
+
+void ccl_b200_batch_set_pk2d(ccl_b200_batch* b, int icosmo, const double* lk_arr, int nk,
+                             const double* a_arr, int na, const double* pk_arr, int order_lok,
+                             int order_hik, int is_logp, int* status) {
+  BATCH_SLOT(b, icosmo);
+  CosmoPlan& p = b->ts.cosmos[icosmo];
+  p.has_psp = b->ts.plan_f2d(p.psp, na, a_arr, nk, lk_arr, pk_arr, nullptr, nullptr, 0, order_lok, order_hik,
+                             GROWTH_CCL, is_logp, 0, 2, status);
+  b->ts.committed = false;
+}
+
+int ccl_b200_batch_add_tracer(ccl_b200_batch* b, int icosmo, int der_bessel, int der_angles, int n_w,
+                              const double* chi_w, const double* w_w, int na_ka, const double* a_ka,
+                              int nk_ka, const double* lk_ka, const double* fka_arr, const double* fk_arr,
+                              const double* fa_arr, int is_fka_log, int is_factorizable,
+                              int extrap_order_lok, int extrap_order_hik, int* status) {
+  if (*status) return -1;
+  if (!b || icosmo < 0 || icosmo >= (int)b->ts.cosmos.size()) { *status = CCL_B200_ERROR_INCONSISTENT; return -1; }
+  CosmoPlan& p = b->ts.cosmos[icosmo];
+  TracerPlan t;
+  if (!b->ts.plan_tracer(t, p.chi_max_nokernel, der_bessel, der_angles, n_w, chi_w, w_w, na_ka, a_ka, nk_ka,
+                         lk_ka, fka_arr, fk_arr, fa_arr, is_fka_log, is_factorizable, extrap_order_lok,
+                         extrap_order_hik, status))
+    return -1;
+  p.tracers.push_back(t);
+  b->ts.committed = false;
+  return (int)p.tracers.size() - 1;
+}
+
+void ccl_b200_batch_tracer_chi_range(const ccl_b200_batch* b, int icosmo, int itracer, double* chi_min,
+                                     double* chi_max) {
+  const TracerPlan& t = b->ts.cosmos[icosmo].tracers[itracer];
+  *chi_min = t.chi_min;
+  *chi_max = t.chi_max;
+}
+
+void ccl_b200_batch_reset(ccl_b200_batch* b) { if (b) b->ts.reset(); }
+
+void ccl_b200_batch_commit(ccl_b200_batch* b, int* status) {
+  if (*status || !b) return;
+  b->ts.commit(0, status);
+}
+
+unsigned long long ccl_b200_batch_h2d_bytes(const ccl_b200_batch* b) { return b->ts.last_h2d; }
+unsigned long long ccl_b200_batch_arena_bytes(const ccl_b200_batch* b) { return b->ts.dev.cap; }
+
+void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const int* coll_start,
+                                           const int* coll_count, int npair, const int* pair1,
+                                           const int* pair2, int nl, const double* ell,
+                                           int integration_method, double* d_cl_out, int* d_status_out,
+                                           void* stream_v, int* status) {
+  if (*status || !b) return;
+  if (!batch_check(b, ncoll, coll_start, coll_count, npair, pair1, pair2, status)) return;
+  if (integration_method != INTEG_QAG && integration_method != INTEG_SPLINE) {
+    *status = CCL_B200_ERROR_NOT_IMPLEMENTED;
+    return;
+  }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!cuda_ok(cudaSetDevice(b->ts.device), "cudaSetDevice", status)) return;
+  const int nc = (int)b->ts.cosmos.size();
+  std::vector<int2> colls(ncoll), pairs(npair);
+  for (int i = 0; i < ncoll; ++i) colls[i] = make_int2(coll_start[i], coll_count[i]);
+  for (int i = 0; i < npair; ++i) pairs[i] = make_int2(pair1[i], pair2[i]);
+  const size_t o_co = 0;
+  const size_t o_pr = o_co + ((size_t)ncoll * 8 + 255) / 256 * 256;
+  const size_t o_el = o_pr + ((size_t)npair * 8 + 255) / 256 * 256;
+  const size_t o_ct = o_el + ((size_t)nl * 8 + 255) / 256 * 256;
+  const size_t total = o_ct + 256;
+  if (!b->call.reserve(total, status)) return;
+  char* base = b->call.p;
+  // small pageable copies: the driver stages them before returning
+  cudaMemcpyAsync(base + o_co, colls.data(), (size_t)ncoll * 8, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(base + o_pr, pairs.data(), (size_t)npair * 8, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(base + o_el, ell, (size_t)nl * 8, cudaMemcpyHostToDevice, stream);
+  cudaMemsetAsync(base + o_ct, 0, 256, stream);
+  cudaMemsetAsync(d_status_out, 0, sizeof(int) * 2 * (size_t)nc * npair, stream);
+  LimberProblem P;
+  P.cosmos = b->ts.d_cosmos;
+  P.colls = reinterpret_cast<const int2*>(base + o_co);
+  P.pairs = reinterpret_cast<const int2*>(base + o_pr);
+  P.ells = reinterpret_cast<const double*>(base + o_el);
+  P.ncosmo = nc; P.npair = npair; P.nl = nl; P.ncoll = ncoll;
+  P.par = to_limber_params(b->params);
+  P.cl = d_cl_out;
+  P.status = d_status_out;
+  P.status_detail = d_status_out + (size_t)nc * npair;
+  P.counters = reinterpret_cast<unsigned long long*>(base + o_ct);
+  double* ws = nullptr;
+  size_t wsb = 0;
+  DeviceScratch& sc = scratch_for(b->ts.device);
+  std::unique_lock<std::mutex> lk(sc.mu, std::defer_lock);
+  if (integration_method == INTEG_QAG) {
+    lk.lock();
+    wsb = limber_qag_workspace_bytes(P.par.N_ITERATION);
+    if (!sc.qag.reserve(wsb, status)) return;
+    ws = reinterpret_cast<double*>(sc.qag.p);
+  }
+  if (!cuda_ok(launch_limber(P, integration_method, ws, wsb, stream), "limber launch", status)) return;
+  if (integration_method == INTEG_QAG) {
+    // the shared workspace must not be reused before this launch has drained
+    cuda_ok(cudaStreamSynchronize(stream), "limber qag kernel", status);
+    cudaMemcpy(&b->last_qag_evals, P.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  }
+}
+
+void ccl_b200_batch_angular_cls_limber(ccl_b200_batch* b, int ncoll, const int* coll_start,
+                                       const int* coll_count, int npair, const int* pair1,
+                                       const int* pair2, int nl, const double* ell, int integration_method,
+                                       double* cl_out, int* status_out, int* status) {
+  if (*status || !b) return;
+  if (!cuda_ok(cudaSetDevice(b->ts.device), "cudaSetDevice", status)) return;
+  const size_t nc = b->ts.cosmos.size();
+  const size_t ncl = nc * npair * (size_t)nl;
+  const size_t nst = nc * (size_t)npair;
+  DevBuf out;
+  if (!out.reserve(ncl * 8 + nst * 2 * sizeof(int) + 512, status)) return;
+  double* d_cl = reinterpret_cast<double*>(out.p);
+  int* d_st = reinterpret_cast<int*>(out.p + (ncl * 8 + 255) / 256 * 256);
+  ccl_b200_batch_angular_cls_limber_dev(b, ncoll, coll_start, coll_count, npair, pair1, pair2, nl, ell,
+                                        integration_method, d_cl, d_st, nullptr, status);
+  if (*status) return;
+  if (!cuda_ok(cudaMemcpy(cl_out, d_cl, ncl * 8, cudaMemcpyDeviceToHost), "limber kernel", status)) return;
+  std::vector<int> st(nst);
+  cudaMemcpy(st.data(), d_st, nst * sizeof(int), cudaMemcpyDeviceToHost);
+  bool any = false;
+  for (size_t i = 0; i < nst; ++i) {
+    if (status_out) status_out[i] = st[i];
+    any = any || st[i];
+  }
+  if (any) {
+    *status = CCL_B200_ERROR_INTEG;
+    set_err("ccl_cls.c: ccl_angular_cls_limber(); integration error\n");
+  }
+}
+
+unsigned long long ccl_b200_batch_spline_nodes(const ccl_b200_batch* b, int ncoll, const int* coll_start,
+                                               const int* coll_count, int npair, const int* pair1,
+                                               const int* pair2, int nl, const double* ell) {
+  unsigned long long tot = 0;
+  const ccl_b200_params& p = b->params;
+  for (const CosmoPlan& c : b->ts.cosmos) {
+    std::vector<double> cmin(ncoll, 1e15), cmax(ncoll, -1e15);
+    for (int k = 0; k < ncoll; ++k)
+      for (int t = coll_start[k]; t < coll_start[k] + coll_count[k]; ++t) {
+        cmin[k] = std::min(cmin[k], c.tracers[t].chi_min);
+        cmax[k] = std::max(cmax[k], c.tracers[t].chi_max);
+      }
+    for (int q = 0; q < npair; ++q) {
+      const double chi_max = std::min(cmax[pair1[q]], cmax[pair2[q]]);
+      const double chi_min0 = std::max(cmin[pair1[q]], cmin[pair2[q]]);
+      for (int l = 0; l < nl; ++l) {
+        double chi_min = chi_min0;
+        if (chi_min <= 0) chi_min = 0.5 * (ell[l] + 0.5) / p.K_MAX;
+        const double lkmax = log(std::min(p.K_MAX, 2 * (ell[l] + 0.5) / chi_min));
+        const double lkmin = log(std::max(p.K_MIN, (ell[l] + 0.5) / chi_max));
+        const int nk = (int)(std::max((lkmax - lkmin) / p.DLOGK_INTEGRATION + 0.5, 1.0)) + 1;
+        if (nk >= 5) tot += nk;
+      }
+    }
+  }
+  return tot;
+}
+
+unsigned long long ccl_b200_batch_last_qag_evals(const ccl_b200_batch* b) { return b->last_qag_evals; }
+
+}  // extern "C"

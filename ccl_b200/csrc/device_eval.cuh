@@ -1,0 +1,296 @@
+// Device evaluators for the tables the Limber integrand reads.
+//
+// Each function restates one reference routine on flattened device tables; the reference
+// call it replaces is cited above it.  All arithmetic is IEEE fp64.  Interval selection
+// follows gsl_interp_bsearch exactly (x_i <= x < x_{i+1}, last interval closed), so a
+// node that lands on a table node picks the same polynomial piece as the reference.
+#pragma once
+#include "tables.h"
+
+namespace cclb {
+
+__device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
+
+__device__ __forceinline__ double4 ldg4(const double4* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// gsl_interp_bsearch(x, v, 0, n-1) for x[0] <= v <= x[n-1]: largest i <= n-2 with x[i] <= v.
+__device__ __forceinline__ int find_interval(const Spline1D& s, double v) {
+  int j = (int)((v - s.x0) * s.inv_bin);
+  j = min(max(j, 0), s.nlut - 1);
+  int i = __ldg(s.lut + j);
+  const int last = s.n - 2;
+  while (i > 0 && ldg(s.x + i) > v) --i;  // bin-edge rounding
+  int steps = 0;
+  while (i < last && ldg(s.x + i + 1) <= v) {
+    ++i;
+    if (++steps > 6) {  // strongly non-uniform grid: finish by bisection
+      int lo = i, hi = s.n - 1;
+      while (hi > lo + 1) {
+        int m = (hi + lo) >> 1;
+        if (ldg(s.x + m) > v) hi = m; else lo = m;
+      }
+      i = lo;
+      break;
+    }
+  }
+  return i;
+}
+
+// gsl_spline_eval_e on an akima/cspline object: y_i + dx (b + dx (c + dx d)); EDOM outside.
+// which = 0 value, 1 first derivative, 2 second derivative (cspline_eval_deriv / _deriv2).
+__device__ __forceinline__ double spline_eval(const Spline1D& s, double v, int which, int& st) {
+  if (v < s.x0 || v > s.xn) { st |= ST_GSL_EDOM; return nan(""); }
+  const int i = find_interval(s, v);
+  const double delx = v - ldg(s.x + i);
+  const double4 c = ldg4(s.co + i);
+  if (which == 0) return c.x + delx * (c.y + delx * (c.z + delx * c.w));
+  if (which == 1) return c.y + delx * (2.0 * c.z + 3.0 * c.w * delx);
+  return 2.0 * c.z + 6.0 * c.w * delx;
+}
+
+// ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277)
+__device__ __forceinline__ double scale_factor_of_chi(const Cosmo& cs, double chi, int& st) {
+  if ((chi < 1.e-8) && (chi >= 0.)) return 1.;
+  if (chi < 0.) { st = ST_ERR_COMPUTECHI; return nan(""); }
+  if (!cs.has_achi) { st = ST_ERR_DISTANCES_INIT; return nan(""); }
+  return spline_eval(cs.achi, chi, 0, st);
+}
+
+// ccl_growth_factor (src/ccl_background.c:1290-1325)
+__device__ __forceinline__ double growth_factor(const Cosmo& cs, double a, int& st) {
+  if (a == 1.) return 1.;
+  if (a > 1.) { st = ST_ERR_COMPUTECHI; return nan(""); }
+  if (!cs.has_growth) { st = ST_ERR_GROWTH_INIT; return nan(""); }
+  int s2 = 0;
+  double D = spline_eval(cs.growth, a, 0, s2);
+  if (s2) { st |= s2; return nan(""); }
+  return D;
+}
+
+// gsl_spline2d_eval_e / _deriv_x_e / _deriv_xx_e with gsl_interp2d_bicubic
+// (interp2d/bicubic.c).  The bicubic Hermite patch is evaluated in tensor Hermite-basis
+// form (same polynomial as GSL's 16-coefficient expansion, ~45 fp64 instructions).
+__device__ __forceinline__ double bicubic_eval(const F2D& f, double x, double y, int which) {
+  const int xi = find_interval(f.gk, x);
+  const int yi = find_interval(f.ga, y);
+  const double xmin = ldg(f.gk.x + xi), xmax = ldg(f.gk.x + xi + 1);
+  const double ymin = ldg(f.ga.x + yi), ymax = ldg(f.ga.x + yi + 1);
+  const int nk = f.gk.n;
+  const double4* r0 = f.tab + (size_t)yi * nk + xi;
+  const double4* r1 = r0 + nk;
+  const double4 c00 = ldg4(r0), c10 = ldg4(r0 + 1);  // (xmin,ymin) (xmax,ymin)
+  const double4 c01 = ldg4(r1), c11 = ldg4(r1 + 1);  // (xmin,ymax) (xmax,ymax)
+  const double dx = xmax - xmin, dy = ymax - ymin;
+  const double t = (x - xmin) / dx, u = (y - ymin) / dy;
+  const double um = 1.0 - u;
+  const double u00 = (1.0 + 2.0 * u) * um * um;  // value weight, y-min edge
+  const double u01 = u * u * (3.0 - 2.0 * u);    // value weight, y-max edge
+  const double u10 = u * um * um * dy;           // slope weight, y-min edge
+  const double u11 = u * u * (u - 1.0) * dy;     // slope weight, y-max edge
+  double t00, t01, t10, t11;
+  const double tm = 1.0 - t;
+  if (which == 0) {
+    t00 = (1.0 + 2.0 * t) * tm * tm;
+    t01 = t * t * (3.0 - 2.0 * t);
+    t10 = t * tm * tm * dx;
+    t11 = t * t * (t - 1.0) * dx;
+  } else if (which == 1) {
+    const double idx = 1.0 / dx;
+    t00 = 6.0 * t * (t - 1.0) * idx;
+    t01 = -t00;
+    t10 = (3.0 * t * t - 4.0 * t + 1.0);
+    t11 = (3.0 * t * t - 2.0 * t);
+  } else {
+    const double idx = 1.0 / dx;
+    t00 = (12.0 * t - 6.0) * idx * idx;
+    t01 = -t00;
+    t10 = (6.0 * t - 4.0) * idx;
+    t11 = (6.0 * t - 2.0) * idx;
+  }
+  // y-direction Hermite interpolation of value (p) and x-slope (q) on both x edges
+  const double p0 = u00 * c00.x + u01 * c01.x + u10 * c00.z + u11 * c01.z;
+  const double p1 = u00 * c10.x + u01 * c11.x + u10 * c10.z + u11 * c11.z;
+  const double q0 = u00 * c00.y + u01 * c01.y + u10 * c00.w + u11 * c01.w;
+  const double q1 = u00 * c10.y + u01 * c11.y + u10 * c10.w + u11 * c11.w;
+  return t00 * p0 + t01 * p1 + t10 * q0 + t11 * q1;
+}
+
+// ccl_f2d_t_eval (src/ccl_f2d.c:203-373)
+__device__ __noinline__ double f2d_eval(const F2D& f, double lk, double a, const Cosmo* cs, int& st) {
+  bool is_hiz = false, is_loz = false;
+  double a_ev = a;
+  if (!f.is_a_constant) {
+    is_hiz = a < f.amin;
+    is_loz = a > f.amax;
+    if (is_loz) {
+      if (f.extrap_linear_growth == GROWTH_NONE) { st = ST_ERR_SPLINE_EV; return nan(""); }
+      a_ev = f.amax;
+    } else if (is_hiz) {
+      if (f.extrap_linear_growth == GROWTH_NONE) { st = ST_ERR_SPLINE_EV; return nan(""); }
+      a_ev = f.amin;
+    }
+  }
+  bool is_hik = false, is_lok = false;
+  double lk_ev = lk;
+  if (!f.is_k_constant) {
+    is_hik = lk > f.lkmax;
+    is_lok = lk < f.lkmin;
+    if (is_hik) lk_ev = f.lkmax;
+    else if (is_lok) lk_ev = f.lkmin;
+  }
+  double pre;
+  int sp = 0;
+  if (f.is_factorizable) {
+    double fk = f.is_log ? 0. : 1., fa = f.is_log ? 0. : 1.;
+    if (f.has_fk) fk = spline_eval(f.fk, lk_ev, 0, sp);
+    if (f.has_fa) fa = spline_eval(f.fa, a_ev, 0, sp);
+    pre = f.is_log ? fk + fa : fk * fa;
+  } else {
+    if (!f.has_fka) pre = f.is_log ? 0. : 1.;
+    else {
+      // gsl_interp2d_eval_e domain check (NaN inputs fail it)
+      if (!(lk_ev >= f.gk.x0 && lk_ev <= f.gk.xn && a_ev >= f.ga.x0 && a_ev <= f.ga.xn)) sp = ST_GSL_EDOM;
+      else pre = bicubic_eval(f, lk_ev, a_ev, 0);
+    }
+  }
+  if (sp) { st = ST_ERR_SPLINE_EV; return nan(""); }
+  double post = pre;
+  if (is_hik || is_lok) {
+    const int order = is_hik ? f.extrap_order_hik : f.extrap_order_lok;
+    if (order > 0) {
+      const double dlk = lk - lk_ev;
+      double pd = f.is_factorizable ? spline_eval(f.fk, lk_ev, 1, sp) : bicubic_eval(f, lk_ev, a_ev, 1);
+      if (sp) { st = ST_ERR_SPLINE_EV; return nan(""); }
+      post += pd * dlk;
+      if (order > 1) {
+        pd = f.is_factorizable ? spline_eval(f.fk, lk_ev, 2, sp) : bicubic_eval(f, lk_ev, a_ev, 2);
+        if (sp) { st = ST_ERR_SPLINE_EV; return nan(""); }
+        post += pd * dlk * dlk * 0.5;
+      }
+    }
+  }
+  if (f.is_log) post = exp(post);
+  if (is_hiz) {
+    double gz;
+    if (f.extrap_linear_growth == GROWTH_CCL) {
+      if (cs == nullptr || !cs->has_growth) { st = ST_ERR_GROWTH_INIT; return nan(""); }
+      gz = growth_factor(*cs, a, st) / growth_factor(*cs, a_ev, st);
+    } else
+      gz = f.growth_factor_0;
+    post *= pow(gz, (double)f.growth_exponent);
+  }
+  return post;
+}
+
+// ccl_cl_tracer_t_get_f_ell (src/ccl_tracers.c:703-726)
+__device__ __forceinline__ double tracer_f_ell(int der_angles, double ell) {
+  if (der_angles == 1) return ell * (ell + 1.);
+  if (der_angles == 2) {
+    if (ell <= 1) return 0;
+    if (ell <= 10) return sqrt((ell + 2) * (ell + 1) * ell * (ell - 1));
+    const double lp1h = ell + 0.5;
+    const double lp1h2 = lp1h * lp1h;
+    if (ell <= 1000) return lp1h2 * (1 - 1.25 / lp1h2);
+    return lp1h2;
+  }
+  return 1;
+}
+
+// ccl_cl_tracer_t_get_kernel (src/ccl_tracers.c:728-737) + ccl_f1d_t_eval constant branch
+__device__ __forceinline__ double tracer_kernel(const Tracer& tr, double chi) {
+  if (!tr.has_kernel) return 1;
+  if (chi <= tr.kernel.x0) return 0;  // y0 = 0, end node itself counts as outside
+  if (chi >= tr.kernel.xn) return 0;  // yf = 0 (a NaN chi falls through to the spline: NaN)
+  int st = 0;
+  return spline_eval(tr.kernel, chi, 0, st);
+}
+
+// ccl_cl_tracer_t_get_transfer (src/ccl_tracers.c:739-749)
+__device__ __forceinline__ double tracer_transfer(const Tracer& tr, double lk, double a, int& st) {
+  if (!tr.has_transfer) return 1;
+  return f2d_eval(tr.transfer, lk, a, nullptr, st);
+}
+
+struct TaskCtx {
+  const Cosmo* cs;
+  const Tracer* t1;
+  const Tracer* t2;
+  int n1, n2;
+  bool same;  // both collections are the same tracer list
+  double l;
+};
+
+// transfer_limber_single + transfer_limber_wrap (src/ccl_cls.c:102-164)
+__device__ __forceinline__ double transfer_limber_wrap(const TaskCtx& c, const Tracer* trs, int n, double lk,
+                                                       double k, double chi, double a, int& st) {
+  double transfer = 0;
+  const double l = c.l;
+  for (int itr = 0; itr < n; ++itr) {
+    const Tracer& tr = trs[itr];
+    double dd;
+    const double w = tracer_kernel(tr, chi);
+    const double t = tracer_transfer(tr, lk, a, st);
+    const double fl = tracer_f_ell(tr.der_angles, l);
+    if (tr.der_bessel < 1) {
+      dd = w * t;
+      if (tr.der_bessel == -1) {
+        const double lp1h = l + 0.5;
+        dd /= (lp1h * lp1h);
+      }
+    } else {
+      const double lp1h = l + 0.5;
+      const double lp3h = l + 1.5;
+      const double chi_lp = lp3h / k;
+      const double a_lp = scale_factor_of_chi(*c.cs, chi_lp, st);
+      const double pk_ratio =
+          fabs(f2d_eval(*c.cs->psp, lk, a_lp, c.cs, st) / f2d_eval(*c.cs->psp, lk, a, c.cs, st));
+      const double w_p = tracer_kernel(tr, chi_lp);
+      const double t_p = tracer_transfer(tr, lk, a_lp, st);
+      const double sqell = sqrt(lp1h * pk_ratio / lp3h);
+      if (tr.der_bessel == 1) dd = l * w * t / lp1h - sqell * w_p * t_p;
+      else dd = sqell * 2 * w_p * t_p / lp3h - (0.25 + 2 * l) * w * t / (lp1h * lp1h);
+    }
+    transfer += dd * fl;
+    if (st != 0) return -1;
+  }
+  return transfer;
+}
+
+// cl_integrand (src/ccl_cls.c:166-187)
+__device__ __forceinline__ double cl_integrand(const TaskCtx& c, double lk, int& st) {
+  const double k = exp(lk);
+  const double chi = (c.l + 0.5) / k;
+  const double a = scale_factor_of_chi(*c.cs, chi, st);
+  const double d1 = transfer_limber_wrap(c, c.t1, c.n1, lk, k, chi, a, st);
+  if (d1 == 0) return 0;
+  const double d2 = c.same ? d1 : transfer_limber_wrap(c, c.t2, c.n2, lk, k, chi, a, st);
+  if (d2 == 0) return 0;
+  const double pk = f2d_eval(*c.cs->psp, lk, a, c.cs, st);
+  return k * pk * d1 * d2;
+}
+
+// get_k_interval (src/ccl_cls.c:64-100)
+__device__ __forceinline__ void get_k_interval(const TaskCtx& c, const LimberParams& par, double& lkmin,
+                                               double& lkmax) {
+  double chi_min1 = 1E15, chi_max1 = -1E15;
+  for (int i = 0; i < c.n1; ++i) {
+    chi_min1 = fmin(chi_min1, c.t1[i].chi_min);
+    chi_max1 = fmax(chi_max1, c.t1[i].chi_max);
+  }
+  double chi_min2 = 1E15, chi_max2 = -1E15;
+  for (int i = 0; i < c.n2; ++i) {
+    chi_min2 = fmin(chi_min2, c.t2[i].chi_min);
+    chi_max2 = fmax(chi_max2, c.t2[i].chi_max);
+  }
+  double chi_min = fmax(chi_min1, chi_min2);
+  const double chi_max = fmin(chi_max1, chi_max2);
+  if (chi_min <= 0) chi_min = 0.5 * (c.l + 0.5) / par.K_MAX;
+  lkmax = log(fmin(par.K_MAX, 2 * (c.l + 0.5) / chi_min));
+  lkmin = log(fmax(par.K_MIN, (c.l + 0.5) / chi_max));
+}
+
+}  // namespace cclb

@@ -1,0 +1,700 @@
+// sm_100a kernels of the Limber C_ell path:
+//   * table preparation (GSL akima / natural cspline / bicubic derivative planes, index LUTs)
+//   * the Limber integrators: 'spline' (src/ccl_cls.c:189-225 + src/ccl_utils.c:274-345)
+//     and 'qag_quad' (src/ccl_cls.c:227-263, gsl_integration_qag with GK41)
+// One warp owns one (cosmology, pair, ell) C_ell: lanes walk the ln k sample axis, the
+// integrand samples live in shared memory, the Akima / Gauss-Kronrod sums are reduced with
+// warp shuffles.  Bound: fp64 DFMA pipe.
+#include <cfloat>
+#include <cstdio>
+
+#include "device_eval.cuh"
+#include "gk41_table.h"
+
+namespace cclb {
+
+// ------------------------------------------------------------------------------------------
+// Table preparation
+// ------------------------------------------------------------------------------------------
+
+// gsl akima_init + akima_calc (interpolation/akima.c), one CTA per spline.
+__global__ void akima_coef_kernel(const AkimaJob* jobs) {
+  const AkimaJob jb = jobs[blockIdx.x];
+  const int n = jb.n;
+  const double* x = jb.x;
+  const double* y = jb.y;
+  auto slope = [&](int j) -> double {  // m[j], j in [-2, n]
+    auto raw = [&](int q) { return (y[q + 1] - y[q]) / (x[q + 1] - x[q]); };
+    if (j >= 0 && j <= n - 2) return raw(j);
+    if (j == -1) return 2.0 * raw(0) - raw(1);
+    if (j == -2) return 3.0 * raw(0) - 2.0 * raw(1);
+    if (j == n - 1) return 2.0 * raw(n - 2) - raw(n - 3);
+    return 3.0 * raw(n - 2) - 2.0 * raw(n - 3);
+  };
+  for (int i = threadIdx.x; i < n - 1; i += blockDim.x) {
+    const double mm2 = slope(i - 2), mm1 = slope(i - 1), m0 = slope(i), mp1 = slope(i + 1),
+                 mp2 = slope(i + 2);
+    const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
+    double b, c, d;
+    if (NE == 0.0) {
+      b = m0; c = 0.0; d = 0.0;
+    } else {
+      const double h_i = x[i + 1] - x[i];
+      const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
+      const double alpha_i = fabs(mm1 - mm2) / NE;
+      double tL_ip1;
+      if (NE_next == 0.0) tL_ip1 = m0;
+      else {
+        const double alpha_ip1 = fabs(m0 - mm1) / NE_next;
+        tL_ip1 = (1.0 - alpha_ip1) * m0 + alpha_ip1 * mp1;
+      }
+      b = (1.0 - alpha_i) * mm1 + alpha_i * m0;
+      c = (3.0 * m0 - 2.0 * b - tL_ip1) / h_i;
+      d = (b + tL_ip1 - 2.0 * m0) / (h_i * h_i);
+    }
+    jb.co[i] = make_double4(y[i], b, c, d);
+  }
+}
+
+// Index LUT: lut[j] = gsl_interp_bsearch(x, x0 + j*bin).
+__global__ void lut_kernel(const LutJob* jobs) {
+  const LutJob jb = jobs[blockIdx.x];
+  const double x0 = jb.x[0];
+  const double bin = (jb.x[jb.n - 1] - x0) / jb.nlut;
+  for (int j = threadIdx.x; j < jb.nlut; j += blockDim.x) {
+    const double v = x0 + j * bin;
+    int lo = 0, hi = jb.n - 1;
+    while (hi > lo + 1) {
+      const int m = (hi + lo) >> 1;
+      if (jb.x[m] > v) hi = m; else lo = m;
+    }
+    // guard against rounding of x0 + j*bin: never start past the true interval
+    while (lo > 0 && jb.x[lo] > v) --lo;
+    jb.lut[j] = lo;
+  }
+}
+
+// LDL^T factors of the natural-spline tridiagonal system (gsl linalg/tridiag.c solve_tridiag):
+// alpha/gamma depend on the node spacing only.  sys = n-2 unknowns c_1..c_{n-2}.
+__device__ void tridiag_factor(const double* x, int n, double* alpha, double* gamma) {
+  const int N = n - 2;
+  if (N < 1) return;
+  auto diag = [&](int i) { return 2.0 * ((x[i + 2] - x[i + 1]) + (x[i + 1] - x[i])); };
+  auto off = [&](int i) { return x[i + 2] - x[i + 1]; };
+  alpha[0] = diag(0);
+  gamma[0] = off(0) / alpha[0];
+  for (int i = 1; i < N - 1; ++i) {
+    alpha[i] = diag(i) - off(i - 1) * gamma[i - 1];
+    gamma[i] = off(i) / alpha[i];
+  }
+  if (N > 1) alpha[N - 1] = diag(N - 1) - off(N - 2) * gamma[N - 2];
+}
+
+// Solve for the natural-spline c_i of data y(stride) on nodes x and emit, per node, the
+// first derivative gsl_spline_eval_deriv(spline, x_i) into out(stride).  `tmp` (same
+// indexing as out) is used as scratch for the forward sweep, so out may alias nothing
+// else.  Mirrors cspline_init + cspline_eval_deriv.
+__device__ void natural_spline_node_derivs(const double* x, int n, const double* y, size_t ystride,
+                                           double* out, size_t ostride, const double* alpha,
+                                           const double* gamma) {
+  const int N = n - 2;
+  auto Y = [&](int i) { return y[(size_t)i * ystride]; };
+  auto G = [&](int i) {
+    const double h_i = x[i + 1] - x[i];
+    const double h_ip1 = x[i + 2] - x[i + 1];
+    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0;
+    const double g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    return 3.0 * ((Y(i + 2) - Y(i + 1)) * g_ip1 - (Y(i + 1) - Y(i)) * g_i);
+  };
+  // forward sweep: z_i, then c~_i = z_i / alpha_i stored at node i+1
+  if (N == 1) {
+    out[ostride] = G(0) / (2.0 * ((x[2] - x[1]) + (x[1] - x[0])));
+  } else {
+    double z = G(0);
+    out[ostride] = z / alpha[0];
+    for (int i = 1; i < N; ++i) {
+      z = G(i) - gamma[i - 1] * z;
+      out[(size_t)(i + 1) * ostride] = z / alpha[i];
+    }
+  }
+  // back substitution fused with the derivative evaluation.  c_node[n-1] = 0.
+  double c_next = 0.0;  // c at node i+1
+  // last node: derivative of the last interval at its right end
+  // first get c at node n-2
+  double c_cur;
+  {
+    // node n-2 corresponds to system index N-1
+    c_cur = out[(size_t)(n - 2) * ostride];  // x[N-1] = c~[N-1]
+    const double h = x[n - 1] - x[n - 2];
+    const double dyv = Y(n - 1) - Y(n - 2);
+    const double b = (dyv / h) - h * (c_next + 2.0 * c_cur) / 3.0;
+    const double d = (c_next - c_cur) / (3.0 * h);
+    out[(size_t)(n - 1) * ostride] = b + h * (2.0 * c_cur + 3.0 * d * h);
+    out[(size_t)(n - 2) * ostride] = b;
+  }
+  c_next = c_cur;
+  for (int node = n - 3; node >= 0; --node) {
+    if (node >= 1) {
+      const int i = node - 1;  // system index
+      c_cur = out[(size_t)node * ostride] - gamma[i] * c_next;
+    } else
+      c_cur = 0.0;
+    const double h = x[node + 1] - x[node];
+    const double dyv = Y(node + 1) - Y(node);
+    out[(size_t)node * ostride] = (dyv / h) - h * (c_next + 2.0 * c_cur) / 3.0;
+    c_next = c_cur;
+  }
+}
+
+// Factorised-transfer splines: natural cspline coefficients {y, b, c, d} per interval
+// (cspline_init + coeff_calc of interpolation/cspline.c).  One thread per job.
+__global__ void cspline_coef_kernel(const CsplineJob* jobs, int njobs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  const CsplineJob jb = jobs[j];
+  const int n = jb.n;
+  const double* x = jb.x;
+  const double* y = jb.y;
+  double* alpha = jb.scratch;
+  double* gamma = jb.scratch + n;
+  double* c = jb.scratch + 2 * n;  // c at the nodes
+  const int N = n - 2;
+  c[0] = 0.0;
+  c[n - 1] = 0.0;
+  auto G = [&](int i) {
+    const double h_i = x[i + 1] - x[i];
+    const double h_ip1 = x[i + 2] - x[i + 1];
+    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0;
+    const double g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    return 3.0 * ((y[i + 2] - y[i + 1]) * g_ip1 - (y[i + 1] - y[i]) * g_i);
+  };
+  if (N == 1) {
+    c[1] = G(0) / (2.0 * ((x[2] - x[1]) + (x[1] - x[0])));
+  } else {
+    tridiag_factor(x, n, alpha, gamma);
+    double z = G(0);
+    c[1] = z / alpha[0];
+    for (int i = 1; i < N; ++i) {
+      z = G(i) - gamma[i - 1] * z;
+      c[i + 1] = z / alpha[i];
+    }
+    for (int i = N - 2; i >= 0; --i) c[i + 1] = c[i + 1] - gamma[i] * c[i + 2];
+  }
+  for (int i = 0; i < n - 1; ++i) {
+    const double dx = x[i + 1] - x[i];
+    const double dy = y[i + 1] - y[i];
+    const double b = (dy / dx) - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
+    const double d = (c[i + 1] - c[i]) / (3.0 * dx);
+    jb.co[i] = make_double4(y[i], b, c[i], d);
+  }
+}
+
+// bicubic_init (interp2d/bicubic.c).  Pass 0: tridiagonal factors of both axes + copy z.
+__global__ void bicubic_factor_kernel(const BicubicJob* jobs) {
+  const BicubicJob jb = jobs[blockIdx.x];
+  double* ak = jb.scratch;
+  double* gk = ak + jb.nk;
+  double* aa = gk + jb.nk;
+  double* ga = aa + jb.na;
+  if (threadIdx.x == 0) tridiag_factor(jb.xk, jb.nk, ak, gk);
+  if (threadIdx.x == 32) tridiag_factor(jb.ya, jb.na, aa, ga);
+  const int nn = jb.nk * jb.na;
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) jb.tab[i].x = jb.z[i];
+}
+
+// Pass 1: zx (rows, spline along ln k) and zy (columns, spline along a).
+// Pass 2: zxy = d/dx of the zy plane (rows).
+__global__ void bicubic_deriv_kernel(const BicubicJob* jobs, int pass) {
+  const BicubicJob jb = jobs[blockIdx.y];
+  const int nk = jb.nk, na = jb.na;
+  const double* ak = jb.scratch;
+  const double* gk = ak + nk;
+  const double* aa = gk + nk;
+  const double* ga = aa + na;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double* tab = reinterpret_cast<double*>(jb.tab);
+  if (pass == 1) {
+    if (t < na) {
+      // row t: y = z[t][*] (slot .x), out = zx (slot .y)
+      double* row = tab + (size_t)t * nk * 4;
+      natural_spline_node_derivs(jb.xk, nk, row + 0, 4, row + 1, 4, ak, gk);
+    } else if (t < na + nk) {
+      const int ik = t - na;
+      double* col = tab + (size_t)ik * 4;
+      natural_spline_node_derivs(jb.ya, na, col + 0, (size_t)nk * 4, col + 2, (size_t)nk * 4, aa, ga);
+    }
+  } else {
+    if (t < na) {
+      double* row = tab + (size_t)t * nk * 4;
+      natural_spline_node_derivs(jb.xk, nk, row + 2, 4, row + 3, 4, ak, gk);
+    }
+  }
+}
+
+void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs, const LutJob* d_lut,
+                 int nlut, const BicubicJob* d_bc, int nbc, int max_nk, int max_na,
+                 cudaStream_t stream) {
+  if (nak > 0) akima_coef_kernel<<<nak, 128, 0, stream>>>(d_ak);
+  if (nlut > 0) lut_kernel<<<nlut, 128, 0, stream>>>(d_lut);
+  if (ncs > 0) cspline_coef_kernel<<<(ncs + 63) / 64, 64, 0, stream>>>(d_cs, ncs);
+  if (nbc > 0) {
+    bicubic_factor_kernel<<<nbc, 256, 0, stream>>>(d_bc);
+    dim3 g1((max_na + max_nk + 63) / 64, nbc), g2((max_na + 63) / 64, nbc);
+    bicubic_deriv_kernel<<<g1, 64, 0, stream>>>(d_bc, 1);
+    bicubic_deriv_kernel<<<g2, 64, 0, stream>>>(d_bc, 2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Vectorised accessors (the pyccl-facing getters; not on the hot path)
+// ------------------------------------------------------------------------------------------
+__global__ void eval_achi_kernel(const Cosmo* cs, int n, const double* chi, double* out, int* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = 0;
+  out[i] = scale_factor_of_chi(*cs, chi[i], st);
+  if (st) atomicOr(status, st);  // ccl_scale_factor_of_chis: *status |= _status
+}
+
+__global__ void eval_f2d_kernel(const F2D* f, const Cosmo* cs, int n, const double* lk, const double* a,
+                                double* out, int* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = 0;
+  out[i] = f2d_eval(*f, lk[i], a[i], cs, st);
+  if (st) atomicCAS(status, 0, st);
+}
+
+__global__ void eval_tracer_kernel_kernel(const Tracer* tr, int n, const double* chi, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = tracer_kernel(*tr, chi[i]);
+}
+
+__global__ void eval_tracer_transfer_kernel(const Tracer* tr, int n, const double* lk, const double* a,
+                                            double* out, int* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = 0;
+  out[i] = tracer_transfer(*tr, lk[i], a[i], st);
+  if (st) atomicCAS(status, 0, st);
+}
+
+void launch_eval_achi(const Cosmo* d_cs, int n, const double* d_chi, double* d_out, int* d_status,
+                      cudaStream_t stream) {
+  if (n > 0) eval_achi_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_cs, n, d_chi, d_out, d_status);
+}
+void launch_eval_f2d(const F2D* d_f, const Cosmo* d_cs, int n, const double* d_lk, const double* d_a,
+                     double* d_out, int* d_status, cudaStream_t stream) {
+  if (n > 0) eval_f2d_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_f, d_cs, n, d_lk, d_a, d_out, d_status);
+}
+void launch_eval_tracer_kernel(const Tracer* d_tr, int n, const double* d_chi, double* d_out,
+                               cudaStream_t stream) {
+  if (n > 0) eval_tracer_kernel_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_tr, n, d_chi, d_out);
+}
+void launch_eval_tracer_transfer(const Tracer* d_tr, int n, const double* d_lk, const double* d_a,
+                                 double* d_out, int* d_status, cudaStream_t stream) {
+  if (n > 0)
+    eval_tracer_transfer_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_tr, n, d_lk, d_a, d_out, d_status);
+}
+
+// ------------------------------------------------------------------------------------------
+// Limber integrators
+// ------------------------------------------------------------------------------------------
+constexpr int WARPS_PER_CTA = 4;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ bool setup_task(const LimberProblem& P, long long task, TaskCtx& c, int& ic,
+                                           int& ip, int& il) {
+  il = (int)(task % P.nl);
+  const long long r = task / P.nl;
+  ip = (int)(r % P.npair);
+  ic = (int)(r / P.npair);
+  const Cosmo* cs = P.cosmos + ic;
+  const int2 pr = P.pairs[ip];
+  const int2 c1 = P.colls[pr.x], c2 = P.colls[pr.y];
+  c.cs = cs;
+  c.t1 = cs->tracers + c1.x;
+  c.n1 = c1.y;
+  c.t2 = cs->tracers + c2.x;
+  c.n2 = c2.y;
+  c.same = (pr.x == pr.y);
+  c.l = P.ells[il];
+  return true;
+}
+
+__device__ __forceinline__ void finish_task(const LimberProblem& P, int ic, int ip, int il, double result,
+                                            int st, int lane) {
+  if (lane != 0) return;
+  const size_t o = ((size_t)ic * P.npair + ip) * P.nl + il;
+  if (st == 0) {
+    P.cl[o] = result / (P.ells[il] + 0.5);  // src/ccl_cls.c:340
+  } else {
+    P.cl[o] = nan("");                       // src/ccl_cls.c:343-345
+    const size_t s = (size_t)ic * P.npair + ip;
+    P.status[s] = ST_ERR_INTEG;
+    atomicCAS(P.status_detail + s, 0, st);
+  }
+}
+
+// integ_cls_limber_spline (src/ccl_cls.c:189-225) + ccl_integ_spline/akima_eval_integ.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+limber_spline_kernel(const LimberProblem P, long long ntasks) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sf = smem + (size_t)warp * P.par.nk_cap;
+  const long long task = (long long)blockIdx.x * WARPS_PER_CTA + warp;
+  if (task >= ntasks) return;
+  TaskCtx c;
+  int ic, ip, il;
+  setup_task(P, task, c, ic, ip, il);
+  if (!c.cs->has_achi) {  // src/ccl_cls.c:274-280
+    finish_task(P, ic, ip, il, 0.0, ST_ERR_DISTANCES_INIT, lane);
+    return;
+  }
+  double lkmin, lkmax;
+  get_k_interval(c, P.par, lkmin, lkmax);
+  const int nk = (int)(fmax((lkmax - lkmin) / P.par.DLOGK_INTEGRATION + 0.5, 1.0)) + 1;
+  if (nk < 5 || nk > P.par.nk_cap) {
+    // gsl_spline_alloc(akima, n<5) == NULL -> CCL_ERROR_MEMORY.  nk > cap cannot
+    // happen: the host sizes nk_cap from (K_MAX, K_MIN, DLOGK); flagged rather than overrun.
+    finish_task(P, ic, ip, il, 0.0, ST_ERR_MEMORY, lane);
+    return;
+  }
+  // ccl_linear_spacing (src/ccl_utils.c:17-37)
+  const double dx = (lkmax - lkmin) / (nk - 1.);
+  auto node = [&](int i) -> double {
+    return (i == 0) ? lkmin : ((i == nk - 1) ? lkmax : lkmin + dx * i);
+  };
+  int st = 0;
+  for (int s = lane; s < nk; s += 32) {
+    int s1 = 0;
+    sf[s] = cl_integrand(c, node(s), s1);
+    if (s1 && !st) st = s1;
+  }
+  // any failing node fails the C_ell
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int other = __shfl_xor_sync(0xffffffffu, st, o);
+    if (!st) st = other;
+  }
+  __syncwarp();
+  if (st) {
+    finish_task(P, ic, ip, il, 0.0, st, lane);
+    return;
+  }
+  // Akima spline of the samples, integrated over [lk_0, lk_{nk-1}]
+  auto raw = [&](int q) -> double { return (sf[q + 1] - sf[q]) / (node(q + 1) - node(q)); };
+  auto slope = [&](int j) -> double {
+    if (j >= 0 && j <= nk - 2) return raw(j);
+    if (j == -1) return 2.0 * raw(0) - raw(1);
+    if (j == -2) return 3.0 * raw(0) - 2.0 * raw(1);
+    if (j == nk - 1) return 2.0 * raw(nk - 2) - raw(nk - 3);
+    return 3.0 * raw(nk - 2) - 2.0 * raw(nk - 3);
+  };
+  double acc = 0.0;
+  for (int i = lane; i < nk - 1; i += 32) {
+    const double mm2 = slope(i - 2), mm1 = slope(i - 1), m0 = slope(i), mp1 = slope(i + 1),
+                 mp2 = slope(i + 2);
+    const double x_lo = node(i), x_hi = node(i + 1);
+    const double h = x_hi - x_lo;
+    const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
+    double b, cc, d;
+    if (NE == 0.0) {
+      b = m0; cc = 0.0; d = 0.0;
+    } else {
+      const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
+      const double alpha_i = fabs(mm1 - mm2) / NE;
+      double tL;
+      if (NE_next == 0.0) tL = m0;
+      else {
+        const double alpha_ip1 = fabs(m0 - mm1) / NE_next;
+        tL = (1.0 - alpha_ip1) * m0 + alpha_ip1 * mp1;
+      }
+      b = (1.0 - alpha_i) * mm1 + alpha_i * m0;
+      cc = (3.0 * m0 - 2.0 * b - tL) / h;
+      d = (b + tL - 2.0 * m0) / (h * h);
+    }
+    const double y_lo = sf[i];
+    if (i == 0 || i == nk - 2) {
+      // integ_eval(y_lo, b, c, d, x_lo, x_lo, x_hi) (interpolation/integ_eval.h)
+      const double r1 = 0.0, r2 = x_hi - x_lo;
+      const double r12 = r1 + r2;
+      const double bterm = 0.5 * b * r12;
+      const double cterm = (1.0 / 3.0) * cc * (r1 * r1 + r2 * r2 + r1 * r2);
+      const double dterm = 0.25 * d * r12 * (r1 * r1 + r2 * r2);
+      acc += (x_hi - x_lo) * (y_lo + bterm + cterm + dterm);
+    } else {
+      acc += h * (y_lo + h * (0.5 * b + h * (cc / 3.0 + 0.25 * d * h)));
+    }
+  }
+  acc = warp_sum(acc);
+  finish_task(P, ic, ip, il, acc, 0, lane);
+}
+
+// ---- qag_quad ------------------------------------------------------------------------
+__constant__ double c_xgk[21];
+__constant__ double c_wgk[21];
+__constant__ double c_wg[10];
+static bool g_gk_uploaded[64] = {false};
+
+// rescale_error (integration/qk.c)
+__device__ __forceinline__ double rescale_error(double err, double result_abs, double result_asc) {
+  err = fabs(err);
+  if (result_asc != 0 && err != 0) {
+    const double scale = pow((200 * err / result_asc), 1.5);
+    err = (scale < 1) ? result_asc * scale : result_asc;
+  }
+  if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
+    const double min_err = 50 * DBL_EPSILON * result_abs;
+    if (min_err > err) err = min_err;
+  }
+  return err;
+}
+
+// gsl_integration_qk with the 41-point rule over NP (1 or 2) panels at once: the 41*NP
+// abscissae are spread over the warp's lanes, the four sums are shuffle-reduced.
+// fv: per-warp shared buffer of 2*41 doubles.
+template <int NP>
+__device__ __forceinline__ void qk41_warp(const TaskCtx& c, const double* pa, const double* pb, double* fv,
+                                          int lane, double* result, double* abserr, double* resabs,
+                                          double* resasc, int& st) {
+  // evaluation e in [0, 41): e<20 -> center - h*xgk[e]; 20<=e<40 -> center + h*xgk[e-20]; 40 -> center
+  for (int e = lane; e < 41 * NP; e += 32) {
+    const int p = e / 41, q = e - p * 41;
+    const double center = 0.5 * (pa[p] + pb[p]);
+    const double half_length = 0.5 * (pb[p] - pa[p]);
+    double xq;
+    if (q == 40) xq = center;
+    else if (q < 20) xq = center - half_length * c_xgk[q];
+    else xq = center + half_length * c_xgk[q - 20];
+    int s1 = 0;
+    fv[e] = cl_integrand(c, xq, s1);
+    if (s1 && !st) st = s1;
+  }
+  // every lane leaves with the same status word (first failing lane wins)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int other = __shfl_xor_sync(0xffffffffu, st, o);
+    if (!st) st = other;
+  }
+  {
+    const unsigned bad = __ballot_sync(0xffffffffu, st != 0);
+    if (bad) st = __shfl_sync(0xffffffffu, st, __ffs(bad) - 1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const double* f = fv + 41 * p;
+    const double half_length = 0.5 * (pb[p] - pa[p]);
+    const double abs_half_length = fabs(half_length);
+    double rk = 0, rg = 0, ra = 0;
+    double f1 = 0, f2 = 0;
+    if (lane < 20) {
+      f1 = f[lane];
+      f2 = f[lane + 20];
+      const double fsum = f1 + f2;
+      rk = c_wgk[lane] * fsum;
+      ra = c_wgk[lane] * (fabs(f1) + fabs(f2));
+      if (lane & 1) rg = c_wg[lane >> 1] * fsum;
+    } else if (lane == 20) {
+      f1 = f[40];
+      rk = f1 * c_wgk[20];
+      ra = fabs(rk);
+    }
+    rk = warp_sum(rk);
+    rg = warp_sum(rg);
+    ra = warp_sum(ra);
+    const double mean = rk * 0.5;
+    double rs = 0;
+    if (lane < 20) rs = c_wgk[lane] * (fabs(f1 - mean) + fabs(f2 - mean));
+    else if (lane == 20) rs = c_wgk[20] * fabs(f1 - mean);
+    rs = warp_sum(rs);
+    const double err = (rk - rg) * half_length;
+    rk *= half_length;
+    ra *= abs_half_length;
+    rs *= abs_half_length;
+    result[p] = rk;
+    resabs[p] = ra;
+    resasc[p] = rs;
+    abserr[p] = rescale_error(err, ra, rs);
+  }
+  __syncwarp();
+}
+
+// subinterval_too_small (integration/util.c)
+__device__ __forceinline__ bool subinterval_too_small(double a1, double a2, double b2) {
+  const double tmp = (1 + 100 * DBL_EPSILON) * (fabs(a2) + 1000 * DBL_MIN);
+  return fabs(a1) <= tmp && fabs(b2) <= tmp;
+}
+
+// integ_cls_limber_qag_quad (src/ccl_cls.c:227-263): gsl_integration_qag(F, lkmin, lkmax, 0,
+// epsrel, limit, GSL_INTEG_GAUSS41).  Persistent warps pull tasks from a counter; the
+// interval list (a, b, r, e) of the warp lives in its slice of a global workspace.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned long long* next_task) {
+  __shared__ double s_fv[WARPS_PER_CTA][2 * 41];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int limit = P.par.N_ITERATION;
+  double* alist = ws + ((size_t)blockIdx.x * WARPS_PER_CTA + warp) * 4 * (size_t)limit;
+  double* blist = alist + limit;
+  double* rlist = blist + limit;
+  double* elist = rlist + limit;
+  double* fv = s_fv[warp];
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(next_task, 1ull);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if ((long long)t >= ntasks) break;
+    TaskCtx c;
+    int ic, ip, il;
+    setup_task(P, (long long)t, c, ic, ip, il);
+    if (!c.cs->has_achi) {
+      finish_task(P, ic, ip, il, 0.0, ST_ERR_DISTANCES_INIT, lane);
+      continue;
+    }
+    double lkmin, lkmax;
+    get_k_interval(c, P.par, lkmin, lkmax);
+    const double epsabs = 0.0, epsrel = P.par.LIMBER_EPSREL;
+    int st = 0, gsl = 0;
+    unsigned long long nev = 41;
+    double result = 0.0;
+    if (epsabs <= 0 && (epsrel < 50 * DBL_EPSILON || epsrel < 0.5e-28)) {
+      gsl = ST_GSL_EBADTOL;
+    } else {
+      double r0[1], e0[1], ab0[1], as0[1];
+      const double pa0[1] = {lkmin}, pb0[1] = {lkmax};
+      qk41_warp<1>(c, pa0, pb0, fv, lane, r0, e0, ab0, as0, st);
+      double tolerance = fmax(epsabs, epsrel * fabs(r0[0]));
+      const double round_off = 50 * DBL_EPSILON * ab0[0];
+      result = r0[0];
+      if (e0[0] <= round_off && e0[0] > tolerance) gsl = ST_GSL_EROUND;
+      else if ((e0[0] <= tolerance && e0[0] != as0[0]) || e0[0] == 0.0) gsl = 0;
+      else if (limit == 1) gsl = ST_GSL_EMAXITER;
+      else {
+        if (lane == 0) { alist[0] = lkmin; blist[0] = lkmax; rlist[0] = r0[0]; elist[0] = e0[0]; }
+        __syncwarp();
+        int size = 1;
+        double area = r0[0], errsum = e0[0];
+        int iteration = 1, roundoff_type1 = 0, roundoff_type2 = 0, error_type = 0;
+        do {
+          // retrieve(): interval with the largest error estimate
+          double emax = -1.0;
+          int imax = 0;
+          for (int i = lane; i < size; i += 32) {
+            const double e = elist[i];
+            if (e > emax) { emax = e; imax = i; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double eo = __shfl_xor_sync(0xffffffffu, emax, o);
+            const int io = __shfl_xor_sync(0xffffffffu, imax, o);
+            if (eo > emax || (eo == emax && io < imax)) { emax = eo; imax = io; }
+          }
+          const double a_i = alist[imax], b_i = blist[imax], r_i = rlist[imax], e_i = elist[imax];
+          const double a1 = a_i, b1 = 0.5 * (a_i + b_i), a2 = b1, b2 = b_i;
+          double ar[2], er[2], rab[2], ras[2];
+          const double pa[2] = {a1, a2}, pb[2] = {b1, b2};
+          qk41_warp<2>(c, pa, pb, fv, lane, ar, er, rab, ras, st);
+          nev += 82;
+          const double area12 = ar[0] + ar[1];
+          const double error12 = er[0] + er[1];
+          errsum += (error12 - e_i);
+          area += area12 - r_i;
+          if (ras[0] != er[0] && ras[1] != er[1]) {
+            const double delta = r_i - area12;
+            if (fabs(delta) <= 1.0e-5 * fabs(area12) && error12 >= 0.99 * e_i) roundoff_type1++;
+            if (iteration >= 10 && error12 > e_i) roundoff_type2++;
+          }
+          tolerance = fmax(epsabs, epsrel * fabs(area));
+          if (errsum > tolerance) {
+            if (roundoff_type1 >= 6 || roundoff_type2 >= 20) error_type = 2;
+            if (subinterval_too_small(a1, a2, b2)) error_type = 3;
+          }
+          // update(): larger-error half stays at imax, the other is appended
+          __syncwarp();
+          if (lane == 0) {
+            if (er[1] > er[0]) {
+              alist[imax] = a2; rlist[imax] = ar[1]; elist[imax] = er[1];
+              alist[size] = a1; blist[size] = b1; rlist[size] = ar[0]; elist[size] = er[0];
+            } else {
+              blist[imax] = b1; rlist[imax] = ar[0]; elist[imax] = er[0];
+              alist[size] = a2; blist[size] = b2; rlist[size] = ar[1]; elist[size] = er[1];
+            }
+          }
+          __syncwarp();
+          size++;
+          iteration++;
+          if (st) break;  // integrand status poisons the C_ell anyway
+        } while (iteration < limit && !error_type && errsum > tolerance);
+        double sum = 0.0;
+        for (int i = lane; i < size; i += 32) sum += rlist[i];
+        result = warp_sum(sum);
+        if (errsum <= tolerance) gsl = 0;
+        else if (error_type == 2) gsl = ST_GSL_EROUND;
+        else if (error_type == 3) gsl = ST_GSL_ESING;
+        else if (iteration == limit) gsl = ST_GSL_EMAXITER;
+        else gsl = ST_GSL_EFAILED;
+      }
+    }
+    if (P.counters && lane == 0) atomicAdd(P.counters, nev);
+    // GSL_EROUND would switch the reference to CQUAD (src/ccl_cls.c:245-259); that branch is
+    // not implemented on the device and is reported as a failed C_ell with detail GSL_EROUND.
+    finish_task(P, ic, ip, il, result, st ? st : gsl, lane);
+  }
+}
+
+size_t limber_qag_workspace_bytes(int n_iteration) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t warps = (size_t)sms * 8 * WARPS_PER_CTA;
+  return warps * 4 * (size_t)n_iteration * sizeof(double) + 64;  // + task counter
+}
+
+int limber_nk_cap(const LimberParams& par) {
+  // upper bound of nk over all (pair, ell): lkmax - lkmin <= ln(K_MAX / K_MIN)
+  const double span = log(par.K_MAX / par.K_MIN);
+  int cap = (int)(fmax(span / par.DLOGK_INTEGRATION + 0.5, 1.0)) + 2;
+  return (cap + 3) & ~3;
+}
+
+cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws, size_t qag_ws_bytes,
+                          cudaStream_t stream) {
+  const long long ntasks = (long long)prob.ncosmo * prob.npair * prob.nl;
+  if (ntasks == 0) return cudaSuccess;
+  if (method == INTEG_SPLINE) {
+    const size_t smem = (size_t)WARPS_PER_CTA * prob.par.nk_cap * sizeof(double);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(limber_spline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long nblk = (ntasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (nblk > 0x7fffffffLL) return cudaErrorInvalidValue;
+    limber_spline_kernel<<<(unsigned)nblk, WARPS_PER_CTA * 32, smem, stream>>>(prob, ntasks);
+  } else {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!g_gk_uploaded[dev & 63]) {
+      cudaMemcpyToSymbol(c_xgk, GK41_XGK, sizeof(double) * 21);
+      cudaMemcpyToSymbol(c_wgk, GK41_WGK, sizeof(double) * 21);
+      cudaMemcpyToSymbol(c_wg, GK41_WG, sizeof(double) * 10);
+      g_gk_uploaded[dev & 63] = true;
+    }
+    const int nblk = sms * 8;
+    if ((size_t)nblk * WARPS_PER_CTA * 4 * (size_t)prob.par.N_ITERATION * sizeof(double) + 64 > qag_ws_bytes)
+      return cudaErrorInvalidValue;
+    unsigned long long* next =
+        reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(qag_ws) + qag_ws_bytes - 64);
+    cudaMemsetAsync(next, 0, sizeof(unsigned long long), stream);
+    limber_qag_kernel<<<nblk, WARPS_PER_CTA * 32, 0, stream>>>(prob, ntasks, qag_ws, next);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace cclb

@@ -1,0 +1,139 @@
+// Device table descriptors for the B200 Limber C_ell path.
+//
+// Every reference object the hot path reads is flattened into
+// plain-old-data descriptors holding device pointers into one HBM arena:
+//   ccl_f1d_t / gsl akima spline      -> Spline1D   (include/ccl_f1d.h:25-34)
+//   gsl cspline (factorised f2d)      -> Spline1D   (src/ccl_f2d.c:152,161)
+//   ccl_f2d_t                          -> F2D        (include/ccl_f2d.h:29-44)
+//   ccl_cl_tracer_t                    -> Tracer     (include/ccl_tracers.h:15-22)
+//   ccl_cosmology (a(chi), growth)     -> Cosmo      (include/ccl_core.h:260)
+// Spline polynomial coefficients are precomputed per interval as one 32-byte record
+// {y_i, b_i, c_i, d_i} so that an evaluation is one index search plus one aligned
+// 2 x fp64x2 load; the bicubic P(k,a) keeps {z, zx, zy, zxy} interleaved per node.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace cclb {
+
+// GSL / CCL status codes reproduced on the device (include/ccl_error.h:10-48, gsl_errno.h)
+enum : int {
+  ST_OK = 0,
+  ST_GSL_EDOM = 1,
+  ST_GSL_EINVAL = 4,
+  ST_GSL_EFAILED = 5,
+  ST_GSL_EMAXITER = 11,
+  ST_GSL_EBADTOL = 13,
+  ST_GSL_EROUND = 18,
+  ST_GSL_ESING = 21,
+  ST_ERR_MEMORY = 1025,
+  ST_ERR_INCONSISTENT = 1027,
+  ST_ERR_SPLINE = 1028,
+  ST_ERR_SPLINE_EV = 1029,
+  ST_ERR_INTEG = 1030,
+  ST_ERR_COMPUTECHI = 1033,
+  ST_ERR_NOT_IMPLEMENTED = 1040,
+  ST_ERR_GROWTH_INIT = 1058,
+  ST_ERR_DISTANCES_INIT = 1059,
+};
+
+enum : int { GROWTH_CCL = 401, GROWTH_CONST = 403, GROWTH_NONE = 404 };  // include/ccl_f2d.h:13-18
+enum : int { INTEG_QAG = 500, INTEG_SPLINE = 501 };                      // include/ccl_utils.h:12-15
+
+// One piecewise-cubic 1-D interpolant with GSL's interval convention
+// (x_i <= x < x_{i+1}, last interval closed).  `lut` maps nlut uniform bins of
+// [x[0], x[n-1]] to the interval holding the bin's left edge, so a lookup is one LUT
+// load plus a short forward scan instead of a log2(n)-step binary search.
+struct Spline1D {
+  const double* x;    // [n] nodes, strictly increasing
+  const double4* co;  // [n-1] {y_i, b_i, c_i, d_i}
+  const int* lut;     // [nlut]
+  int n;
+  int nlut;
+  double x0;       // x[0]
+  double xn;       // x[n-1]
+  double inv_bin;  // nlut / (xn - x0)
+};
+
+struct F2D {
+  int is_factorizable, is_k_constant, is_a_constant, is_log;
+  int extrap_order_lok, extrap_order_hik, extrap_linear_growth, growth_exponent;
+  int has_fk, has_fa, has_fka, pad0;
+  double growth_factor_0;
+  double lkmin, lkmax, amin, amax;
+  Spline1D fk;  // natural cspline in ln k (factorised form)
+  Spline1D fa;  // natural cspline in a   (factorised form)
+  // bicubic form: tab[ia*nk + ik] = {z, dz/dlnk, dz/da, d2z/dlnk da} (GSL zx, zy, zxy)
+  const double4* tab;
+  Spline1D gk;  // node array + LUT of the ln k axis (co unused)
+  Spline1D ga;  // node array + LUT of the a axis    (co unused)
+};
+
+struct Tracer {
+  int der_bessel, der_angles, has_kernel, has_transfer;
+  double chi_min, chi_max;
+  Spline1D kernel;  // Akima W(chi); value 0 at and outside the end nodes (src/ccl_f1d.c:137-161)
+  F2D transfer;
+};
+
+struct Cosmo {
+  Spline1D achi;    // Akima a(chi)
+  Spline1D growth;  // Akima D(a), normalised to D(1)=1
+  int has_achi, has_growth;
+  const F2D* psp;          // P(k,a) used for this cosmology
+  const Tracer* tracers;   // all sub-tracers of this cosmology
+  int ntracers, pad0;
+};
+
+// Parameters the path reads from ccl_spline_params / ccl_gsl_params
+struct LimberParams {
+  double K_MAX, K_MIN, DLOGK_INTEGRATION, LIMBER_EPSREL;
+  int N_ITERATION;
+  int nk_cap;  // capacity (nodes) of the per-warp integrand buffer
+};
+
+// One launch: cl[(ic*npair + ip)*nl + il]
+struct LimberProblem {
+  const Cosmo* cosmos;
+  const int2* colls;  // [ncoll] {first sub-tracer, count}
+  const int2* pairs;  // [npair] {collection 1, collection 2}
+  const double* ells;
+  int ncosmo, npair, nl, ncoll;
+  LimberParams par;
+  double* cl;
+  int* status;         // [ncosmo*npair] 0 or CCL_ERROR_INTEG
+  int* status_detail;  // [ncosmo*npair] first underlying code
+  unsigned long long* counters;  // [0] integrand evaluations (qag only)
+};
+
+// ---- table-preparation jobs (device kernels fill the derived regions of the arena) ----
+struct AkimaJob { const double* x; const double* y; double4* co; int n; };
+struct CsplineJob { const double* x; const double* y; double4* co; double* scratch; int n; };
+struct LutJob { const double* x; int* lut; int n; int nlut; };
+struct BicubicJob {
+  const double* xk;  // [nk]
+  const double* ya;  // [na]
+  const double* z;   // [na*nk]
+  double4* tab;      // [na*nk]
+  double* scratch;   // [2*(nk+na)] alpha/gamma of both axes
+  int nk, na;
+};
+
+// launchers (kernels.cu)
+void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs, const LutJob* d_lut,
+                 int nlut, const BicubicJob* d_bc, int nbc, int max_nk, int max_na,
+                 cudaStream_t stream);
+cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws, size_t qag_ws_bytes,
+                          cudaStream_t stream);
+size_t limber_qag_workspace_bytes(int n_iteration);
+int limber_nk_cap(const LimberParams& par);
+// vectorised accessors (ccl_scale_factor_of_chis, pk2d_eval_multi, cl_tracer_get_kernel/_transfer)
+void launch_eval_achi(const Cosmo* d_cs, int n, const double* d_chi, double* d_out, int* d_status,
+                      cudaStream_t stream);
+void launch_eval_f2d(const F2D* d_f, const Cosmo* d_cs, int n, const double* d_lk, const double* d_a,
+                     double* d_out, int* d_status, cudaStream_t stream);
+void launch_eval_tracer_kernel(const Tracer* d_tr, int n, const double* d_chi, double* d_out,
+                               cudaStream_t stream);
+void launch_eval_tracer_transfer(const Tracer* d_tr, int n, const double* d_lk, const double* d_a,
+                                 double* d_out, int* d_status, cudaStream_t stream);
+
+}  // namespace cclb

@@ -1,0 +1,299 @@
+"""Thin object wrappers over the C ABI (one Python object per C handle).
+
+These are what pyccl's SWIG proxies are for the reference: ``Cosmology.cosmo``, ``Pk2D.psp``,
+``Tracer._trc[i]`` hold one of these.  All numerical work happens in libccl_b200.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import darr, iarr
+
+
+class CCLB200Error(RuntimeError):
+    pass
+
+
+def _check(status, where=""):
+    if status != 0:
+        raise CCLB200Error("status %d in %s: %s" % (status, where, _lib.last_error()))
+
+
+def make_params(K_MAX=1e3, K_MIN=5e-5, DLOGK_INTEGRATION=0.025, INTEGRATION_LIMBER_EPSREL=1e-4,
+                N_ITERATION=1000, A_SPLINE_MIN=0.1):
+    return _lib.Params(K_MAX, K_MIN, DLOGK_INTEGRATION, INTEGRATION_LIMBER_EPSREL, N_ITERATION, A_SPLINE_MIN)
+
+
+def _tracer_args(sub):
+    """Map a sub-tracer dict (keys like Tracer.add_tracer) to ccl_cl_tracer_t_new's argument list."""
+    chi, pchi = darr(sub.get("chi"))
+    w, pw = darr(sub.get("w"))
+    a, pa = darr(sub.get("a"))
+    lk, plk = darr(sub.get("lk"))
+    fka = sub.get("fka")
+    fka, pfka = darr(None if fka is None else np.asarray(fka).ravel())
+    fk, pfk = darr(sub.get("fk"))
+    fa, pfa = darr(sub.get("fa"))
+    keep = (chi, w, a, lk, fka, fk, fa)
+    is_fact = int(fka is None)
+    args = [int(sub.get("der_bessel", 0)), int(sub.get("der_angles", 0)),
+            0 if chi is None else len(chi), pchi, pw,
+            0 if a is None else len(a), pa, 0 if lk is None else len(lk), plk, pfka, pfk, pfa,
+            int(sub.get("is_logt", False)), is_fact, int(sub.get("extrap_order_lok", 0)),
+            int(sub.get("extrap_order_hik", 2))]
+    return keep, args
+
+
+class LibCosmology:
+    def __init__(self, params=None):
+        L = _lib.load()
+        st = C.c_int(0)
+        self.params = params or make_params()
+        self.h = L.ccl_b200_cosmology_new(C.byref(self.params), C.byref(st))
+        _check(st.value, "cosmology_new")
+
+    def set_achi(self, chi, a):
+        st = C.c_int(0)
+        k1, p1 = darr(chi)
+        k2, p2 = darr(a)
+        _lib.load().ccl_b200_cosmology_set_achi(self.h, len(k1), p1, p2, C.byref(st))
+        _check(st.value, "set_achi")
+
+    def distances_from_input(self, a, chi):
+        st = C.c_int(0)
+        k1, p1 = darr(a)
+        k2, p2 = darr(chi)
+        _lib.load().ccl_b200_cosmology_distances_from_input(self.h, len(k1), p1, p2, C.byref(st))
+        _check(st.value, "distances_from_input")
+
+    def set_growth(self, a, growth):
+        st = C.c_int(0)
+        k1, p1 = darr(a)
+        k2, p2 = darr(growth)
+        _lib.load().ccl_b200_cosmology_set_growth(self.h, len(k1), p1, p2, C.byref(st))
+        _check(st.value, "set_growth")
+
+    def set_chi_max_nokernel(self, chi):
+        _lib.load().ccl_b200_cosmology_set_chi_max_nokernel(self.h, float(chi))
+
+    def scale_factor_of_chi(self, chi):
+        k, p = darr(np.atleast_1d(chi))
+        out = np.empty_like(k)
+        st = C.c_int(0)
+        _lib.load().ccl_b200_scale_factor_of_chis(self.h, len(k), p, out.ctypes.data_as(_lib._dp), C.byref(st))
+        return out, st.value
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib._LIB is not None:
+            _lib._LIB.ccl_b200_cosmology_free(self.h)
+            self.h = None
+
+
+class LibF2D:
+    def __init__(self, a=None, lk=None, fka=None, fk=None, fa=None, is_factorizable=False,
+                 extrap_order_lok=1, extrap_order_hik=2, extrap_linear_growth=_lib.F2D_CCLGROWTH,
+                 is_log=False, growth_factor_0=1.0, growth_exponent=0):
+        ka, pa = darr(a)
+        kl, pl = darr(lk)
+        kf, pf = darr(None if fka is None else np.asarray(fka).ravel())
+        kk, pk = darr(fk)
+        kz, pz = darr(fa)
+        st = C.c_int(0)
+        self.h = _lib.load().ccl_b200_f2d_new(0 if a is None else len(ka), pa, 0 if lk is None else len(kl), pl,
+                                              pf, pk, pz, int(is_factorizable), extrap_order_lok,
+                                              extrap_order_hik, extrap_linear_growth, int(is_log),
+                                              growth_factor_0, growth_exponent, C.byref(st))
+        self.status = st.value
+        _check(st.value, "f2d_new")
+
+    def eval(self, lk, a, cosmo=None):
+        k, p = darr(np.atleast_1d(lk))
+        out = np.empty_like(k)
+        st = C.c_int(0)
+        _lib.load().ccl_b200_f2d_eval_multi(self.h, p, len(k), float(a), cosmo.h if cosmo is not None else None,
+                                            out.ctypes.data_as(_lib._dp), C.byref(st))
+        return out, st.value
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib._LIB is not None:
+            _lib._LIB.ccl_b200_f2d_free(self.h)
+            self.h = None
+
+
+class LibTracer:
+    """One ccl_cl_tracer_t."""
+
+    def __init__(self, cosmo, **sub):
+        keep, args = _tracer_args(sub)
+        st = C.c_int(0)
+        self.h = _lib.load().ccl_b200_cl_tracer_t_new(cosmo.h if cosmo is not None else None, *args, C.byref(st))
+        _check(st.value, "cl_tracer_t_new")
+        self.der_bessel = args[0]
+        self.der_angles = args[1]
+
+    @property
+    def chi_min(self):
+        return _lib.load().ccl_b200_cl_tracer_t_chi_min(self.h)
+
+    @property
+    def chi_max(self):
+        return _lib.load().ccl_b200_cl_tracer_t_chi_max(self.h)
+
+    def f_ell(self, ell):
+        k, p = darr(np.atleast_1d(ell))
+        out = np.empty_like(k)
+        st = C.c_int(0)
+        _lib.load().ccl_b200_cl_tracer_get_f_ell(self.h, len(k), p, out.ctypes.data_as(_lib._dp), C.byref(st))
+        _check(st.value, "get_f_ell")
+        return out
+
+    def kernel(self, chi):
+        k, p = darr(np.atleast_1d(chi))
+        out = np.empty_like(k)
+        st = C.c_int(0)
+        _lib.load().ccl_b200_cl_tracer_get_kernel(self.h, len(k), p, out.ctypes.data_as(_lib._dp), C.byref(st))
+        _check(st.value, "get_kernel")
+        return out
+
+    def transfer(self, lk, a):
+        kl, pl = darr(np.atleast_1d(lk))
+        ka, pa = darr(np.atleast_1d(a))
+        out = np.empty(len(kl) * len(ka))
+        st = C.c_int(0)
+        _lib.load().ccl_b200_cl_tracer_get_transfer(self.h, len(kl), pl, len(ka), pa,
+                                                    out.ctypes.data_as(_lib._dp), C.byref(st))
+        _check(st.value, "get_transfer")
+        return out.reshape(len(kl), len(ka))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib._LIB is not None:
+            _lib._LIB.ccl_b200_cl_tracer_t_free(self.h)
+            self.h = None
+
+
+def angular_cls_limber(cosmo, trs1, trs2, psp, ells, method=_lib.INTEGRATION_SPLINE):
+    """ccl_angular_cls_limber through the single-pair C entry.  Returns (cl, status)."""
+    L = _lib.load()
+    st = C.c_int(0)
+    c1 = L.ccl_b200_cl_tracer_collection_t_new(C.byref(st))
+    same = trs1 is trs2
+    c2 = c1 if same else L.ccl_b200_cl_tracer_collection_t_new(C.byref(st))
+    for t in trs1:
+        L.ccl_b200_add_cl_tracer_to_collection(c1, t.h, C.byref(st))
+    if not same:
+        for t in trs2:
+            L.ccl_b200_add_cl_tracer_to_collection(c2, t.h, C.byref(st))
+    ke, pe = darr(np.atleast_1d(ells))
+    cl = np.empty(len(ke))
+    L.ccl_b200_angular_cls_limber(cosmo.h, c1, c2, psp.h, len(ke), pe, cl.ctypes.data_as(_lib._dp), int(method),
+                                  C.byref(st))
+    L.ccl_b200_cl_tracer_collection_t_free(c1)
+    if not same:
+        L.ccl_b200_cl_tracer_collection_t_free(c2)
+    return cl, st.value
+
+
+class LibBatch:
+    """ccl_b200_batch: N cosmologies' tables in one HBM arena + the batched Limber entry."""
+
+    def __init__(self, ncosmo, params=None):
+        st = C.c_int(0)
+        self.params = params or make_params()
+        self.ncosmo = ncosmo
+        self.h = _lib.load().ccl_b200_batch_new(ncosmo, C.byref(self.params), C.byref(st))
+        _check(st.value, "batch_new")
+        self._geom = None
+
+    def reset(self):
+        _lib.load().ccl_b200_batch_reset(self.h)
+
+    def set_cosmology(self, ic, chi, a, a_growth=None, growth=None, chi_max_nokernel=None):
+        L = _lib.load()
+        st = C.c_int(0)
+        k1, p1 = darr(chi)
+        k2, p2 = darr(a)
+        L.ccl_b200_batch_set_achi(self.h, ic, len(k1), p1, p2, C.byref(st))
+        _check(st.value, "batch_set_achi")
+        if a_growth is not None:
+            k3, p3 = darr(a_growth)
+            k4, p4 = darr(growth)
+            L.ccl_b200_batch_set_growth(self.h, ic, len(k3), p3, p4, C.byref(st))
+            _check(st.value, "batch_set_growth")
+        if chi_max_nokernel is not None:
+            L.ccl_b200_batch_set_chi_max_nokernel(self.h, ic, float(chi_max_nokernel))
+
+    def set_pk2d(self, ic, lk, a, pk, order_lok=1, order_hik=2, is_logp=True):
+        st = C.c_int(0)
+        k1, p1 = darr(lk)
+        k2, p2 = darr(a)
+        k3, p3 = darr(np.asarray(pk).ravel())
+        _lib.load().ccl_b200_batch_set_pk2d(self.h, ic, p1, len(k1), p2, len(k2), p3, order_lok, order_hik,
+                                            int(is_logp), C.byref(st))
+        _check(st.value, "batch_set_pk2d")
+
+    def add_tracer(self, ic, **sub):
+        keep, args = _tracer_args(sub)
+        st = C.c_int(0)
+        idx = _lib.load().ccl_b200_batch_add_tracer(self.h, ic, *args, C.byref(st))
+        _check(st.value, "batch_add_tracer")
+        return idx
+
+    def tracer_chi_range(self, ic, it):
+        lo, hi = C.c_double(), C.c_double()
+        _lib.load().ccl_b200_batch_tracer_chi_range(self.h, ic, it, C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    def commit(self):
+        st = C.c_int(0)
+        _lib.load().ccl_b200_batch_commit(self.h, C.byref(st))
+        _check(st.value, "batch_commit")
+
+    @property
+    def h2d_bytes(self):
+        return _lib.load().ccl_b200_batch_h2d_bytes(self.h)
+
+    @property
+    def arena_bytes(self):
+        return _lib.load().ccl_b200_batch_arena_bytes(self.h)
+
+    def _geometry(self, collections, pairs, ells):
+        cs, pcs = iarr([c[0] for c in collections])
+        cc, pcc = iarr([c[1] for c in collections])
+        p1, pp1 = iarr([p[0] for p in pairs])
+        p2, pp2 = iarr([p[1] for p in pairs])
+        el, pel = darr(ells)
+        return (cs, cc, p1, p2, el), (len(collections), pcs, pcc, len(pairs), pp1, pp2, len(el), pel)
+
+    def angular_cl(self, collections, pairs, ells, method=_lib.INTEGRATION_SPLINE):
+        """Host-buffer entry: returns (cl[ncosmo, npair, nl], status[ncosmo, npair], status)."""
+        keep, g = self._geometry(collections, pairs, ells)
+        cl = np.empty((self.ncosmo, len(pairs), len(keep[4])))
+        stat = np.zeros((self.ncosmo, len(pairs)), dtype=np.int32)
+        st = C.c_int(0)
+        _lib.load().ccl_b200_batch_angular_cls_limber(self.h, *g, int(method), cl.ctypes.data_as(_lib._dp),
+                                                      stat.ctypes.data_as(_lib._ip), C.byref(st))
+        if st.value not in (0, 1030):
+            _check(st.value, "batch_angular_cls_limber")
+        return cl, stat, st.value
+
+    def angular_cl_dev(self, collections, pairs, ells, d_cl, d_status, method=_lib.INTEGRATION_SPLINE, stream=0):
+        """Device-buffer entry: d_cl / d_status are raw device pointers (ints), e.g. tensor.data_ptr()."""
+        keep, g = self._geometry(collections, pairs, ells)
+        st = C.c_int(0)
+        _lib.load().ccl_b200_batch_angular_cls_limber_dev(self.h, *g, int(method), C.c_void_p(d_cl),
+                                                          C.c_void_p(d_status), C.c_void_p(stream), C.byref(st))
+        _check(st.value, "batch_angular_cls_limber_dev")
+
+    def spline_nodes(self, collections, pairs, ells):
+        keep, g = self._geometry(collections, pairs, ells)
+        return _lib.load().ccl_b200_batch_spline_nodes(self.h, *g)
+
+    @property
+    def last_qag_evals(self):
+        return _lib.load().ccl_b200_batch_last_qag_evals(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib._LIB is not None:
+            _lib._LIB.ccl_b200_batch_free(self.h)
+            self.h = None

@@ -1,0 +1,199 @@
+/*
+ * ccl_b200.h -- C ABI of the B200-native Limber angular power spectrum path.
+ *
+ * Drop-in boundary for ccl_angular_cls_limber (reference: /root/reference/src/ccl_cls.c:265-363,
+ * declared include/ccl_cls.h:20-26, bound by pyccl/ccl_cls.i:98-112) and for the object
+ * constructors that sit on the same boundary.  Plain pointers and sizes only; every entry
+ * takes `int *status` with the reference's convention (pyccl/ccl.i:34): in/out, 0 = OK,
+ * CCL_ERROR_* / GSL codes otherwise, and a call is a no-op when *status != 0 on entry.
+ *
+ * There is NO CPU fallback: every compute entry runs hand-written sm_100a kernels and fails
+ * with CCL_B200_ERROR_CUDA when no usable GPU is present.
+ *
+ * Ownership: input arrays are borrowed for the duration of the call and copied into the
+ * object's HBM arena; objects are freed by their *_free function.  Thread-safety matches the
+ * reference: objects are immutable after construction; concurrent calls on distinct objects
+ * are safe; one object must not be freed while a call uses it.
+ */
+#ifndef CCL_B200_H
+#define CCL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes shared with the reference (include/ccl_error.h:10-48) */
+#define CCL_B200_ERROR_MEMORY 1025
+#define CCL_B200_ERROR_INCONSISTENT 1027
+#define CCL_B200_ERROR_SPLINE 1028
+#define CCL_B200_ERROR_SPLINE_EV 1029
+#define CCL_B200_ERROR_INTEG 1030
+#define CCL_B200_ERROR_NOT_IMPLEMENTED 1040
+#define CCL_B200_ERROR_GROWTH_INIT 1058
+#define CCL_B200_ERROR_DISTANCES_INIT 1059
+/* library-specific: CUDA runtime failure / no device / extension unusable */
+#define CCL_B200_ERROR_CUDA 2001
+
+/* ccl_integration_t (include/ccl_utils.h:12-15) */
+#define CCL_B200_INTEGRATION_QAG_QUAD 500
+#define CCL_B200_INTEGRATION_SPLINE 501
+/* ccl_f2d_extrap_growth_t (include/ccl_f2d.h:13-18) */
+#define CCL_B200_F2D_CCLGROWTH 401
+#define CCL_B200_F2D_CONSTANTGROWTH 403
+#define CCL_B200_F2D_NO_EXTRAPOL 404
+
+typedef struct ccl_b200_cosmology ccl_b200_cosmology;    /* ccl_cosmology, as seen by the path */
+typedef struct ccl_b200_f2d ccl_b200_f2d;                /* ccl_f2d_t */
+typedef struct ccl_b200_tracer ccl_b200_tracer;          /* ccl_cl_tracer_t */
+typedef struct ccl_b200_collection ccl_b200_collection;  /* ccl_cl_tracer_collection_t */
+typedef struct ccl_b200_batch ccl_b200_batch;            /* N cosmologies' table packs in one arena */
+
+/* The spline/gsl parameters the path reads (include/ccl_core.h:94-178; defaults
+ * src/ccl_core.c:67-141).  Snapshotted by value at cosmology creation like the reference
+ * (src/ccl_core.c:247-248). */
+typedef struct {
+  double K_MAX;                     /* 1e3   */
+  double K_MIN;                     /* 5e-5  */
+  double DLOGK_INTEGRATION;         /* 0.025 */
+  double INTEGRATION_LIMBER_EPSREL; /* 1e-4  */
+  int N_ITERATION;                  /* 1000  */
+  double A_SPLINE_MIN;              /* 0.1: chi_max of kernel-less tracers = chi(A_SPLINE_MIN) */
+} ccl_b200_params;
+
+/* ---- library ---- */
+/* Select the CUDA device used by subsequently created objects (per calling thread). */
+void ccl_b200_set_device(int device, int *status);
+int ccl_b200_device_count(void);
+/* Human-readable message of the last failure on this thread (ccl_cosmology.status_message). */
+const char *ccl_b200_last_error(void);
+const char *ccl_b200_version(void);
+void ccl_b200_default_params(ccl_b200_params *p);
+
+/* ---- cosmology: background tables (src/ccl_background.c) ---- */
+ccl_b200_cosmology *ccl_b200_cosmology_new(const ccl_b200_params *params, int *status);
+void ccl_b200_cosmology_free(ccl_b200_cosmology *cosmo);
+/* Install the a(chi) Akima table that ccl_cosmology_compute_distances leaves in
+ * cosmo->data.achi (src/ccl_background.c:521-571): chi increasing, chi[0] = 0. */
+void ccl_b200_cosmology_set_achi(ccl_b200_cosmology *cosmo, int n, const double *chi, const double *a,
+                                 int *status);
+/* ccl_cosmology_distances_from_input (src/ccl_background.c:595-680): a increasing, chi(a)
+ * decreasing; the a(chi) spline is built on the reversed arrays.  Also sets A_SPLINE_MIN = a[0]. */
+void ccl_b200_cosmology_distances_from_input(ccl_b200_cosmology *cosmo, int na, const double *a,
+                                             const double *chi_a, int *status);
+/* Growth factor table D(a) normalised to D(1) = 1 (cosmo->data.growth,
+ * src/ccl_background.c:763-1002 / ccl_cosmology_growth_from_input :686-756).  Only read when a
+ * P(k) with ccl_f2d_cclgrowth is evaluated below its amin (src/ccl_f2d.c:351-370). */
+void ccl_b200_cosmology_set_growth(ccl_b200_cosmology *cosmo, int n, const double *a, const double *growth,
+                                   int *status);
+/* chi(A_SPLINE_MIN) used as chi_max of kernel-less tracers (src/ccl_tracers.c:632). */
+void ccl_b200_cosmology_set_chi_max_nokernel(ccl_b200_cosmology *cosmo, double chi);
+/* ccl_scale_factor_of_chis (src/ccl_background.c:1279-1288), evaluated on the device. */
+void ccl_b200_scale_factor_of_chis(ccl_b200_cosmology *cosmo, int n, const double *chi, double *a_out,
+                                   int *status);
+
+/* ---- ccl_f2d_t (include/ccl_f2d.h:65-89, src/ccl_f2d.c:92-201) ---- */
+/* Same argument order and NULL conventions as ccl_f2d_t_new; interp_type is always bicubic. */
+ccl_b200_f2d *ccl_b200_f2d_new(int na, const double *a_arr, int nk, const double *lk_arr,
+                               const double *fka_arr, const double *fk_arr, const double *fa_arr,
+                               int is_factorizable, int extrap_order_lok, int extrap_order_hik,
+                               int extrap_linear_growth, int is_fka_log, double growth_factor_0,
+                               int growth_exponent, int *status);
+/* set_pk2d_new_from_arrays (pyccl/ccl_pk2d.i:17-28) */
+ccl_b200_f2d *ccl_b200_pk2d_new_from_arrays(const double *lk_arr, int nk, const double *a_arr, int na,
+                                            const double *pk_arr, int order_lok, int order_hik,
+                                            int is_logp, int *status);
+void ccl_b200_f2d_free(ccl_b200_f2d *f2d);
+/* pk2d_eval_multi (pyccl/ccl_pk2d.i:55-62): out[i] = ccl_f2d_t_eval(f2d, lk[i], a, cosmo).
+ * cosmo may be NULL when no growth extrapolation is needed. */
+void ccl_b200_f2d_eval_multi(ccl_b200_f2d *f2d, const double *lk, int nk, double a, ccl_b200_cosmology *cosmo,
+                             double *out, int *status);
+
+/* ---- ccl_cl_tracer_t (include/ccl_tracers.h:46-59, src/ccl_tracers.c:569-691) ---- */
+ccl_b200_tracer *ccl_b200_cl_tracer_t_new(ccl_b200_cosmology *cosmo, int der_bessel, int der_angles,
+                                          int n_w, const double *chi_w, const double *w_w, int na_ka,
+                                          const double *a_ka, int nk_ka, const double *lk_ka,
+                                          const double *fka_arr, const double *fk_arr,
+                                          const double *fa_arr, int is_fka_log, int is_factorizable,
+                                          int extrap_order_lok, int extrap_order_hik, int *status);
+void ccl_b200_cl_tracer_t_free(ccl_b200_tracer *tr);
+double ccl_b200_cl_tracer_t_chi_min(const ccl_b200_tracer *tr);
+double ccl_b200_cl_tracer_t_chi_max(const ccl_b200_tracer *tr);
+/* ccl_cl_tracer_t_get_f_ell / _get_kernel / _get_transfer (src/ccl_tracers.c:703-749), vectorised
+ * like pyccl/ccl_tracers.i cl_tracer_get_*; kernel and transfer run on the device. */
+void ccl_b200_cl_tracer_get_f_ell(const ccl_b200_tracer *tr, int n, const double *ell, double *out,
+                                  int *status);
+void ccl_b200_cl_tracer_get_kernel(ccl_b200_tracer *tr, int n, const double *chi, double *out, int *status);
+void ccl_b200_cl_tracer_get_transfer(ccl_b200_tracer *tr, int nk, const double *lk, int na, const double *a,
+                                     double *out /* [nk*na] */, int *status);
+
+/* ---- ccl_cl_tracer_collection_t (src/ccl_tracers.c:13-50) ---- */
+ccl_b200_collection *ccl_b200_cl_tracer_collection_t_new(int *status);
+void ccl_b200_cl_tracer_collection_t_free(ccl_b200_collection *trc);
+void ccl_b200_add_cl_tracer_to_collection(ccl_b200_collection *trc, ccl_b200_tracer *tr, int *status);
+
+/* ---- the hot path ---- */
+/* ccl_angular_cls_limber (include/ccl_cls.h:20-26): same argument order and semantics.  On an
+ * integration failure cl_out[l] = NaN and *status = CCL_ERROR_INTEG (src/ccl_cls.c:343-345);
+ * without distances *status = CCL_ERROR_DISTANCES_INIT (:274-280). */
+void ccl_b200_angular_cls_limber(ccl_b200_cosmology *cosmo, ccl_b200_collection *trc1,
+                                 ccl_b200_collection *trc2, ccl_b200_f2d *psp, int nl_out,
+                                 const double *l_out, double *cl_out, int integration_method,
+                                 int *status);
+
+/* ---- batched entry: (ncosmo, npair, nl) in one launch ---- */
+/* A batch owns one HBM arena holding the table packs of ncosmo cosmologies.  Slots are filled
+ * with the same flat arrays as the single-object constructors, then committed (one H2D copy of
+ * the raw region + device kernels that build every spline coefficient table in place). */
+ccl_b200_batch *ccl_b200_batch_new(int ncosmo, const ccl_b200_params *params, int *status);
+void ccl_b200_batch_free(ccl_b200_batch *b);
+void ccl_b200_batch_set_achi(ccl_b200_batch *b, int icosmo, int n, const double *chi, const double *a,
+                             int *status);
+void ccl_b200_batch_set_growth(ccl_b200_batch *b, int icosmo, int n, const double *a, const double *growth,
+                               int *status);
+void ccl_b200_batch_set_chi_max_nokernel(ccl_b200_batch *b, int icosmo, double chi);
+void ccl_b200_batch_set_pk2d(ccl_b200_batch *b, int icosmo, const double *lk_arr, int nk,
+                             const double *a_arr, int na, const double *pk_arr, int order_lok,
+                             int order_hik, int is_logp, int *status);
+/* Returns the index of the new sub-tracer inside cosmology icosmo (-1 on failure). */
+int ccl_b200_batch_add_tracer(ccl_b200_batch *b, int icosmo, int der_bessel, int der_angles, int n_w,
+                              const double *chi_w, const double *w_w, int na_ka, const double *a_ka,
+                              int nk_ka, const double *lk_ka, const double *fka_arr, const double *fk_arr,
+                              const double *fa_arr, int is_fka_log, int is_factorizable,
+                              int extrap_order_lok, int extrap_order_hik, int *status);
+void ccl_b200_batch_tracer_chi_range(const ccl_b200_batch *b, int icosmo, int itracer, double *chi_min,
+                                     double *chi_max);
+/* Forget all slots but keep the arena (re-use for the next set of cosmologies). */
+void ccl_b200_batch_reset(ccl_b200_batch *b);
+void ccl_b200_batch_commit(ccl_b200_batch *b, int *status);
+/* Bytes uploaded by the last commit, and bytes of HBM the arena holds. */
+unsigned long long ccl_b200_batch_h2d_bytes(const ccl_b200_batch *b);
+unsigned long long ccl_b200_batch_arena_bytes(const ccl_b200_batch *b);
+
+/* Collections are [coll_start[i], coll_start[i]+coll_count[i]) ranges of sub-tracer indices,
+ * identical for every cosmology of the batch; pair p correlates collections pair1[p], pair2[p].
+ * cl_out[(icosmo*npair + p)*nl + l]; status_out[icosmo*npair + p] is 0 or CCL_ERROR_INTEG.
+ * *status is set to CCL_ERROR_INTEG if any entry failed. */
+void ccl_b200_batch_angular_cls_limber(ccl_b200_batch *b, int ncoll, const int *coll_start,
+                                       const int *coll_count, int npair, const int *pair1,
+                                       const int *pair2, int nl, const double *ell, int integration_method,
+                                       double *cl_out, int *status_out, int *status);
+/* Same, asynchronous on `stream` (a cudaStream_t, may be NULL) with DEVICE output buffers;
+ * d_status_out holds 2*ncosmo*npair ints (status, then first underlying code). */
+void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch *b, int ncoll, const int *coll_start,
+                                           const int *coll_count, int npair, const int *pair1,
+                                           const int *pair2, int nl, const double *ell,
+                                           int integration_method, double *d_cl_out, int *d_status_out,
+                                           void *stream, int *status);
+/* Number of ln k integrand nodes the 'spline' method evaluates for this problem
+ * (sum over cosmology, pair, ell of nk; src/ccl_cls.c:194-195) -- the unit of the roofline
+ * accounting.  Computed on the host from the chi ranges; qag counts come from the device. */
+unsigned long long ccl_b200_batch_spline_nodes(const ccl_b200_batch *b, int ncoll, const int *coll_start,
+                                               const int *coll_count, int npair, const int *pair1,
+                                               const int *pair2, int nl, const double *ell);
+/* Integrand evaluations of the last qag_quad launch on this batch. */
+unsigned long long ccl_b200_batch_last_qag_evals(const ccl_b200_batch *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,343 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end of the CPU oracle (oracle/limber_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  The product (ccl_b200/) never does.  See limber_oracle.c for the list of
+reference files (file:line) each function restates and for the parity-pin status.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+INTEG_QAG = 500      # include/ccl_utils.h:12-15 (ccl_integration_qag_quad)
+INTEG_SPLINE = 501   # ccl_integration_spline
+F2D_CCLGROWTH = 401  # include/ccl_f2d.h:13-18
+F2D_CONSTGROWTH = 403
+F2D_NOEXTRAPOL = 404
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    """Compile liblimber_oracle.so with the committed Makefile (gcc, OpenMP if available)."""
+    so = os.path.join(_HERE, "liblimber_oracle.so")
+    src = os.path.join(_HERE, "limber_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        r = subprocess.run(["make", "-C", _HERE, "-B"], capture_output=True, text=True)
+        if r.returncode != 0:
+            # no OpenMP runtime: scalar build
+            r = subprocess.run(["gcc", "-O2", "-fPIC", "-std=gnu99", "-ffp-contract=off", "-shared",
+                                "-o", so, src, "-lm"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("oracle build failed:\n" + r.stderr)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        vp = C.c_void_p
+        L.o_akima_new.restype = vp
+        L.o_akima_new.argtypes = [C.c_int, _dp, _dp]
+        L.o_akima_free.argtypes = [vp]
+        L.o_akima_eval_e.argtypes = [vp, C.c_double, _dp]
+        L.o_akima_integ_e.argtypes = [vp, C.c_double, C.c_double, _dp]
+        L.o_cspline_new.restype = vp
+        L.o_cspline_new.argtypes = [C.c_int, _dp, _dp]
+        L.o_cspline_free.argtypes = [vp]
+        L.o_cspline_eval_e.argtypes = [vp, C.c_double, C.c_int, _dp]
+        L.o_bicubic_new.restype = vp
+        L.o_bicubic_new.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
+        L.o_bicubic_free.argtypes = [vp]
+        L.o_bicubic_eval_e.argtypes = [vp, C.c_double, C.c_double, C.c_int, _dp]
+        L.o_cosmo_new.restype = vp
+        L.o_cosmo_new.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp, _dp, C.c_double, C.c_double,
+                                  C.c_double, C.c_double, C.c_int]
+        L.o_cosmo_free.argtypes = [vp]
+        L.o_scale_factor_of_chi.restype = C.c_double
+        L.o_scale_factor_of_chi.argtypes = [vp, C.c_double, _ip]
+        L.o_f2d_new.restype = vp
+        L.o_f2d_new.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.c_double, C.c_int, _ip]
+        L.o_f2d_free.argtypes = [vp]
+        L.o_f2d_eval.restype = C.c_double
+        L.o_f2d_eval.argtypes = [vp, C.c_double, C.c_double, vp, _ip]
+        L.o_tracer_new.restype = vp
+        L.o_tracer_new.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp,
+                                   _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _ip]
+        L.o_tracer_free.argtypes = [vp]
+        L.o_tracer_chi_min.restype = C.c_double
+        L.o_tracer_chi_min.argtypes = [vp]
+        L.o_tracer_chi_max.restype = C.c_double
+        L.o_tracer_chi_max.argtypes = [vp]
+        L.o_tracer_f_ell.restype = C.c_double
+        L.o_tracer_f_ell.argtypes = [vp, C.c_double]
+        L.o_tracer_kernel.restype = C.c_double
+        L.o_tracer_kernel.argtypes = [vp, C.c_double]
+        L.o_tracer_transfer.restype = C.c_double
+        L.o_tracer_transfer.argtypes = [vp, C.c_double, C.c_double, _ip]
+        L.o_angular_cls_limber.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), vp,
+                                           C.c_int, _dp, _dp, C.c_int, C.POINTER(C.c_long), _ip]
+        L.o_angular_cls_limber_each.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), vp,
+                                                C.c_int, _dp, _dp, C.c_int, _ip]
+        L.o_get_k_interval_pub.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp),
+                                           C.c_double, _dp, _dp]
+        L.o_limber_nk.restype = C.c_int
+        L.o_limber_nk.argtypes = [C.c_double, C.c_double, C.c_double]
+        L.o_integ_spline.argtypes = [C.c_int, _dp, _dp, C.c_double, C.c_double, _dp, _ip]
+        L.o_qag41_test.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_int, _dp, _dp, _ip]
+        L.o_num_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _arr(x):
+    if x is None:
+        return None, None
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+class Akima:
+    """GSL akima spline (interpolation/akima.c)."""
+
+    def __init__(self, x, y):
+        self._x, px = _arr(x)
+        self._y, py = _arr(y)
+        self.h = lib().o_akima_new(len(self._x), px, py)
+        if not self.h:
+            raise ValueError("akima needs >= 5 points")
+
+    def __call__(self, x):
+        out = np.empty(np.size(x))
+        v = C.c_double()
+        for i, xi in enumerate(np.atleast_1d(x)):
+            lib().o_akima_eval_e(self.h, float(xi), C.byref(v))
+            out[i] = v.value
+        return out
+
+    def integ(self, a, b):
+        v = C.c_double()
+        st = lib().o_akima_integ_e(self.h, float(a), float(b), C.byref(v))
+        return v.value, st
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().o_akima_free(self.h)
+
+
+class CSpline:
+    """GSL natural cubic spline (interpolation/cspline.c)."""
+
+    def __init__(self, x, y):
+        self._x, px = _arr(x)
+        self._y, py = _arr(y)
+        self.h = lib().o_cspline_new(len(self._x), px, py)
+
+    def __call__(self, x, which=0):
+        out = np.empty(np.size(x))
+        v = C.c_double()
+        for i, xi in enumerate(np.atleast_1d(x)):
+            lib().o_cspline_eval_e(self.h, float(xi), which, C.byref(v))
+            out[i] = v.value
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().o_cspline_free(self.h)
+
+
+class Bicubic:
+    """GSL bicubic (interp2d/bicubic.c); z[j, i] = f(x_i, y_j)."""
+
+    def __init__(self, x, y, z):
+        self._x, px = _arr(x)
+        self._y, py = _arr(y)
+        self._z, pz = _arr(np.asarray(z).ravel())
+        self.h = lib().o_bicubic_new(len(self._x), len(self._y), px, py, pz)
+
+    def __call__(self, x, y, which=0):
+        v = C.c_double()
+        st = lib().o_bicubic_eval_e(self.h, float(x), float(y), which, C.byref(v))
+        return v.value, st
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().o_bicubic_free(self.h)
+
+
+class Cosmo:
+    """a(chi) + growth splines and the spline/gsl params the path reads (SURVEY 8a a14,a15,a18)."""
+
+    def __init__(self, chi, a, a_growth=None, growth=None, K_MAX=1e3, K_MIN=5e-5, DLOGK=0.025,
+                 LIMBER_EPSREL=1e-4, N_ITERATION=1000):
+        self._chi, pchi = _arr(chi)
+        self._a, pa = _arr(a)
+        self._ag, pag = _arr(a_growth)
+        self._g, pg = _arr(growth)
+        ng = 0 if a_growth is None else len(self._ag)
+        self.h = lib().o_cosmo_new(len(self._chi), pchi, pa, ng, pag, pg, K_MAX, K_MIN, DLOGK,
+                                   LIMBER_EPSREL, N_ITERATION)
+
+    def scale_factor_of_chi(self, chi):
+        st = C.c_int(0)
+        out = np.array([lib().o_scale_factor_of_chi(self.h, float(c), C.byref(st))
+                        for c in np.atleast_1d(chi)])
+        return out, st.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().o_cosmo_free(self.h)
+
+
+class F2D:
+    """ccl_f2d_t (src/ccl_f2d.c:92-201); fka is [na, nk] row-major like the reference."""
+
+    def __init__(self, a=None, lk=None, fka=None, fk=None, fa=None, is_factorizable=False,
+                 extrap_order_lok=1, extrap_order_hik=2, extrap_linear_growth=F2D_CCLGROWTH,
+                 is_log=False, growth_factor_0=1.0, growth_exponent=0):
+        self._a, pa = _arr(a)
+        self._lk, plk = _arr(lk)
+        self._fka, pfka = _arr(None if fka is None else np.asarray(fka).ravel())
+        self._fk, pfk = _arr(fk)
+        self._fa, pfa = _arr(fa)
+        st = C.c_int(0)
+        self.h = lib().o_f2d_new(0 if a is None else len(self._a), pa,
+                                 0 if lk is None else len(self._lk), plk, pfka, pfk, pfa,
+                                 int(is_factorizable), extrap_order_lok, extrap_order_hik,
+                                 extrap_linear_growth, int(is_log), growth_factor_0,
+                                 growth_exponent, C.byref(st))
+        self.status = st.value
+
+    def __call__(self, lk, a, cosmo=None):
+        st = C.c_int(0)
+        v = lib().o_f2d_eval(self.h, float(lk), float(a), cosmo.h if cosmo else None, C.byref(st))
+        return v, st.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().o_f2d_free(self.h)
+
+
+class Tracer:
+    """One ccl_cl_tracer_t (src/ccl_tracers.c:569-691)."""
+
+    def __init__(self, der_bessel=0, der_angles=0, kernel=None, transfer_ka=None, transfer_k=None,
+                 transfer_a=None, is_logt=False, extrap_order_lok=0, extrap_order_hik=2,
+                 chi_max_nokernel=1e15):
+        chi_w = w_w = a_s = lk_s = tka = tk = ta = None
+        if kernel is not None:
+            chi_w, w_w = kernel
+        is_fact = transfer_ka is None
+        if transfer_ka is not None:
+            a_s, lk_s, tka = transfer_ka
+            tka = np.asarray(tka).ravel()
+        else:
+            if transfer_k is not None:
+                lk_s, tk = transfer_k
+            if transfer_a is not None:
+                a_s, ta = transfer_a
+        self._keep = [_arr(v) for v in (chi_w, w_w, a_s, lk_s, tka, tk, ta)]
+        p = [k[1] for k in self._keep]
+        st = C.c_int(0)
+        self.h = lib().o_tracer_new(int(der_bessel), int(der_angles),
+                                    0 if chi_w is None else len(chi_w), p[0], p[1],
+                                    0 if a_s is None else len(a_s), p[2],
+                                    0 if lk_s is None else len(lk_s), p[3], p[4], p[5], p[6],
+                                    int(is_logt), int(is_fact), extrap_order_lok, extrap_order_hik,
+                                    float(chi_max_nokernel), C.byref(st))
+        self.status = st.value
+        if not self.h:
+            raise ValueError("oracle tracer construction failed, status %d" % st.value)
+
+    @property
+    def chi_min(self):
+        return lib().o_tracer_chi_min(self.h)
+
+    @property
+    def chi_max(self):
+        return lib().o_tracer_chi_max(self.h)
+
+    def f_ell(self, ell):
+        return np.array([lib().o_tracer_f_ell(self.h, float(l)) for l in np.atleast_1d(ell)])
+
+    def kernel(self, chi):
+        return np.array([lib().o_tracer_kernel(self.h, float(c)) for c in np.atleast_1d(chi)])
+
+    def transfer(self, lk, a):
+        st = C.c_int(0)
+        return lib().o_tracer_transfer(self.h, float(lk), float(a), C.byref(st)), st.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().o_tracer_free(self.h)
+
+
+def _coll(trs):
+    arr = (C.c_void_p * len(trs))(*[t.h for t in trs])
+    return arr
+
+
+def angular_cl(cosmo, trc1, trc2, psp, ells, method=INTEG_SPLINE, each=False, return_neval=False):
+    """ccl_angular_cls_limber (src/ccl_cls.c:265-363) for one pair of tracer collections.
+
+    trc1/trc2 are lists of oracle Tracer objects (one pyccl Tracer = one collection).
+    Returns (cl, status); with each=True status is a per-ell array and every ell is evaluated
+    independently.
+    """
+    L = lib()
+    ells = np.ascontiguousarray(ells, dtype=np.float64)
+    cl = np.full(ells.size, np.nan)
+    c1, c2 = _coll(trc1), _coll(trc2)
+    if each:
+        st = np.zeros(ells.size, dtype=np.int32)
+        L.o_angular_cls_limber_each(cosmo.h, len(trc1), c1, len(trc2), c2, psp.h, ells.size,
+                                    ells.ctypes.data_as(_dp), cl.ctypes.data_as(_dp), method,
+                                    st.ctypes.data_as(_ip))
+        return cl, st
+    st = C.c_int(0)
+    nev = np.zeros(ells.size, dtype=np.int64)
+    L.o_angular_cls_limber(cosmo.h, len(trc1), c1, len(trc2), c2, psp.h, ells.size,
+                           ells.ctypes.data_as(_dp), cl.ctypes.data_as(_dp), method,
+                           nev.ctypes.data_as(C.POINTER(C.c_long)), C.byref(st))
+    if return_neval:
+        return cl, st.value, nev
+    return cl, st.value
+
+
+def k_interval(cosmo, trc1, trc2, ell):
+    lo, hi = C.c_double(), C.c_double()
+    lib().o_get_k_interval_pub(cosmo.h, len(trc1), _coll(trc1), len(trc2), _coll(trc2), float(ell),
+                               C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def limber_nk(lkmin, lkmax, dlogk=0.025):
+    return lib().o_limber_nk(lkmin, lkmax, dlogk)
+
+
+def integ_spline(x, y):
+    x, px = _arr(x)
+    y, py = _arr(y)
+    r = C.c_double()
+    st = C.c_int(0)
+    lib().o_integ_spline(len(x), px, py, 1.0, -1.0, C.byref(r), C.byref(st))
+    return r.value, st.value
+
+
+def qag41_test(kind, p, a, b, epsabs=0.0, epsrel=1e-4, limit=1000):
+    r, e = C.c_double(), C.c_double()
+    n = C.c_int()
+    st = lib().o_qag41_test(kind, p, a, b, epsabs, epsrel, limit, C.byref(r), C.byref(e), C.byref(n))
+    return r.value, e.value, n.value, st
+
+
+def num_threads():
+    return lib().o_num_threads()

@@ -1,0 +1,1261 @@
+/*
+ * oracle/limber_oracle.c -- TEST INFRASTRUCTURE ONLY. NOT PART OF THE PRODUCT.
+ *
+ * CPU restatement (kind: "port") of the reference's Limber angular-power-spectrum path,
+ * used only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs as the checker.  The product (ccl_b200/) never links, imports or
+ * executes anything in this directory.
+ *
+ * PARITY STATUS: the reference's arithmetic for this path lives in GSL (>= 2.1, fallback
+ * tarball 2.4: /root/reference/CMakeLists.txt:118, cmake/Modules/BuildGSL.cmake:3), which is
+ * not vendored under /root/reference and is not installed in the build container, so the
+ * reference itself is unbuildable here.  The GSL algorithms (interpolation/akima.c,
+ * cspline.c, linalg/tridiag.c, interpolation/bsearch.h, integ_eval.h, interp2d/bicubic.c,
+ * integration/qag.c, qk.c, qk41.c, qpsrt.c, util.c) are restated from their published
+ * sources.  Pins: scipy Akima1DInterpolator / CubicSpline(natural) (tests/test_oracle.py),
+ * the reference's 23 golden C_ell benchmark curves (benchmarks/data/run_*_log_cl_*.txt via
+ * tests/golden/), the closed-form power-law C_ell of benchmarks/test_tracers.py:6-18.
+ * No reference fixture pins this path at 1e-10 ("parity unpinned" at that level; see
+ * DESIGN.md).
+ *
+ * Reference files followed (all under /root/reference):
+ *   src/ccl_cls.c:64-363        get_k_interval, transfer_limber_*, cl_integrand,
+ *                               integ_cls_limber_spline / _qag_quad, ccl_angular_cls_limber
+ *   src/ccl_tracers.c:569-749   ccl_cl_tracer_t_new (chi range rule), get_f_ell/kernel/transfer
+ *   src/ccl_f1d.c:15-191        ccl_f1d_t_new / eval (constant extrapolation branch)
+ *   src/ccl_f2d.c:92-373        ccl_f2d_t_new / eval
+ *   src/ccl_utils.c:17-37       ccl_linear_spacing
+ *   src/ccl_utils.c:274-345     ccl_integ_spline
+ *   src/ccl_background.c:1251-1325  ccl_scale_factor_of_chi, ccl_growth_factor
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "gk41_table.h"
+
+#define O_SUCCESS 0
+#define O_GSL_EDOM 1
+#define O_GSL_EINVAL 4
+#define O_GSL_EFAILED 5
+#define O_GSL_EMAXITER 11
+#define O_GSL_EBADTOL 13
+#define O_GSL_EROUND 18
+#define O_GSL_ESING 21
+#define O_ERR_MEMORY 1025
+#define O_ERR_INCONSISTENT 1027
+#define O_ERR_SPLINE 1028
+#define O_ERR_SPLINE_EV 1029
+#define O_ERR_INTEG 1030
+#define O_ERR_COMPUTECHI 1033
+#define O_ERR_NOT_IMPLEMENTED 1040
+#define O_ERR_GROWTH_INIT 1058
+#define O_ERR_DISTANCES_INIT 1059
+/* oracle-only: GSL_EROUND in QAG would make the reference retry with CQUAD
+ * (src/ccl_cls.c:245-259); CQUAD is not restated, the case is flagged instead. */
+#define O_ERR_CQUAD_NEEDED 9001
+
+#define O_F2D_CCLGROWTH 401
+#define O_F2D_CONSTGROWTH 403
+#define O_F2D_NOEXTRAPOL 404
+#define O_INTEG_QAG 500
+#define O_INTEG_SPLINE 501
+
+/* ------------------------------------------------------------------ */
+/* GSL interpolation/bsearch.h: gsl_interp_bsearch                     */
+/* ------------------------------------------------------------------ */
+static size_t o_bsearch(const double *xa, double x, size_t ilo, size_t ihi) {
+  while (ihi > ilo + 1) {
+    size_t i = (ihi + ilo) / 2;
+    if (xa[i] > x) ihi = i; else ilo = i;
+  }
+  return ilo;
+}
+
+/* ------------------------------------------------------------------ */
+/* GSL interpolation/akima.c (non-periodic)                            */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int n;
+  double *x, *y, *b, *c, *d;
+} o_akima;
+
+void o_akima_free(o_akima *s) {
+  if (!s) return;
+  free(s->x); free(s->y); free(s->b); free(s->c); free(s->d); free(s);
+}
+
+/* gsl_spline_alloc(gsl_interp_akima, n) returns NULL for n < 5 (min_size) */
+o_akima *o_akima_new(int n, const double *x, const double *y) {
+  if (n < 5) return NULL;
+  o_akima *s = calloc(1, sizeof(o_akima));
+  s->n = n;
+  s->x = malloc(sizeof(double) * n);
+  s->y = malloc(sizeof(double) * n);
+  s->b = malloc(sizeof(double) * n);
+  s->c = malloc(sizeof(double) * n);
+  s->d = malloc(sizeof(double) * n);
+  memcpy(s->x, x, sizeof(double) * n);
+  memcpy(s->y, y, sizeof(double) * n);
+  double *mm = malloc(sizeof(double) * (n + 4));
+  double *m = mm + 2;
+  for (int i = 0; i <= n - 2; i++)
+    m[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+  m[-2] = 3.0 * m[0] - 2.0 * m[1];
+  m[-1] = 2.0 * m[0] - m[1];
+  m[n - 1] = 2.0 * m[n - 2] - m[n - 3];
+  m[n] = 3.0 * m[n - 2] - 2.0 * m[n - 3];
+  for (int i = 0; i < n - 1; i++) {
+    const double NE = fabs(m[i + 1] - m[i]) + fabs(m[i - 1] - m[i - 2]);
+    if (NE == 0.0) {
+      s->b[i] = m[i]; s->c[i] = 0.0; s->d[i] = 0.0;
+    } else {
+      const double h_i = x[i + 1] - x[i];
+      const double NE_next = fabs(m[i + 2] - m[i + 1]) + fabs(m[i] - m[i - 1]);
+      const double alpha_i = fabs(m[i - 1] - m[i - 2]) / NE;
+      double alpha_ip1, tL_ip1;
+      if (NE_next == 0.0) {
+        tL_ip1 = m[i];
+      } else {
+        alpha_ip1 = fabs(m[i] - m[i - 1]) / NE_next;
+        tL_ip1 = (1.0 - alpha_ip1) * m[i] + alpha_ip1 * m[i + 1];
+      }
+      s->b[i] = (1.0 - alpha_i) * m[i - 1] + alpha_i * m[i];
+      s->c[i] = (3.0 * m[i] - 2.0 * s->b[i] - tL_ip1) / h_i;
+      s->d[i] = (s->b[i] + tL_ip1 - 2.0 * m[i]) / (h_i * h_i);
+    }
+  }
+  free(mm);
+  return s;
+}
+
+/* gsl_spline_eval_e: EDOM + NaN outside [xmin, xmax] */
+int o_akima_eval_e(const o_akima *s, double x, double *y) {
+  if (x < s->x[0] || x > s->x[s->n - 1]) { *y = NAN; return O_GSL_EDOM; }
+  size_t i = o_bsearch(s->x, x, 0, s->n - 1);
+  const double delx = x - s->x[i];
+  *y = s->y[i] + delx * (s->b[i] + delx * (s->c[i] + s->d[i] * delx));
+  return O_SUCCESS;
+}
+
+/* GSL interpolation/integ_eval.h */
+static double o_integ_eval(double ai, double bi, double ci, double di, double xi,
+                           double a, double b) {
+  const double r1 = a - xi;
+  const double r2 = b - xi;
+  const double r12 = r1 + r2;
+  const double bterm = 0.5 * bi * r12;
+  const double cterm = (1.0 / 3.0) * ci * (r1 * r1 + r2 * r2 + r1 * r2);
+  const double dterm = 0.25 * di * r12 * (r1 * r1 + r2 * r2);
+  return (b - a) * (ai + bterm + cterm + dterm);
+}
+
+/* akima_eval_integ behind gsl_spline_eval_integ_e */
+int o_akima_integ_e(const o_akima *s, double a, double b, double *result) {
+  if (a > b || a < s->x[0] || b > s->x[s->n - 1]) { *result = NAN; return O_GSL_EDOM; }
+  if (a == b) { *result = 0.0; return O_SUCCESS; }
+  size_t index_a = o_bsearch(s->x, a, 0, s->n - 1);
+  size_t index_b = o_bsearch(s->x, b, 0, s->n - 1);
+  double res = 0.0;
+  for (size_t i = index_a; i <= index_b; i++) {
+    const double x_hi = s->x[i + 1];
+    const double x_lo = s->x[i];
+    const double y_lo = s->y[i];
+    const double dx = x_hi - x_lo;
+    if (dx != 0.0) {
+      if (i == index_a || i == index_b) {
+        double x1 = (i == index_a) ? a : x_lo;
+        double x2 = (i == index_b) ? b : x_hi;
+        res += o_integ_eval(y_lo, s->b[i], s->c[i], s->d[i], x_lo, x1, x2);
+      } else {
+        res += dx * (y_lo + dx * (0.5 * s->b[i] + dx * (s->c[i] / 3.0 + 0.25 * s->d[i] * dx)));
+      }
+    } else {
+      *result = 0.0;
+      return O_GSL_EINVAL;
+    }
+  }
+  *result = res;
+  return O_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ */
+/* GSL interpolation/cspline.c (natural) + linalg/tridiag.c            */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int n;
+  double *x, *y, *c;
+} o_cspline;
+
+void o_cspline_free(o_cspline *s) {
+  if (!s) return;
+  free(s->x); free(s->y); free(s->c); free(s);
+}
+
+static void o_solve_symm_tridiag(const double *diag, const double *offdiag,
+                                 const double *b, double *x, size_t N) {
+  double *gamma = malloc(N * sizeof(double));
+  double *alpha = malloc(N * sizeof(double));
+  double *c = malloc(N * sizeof(double));
+  double *z = malloc(N * sizeof(double));
+  size_t i, j;
+  alpha[0] = diag[0];
+  gamma[0] = offdiag[0] / alpha[0];
+  for (i = 1; i < N - 1; i++) {
+    alpha[i] = diag[i] - offdiag[i - 1] * gamma[i - 1];
+    gamma[i] = offdiag[i] / alpha[i];
+  }
+  if (N > 1) alpha[N - 1] = diag[N - 1] - offdiag[N - 2] * gamma[N - 2];
+  z[0] = b[0];
+  for (i = 1; i < N; i++) z[i] = b[i] - gamma[i - 1] * z[i - 1];
+  for (i = 0; i < N; i++) c[i] = z[i] / alpha[i];
+  x[N - 1] = c[N - 1];
+  if (N >= 2) {
+    for (i = N - 2, j = 0; j <= N - 2; j++, i--) x[i] = c[i] - gamma[i] * x[i + 1];
+  }
+  free(gamma); free(alpha); free(c); free(z);
+}
+
+/* gsl_interp_cspline min_size is 3 */
+o_cspline *o_cspline_new(int n, const double *xa, const double *ya) {
+  if (n < 3) return NULL;
+  o_cspline *s = calloc(1, sizeof(o_cspline));
+  s->n = n;
+  s->x = malloc(sizeof(double) * n);
+  s->y = malloc(sizeof(double) * n);
+  s->c = malloc(sizeof(double) * n);
+  memcpy(s->x, xa, sizeof(double) * n);
+  memcpy(s->y, ya, sizeof(double) * n);
+  size_t max_index = n - 1;
+  size_t sys_size = max_index - 1;
+  double *g = malloc(sizeof(double) * n);
+  double *diag = malloc(sizeof(double) * n);
+  double *offdiag = malloc(sizeof(double) * n);
+  s->c[0] = 0.0;
+  s->c[max_index] = 0.0;
+  for (size_t i = 0; i < sys_size; i++) {
+    const double h_i = xa[i + 1] - xa[i];
+    const double h_ip1 = xa[i + 2] - xa[i + 1];
+    const double ydiff_i = ya[i + 1] - ya[i];
+    const double ydiff_ip1 = ya[i + 2] - ya[i + 1];
+    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0;
+    const double g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    offdiag[i] = h_ip1;
+    diag[i] = 2.0 * (h_ip1 + h_i);
+    g[i] = 3.0 * (ydiff_ip1 * g_ip1 - ydiff_i * g_i);
+  }
+  if (sys_size == 1) {
+    s->c[1] = g[0] / diag[0];
+  } else {
+    o_solve_symm_tridiag(diag, offdiag, g, s->c + 1, sys_size);
+  }
+  free(g); free(diag); free(offdiag);
+  return s;
+}
+
+static void o_cs_coeff(const double *c_array, double dy, double dx, size_t index,
+                       double *b, double *c, double *d) {
+  const double c_i = c_array[index];
+  const double c_ip1 = c_array[index + 1];
+  *b = (dy / dx) - dx * (c_ip1 + 2.0 * c_i) / 3.0;
+  *c = c_i;
+  *d = (c_ip1 - c_i) / (3.0 * dx);
+}
+
+/* which: 0 value, 1 first derivative, 2 second derivative */
+int o_cspline_eval_e(const o_cspline *s, double x, int which, double *out) {
+  if (x < s->x[0] || x > s->x[s->n - 1]) { *out = NAN; return O_GSL_EDOM; }
+  size_t i = o_bsearch(s->x, x, 0, s->n - 1);
+  const double x_hi = s->x[i + 1], x_lo = s->x[i];
+  const double dx = x_hi - x_lo;
+  if (dx > 0.0) {
+    const double y_lo = s->y[i], y_hi = s->y[i + 1];
+    const double dy = y_hi - y_lo;
+    double delx = x - x_lo;
+    double b_i, c_i, d_i;
+    o_cs_coeff(s->c, dy, dx, i, &b_i, &c_i, &d_i);
+    if (which == 0) *out = y_lo + delx * (b_i + delx * (c_i + delx * d_i));
+    else if (which == 1) *out = b_i + delx * (2.0 * c_i + 3.0 * d_i * delx);
+    else *out = 2.0 * c_i + 6.0 * d_i * delx;
+    return O_SUCCESS;
+  }
+  *out = 0.0;
+  return O_GSL_EINVAL;
+}
+
+/* ------------------------------------------------------------------ */
+/* GSL interp2d/bicubic.c                                              */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int nx, ny;
+  double *x, *y, *z, *zx, *zy, *zxy;
+} o_bicubic;
+
+void o_bicubic_free(o_bicubic *s) {
+  if (!s) return;
+  free(s->x); free(s->y); free(s->z); free(s->zx); free(s->zy); free(s->zxy); free(s);
+}
+
+#define IDX2D(i, j, nx) ((j) * (nx) + (i))
+
+/* z[j*nx + i] = f(x_i, y_j) (gsl_spline2d layout; CCL passes x=ln k, y=a, src/ccl_f2d.c:194) */
+o_bicubic *o_bicubic_new(int nx, int ny, const double *xa, const double *ya, const double *za) {
+  if (nx < 4 || ny < 4) return NULL; /* gsl_interp2d_bicubic min_size 4 */
+  o_bicubic *s = calloc(1, sizeof(o_bicubic));
+  s->nx = nx; s->ny = ny;
+  s->x = malloc(sizeof(double) * nx);
+  s->y = malloc(sizeof(double) * ny);
+  size_t nn = (size_t)nx * ny;
+  s->z = malloc(sizeof(double) * nn);
+  s->zx = malloc(sizeof(double) * nn);
+  s->zy = malloc(sizeof(double) * nn);
+  s->zxy = malloc(sizeof(double) * nn);
+  memcpy(s->x, xa, sizeof(double) * nx);
+  memcpy(s->y, ya, sizeof(double) * ny);
+  memcpy(s->z, za, sizeof(double) * nn);
+  double *tx = malloc(sizeof(double) * (nx > ny ? nx : ny));
+  /* zx: natural cspline along x for every y row, first derivative at the nodes */
+  for (int j = 0; j < ny; j++) {
+    for (int i = 0; i < nx; i++) tx[i] = za[IDX2D(i, j, nx)];
+    o_cspline *sp = o_cspline_new(nx, xa, tx);
+    for (int i = 0; i < nx; i++) o_cspline_eval_e(sp, xa[i], 1, &s->zx[IDX2D(i, j, nx)]);
+    o_cspline_free(sp);
+  }
+  /* zy: along y for every x column */
+  for (int i = 0; i < nx; i++) {
+    for (int j = 0; j < ny; j++) tx[j] = za[IDX2D(i, j, nx)];
+    o_cspline *sp = o_cspline_new(ny, ya, tx);
+    for (int j = 0; j < ny; j++) o_cspline_eval_e(sp, ya[j], 1, &s->zy[IDX2D(i, j, nx)]);
+    o_cspline_free(sp);
+  }
+  /* zxy: x-derivative of the zy plane (spline along x of zy for every y row) */
+  for (int j = 0; j < ny; j++) {
+    for (int i = 0; i < nx; i++) tx[i] = s->zy[IDX2D(i, j, nx)];
+    o_cspline *sp = o_cspline_new(nx, xa, tx);
+    for (int i = 0; i < nx; i++) o_cspline_eval_e(sp, xa[i], 1, &s->zxy[IDX2D(i, j, nx)]);
+    o_cspline_free(sp);
+  }
+  free(tx);
+  return s;
+}
+
+/* which: 0 value, 1 d/dx, 2 d2/dx2 */
+int o_bicubic_eval_e(const o_bicubic *s, double x, double y, int which, double *out) {
+  if (x < s->x[0] || x > s->x[s->nx - 1] || y < s->y[0] || y > s->y[s->ny - 1]) {
+    *out = NAN;
+    return O_GSL_EDOM;
+  }
+  const int nx = s->nx;
+  size_t xi = o_bsearch(s->x, x, 0, s->nx - 1);
+  size_t yi = o_bsearch(s->y, y, 0, s->ny - 1);
+  const double xmin = s->x[xi], xmax = s->x[xi + 1];
+  const double ymin = s->y[yi], ymax = s->y[yi + 1];
+  const double zminmin = s->z[IDX2D(xi, yi, nx)];
+  const double zminmax = s->z[IDX2D(xi, yi + 1, nx)];
+  const double zmaxmin = s->z[IDX2D(xi + 1, yi, nx)];
+  const double zmaxmax = s->z[IDX2D(xi + 1, yi + 1, nx)];
+  const double dx = xmax - xmin, dy = ymax - ymin;
+  const double t = (x - xmin) / dx, u = (y - ymin) / dy;
+  const double dt = 1. / dx, du = 1. / dy;
+  const double zxminmin = s->zx[IDX2D(xi, yi, nx)] / dt;
+  const double zxminmax = s->zx[IDX2D(xi, yi + 1, nx)] / dt;
+  const double zxmaxmin = s->zx[IDX2D(xi + 1, yi, nx)] / dt;
+  const double zxmaxmax = s->zx[IDX2D(xi + 1, yi + 1, nx)] / dt;
+  const double zyminmin = s->zy[IDX2D(xi, yi, nx)] / du;
+  const double zyminmax = s->zy[IDX2D(xi, yi + 1, nx)] / du;
+  const double zymaxmin = s->zy[IDX2D(xi + 1, yi, nx)] / du;
+  const double zymaxmax = s->zy[IDX2D(xi + 1, yi + 1, nx)] / du;
+  const double zxyminmin = s->zxy[IDX2D(xi, yi, nx)] / (dt * du);
+  const double zxyminmax = s->zxy[IDX2D(xi, yi + 1, nx)] / (dt * du);
+  const double zxymaxmin = s->zxy[IDX2D(xi + 1, yi, nx)] / (dt * du);
+  const double zxymaxmax = s->zxy[IDX2D(xi + 1, yi + 1, nx)] / (dt * du);
+  const double t0 = 1, t1 = t, t2 = t * t, t3 = t * t2;
+  const double u0 = 1, u1 = u, u2 = u * u, u3 = u * u2;
+  double v, z = 0;
+  if (which == 0) {
+    v = zminmin; z += v * t0 * u0;
+    v = zyminmin; z += v * t0 * u1;
+    v = -3 * zminmin + 3 * zminmax - 2 * zyminmin - zyminmax; z += v * t0 * u2;
+    v = 2 * zminmin - 2 * zminmax + zyminmin + zyminmax; z += v * t0 * u3;
+    v = zxminmin; z += v * t1 * u0;
+    v = zxyminmin; z += v * t1 * u1;
+    v = -3 * zxminmin + 3 * zxminmax - 2 * zxyminmin - zxyminmax; z += v * t1 * u2;
+    v = 2 * zxminmin - 2 * zxminmax + zxyminmin + zxyminmax; z += v * t1 * u3;
+    v = -3 * zminmin + 3 * zmaxmin - 2 * zxminmin - zxmaxmin; z += v * t2 * u0;
+    v = -3 * zyminmin + 3 * zymaxmin - 2 * zxyminmin - zxymaxmin; z += v * t2 * u1;
+    v = 9 * zminmin - 9 * zmaxmin + 9 * zmaxmax - 9 * zminmax + 6 * zxminmin + 3 * zxmaxmin
+        - 3 * zxmaxmax - 6 * zxminmax + 6 * zyminmin - 6 * zymaxmin - 3 * zymaxmax
+        + 3 * zyminmax + 4 * zxyminmin + 2 * zxymaxmin + zxymaxmax + 2 * zxyminmax;
+    z += v * t2 * u2;
+    v = -6 * zminmin + 6 * zmaxmin - 6 * zmaxmax + 6 * zminmax - 4 * zxminmin - 2 * zxmaxmin
+        + 2 * zxmaxmax + 4 * zxminmax - 3 * zyminmin + 3 * zymaxmin + 3 * zymaxmax
+        - 3 * zyminmax - 2 * zxyminmin - zxymaxmin - zxymaxmax - 2 * zxyminmax;
+    z += v * t2 * u3;
+    v = 2 * zminmin - 2 * zmaxmin + zxminmin + zxmaxmin; z += v * t3 * u0;
+    v = 2 * zyminmin - 2 * zymaxmin + zxyminmin + zxymaxmin; z += v * t3 * u1;
+    v = -6 * zminmin + 6 * zmaxmin - 6 * zmaxmax + 6 * zminmax - 3 * zxminmin - 3 * zxmaxmin
+        + 3 * zxmaxmax + 3 * zxminmax - 4 * zyminmin + 4 * zymaxmin + 2 * zymaxmax
+        - 2 * zyminmax - 2 * zxyminmin - 2 * zxymaxmin - zxymaxmax - zxyminmax;
+    z += v * t3 * u2;
+    v = 4 * zminmin - 4 * zmaxmin + 4 * zmaxmax - 4 * zminmax + 2 * zxminmin + 2 * zxmaxmin
+        - 2 * zxmaxmax - 2 * zxminmax + 2 * zyminmin - 2 * zymaxmin - 2 * zymaxmax
+        + 2 * zyminmax + zxyminmin + zxymaxmin + zxymaxmax + zxyminmax;
+    z += v * t3 * u3;
+    *out = z;
+  } else if (which == 1) {
+    /* bicubic_deriv_x: d/dt of the same polynomial, times dt */
+    v = zxminmin; z += v * t0 * u0;
+    v = zxyminmin; z += v * t0 * u1;
+    v = -3 * zxminmin + 3 * zxminmax - 2 * zxyminmin - zxyminmax; z += v * t0 * u2;
+    v = 2 * zxminmin - 2 * zxminmax + zxyminmin + zxyminmax; z += v * t0 * u3;
+    v = -3 * zminmin + 3 * zmaxmin - 2 * zxminmin - zxmaxmin; z += 2 * v * t1 * u0;
+    v = -3 * zyminmin + 3 * zymaxmin - 2 * zxyminmin - zxymaxmin; z += 2 * v * t1 * u1;
+    v = 9 * zminmin - 9 * zmaxmin + 9 * zmaxmax - 9 * zminmax + 6 * zxminmin + 3 * zxmaxmin
+        - 3 * zxmaxmax - 6 * zxminmax + 6 * zyminmin - 6 * zymaxmin - 3 * zymaxmax
+        + 3 * zyminmax + 4 * zxyminmin + 2 * zxymaxmin + zxymaxmax + 2 * zxyminmax;
+    z += 2 * v * t1 * u2;
+    v = -6 * zminmin + 6 * zmaxmin - 6 * zmaxmax + 6 * zminmax - 4 * zxminmin - 2 * zxmaxmin
+        + 2 * zxmaxmax + 4 * zxminmax - 3 * zyminmin + 3 * zymaxmin + 3 * zymaxmax
+        - 3 * zyminmax - 2 * zxyminmin - zxymaxmin - zxymaxmax - 2 * zxyminmax;
+    z += 2 * v * t1 * u3;
+    v = 2 * zminmin - 2 * zmaxmin + zxminmin + zxmaxmin; z += 3 * v * t2 * u0;
+    v = 2 * zyminmin - 2 * zymaxmin + zxyminmin + zxymaxmin; z += 3 * v * t2 * u1;
+    v = -6 * zminmin + 6 * zmaxmin - 6 * zmaxmax + 6 * zminmax - 3 * zxminmin - 3 * zxmaxmin
+        + 3 * zxmaxmax + 3 * zxminmax - 4 * zyminmin + 4 * zymaxmin + 2 * zymaxmax
+        - 2 * zyminmax - 2 * zxyminmin - 2 * zxymaxmin - zxymaxmax - zxyminmax;
+    z += 3 * v * t2 * u2;
+    v = 4 * zminmin - 4 * zmaxmin + 4 * zmaxmax - 4 * zminmax + 2 * zxminmin + 2 * zxmaxmin
+        - 2 * zxmaxmax - 2 * zxminmax + 2 * zyminmin - 2 * zymaxmin - 2 * zymaxmax
+        + 2 * zyminmax + zxyminmin + zxymaxmin + zxymaxmax + zxyminmax;
+    z += 3 * v * t2 * u3;
+    *out = z * dt;
+  } else {
+    /* bicubic_deriv_xx */
+    v = -3 * zminmin + 3 * zmaxmin - 2 * zxminmin - zxmaxmin; z += 2 * v * t0 * u0;
+    v = -3 * zyminmin + 3 * zymaxmin - 2 * zxyminmin - zxymaxmin; z += 2 * v * t0 * u1;
+    v = 9 * zminmin - 9 * zmaxmin + 9 * zmaxmax - 9 * zminmax + 6 * zxminmin + 3 * zxmaxmin
+        - 3 * zxmaxmax - 6 * zxminmax + 6 * zyminmin - 6 * zymaxmin - 3 * zymaxmax
+        + 3 * zyminmax + 4 * zxyminmin + 2 * zxymaxmin + zxymaxmax + 2 * zxyminmax;
+    z += 2 * v * t0 * u2;
+    v = -6 * zminmin + 6 * zmaxmin - 6 * zmaxmax + 6 * zminmax - 4 * zxminmin - 2 * zxmaxmin
+        + 2 * zxmaxmax + 4 * zxminmax - 3 * zyminmin + 3 * zymaxmin + 3 * zymaxmax
+        - 3 * zyminmax - 2 * zxyminmin - zxymaxmin - zxymaxmax - 2 * zxyminmax;
+    z += 2 * v * t0 * u3;
+    v = 2 * zminmin - 2 * zmaxmin + zxminmin + zxmaxmin; z += 6 * v * t1 * u0;
+    v = 2 * zyminmin - 2 * zymaxmin + zxyminmin + zxymaxmin; z += 6 * v * t1 * u1;
+    v = -6 * zminmin + 6 * zmaxmin - 6 * zmaxmax + 6 * zminmax - 3 * zxminmin - 3 * zxmaxmin
+        + 3 * zxmaxmax + 3 * zxminmax - 4 * zyminmin + 4 * zymaxmin + 2 * zymaxmax
+        - 2 * zyminmax - 2 * zxyminmin - 2 * zxymaxmin - zxymaxmax - zxyminmax;
+    z += 6 * v * t1 * u2;
+    v = 4 * zminmin - 4 * zmaxmin + 4 * zmaxmax - 4 * zminmax + 2 * zxminmin + 2 * zxmaxmin
+        - 2 * zxmaxmax - 2 * zxminmax + 2 * zyminmin - 2 * zymaxmin - 2 * zymaxmax
+        + 2 * zyminmax + zxyminmin + zxymaxmin + zxymaxmax + zxyminmax;
+    z += 6 * v * t1 * u3;
+    *out = z * dt * dt;
+  }
+  return O_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ */
+/* ccl_f1d_t (src/ccl_f1d.c), constant extrapolation only              */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  o_akima *spl;
+  double y0, yf, x_ini, x_end;
+} o_f1d;
+
+void o_f1d_free(o_f1d *f) {
+  if (!f) return;
+  o_akima_free(f->spl);
+  free(f);
+}
+
+o_f1d *o_f1d_new(int n, const double *x, const double *y, double y0, double yf) {
+  o_akima *s = o_akima_new(n, x, y);
+  if (!s) return NULL;
+  o_f1d *f = calloc(1, sizeof(o_f1d));
+  f->spl = s; f->y0 = y0; f->yf = yf; f->x_ini = x[0]; f->x_end = x[n - 1];
+  return f;
+}
+
+/* src/ccl_f1d.c:118-191: the end nodes themselves take the extrapolation value */
+double o_f1d_eval(const o_f1d *f, double x) {
+  if (x <= f->x_ini) return f->y0;
+  else if (x >= f->x_end) return f->yf;
+  double y;
+  if (o_akima_eval_e(f->spl, x, &y) != O_SUCCESS) return NAN;
+  return y;
+}
+
+/* ------------------------------------------------------------------ */
+/* cosmology subset: a(chi) and growth splines                         */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  o_akima *achi;    /* x = chi increasing, y = a */
+  o_akima *growth;  /* x = a, y = D(a) normalised to D(1)=1; may be NULL */
+  double K_MAX, K_MIN, DLOGK_INTEGRATION;
+  double LIMBER_EPSREL;
+  int N_ITERATION;
+} o_cosmo;
+
+o_cosmo *o_cosmo_new(int n_achi, const double *chi, const double *a,
+                     int n_growth, const double *a_g, const double *d_g,
+                     double k_max, double k_min, double dlogk, double epsrel, int n_iter) {
+  o_cosmo *c = calloc(1, sizeof(o_cosmo));
+  c->achi = (n_achi > 0) ? o_akima_new(n_achi, chi, a) : NULL;
+  c->growth = (n_growth > 0) ? o_akima_new(n_growth, a_g, d_g) : NULL;
+  c->K_MAX = k_max; c->K_MIN = k_min; c->DLOGK_INTEGRATION = dlogk;
+  c->LIMBER_EPSREL = epsrel; c->N_ITERATION = n_iter;
+  return c;
+}
+
+void o_cosmo_free(o_cosmo *c) {
+  if (!c) return;
+  o_akima_free(c->achi); o_akima_free(c->growth); free(c);
+}
+
+/* src/ccl_background.c:1251-1277 */
+double o_scale_factor_of_chi(const o_cosmo *c, double chi, int *status) {
+  if ((chi < 1.e-8) && (chi >= 0.)) return 1.;
+  else if (chi < 0.) { *status = O_ERR_COMPUTECHI; return NAN; }
+  if (!c->achi) { *status = O_ERR_DISTANCES_INIT; return NAN; }
+  double a;
+  int st = o_akima_eval_e(c->achi, chi, &a);
+  if (st != O_SUCCESS) *status |= st;
+  return a;
+}
+
+/* src/ccl_background.c:1290-1325 */
+double o_growth_factor(const o_cosmo *c, double a, int *status) {
+  if (a == 1.) return 1.;
+  else if (a > 1.) { *status = O_ERR_COMPUTECHI; return NAN; }
+  if (!c->growth) { *status = O_ERR_GROWTH_INIT; return NAN; }
+  double D;
+  int st = o_akima_eval_e(c->growth, a, &D);
+  if (st != O_SUCCESS) { *status |= st; return NAN; }
+  return D;
+}
+
+/* ------------------------------------------------------------------ */
+/* ccl_f2d_t (src/ccl_f2d.c:92-373)                                    */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  double lkmin, lkmax, amin, amax;
+  int is_factorizable, is_k_constant, is_a_constant;
+  int extrap_order_lok, extrap_order_hik, extrap_linear_growth, is_log;
+  double growth_factor_0;
+  int growth_exponent;
+  o_cspline *fk, *fa;
+  o_bicubic *fka;
+} o_f2d;
+
+void o_f2d_free(o_f2d *f) {
+  if (!f) return;
+  o_cspline_free(f->fk); o_cspline_free(f->fa); o_bicubic_free(f->fka); free(f);
+}
+
+/* NULL array pointers mean "absent" exactly as in ccl_f2d_t_new */
+o_f2d *o_f2d_new(int na, const double *a_arr, int nk, const double *lk_arr,
+                 const double *fka_arr, const double *fk_arr, const double *fa_arr,
+                 int is_factorizable, int extrap_order_lok, int extrap_order_hik,
+                 int extrap_linear_growth, int is_fka_log, double growth_factor_0,
+                 int growth_exponent, int *status) {
+  o_f2d *f = calloc(1, sizeof(o_f2d));
+  is_factorizable = is_factorizable || (a_arr == NULL) || (lk_arr == NULL) || (fka_arr == NULL);
+  f->is_factorizable = is_factorizable;
+  f->is_k_constant = ((lk_arr == NULL) || ((fka_arr == NULL) && (fk_arr == NULL)));
+  f->is_a_constant = ((a_arr == NULL) || ((fka_arr == NULL) && (fa_arr == NULL)));
+  f->extrap_order_lok = extrap_order_lok;
+  f->extrap_order_hik = extrap_order_hik;
+  f->extrap_linear_growth = extrap_linear_growth;
+  f->is_log = is_fka_log;
+  f->growth_factor_0 = growth_factor_0;
+  f->growth_exponent = growth_exponent;
+  if (!f->is_k_constant) { f->lkmin = lk_arr[0]; f->lkmax = lk_arr[nk - 1]; }
+  if (!f->is_a_constant) { f->amin = a_arr[0]; f->amax = a_arr[na - 1]; }
+  if ((extrap_order_lok > 2) || (extrap_order_lok < 0) || (extrap_order_hik > 2) ||
+      (extrap_order_hik < 0))
+    *status = O_ERR_INCONSISTENT;
+  if ((extrap_linear_growth != O_F2D_CCLGROWTH) && (extrap_linear_growth != O_F2D_CONSTGROWTH) &&
+      (extrap_linear_growth != O_F2D_NOEXTRAPOL))
+    *status = O_ERR_INCONSISTENT;
+  if (*status == 0) {
+    if (f->is_factorizable) {
+      if (!f->is_k_constant) {
+        f->fk = o_cspline_new(nk, lk_arr, fk_arr);
+        if (!f->fk) *status = O_ERR_MEMORY;
+      }
+      if (!f->is_a_constant) {
+        f->fa = o_cspline_new(na, a_arr, fa_arr);
+        if (!f->fa) *status = O_ERR_MEMORY;
+      }
+    } else if (!(f->is_k_constant || f->is_a_constant)) {
+      f->fka = o_bicubic_new(nk, na, lk_arr, a_arr, fka_arr);
+      if (!f->fka) *status = O_ERR_MEMORY;
+    }
+  }
+  return f;
+}
+
+double o_f2d_eval(const o_f2d *f2d, double lk, double a, const o_cosmo *cosmo, int *status) {
+  int is_hiz, is_loz;
+  double a_ev = a;
+  if (f2d->is_a_constant) { is_hiz = 0; is_loz = 0; }
+  else {
+    is_hiz = a < f2d->amin;
+    is_loz = a > f2d->amax;
+    if (is_loz) {
+      if (f2d->extrap_linear_growth == O_F2D_NOEXTRAPOL) { *status = O_ERR_SPLINE_EV; return NAN; }
+      a_ev = f2d->amax;
+    } else if (is_hiz) {
+      if (f2d->extrap_linear_growth == O_F2D_NOEXTRAPOL) { *status = O_ERR_SPLINE_EV; return NAN; }
+      a_ev = f2d->amin;
+    }
+  }
+  int is_hik, is_lok;
+  double fka_pre, fka_post;
+  double lk_ev = lk;
+  if (f2d->is_k_constant) { is_hik = 0; is_lok = 0; }
+  else {
+    is_hik = lk > f2d->lkmax;
+    is_lok = lk < f2d->lkmin;
+    if (is_hik) lk_ev = f2d->lkmax;
+    else if (is_lok) lk_ev = f2d->lkmin;
+  }
+  int spstatus = 0;
+  if (f2d->is_factorizable) {
+    double fk, fa;
+    if (f2d->fk == NULL) fk = f2d->is_log ? 0 : 1;
+    else spstatus |= o_cspline_eval_e(f2d->fk, lk_ev, 0, &fk);
+    if (f2d->fa == NULL) fa = f2d->is_log ? 0 : 1;
+    else spstatus |= o_cspline_eval_e(f2d->fa, a_ev, 0, &fa);
+    fka_pre = f2d->is_log ? fk + fa : fk * fa;
+  } else {
+    if (f2d->fka == NULL) fka_pre = f2d->is_log ? 0 : 1;
+    else spstatus = o_bicubic_eval_e(f2d->fka, lk_ev, a_ev, 0, &fka_pre);
+  }
+  if (spstatus) { *status = O_ERR_SPLINE_EV; return NAN; }
+
+  if (is_hik || is_lok) {
+    int order = is_hik ? f2d->extrap_order_hik : f2d->extrap_order_lok;
+    fka_post = fka_pre;
+    if (order > 0) {
+      double pd;
+      double dlk = lk - lk_ev;
+      if (f2d->is_factorizable) spstatus = o_cspline_eval_e(f2d->fk, lk_ev, 1, &pd);
+      else spstatus = o_bicubic_eval_e(f2d->fka, lk_ev, a_ev, 1, &pd);
+      if (spstatus) { *status = O_ERR_SPLINE_EV; return NAN; }
+      fka_post += pd * dlk;
+      if (order > 1) {
+        if (f2d->is_factorizable) spstatus = o_cspline_eval_e(f2d->fk, lk_ev, 2, &pd);
+        else spstatus = o_bicubic_eval_e(f2d->fka, lk_ev, a_ev, 2, &pd);
+        if (spstatus) { *status = O_ERR_SPLINE_EV; return NAN; }
+        fka_post += pd * dlk * dlk * 0.5;
+      }
+    }
+  } else
+    fka_post = fka_pre;
+
+  if (f2d->is_log) fka_post = exp(fka_post);
+
+  if (is_hiz) {
+    double gz;
+    if (f2d->extrap_linear_growth == O_F2D_CCLGROWTH) {
+      if (!cosmo || !cosmo->growth) { *status = O_ERR_GROWTH_INIT; return NAN; }
+      gz = o_growth_factor(cosmo, a, status) / o_growth_factor(cosmo, a_ev, status);
+    } else
+      gz = f2d->growth_factor_0;
+    fka_post *= pow(gz, f2d->growth_exponent);
+  }
+  return fka_post;
+}
+
+/* ------------------------------------------------------------------ */
+/* ccl_cl_tracer_t (src/ccl_tracers.c:569-749)                         */
+/* ------------------------------------------------------------------ */
+#define O_FRAC_RELEVANT 5E-4 /* include/ccl_tracers.h:13 */
+
+typedef struct {
+  int der_bessel, der_angles;
+  o_f1d *kernel;
+  o_f2d *transfer;
+  double chi_min, chi_max;
+} o_tracer;
+
+void o_tracer_free(o_tracer *t) {
+  if (!t) return;
+  o_f1d_free(t->kernel); o_f2d_free(t->transfer); free(t);
+}
+
+/* chi_max_nokernel = comoving distance to A_SPLINE_MIN, computed by the caller
+ * (src/ccl_tracers.c:632). */
+o_tracer *o_tracer_new(int der_bessel, int der_angles, int n_w, const double *chi_w,
+                       const double *w_w, int na_ka, const double *a_ka, int nk_ka,
+                       const double *lk_ka, const double *fka_arr, const double *fk_arr,
+                       const double *fa_arr, int is_fka_log, int is_factorizable,
+                       int extrap_order_lok, int extrap_order_hik, double chi_max_nokernel,
+                       int *status) {
+  if ((der_angles < 0) || (der_angles > 2)) *status = O_ERR_INCONSISTENT;
+  if ((der_bessel < -1) || (der_bessel > 2)) *status = O_ERR_INCONSISTENT;
+  if (*status) return NULL;
+  o_tracer *tr = calloc(1, sizeof(o_tracer));
+  tr->der_angles = der_angles;
+  tr->der_bessel = der_bessel;
+  tr->chi_min = 0;
+  tr->chi_max = 1E15;
+  if ((n_w > 0) && (chi_w != NULL) && (w_w != NULL)) {
+    tr->kernel = o_f1d_new(n_w, chi_w, w_w, 0, 0);
+    if (tr->kernel == NULL) *status = O_ERR_MEMORY;
+  }
+  if (*status == 0) {
+    if (tr->kernel == NULL) {
+      tr->chi_min = 0;
+      tr->chi_max = chi_max_nokernel;
+    } else {
+      int ichi;
+      double w_max = fabs(w_w[0]);
+      for (ichi = 0; ichi < n_w; ichi++)
+        if (fabs(w_w[ichi]) >= w_max) w_max = fabs(w_w[ichi]);
+      w_max *= O_FRAC_RELEVANT;
+      tr->chi_min = chi_w[0];
+      tr->chi_max = chi_w[n_w - 1];
+      for (ichi = 0; ichi < n_w - 1; ichi++)
+        if (fabs(w_w[ichi + 1]) >= w_max) { tr->chi_min = chi_w[ichi]; break; }
+      for (ichi = n_w - 1; ichi >= 1; ichi--)
+        if (fabs(w_w[ichi - 1]) >= w_max) { tr->chi_max = chi_w[ichi]; break; }
+    }
+  }
+  if (*status == 0) {
+    if ((fka_arr != NULL) || (fk_arr != NULL) || (fa_arr != NULL)) {
+      tr->transfer = o_f2d_new(na_ka, a_ka, nk_ka, lk_ka, fka_arr, fk_arr, fa_arr,
+                               is_factorizable, extrap_order_lok, extrap_order_hik,
+                               O_F2D_CONSTGROWTH, is_fka_log, 1, 0, status);
+    }
+  }
+  return tr;
+}
+
+double o_tracer_chi_min(const o_tracer *t) { return t->chi_min; }
+double o_tracer_chi_max(const o_tracer *t) { return t->chi_max; }
+
+double o_tracer_f_ell(const o_tracer *tr, double ell) {
+  if (tr->der_angles == 1) return ell * (ell + 1.);
+  else if (tr->der_angles == 2) {
+    if (ell <= 1) return 0;
+    else if (ell <= 10) return sqrt((ell + 2) * (ell + 1) * ell * (ell - 1));
+    else {
+      double lp1h = ell + 0.5;
+      double lp1h2 = lp1h * lp1h;
+      if (ell <= 1000) return lp1h2 * (1 - 1.25 / lp1h2);
+      else return lp1h2;
+    }
+  }
+  return 1;
+}
+
+double o_tracer_kernel(const o_tracer *tr, double chi) {
+  return tr->kernel ? o_f1d_eval(tr->kernel, chi) : 1;
+}
+
+double o_tracer_transfer(const o_tracer *tr, double lk, double a, int *status) {
+  return tr->transfer ? o_f2d_eval(tr->transfer, lk, a, NULL, status) : 1;
+}
+
+/* ------------------------------------------------------------------ */
+/* src/ccl_cls.c:64-263                                                */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  double l;
+  const o_cosmo *cosmo;
+  int n1, n2;
+  o_tracer *const *trc1;
+  o_tracer *const *trc2;
+  const o_f2d *psp;
+  int *status;
+  long neval;
+} o_integ_par;
+
+static void o_get_k_interval(const o_cosmo *cosmo, int n1, o_tracer *const *t1, int n2,
+                             o_tracer *const *t2, double l, double *lkmin, double *lkmax) {
+  double chi_min1 = 1E15, chi_max1 = -1E15;
+  for (int i = 0; i < n1; i++) {
+    if (t1[i]->chi_min < chi_min1) chi_min1 = t1[i]->chi_min;
+    if (t1[i]->chi_max > chi_max1) chi_max1 = t1[i]->chi_max;
+  }
+  double chi_min2 = 1E15, chi_max2 = -1E15;
+  for (int i = 0; i < n2; i++) {
+    if (t2[i]->chi_min < chi_min2) chi_min2 = t2[i]->chi_min;
+    if (t2[i]->chi_max > chi_max2) chi_max2 = t2[i]->chi_max;
+  }
+  double chi_min = fmax(chi_min1, chi_min2);
+  double chi_max = fmin(chi_max1, chi_max2);
+  if (chi_min <= 0) chi_min = 0.5 * (l + 0.5) / cosmo->K_MAX;
+  *lkmax = log(fmin(cosmo->K_MAX, 2 * (l + 0.5) / chi_min));
+  *lkmin = log(fmax(cosmo->K_MIN, (l + 0.5) / chi_max));
+}
+
+static double o_transfer_limber_single(const o_tracer *tr, double l, double lk, double k,
+                                       double chi_l, double a_l, const o_cosmo *cosmo,
+                                       const o_f2d *psp, int *status) {
+  double dd = 0;
+  double w = o_tracer_kernel(tr, chi_l);
+  double t = o_tracer_transfer(tr, lk, a_l, status);
+  double fl = o_tracer_f_ell(tr, l);
+  if (tr->der_bessel < 1) {
+    dd = w * t;
+    if (tr->der_bessel == -1) {
+      double lp1h = l + 0.5;
+      dd /= (lp1h * lp1h);
+    }
+  } else {
+    double lp1h = l + 0.5;
+    double lp3h = l + 1.5;
+    double chi_lp = lp3h / k;
+    double a_lp = o_scale_factor_of_chi(cosmo, chi_lp, status);
+    double pk_ratio = fabs(o_f2d_eval(psp, lk, a_lp, cosmo, status) /
+                           o_f2d_eval(psp, lk, a_l, cosmo, status));
+    double w_p = o_tracer_kernel(tr, chi_lp);
+    double t_p = o_tracer_transfer(tr, lk, a_lp, status);
+    double sqell = sqrt(lp1h * pk_ratio / lp3h);
+    if (tr->der_bessel == 1) dd = l * w * t / lp1h - sqell * w_p * t_p;
+    else dd = sqell * 2 * w_p * t_p / lp3h - (0.25 + 2 * l) * w * t / (lp1h * lp1h);
+  }
+  return dd * fl;
+}
+
+static double o_transfer_limber_wrap(double l, double lk, double k, double chi, double a, int n,
+                                     o_tracer *const *trc, const o_cosmo *cosmo,
+                                     const o_f2d *psp, int *status) {
+  double transfer = 0;
+  for (int itr = 0; itr < n; itr++) {
+    transfer += o_transfer_limber_single(trc[itr], l, lk, k, chi, a, cosmo, psp, status);
+    if (*status != 0) return -1;
+  }
+  return transfer;
+}
+
+static double o_cl_integrand(double lk, void *params) {
+  o_integ_par *p = (o_integ_par *)params;
+  p->neval++;
+  double k = exp(lk);
+  double chi = (p->l + 0.5) / k;
+  double a = o_scale_factor_of_chi(p->cosmo, chi, p->status);
+  double d1 = o_transfer_limber_wrap(p->l, lk, k, chi, a, p->n1, p->trc1, p->cosmo, p->psp, p->status);
+  if (d1 == 0) return 0;
+  double d2 = o_transfer_limber_wrap(p->l, lk, k, chi, a, p->n2, p->trc2, p->cosmo, p->psp, p->status);
+  if (d2 == 0) return 0;
+  double pk = o_f2d_eval(p->psp, lk, a, p->cosmo, p->status);
+  return k * pk * d1 * d2;
+}
+
+/* src/ccl_utils.c:17-37 */
+static double *o_linear_spacing(double xmin, double xmax, int N) {
+  double dx = (xmax - xmin) / (N - 1.);
+  double *x = malloc(sizeof(double) * N);
+  for (int i = 0; i < N; i++) x[i] = xmin + dx * i;
+  x[0] = xmin;
+  x[N - 1] = xmax;
+  return x;
+}
+
+/* src/ccl_utils.c:274-345 with ny = 1, T = akima */
+void o_integ_spline(int nx, const double *x, const double *y, double a, double b,
+                    double *result, int *status) {
+  if (b == a) { *result = 0; return; }
+  if (b < a) { b = x[nx - 1]; a = x[0]; }
+  if ((b > x[nx - 1]) || (a < x[0])) { *status = O_ERR_SPLINE; return; }
+  if (*status == 0) {
+    o_akima *s = o_akima_new(nx, x, y);
+    if (s == NULL) { *status = O_ERR_MEMORY; return; }
+    int sstat = o_akima_integ_e(s, a, b, result);
+    if (sstat) { *status = O_ERR_SPLINE_EV; *result = NAN; }
+    o_akima_free(s);
+  }
+}
+
+int o_limber_nk(double lkmin, double lkmax, double dlogk) {
+  return (int)(fmax((lkmax - lkmin) / dlogk + 0.5, 1)) + 1;
+}
+
+static void o_integ_cls_limber_spline(const o_cosmo *cosmo, o_integ_par *ipar, double lkmin,
+                                      double lkmax, double *result, int *status) {
+  int nk = o_limber_nk(lkmin, lkmax, cosmo->DLOGK_INTEGRATION);
+  double *lk_arr = o_linear_spacing(lkmin, lkmax, nk);
+  double *fk_arr = malloc(nk * sizeof(double));
+  if (*status == 0) {
+    for (int ik = 0; ik < nk; ik++) {
+      fk_arr[ik] = o_cl_integrand(lk_arr[ik], ipar);
+      if (*(ipar->status)) { *status = *(ipar->status); break; }
+    }
+  }
+  if (*status == 0) o_integ_spline(nk, lk_arr, fk_arr, 1, -1, result, status);
+  free(fk_arr);
+  free(lk_arr);
+}
+
+/* ------------------------------------------------------------------ */
+/* GSL integration/qk.c + qk41.c + qag.c + workspace (qpsrt.c, util.c) */
+/* ------------------------------------------------------------------ */
+typedef double (*o_func)(double, void *);
+
+static double o_rescale_error(double err, const double result_abs, const double result_asc) {
+  err = fabs(err);
+  if (result_asc != 0 && err != 0) {
+    double scale = pow((200 * err / result_asc), 1.5);
+    if (scale < 1) err = result_asc * scale;
+    else err = result_asc;
+  }
+  if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
+    double min_err = 50 * DBL_EPSILON * result_abs;
+    if (min_err > err) err = min_err;
+  }
+  return err;
+}
+
+static void o_qk41(o_func f, void *par, double a, double b, double *result, double *abserr,
+                   double *resabs, double *resasc) {
+  const int n = 21;
+  const double *xgk = GK41_XGK, *wg = GK41_WG, *wgk = GK41_WGK;
+  double fv1[21], fv2[21];
+  const double center = 0.5 * (a + b);
+  const double half_length = 0.5 * (b - a);
+  const double abs_half_length = fabs(half_length);
+  const double f_center = f(center, par);
+  double result_gauss = 0;
+  double result_kronrod = f_center * wgk[n - 1];
+  double result_abs = fabs(result_kronrod);
+  double result_asc = 0;
+  double mean = 0, err = 0;
+  int j;
+  if (n % 2 == 0) result_gauss = f_center * wg[n / 2 - 1];
+  for (j = 0; j < (n - 1) / 2; j++) {
+    const int jtw = j * 2 + 1;
+    const double abscissa = half_length * xgk[jtw];
+    const double fval1 = f(center - abscissa, par);
+    const double fval2 = f(center + abscissa, par);
+    const double fsum = fval1 + fval2;
+    fv1[jtw] = fval1;
+    fv2[jtw] = fval2;
+    result_gauss += wg[j] * fsum;
+    result_kronrod += wgk[jtw] * fsum;
+    result_abs += wgk[jtw] * (fabs(fval1) + fabs(fval2));
+  }
+  for (j = 0; j < n / 2; j++) {
+    int jtwm1 = j * 2;
+    const double abscissa = half_length * xgk[jtwm1];
+    const double fval1 = f(center - abscissa, par);
+    const double fval2 = f(center + abscissa, par);
+    fv1[jtwm1] = fval1;
+    fv2[jtwm1] = fval2;
+    result_kronrod += wgk[jtwm1] * (fval1 + fval2);
+    result_abs += wgk[jtwm1] * (fabs(fval1) + fabs(fval2));
+  }
+  mean = result_kronrod * 0.5;
+  result_asc = wgk[n - 1] * fabs(f_center - mean);
+  for (j = 0; j < n - 1; j++)
+    result_asc += wgk[j] * (fabs(fv1[j] - mean) + fabs(fv2[j] - mean));
+  err = (result_kronrod - result_gauss) * half_length;
+  result_kronrod *= half_length;
+  result_abs *= abs_half_length;
+  result_asc *= abs_half_length;
+  *result = result_kronrod;
+  *resabs = result_abs;
+  *resasc = result_asc;
+  *abserr = o_rescale_error(err, result_abs, result_asc);
+}
+
+typedef struct {
+  size_t limit, size, nrmax, i, maximum_level;
+  double *alist, *blist, *rlist, *elist;
+  size_t *order, *level;
+} o_ws;
+
+static o_ws *o_ws_alloc(size_t n) {
+  o_ws *w = calloc(1, sizeof(o_ws));
+  w->limit = n;
+  w->alist = malloc(n * sizeof(double));
+  w->blist = malloc(n * sizeof(double));
+  w->rlist = malloc(n * sizeof(double));
+  w->elist = malloc(n * sizeof(double));
+  w->order = malloc(n * sizeof(size_t));
+  w->level = malloc(n * sizeof(size_t));
+  return w;
+}
+
+static void o_ws_free(o_ws *w) {
+  if (!w) return;
+  free(w->alist); free(w->blist); free(w->rlist); free(w->elist); free(w->order); free(w->level);
+  free(w);
+}
+
+/* integration/qpsrt.c */
+static void o_qpsrt(o_ws *workspace) {
+  const size_t last = workspace->size - 1;
+  const size_t limit = workspace->limit;
+  double *elist = workspace->elist;
+  size_t *order = workspace->order;
+  double errmax, errmin;
+  int i, k, top;
+  size_t i_nrmax = workspace->nrmax;
+  size_t i_maxerr = order[i_nrmax];
+  if (last < 2) {
+    order[0] = 0;
+    order[1] = 1;
+    workspace->i = i_maxerr;
+    return;
+  }
+  errmax = elist[i_maxerr];
+  while (i_nrmax > 0 && errmax > elist[order[i_nrmax - 1]]) {
+    order[i_nrmax] = order[i_nrmax - 1];
+    i_nrmax--;
+  }
+  if (last < (limit / 2 + 2)) top = last;
+  else top = limit - last + 1;
+  i = i_nrmax + 1;
+  while (i < top && errmax < elist[order[i]]) {
+    order[i - 1] = order[i];
+    i++;
+  }
+  order[i - 1] = i_maxerr;
+  errmin = elist[last];
+  k = top - 1;
+  while (k > i - 2 && errmin >= elist[order[k]]) {
+    order[k + 1] = order[k];
+    k--;
+  }
+  order[k + 1] = last;
+  i_maxerr = order[i_nrmax];
+  workspace->i = i_maxerr;
+  workspace->nrmax = i_nrmax;
+}
+
+static void o_ws_update(o_ws *workspace, double a1, double b1, double area1, double error1,
+                        double a2, double b2, double area2, double error2) {
+  double *alist = workspace->alist, *blist = workspace->blist;
+  double *rlist = workspace->rlist, *elist = workspace->elist;
+  size_t *level = workspace->level;
+  const size_t i_max = workspace->i;
+  const size_t i_new = workspace->size;
+  const size_t new_level = workspace->level[i_max] + 1;
+  if (error2 > error1) {
+    alist[i_max] = a2;
+    rlist[i_max] = area2;
+    elist[i_max] = error2;
+    level[i_max] = new_level;
+    alist[i_new] = a1;
+    blist[i_new] = b1;
+    rlist[i_new] = area1;
+    elist[i_new] = error1;
+    level[i_new] = new_level;
+  } else {
+    blist[i_max] = b1;
+    rlist[i_max] = area1;
+    elist[i_max] = error1;
+    level[i_max] = new_level;
+    alist[i_new] = a2;
+    blist[i_new] = b2;
+    rlist[i_new] = area2;
+    elist[i_new] = error2;
+    level[i_new] = new_level;
+  }
+  workspace->size++;
+  if (new_level > workspace->maximum_level) workspace->maximum_level = new_level;
+  o_qpsrt(workspace);
+}
+
+static int o_subinterval_too_small(double a1, double a2, double b2) {
+  const double e = DBL_EPSILON;
+  const double u = DBL_MIN;
+  double tmp = (1 + 100 * e) * (fabs(a2) + 1000 * u);
+  return fabs(a1) <= tmp && fabs(b2) <= tmp;
+}
+
+/* gsl_integration_qag with key = GSL_INTEG_GAUSS41 */
+int o_qag41(o_func f, void *par, double a, double b, double epsabs, double epsrel, size_t limit,
+            double *result, double *abserr, int *nintervals) {
+  double area, errsum;
+  double result0, abserr0, resabs0, resasc0;
+  double tolerance;
+  size_t iteration = 0;
+  int roundoff_type1 = 0, roundoff_type2 = 0, error_type = 0;
+  double round_off;
+  o_ws *workspace = o_ws_alloc(limit);
+  workspace->size = 0; workspace->nrmax = 0; workspace->i = 0;
+  workspace->alist[0] = a; workspace->blist[0] = b;
+  workspace->rlist[0] = 0.0; workspace->elist[0] = 0.0;
+  workspace->order[0] = 0; workspace->level[0] = 0; workspace->maximum_level = 0;
+  *result = 0; *abserr = 0;
+  if (nintervals) *nintervals = 1;
+  if (epsabs <= 0 && (epsrel < 50 * DBL_EPSILON || epsrel < 0.5e-28)) {
+    o_ws_free(workspace);
+    return O_GSL_EBADTOL;
+  }
+  o_qk41(f, par, a, b, &result0, &abserr0, &resabs0, &resasc0);
+  workspace->size = 1;
+  workspace->rlist[0] = result0;
+  workspace->elist[0] = abserr0;
+  tolerance = fmax(epsabs, epsrel * fabs(result0));
+  { volatile double ro = 50 * DBL_EPSILON * resabs0; round_off = ro; }
+  if (abserr0 <= round_off && abserr0 > tolerance) {
+    *result = result0; *abserr = abserr0; o_ws_free(workspace);
+    return O_GSL_EROUND;
+  } else if ((abserr0 <= tolerance && abserr0 != resasc0) || abserr0 == 0.0) {
+    *result = result0; *abserr = abserr0; o_ws_free(workspace);
+    return O_SUCCESS;
+  } else if (limit == 1) {
+    *result = result0; *abserr = abserr0; o_ws_free(workspace);
+    return O_GSL_EMAXITER;
+  }
+  area = result0;
+  errsum = abserr0;
+  iteration = 1;
+  do {
+    double a1, b1, a2, b2;
+    double a_i, b_i, r_i, e_i;
+    double area1 = 0, area2 = 0, area12 = 0;
+    double error1 = 0, error2 = 0, error12 = 0;
+    double resasc1, resasc2, resabs1, resabs2;
+    a_i = workspace->alist[workspace->i];
+    b_i = workspace->blist[workspace->i];
+    r_i = workspace->rlist[workspace->i];
+    e_i = workspace->elist[workspace->i];
+    a1 = a_i;
+    b1 = 0.5 * (a_i + b_i);
+    a2 = b1;
+    b2 = b_i;
+    o_qk41(f, par, a1, b1, &area1, &error1, &resabs1, &resasc1);
+    o_qk41(f, par, a2, b2, &area2, &error2, &resabs2, &resasc2);
+    area12 = area1 + area2;
+    error12 = error1 + error2;
+    errsum += (error12 - e_i);
+    area += area12 - r_i;
+    if (resasc1 != error1 && resasc2 != error2) {
+      double delta = r_i - area12;
+      if (fabs(delta) <= 1.0e-5 * fabs(area12) && error12 >= 0.99 * e_i) roundoff_type1++;
+      if (iteration >= 10 && error12 > e_i) roundoff_type2++;
+    }
+    tolerance = fmax(epsabs, epsrel * fabs(area));
+    if (errsum > tolerance) {
+      if (roundoff_type1 >= 6 || roundoff_type2 >= 20) error_type = 2;
+      if (o_subinterval_too_small(a1, a2, b2)) error_type = 3;
+    }
+    o_ws_update(workspace, a1, b1, area1, error1, a2, b2, area2, error2);
+    iteration++;
+  } while (iteration < limit && !error_type && errsum > tolerance);
+  {
+    double result_sum = 0;
+    for (size_t k = 0; k < workspace->size; k++) result_sum += workspace->rlist[k];
+    *result = result_sum;
+  }
+  *abserr = errsum;
+  if (nintervals) *nintervals = (int)workspace->size;
+  o_ws_free(workspace);
+  if (errsum <= tolerance) return O_SUCCESS;
+  else if (error_type == 2) return O_GSL_EROUND;
+  else if (error_type == 3) return O_GSL_ESING;
+  else if (iteration == limit) return O_GSL_EMAXITER;
+  return O_GSL_EFAILED;
+}
+
+static void o_integ_cls_limber_qag_quad(const o_cosmo *cosmo, o_integ_par *ipar, double lkmin,
+                                        double lkmax, double *result, double *eresult,
+                                        int *status) {
+  int gslstatus = o_qag41(o_cl_integrand, ipar, lkmin, lkmax, 0, cosmo->LIMBER_EPSREL,
+                          cosmo->N_ITERATION, result, eresult, NULL);
+  if (gslstatus == O_GSL_EROUND) gslstatus = O_ERR_CQUAD_NEEDED;
+  if (*status == 0) *status = gslstatus;
+}
+
+/* src/ccl_cls.c:265-363.  neval_out (may be NULL) receives the integrand evaluations per ell. */
+void o_angular_cls_limber(const o_cosmo *cosmo, int n1, o_tracer *const *trc1, int n2,
+                          o_tracer *const *trc2, const o_f2d *psp, int nl_out,
+                          const double *l_out, double *cl_out, int integration_method,
+                          long *neval_out, int *status) {
+  if (!cosmo->achi) { *status = O_ERR_DISTANCES_INIT; return; }
+#pragma omp parallel
+  {
+    int clastatus, lind;
+    o_integ_par ipar;
+    int local_status = *status;
+    double lkmin, lkmax, l, result, eresult;
+    ipar.cosmo = cosmo; ipar.n1 = n1; ipar.n2 = n2; ipar.trc1 = trc1; ipar.trc2 = trc2;
+    ipar.psp = psp; ipar.status = &clastatus;
+#pragma omp for schedule(dynamic)
+    for (lind = 0; lind < nl_out; ++lind) {
+      if (local_status == 0) {
+        l = l_out[lind];
+        clastatus = 0;
+        ipar.l = l;
+        ipar.neval = 0;
+        o_get_k_interval(cosmo, n1, trc1, n2, trc2, l, &lkmin, &lkmax);
+        if (integration_method == O_INTEG_QAG)
+          o_integ_cls_limber_qag_quad(cosmo, &ipar, lkmin, lkmax, &result, &eresult, &local_status);
+        else if (integration_method == O_INTEG_SPLINE)
+          o_integ_cls_limber_spline(cosmo, &ipar, lkmin, lkmax, &result, &local_status);
+        else
+          local_status = O_ERR_NOT_IMPLEMENTED;
+        if (neval_out) neval_out[lind] = ipar.neval;
+        if ((*ipar.status == 0) && (local_status == 0)) {
+          cl_out[lind] = result / (l + 0.5);
+        } else {
+          cl_out[lind] = NAN;
+          local_status = O_ERR_INTEG;
+        }
+      }
+    }
+    if (local_status) {
+#pragma omp atomic write
+      *status = local_status;
+    }
+  }
+}
+
+/* Unlike the reference (a failing ell poisons its OpenMP thread, src/ccl_cls.c:319), this
+ * variant evaluates every ell independently and reports a per-ell status; used to check the
+ * GPU's per-(pair, ell) status words. */
+void o_angular_cls_limber_each(const o_cosmo *cosmo, int n1, o_tracer *const *trc1, int n2,
+                               o_tracer *const *trc2, const o_f2d *psp, int nl_out,
+                               const double *l_out, double *cl_out, int integration_method,
+                               int *status_each) {
+  for (int i = 0; i < nl_out; i++) {
+    int st = 0;
+    o_angular_cls_limber(cosmo, n1, trc1, n2, trc2, psp, 1, l_out + i, cl_out + i,
+                         integration_method, NULL, &st);
+    status_each[i] = st;
+  }
+}
+
+void o_get_k_interval_pub(const o_cosmo *cosmo, int n1, o_tracer *const *t1, int n2,
+                          o_tracer *const *t2, double l, double *lkmin, double *lkmax) {
+  o_get_k_interval(cosmo, n1, t1, n2, t2, l, lkmin, lkmax);
+}
+
+/* test helper: integrate exp(-x^2) * cos(w x) type functions through the qag restatement */
+typedef struct { int kind; double p; } o_testf_par;
+static double o_testf(double x, void *v) {
+  o_testf_par *p = (o_testf_par *)v;
+  switch (p->kind) {
+    case 0: return exp(-x * x) * cos(p->p * x);
+    case 1: return pow(fabs(x), p->p);
+    case 2: return 1.0 / (1.0 + p->p * x * x);
+    default: return x;
+  }
+}
+int o_qag41_test(int kind, double p, double a, double b, double epsabs, double epsrel, int limit,
+                 double *result, double *abserr, int *nint) {
+  o_testf_par par = {kind, p};
+  return o_qag41(o_testf, &par, a, b, epsabs, epsrel, limit, result, abserr, nint);
+}
+
+int o_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
