@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- Limber C_ell throughput of the B200 path (driver contract).
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on):
+  4096 cosmologies x LSST-Y1-like 3x2pt (5 NumberCounts + 10 WeakLensing -> 120 pairs) x 100
+  log-spaced ells 2..3000, 'spline' Limber integration, fp64.  The batch is sharded by
+  cosmology over the N ranks (strong scaling of the 4096-cosmology job) and the C_ell blocks
+  are gathered to rank 0 with one NCCL gather inside the timed region.
+
+One "step" = one pass of the hot path (ccl_angular_cls_limber for every cosmology, pair, ell)
+over the resident batch.  `value` is C_ell/s with all tables already in HBM; `e2e` times the
+host-buffer C-ABI path per step: staging of the flat host tables, one H2D copy, the device
+table preparation (spline coefficients / bicubic planes), the Limber kernel and the D2H copy
+of every C_ell.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP over ell like
+src/ccl_cls.c:282-356, pairs serial like benchmarks/test_timing.py:31-34) on a bounded sample
+of the same workload; the GSL-based reference itself cannot be built in this image.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NCOSMO_TOTAL = 4096
+N_DISTINCT = 8          # distinct synthetic cosmologies; slots cycle through them with a P(k) offset
+NL = 100
+# algorithmic flops per integrand node: base + per-sub-tracer + Akima integral
+F_BASE, F_AKIMA = 81.0, 33.0
+F_SUB = {"wl": 10.0, "nc": 26.0}
+
+
+def build_host_tables(n_distinct, seed=0):
+    """Flat host tables (what pyccl's constructors hand to the C layer) for n_distinct cosmologies."""
+    from ccl_b200 import synthetic as S
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_distinct):
+        Om = 0.25 + 0.1 * rng.random()
+        h = 0.6 + 0.2 * rng.random()
+        w0 = -1.3 + 0.6 * rng.random()
+        wa = -0.5 + rng.random()
+        bg = S.background(Om=Om, h=h, w0=w0, wa=wa)
+        pk = S.power(bg, ns=0.92 + 0.08 * rng.random(), sigma_like=0.8 + 0.4 * rng.random())
+        subs, colls = S.lsst_like_tracers(bg, w0=w0, wa=wa)
+        a, chi = bg["chi_of_a"]
+        out.append(dict(bg=bg, pk=pk, subs=subs, colls=colls, cmax=float(np.interp(0.1, a, chi))))
+    return out
+
+
+def fill_batch(batch, tables, nslots, offset0=0):
+    """Stage nslots cosmologies (cycling through the distinct tables, perturbing log P)."""
+    for ic in range(nslots):
+        t = tables[(ic + offset0) % len(tables)]
+        bg, pk = t["bg"], t["pk"]
+        batch.set_cosmology(ic, bg["chi"], bg["a"], bg["a_growth"], bg["growth"], t["cmax"])
+        batch.set_pk2d(ic, pk["lk"], pk["a"], pk["logp"] + 1e-3 * ((ic + offset0) // len(tables)))
+        for s in t["subs"]:
+            batch.add_tracer(ic, **s)
+
+
+def algorithmic_flops(batch, tables, nslots, colls, pairs, ells, offset0=0):
+    """Sum over (cosmology, pair, ell) of nk * (F_base + sum F_tracer + F_akima)."""
+    kinds = ["nc" if t[0] < 5 else "wl" for t in enumerate(colls)]
+    per_distinct = {}
+    nodes_tot, flops_tot = 0, 0.0
+    for ic in range(nslots):
+        key = (ic + offset0) % len(tables)
+        if key not in per_distinct:
+            rng_ = [batch.tracer_chi_range(ic, c[0]) for c in colls]   # one sub-tracer per collection here
+            nodes, flops = 0, 0.0
+            for (i, j) in pairs:
+                chi_min = max(rng_[i][0], rng_[j][0])
+                chi_max = min(rng_[i][1], rng_[j][1])
+                cm = np.where(chi_min <= 0, 0.5 * (ells + 0.5) / 1e3, chi_min)
+                lkmax = np.log(np.minimum(1e3, 2 * (ells + 0.5) / cm))
+                lkmin = np.log(np.maximum(5e-5, (ells + 0.5) / chi_max))
+                nk = (np.maximum((lkmax - lkmin) / 0.025 + 0.5, 1.0)).astype(int) + 1
+                nk = np.where(nk >= 5, nk, 0)
+                nodes += int(nk.sum())
+                flops += float(nk.sum()) * (F_BASE + F_SUB[kinds[i]] + F_SUB[kinds[j]] + F_AKIMA)
+            per_distinct[key] = (nodes, flops)
+        nodes_tot += per_distinct[key][0]
+        flops_tot += per_distinct[key][1]
+    return nodes_tot, flops_tot
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.02)
+        except Exception as e:  # NVML unavailable: report that, never fake numbers
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def geometry():
+    from ccl_b200 import synthetic as S
+    colls = [(i, 1) for i in range(15)]
+    pairs = S.all_pairs(15)
+    ells = np.geomspace(2, 3000, NL)
+    return colls, pairs, ells
+
+
+def run_reference(args, rank):
+    """CPU restatement of the reference on a bounded sample: 1 cosmology x 120 pairs x 100 ells."""
+    if rank != 0:
+        return
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import oracle_cosmo, oracle_pk, oracle_tracer
+    tables = build_host_tables(1)
+    t = tables[0]
+    colls, pairs, ells = geometry()
+    oc, op = oracle_cosmo(t["bg"]), oracle_pk(t["pk"])
+    otr = [oracle_tracer(s, t["cmax"]) for s in t["subs"]]
+    cores = oracle.num_threads()
+
+    def one_pass():
+        for (i, j) in pairs:
+            oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, oracle.INTEG_SPLINE)
+
+    for _ in range(max(args.warmup, 1)):
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_pass()
+    dt = (time.perf_counter() - t0) / args.steps
+    n_cl = len(pairs) * len(ells)
+    val = n_cl / dt
+    sample = "1 of 4096 cosmologies x 120 pairs x 100 ells per step ('spline'), pairs serial, OpenMP over ell"
+    print(json.dumps({
+        "impl": "reference", "metric": "3x2pt C_ell/s (pair x ell), Limber 'spline'", "value": val,
+        "unit": "C_ell/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "LSST-Y1-like 3x2pt likelihood batch: 4096 cosmologies x 120 pairs x 100 ells",
+                   "reference_impl": "oracle/ CPU restatement (GSL-based reference not buildable here)"},
+        "cpu_baseline": {"value": val, "unit": "C_ell/s", "cores": cores, "kind": "port", "sample": sample,
+                         "cosmologies_per_s": 1.0 / dt},
+        "e2e": {"value": val, "unit": "C_ell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ncosmo", type=int, default=NCOSMO_TOTAL, help="total cosmologies in the job")
+    ap.add_argument("--method", default="spline", choices=["spline", "qag_quad"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ccl_b200 as cb
+    from ccl_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import ctypes as C
+    st = C.c_int(0)
+    _lib.load().ccl_b200_set_device(local_rank, C.byref(st))
+    assert st.value == 0, _lib.last_error()
+
+    method = _lib.INTEGRATION_SPLINE if args.method == "spline" else _lib.INTEGRATION_QAG_QUAD
+    colls, pairs, ells = geometry()
+    npair, nl = len(pairs), len(ells)
+    # shard by cosmology: contiguous blocks, remainder to the first ranks
+    base, rem = divmod(args.ncosmo, world)
+    nloc = base + (1 if rank < rem else 0)
+    off = rank * base + min(rank, rem)
+
+    tables = build_host_tables(N_DISTINCT)
+    batch = cb.LibBatch(nloc)
+    fill_batch(batch, tables, nloc, off)
+    batch.commit()
+    nodes, flops = algorithmic_flops(batch, tables, nloc, colls, pairs, ells, off)
+
+    d_cl = torch.empty((nloc, npair, nl), dtype=torch.float64, device="cuda")
+    d_st = torch.zeros((2, nloc, npair), dtype=torch.int32, device="cuda")
+    gather_list = None
+    if world > 1 and rank == 0:
+        sizes = [base + (1 if r < rem else 0) for r in range(world)]
+        gather_list = [torch.empty((s, npair, nl), dtype=torch.float64, device="cuda") for s in sizes]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        batch.angular_cl_dev(colls, pairs, ells, d_cl.data_ptr(), d_st.data_ptr(), method, stream)
+        if world > 1:
+            # equal-sized shards go through one NCCL gather; ragged ones through send/recv
+            if rem == 0:
+                dist.gather(d_cl, gather_list, dst=0)
+            else:
+                if rank == 0:
+                    gather_list[0].copy_(d_cl)
+                    reqs = [dist.irecv(gather_list[r], src=r) for r in range(1, world)]
+                    for q in reqs:
+                        q.wait()
+                else:
+                    dist.send(d_cl, dst=0)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record()
+    for i in range(args.steps):
+        kev[i][0].record()
+        batch.angular_cl_dev(colls, pairs, ells, d_cl.data_ptr(), d_st.data_ptr(), method, stream)
+        kev[i][1].record()
+        if world > 1:
+            if rem == 0:
+                dist.gather(d_cl, gather_list, dst=0)
+            elif rank == 0:
+                gather_list[0].copy_(d_cl)
+                for q in [dist.irecv(gather_list[r], src=r) for r in range(1, world)]:
+                    q.wait()
+            else:
+                dist.send(d_cl, dst=0)
+    ev1.record()
+    sync_all()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    ms_per_step = elapsed_ms / args.steps
+    n_cl_total = args.ncosmo * npair * nl
+    value = n_cl_total / (ms_per_step * 1e-3)
+    n_fail = int((d_st[0] != 0).sum().item())
+
+    # ---- fp64 roofline of the dominant kernel (this rank's launch) ----
+    st = C.c_int(0)
+    peak = _lib.load().ccl_b200_measure_fp64_peak(C.byref(st))
+    achieved = flops / (kern_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak and peak > 0 else None, "traffic": None,
+                "kernel": "limber_spline_kernel" if args.method == "spline" else "limber_qag_kernel",
+                "kernel_ms": kern_ms, "algorithmic_flops_per_launch": flops, "integrand_nodes_per_launch": nodes,
+                "peak_source": "measured in-run: DFMA microbenchmark ccl_b200_measure_fp64_peak "
+                               "(MEASURED_PEAKS.json holds no fp64 figure)"}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        cl_host = None
+        e2e_steps = max(1, min(args.steps, 3))
+
+        def e2e_step():
+            batch.reset()
+            fill_batch(batch, tables, nloc, off)
+            batch.commit()
+            return batch.angular_cl(colls, pairs, ells, method)
+
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            cl_host, stat_host, _ = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        h2d = int(batch.h2d_bytes) + nl * 8 + (len(colls) + npair) * 8
+        d2h = int(cl_host.nbytes + stat_host.nbytes)
+        e2e = {"value": n_cl_total / dt, "unit": "C_ell/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": dt * 1e3,
+               "note": "per step: stage host tables, 1 H2D copy, device table prep, Limber kernel, D2H of all C_ell"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from common import oracle_cosmo, oracle_pk, oracle_tracer
+        t = tables[off % len(tables)]
+        oc, op = oracle_cosmo(t["bg"]), oracle_pk(t["pk"])
+        otr = [oracle_tracer(s, t["cmax"]) for s in t["subs"]]
+        t0 = time.perf_counter()
+        ref = np.empty((npair, nl))
+        for q, (i, j) in enumerate(pairs):
+            ref[q], _ = oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, oracle.INTEG_SPLINE)
+        dtc = time.perf_counter() - t0
+        got = d_cl[0].cpu().numpy()
+        err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
+        cpu_baseline = {"value": npair * nl / dtc, "unit": "C_ell/s", "cores": oracle.num_threads(),
+                        "kind": "port", "cosmologies_per_s": 1.0 / dtc,
+                        "sample": "1 of %d cosmologies x 120 pairs x 100 ells, 'spline', pairs serial, "
+                                  "OpenMP over ell (oracle restatement of src/ccl_cls.c)" % args.ncosmo,
+                        "max_rel_err_gpu_vs_cpu_on_sample": err}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "3x2pt C_ell/s (pair x ell), Limber '%s'" % args.method, "value": value, "unit": "C_ell/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "LSST-Y1-like 3x2pt likelihood batch (BASELINE configs[3]): %d cosmologies x "
+                                   "120 pairs (5 NumberCounts + 10 WeakLensing) x 100 log-spaced ells 2..3000"
+                                   % args.ncosmo,
+                       "method": args.method, "sharding": "by cosmology, contiguous blocks, one NCCL gather",
+                       "cosmologies_per_s": value / (npair * nl),
+                       "l2": "inputs larger than L2 (%.1f GB of tables per rank)" % (batch.arena_bytes / 1e9),
+                       "distinct_cosmologies": N_DISTINCT, "failed_cl_entries": n_fail},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": args.steps, "clocks": clocks,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

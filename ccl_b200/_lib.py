@@ -39,6 +39,7 @@ SIGNATURES = {
     "ccl_b200_last_error": (C.c_char_p, []),
     "ccl_b200_version": (C.c_char_p, []),
     "ccl_b200_default_params": (None, [C.POINTER(Params)]),
+    "ccl_b200_measure_fp64_peak": (C.c_double, [_ip]),
     "ccl_b200_cosmology_new": (_vp, [C.POINTER(Params), _ip]),
     "ccl_b200_cosmology_free": (None, [_vp]),
     "ccl_b200_cosmology_set_achi": (None, [_vp, C.c_int, _dp, _dp, _ip]),

@@ -603,6 +603,14 @@ int ccl_b200_device_count(void) {
 const char* ccl_b200_last_error(void) { return g_err.c_str(); }
 const char* ccl_b200_version(void) { return "ccl_b200 0.1 (sm_100a)"; }
 
+double ccl_b200_measure_fp64_peak(int* status) {
+  if (*status) return -1.0;
+  if (!use_device(status)) return -1.0;
+  const double t = measure_fp64_peak_tflops(0);
+  if (t <= 0) { *status = CCL_B200_ERROR_CUDA; set_err("ccl_b200: fp64 peak measurement failed"); }
+  return t;
+}
+
 void ccl_b200_default_params(ccl_b200_params* p) {
   p->K_MAX = 1e3; p->K_MIN = 5e-5; p->DLOGK_INTEGRATION = 0.025;
   p->INTEGRATION_LIMBER_EPSREL = 1e-4; p->N_ITERATION = 1000; p->A_SPLINE_MIN = 0.1;

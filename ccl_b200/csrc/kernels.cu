@@ -649,6 +649,50 @@ limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned 
   }
 }
 
+// ---- fp64 vector-pipe peak: 16 independent DFMA chains per thread ------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + i * 1e-3 + threadIdx.x * 1e-6;
+  const double m = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+
+double measure_fp64_peak_tflops(cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return -1.0;
+  const int iters = 1 << 15, blocks = sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  dfma_peak_kernel<<<blocks, threads, 0, stream>>>(d, 1 << 10, 1.0);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, stream);
+    dfma_peak_kernel<<<blocks, threads, 0, stream>>>(d, iters, 1.0 + rep);
+    cudaEventRecord(e1, stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+    best = fmax(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+
 size_t limber_qag_workspace_bytes(int n_iteration) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -126,6 +126,7 @@ cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws,
                           cudaStream_t stream);
 size_t limber_qag_workspace_bytes(int n_iteration);
 int limber_nk_cap(const LimberParams& par);
+double measure_fp64_peak_tflops(cudaStream_t stream);
 // vectorised accessors (ccl_scale_factor_of_chis, pk2d_eval_multi, cl_tracer_get_kernel/_transfer)
 void launch_eval_achi(const Cosmo* d_cs, int n, const double* d_chi, double* d_out, int* d_status,
                       cudaStream_t stream);

@@ -68,6 +68,9 @@ int ccl_b200_device_count(void);
 const char *ccl_b200_last_error(void);
 const char *ccl_b200_version(void);
 void ccl_b200_default_params(ccl_b200_params *p);
+/* Measured fp64 FMA throughput of the current device in TFLOP/s (DFMA microbenchmark, best of
+ * 5): the roofline denominator of the Limber kernels (MEASURED_PEAKS.json has no fp64 figure). */
+double ccl_b200_measure_fp64_peak(int *status);
 
 /* ---- cosmology: background tables (src/ccl_background.c) ---- */
 ccl_b200_cosmology *ccl_b200_cosmology_new(const ccl_b200_params *params, int *status);

@@ -88,4 +88,8 @@ def test_accessors_match_oracle(setup):
         p, st = s["psp"].eval(lk, a, s["cos"])
         pr = np.array([s["opk"](x, a, s["ocos"])[0] for x in lk])
         assert st == 0
-        assert np.max(np.abs(p / pr - 1)) < 1e-12
+        inside = (lk >= s["opk"]._lk[0]) & (lk <= s["opk"]._lk[-1])
+        assert np.max(np.abs(p / pr - 1)[inside]) < 1e-13
+        # Outside the table the order-2 term multiplies d2/dlnk2 of a *natural* spline at its end
+        # node, i.e. rounding noise of order eps*|z|/dx^2 ~ 1e-10 in both implementations.
+        assert np.max(np.abs(p / pr - 1)[~inside]) < 5e-9
