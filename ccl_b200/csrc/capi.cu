@@ -55,8 +55,8 @@ constexpr size_t ALIGN_D = 4;  // raw region alignment in doubles (32 B)
 // ---- plans: offsets into the arena, turned into device descriptors at commit ----
 struct S1Plan {
   bool present = false;
-  int kind = 0;  // 0 akima, 1 natural cspline, 2 grid only (nodes + LUT)
-  int n = 0, nlut = 0;
+  int kind = 0;  // 0 akima, 1 natural cspline, 2 bicubic axis (nodes + LUT)
+  int n = 0, nlut = 0, uniform = 0;
   size_t x_off = 0, y_off = 0;               // raw region, in doubles
   size_t co_off = 0, lut_off = 0, scr_off = 0;  // derived region, in bytes
   double x0 = 0, xn = 0;
@@ -177,9 +177,15 @@ struct TableSet {
         *status = CCL_B200_ERROR_SPLINE;
         return false;
       }
+    // quasi-uniform grid: the analytic index guess is within +-1 interval of the true one
+    const double step = (s.xn - s.x0) / (n - 1.);
+    s.uniform = 1;
+    for (int i = 0; i < n; ++i)
+      if (fabs(x[i] - (s.x0 + step * i)) > 0.3 * step) { s.uniform = 0; break; }
     s.nlut = lut_size(n);
     s.lut_off = derive(sizeof(int) * s.nlut);
-    if (kind != 2) s.co_off = derive(sizeof(double4) * (n - 1));
+    if (kind != 2) s.co_off = derive(sizeof(Rec1) * (n - 1));
+    else s.co_off = derive(sizeof(AxisRec) * (n - 1));
     if (kind == 1) s.scr_off = derive(sizeof(double) * 3 * n);
     return true;
   }
@@ -300,10 +306,22 @@ struct TableSet {
     Spline1D d;
     memset(&d, 0, sizeof(d));
     if (!s.present) return d;
-    d.x = reinterpret_cast<const double*>(base_raw) + s.x_off;
-    d.co = reinterpret_cast<const double4*>(base_der + s.co_off);
+    d.rec = reinterpret_cast<const Rec1*>(base_der + s.co_off);
     d.lut = reinterpret_cast<const int*>(base_der + s.lut_off);
-    d.n = s.n; d.nlut = s.nlut; d.x0 = s.x0; d.xn = s.xn;
+    d.n = s.n; d.nlut = s.nlut; d.uniform = s.uniform; d.x0 = s.x0; d.xn = s.xn;
+    d.inv_step = (s.n - 1) / (s.xn - s.x0);
+    d.inv_bin = s.nlut / (s.xn - s.x0);
+    return d;
+  }
+
+  Axis mk_axis(const S1Plan& s, char* base_der) const {
+    Axis d;
+    memset(&d, 0, sizeof(d));
+    if (!s.present) return d;
+    d.rec = reinterpret_cast<const AxisRec*>(base_der + s.co_off);
+    d.lut = reinterpret_cast<const int*>(base_der + s.lut_off);
+    d.n = s.n; d.nlut = s.nlut; d.uniform = s.uniform; d.x0 = s.x0; d.xn = s.xn;
+    d.inv_step = (s.n - 1) / (s.xn - s.x0);
     d.inv_bin = s.nlut / (s.xn - s.x0);
     return d;
   }
@@ -312,26 +330,30 @@ struct TableSet {
     F2D d = f.flags;
     d.fk = mk_s1(f.fk, br, bd);
     d.fa = mk_s1(f.fa, br, bd);
-    d.gk = mk_s1(f.gk, br, bd);
-    d.ga = mk_s1(f.ga, br, bd);
+    d.gk = mk_axis(f.gk, bd);
+    d.ga = mk_axis(f.ga, bd);
     d.tab = d.has_fka ? reinterpret_cast<const double4*>(bd + f.tab_off) : nullptr;
     return d;
   }
 
   void jobs_s1(const S1Plan& s, char* br, char* bd, std::vector<AkimaJob>& ak, std::vector<CsplineJob>& cs,
-               std::vector<LutJob>& lu) const {
+               std::vector<LutJob>& lu) {
     if (!s.present) return;
     const double* x = reinterpret_cast<const double*>(br) + s.x_off;
     const double* y = reinterpret_cast<const double*>(br) + s.y_off;
-    lu.push_back(LutJob{x, reinterpret_cast<int*>(bd + s.lut_off), s.n, s.nlut});
-    if (s.kind == 0) ak.push_back(AkimaJob{x, y, reinterpret_cast<double4*>(bd + s.co_off), s.n});
+    if (!s.uniform) lu.push_back(LutJob{x, reinterpret_cast<int*>(bd + s.lut_off), s.n, s.nlut});
+    if (s.kind == 0) ak.push_back(AkimaJob{x, y, reinterpret_cast<Rec1*>(bd + s.co_off), s.n});
     else if (s.kind == 1)
-      cs.push_back(CsplineJob{x, y, reinterpret_cast<double4*>(bd + s.co_off),
+      cs.push_back(CsplineJob{x, y, reinterpret_cast<Rec1*>(bd + s.co_off),
                               reinterpret_cast<double*>(bd + s.scr_off), s.n});
+    else
+      ax_jobs.push_back(AxisJob{x, reinterpret_cast<AxisRec*>(bd + s.co_off), s.n});
   }
 
+  std::vector<AxisJob> ax_jobs;
+
   void jobs_f2d(const F2DPlan& f, char* br, char* bd, std::vector<AkimaJob>& ak, std::vector<CsplineJob>& cs,
-                std::vector<LutJob>& lu, std::vector<BicubicJob>& bc, int& max_nk, int& max_na) const {
+                std::vector<LutJob>& lu, std::vector<BicubicJob>& bc, int& max_nk, int& max_na) {
     jobs_s1(f.fk, br, bd, ak, cs, lu);
     jobs_s1(f.fa, br, bd, ak, cs, lu);
     jobs_s1(f.gk, br, bd, ak, cs, lu);
@@ -377,6 +399,7 @@ struct TableSet {
     std::vector<CsplineJob> cs;
     std::vector<LutJob> lu;
     std::vector<BicubicJob> bc;
+    ax_jobs.clear();
     int max_nk = 0, max_na = 0;
     for (size_t i = 0; i < nc; ++i) {
       const CosmoPlan& c = cosmos[i];
@@ -423,7 +446,8 @@ struct TableSet {
     last_h2d += nc * (sizeof(Cosmo) + sizeof(F2D)) + ntr * sizeof(Tracer);
     // upload jobs
     const size_t jb = ak.size() * sizeof(AkimaJob) + cs.size() * sizeof(CsplineJob) +
-                      lu.size() * sizeof(LutJob) + bc.size() * sizeof(BicubicJob) + 1024;
+                      lu.size() * sizeof(LutJob) + bc.size() * sizeof(BicubicJob) +
+                      ax_jobs.size() * sizeof(AxisJob) + 2048;
     if (!jobs.reserve(jb, status)) return false;
     char* q = jobs.p;
     auto up = [&](const void* src, size_t bytes) -> char* {
@@ -438,9 +462,10 @@ struct TableSet {
     CsplineJob* d_cs = (CsplineJob*)up(cs.data(), cs.size() * sizeof(CsplineJob));
     LutJob* d_lu = (LutJob*)up(lu.data(), lu.size() * sizeof(LutJob));
     BicubicJob* d_bc = (BicubicJob*)up(bc.data(), bc.size() * sizeof(BicubicJob));
-    last_h2d += jb - 1024;
-    launch_prep(d_ak, (int)ak.size(), d_cs, (int)cs.size(), d_lu, (int)lu.size(), d_bc, (int)bc.size(),
-                max_nk, max_na, stream);
+    AxisJob* d_ax = (AxisJob*)up(ax_jobs.data(), ax_jobs.size() * sizeof(AxisJob));
+    last_h2d += jb - 2048;
+    launch_prep(d_ak, (int)ak.size(), d_cs, (int)cs.size(), d_lu, (int)lu.size(), d_ax, (int)ax_jobs.size(),
+                d_bc, (int)bc.size(), max_nk, max_na, stream);
     if (!cuda_ok(cudaGetLastError(), "table preparation launch", status)) return false;
     if (!cuda_ok(cudaStreamSynchronize(stream), "table preparation", status)) return false;
     committed = true;

@@ -9,47 +9,79 @@
 
 namespace cclb {
 
-__device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
+__device__ __forceinline__ Rec1 load_rec(const Rec1* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  Rec1 r;
+  r.x0 = a.x; r.x1 = a.y; r.y = b.x; r.b = b.y; r.c = c.x; r.d = c.y;
+  return r;
+}
 
 __device__ __forceinline__ double4 ldg4(const double4* p) {
   const double2* q = reinterpret_cast<const double2*>(p);
-  double2 a = __ldg(q), b = __ldg(q + 1);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
-// gsl_interp_bsearch(x, v, 0, n-1) for x[0] <= v <= x[n-1]: largest i <= n-2 with x[i] <= v.
-__device__ __forceinline__ int find_interval(const Spline1D& s, double v) {
-  int j = (int)((v - s.x0) * s.inv_bin);
-  j = min(max(j, 0), s.nlut - 1);
-  int i = __ldg(s.lut + j);
+// Record of the interval gsl_interp_bsearch(x, v, 0, n-1) would return, for x[0] <= v <= x[n-1].
+__device__ __forceinline__ Rec1 find_rec(const Spline1D& s, double v) {
+  int i;
+  if (s.uniform) {
+    i = (int)((v - s.x0) * s.inv_step);
+  } else {
+    int j = (int)((v - s.x0) * s.inv_bin);
+    j = min(max(j, 0), s.nlut - 1);
+    i = __ldg(s.lut + j);
+  }
   const int last = s.n - 2;
-  while (i > 0 && ldg(s.x + i) > v) --i;  // bin-edge rounding
+  i = min(max(i, 0), last);
+  Rec1 r = load_rec(s.rec + i);
+  while (v < r.x0 && i > 0) r = load_rec(s.rec + (--i));
   int steps = 0;
-  while (i < last && ldg(s.x + i + 1) <= v) {
-    ++i;
-    if (++steps > 6) {  // strongly non-uniform grid: finish by bisection
-      int lo = i, hi = s.n - 1;
+  while (v >= r.x1 && i < last) {
+    if (++steps > 4) {  // strongly non-uniform grid: finish by bisection on the interval starts
+      int lo = i, hi = last + 1;
       while (hi > lo + 1) {
-        int m = (hi + lo) >> 1;
-        if (ldg(s.x + m) > v) hi = m; else lo = m;
+        const int m = (hi + lo) >> 1;  // m <= last
+        if (__ldg(&s.rec[m].x0) > v) hi = m; else lo = m;
       }
       i = lo;
+      r = load_rec(s.rec + i);
       break;
     }
+    r = load_rec(s.rec + (++i));
   }
+  return r;
+}
+
+__device__ __forceinline__ int find_axis(const Axis& s, double v, AxisRec& out) {
+  int i;
+  if (s.uniform) {
+    i = (int)((v - s.x0) * s.inv_step);
+  } else {
+    int j = (int)((v - s.x0) * s.inv_bin);
+    j = min(max(j, 0), s.nlut - 1);
+    i = __ldg(s.lut + j);
+  }
+  const int last = s.n - 2;
+  i = min(max(i, 0), last);
+  const double4* p = reinterpret_cast<const double4*>(s.rec);
+  double4 r = ldg4(p + i);
+  while (v < r.x && i > 0) r = ldg4(p + (--i));
+  while (v >= r.y && i < last) r = ldg4(p + (++i));
+  out.x0 = r.x; out.x1 = r.y; out.inv_dx = r.z;
   return i;
 }
 
-// gsl_spline_eval_e on an akima/cspline object: y_i + dx (b + dx (c + dx d)); EDOM outside.
+// gsl_spline_eval_e on an akima/cspline object; EDOM outside the node range.
 // which = 0 value, 1 first derivative, 2 second derivative (cspline_eval_deriv / _deriv2).
 __device__ __forceinline__ double spline_eval(const Spline1D& s, double v, int which, int& st) {
-  if (v < s.x0 || v > s.xn) { st |= ST_GSL_EDOM; return nan(""); }
-  const int i = find_interval(s, v);
-  const double delx = v - ldg(s.x + i);
-  const double4 c = ldg4(s.co + i);
-  if (which == 0) return c.x + delx * (c.y + delx * (c.z + delx * c.w));
-  if (which == 1) return c.y + delx * (2.0 * c.z + 3.0 * c.w * delx);
-  return 2.0 * c.z + 6.0 * c.w * delx;
+  if (!(v >= s.x0 && v <= s.xn)) { st |= ST_GSL_EDOM; return nan(""); }
+  const Rec1 r = find_rec(s, v);
+  const double delx = v - r.x0;
+  if (which == 0) return r.y + delx * (r.b + delx * (r.c + delx * r.d));
+  if (which == 1) return r.b + delx * (2.0 * r.c + 3.0 * r.d * delx);
+  return 2.0 * r.c + 6.0 * r.d * delx;
 }
 
 // ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277)
@@ -66,7 +98,7 @@ __device__ __forceinline__ double growth_factor(const Cosmo& cs, double a, int& 
   if (a > 1.) { st = ST_ERR_COMPUTECHI; return nan(""); }
   if (!cs.has_growth) { st = ST_ERR_GROWTH_INIT; return nan(""); }
   int s2 = 0;
-  double D = spline_eval(cs.growth, a, 0, s2);
+  const double D = spline_eval(cs.growth, a, 0, s2);
   if (s2) { st |= s2; return nan(""); }
   return D;
 }
@@ -75,41 +107,40 @@ __device__ __forceinline__ double growth_factor(const Cosmo& cs, double a, int& 
 // (interp2d/bicubic.c).  The bicubic Hermite patch is evaluated in tensor Hermite-basis
 // form (same polynomial as GSL's 16-coefficient expansion, ~45 fp64 instructions).
 __device__ __forceinline__ double bicubic_eval(const F2D& f, double x, double y, int which) {
-  const int xi = find_interval(f.gk, x);
-  const int yi = find_interval(f.ga, y);
-  const double xmin = ldg(f.gk.x + xi), xmax = ldg(f.gk.x + xi + 1);
-  const double ymin = ldg(f.ga.x + yi), ymax = ldg(f.ga.x + yi + 1);
+  AxisRec ax, ay;
+  const int xi = find_axis(f.gk, x, ax);
+  const int yi = find_axis(f.ga, y, ay);
   const int nk = f.gk.n;
   const double4* r0 = f.tab + (size_t)yi * nk + xi;
   const double4* r1 = r0 + nk;
   const double4 c00 = ldg4(r0), c10 = ldg4(r0 + 1);  // (xmin,ymin) (xmax,ymin)
   const double4 c01 = ldg4(r1), c11 = ldg4(r1 + 1);  // (xmin,ymax) (xmax,ymax)
-  const double dx = xmax - xmin, dy = ymax - ymin;
-  const double t = (x - xmin) / dx, u = (y - ymin) / dy;
+  const double dx = ax.x1 - ax.x0, dy = ay.x1 - ay.x0;
+  const double t = (x - ax.x0) * ax.inv_dx, u = (y - ay.x0) * ay.inv_dx;
   const double um = 1.0 - u;
-  const double u00 = (1.0 + 2.0 * u) * um * um;  // value weight, y-min edge
-  const double u01 = u * u * (3.0 - 2.0 * u);    // value weight, y-max edge
-  const double u10 = u * um * um * dy;           // slope weight, y-min edge
-  const double u11 = u * u * (u - 1.0) * dy;     // slope weight, y-max edge
+  const double u2 = u * u, um2 = um * um;
+  const double u00 = (1.0 + 2.0 * u) * um2;  // value weight, y-min edge
+  const double u01 = u2 * (3.0 - 2.0 * u);   // value weight, y-max edge
+  const double u10 = u * um2 * dy;           // slope weight, y-min edge
+  const double u11 = -u2 * um * dy;          // slope weight, y-max edge
   double t00, t01, t10, t11;
   const double tm = 1.0 - t;
   if (which == 0) {
-    t00 = (1.0 + 2.0 * t) * tm * tm;
-    t01 = t * t * (3.0 - 2.0 * t);
-    t10 = t * tm * tm * dx;
-    t11 = t * t * (t - 1.0) * dx;
+    const double t2 = t * t, tm2 = tm * tm;
+    t00 = (1.0 + 2.0 * t) * tm2;
+    t01 = t2 * (3.0 - 2.0 * t);
+    t10 = t * tm2 * dx;
+    t11 = -t2 * tm * dx;
   } else if (which == 1) {
-    const double idx = 1.0 / dx;
-    t00 = 6.0 * t * (t - 1.0) * idx;
+    t00 = 6.0 * t * (t - 1.0) * ax.inv_dx;
     t01 = -t00;
     t10 = (3.0 * t * t - 4.0 * t + 1.0);
     t11 = (3.0 * t * t - 2.0 * t);
   } else {
-    const double idx = 1.0 / dx;
-    t00 = (12.0 * t - 6.0) * idx * idx;
+    t00 = (12.0 * t - 6.0) * ax.inv_dx * ax.inv_dx;
     t01 = -t00;
-    t10 = (6.0 * t - 4.0) * idx;
-    t11 = (6.0 * t - 2.0) * idx;
+    t10 = (6.0 * t - 4.0) * ax.inv_dx;
+    t11 = (6.0 * t - 2.0) * ax.inv_dx;
   }
   // y-direction Hermite interpolation of value (p) and x-slope (q) on both x edges
   const double p0 = u00 * c00.x + u01 * c01.x + u10 * c00.z + u11 * c01.z;
@@ -119,7 +150,7 @@ __device__ __forceinline__ double bicubic_eval(const F2D& f, double x, double y,
   return t00 * p0 + t01 * p1 + t10 * q0 + t11 * q1;
 }
 
-// ccl_f2d_t_eval (src/ccl_f2d.c:203-373)
+// ccl_f2d_t_eval (src/ccl_f2d.c:203-373), every branch.
 __device__ __noinline__ double f2d_eval(const F2D& f, double lk, double a, const Cosmo* cs, int& st) {
   bool is_hiz = false, is_loz = false;
   double a_ev = a;
@@ -142,7 +173,7 @@ __device__ __noinline__ double f2d_eval(const F2D& f, double lk, double a, const
     if (is_hik) lk_ev = f.lkmax;
     else if (is_lok) lk_ev = f.lkmin;
   }
-  double pre;
+  double pre = 0.0;
   int sp = 0;
   if (f.is_factorizable) {
     double fk = f.is_log ? 0. : 1., fa = f.is_log ? 0. : 1.;
@@ -186,6 +217,16 @@ __device__ __noinline__ double f2d_eval(const F2D& f, double lk, double a, const
   return post;
 }
 
+// P(k,a) with the in-range bicubic case inlined (what the Limber path hits on default tables:
+// ln k never leaves the table, a < amin only for z > 99), everything else through f2d_eval.
+__device__ __forceinline__ double psp_eval(const F2D& f, double lk, double a, const Cosmo* cs, int& st) {
+  if (f.has_fka && lk >= f.lkmin && lk <= f.lkmax && a >= f.amin && a <= f.amax) {
+    const double z = bicubic_eval(f, lk, a, 0);
+    return f.is_log ? exp(z) : z;
+  }
+  return f2d_eval(f, lk, a, cs, st);
+}
+
 // ccl_cl_tracer_t_get_f_ell (src/ccl_tracers.c:703-726)
 __device__ __forceinline__ double tracer_f_ell(int der_angles, double ell) {
   if (der_angles == 1) return ell * (ell + 1.);
@@ -209,10 +250,20 @@ __device__ __forceinline__ double tracer_kernel(const Tracer& tr, double chi) {
   return spline_eval(tr.kernel, chi, 0, st);
 }
 
-// ccl_cl_tracer_t_get_transfer (src/ccl_tracers.c:739-749)
+// ccl_cl_tracer_t_get_transfer (src/ccl_tracers.c:739-749); the a-only factorised transfer
+// (galaxy bias, IA amplitude, growth rate) is the common case and is inlined.
 __device__ __forceinline__ double tracer_transfer(const Tracer& tr, double lk, double a, int& st) {
   if (!tr.has_transfer) return 1;
-  return f2d_eval(tr.transfer, lk, a, nullptr, st);
+  const F2D& f = tr.transfer;
+  if (f.is_factorizable && !f.has_fk && f.has_fa && !f.is_log) {
+    // constant in k, clamped in a (growth_factor_0 = 1, exponent 0: src/ccl_tracers.c:670-684)
+    const double a_ev = fmin(fmax(a, f.amin), f.amax);
+    int sp = 0;
+    const double v = spline_eval(f.fa, a_ev, 0, sp);
+    if (sp) { st = ST_ERR_SPLINE_EV; return nan(""); }
+    return v;
+  }
+  return f2d_eval(f, lk, a, nullptr, st);
 }
 
 struct TaskCtx {
@@ -224,9 +275,22 @@ struct TaskCtx {
   double l;
 };
 
-// transfer_limber_single + transfer_limber_wrap (src/ccl_cls.c:102-164)
-__device__ __forceinline__ double transfer_limber_wrap(const TaskCtx& c, const Tracer* trs, int n, double lk,
-                                                       double k, double chi, double a, int& st) {
+constexpr int MAX_SUB = 8;  // sub-tracers per collection whose prefactors are hoisted
+
+__device__ __forceinline__ double tracer_prefactor(const Tracer& tr, double l) {
+  double p = tracer_f_ell(tr.der_angles, l);
+  if (tr.der_bessel == -1) {
+    const double lp1h = l + 0.5;
+    p /= (lp1h * lp1h);
+  }
+  return p;
+}
+
+// transfer_limber_single + transfer_limber_wrap (src/ccl_cls.c:102-164).
+// pref[itr] = f_ell (/ (l+1/2)^2 when der_bessel == -1), hoisted out of the node loop.
+__device__ __forceinline__ double transfer_limber_wrap(const TaskCtx& c, const Tracer* trs, int n,
+                                                       const double* pref, double lk, double k, double chi,
+                                                       double a, int& st) {
   double transfer = 0;
   const double l = c.l;
   for (int itr = 0; itr < n; ++itr) {
@@ -234,43 +298,44 @@ __device__ __forceinline__ double transfer_limber_wrap(const TaskCtx& c, const T
     double dd;
     const double w = tracer_kernel(tr, chi);
     const double t = tracer_transfer(tr, lk, a, st);
-    const double fl = tracer_f_ell(tr.der_angles, l);
     if (tr.der_bessel < 1) {
       dd = w * t;
-      if (tr.der_bessel == -1) {
-        const double lp1h = l + 0.5;
-        dd /= (lp1h * lp1h);
-      }
     } else {
       const double lp1h = l + 0.5;
       const double lp3h = l + 1.5;
       const double chi_lp = lp3h / k;
       const double a_lp = scale_factor_of_chi(*c.cs, chi_lp, st);
       const double pk_ratio =
-          fabs(f2d_eval(*c.cs->psp, lk, a_lp, c.cs, st) / f2d_eval(*c.cs->psp, lk, a, c.cs, st));
+          fabs(psp_eval(*c.cs->psp, lk, a_lp, c.cs, st) / psp_eval(*c.cs->psp, lk, a, c.cs, st));
       const double w_p = tracer_kernel(tr, chi_lp);
       const double t_p = tracer_transfer(tr, lk, a_lp, st);
       const double sqell = sqrt(lp1h * pk_ratio / lp3h);
       if (tr.der_bessel == 1) dd = l * w * t / lp1h - sqell * w_p * t_p;
       else dd = sqell * 2 * w_p * t_p / lp3h - (0.25 + 2 * l) * w * t / (lp1h * lp1h);
     }
-    transfer += dd * fl;
+    transfer += dd * (itr < MAX_SUB ? pref[itr] : tracer_prefactor(tr, l));
     if (st != 0) return -1;
   }
   return transfer;
 }
 
-// cl_integrand (src/ccl_cls.c:166-187)
-__device__ __forceinline__ double cl_integrand(const TaskCtx& c, double lk, int& st) {
+// cl_integrand (src/ccl_cls.c:166-187) with k = exp(lk) and chi = (l+1/2)/k supplied by the caller
+__device__ __forceinline__ double cl_integrand_kchi(const TaskCtx& c, const double* pref1, const double* pref2,
+                                                    double lk, double k, double chi, int& st) {
+  const double a = scale_factor_of_chi(*c.cs, chi, st);
+  const double d1 = transfer_limber_wrap(c, c.t1, c.n1, pref1, lk, k, chi, a, st);
+  if (d1 == 0) return 0;
+  const double d2 = c.same ? d1 : transfer_limber_wrap(c, c.t2, c.n2, pref2, lk, k, chi, a, st);
+  if (d2 == 0) return 0;
+  const double pk = psp_eval(*c.cs->psp, lk, a, c.cs, st);
+  return k * pk * d1 * d2;
+}
+
+__device__ __forceinline__ double cl_integrand(const TaskCtx& c, const double* pref1, const double* pref2,
+                                               double lk, int& st) {
   const double k = exp(lk);
   const double chi = (c.l + 0.5) / k;
-  const double a = scale_factor_of_chi(*c.cs, chi, st);
-  const double d1 = transfer_limber_wrap(c, c.t1, c.n1, lk, k, chi, a, st);
-  if (d1 == 0) return 0;
-  const double d2 = c.same ? d1 : transfer_limber_wrap(c, c.t2, c.n2, lk, k, chi, a, st);
-  if (d2 == 0) return 0;
-  const double pk = f2d_eval(*c.cs->psp, lk, a, c.cs, st);
-  return k * pk * d1 * d2;
+  return cl_integrand_kchi(c, pref1, pref2, lk, k, chi, st);
 }
 
 // get_k_interval (src/ccl_cls.c:64-100)

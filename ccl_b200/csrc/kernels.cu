@@ -52,7 +52,7 @@ __global__ void akima_coef_kernel(const AkimaJob* jobs) {
       c = (3.0 * m0 - 2.0 * b - tL_ip1) / h_i;
       d = (b + tL_ip1 - 2.0 * m0) / (h_i * h_i);
     }
-    jb.co[i] = make_double4(y[i], b, c, d);
+    jb.rec[i] = Rec1{x[i], x[i + 1], y[i], b, c, d};
   }
 }
 
@@ -71,6 +71,15 @@ __global__ void lut_kernel(const LutJob* jobs) {
     // guard against rounding of x0 + j*bin: never start past the true interval
     while (lo > 0 && jb.x[lo] > v) --lo;
     jb.lut[j] = lo;
+  }
+}
+
+// Bicubic axis records {x_i, x_{i+1}, 1/(x_{i+1}-x_i)}.
+__global__ void axis_kernel(const AxisJob* jobs) {
+  const AxisJob jb = jobs[blockIdx.x];
+  for (int i = threadIdx.x; i < jb.n - 1; i += blockDim.x) {
+    const double x0 = jb.x[i], x1 = jb.x[i + 1];
+    jb.rec[i] = AxisRec{x0, x1, 1.0 / (x1 - x0), 0.0};
   }
 }
 
@@ -185,7 +194,7 @@ __global__ void cspline_coef_kernel(const CsplineJob* jobs, int njobs) {
     const double dy = y[i + 1] - y[i];
     const double b = (dy / dx) - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
     const double d = (c[i + 1] - c[i]) / (3.0 * dx);
-    jb.co[i] = make_double4(y[i], b, c[i], d);
+    jb.rec[i] = Rec1{x[i], x[i + 1], y[i], b, c[i], d};
   }
 }
 
@@ -232,10 +241,11 @@ __global__ void bicubic_deriv_kernel(const BicubicJob* jobs, int pass) {
 }
 
 void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs, const LutJob* d_lut,
-                 int nlut, const BicubicJob* d_bc, int nbc, int max_nk, int max_na,
-                 cudaStream_t stream) {
+                 int nlut, const AxisJob* d_ax, int nax, const BicubicJob* d_bc, int nbc, int max_nk,
+                 int max_na, cudaStream_t stream) {
   if (nak > 0) akima_coef_kernel<<<nak, 128, 0, stream>>>(d_ak);
   if (nlut > 0) lut_kernel<<<nlut, 128, 0, stream>>>(d_lut);
+  if (nax > 0) axis_kernel<<<nax, 128, 0, stream>>>(d_ax);
   if (ncs > 0) cspline_coef_kernel<<<(ncs + 63) / 64, 64, 0, stream>>>(d_cs, ncs);
   if (nbc > 0) {
     bicubic_factor_kernel<<<nbc, 256, 0, stream>>>(d_bc);
@@ -309,6 +319,11 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+__device__ __forceinline__ int warp_first_nonzero(int st) {
+  const unsigned bad = __ballot_sync(0xffffffffu, st != 0);
+  return bad ? __shfl_sync(0xffffffffu, st, __ffs(bad) - 1) : 0;
+}
+
 __device__ __forceinline__ bool setup_task(const LimberProblem& P, long long task, TaskCtx& c, int& ic,
                                            int& ip, int& il) {
   il = (int)(task % P.nl);
@@ -328,6 +343,15 @@ __device__ __forceinline__ bool setup_task(const LimberProblem& P, long long tas
   return true;
 }
 
+// per-warp prefactor table: f_ell (/ (l+1/2)^2) of the first MAX_SUB sub-tracers of each side
+__device__ __forceinline__ void setup_prefactors(const TaskCtx& c, double* pref, int lane) {
+  if (lane < MAX_SUB) {
+    if (lane < c.n1) pref[lane] = tracer_prefactor(c.t1[lane], c.l);
+    if (lane < c.n2) pref[MAX_SUB + lane] = tracer_prefactor(c.t2[lane], c.l);
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void finish_task(const LimberProblem& P, int ic, int ip, int il, double result,
                                             int st, int lane) {
   if (lane != 0) return;
@@ -342,12 +366,26 @@ __device__ __forceinline__ void finish_task(const LimberProblem& P, int ic, int 
   }
 }
 
-// integ_cls_limber_spline (src/ccl_cls.c:189-225) + ccl_integ_spline/akima_eval_integ.
+// integ_cls_limber_spline (src/ccl_cls.c:189-225) + ccl_integ_spline / akima_eval_integ
+// (src/ccl_utils.c:274-345, gsl interpolation/akima.c).
+//
+// Node abscissae: lk_s = lkmin + dx*s (ccl_linear_spacing, ends overwritten).  k_s = exp(lk_s) is
+// advanced per lane by the constant ratio exp(32 dx) (one exp per lane per C_ell instead of one
+// per node; relative drift <= 22 steps * 2 ulp), chi_s = (l+1/2)/k_s by the inverse ratio.
+//
+// Akima integral on the (uniform) node grid.  With m_i the slopes, b_i the left-node derivative
+// and tL_{i+1} the right-node derivative GSL assigns to interval i, its cubic integrates to
+//     h (y_i + y_{i+1})/2 + h^2 (b_i - tL_{i+1}) / 12            (c = d = 0 when NE_i == 0),
+// and for NE != 0 both b_i and tL_i equal the same Akima node derivative t_i, so the correction
+// telescopes to t_0 - t_{n-1} unless some NE vanishes (exact ties, e.g. stretches of zeros), in
+// which case the per-interval form is evaluated.  Same polynomial as akima_eval_integ; only the
+// association of the sum differs (<= 1e-15 relative).
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 limber_spline_kernel(const LimberProblem P, long long ntasks) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sf = smem + (size_t)warp * P.par.nk_cap;
+  double* sf = smem + (size_t)warp * (P.par.nk_cap + 2 * MAX_SUB);
+  double* pref = sf + P.par.nk_cap;
   const long long task = (long long)blockIdx.x * WARPS_PER_CTA + warp;
   if (task >= ntasks) return;
   TaskCtx c;
@@ -366,74 +404,84 @@ limber_spline_kernel(const LimberProblem P, long long ntasks) {
     finish_task(P, ic, ip, il, 0.0, ST_ERR_MEMORY, lane);
     return;
   }
+  setup_prefactors(c, pref, lane);
   // ccl_linear_spacing (src/ccl_utils.c:17-37)
   const double dx = (lkmax - lkmin) / (nk - 1.);
-  auto node = [&](int i) -> double {
-    return (i == 0) ? lkmin : ((i == nk - 1) ? lkmax : lkmin + dx * i);
-  };
+  const double lp1h = c.l + 0.5;
+  double k = exp(lkmin + dx * lane);
+  double chi = lp1h / k;
+  const double ratio = exp(32.0 * dx);
+  const double iratio = 1.0 / ratio;
   int st = 0;
   for (int s = lane; s < nk; s += 32) {
+    const double lk = (s == 0) ? lkmin : ((s == nk - 1) ? lkmax : lkmin + dx * s);
     int s1 = 0;
-    sf[s] = cl_integrand(c, node(s), s1);
+    sf[s] = cl_integrand_kchi(c, pref, pref + MAX_SUB, lk, k, chi, s1);
     if (s1 && !st) st = s1;
+    k *= ratio;
+    chi *= iratio;
   }
-  // any failing node fails the C_ell
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const int other = __shfl_xor_sync(0xffffffffu, st, o);
-    if (!st) st = other;
-  }
+  st = warp_first_nonzero(st);  // any failing node fails the C_ell
   __syncwarp();
   if (st) {
     finish_task(P, ic, ip, il, 0.0, st, lane);
     return;
   }
-  // Akima spline of the samples, integrated over [lk_0, lk_{nk-1}]
-  auto raw = [&](int q) -> double { return (sf[q + 1] - sf[q]) / (node(q + 1) - node(q)); };
-  auto slope = [&](int j) -> double {
+  // ---- Akima integral ----
+  // node spacing: interior nodes are lkmin + dx*s; the two end intervals use the overwritten ends
+  const double inv_dx = 1.0 / dx;
+  auto slope = [&](int j) -> double {  // m_j for j in [-2, nk]
+    auto raw = [&](int q) -> double {
+      if (q == nk - 2) return (sf[q + 1] - sf[q]) / (lkmax - (lkmin + dx * q));
+      return (sf[q + 1] - sf[q]) * inv_dx;
+    };
     if (j >= 0 && j <= nk - 2) return raw(j);
     if (j == -1) return 2.0 * raw(0) - raw(1);
     if (j == -2) return 3.0 * raw(0) - 2.0 * raw(1);
     if (j == nk - 1) return 2.0 * raw(nk - 2) - raw(nk - 3);
     return 3.0 * raw(nk - 2) - 2.0 * raw(nk - 3);
   };
-  double acc = 0.0;
-  for (int i = lane; i < nk - 1; i += 32) {
-    const double mm2 = slope(i - 2), mm1 = slope(i - 1), m0 = slope(i), mp1 = slope(i + 1),
-                 mp2 = slope(i + 2);
-    const double x_lo = node(i), x_hi = node(i + 1);
-    const double h = x_hi - x_lo;
+  // pass 1: trapezoid sum and tie detection (NE_j == 0 at any node j in [0, nk-1])
+  double trap = 0.0;
+  bool tie = false;
+  for (int j = lane; j < nk; j += 32) {
+    const double mm2 = slope(j - 2), mm1 = slope(j - 1), m0 = slope(j), mp1 = slope(j + 1);
     const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
-    double b, cc, d;
-    if (NE == 0.0) {
-      b = m0; cc = 0.0; d = 0.0;
-    } else {
-      const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
-      const double alpha_i = fabs(mm1 - mm2) / NE;
-      double tL;
-      if (NE_next == 0.0) tL = m0;
-      else {
-        const double alpha_ip1 = fabs(m0 - mm1) / NE_next;
-        tL = (1.0 - alpha_ip1) * m0 + alpha_ip1 * mp1;
-      }
-      b = (1.0 - alpha_i) * mm1 + alpha_i * m0;
-      cc = (3.0 * m0 - 2.0 * b - tL) / h;
-      d = (b + tL - 2.0 * m0) / (h * h);
-    }
-    const double y_lo = sf[i];
-    if (i == 0 || i == nk - 2) {
-      // integ_eval(y_lo, b, c, d, x_lo, x_lo, x_hi) (interpolation/integ_eval.h)
-      const double r1 = 0.0, r2 = x_hi - x_lo;
-      const double r12 = r1 + r2;
-      const double bterm = 0.5 * b * r12;
-      const double cterm = (1.0 / 3.0) * cc * (r1 * r1 + r2 * r2 + r1 * r2);
-      const double dterm = 0.25 * d * r12 * (r1 * r1 + r2 * r2);
-      acc += (x_hi - x_lo) * (y_lo + bterm + cterm + dterm);
-    } else {
-      acc += h * (y_lo + h * (0.5 * b + h * (cc / 3.0 + 0.25 * d * h)));
+    tie = tie || (NE == 0.0);
+    if (j < nk - 1) {
+      const double h = (j == nk - 2) ? (lkmax - (lkmin + dx * j)) : dx;
+      trap += 0.5 * h * (sf[j] + sf[j + 1]);
     }
   }
-  acc = warp_sum(acc);
+  const bool any_tie = __any_sync(0xffffffffu, tie);
+  auto node_deriv = [&](int j, bool from_left) -> double {
+    // Akima derivative at node j as used by interval j (b_j, from_left = false) or by interval
+    // j-1 (tL_j, from_left = true); they differ only in GSL's NE == 0 rule.
+    const double mm2 = slope(j - 2), mm1 = slope(j - 1), m0 = slope(j), mp1 = slope(j + 1);
+    const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
+    if (NE == 0.0) return from_left ? mm1 : m0;
+    const double alpha = fabs(mm1 - mm2) / NE;
+    return (1.0 - alpha) * mm1 + alpha * m0;
+  };
+  double corr = 0.0;
+  if (!any_tie) {
+    if (lane == 0) {
+      const double h0 = dx, hl = lkmax - (lkmin + dx * (nk - 2));
+      // sum_i h_i^2 (t_i - t_{i+1}) with h uniform except the last interval
+      corr = h0 * h0 * (node_deriv(0, false) - node_deriv(nk - 2, true)) +
+             hl * hl * (node_deriv(nk - 2, false) - node_deriv(nk - 1, true));
+    }
+  } else {
+    for (int i = lane; i < nk - 1; i += 32) {
+      const double mm2 = slope(i - 2), mm1 = slope(i - 1), m0 = slope(i), mp1 = slope(i + 1);
+      const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
+      if (NE != 0.0) {
+        const double h = (i == nk - 2) ? (lkmax - (lkmin + dx * i)) : dx;
+        corr += h * h * (node_deriv(i, false) - node_deriv(i + 1, true));
+      }
+    }
+  }
+  const double acc = warp_sum(trap + corr * (1.0 / 12.0));
   finish_task(P, ic, ip, il, acc, 0, lane);
 }
 
@@ -461,9 +509,9 @@ __device__ __forceinline__ double rescale_error(double err, double result_abs, d
 // abscissae are spread over the warp's lanes, the four sums are shuffle-reduced.
 // fv: per-warp shared buffer of 2*41 doubles.
 template <int NP>
-__device__ __forceinline__ void qk41_warp(const TaskCtx& c, const double* pa, const double* pb, double* fv,
-                                          int lane, double* result, double* abserr, double* resabs,
-                                          double* resasc, int& st) {
+__device__ __forceinline__ void qk41_warp(const TaskCtx& c, const double* pref, const double* pa,
+                                          const double* pb, double* fv, int lane, double* result,
+                                          double* abserr, double* resabs, double* resasc, int& st) {
   // evaluation e in [0, 41): e<20 -> center - h*xgk[e]; 20<=e<40 -> center + h*xgk[e-20]; 40 -> center
   for (int e = lane; e < 41 * NP; e += 32) {
     const int p = e / 41, q = e - p * 41;
@@ -474,19 +522,10 @@ __device__ __forceinline__ void qk41_warp(const TaskCtx& c, const double* pa, co
     else if (q < 20) xq = center - half_length * c_xgk[q];
     else xq = center + half_length * c_xgk[q - 20];
     int s1 = 0;
-    fv[e] = cl_integrand(c, xq, s1);
+    fv[e] = cl_integrand(c, pref, pref + MAX_SUB, xq, s1);
     if (s1 && !st) st = s1;
   }
-  // every lane leaves with the same status word (first failing lane wins)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const int other = __shfl_xor_sync(0xffffffffu, st, o);
-    if (!st) st = other;
-  }
-  {
-    const unsigned bad = __ballot_sync(0xffffffffu, st != 0);
-    if (bad) st = __shfl_sync(0xffffffffu, st, __ffs(bad) - 1);
-  }
+  st = warp_first_nonzero(st);  // every lane leaves with the same status word
   __syncwarp();
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
@@ -539,6 +578,7 @@ __device__ __forceinline__ bool subinterval_too_small(double a1, double a2, doub
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned long long* next_task) {
   __shared__ double s_fv[WARPS_PER_CTA][2 * 41];
+  __shared__ double s_pref[WARPS_PER_CTA][2 * MAX_SUB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int limit = P.par.N_ITERATION;
   double* alist = ws + ((size_t)blockIdx.x * WARPS_PER_CTA + warp) * 4 * (size_t)limit;
@@ -546,6 +586,7 @@ limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned 
   double* rlist = blist + limit;
   double* elist = rlist + limit;
   double* fv = s_fv[warp];
+  double* pref = s_pref[warp];
   for (;;) {
     unsigned long long t = 0;
     if (lane == 0) t = atomicAdd(next_task, 1ull);
@@ -560,6 +601,8 @@ limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned 
     }
     double lkmin, lkmax;
     get_k_interval(c, P.par, lkmin, lkmax);
+    __syncwarp();
+    setup_prefactors(c, pref, lane);
     const double epsabs = 0.0, epsrel = P.par.LIMBER_EPSREL;
     int st = 0, gsl = 0;
     unsigned long long nev = 41;
@@ -569,7 +612,7 @@ limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned 
     } else {
       double r0[1], e0[1], ab0[1], as0[1];
       const double pa0[1] = {lkmin}, pb0[1] = {lkmax};
-      qk41_warp<1>(c, pa0, pb0, fv, lane, r0, e0, ab0, as0, st);
+      qk41_warp<1>(c, pref, pa0, pb0, fv, lane, r0, e0, ab0, as0, st);
       double tolerance = fmax(epsabs, epsrel * fabs(r0[0]));
       const double round_off = 50 * DBL_EPSILON * ab0[0];
       result = r0[0];
@@ -600,7 +643,7 @@ limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned 
           const double a1 = a_i, b1 = 0.5 * (a_i + b_i), a2 = b1, b2 = b_i;
           double ar[2], er[2], rab[2], ras[2];
           const double pa[2] = {a1, a2}, pb[2] = {b1, b2};
-          qk41_warp<2>(c, pa, pb, fv, lane, ar, er, rab, ras, st);
+          qk41_warp<2>(c, pref, pa, pb, fv, lane, ar, er, rab, ras, st);
           nev += 82;
           const double area12 = ar[0] + ar[1];
           const double error12 = er[0] + er[1];
@@ -713,7 +756,7 @@ cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws,
   const long long ntasks = (long long)prob.ncosmo * prob.npair * prob.nl;
   if (ntasks == 0) return cudaSuccess;
   if (method == INTEG_SPLINE) {
-    const size_t smem = (size_t)WARPS_PER_CTA * prob.par.nk_cap * sizeof(double);
+    const size_t smem = (size_t)WARPS_PER_CTA * (prob.par.nk_cap + 2 * MAX_SUB) * sizeof(double);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(limber_spline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -7,9 +7,9 @@
 //   ccl_f2d_t                          -> F2D        (include/ccl_f2d.h:29-44)
 //   ccl_cl_tracer_t                    -> Tracer     (include/ccl_tracers.h:15-22)
 //   ccl_cosmology (a(chi), growth)     -> Cosmo      (include/ccl_core.h:260)
-// Spline polynomial coefficients are precomputed per interval as one 32-byte record
-// {y_i, b_i, c_i, d_i} so that an evaluation is one index search plus one aligned
-// 2 x fp64x2 load; the bicubic P(k,a) keeps {z, zx, zy, zxy} interleaved per node.
+// Spline polynomial coefficients are precomputed per interval as one 48-byte record
+// {x_i, x_{i+1}, y_i, b_i, c_i, d_i} so that an evaluation is one index guess plus three
+// fp64x2 loads; the bicubic P(k,a) keeps {z, zx, zy, zxy} interleaved per node (32 bytes).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -39,19 +39,38 @@ enum : int {
 enum : int { GROWTH_CCL = 401, GROWTH_CONST = 403, GROWTH_NONE = 404 };  // include/ccl_f2d.h:13-18
 enum : int { INTEG_QAG = 500, INTEG_SPLINE = 501 };                      // include/ccl_utils.h:12-15
 
-// One piecewise-cubic 1-D interpolant with GSL's interval convention
-// (x_i <= x < x_{i+1}, last interval closed).  `lut` maps nlut uniform bins of
-// [x[0], x[n-1]] to the interval holding the bin's left edge, so a lookup is one LUT
-// load plus a short forward scan instead of a log2(n)-step binary search.
+// One interval of a piecewise-cubic 1-D interpolant: p(x) = y + dx (b + dx (c + dx d)),
+// dx = x - x0, valid for x0 <= x < x1 (GSL's interval convention; last interval closed).
+// The interval's own end points travel with the coefficients so that a lookup is ONE 48-byte
+// record fetch: the index guess is verified against (x0, x1) without touching a node array.
+struct __align__(16) Rec1 {
+  double x0, x1, y, b, c, d;
+};
+
+// One cell edge of a bicubic axis: node, next node, 1 / spacing.
+struct __align__(32) AxisRec {
+  double x0, x1, inv_dx, pad;
+};
+
+// Index guess for a strictly increasing grid of n nodes:
+//   uniform != 0 : i = (x - x0) * inv_step        (grid is uniform to within +-1 interval)
+//   uniform == 0 : i = lut[(x - x0) * inv_bin]    (nlut uniform bins -> interval of left edge)
+// followed by a +-1 walk on the records until x0 <= x < x1, which reproduces
+// gsl_interp_bsearch exactly for any grid.
 struct Spline1D {
-  const double* x;    // [n] nodes, strictly increasing
-  const double4* co;  // [n-1] {y_i, b_i, c_i, d_i}
-  const int* lut;     // [nlut]
-  int n;
-  int nlut;
-  double x0;       // x[0]
-  double xn;       // x[n-1]
-  double inv_bin;  // nlut / (xn - x0)
+  const Rec1* rec;  // [n-1]
+  const int* lut;   // [nlut] (unused when uniform)
+  int n, nlut, uniform, pad;
+  double x0, xn;     // x[0], x[n-1]
+  double inv_step;   // (n-1)/(xn-x0)
+  double inv_bin;    // nlut/(xn-x0)
+};
+
+struct Axis {
+  const AxisRec* rec;  // [n-1]
+  const int* lut;
+  int n, nlut, uniform, pad;
+  double x0, xn, inv_step, inv_bin;
 };
 
 struct F2D {
@@ -64,8 +83,8 @@ struct F2D {
   Spline1D fa;  // natural cspline in a   (factorised form)
   // bicubic form: tab[ia*nk + ik] = {z, dz/dlnk, dz/da, d2z/dlnk da} (GSL zx, zy, zxy)
   const double4* tab;
-  Spline1D gk;  // node array + LUT of the ln k axis (co unused)
-  Spline1D ga;  // node array + LUT of the a axis    (co unused)
+  Axis gk;  // ln k axis
+  Axis ga;  // a axis
 };
 
 struct Tracer {
@@ -106,9 +125,10 @@ struct LimberProblem {
 };
 
 // ---- table-preparation jobs (device kernels fill the derived regions of the arena) ----
-struct AkimaJob { const double* x; const double* y; double4* co; int n; };
-struct CsplineJob { const double* x; const double* y; double4* co; double* scratch; int n; };
+struct AkimaJob { const double* x; const double* y; Rec1* rec; int n; };
+struct CsplineJob { const double* x; const double* y; Rec1* rec; double* scratch; int n; };
 struct LutJob { const double* x; int* lut; int n; int nlut; };
+struct AxisJob { const double* x; AxisRec* rec; int n; };
 struct BicubicJob {
   const double* xk;  // [nk]
   const double* ya;  // [na]
@@ -120,8 +140,8 @@ struct BicubicJob {
 
 // launchers (kernels.cu)
 void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs, const LutJob* d_lut,
-                 int nlut, const BicubicJob* d_bc, int nbc, int max_nk, int max_na,
-                 cudaStream_t stream);
+                 int nlut, const AxisJob* d_ax, int nax, const BicubicJob* d_bc, int nbc, int max_nk,
+                 int max_na, cudaStream_t stream);
 cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws, size_t qag_ws_bytes,
                           cudaStream_t stream);
 size_t limber_qag_workspace_bytes(int n_iteration);
