@@ -1,0 +1,71 @@
+"""Multi-GPU sharding of the Limber path.
+
+Every (cosmology, pair, ell) is independent: there is no halo and no reduction.  A batch is
+partitioned by cosmology into contiguous blocks, one process per GPU computes its block, and
+the C_ell blocks are assembled on the caller's rank with ONE collective (a gather).  For a
+single cosmology with many pairs (BASELINE configs[4]) the pair x ell-tile list is partitioned
+instead, balanced on the number of integrand nodes because nk varies 17..600 per C_ell.
+
+The reference has no counterpart (it is single-process OpenMP over ell, src/ccl_cls.c:282-356).
+"""
+import numpy as np
+
+
+def shard_range(n, world, rank):
+    """Contiguous block of `n` items owned by `rank`: (offset, count); remainder to the first ranks."""
+    base, rem = divmod(int(n), int(world))
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n, world):
+    return [shard_range(n, world, r)[1] for r in range(world)]
+
+
+def balance_tiles(weights, world):
+    """Longest-processing-time partition of tiles with the given weights (integrand nodes).
+
+    Returns a list of index arrays, one per rank; deterministic (ties broken by tile index)."""
+    w = np.asarray(weights, dtype=np.float64)
+    order = np.lexsort((np.arange(w.size), -w))
+    load = np.zeros(world)
+    owner = np.empty(w.size, dtype=np.int64)
+    for t in order:
+        r = int(np.argmin(load))
+        owner[t] = r
+        load[r] += w[t]
+    return [np.flatnonzero(owner == r) for r in range(world)]
+
+
+def gather_blocks(local, sizes, dst=0, group=None):
+    """Assemble per-rank blocks [sizes[r], ...] on rank `dst` with one collective.
+
+    Equal-sized shards use one gather (NCCL over NVLink on GPU tensors, gloo on CPU tensors);
+    ragged shards use grouped point-to-point transfers into the preallocated output.
+    Returns the concatenated tensor on `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    assert len(sizes) == world and local.shape[0] == sizes[rank]
+    tail = tuple(local.shape[1:])
+    out = None
+    if rank == dst:
+        out = torch.empty((int(sum(sizes)),) + tail, dtype=local.dtype, device=local.device)
+    if len(set(sizes)) == 1:
+        views = None
+        if rank == dst:
+            views = list(out.split(sizes[0], dim=0))
+        dist.gather(local.contiguous(), views, dst=dst, group=group)
+        return out
+    if rank == dst:
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        out[offs[dst]:offs[dst + 1]].copy_(local)
+        reqs = [dist.irecv(out[offs[r]:offs[r + 1]], src=r, group=group)
+                for r in range(world) if r != dst and sizes[r] > 0]
+        for q in reqs:
+            q.wait()
+        return out
+    if sizes[rank] > 0:
+        dist.send(local.contiguous(), dst=dst, group=group)
+    return None

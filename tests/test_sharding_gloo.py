@@ -1,0 +1,74 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes shard a batch by cosmology and assemble
+the C_ell blocks on rank 0 with one gather (ccl_b200/sharding.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ccl_b200 import sharding
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ncosmo, npair, nl, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        off, cnt = sharding.shard_range(ncosmo, world, rank)
+        # stand-in for the device result of this rank's block: value encodes (cosmology, pair, ell)
+        ic = torch.arange(off, off + cnt, dtype=torch.float64)[:, None, None]
+        ip = torch.arange(npair, dtype=torch.float64)[None, :, None]
+        il = torch.arange(nl, dtype=torch.float64)[None, None, :]
+        local = ic * 1e6 + ip * 1e3 + il
+        out = sharding.gather_blocks(local, sharding.shard_sizes(ncosmo, world), dst=0)
+        if rank == 0:
+            q.put(out.numpy())
+        else:
+            assert out is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ncosmo", [8, 7])   # equal shards -> one gather; ragged -> send/recv
+def test_gather_by_cosmology_world2(ncosmo):
+    world, npair, nl = 2, 6, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ncosmo, npair, nl, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ic, ip, il = np.meshgrid(np.arange(ncosmo), np.arange(npair), np.arange(nl), indexing="ij")
+    assert got.shape == (ncosmo, npair, nl)
+    assert np.array_equal(got, ic * 1e6 + ip * 1e3 + il)
+
+
+def test_shard_ranges_cover_exactly():
+    for n in (0, 1, 7, 4096, 4099):
+        for world in (1, 2, 4, 8):
+            spans = [sharding.shard_range(n, world, r) for r in range(world)]
+            assert sum(c for _, c in spans) == n
+            assert all(spans[r][0] + spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_balance_tiles_on_nodes():
+    rng = np.random.default_rng(0)
+    w = rng.integers(17, 600, size=2100)          # nk per (pair, ell-tile), SURVEY 8e
+    parts = sharding.balance_tiles(w, 8)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(w.size))
+    loads = np.array([w[p].sum() for p in parts])
+    assert loads.max() / loads.mean() < 1.01
