@@ -286,13 +286,15 @@ def main():
     value = n_cl_total / (ms_per_step * 1e-3)
     n_fail = int((d_st[0] != 0).sum().item())
 
+    fast_path = args.method == "spline" and batch.last_used_fast_path
     # ---- fp64 roofline of the dominant kernel (this rank's launch) ----
     st = C.c_int(0)
     peak = _lib.load().ccl_b200_measure_fp64_peak(C.byref(st))
     achieved = flops / (kern_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak and peak > 0 else None, "traffic": None,
-                "kernel": "limber_spline_kernel" if args.method == "spline" else "limber_qag_kernel",
+                "kernel": ("limber_spline_fast_kernel" if batch.last_used_fast_path else "limber_spline_kernel")
+                if args.method == "spline" else "limber_qag_kernel",
                 "kernel_ms": kern_ms, "algorithmic_flops_per_launch": flops, "integrand_nodes_per_launch": nodes,
                 "peak_source": "measured in-run: DFMA microbenchmark ccl_b200_measure_fp64_peak "
                                "(MEASURED_PEAKS.json holds no fp64 figure)"}
@@ -361,7 +363,8 @@ def main():
                        "l2": "inputs larger than L2 (%.1f GB of tables per rank)" % (batch.arena_bytes / 1e9),
                        "distinct_cosmologies": N_DISTINCT, "failed_cl_entries": n_fail},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": args.steps, "clocks": clocks,
+            # fast 'spline' path: grouping + integrator + redo kernels per step; otherwise one kernel
+            "gpu_launches": args.steps * (3 if fast_path else 1), "clocks": clocks,
         }))
     if world > 1:
         dist.destroy_process_group()

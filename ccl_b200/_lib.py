@@ -85,6 +85,7 @@ SIGNATURES = {
                                                      C.c_int, _vp, _vp, _vp, _ip]),
     "ccl_b200_batch_spline_nodes": (C.c_ulonglong, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp]),
     "ccl_b200_batch_last_qag_evals": (C.c_ulonglong, [_vp]),
+    "ccl_b200_batch_last_used_fast_path": (C.c_int, [_vp]),
 }
 
 _LIB = None

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -514,6 +515,7 @@ struct ccl_b200_batch {
   ccl_b200_params params;
   TableSet ts;
   unsigned long long last_qag_evals = 0;
+  bool last_fast = false;  // the last 'spline' launch used the grid-sharing kernels
   DevBuf call;  // per-batch call buffers (colls, pairs, ells, counters, outputs)
 };
 
@@ -603,6 +605,28 @@ static bool batch_check(ccl_b200_batch* b, int ncoll, const int* coll_start, con
       set_err("ccl_b200: pair %d names an unknown collection", p);
       return false;
     }
+  return true;
+}
+
+// The fast 'spline' kernels (limber_fast.cu) cover the table forms pyccl's own tracers produce on
+// the default path: log bicubic P(k,a); sub-tracers with an Akima kernel, der_bessel in {-1, 0}
+// and either no transfer or an a-only (factorised, linear) one.  Anything else runs on the
+// general kernel.
+static bool fast_eligible(const ccl_b200_batch* b, int ncoll, int npair) {
+  if (getenv("CCL_B200_NO_FAST")) return false;
+  if (ncoll > FAST_MAX_COLLS || npair > FAST_MAX_PAIRS) return false;
+  for (const CosmoPlan& c : b->ts.cosmos) {
+    const F2D& g = c.psp.flags;
+    if (!c.has_psp || !g.has_fka || !g.is_log || g.is_factorizable) return false;
+    if ((int)c.tracers.size() > FAST_MAX_TRACERS) return false;
+    for (const TracerPlan& t : c.tracers) {
+      if (!t.kernel.present || t.der_bessel > 0) return false;
+      if (t.has_transfer) {
+        const F2D& f = t.transfer.flags;
+        if (!f.is_factorizable || f.has_fk || !f.has_fa || f.is_log) return false;
+      }
+    }
+  }
   return true;
 }
 
@@ -1041,7 +1065,10 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
   const size_t o_pr = o_co + ((size_t)ncoll * 8 + 255) / 256 * 256;
   const size_t o_el = o_pr + ((size_t)npair * 8 + 255) / 256 * 256;
   const size_t o_ct = o_el + ((size_t)nl * 8 + 255) / 256 * 256;
-  const size_t total = o_ct + 256;
+  const size_t o_fp = o_ct + 256;
+  const bool fast = (integration_method == INTEG_SPLINE) && fast_eligible(b, ncoll, npair);
+  const unsigned long long redo_cap = 1ull << 20;
+  const size_t total = o_fp + (fast ? limber_fast_plan_bytes(nc, npair, redo_cap) : 0);
   if (!b->call.reserve(total, status)) return;
   char* base = b->call.p;
   // small pageable copies: the driver stages them before returning
@@ -1070,6 +1097,12 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
     wsb = limber_qag_workspace_bytes(P.par.N_ITERATION);
     if (!sc.qag.reserve(wsb, status)) return;
     ws = reinterpret_cast<double*>(sc.qag.p);
+  }
+  b->last_fast = fast;
+  if (fast) {
+    const FastPlan plan = limber_fast_plan_carve(base + o_fp, nc, npair, redo_cap);
+    if (!cuda_ok(launch_limber_fast(P, plan, stream), "limber fast launch", status)) return;
+    return;
   }
   if (!cuda_ok(launch_limber(P, integration_method, ws, wsb, stream), "limber launch", status)) return;
   if (integration_method == INTEG_QAG) {
@@ -1138,5 +1171,7 @@ unsigned long long ccl_b200_batch_spline_nodes(const ccl_b200_batch* b, int ncol
 }
 
 unsigned long long ccl_b200_batch_last_qag_evals(const ccl_b200_batch* b) { return b->last_qag_evals; }
+
+int ccl_b200_batch_last_used_fast_path(const ccl_b200_batch* b) { return b->last_fast ? 1 : 0; }
 
 }  // extern "C"

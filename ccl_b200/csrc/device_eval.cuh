@@ -151,7 +151,7 @@ __device__ __forceinline__ double bicubic_eval(const F2D& f, double x, double y,
 }
 
 // ccl_f2d_t_eval (src/ccl_f2d.c:203-373), every branch.
-__device__ __noinline__ double f2d_eval(const F2D& f, double lk, double a, const Cosmo* cs, int& st) {
+static __device__ __noinline__ double f2d_eval(const F2D& f, double lk, double a, const Cosmo* cs, int& st) {
   bool is_hiz = false, is_loz = false;
   double a_ev = a;
   if (!f.is_a_constant) {

@@ -380,14 +380,8 @@ __device__ __forceinline__ void finish_task(const LimberProblem& P, int ic, int 
 // telescopes to t_0 - t_{n-1} unless some NE vanishes (exact ties, e.g. stretches of zeros), in
 // which case the per-interval form is evaluated.  Same polynomial as akima_eval_integ; only the
 // association of the sum differs (<= 1e-15 relative).
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-limber_spline_kernel(const LimberProblem P, long long ntasks) {
-  extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sf = smem + (size_t)warp * (P.par.nk_cap + 2 * MAX_SUB);
-  double* pref = sf + P.par.nk_cap;
-  const long long task = (long long)blockIdx.x * WARPS_PER_CTA + warp;
-  if (task >= ntasks) return;
+__device__ __forceinline__ void spline_task(const LimberProblem& P, long long task, double* sf, double* pref,
+                                            int lane) {
   TaskCtx c;
   int ic, ip, il;
   setup_task(P, task, c, ic, ip, il);
@@ -483,6 +477,40 @@ limber_spline_kernel(const LimberProblem P, long long ntasks) {
   }
   const double acc = warp_sum(trap + corr * (1.0 / 12.0));
   finish_task(P, ic, ip, il, acc, 0, lane);
+}
+
+// General 'spline' kernel: one warp per (cosmology, pair, ell), every tracer / P(k) form.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+limber_spline_kernel(const LimberProblem P, long long ntasks) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sf = smem + (size_t)warp * (P.par.nk_cap + 2 * MAX_SUB);
+  double* pref = sf + P.par.nk_cap;
+  const long long task = (long long)blockIdx.x * WARPS_PER_CTA + warp;
+  if (task >= ntasks) return;
+  spline_task(P, task, sf, pref, lane);
+}
+
+// Persistent variant over the redo list the fast kernel leaves behind (tasks it could not take:
+// a node outside the a(chi) or P(k,a) tables, ...).  list[0] = count; when the list overflowed
+// every task is recomputed.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+limber_spline_redo_kernel(const LimberProblem P, long long ntasks, const unsigned long long* list,
+                          unsigned long long cap) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sf = smem + (size_t)warp * (P.par.nk_cap + 2 * MAX_SUB);
+  double* pref = sf + P.par.nk_cap;
+  const unsigned long long count = list[0];
+  if (count == 0) return;
+  const bool overflow = count > cap;
+  const unsigned long long n = overflow ? (unsigned long long)ntasks : count;
+  const unsigned long long stride = (unsigned long long)gridDim.x * WARPS_PER_CTA;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * WARPS_PER_CTA + warp; t < n; t += stride) {
+    const long long task = overflow ? (long long)t : (long long)list[1 + t];
+    __syncwarp();
+    spline_task(P, task, sf, pref, lane);
+  }
 }
 
 // ---- qag_quad ------------------------------------------------------------------------
@@ -749,6 +777,17 @@ int limber_nk_cap(const LimberParams& par) {
   const double span = log(par.K_MAX / par.K_MIN);
   int cap = (int)(fmax(span / par.DLOGK_INTEGRATION + 0.5, 1.0)) + 2;
   return (cap + 3) & ~3;
+}
+
+void launch_limber_redo(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream) {
+  const long long ntasks = (long long)prob.ncosmo * prob.npair * prob.nl;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = (size_t)WARPS_PER_CTA * (prob.par.nk_cap + 2 * MAX_SUB) * sizeof(double);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(limber_spline_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  limber_spline_redo_kernel<<<sms * 4, WARPS_PER_CTA * 32, smem, stream>>>(prob, ntasks, plan.redo, plan.redo_cap);
 }
 
 cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws, size_t qag_ws_bytes,

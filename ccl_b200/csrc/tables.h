@@ -124,6 +124,29 @@ struct LimberProblem {
   unsigned long long* counters;  // [0] integrand evaluations (qag only)
 };
 
+// ---- fast 'spline' path: ln k node grids shared by the pairs of one cosmology ----
+// Two pairs of one cosmology share a node grid for every ell when their (chi_min, chi_max) from
+// get_k_interval (src/ccl_cls.c:64-100) coincide; a(chi), k P(k,a) and each collection's
+// Delta(node) are then evaluated once per grid instead of once per pair.
+struct GridDesc {
+  double chi_min, chi_max;
+  int coll_begin, ncoll;  // into gcolls (collection indices used by this grid's pairs)
+  int pair_begin, npair;  // into gpairs
+};
+struct GridPair {
+  int out;     // pair index in the caller's list
+  short a, b;  // slots in the grid's collection list
+};
+struct FastPlan {
+  GridDesc* grids;  // [ncosmo][gstride]
+  GridPair* gpairs; // [ncosmo][gstride]
+  int* gcolls;      // [ncosmo][cstride]
+  int* ngrids;      // [ncosmo]
+  int gstride, cstride;
+  unsigned long long* redo;  // [0] = count, [1..redo_cap] = task ids left to the general kernel
+  unsigned long long redo_cap;
+};
+
 // ---- table-preparation jobs (device kernels fill the derived regions of the arena) ----
 struct AkimaJob { const double* x; const double* y; Rec1* rec; int n; };
 struct CsplineJob { const double* x; const double* y; Rec1* rec; double* scratch; int n; };
@@ -145,6 +168,15 @@ void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs,
 cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws, size_t qag_ws_bytes,
                           cudaStream_t stream);
 size_t limber_qag_workspace_bytes(int n_iteration);
+// fast path (limber_fast.cu): eligibility limits, plan sizing, launch (group + fast + redo kernels)
+constexpr int FAST_MAX_TRACERS = 48;  // sub-tracers per cosmology
+constexpr int FAST_MAX_COLLS = 48;    // collections per call
+constexpr int FAST_MAX_PAIRS = 2048;  // pairs per call
+size_t limber_fast_plan_bytes(int ncosmo, int npair, unsigned long long redo_cap);
+FastPlan limber_fast_plan_carve(void* base, int ncosmo, int npair, unsigned long long redo_cap);
+cudaError_t launch_limber_fast(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream);
+// the general one-warp-per-C_ell kernel over the plan's redo list (kernels.cu)
+void launch_limber_redo(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream);
 int limber_nk_cap(const LimberParams& par);
 double measure_fp64_peak_tflops(cudaStream_t stream);
 // vectorised accessors (ccl_scale_factor_of_chis, pk2d_eval_multi, cl_tracer_get_kernel/_transfer)

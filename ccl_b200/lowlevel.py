@@ -290,6 +290,11 @@ class LibBatch:
         return _lib.load().ccl_b200_batch_spline_nodes(self.h, *g)
 
     @property
+    def last_used_fast_path(self):
+        """True if the last 'spline' launch ran the grid-sharing kernels (limber_fast.cu)."""
+        return bool(_lib.load().ccl_b200_batch_last_used_fast_path(self.h))
+
+    @property
     def last_qag_evals(self):
         return _lib.load().ccl_b200_batch_last_qag_evals(self.h)
 

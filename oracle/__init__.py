@@ -88,6 +88,7 @@ def lib():
                                                 C.c_int, _dp, _dp, C.c_int, _ip]
         L.o_get_k_interval_pub.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp),
                                            C.c_double, _dp, _dp]
+        L.o_set_lkmin_ulps.argtypes = [C.c_int]
         L.o_limber_nk.restype = C.c_int
         L.o_limber_nk.argtypes = [C.c_double, C.c_double, C.c_double]
         L.o_integ_spline.argtypes = [C.c_int, _dp, _dp, C.c_double, C.c_double, _dp, _ip]
@@ -310,6 +311,11 @@ def angular_cl(cosmo, trc1, trc2, psp, ells, method=INTEG_SPLINE, each=False, re
     if return_neval:
         return cl, st.value, nev
     return cl, st.value
+
+
+def set_lkmin_ulps(n):
+    """Test knob: shift the lower integration limit by n ulps (see o_set_lkmin_ulps in the C file)."""
+    lib().o_set_lkmin_ulps(int(n))
 
 
 def k_interval(cosmo, trc1, trc2, ell):

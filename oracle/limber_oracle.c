@@ -780,6 +780,15 @@ typedef struct {
   long neval;
 } o_integ_par;
 
+/* Test knob (not in the reference): shift lkmin by n units in the last place.  With the default
+ * tracers chi_max IS the last node of a kernel spline, so the integrand's first node sits exactly
+ * on a support edge, chi_0 = (l+1/2)/exp(log((l+1/2)/chi_max)), where ccl_f1d_t_eval jumps from
+ * W(chi_max) to 0 (src/ccl_f1d.c:159-161).  Which side chi_0 falls on is decided by the last bit
+ * of libm's log/exp, so the reference's own value is only defined up to that choice; the parity
+ * tests use this knob to enumerate the outcomes a <= 1 ulp libm can produce. */
+static int o_lkmin_ulps = 0;
+void o_set_lkmin_ulps(int n) { o_lkmin_ulps = n; }
+
 static void o_get_k_interval(const o_cosmo *cosmo, int n1, o_tracer *const *t1, int n2,
                              o_tracer *const *t2, double l, double *lkmin, double *lkmax) {
   double chi_min1 = 1E15, chi_max1 = -1E15;
@@ -797,6 +806,8 @@ static void o_get_k_interval(const o_cosmo *cosmo, int n1, o_tracer *const *t1, 
   if (chi_min <= 0) chi_min = 0.5 * (l + 0.5) / cosmo->K_MAX;
   *lkmax = log(fmin(cosmo->K_MAX, 2 * (l + 0.5) / chi_min));
   *lkmin = log(fmax(cosmo->K_MIN, (l + 0.5) / chi_max));
+  for (int i = 0; i < abs(o_lkmin_ulps); i++)
+    *lkmin = nextafter(*lkmin, o_lkmin_ulps > 0 ? INFINITY : -INFINITY);
 }
 
 static double o_transfer_limber_single(const o_tracer *tr, double l, double lk, double k,
