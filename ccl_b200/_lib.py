@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libccl_b200.so")
+# CCL_B200_LIB selects another build of the same sources (kernel tuning A/B runs)
+LIB_PATH = os.environ.get("CCL_B200_LIB") or os.path.join(_HERE, "libccl_b200.so")
 
 INTEGRATION_QAG_QUAD = 500
 INTEGRATION_SPLINE = 501

@@ -20,16 +20,40 @@ namespace cclb {
 
 namespace {
 
-constexpr int FW = 8;     // warps per CTA
-constexpr int NCG = 12;   // collections per grid task
-constexpr int NPG = 12;   // pairs per grid task
-constexpr int WIN = 36;   // window columns
+#ifndef CCLB_FW
+#define CCLB_FW 8
+#endif
+#ifndef CCLB_NCG
+#define CCLB_NCG 12
+#endif
+#ifndef CCLB_NPG
+#define CCLB_NPG 12
+#endif
+#ifndef CCLB_LPC
+#define CCLB_LPC 4
+#endif
+#ifndef CCLB_MINB
+#define CCLB_MINB 3
+#endif
+constexpr int FW = CCLB_FW;     // warps per CTA
+constexpr int NCG = CCLB_NCG;   // collections per grid task
+constexpr int NPG = CCLB_NPG;   // pairs per grid task
+static_assert(CCLB_NPG <= 16, "pair flags are packed two bits per pair");
+constexpr int LPC = CCLB_LPC;   // ells per CTA (descriptor staging is amortised over them)
+constexpr int NSG = 2 * CCLB_NCG;  // sub-tracers per grid task
+constexpr int GB = 64;          // grids whose limits are precomputed per CTA pass
 
 struct FastTr {
   Spline1D kernel;
   Spline1D fa;
-  double pref;  // f_ell (/(l+1/2)^2 when der_bessel == -1)
+  double pref[LPC];  // f_ell (/(l+1/2)^2 when der_bessel == -1) for each ell of this CTA
   int has_fa, pad;
+};
+
+// ln k limits and node spacing of one (ell, grid) task (get_k_interval + ccl_linear_spacing)
+struct GridPar {
+  double lkmin, lkmax, dx, hl, inv_dx, inv_hl, ratio, iratio;
+  int nk, grid, ls, pad;
 };
 
 struct FastCta {
@@ -37,15 +61,22 @@ struct FastCta {
   F2D psp;
   FastTr tr[FAST_MAX_TRACERS];
   int2 colls[FAST_MAX_COLLS];
-  int next_grid, ngrids;
+  GridPar gp[GB];
+  int next_task, pad;
 };
 
+// sub-tracer list entry of a grid task: tracer index | collection slot << 8 | first << 16 | last << 17
+constexpr unsigned SUB_FIRST = 1u << 16, SUB_LAST = 1u << 17;
+
 struct FastWarp {
-  double w[1 + NCG][WIN];  // row 0: k P(k,a); row 1+c: D of the grid's collection c
-  double sf[2][WIN + 4];   // integrand of the current pair over the window (double-buffered)
-  double acc[NPG][32];     // per-lane partial integrals
+  double d[NCG][32];      // D of the grid's collection c at this lane's node
+  double sf[2][36];       // integrand of the current pair: 4 carried + 32 new nodes (double-buffered)
+  double fc[NPG][4];      // last 4 integrand values of the previous chunk, per pair
+  double acc[NPG][32];    // per-lane partial integrals
   GridPair prs[NPG];
-  int cl[NCG];
+  unsigned pf[NPG];       // per pair: bits 0-1 equal-difference flags of the previous chunk's last
+                          // two lanes, bit 2 Akima tie flag of its last integrated node
+  unsigned subs[NSG];
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -107,6 +138,7 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
   for (int p = 0; p < npair; ++p) {
     if (leader[p] != p) continue;
     GridDesc cur{pmin[p], pmax[p], ncw, 0, npw, 0};
+    int cur_nsub = 0;
     for (int q = p; q < npair; ++q) {
       if (leader[q] != p) continue;
       const int2 pr = P.pairs[q];
@@ -115,17 +147,21 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
         if (gc[cur.coll_begin + i] == pr.x) sa = i;
         if (gc[cur.coll_begin + i] == pr.y) sb = i;
       }
-      const int need = (sa < 0) + ((sb < 0) && (pr.y != pr.x));
-      if (cur.ncoll + need > NCG || cur.npair + 1 > NPG) {  // close this task, open another on the same grid
+      const bool new_b = (sb < 0) && (pr.y != pr.x);
+      const int need = (sa < 0) + new_b;
+      const int need_sub = (sa < 0 ? P.colls[pr.x].y : 0) + (new_b ? P.colls[pr.y].y : 0);
+      if (cur.npair > 0 && (cur.ncoll + need > NCG || cur.npair + 1 > NPG || cur_nsub + need_sub > NSG)) {
+        // close this task, open another on the same grid
         grids[ng++] = cur;
         ncw += cur.ncoll;
         npw += cur.npair;
         cur = GridDesc{pmin[p], pmax[p], ncw, 0, npw, 0};
+        cur_nsub = 0;
         sa = sb = -1;
       }
-      if (sa < 0) { sa = cur.ncoll; gc[cur.coll_begin + cur.ncoll++] = pr.x; }
+      if (sa < 0) { sa = cur.ncoll; gc[cur.coll_begin + cur.ncoll++] = pr.x; cur_nsub += P.colls[pr.x].y; }
       if (pr.y == pr.x) sb = sa;
-      else if (sb < 0) { sb = cur.ncoll; gc[cur.coll_begin + cur.ncoll++] = pr.y; }
+      else if (sb < 0) { sb = cur.ncoll; gc[cur.coll_begin + cur.ncoll++] = pr.y; cur_nsub += P.colls[pr.y].y; }
       gp[cur.pair_begin + cur.npair++] = GridPair{q, (short)sa, (short)sb};
     }
     grids[ng++] = cur;
@@ -138,172 +174,217 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
 // ------------------------------------------------------------------------------------------
 // The fast integrator.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FW * 32, 3) limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
+__global__ void __launch_bounds__(FW * 32, CCLB_MINB)
+limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   FastCta& S = *reinterpret_cast<FastCta*>(smraw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FastWarp& W = reinterpret_cast<FastWarp*>(smraw + ((sizeof(FastCta) + 15) & ~size_t(15)))[warp];
-  const int il = blockIdx.x % P.nl;
-  const int ic = blockIdx.x / P.nl;
+  const int nlt = (P.nl + LPC - 1) / LPC;
+  const int il0 = (blockIdx.x % nlt) * LPC;
+  const int ic = blockIdx.x / nlt;
+  const int nls = min(LPC, P.nl - il0);
   const Cosmo* cs = P.cosmos + ic;
-  const double l = P.ells[il];
-  const double lp1h = l + 0.5;
 
-  // ---- per-CTA staging of the descriptors this (cosmology, ell) needs ----
+  // ---- per-CTA staging of the descriptors this (cosmology, ell tile) needs ----
   for (int t = threadIdx.x; t < cs->ntracers; t += blockDim.x) {
     const Tracer& tr = cs->tracers[t];
     S.tr[t].kernel = tr.kernel;
     S.tr[t].fa = tr.transfer.fa;
     S.tr[t].has_fa = tr.has_transfer;
-    S.tr[t].pref = tracer_prefactor(tr, l);
+    for (int ls = 0; ls < nls; ++ls) S.tr[t].pref[ls] = tracer_prefactor(tr, P.ells[il0 + ls]);
   }
   for (int c = threadIdx.x; c < P.ncoll; c += blockDim.x) S.colls[c] = P.colls[c];
   if (threadIdx.x == 32) S.achi = cs->achi;
   if (threadIdx.x == 64) S.psp = *cs->psp;
-  if (threadIdx.x == 0) {
-    S.next_grid = 0;
-    S.ngrids = G.ngrids[ic];
-  }
-  __syncthreads();
 
   const GridDesc* grids = G.grids + (size_t)ic * G.gstride;
   const GridPair* gpairs = G.gpairs + (size_t)ic * G.gstride;
   const int* gcolls = G.gcolls + (size_t)ic * G.cstride;
   const unsigned FULL = 0xffffffffu;
+  const int ngrids = G.ngrids[ic];
+  const int ntasks = ngrids * nls;  // task = (ell of the tile, grid)
 
-  for (;;) {
-    int g = 0;
-    if (lane == 0) g = atomicAdd(&S.next_grid, 1);
-    g = __shfl_sync(FULL, g, 0);
-    if (g >= S.ngrids) break;
-    const GridDesc gd = grids[g];
-    const int ncoll = gd.ncoll, np = gd.npair;
-    __syncwarp();
-    if (lane < np) W.prs[lane] = gpairs[gd.pair_begin + lane];
-    if (lane < ncoll) W.cl[lane] = gcolls[gd.coll_begin + lane];
-    // get_k_interval (src/ccl_cls.c:91-99)
-    double chi_min = gd.chi_min;
-    if (chi_min <= 0) chi_min = 0.5 * lp1h / P.par.K_MAX;
-    const double lkmax = log(fmin(P.par.K_MAX, 2 * lp1h / chi_min));
-    const double lkmin = log(fmax(P.par.K_MIN, lp1h / gd.chi_max));
-    const int nk = (int)(fmax((lkmax - lkmin) / P.par.DLOGK_INTEGRATION + 0.5, 1.0)) + 1;
-    __syncwarp();
-    if (nk < 5) {  // gsl_spline_alloc(akima, n < 5) fails: NaN + CCL_ERROR_INTEG
-      if (lane < np) {
-        const int ip = W.prs[lane].out;
-        const size_t s = (size_t)ic * P.npair + ip;
-        P.cl[s * P.nl + il] = nan("");
-        P.status[s] = ST_ERR_INTEG;
-        atomicCAS(P.status_detail + s, 0, (int)ST_ERR_MEMORY);
-      }
-      continue;
+  for (int t0 = 0; t0 < ntasks; t0 += GB) {
+    __syncthreads();  // staging done / previous pass drained
+    const int nb = min(GB, ntasks - t0);
+    if (threadIdx.x < nb) {
+      // get_k_interval (src/ccl_cls.c:91-99) and ccl_linear_spacing (src/ccl_utils.c:17-37), once
+      // per (grid, ell) instead of once per lane
+      const int task = t0 + threadIdx.x;
+      GridPar q;
+      q.ls = task / ngrids;
+      q.grid = task - q.ls * ngrids;
+      const GridDesc gd = grids[q.grid];
+      const double lp1h = P.ells[il0 + q.ls] + 0.5;
+      double chi_min = gd.chi_min;
+      if (chi_min <= 0) chi_min = 0.5 * lp1h / P.par.K_MAX;
+      q.lkmax = log(fmin(P.par.K_MAX, 2 * lp1h / chi_min));
+      q.lkmin = log(fmax(P.par.K_MIN, lp1h / gd.chi_max));
+      q.nk = (int)(fmax((q.lkmax - q.lkmin) / P.par.DLOGK_INTEGRATION + 0.5, 1.0)) + 1;
+      q.dx = (q.lkmax - q.lkmin) / (q.nk - 1.);
+      q.hl = q.lkmax - (q.lkmin + q.dx * (q.nk - 2));  // last interval (end node overwritten)
+      q.inv_dx = 1.0 / q.dx;
+      q.inv_hl = 1.0 / q.hl;
+      q.ratio = exp(32.0 * q.dx);
+      q.iratio = 1.0 / q.ratio;
+      q.pad = 0;
+      S.gp[threadIdx.x] = q;
     }
-    bool redo = !(lkmin >= S.psp.lkmin && lkmax <= S.psp.lkmax);
-    // ccl_linear_spacing (src/ccl_utils.c:17-37); k and chi advance by constant ratios per chunk
-    const double dx = (lkmax - lkmin) / (nk - 1.);
-    const double hl = lkmax - (lkmin + dx * (nk - 2));  // last interval (end node overwritten)
-    const double inv_dx = 1.0 / dx;
-    double k = exp(lkmin + dx * lane);
-    double chi = lp1h / k;
-    const double ratio = exp(32.0 * dx);
-    const double iratio = 1.0 / ratio;
-    unsigned zcarry = 0;  // bit q: Akima tie flag of the last node of the previous chunk, pair q
+    if (threadIdx.x == 0) S.next_task = 0;
+    __syncthreads();
+
+    for (;;) {
+      int gl = 0;
+      if (lane == 0) gl = atomicAdd(&S.next_task, 1);
+      gl = __shfl_sync(FULL, gl, 0);
+      if (gl >= nb) break;
+      const GridDesc gd = grids[S.gp[gl].grid];
+      const int ls = S.gp[gl].ls;
+      const int il = il0 + ls;
+      const double lp1h = P.ells[il] + 0.5;
+      const int ncoll = gd.ncoll, np = gd.npair;
+      __syncwarp();
+      if (lane < np) {
+        W.prs[lane] = gpairs[gd.pair_begin + lane];
+        W.pf[lane] = 0u;
+      }
+      // flatten the grid's collections into one sub-tracer list (lane c expands collection c)
+      int2 cr = make_int2(0, 0);
+      if (lane < ncoll) cr = S.colls[gcolls[gd.coll_begin + lane]];
+      int off = cr.y;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, off, o);
+        if (lane >= o) off += v;
+      }
+      const int nsub = __shfl_sync(FULL, off, 31);
+      off -= cr.y;
+      if (nsub <= NSG)
+        for (int j = 0; j < cr.y; ++j)
+          W.subs[off + j] = (unsigned)(cr.x + j) | ((unsigned)lane << 8) | (j == 0 ? SUB_FIRST : 0u) |
+                            (j == cr.y - 1 ? SUB_LAST : 0u);
+      const int nk = S.gp[gl].nk;
+      const double lkmin = S.gp[gl].lkmin, lkmax = S.gp[gl].lkmax;
+      __syncwarp();
+      if (nk < 5) {  // gsl_spline_alloc(akima, n < 5) fails: NaN + CCL_ERROR_INTEG
+        if (lane < np) {
+          const int ip = W.prs[lane].out;
+          const size_t s = (size_t)ic * P.npair + ip;
+          P.cl[s * P.nl + il] = nan("");
+          P.status[s] = ST_ERR_INTEG;
+          atomicCAS(P.status_detail + s, 0, (int)ST_ERR_MEMORY);
+        }
+        continue;
+      }
+      // outside the P(k,a) table in ln k, or more sub-tracers than the list holds: general kernel
+      bool redo = !(lkmin >= S.psp.lkmin && lkmax <= S.psp.lkmax) || nsub > NSG;
+      const double dx = S.gp[gl].dx, hl = S.gp[gl].hl, inv_dx = S.gp[gl].inv_dx, inv_hl = S.gp[gl].inv_hl;
+      // k and chi advance by constant ratios from chunk to chunk (one exp per lane per grid)
+      double k = exp(lkmin + dx * lane);
+      double chi = lp1h / k;
 #pragma unroll 1
-    for (int q = 0; q < np; ++q) W.acc[q][lane] = 0.0;
+      for (int q = 0; q < np; ++q) W.acc[q][lane] = 0.0;
 
 #pragma unroll 1
-    for (int base = 0; base < nk + 2 && !redo; base += 32) {
-      if (base > 0 && lane < 4) {
-#pragma unroll 1
-        for (int r = 0; r <= ncoll; ++r) W.w[r][lane] = W.w[r][32 + lane];
-      }
-      __syncwarp();
-      // ---------------- phase 1: node quantities ----------------
-      const int s = base + lane;
-      bool bad = false;
-      if (s < nk) {
-        const double lk = (s == 0) ? lkmin : ((s == nk - 1) ? lkmax : lkmin + dx * s);
-        // ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277); chi > 0 here
-        double a = 1.0;
-        if (!(chi < 1.e-8)) {
-          if (chi >= S.achi.x0 && chi <= S.achi.xn) a = rec_value(find_rec(S.achi, chi), chi);
-          else bad = true;  // GSL_EDOM: the general kernel reports it
-        }
-        if (!(a >= S.psp.amin && a <= S.psp.amax)) bad = true;  // growth extrapolation: general kernel
+      for (int base = 0; base < nk + 2 && !redo; base += 32) {
+        // ---------------- phase 1: node quantities (lane = node base + lane) ----------------
+        const int s = base + lane;
+        bool bad = false;
         double kp = 0.0;
-        if (!bad) kp = k * exp(bicubic_eval(S.psp, lk, a, 0));
-        W.w[0][4 + lane] = kp;
-#pragma unroll 1
-        for (int c = 0; c < ncoll; ++c) {
-          const int2 cr = S.colls[W.cl[c]];
+        if (s < nk) {
+          const double lk = (s == 0) ? lkmin : ((s == nk - 1) ? lkmax : lkmin + dx * s);
+          // ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277); chi > 0 here
+          double a = 1.0;
+          if (!(chi < 1.e-8)) {
+            if (chi >= S.achi.x0 && chi <= S.achi.xn) a = rec_value(find_rec(S.achi, chi), chi);
+            else bad = true;  // GSL_EDOM: the general kernel reports it
+          }
+          if (!(a >= S.psp.amin && a <= S.psp.amax)) bad = true;  // growth extrapolation: general kernel
+          if (!bad) kp = k * exp(bicubic_eval(S.psp, lk, a, 0));
+          // transfer_limber_wrap (src/ccl_cls.c:150-164) for every collection of the grid, as one
+          // branch-free loop over the flattened sub-tracer list so that independent table lookups
+          // overlap.  Outside a kernel's support the lookup runs on the clamped abscissa and the
+          // term is dropped (ccl_f1d_t_eval: the end nodes count as outside, src/ccl_f1d.c:137-161).
           double D = 0.0;
-#pragma unroll 1
-          for (int t = cr.x; t < cr.x + cr.y; ++t) {
-            const FastTr& tr = S.tr[t];
-            // ccl_f1d_t_eval: the end nodes count as outside (src/ccl_f1d.c:137-161)
-            if (chi > tr.kernel.x0 && chi < tr.kernel.xn) {
-              double wt = rec_value(find_rec(tr.kernel, chi), chi);
-              if (tr.has_fa) {
-                const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
-                wt *= rec_value(find_rec(tr.fa, a_ev), a_ev);
-              }
-              D += wt * tr.pref;
+#pragma unroll 2
+          for (int e = 0; e < nsub; ++e) {
+            const unsigned ent = W.subs[e];
+            const FastTr& tr = S.tr[ent & 0xffu];
+            const bool inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
+            const double chic = fmin(fmax(chi, tr.kernel.x0), tr.kernel.xn);
+            double wt = rec_value(find_rec(tr.kernel, chic), chic);
+            if (tr.has_fa) {
+              const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
+              wt *= rec_value(find_rec(tr.fa, a_ev), a_ev);
             }
+            const double val = inside ? wt * tr.pref[ls] : 0.0;
+            D = (ent & SUB_FIRST) ? val : D + val;
+            if (ent & SUB_LAST) W.d[(ent >> 8) & 0xffu][lane] = D;
           }
-          W.w[1 + c][4 + lane] = D;
+          k *= S.gp[gl].ratio;
+          chi *= S.gp[gl].iratio;
         }
-        k *= ratio;
-        chi *= iratio;
-      }
-      if (__any_sync(FULL, bad)) { redo = true; break; }
-      __syncwarp();
-      // ---------------- phase 2: per-pair integrand and Akima integral ----------------
-      const int cn = base + lane - 2;  // node integrated by this lane (window column lane + 2)
-      const bool cvalid = (cn >= 0) && (cn < nk);
-      const bool edge = (cn < 2) || (cn > nk - 4);
+        if (__any_sync(FULL, bad)) { redo = true; break; }
+        // ---------------- phase 2: per-pair integrand and Akima integral ----------------
+        // With m_j the slopes and t_j the Akima node derivatives, GSL's piecewise cubic integrates to
+        //   sum_i h_i (f_i + f_{i+1}) / 2  +  (1/12) sum_{i: NE_i != 0} h_i^2 (t_i - tL_{i+1}),
+        // tL_{i+1} = t_{i+1} unless NE_{i+1} == 0 (then m_i).  On a uniform grid without ties the
+        // second sum telescopes to the end nodes, so interior chunks only add trapezoids and test
+        // for ties: NE_c == 0 <=> m_{c+1} == m_c and m_{c-1} == m_{c-2}, i.e. equal consecutive first
+        // differences (bit e of a lane: d_{s-1} == d_{s-2}; z_{s-2} = e_s & e_{s-2}).
+        const bool edge_chunk = (base == 0) || (base + 31 >= nk - 1);
 #pragma unroll 1
-      for (int q = 0; q < np; ++q) {
-        const GridPair pr = W.prs[q];
-        const double* da = W.w[1 + pr.a];
-        const double* db = W.w[1 + pr.b];
-        double* sf = W.sf[q & 1];
-        {
+        for (int q = 0; q < np; ++q) {
+          const GridPair pr = W.prs[q];
+          double* sf = W.sf[q & 1];
           // cl_integrand (src/ccl_cls.c:166-187): 0 when either transfer vanishes
-          const double d1 = da[4 + lane], d2 = db[4 + lane];
-          sf[4 + lane] = (d1 == 0.0 || d2 == 0.0) ? 0.0 : W.w[0][4 + lane] * d1 * d2;
-          if (lane < 4) {
-            const double e1 = da[lane], e2 = db[lane];
-            sf[lane] = (e1 == 0.0 || e2 == 0.0) ? 0.0 : W.w[0][lane] * e1 * e2;
+          double f4 = 0.0;
+          if (s < nk) {
+            const double d1 = W.d[pr.a][lane], d2 = W.d[pr.b][lane];
+            f4 = (d1 == 0.0 || d2 == 0.0) ? 0.0 : kp * d1 * d2;
           }
-        }
-        __syncwarp();
-        const double f0 = sf[lane], f1 = sf[lane + 1], f2 = sf[lane + 2], f3 = sf[lane + 3], f4 = sf[lane + 4];
-        // slopes m_{c-2}, m_{c-1}, m_c, m_{c+1} (gsl akima_init boundary rules at the ends)
-        double mm2 = (f1 - f0) * inv_dx, mm1 = (f2 - f1) * inv_dx, m0 = (f3 - f2) * inv_dx,
-               mp1 = (f4 - f3) * inv_dx;
-        double h = dx, hprev = dx;
-        if (edge) {
-          if (cn == nk - 3) mp1 = (f4 - f3) / hl;
-          if (cn == nk - 2) { m0 = (f3 - f2) / hl; h = hl; mp1 = 2.0 * m0 - mm1; }
+          sf[4 + lane] = f4;
+          if (lane < 4) sf[lane] = W.fc[q][lane];
+          __syncwarp();
+          const double f2 = sf[lane + 2], f3 = sf[lane + 3];
+          if (lane >= 28) W.fc[q][lane - 28] = f4;
+          const double dlast = f4 - f3;
+          const unsigned E = __ballot_sync(FULL, dlast == (f3 - f2));
+          const unsigned pf = W.pf[q];
+          const unsigned Z = E & ((E << 2) | (pf & 3u));
+          const bool zc_in = (pf >> 2) & 1u;
+          if (!(edge_chunk || Z != 0u || zc_in)) {
+            W.acc[q][lane] += (0.5 * dx) * (f3 + f4);  // interval (s-1, s)
+            if (lane == 0) W.pf[q] = E >> 30;
+            continue;
+          }
+          // ---- chunks holding an end node or a tie: the full per-node form ----
+          const int cn = s - 2;  // node whose correction term this lane owns
+          const bool cvalid = (cn >= 0) && (cn < nk);
+          const double f0 = sf[lane], f1 = sf[lane + 1];
+          double mm2 = (f1 - f0) * inv_dx, mm1 = (f2 - f1) * inv_dx, m0 = (f3 - f2) * inv_dx,
+                 mp1 = dlast * inv_dx;
+          double h = dx, hprev = dx;
+          if (cn == nk - 3) mp1 = dlast * inv_hl;
+          if (cn == nk - 2) { m0 = (f3 - f2) * inv_hl; h = hl; mp1 = 2.0 * m0 - mm1; }
           if (cn == nk - 1) {
-            mm1 = (f2 - f1) / hl;
+            mm1 = (f2 - f1) * inv_hl;
             hprev = hl;
             m0 = 2.0 * mm1 - mm2;
             mp1 = 3.0 * mm1 - 2.0 * mm2;
           }
           if (cn == 1) mm2 = 2.0 * mm1 - m0;
           if (cn == 0) { mm1 = 2.0 * m0 - mp1; mm2 = 3.0 * m0 - 2.0 * mp1; }
-        }
-        const double d12 = fabs(mm1 - mm2);
-        const double NE = fabs(mp1 - m0) + d12;
-        const bool z = (NE == 0.0);
-        const unsigned zm = __ballot_sync(FULL, cvalid && z);
-        const bool zprev = lane ? ((zm >> (lane - 1)) & 1u) : ((zcarry >> q) & 1u);
-        zcarry = (zcarry & ~(1u << q)) | (((zm >> 31) & 1u) << q);
-        if (cvalid) {
+          const double d12 = fabs(mm1 - mm2);
+          const double NE = fabs(mp1 - m0) + d12;
+          const bool z = (NE == 0.0);
+          const unsigned zm = __ballot_sync(FULL, cvalid && z);
+          const bool zprev = lane ? ((zm >> (lane - 1)) & 1u) : zc_in;
+          if (lane == 0) W.pf[q] = (E >> 30) | (((zm >> 31) & 1u) << 2);
           double add = 0.0;
-          if (cn < nk - 1) add = 0.5 * h * (f2 + f3);  // trapezoid part of interval cn
-          if (edge || z || zprev) {
+          if (s >= 1 && s < nk) add = 0.5 * ((s == nk - 1) ? hl : dx) * (f3 + f4);  // interval (s-1, s)
+          if (cvalid && (cn == 0 || cn >= nk - 2 || z || zprev)) {
             // h_c^2 b_c - h_{c-1}^2 tL_c: vanishes at regular interior nodes (uniform h, no ties)
             double tc = 0.0;
             if (!z) {
@@ -317,23 +398,23 @@ __global__ void __launch_bounds__(FW * 32, 3) limber_spline_fast_kernel(const Li
           }
           W.acc[q][lane] += add;
         }
+        __syncwarp();
       }
-      __syncwarp();
-    }
 
-    if (redo) {
-      if (lane < np) {
-        const unsigned long long task =
-            ((unsigned long long)ic * P.npair + W.prs[lane].out) * P.nl + il;
-        const unsigned long long at = atomicAdd(G.redo, 1ull);
-        if (at < G.redo_cap) G.redo[1 + at] = task;
+      if (redo) {
+        if (lane < np) {
+          const unsigned long long task =
+              ((unsigned long long)ic * P.npair + W.prs[lane].out) * P.nl + il;
+          const unsigned long long at = atomicAdd(G.redo, 1ull);
+          if (at < G.redo_cap) G.redo[1 + at] = task;
+        }
+        continue;
       }
-      continue;
-    }
 #pragma unroll 1
-    for (int q = 0; q < np; ++q) {
-      const double v = warp_sum(W.acc[q][lane]);
-      if (lane == 0) P.cl[((size_t)ic * P.npair + W.prs[q].out) * P.nl + il] = v / lp1h;  // src/ccl_cls.c:340
+      for (int q = 0; q < np; ++q) {
+        const double v = warp_sum(W.acc[q][lane]);
+        if (lane == 0) P.cl[((size_t)ic * P.npair + W.prs[q].out) * P.nl + il] = v / lp1h;  // src/ccl_cls.c:340
+      }
     }
   }
 }
@@ -377,7 +458,8 @@ cudaError_t launch_limber_fast(const LimberProblem& prob, const FastPlan& plan, 
     cudaFuncSetAttribute(limber_spline_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     attr_set[dev & 63] = true;
   }
-  limber_spline_fast_kernel<<<(unsigned)((long long)prob.ncosmo * prob.nl), FW * 32, fsm, stream>>>(prob, plan);
+  const long long nlt = (prob.nl + LPC - 1) / LPC;
+  limber_spline_fast_kernel<<<(unsigned)((long long)prob.ncosmo * nlt), FW * 32, fsm, stream>>>(prob, plan);
   launch_limber_redo(prob, plan, stream);
   return cudaGetLastError();
 }
