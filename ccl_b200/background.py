@@ -140,7 +140,9 @@ class Background:
             return [a * y[1] / (a * a * a * hn), a * 1.5 * hn * a * om * y[0]]
 
         y0 = [ai, ai ** 3 * float(h_over_h0(ai, p))]
-        nodes = np.concatenate([self.a[self.a >= ai], [1.0]])
+        an = self.a[self.a >= ai]
+        nodes = an if an[-1] == 1.0 else np.concatenate([an, [1.0]])
+        appended = nodes.size - an.size
         sol = solve_ivp(rhs, (np.log(ai), 0.0), y0, method="DOP853", t_eval=np.log(nodes), rtol=1e-11,
                         atol=1e-30)
         g = sol.y[0]
@@ -151,9 +153,9 @@ class Background:
         lo = self.a < ai
         D[lo] = self.a[lo]
         f[lo] = 1.0
-        an = nodes[:-1]
-        D[~lo] = g[:-1]
-        f[~lo] = yy[:-1] / (an * an * h_over_h0(an, p) * g[:-1])
+        ng = nodes.size - appended
+        D[~lo] = g[:ng]
+        f[~lo] = yy[:ng] / (an * an * h_over_h0(an, p) * g[:ng])
         self.growth = D / growth0
         self.fgrowth = f
         self.growth0 = growth0

@@ -1,0 +1,54 @@
+"""``angular_cl`` with the pyccl signature (pyccl/cells.py:10-175), Limber branch.
+
+The call site of the hot path: ``lib.angular_cl_vec_limber(cosmo.cosmo, clt1, clt2, psp, ell,
+integ_type, nell, status)`` (pyccl/cells.py:149-158) becomes one C-ABI call,
+``ccl_b200_angular_cls_limber`` (include/ccl_b200.h), on device-resident tables.
+"""
+import numpy as np
+
+from . import _lib, lowlevel
+from .errors import CCLWarning, check, warnings
+from .parameters import DEFAULT_POWER_SPECTRUM
+
+__all__ = ("angular_cl", "integ_types")
+
+# pyccl/pyutils.py:33-35 (ccl_integration_t, include/ccl_utils.h:12-15)
+integ_types = {'qag_quad': _lib.INTEGRATION_QAG_QUAD, 'spline': _lib.INTEGRATION_SPLINE}
+
+
+def angular_cl(cosmo, tracer1, tracer2, ell, *, p_of_k_a=DEFAULT_POWER_SPECTRUM, l_limber=-1,
+               limber_max_error=0.01, limber_integration_method="qag_quad",
+               non_limber_integration_method="FKEM", fkem_chi_min=None, fkem_Nchi=None,
+               p_of_k_a_lin=DEFAULT_POWER_SPECTRUM, return_meta=False):
+    if cosmo["Omega_k"] != 0:
+        warnings.warn("CCL does not properly use the hyperspherical Bessel functions when computing angular "
+                      "power spectra in non-flat cosmologies!", category=CCLWarning, importance='low')
+    if limber_integration_method not in integ_types:
+        raise ValueError("Limber integration method %s not supported" % limber_integration_method)
+    if non_limber_integration_method not in ["FKEM"]:
+        raise ValueError("Non-Limber integration method %s not supported" % limber_integration_method)
+    if type(l_limber) is str:
+        if l_limber != "auto":
+            raise ValueError("l_limber must be an integer or'auto'")
+        raise NotImplementedError("the FKEM non-Limber integrator is outside the Limber hot path (SURVEY.md 2b)")
+    cosmo.compute_distances()
+    if p_of_k_a is None:
+        p_of_k_a = DEFAULT_POWER_SPECTRUM
+    psp = cosmo.parse_pk2d(p_of_k_a, is_linear=False)
+    ell_use = np.atleast_1d(np.asarray(ell, dtype=float))
+    if not (np.diff(ell_use) > 0).all():
+        raise ValueError("ell values must be monotonically increasing")
+    if ell_use[0] < l_limber:
+        raise NotImplementedError("the FKEM non-Limber integrator is outside the Limber hot path (SURVEY.md 2b)")
+    # growth is only read when P(k,a) is evaluated below its a-range (src/ccl_f2d.c:351-370)
+    need_growth = any(r[1] > cosmo.comoving_radial_distance(max(psp._a[0], cosmo._bg.a[0]))
+                      for t in (tracer1, tracer2) for r in t._chi_range) if psp._a[0] > cosmo._bg.a[0] else False
+    dev = cosmo._device(need_growth=need_growth)
+    trs1 = tracer1._device(cosmo)
+    trs2 = trs1 if tracer2 is tracer1 else tracer2._device(cosmo)
+    cl, status = lowlevel.angular_cls_limber(dev, trs1, trs2, psp._device(), ell_use,
+                                             integ_types[limber_integration_method])
+    if np.ndim(ell) == 0:
+        cl = cl[0]
+    check(status, cosmo)
+    return (cl, {"l_limber": l_limber}) if return_meta else cl

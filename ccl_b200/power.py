@@ -187,7 +187,7 @@ def halofit_table(p, a_arr, lk_arr, logplin):
 
         def moments(R, which):
             lnkmax = max(lnkmax_t, np.log(30. / R))
-            x, w = _gl_nodes(lnkmin, lnkmax, 400)
+            x, w = _gl_nodes(lnkmin, lnkmax, int(400 * max(1.0, (lnkmax - lnkmin) / 25.0)))
             kk = np.exp(x)
             k2 = kk * kk
             base = _plin_row_eval(spl, lk_arr, x) * kk * k2 / 2.0 / np.pi / np.pi * np.exp(-k2 * R * R)
@@ -201,7 +201,11 @@ def halofit_table(p, a_arr, lk_arr, logplin):
         lo, hi = np.log(1e-64), np.log(1e16)
         # bracket more tightly first: sigma2(R) is monotonically decreasing in R
         lo, hi = np.log(1e-6), np.log(1e4)
-        if f(lo) * f(hi) > 0:
+        flo = f(lo)
+        while flo < 0 and lo > np.log(1e-64):   # the reference brackets with [1e-64, 1e16]
+            lo = max(lo - np.log(1e4), np.log(1e-64))
+            flo = f(lo)
+        if flo * f(hi) > 0:
             raise RuntimeError("could not solve for non-linear scale for halofit at scale factor %f" % a_arr[i])
         lnr = brentq(f, lo, hi, xtol=1e-13, rtol=1e-13)
         R = np.exp(lnr)

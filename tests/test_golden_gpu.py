@@ -1,0 +1,75 @@
+"""GPU: the pyccl-compatible API (Cosmology, tracers, angular_cl) through the C ABI against
+(i) the reference's golden C_ell curves at its own tolerances (benchmarks/test_cells.py) and
+(ii) the CPU oracle on the same tables at BASELINE.json's parity tolerances."""
+import numpy as np
+import pytest
+
+import oracle
+from common import parity_error
+from golden_setup import CASES, SPLINE_CASES, oracle_objects, set_up, sigma_cv
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["analytic", "histo"])
+def golden(request):
+    cosmo, trc, lfc, bmk = set_up(request.param)
+    oc, op, otr = oracle_objects(cosmo, trc)
+    return dict(cosmo=cosmo, trc=trc, oc=oc, op=op, otr=otr, lfc=lfc, bmk=bmk)
+
+
+@pytest.mark.parametrize("t1,t2,bm,a1b1,a1b2,a2b1,a2b2,fl", CASES)
+def test_cells_qag(golden, t1, t2, bm, a1b1, a1b2, a2b1, a2b2, fl):
+    import ccl_b200 as ccl
+    g = golden
+    ells = g["lfc"]['ells']
+    cl = ccl.angular_cl(g["cosmo"], g["trc"][t1], g["trc"][t2], ells, limber_integration_method='qag_quad')
+    el = sigma_cv(g["bmk"], g["lfc"], a1b1, a1b2, a2b1, a2b2)
+    assert np.all(np.fabs(cl * g["lfc"][fl] - g["bmk"][bm]) < 0.1 * el)          # the reference's assertion
+    ref, st = oracle.angular_cl(g["oc"], g["otr"][t1], g["otr"][t2], g["op"], ells, oracle.INTEG_QAG)
+    assert st == 0
+    assert parity_error(cl, ref, None, 1e-5) < 1e-5                                # qag_quad parity
+
+
+@pytest.mark.parametrize("t1,t2,bm,a1b1,a1b2,a2b1,a2b2,fl", SPLINE_CASES + [CASES[3], CASES[11], CASES[16], CASES[18]])
+def test_cells_spline(golden, t1, t2, bm, a1b1, a1b2, a2b1, a2b2, fl):
+    import ccl_b200 as ccl
+    g = golden
+    ells = g["lfc"]['ells']
+    cl = ccl.angular_cl(g["cosmo"], g["trc"][t1], g["trc"][t2], ells, limber_integration_method='spline')
+    el = sigma_cv(g["bmk"], g["lfc"], a1b1, a1b2, a2b1, a2b2)
+    assert np.all(np.fabs(cl * g["lfc"][fl] - g["bmk"][bm]) < 0.2 * el)
+    redo = lambda: oracle.angular_cl(g["oc"], g["otr"][t1], g["otr"][t2], g["op"], ells, oracle.INTEG_SPLINE)[0]
+    assert parity_error(cl, redo(), redo, 1e-10) < 1e-10                            # spline parity
+
+
+def test_api_contract(golden):
+    """pyccl/tests/test_cells.py:24-101: scalar ell, symmetry, error paths."""
+    import ccl_b200 as ccl
+    g = golden
+    c, t = g["cosmo"], g["trc"]
+    v = ccl.angular_cl(c, t['g1'], t['l2'], 50.0, limber_integration_method='spline')
+    assert np.ndim(v) == 0 and np.isfinite(v)
+    ells = np.array([10., 100., 1000.])
+    a = ccl.angular_cl(c, t['g1'], t['l2'], ells, limber_integration_method='spline')
+    b = c.angular_cl(t['l2'], t['g1'], ells, limber_integration_method='spline')
+    assert np.allclose(a, b, rtol=1e-12, atol=0)
+    with pytest.raises(ValueError):
+        ccl.angular_cl(c, t['g1'], t['g1'], ells[::-1])
+    with pytest.raises(ValueError):
+        ccl.angular_cl(c, t['g1'], t['g1'], ells, limber_integration_method='guad')
+    with pytest.raises(ValueError):
+        ccl.angular_cl(c, t['g1'], t['g1'], ells, non_limber_integration_method='xx')
+    # Pk2D passed explicitly gives the same answer as the cosmology's own spectrum
+    pk = c.get_nonlin_power()
+    d = ccl.angular_cl(c, t['g1'], t['l2'], ells, p_of_k_a=pk, limber_integration_method='spline')
+    assert np.array_equal(a, d)
+    # accessors evaluated on the device agree with the host tables
+    chi = np.linspace(10., 3000., 7)
+    w = t['g1'].get_kernel(chi, cosmo=c)
+    assert w.shape == (1, 7) and np.all(np.isfinite(w))
+    assert np.allclose(t['l1'].get_f_ell(np.array([2., 20.]), cosmo=c)[0],
+                       [np.sqrt(4 * 3 * 2 * 1.), 20.5 ** 2 * (1 - 1.25 / 20.5 ** 2)])
+    kk = np.array([1e-3, 1e-1, 1.0])
+    p = pk(kk, 0.5, c)
+    assert p.shape == (3,) and np.all(p > 0)

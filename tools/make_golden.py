@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Extract the reference's golden vectors for the Limber path into tests/golden/.
+
+Source (read-only, only available in the build container): /root/reference/benchmarks/data/
+  * run_{b1b1,b1b2,b2b1,b2b2}{analytic,histo}_log_cl_{dd,dl,di,dc,ll,li,lc,ii}.txt, run_log_cl_cc.txt:
+    C_ell of 23 tracer-pair types from an independent code, asserted by the reference at
+    0.1 sigma (qag_quad) / 0.2 sigma (spline) of cosmic variance (benchmarks/test_cells.py:125-223)
+  * bin{1,2}_histo.txt, ia_amp_{analytic,histo}_{1,2}.txt: the n(z) and IA amplitude inputs
+Only the 541 multipoles the reference test reads are kept (benchmarks/test_cells.py:22-26).
+"""
+import os
+import sys
+
+import numpy as np
+
+SRC = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/benchmarks/data/"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+nls = 541
+ells = np.zeros(nls)
+ells[:50] = np.arange(50) + 2
+ells[50:] = ells[49] + 6 * (np.arange(nls - 50) + 1)
+out = {"ells": ells}
+for nztyp in ("analytic", "histo"):
+    for b in ("b1b1", "b1b2", "b2b1", "b2b2"):
+        for kind in ("dd", "dl", "di", "dc", "ll", "li", "lc", "ii"):
+            f = os.path.join(SRC, "run_%s%s_log_cl_%s.txt" % (b, nztyp, kind))
+            if os.path.exists(f):
+                out["%s_%s_%s" % (nztyp, b, kind)] = np.loadtxt(f, unpack=True)[1][ells.astype(int)]
+    for i in (1, 2):
+        out["ia_amp_%s_%d" % (nztyp, i)] = np.loadtxt(os.path.join(SRC, "ia_amp_%s_%d.txt" % (nztyp, i)))
+for i in (1, 2):
+    out["bin%d_histo" % i] = np.loadtxt(os.path.join(SRC, "bin%d_histo.txt" % i))
+out["cc"] = np.loadtxt(os.path.join(SRC, "run_log_cl_cc.txt"), unpack=True)[1][ells.astype(int)]
+np.savez_compressed(os.path.join(OUT, "cells_benchmark.npz"), **out)
+print("wrote %d arrays to %s" % (len(out), os.path.join(OUT, "cells_benchmark.npz")))
