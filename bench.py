@@ -66,6 +66,38 @@ def fill_batch(batch, tables, nslots, offset0=0):
             batch.add_tracer(ic, **s)
 
 
+def stack_host_tables(tables, nslots, offset0=0):
+    """The same per-slot tables as fill_batch, as stacked host arrays with a leading cosmology axis
+    (what a likelihood code holds for a batch of cosmologies); consumed by LibBatch.set_stacked."""
+    idx = [(ic + offset0) % len(tables) for ic in range(nslots)]
+    shift = np.array([1e-3 * ((ic + offset0) // len(tables)) for ic in range(nslots)])
+    nmax = max(t["bg"]["chi"].size for t in tables)
+    n_per = np.array([tables[i]["bg"]["chi"].size for i in idx], dtype=np.int32)
+    chi = np.zeros((nslots, nmax))
+    a = np.zeros((nslots, nmax))
+    for ic, i in enumerate(idx):
+        bg = tables[i]["bg"]
+        chi[ic, :n_per[ic]] = bg["chi"]
+        a[ic, :n_per[ic]] = bg["a"]
+    t0 = tables[0]
+    stk = dict(count=nslots, achi=(n_per, chi, a),
+               growth=(np.stack([tables[i]["bg"]["a_growth"] for i in idx]),
+                       np.stack([tables[i]["bg"]["growth"] for i in idx])),
+               chi_max_nokernel=np.array([tables[i]["cmax"] for i in idx]),
+               pk=(t0["pk"]["lk"], t0["pk"]["a"],
+                   np.stack([tables[i]["pk"]["logp"] for i in idx]) + shift[:, None, None], 1, 2, True),
+               tracers=[])
+    for it, s0 in enumerate(t0["subs"]):
+        tr = dict(der_bessel=s0.get("der_bessel", 0), der_angles=s0.get("der_angles", 0),
+                  chi=np.stack([tables[i]["subs"][it]["chi"] for i in idx]),
+                  w=np.stack([tables[i]["subs"][it]["w"] for i in idx]))
+        if s0.get("fa") is not None:
+            tr["a"] = s0["a"]                                   # a = 1/(1+z) grid shared by all cosmologies
+            tr["fa"] = np.stack([tables[i]["subs"][it]["fa"] for i in idx])
+        stk["tracers"].append(tr)
+    return stk
+
+
 def algorithmic_flops(batch, tables, nslots, colls, pairs, ells, offset0=0):
     """Sum over (cosmology, pair, ell) of nk * (F_base + sum F_tracer + F_akima)."""
     kinds = ["nc" if t[0] < 5 else "wl" for t in enumerate(colls)]
@@ -291,8 +323,14 @@ def main():
     st = C.c_int(0)
     peak = _lib.load().ccl_b200_measure_fp64_peak(C.byref(st))
     achieved = flops / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes of one ncu capture (tools/ncu_traffic.sh)
+    if os.path.exists(tfile):
+        tj = json.load(open(tfile))
+        if tj.get("ncosmo") == nloc and tj.get("method") == args.method:
+            traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak and peak > 0 else None, "traffic": None,
+                "frac": achieved / peak if peak and peak > 0 else None, "traffic": traffic,
                 "kernel": ("limber_spline_fast_kernel" if batch.last_used_fast_path else "limber_spline_kernel")
                 if args.method == "spline" else "limber_qag_kernel",
                 "kernel_ms": kern_ms, "algorithmic_flops_per_launch": flops, "integrand_nodes_per_launch": nodes,
@@ -305,14 +343,28 @@ def main():
         cl_host = None
         e2e_steps = max(1, min(args.steps, 3))
 
+        parts = {"stage_host_tables_ms": 0.0, "h2d_and_table_prep_ms": 0.0, "limber_and_d2h_ms": 0.0}
+        stk = stack_host_tables(tables, nloc, off)              # the caller's host buffers
+        cl_pinned = torch.empty((nloc, npair, nl), dtype=torch.float64, pin_memory=True).numpy()
+
         def e2e_step():
+            t_a = time.perf_counter()
             batch.reset()
-            fill_batch(batch, tables, nloc, off)
+            batch.set_stacked(0, stk)
+            t_b = time.perf_counter()
             batch.commit()
-            return batch.angular_cl(colls, pairs, ells, method)
+            t_c = time.perf_counter()
+            out = batch.angular_cl(colls, pairs, ells, method, out=cl_pinned)
+            t_d = time.perf_counter()
+            parts["stage_host_tables_ms"] += (t_b - t_a) * 1e3
+            parts["h2d_and_table_prep_ms"] += (t_c - t_b) * 1e3
+            parts["limber_and_d2h_ms"] += (t_d - t_c) * 1e3
+            return out
 
         e2e_step()
         sync_all()
+        for k_ in parts:
+            parts[k_] = 0.0
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             cl_host, stat_host, _ = e2e_step()
@@ -326,7 +378,10 @@ def main():
         d2h = int(cl_host.nbytes + stat_host.nbytes)
         e2e = {"value": n_cl_total / dt, "unit": "C_ell/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": dt * 1e3,
-               "note": "per step: stage host tables, 1 H2D copy, device table prep, Limber kernel, D2H of all C_ell"}
+               "breakdown_rank0": {k_: v_ / e2e_steps for k_, v_ in parts.items()},
+               "identical_to_resident_path": bool(np.array_equal(cl_host, d_cl.cpu().numpy())),
+               "note": "per step through the host-buffer C ABI: stacked host tables -> pinned staging arena (host "
+                       "threads), 1 H2D copy, device table prep, Limber kernels, D2H of all C_ell into pinned memory"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

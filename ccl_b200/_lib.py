@@ -78,6 +78,14 @@ SIGNATURES = {
     "ccl_b200_batch_tracer_chi_range": (None, [_vp, C.c_int, C.c_int, _dp, _dp]),
     "ccl_b200_batch_reset": (None, [_vp]),
     "ccl_b200_batch_commit": (None, [_vp, _ip]),
+    "ccl_b200_batch_set_achi_stacked": (None, [_vp, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _ip]),
+    "ccl_b200_batch_set_growth_stacked": (None, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip]),
+    "ccl_b200_batch_set_chi_max_nokernel_stacked": (None, [_vp, C.c_int, C.c_int, _dp]),
+    "ccl_b200_batch_set_pk2d_stacked": (None, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int,
+                                               C.c_int, C.c_int, _ip]),
+    "ccl_b200_batch_add_tracer_stacked": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
+                                                    _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_int,
+                                                    C.c_int, C.c_int, C.c_int, _ip]),
     "ccl_b200_batch_h2d_bytes": (C.c_ulonglong, [_vp]),
     "ccl_b200_batch_arena_bytes": (C.c_ulonglong, [_vp]),
     "ccl_b200_batch_angular_cls_limber": (None, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp,

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ccl_b200.h"
@@ -115,13 +116,37 @@ struct HostBuf {  // growable host staging; pinned once it is large
     p = q; cap = ncap; pinned = want_pinned;
     return true;
   }
+  // With defer set, put() only reserves the destination; flush() then copies every pending block
+  // with several host threads (the stacked setters stage GBs of tables per call).
+  struct Pending { size_t off; const double* src; size_t n; };
+  bool defer = false;
+  std::vector<Pending> pending;
   size_t put(const double* src, size_t n) {
     size_t off = (size + ALIGN_D - 1) / ALIGN_D * ALIGN_D;
     if (!reserve(off + n)) return (size_t)-1;
     if (off > size) memset(p + size, 0, (off - size) * sizeof(double));
-    memcpy(p + off, src, n * sizeof(double));
+    if (defer) pending.push_back(Pending{off, src, n});
+    else memcpy(p + off, src, n * sizeof(double));
     size = off + n;
     return off;
+  }
+  void flush() {
+    if (pending.empty()) return;
+    size_t total = 0;
+    for (const Pending& q : pending) total += q.n;
+    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (total * sizeof(double) < (size_t(8) << 20)) nt = 1;
+    auto work = [&](unsigned t) {
+      for (size_t i = t; i < pending.size(); i += nt)
+        memcpy(p + pending[i].off, pending[i].src, pending[i].n * sizeof(double));
+    };
+    if (nt == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+      for (auto& x : th) x.join();
+    }
+    pending.clear();
   }
 };
 
@@ -516,6 +541,7 @@ struct ccl_b200_batch {
   TableSet ts;
   unsigned long long last_qag_evals = 0;
   bool last_fast = false;  // the last 'spline' launch used the grid-sharing kernels
+  DevBuf out;   // device result buffer of the host-buffer entry (kept across calls)
   DevBuf call;  // per-batch call buffers (colls, pairs, ells, counters, outputs)
 };
 
@@ -1027,6 +1053,94 @@ int ccl_b200_batch_add_tracer(ccl_b200_batch* b, int icosmo, int der_bessel, int
   return (int)p.tracers.size() - 1;
 }
 
+// ---- stacked setters: arrays carry a leading cosmology axis; slot = first + i ----
+#define BATCH_RANGE(b, first, count)                                                        \
+  if (*status) return;                                                                      \
+  if (!(b) || (first) < 0 || (count) < 0 || (first) + (count) > (int)(b)->ts.cosmos.size()) { \
+    *status = CCL_B200_ERROR_INCONSISTENT;                                                  \
+    set_err("ccl_b200: batch slots [%d, %d) out of range", (first), (first) + (count));    \
+    return;                                                                                 \
+  }
+
+void ccl_b200_batch_set_achi_stacked(ccl_b200_batch* b, int first, int count, const int* n_per, int stride,
+                                     const double* chi, const double* a, int* status) {
+  BATCH_RANGE(b, first, count);
+  b->ts.raw.defer = true;
+  for (int i = 0; i < count && !*status; ++i) {
+    const int n = n_per ? n_per[i] : stride;
+    if (n < 5 || n > stride) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: a(chi) spline needs 5 <= n <= stride"); break; }
+    b->ts.plan_s1(b->ts.cosmos[first + i].achi, 0, n, chi + (size_t)i * stride, a + (size_t)i * stride, status);
+  }
+  b->ts.raw.defer = false;
+  b->ts.raw.flush();
+  b->ts.committed = false;
+}
+
+void ccl_b200_batch_set_growth_stacked(ccl_b200_batch* b, int first, int count, int n, int stride_a,
+                                       const double* a, const double* growth, int* status) {
+  BATCH_RANGE(b, first, count);
+  if (n < 5) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: growth spline needs >= 5 nodes"); return; }
+  b->ts.raw.defer = true;
+  for (int i = 0; i < count && !*status; ++i)
+    b->ts.plan_s1(b->ts.cosmos[first + i].growth, 0, n, a + (size_t)i * stride_a, growth + (size_t)i * n, status);
+  b->ts.raw.defer = false;
+  b->ts.raw.flush();
+  b->ts.committed = false;
+}
+
+void ccl_b200_batch_set_chi_max_nokernel_stacked(ccl_b200_batch* b, int first, int count, const double* chi) {
+  if (!b || first < 0 || count < 0 || first + count > (int)b->ts.cosmos.size()) return;
+  for (int i = 0; i < count; ++i) b->ts.cosmos[first + i].chi_max_nokernel = chi[i];
+}
+
+void ccl_b200_batch_set_pk2d_stacked(ccl_b200_batch* b, int first, int count, const double* lk_arr, int nk,
+                                     const double* a_arr, int na, const double* pk_arr, int order_lok,
+                                     int order_hik, int is_logp, int* status) {
+  BATCH_RANGE(b, first, count);
+  b->ts.raw.defer = true;
+  for (int i = 0; i < count && !*status; ++i) {
+    CosmoPlan& p = b->ts.cosmos[first + i];
+    p.has_psp = b->ts.plan_f2d(p.psp, na, a_arr, nk, lk_arr, pk_arr + (size_t)i * na * nk, nullptr, nullptr, 0,
+                               order_lok, order_hik, GROWTH_CCL, is_logp, 0, 2, status);
+  }
+  b->ts.raw.defer = false;
+  b->ts.raw.flush();
+  b->ts.committed = false;
+}
+
+int ccl_b200_batch_add_tracer_stacked(ccl_b200_batch* b, int first, int count, int der_bessel, int der_angles,
+                                      int n_w, int stride_chi, const double* chi_w, const double* w_w,
+                                      int na_ka, int stride_a, const double* a_ka, int nk_ka,
+                                      const double* lk_ka, const double* fka_arr, const double* fk_arr,
+                                      const double* fa_arr, int is_fka_log, int is_factorizable,
+                                      int extrap_order_lok, int extrap_order_hik, int* status) {
+  if (*status) return -1;
+  if (!b || first < 0 || count < 0 || first + count > (int)b->ts.cosmos.size()) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    return -1;
+  }
+  int idx = -1;
+  b->ts.raw.defer = true;
+  for (int i = 0; i < count && !*status; ++i) {
+    CosmoPlan& p = b->ts.cosmos[first + i];
+    TracerPlan t;
+    const size_t si = (size_t)i;
+    if (!b->ts.plan_tracer(t, p.chi_max_nokernel, der_bessel, der_angles, n_w,
+                           chi_w ? chi_w + si * stride_chi : nullptr, w_w ? w_w + si * n_w : nullptr, na_ka,
+                           a_ka ? a_ka + si * stride_a : nullptr, nk_ka, lk_ka,
+                           fka_arr ? fka_arr + si * na_ka * nk_ka : nullptr, fk_arr ? fk_arr + si * nk_ka : nullptr,
+                           fa_arr ? fa_arr + si * na_ka : nullptr, is_fka_log, is_factorizable, extrap_order_lok,
+                           extrap_order_hik, status))
+      break;
+    p.tracers.push_back(t);
+    idx = (int)p.tracers.size() - 1;
+  }
+  b->ts.raw.defer = false;
+  b->ts.raw.flush();
+  b->ts.committed = false;
+  return *status ? -1 : idx;
+}
+
 void ccl_b200_batch_tracer_chi_range(const ccl_b200_batch* b, int icosmo, int itracer, double* chi_min,
                                      double* chi_max) {
   const TracerPlan& t = b->ts.cosmos[icosmo].tracers[itracer];
@@ -1121,10 +1235,9 @@ void ccl_b200_batch_angular_cls_limber(ccl_b200_batch* b, int ncoll, const int* 
   const size_t nc = b->ts.cosmos.size();
   const size_t ncl = nc * npair * (size_t)nl;
   const size_t nst = nc * (size_t)npair;
-  DevBuf out;
-  if (!out.reserve(ncl * 8 + nst * 2 * sizeof(int) + 512, status)) return;
-  double* d_cl = reinterpret_cast<double*>(out.p);
-  int* d_st = reinterpret_cast<int*>(out.p + (ncl * 8 + 255) / 256 * 256);
+  if (!b->out.reserve(ncl * 8 + nst * 2 * sizeof(int) + 512, status)) return;
+  double* d_cl = reinterpret_cast<double*>(b->out.p);
+  int* d_st = reinterpret_cast<int*>(b->out.p + (ncl * 8 + 255) / 256 * 256);
   ccl_b200_batch_angular_cls_limber_dev(b, ncoll, coll_start, coll_count, npair, pair1, pair2, nl, ell,
                                         integration_method, d_cl, d_st, nullptr, status);
   if (*status) return;

@@ -239,6 +239,62 @@ class LibBatch:
         _check(st.value, "batch_add_tracer")
         return idx
 
+    # ---- stacked setters (one C call per table kind for a whole range of slots) ----
+    def set_stacked(self, first, stk):
+        """Fill slots [first, first + count) from stacked host arrays.
+
+        `stk` = dict(count, achi=(n_per, chi[count, nmax], a[count, nmax]), growth=(a[n] or [count, n], D[count, n]),
+        chi_max_nokernel=[count], pk=(lk[nk], a[na], pk[count, na, nk], order_lok, order_hik, is_logp),
+        tracers=[dict(der_bessel, der_angles, chi=[n] or [count, n], w=[count, n], a=..., fa=[count, na], ...)]).
+        """
+        L = _lib.load()
+        st = C.c_int(0)
+        count = int(stk["count"])
+        n_per, chi, a = stk["achi"]
+        kn, pn = iarr(n_per)
+        kc, pc = darr(chi)
+        ka, pa = darr(a)
+        assert kc.shape == ka.shape == (count, kc.shape[1])
+        L.ccl_b200_batch_set_achi_stacked(self.h, first, count, pn, kc.shape[1], pc, pa, C.byref(st))
+        _check(st.value, "batch_set_achi_stacked")
+        if stk.get("growth") is not None:
+            ag, D = stk["growth"]
+            kg, pg = darr(ag)
+            kd, pd_ = darr(D)
+            L.ccl_b200_batch_set_growth_stacked(self.h, first, count, kd.shape[1], 0 if kg.ndim == 1 else kg.shape[1],
+                                                pg, pd_, C.byref(st))
+            _check(st.value, "batch_set_growth_stacked")
+        if stk.get("chi_max_nokernel") is not None:
+            kx, px = darr(stk["chi_max_nokernel"])
+            L.ccl_b200_batch_set_chi_max_nokernel_stacked(self.h, first, count, px)
+        lk, apk, pk, olo, ohi, islog = stk["pk"]
+        kl, pl = darr(lk)
+        kap, pap = darr(apk)
+        kp, pp = darr(pk)
+        assert kp.shape == (count, len(kap), len(kl))
+        L.ccl_b200_batch_set_pk2d_stacked(self.h, first, count, pl, len(kl), pap, len(kap), pp, int(olo), int(ohi),
+                                          int(islog), C.byref(st))
+        _check(st.value, "batch_set_pk2d_stacked")
+        for t in stk["tracers"]:
+            chi_w, w = t.get("chi"), t.get("w")
+            kcw, pcw = darr(chi_w)
+            kw, pw = darr(w)
+            kta, pta = darr(t.get("a"))
+            ktl, ptl = darr(t.get("lk"))
+            kfka, pfka = darr(t.get("fka"))
+            kfk, pfk = darr(t.get("fk"))
+            kfa, pfa = darr(t.get("fa"))
+            n_w = 0 if kw is None else kw.shape[1]
+            na = 0 if kta is None else kta.shape[-1]
+            nk = 0 if ktl is None else len(ktl)
+            L.ccl_b200_batch_add_tracer_stacked(
+                self.h, first, count, int(t.get("der_bessel", 0)), int(t.get("der_angles", 0)), n_w,
+                0 if (kcw is None or kcw.ndim == 1) else kcw.shape[1], pcw, pw, na,
+                0 if (kta is None or kta.ndim == 1) else kta.shape[1], pta, nk, ptl, pfka, pfk, pfa,
+                int(t.get("is_logt", False)), int(kfka is None), int(t.get("extrap_order_lok", 0)),
+                int(t.get("extrap_order_hik", 2)), C.byref(st))
+            _check(st.value, "batch_add_tracer_stacked")
+
     def tracer_chi_range(self, ic, it):
         lo, hi = C.c_double(), C.c_double()
         _lib.load().ccl_b200_batch_tracer_chi_range(self.h, ic, it, C.byref(lo), C.byref(hi))
@@ -265,10 +321,16 @@ class LibBatch:
         el, pel = darr(ells)
         return (cs, cc, p1, p2, el), (len(collections), pcs, pcc, len(pairs), pp1, pp2, len(el), pel)
 
-    def angular_cl(self, collections, pairs, ells, method=_lib.INTEGRATION_SPLINE):
-        """Host-buffer entry: returns (cl[ncosmo, npair, nl], status[ncosmo, npair], status)."""
+    def angular_cl(self, collections, pairs, ells, method=_lib.INTEGRATION_SPLINE, out=None):
+        """Host-buffer entry: returns (cl[ncosmo, npair, nl], status[ncosmo, npair], status).
+        `out` may be a preallocated C-contiguous float64 array (e.g. a view of pinned memory)."""
         keep, g = self._geometry(collections, pairs, ells)
-        cl = np.empty((self.ncosmo, len(pairs), len(keep[4])))
+        shape = (self.ncosmo, len(pairs), len(keep[4]))
+        if out is not None:
+            assert out.shape == shape and out.dtype == np.float64 and out.flags.c_contiguous
+            cl = out
+        else:
+            cl = np.empty(shape)
         stat = np.zeros((self.ncosmo, len(pairs)), dtype=np.int32)
         st = C.c_int(0)
         _lib.load().ccl_b200_batch_angular_cls_limber(self.h, *g, int(method), cl.ctypes.data_as(_lib._dp),

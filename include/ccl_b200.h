@@ -163,6 +163,25 @@ int ccl_b200_batch_add_tracer(ccl_b200_batch *b, int icosmo, int der_bessel, int
                               int nk_ka, const double *lk_ka, const double *fka_arr, const double *fk_arr,
                               const double *fa_arr, int is_fka_log, int is_factorizable,
                               int extrap_order_lok, int extrap_order_hik, int *status);
+/* Stacked setters for likelihood batches: one call fills slots [first, first+count).  Value arrays
+ * carry a leading cosmology axis ([count][n] row-major); abscissa arrays have a stride between
+ * consecutive cosmologies, 0 meaning one grid shared by all.  Same per-slot semantics as the
+ * single-slot setters above (and as ccl_cl_tracer_t_new / set_pk2d_new_from_arrays); the copies into
+ * the pinned staging arena run on several host threads. */
+void ccl_b200_batch_set_achi_stacked(ccl_b200_batch *b, int first, int count, const int *n_per /* NULL: stride */,
+                                     int stride, const double *chi, const double *a, int *status);
+void ccl_b200_batch_set_growth_stacked(ccl_b200_batch *b, int first, int count, int n, int stride_a,
+                                       const double *a, const double *growth, int *status);
+void ccl_b200_batch_set_chi_max_nokernel_stacked(ccl_b200_batch *b, int first, int count, const double *chi);
+void ccl_b200_batch_set_pk2d_stacked(ccl_b200_batch *b, int first, int count, const double *lk_arr, int nk,
+                                     const double *a_arr, int na, const double *pk_arr /* [count][na*nk] */,
+                                     int order_lok, int order_hik, int is_logp, int *status);
+int ccl_b200_batch_add_tracer_stacked(ccl_b200_batch *b, int first, int count, int der_bessel, int der_angles,
+                                      int n_w, int stride_chi, const double *chi_w, const double *w_w,
+                                      int na_ka, int stride_a, const double *a_ka, int nk_ka,
+                                      const double *lk_ka, const double *fka_arr, const double *fk_arr,
+                                      const double *fa_arr, int is_fka_log, int is_factorizable,
+                                      int extrap_order_lok, int extrap_order_hik, int *status);
 void ccl_b200_batch_tracer_chi_range(const ccl_b200_batch *b, int icosmo, int itracer, double *chi_min,
                                      double *chi_max);
 /* Forget all slots but keep the arena (re-use for the next set of cosmologies). */

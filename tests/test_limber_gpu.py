@@ -202,3 +202,25 @@ def test_batch_fast_redo_and_failures():
         if ok[q].any():
             redo = lambda: _oracle_all(bg, pk_cut, subs, colls, [pairs[q]], ELLS)[0][0][ok[q]]
             assert parity_error(cl[0, q][ok[q]], ref[q][ok[q]], redo, SPLINE_RTOL) < SPLINE_RTOL, pairs[q]
+
+
+def test_batch_stacked_setters_equal_per_slot():
+    """ccl_b200_batch_*_stacked fill the arena exactly like the per-slot setters."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import ccl_b200 as cb
+    tables = bench.build_host_tables(3)
+    colls, pairs, ells = bench.geometry()
+    ells = ells[::9]
+    n = 5
+    b1 = cb.LibBatch(n)
+    bench.fill_batch(b1, tables, n, 1)
+    b1.commit()
+    b2 = cb.LibBatch(n)
+    b2.set_stacked(0, bench.stack_host_tables(tables, n, 1))
+    b2.commit()
+    c1, s1, _ = b1.angular_cl(colls, pairs, ells)
+    c2, s2, _ = b2.angular_cl(colls, pairs, ells)
+    assert np.array_equal(c1, c2) and np.array_equal(s1, s2)
+    assert [b1.tracer_chi_range(4, t) for t in range(15)] == [b2.tracer_chi_range(4, t) for t in range(15)]
