@@ -179,6 +179,8 @@ def run_reference(args, rank):
     colls, pairs, ells = geometry()
     oc, op = oracle_cosmo(t["bg"]), oracle_pk(t["pk"])
     otr = [oracle_tracer(s, t["cmax"]) for s in t["subs"]]
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
+    oracle.set_num_threads(len(os.sched_getaffinity(0)))
     cores = oracle.num_threads()
 
     def one_pass():
@@ -199,8 +201,11 @@ def run_reference(args, rank):
         "unit": "C_ell/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "LSST-Y1-like 3x2pt likelihood batch: 4096 cosmologies x 120 pairs x 100 ells",
-                   "reference_impl": "oracle/ CPU restatement (GSL-based reference not buildable here)"},
+        "config": {"workload": "LSST-Y1-like 3x2pt likelihood batch (BASELINE configs[3]): %d cosmologies x "
+                               "120 pairs (5 NumberCounts + 10 WeakLensing) x 100 log-spaced ells 2..3000" % args.ncosmo,
+                   "method": "spline",
+                   "reference_impl": "oracle/ CPU restatement of src/ccl_cls.c + GSL (the GSL-based reference "
+                                     "is not buildable in this image: DESIGN.md section 3)"},
         "cpu_baseline": {"value": val, "unit": "C_ell/s", "cores": cores, "kind": "port", "sample": sample,
                          "cosmologies_per_s": 1.0 / dt},
         "e2e": {"value": val, "unit": "C_ell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -389,6 +394,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from common import oracle_cosmo, oracle_pk, oracle_tracer
         t = tables[off % len(tables)]
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
         oc, op = oracle_cosmo(t["bg"]), oracle_pk(t["pk"])
         otr = [oracle_tracer(s, t["cmax"]) for s in t["subs"]]
         t0 = time.perf_counter()

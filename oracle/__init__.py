@@ -94,6 +94,7 @@ def lib():
         L.o_integ_spline.argtypes = [C.c_int, _dp, _dp, C.c_double, C.c_double, _dp, _ip]
         L.o_qag41_test.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                    C.c_int, _dp, _dp, _ip]
+        L.o_set_num_threads.argtypes = [C.c_int]
         L.o_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -343,6 +344,11 @@ def qag41_test(kind, p, a, b, epsabs=0.0, epsrel=1e-4, limit=1000):
     n = C.c_int()
     st = lib().o_qag41_test(kind, p, a, b, epsabs, epsrel, limit, C.byref(r), C.byref(e), C.byref(n))
     return r.value, e.value, n.value, st
+
+
+def set_num_threads(n):
+    """Use n OpenMP threads (launchers such as torchrun export OMP_NUM_THREADS=1)."""
+    lib().o_set_num_threads(int(n))
 
 
 def num_threads():

@@ -1263,6 +1263,14 @@ int o_qag41_test(int kind, double p, double a, double b, double epsabs, double e
   return o_qag41(o_testf, &par, a, b, epsabs, epsrel, limit, result, abserr, nint);
 }
 
+void o_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int o_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
