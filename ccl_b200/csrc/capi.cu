@@ -1214,7 +1214,9 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
   }
   b->last_fast = fast;
   if (fast) {
-    const FastPlan plan = limber_fast_plan_carve(base + o_fp, nc, npair, redo_cap);
+    FastPlan plan = limber_fast_plan_carve(base + o_fp, nc, npair, redo_cap);
+    plan.ntr_max = 1;
+    for (const CosmoPlan& c : b->ts.cosmos) plan.ntr_max = std::max(plan.ntr_max, (int)c.tracers.size());
     if (!cuda_ok(launch_limber_fast(P, plan, stream), "limber fast launch", status)) return;
     return;
   }

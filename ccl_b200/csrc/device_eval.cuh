@@ -36,7 +36,9 @@ __device__ __forceinline__ Rec1 find_rec(const Spline1D& s, double v) {
   const int last = s.n - 2;
   i = min(max(i, 0), last);
   Rec1 r = load_rec(s.rec + i);
-  while (v < r.x0 && i > 0) r = load_rec(s.rec + (--i));
+  // the LUT entry is the interval of a point just left of the bin (lut_kernel): never past the target
+  if (s.uniform)
+    while (v < r.x0 && i > 0) r = load_rec(s.rec + (--i));
   int steps = 0;
   while (v >= r.x1 && i < last) {
     if (++steps > 4) {  // strongly non-uniform grid: finish by bisection on the interval starts

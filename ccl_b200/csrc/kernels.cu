@@ -62,7 +62,9 @@ __global__ void lut_kernel(const LutJob* jobs) {
   const double x0 = jb.x[0];
   const double bin = (jb.x[jb.n - 1] - x0) / jb.nlut;
   for (int j = threadIdx.x; j < jb.nlut; j += blockDim.x) {
-    const double v = x0 + j * bin;
+    // evaluated just left of the bin edge, so that a lookup whose bin index rounds up by one still
+    // starts at or before its interval (find_rec only walks right on this path)
+    const double v = x0 + (j - 1e-6) * bin;
     int lo = 0, hi = jb.n - 1;
     while (hi > lo + 1) {
       const int m = (hi + lo) >> 1;

@@ -24,10 +24,10 @@ namespace {
 #define CCLB_FW 8
 #endif
 #ifndef CCLB_NCG
-#define CCLB_NCG 12
+#define CCLB_NCG 10
 #endif
 #ifndef CCLB_NPG
-#define CCLB_NPG 12
+#define CCLB_NPG 10
 #endif
 #ifndef CCLB_LPC
 #define CCLB_LPC 4
@@ -41,7 +41,7 @@ constexpr int NPG = CCLB_NPG;   // pairs per grid task
 static_assert(CCLB_NPG <= 16, "pair flags are packed two bits per pair");
 constexpr int LPC = CCLB_LPC;   // ells per CTA (descriptor staging is amortised over them)
 constexpr int NSG = 2 * CCLB_NCG;  // sub-tracers per grid task
-constexpr int GB = 64;          // grids whose limits are precomputed per CTA pass
+constexpr int GB = 64;          // (ell, grid) tasks whose limits are precomputed per CTA pass
 
 struct FastTr {
   Spline1D kernel;
@@ -56,26 +56,30 @@ struct GridPar {
   int nk, grid, ls, pad;
 };
 
+// Per-CTA shared state; followed in shared memory by FastTr tr[ntr_max] and the per-warp blocks.
 struct FastCta {
   Spline1D achi;
   F2D psp;
-  FastTr tr[FAST_MAX_TRACERS];
   int2 colls[FAST_MAX_COLLS];
   GridPar gp[GB];
   int next_task, pad;
 };
 
+__host__ __device__ inline size_t fast_warp_offset(int ntr_max) {
+  return (sizeof(FastCta) + (size_t)ntr_max * sizeof(FastTr) + 15) & ~size_t(15);
+}
+
 // sub-tracer list entry of a grid task: tracer index | collection slot << 8 | first << 16 | last << 17
 constexpr unsigned SUB_FIRST = 1u << 16, SUB_LAST = 1u << 17;
 
 struct FastWarp {
-  double d[NCG][32];      // D of the grid's collection c at this lane's node
+  double dflat[NCG * 32]; // D of the grid's collection c at this lane's node: [c * 32 + lane]
   double sf[2][36];       // integrand of the current pair: 4 carried + 32 new nodes (double-buffered)
   double fc[NPG][4];      // last 4 integrand values of the previous chunk, per pair
+  double fe[NPG][8];      // f_0..f_2 and f_{nk-5}..f_{nk-1} per pair (end-node terms)
+  int2 po[NPG];           // offsets of the pair's two collections in dflat
   double acc[NPG][32];    // per-lane partial integrals
   GridPair prs[NPG];
-  unsigned pf[NPG];       // per pair: bits 0-1 equal-difference flags of the previous chunk's last
-                          // two lanes, bit 2 Akima tie flag of its last integrated node
   unsigned subs[NSG];
 };
 
@@ -172,6 +176,90 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
 }
 
 // ------------------------------------------------------------------------------------------
+// Phase 2 of one chunk: per-pair integrand and Akima integral.
+//
+// With m_j the slopes and t_j the Akima node derivatives, GSL's piecewise cubic integrates to
+//   sum_i h_i (f_i + f_{i+1}) / 2  +  (1/12) sum_{i: NE_i != 0} h_i^2 (t_i - tL_{i+1}),
+// tL_{i+1} = t_{i+1} unless NE_{i+1} == 0 (then m_i).  Per node c the second sum contributes
+// h^2 ([!z_c] t_c - [!z_{c-1}] (z_c ? m_{c-1} : t_c)) with z_c = (NE_c == 0): on the uniform part of the
+// grid that vanishes unless z_c != z_{c-1}.  The chunk loop therefore adds trapezoids and tests for
+// tie transitions (NE_c == 0 <=> m_{c+1} == m_c and m_{c-1} == m_{c-2}, i.e. equal consecutive first
+// differences); only a chunk holding a transition evaluates the per-node form, for the interior
+// nodes 1..nk-3.  The three end-node terms (nodes 0, nk-2, nk-1) are added once per pair after the
+// loop from the saved values fe.  Lane `lane` holds node s = base + lane and owns the trapezoid of
+// interval (s-1, s) and the correction term of node c = s - 2.
+// ------------------------------------------------------------------------------------------
+template <bool EDGE>
+__device__ __forceinline__ void pair_phase(FastWarp& W, int np, int s, int base, int nk, int lane, double kp,
+                                           double dx, double inv_dx, double inv_hl, unsigned& zdirty) {
+  const unsigned FULL = 0xffffffffu;
+  const bool valid = s < nk;
+  const double wtrap = (s >= 1 && valid) ? 0.5 * dx : 0.0;  // the last interval is fixed up after the loop
+  const int cn = s - 2;
+  const bool cvalid = EDGE ? ((cn >= 0) && (cn <= nk - 3)) : true;
+#pragma unroll 1
+  for (int q = 0; q < np; ++q) {
+    const int2 po = W.po[q];
+    double* sf = W.sf[q & 1];
+    // cl_integrand (src/ccl_cls.c:166-187): k P d1 d2, exactly 0 when either transfer vanishes
+    // (lanes past the last node read stale shared memory: select, do not multiply by zero)
+    const double f4 = valid ? kp * W.dflat[po.x + lane] * W.dflat[po.y + lane] : 0.0;
+    sf[4 + lane] = f4;
+    if (lane < 4) sf[lane] = W.fc[q][lane];
+    if (EDGE) {  // f_0..f_2 and f_{nk-5}..f_{nk-1} feed the end-node terms
+      if (s < 3) W.fe[q][s] = f4;
+      const int r = s - (nk - 5);
+      if (r >= 0 && valid) W.fe[q][3 + r] = f4;
+    }
+    __syncwarp();
+    const double f0 = sf[lane], f1 = sf[lane + 1], f2 = sf[lane + 2], f3 = sf[lane + 3];
+    if (lane >= 28) W.fc[q][lane - 28] = f4;
+    const double da = f1 - f0, db = f2 - f1, dc = f3 - f2, dd = f4 - f3;
+    bool z = (dd == dc) && (db == da);  // tie flag of node c
+    if (EDGE) {
+      // boundary slopes repeat the first difference of slopes: z_0 <=> m_1 == m_0; z_1 <=> m_2 == m_1 == m_0
+      if (cn == 0) z = (dd == dc);
+      if (cn == 1) z = (dd == dc) && (dc == db);
+      z = z && cvalid;
+    }
+    const unsigned zm = __ballot_sync(FULL, z);
+    const unsigned carry = (zdirty >> q) & 1u;
+    unsigned trans = (zm ^ ((zm << 1) | carry));
+    if (EDGE) {
+      unsigned m = (base == 0) ? ~7u : ~0u;  // node 0 has no left neighbour term; nodes 1..nk-3 only
+      if (nk - base < 32) m &= (1u << (nk - base)) - 1u;
+      trans &= m;
+    }
+    double add = wtrap * (f3 + f4);
+    if (trans != 0u) {
+      // ---- a tie transition in this chunk: per-node form for its interior nodes ----
+      double mm2 = da * inv_dx, mm1 = db * inv_dx, m0 = dc * inv_dx, mp1 = dd * inv_dx;
+      if (EDGE) {
+        if (cn == nk - 3) mp1 = dd * inv_hl;
+        if (cn == 1) mm2 = 2.0 * mm1 - m0;
+        if (cn == 0) { mm1 = 2.0 * m0 - mp1; mm2 = 3.0 * m0 - 2.0 * mp1; }
+      }
+      const bool zprev = lane ? ((zm >> (lane - 1)) & 1u) : (carry != 0u);
+      if (((trans >> lane) & 1u) != 0u) {
+        const double d12 = fabs(mm1 - mm2);
+        const double NE = fabs(mp1 - m0) + d12;
+        double tc = 0.0;
+        if (!z && NE != 0.0) {
+          const double alpha = d12 / NE;
+          tc = (1.0 - alpha) * mm1 + alpha * m0;
+        }
+        double cc = z ? 0.0 : tc;
+        if (!zprev) cc -= (z ? mm1 : tc);
+        add += cc * (dx * dx * (1.0 / 12.0));
+      }
+    }
+    W.acc[q][lane] += add;
+    const unsigned top = (zm >> 31) & 1u;  // tie flag of this chunk's last node, carried to the next chunk
+    if ((carry | top) != 0u) zdirty = (zdirty & ~(1u << q)) | (top << q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // The fast integrator.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FW * 32, CCLB_MINB)
@@ -179,7 +267,8 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   FastCta& S = *reinterpret_cast<FastCta*>(smraw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  FastWarp& W = reinterpret_cast<FastWarp*>(smraw + ((sizeof(FastCta) + 15) & ~size_t(15)))[warp];
+  FastTr* const s_tr = reinterpret_cast<FastTr*>(smraw + sizeof(FastCta));
+  FastWarp& W = reinterpret_cast<FastWarp*>(smraw + fast_warp_offset(G.ntr_max))[warp];
   const int nlt = (P.nl + LPC - 1) / LPC;
   const int il0 = (blockIdx.x % nlt) * LPC;
   const int ic = blockIdx.x / nlt;
@@ -189,10 +278,10 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
   // ---- per-CTA staging of the descriptors this (cosmology, ell tile) needs ----
   for (int t = threadIdx.x; t < cs->ntracers; t += blockDim.x) {
     const Tracer& tr = cs->tracers[t];
-    S.tr[t].kernel = tr.kernel;
-    S.tr[t].fa = tr.transfer.fa;
-    S.tr[t].has_fa = tr.has_transfer;
-    for (int ls = 0; ls < nls; ++ls) S.tr[t].pref[ls] = tracer_prefactor(tr, P.ells[il0 + ls]);
+    s_tr[t].kernel = tr.kernel;
+    s_tr[t].fa = tr.transfer.fa;
+    s_tr[t].has_fa = tr.has_transfer;
+    for (int ls = 0; ls < nls; ++ls) s_tr[t].pref[ls] = tracer_prefactor(tr, P.ells[il0 + ls]);
   }
   for (int c = threadIdx.x; c < P.ncoll; c += blockDim.x) S.colls[c] = P.colls[c];
   if (threadIdx.x == 32) S.achi = cs->achi;
@@ -246,8 +335,9 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
       const int ncoll = gd.ncoll, np = gd.npair;
       __syncwarp();
       if (lane < np) {
-        W.prs[lane] = gpairs[gd.pair_begin + lane];
-        W.pf[lane] = 0u;
+        const GridPair pr = gpairs[gd.pair_begin + lane];
+        W.prs[lane] = pr;
+        W.po[lane] = make_int2(pr.a * 32, pr.b * 32);
       }
       // flatten the grid's collections into one sub-tracer list (lane c expands collection c)
       int2 cr = make_int2(0, 0);
@@ -283,11 +373,13 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
       // k and chi advance by constant ratios from chunk to chunk (one exp per lane per grid)
       double k = exp(lkmin + dx * lane);
       double chi = lp1h / k;
+      unsigned zdirty = 0u;  // bit q: the last node of pair q's previous chunk was an Akima tie
+      for (int i = lane; i < NPG * 4; i += 32) (&W.fc[0][0])[i] = 0.0;  // f at nodes -4..-1: finite placeholders
 #pragma unroll 1
       for (int q = 0; q < np; ++q) W.acc[q][lane] = 0.0;
 
 #pragma unroll 1
-      for (int base = 0; base < nk + 2 && !redo; base += 32) {
+      for (int base = 0; base < nk && !redo; base += 32) {
         // ---------------- phase 1: node quantities (lane = node base + lane) ----------------
         const int s = base + lane;
         bool bad = false;
@@ -310,94 +402,26 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
 #pragma unroll 2
           for (int e = 0; e < nsub; ++e) {
             const unsigned ent = W.subs[e];
-            const FastTr& tr = S.tr[ent & 0xffu];
+            const FastTr& tr = s_tr[ent & 0xffu];
             const bool inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
-            const double chic = fmin(fmax(chi, tr.kernel.x0), tr.kernel.xn);
-            double wt = rec_value(find_rec(tr.kernel, chic), chic);
+            double wt = rec_value(find_rec(tr.kernel, chi), chi);  // index clamped inside; dropped if outside
             if (tr.has_fa) {
               const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
               wt *= rec_value(find_rec(tr.fa, a_ev), a_ev);
             }
             const double val = inside ? wt * tr.pref[ls] : 0.0;
             D = (ent & SUB_FIRST) ? val : D + val;
-            if (ent & SUB_LAST) W.d[(ent >> 8) & 0xffu][lane] = D;
+            if (ent & SUB_LAST) W.dflat[((ent >> 8) & 0xffu) * 32 + lane] = D;
           }
           k *= S.gp[gl].ratio;
           chi *= S.gp[gl].iratio;
         }
         if (__any_sync(FULL, bad)) { redo = true; break; }
         // ---------------- phase 2: per-pair integrand and Akima integral ----------------
-        // With m_j the slopes and t_j the Akima node derivatives, GSL's piecewise cubic integrates to
-        //   sum_i h_i (f_i + f_{i+1}) / 2  +  (1/12) sum_{i: NE_i != 0} h_i^2 (t_i - tL_{i+1}),
-        // tL_{i+1} = t_{i+1} unless NE_{i+1} == 0 (then m_i).  On a uniform grid without ties the
-        // second sum telescopes to the end nodes, so interior chunks only add trapezoids and test
-        // for ties: NE_c == 0 <=> m_{c+1} == m_c and m_{c-1} == m_{c-2}, i.e. equal consecutive first
-        // differences (bit e of a lane: d_{s-1} == d_{s-2}; z_{s-2} = e_s & e_{s-2}).
-        const bool edge_chunk = (base == 0) || (base + 31 >= nk - 1);
-#pragma unroll 1
-        for (int q = 0; q < np; ++q) {
-          const GridPair pr = W.prs[q];
-          double* sf = W.sf[q & 1];
-          // cl_integrand (src/ccl_cls.c:166-187): 0 when either transfer vanishes
-          double f4 = 0.0;
-          if (s < nk) {
-            const double d1 = W.d[pr.a][lane], d2 = W.d[pr.b][lane];
-            f4 = (d1 == 0.0 || d2 == 0.0) ? 0.0 : kp * d1 * d2;
-          }
-          sf[4 + lane] = f4;
-          if (lane < 4) sf[lane] = W.fc[q][lane];
-          __syncwarp();
-          const double f2 = sf[lane + 2], f3 = sf[lane + 3];
-          if (lane >= 28) W.fc[q][lane - 28] = f4;
-          const double dlast = f4 - f3;
-          const unsigned E = __ballot_sync(FULL, dlast == (f3 - f2));
-          const unsigned pf = W.pf[q];
-          const unsigned Z = E & ((E << 2) | (pf & 3u));
-          const bool zc_in = (pf >> 2) & 1u;
-          if (!(edge_chunk || Z != 0u || zc_in)) {
-            W.acc[q][lane] += (0.5 * dx) * (f3 + f4);  // interval (s-1, s)
-            if (lane == 0) W.pf[q] = E >> 30;
-            continue;
-          }
-          // ---- chunks holding an end node or a tie: the full per-node form ----
-          const int cn = s - 2;  // node whose correction term this lane owns
-          const bool cvalid = (cn >= 0) && (cn < nk);
-          const double f0 = sf[lane], f1 = sf[lane + 1];
-          double mm2 = (f1 - f0) * inv_dx, mm1 = (f2 - f1) * inv_dx, m0 = (f3 - f2) * inv_dx,
-                 mp1 = dlast * inv_dx;
-          double h = dx, hprev = dx;
-          if (cn == nk - 3) mp1 = dlast * inv_hl;
-          if (cn == nk - 2) { m0 = (f3 - f2) * inv_hl; h = hl; mp1 = 2.0 * m0 - mm1; }
-          if (cn == nk - 1) {
-            mm1 = (f2 - f1) * inv_hl;
-            hprev = hl;
-            m0 = 2.0 * mm1 - mm2;
-            mp1 = 3.0 * mm1 - 2.0 * mm2;
-          }
-          if (cn == 1) mm2 = 2.0 * mm1 - m0;
-          if (cn == 0) { mm1 = 2.0 * m0 - mp1; mm2 = 3.0 * m0 - 2.0 * mp1; }
-          const double d12 = fabs(mm1 - mm2);
-          const double NE = fabs(mp1 - m0) + d12;
-          const bool z = (NE == 0.0);
-          const unsigned zm = __ballot_sync(FULL, cvalid && z);
-          const bool zprev = lane ? ((zm >> (lane - 1)) & 1u) : zc_in;
-          if (lane == 0) W.pf[q] = (E >> 30) | (((zm >> 31) & 1u) << 2);
-          double add = 0.0;
-          if (s >= 1 && s < nk) add = 0.5 * ((s == nk - 1) ? hl : dx) * (f3 + f4);  // interval (s-1, s)
-          if (cvalid && (cn == 0 || cn >= nk - 2 || z || zprev)) {
-            // h_c^2 b_c - h_{c-1}^2 tL_c: vanishes at regular interior nodes (uniform h, no ties)
-            double tc = 0.0;
-            if (!z) {
-              const double alpha = d12 / NE;
-              tc = (1.0 - alpha) * mm1 + alpha * m0;
-            }
-            double cc = 0.0;
-            if (cn < nk - 1 && !z) cc = h * h * tc;
-            if (cn >= 1 && !zprev) cc -= hprev * hprev * (z ? mm1 : tc);
-            add += cc * (1.0 / 12.0);
-          }
-          W.acc[q][lane] += add;
-        }
+        if ((base == 0) || (base + 31 >= nk - 5))
+          pair_phase<true>(W, np, s, base, nk, lane, kp, dx, inv_dx, inv_hl, zdirty);
+        else
+          pair_phase<false>(W, np, s, base, nk, lane, kp, dx, inv_dx, inv_hl, zdirty);
         __syncwarp();
       }
 
@@ -410,9 +434,42 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
         }
         continue;
       }
+      // ---- end-node terms, one lane per pair (nodes 0, nk-2, nk-1; gsl akima_init boundary slopes) ----
+      double endc = 0.0;
+      if (lane < np) {
+        const double* e = W.fe[lane];
+        auto blend = [](double d12, double NE, double ml, double mr) {
+          const double alpha = d12 / NE;
+          return (1.0 - alpha) * ml + alpha * mr;
+        };
+        {  // node 0: slopes m_{-2}, m_{-1}, m_0, m_1
+          const double m0 = (e[1] - e[0]) * inv_dx, m1 = (e[2] - e[1]) * inv_dx;
+          const double mm1 = 2.0 * m0 - m1, mm2 = 3.0 * m0 - 2.0 * m1;
+          const double d12 = fabs(mm1 - mm2), NE = fabs(m1 - m0) + d12;
+          if (NE != 0.0) endc += dx * dx * blend(d12, NE, mm1, m0);
+        }
+        const double g0 = e[3], g1 = e[4], g2 = e[5], g3 = e[6], g4 = e[7];
+        const double ma = (g1 - g0) * inv_dx, mb = (g2 - g1) * inv_dx, mc = (g3 - g2) * inv_dx;
+        const double md = (g4 - g3) * inv_hl;  // last interval: its end node was overwritten with lkmax
+        const double me = 2.0 * md - mc, mf = 3.0 * md - 2.0 * mc;
+        const bool z3 = (fabs(md - mc) + fabs(mb - ma)) == 0.0;  // node nk-3
+        {  // node nk-2: h_c = hl, h_{c-1} = dx
+          const double d12 = fabs(mc - mb), NE = fabs(me - md) + d12;
+          const bool z2 = (NE == 0.0);
+          const double t2 = z2 ? 0.0 : blend(d12, NE, mc, md);
+          if (!z2) endc += hl * hl * t2;
+          if (!z3) endc -= dx * dx * (z2 ? mc : t2);
+          // node nk-1: h_{c-1} = hl
+          const double e12 = fabs(md - mc), NE1 = fabs(mf - me) + e12;
+          const bool z1 = (NE1 == 0.0);
+          const double t1 = z1 ? 0.0 : blend(e12, NE1, md, me);
+          if (!z2) endc -= hl * hl * (z1 ? md : t1);
+        }
+        endc = endc * (1.0 / 12.0) + 0.5 * (hl - dx) * (g3 + g4);
+      }
 #pragma unroll 1
       for (int q = 0; q < np; ++q) {
-        const double v = warp_sum(W.acc[q][lane]);
+        const double v = warp_sum(W.acc[q][lane]) + __shfl_sync(FULL, endc, q);
         if (lane == 0) P.cl[((size_t)ic * P.npair + W.prs[q].out) * P.nl + il] = v / lp1h;  // src/ccl_cls.c:340
       }
     }
@@ -439,6 +496,7 @@ FastPlan limber_fast_plan_carve(void* base, int ncosmo, int npair, unsigned long
   G.gstride = npair;
   G.cstride = 2 * npair;
   G.redo_cap = redo_cap;
+  G.ntr_max = FAST_MAX_TRACERS;
   return G;
 }
 
@@ -450,13 +508,13 @@ cudaError_t launch_limber_fast(const LimberProblem& prob, const FastPlan& plan, 
   if (gsm > 48 * 1024)
     cudaFuncSetAttribute(limber_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
   limber_group_kernel<<<prob.ncosmo, 128, gsm, stream>>>(prob, plan);
-  const size_t fsm = ((sizeof(FastCta) + 15) & ~size_t(15)) + FW * sizeof(FastWarp);
-  static bool attr_set[64] = {false};
+  const size_t fsm = fast_warp_offset(plan.ntr_max) + FW * sizeof(FastWarp);
+  static size_t attr_set[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr_set[dev & 63]) {
+  if (attr_set[dev & 63] < fsm) {
     cudaFuncSetAttribute(limber_spline_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-    attr_set[dev & 63] = true;
+    attr_set[dev & 63] = fsm;
   }
   const long long nlt = (prob.nl + LPC - 1) / LPC;
   limber_spline_fast_kernel<<<(unsigned)((long long)prob.ncosmo * nlt), FW * 32, fsm, stream>>>(prob, plan);

@@ -143,6 +143,7 @@ struct FastPlan {
   int* gcolls;      // [ncosmo][cstride]
   int* ngrids;      // [ncosmo]
   int gstride, cstride;
+  int ntr_max, pad;  // largest sub-tracer count of any cosmology of the launch (sizes shared memory)
   unsigned long long* redo;  // [0] = count, [1..redo_cap] = task ids left to the general kernel
   unsigned long long redo_cap;
 };
