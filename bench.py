@@ -167,7 +167,7 @@ def geometry():
     return colls, pairs, ells
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, json_out=sys.stdout):
     """CPU restatement of the reference on a bounded sample: 1 cosmology x 120 pairs x 100 ells."""
     if rank != 0:
         return
@@ -209,10 +209,23 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": val, "unit": "C_ell/s", "cores": cores, "kind": "port", "sample": sample,
                          "cosmologies_per_s": 1.0 / dt},
         "e2e": {"value": val, "unit": "C_ell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=json_out)
 
 
 def main():
+    # Libraries (NCCL's version banner, torchrun) may write to stdout: keep fd 1 for the ONE JSON line
+    # of the contract and send everything else to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
+    try:
+        _main(json_out)
+    finally:
+        json_out.flush()
+
+
+def _main(json_out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -228,7 +241,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, json_out)
         return
 
     import torch
@@ -426,7 +439,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             # fast 'spline' path: grouping + integrator + redo kernels per step; otherwise one kernel
             "gpu_launches": args.steps * (3 if fast_path else 1), "clocks": clocks,
-        }))
+        }), file=json_out)
     if world > 1:
         dist.destroy_process_group()
 
