@@ -224,3 +224,76 @@ def test_batch_stacked_setters_equal_per_slot():
     c2, s2, _ = b2.angular_cl(colls, pairs, ells)
     assert np.array_equal(c1, c2) and np.array_equal(s1, s2)
     assert [b1.tracer_chi_range(4, t) for t in range(15)] == [b2.tracer_chi_range(4, t) for t in range(15)]
+
+
+# ---------------------------------------------------------------------------------------------
+# Full-size properties (BASELINE configs[3]: 4096 cosmologies x 120 pairs x 100 ells) and edge cases
+# ---------------------------------------------------------------------------------------------
+def test_full_size_batch_properties():
+    """Size-independent properties at the bench's full size: the 4096 slots cycle through 8 table sets
+    with log P shifted by 1e-3 per cycle, so (i) C_ell is linear in P: slots of the same set differ by
+    exactly exp(shift); (ii) every entry is finite and flagged OK; (iii) a sample of (cosmology,
+    pair) curves matches the oracle; (iv) a second launch is bit-identical (determinism)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import ccl_b200 as cb
+    n = 4096
+    tables = bench.build_host_tables(bench.N_DISTINCT)
+    colls, pairs, ells = bench.geometry()
+    batch = cb.LibBatch(n)
+    batch.set_stacked(0, bench.stack_host_tables(tables, n, 0))
+    batch.commit()
+    cl, stat, st = batch.angular_cl(colls, pairs, ells)
+    assert batch.last_used_fast_path and st == 0 and not stat.any()
+    assert cl.shape == (n, len(pairs), len(ells)) and np.all(np.isfinite(cl))
+    nd = bench.N_DISTINCT
+    base = cl[:nd]
+    scale = np.max(np.abs(base), axis=2, keepdims=True)
+    for cyc in (1, 17, n // nd - 1):
+        blk = cl[cyc * nd:(cyc + 1) * nd]
+        denom = np.maximum(np.abs(base), 1e-6 * scale)
+        diff = np.abs(blk - base * np.exp(1e-3 * cyc))
+        zero = denom == 0.0                      # identically zero curves (disjoint supports) stay zero
+        assert np.all(diff[zero] == 0.0)
+        assert np.max(diff[~zero] / denom[~zero]) < 1e-11, cyc
+    cl2, _, _ = batch.angular_cl(colls, pairs, ells)
+    assert np.array_equal(cl, cl2)
+    rng = np.random.default_rng(5)
+    for ic, q in zip(rng.integers(0, n, 6), rng.integers(0, len(pairs), 6)):
+        t = tables[ic % nd]
+        shift = 1e-3 * (ic // nd)
+        redo = lambda: _oracle_all(t["bg"], t["pk"], t["subs"], t["colls"], [pairs[q]], ells, logp_shift=shift)[0][0]
+        assert parity_error(cl[ic, q], redo(), redo, SPLINE_RTOL) < SPLINE_RTOL, (ic, pairs[q])
+
+
+def test_batch_edge_cases(synth):
+    """Empty ell / pair lists, ell <= 1 (f_ell = 0 for spin-2 tracers: src/ccl_tracers.c:707-711), a pair
+    listed twice and in both orders, and the qag_quad method through the batched entry."""
+    import ccl_b200 as cb
+    bg, pk = synth["bg"], synth["pk"]
+    from ccl_b200 import synthetic as S
+    subs, colls = S.lsst_like_tracers(bg)
+    batch = cb.LibBatch(1)
+    _fill(batch, 0, bg, pk, subs, chi_max_nokernel(bg))
+    batch.commit()
+    cl, stat, st = batch.angular_cl(colls, [(0, 5)], np.zeros(0))
+    assert cl.shape == (1, 1, 0) and st == 0
+    cl, stat, st = batch.angular_cl(colls, [], np.array([10.0]))
+    assert cl.shape == (1, 0, 1) and st == 0
+    pairs = [(7, 9), (9, 7), (7, 9), (5, 5), (0, 0)]
+    ells = np.array([0.0, 1.0, 2.0, 3.5, 10.0, 11.0, 1000.0, 1001.0, 40000.0])
+    cl, stat, st = batch.angular_cl(colls, pairs, ells)
+    assert st == 0 and not stat.any()
+    assert np.array_equal(cl[0, 0], cl[0, 2])
+    assert np.max(np.abs(cl[0, 0] - cl[0, 1]) / np.abs(cl[0, 0]).max()) < 1e-13
+    assert np.all(cl[0, 0][:2] == 0.0) and np.all(cl[0, 3][:2] == 0.0)      # shear x shear at ell = 0, 1
+    ref, rstat = _oracle_all(bg, pk, subs, colls, pairs, ells)
+    for q in range(len(pairs)):
+        redo = lambda: _oracle_all(bg, pk, subs, colls, [pairs[q]], ells)[0][0]
+        assert parity_error(cl[0, q], ref[q], redo, SPLINE_RTOL) < SPLINE_RTOL, pairs[q]
+    clq, statq, stq = batch.angular_cl(colls, pairs, ells[2:7], cb._lib.INTEGRATION_QAG_QUAD)
+    refq, _ = _oracle_all(bg, pk, subs, colls, pairs, ells[2:7], oracle.INTEG_QAG)
+    assert stq == 0
+    for q in range(len(pairs)):
+        assert parity_error(clq[0, q], refq[q], None, QAG_RTOL) < QAG_RTOL
