@@ -635,8 +635,8 @@ static bool batch_check(ccl_b200_batch* b, int ncoll, const int* coll_start, con
 }
 
 // The fast 'spline' kernels (limber_fast.cu) cover the table forms pyccl's own tracers produce on
-// the default path: log bicubic P(k,a); sub-tracers with an Akima kernel, der_bessel in {-1, 0}
-// and either no transfer or an a-only (factorised, linear) one.  Anything else runs on the
+// the default path: log bicubic P(k,a); sub-tracers with an Akima kernel (any der_bessel) and
+// either no transfer or an a-only (factorised, linear) one.  Anything else runs on the
 // general kernel.
 static bool fast_eligible(const ccl_b200_batch* b, int ncoll, int npair) {
   if (getenv("CCL_B200_NO_FAST")) return false;
@@ -646,7 +646,7 @@ static bool fast_eligible(const ccl_b200_batch* b, int ncoll, int npair) {
     if (!c.has_psp || !g.has_fka || !g.is_log || g.is_factorizable) return false;
     if ((int)c.tracers.size() > FAST_MAX_TRACERS) return false;
     for (const TracerPlan& t : c.tracers) {
-      if (!t.kernel.present || t.der_bessel > 0) return false;
+      if (!t.kernel.present) return false;
       if (t.has_transfer) {
         const F2D& f = t.transfer.flags;
         if (!f.is_factorizable || f.has_fk || !f.has_fa || f.is_log) return false;
@@ -1216,7 +1216,11 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
   if (fast) {
     FastPlan plan = limber_fast_plan_carve(base + o_fp, nc, npair, redo_cap);
     plan.ntr_max = 1;
-    for (const CosmoPlan& c : b->ts.cosmos) plan.ntr_max = std::max(plan.ntr_max, (int)c.tracers.size());
+    plan.has_rsd = 0;
+    for (const CosmoPlan& c : b->ts.cosmos) {
+      plan.ntr_max = std::max(plan.ntr_max, (int)c.tracers.size());
+      for (const TracerPlan& t : c.tracers) plan.has_rsd |= (t.der_bessel > 0);
+    }
     if (!cuda_ok(launch_limber_fast(P, plan, stream), "limber fast launch", status)) return;
     return;
   }

@@ -47,7 +47,7 @@ struct FastTr {
   Spline1D kernel;
   Spline1D fa;
   double pref[LPC];  // f_ell (/(l+1/2)^2 when der_bessel == -1) for each ell of this CTA
-  int has_fa, pad;
+  int has_fa, der_bessel;
 };
 
 // ln k limits and node spacing of one (ell, grid) task (get_k_interval + ccl_linear_spacing)
@@ -262,6 +262,10 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int s, int base,
 // ------------------------------------------------------------------------------------------
 // The fast integrator.
 // ------------------------------------------------------------------------------------------
+// RSD = true adds the der_bessel 1/2 sub-tracers (transfer_limber_single, src/ccl_cls.c:121-145): the
+// second evaluation point chi' = (l+3/2)/k, a' = a(chi') and the ratio P(k,a')/P(k,a) are computed once per
+// node and shared by every such sub-tracer of the grid.
+template <bool RSD>
 __global__ void __launch_bounds__(FW * 32, CCLB_MINB)
 limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -281,6 +285,7 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
     s_tr[t].kernel = tr.kernel;
     s_tr[t].fa = tr.transfer.fa;
     s_tr[t].has_fa = tr.has_transfer;
+    s_tr[t].der_bessel = tr.der_bessel;
     for (int ls = 0; ls < nls; ++ls) s_tr[t].pref[ls] = tracer_prefactor(tr, P.ells[il0 + ls]);
   }
   for (int c = threadIdx.x; c < P.ncoll; c += blockDim.x) S.colls[c] = P.colls[c];
@@ -348,6 +353,12 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
         const int v = __shfl_up_sync(FULL, off, o);
         if (lane >= o) off += v;
       }
+      bool task_rsd = false;
+      if (RSD) {
+        bool mine = false;
+        for (int j = 0; j < cr.y; ++j) mine = mine || (s_tr[cr.x + j].der_bessel >= 1);
+        task_rsd = __any_sync(FULL, mine);
+      }
       const int nsub = __shfl_sync(FULL, off, 31);
       off -= cr.y;
       if (nsub <= NSG)
@@ -393,7 +404,20 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
             else bad = true;  // GSL_EDOM: the general kernel reports it
           }
           if (!(a >= S.psp.amin && a <= S.psp.amax)) bad = true;  // growth extrapolation: general kernel
-          if (!bad) kp = k * exp(bicubic_eval(S.psp, lk, a, 0));
+          double pk = 0.0;
+          if (!bad) pk = exp(bicubic_eval(S.psp, lk, a, 0));
+          kp = k * pk;
+          double chi_lp = 0.0, a_lp = 1.0, sqell = 0.0;
+          if (RSD && task_rsd) {
+            const double lp3h = lp1h + 1.0;
+            chi_lp = lp3h / k;
+            if (!(chi_lp < 1.e-8)) {
+              if (chi_lp >= S.achi.x0 && chi_lp <= S.achi.xn) a_lp = rec_value(find_rec(S.achi, chi_lp), chi_lp);
+              else bad = true;
+            }
+            if (!(a_lp >= S.psp.amin && a_lp <= S.psp.amax)) bad = true;
+            if (!bad) sqell = sqrt(lp1h * fabs(exp(bicubic_eval(S.psp, lk, a_lp, 0)) / pk) / lp3h);
+          }
           // transfer_limber_wrap (src/ccl_cls.c:150-164) for every collection of the grid, as one
           // branch-free loop over the flattened sub-tracer list so that independent table lookups
           // overlap.  Outside a kernel's support the lookup runs on the clamped abscissa and the
@@ -409,7 +433,23 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
               const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
               wt *= rec_value(find_rec(tr.fa, a_ev), a_ev);
             }
-            const double val = inside ? wt * tr.pref[ls] : 0.0;
+            double val = inside ? wt * tr.pref[ls] : 0.0;
+            if (RSD && tr.der_bessel >= 1) {
+              // w t at chi is `inside ? wt : 0`; the second point has its own support test
+              const double l = lp1h - 0.5, lp3h = lp1h + 1.0;
+              const double w_t = inside ? wt : 0.0;
+              const bool inside_p = (chi_lp > tr.kernel.x0) && (chi_lp < tr.kernel.xn);
+              double wt_p = rec_value(find_rec(tr.kernel, chi_lp), chi_lp);
+              if (tr.has_fa) {
+                const double a_ev = fmin(fmax(a_lp, tr.fa.x0), tr.fa.xn);
+                wt_p *= rec_value(find_rec(tr.fa, a_ev), a_ev);
+              }
+              if (!inside_p) wt_p = 0.0;
+              double dd;
+              if (tr.der_bessel == 1) dd = l * w_t / lp1h - sqell * wt_p;
+              else dd = sqell * 2 * wt_p / lp3h - (0.25 + 2 * l) * w_t / (lp1h * lp1h);
+              val = dd * tr.pref[ls];
+            }
             D = (ent & SUB_FIRST) ? val : D + val;
             if (ent & SUB_LAST) W.dflat[((ent >> 8) & 0xffu) * 32 + lane] = D;
           }
@@ -497,6 +537,7 @@ FastPlan limber_fast_plan_carve(void* base, int ncosmo, int npair, unsigned long
   G.cstride = 2 * npair;
   G.redo_cap = redo_cap;
   G.ntr_max = FAST_MAX_TRACERS;
+  G.has_rsd = 1;
   return G;
 }
 
@@ -513,11 +554,14 @@ cudaError_t launch_limber_fast(const LimberProblem& prob, const FastPlan& plan, 
   int dev = 0;
   cudaGetDevice(&dev);
   if (attr_set[dev & 63] < fsm) {
-    cudaFuncSetAttribute(limber_spline_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
+    cudaFuncSetAttribute(limber_spline_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
+    cudaFuncSetAttribute(limber_spline_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     attr_set[dev & 63] = fsm;
   }
   const long long nlt = (prob.nl + LPC - 1) / LPC;
-  limber_spline_fast_kernel<<<(unsigned)((long long)prob.ncosmo * nlt), FW * 32, fsm, stream>>>(prob, plan);
+  const unsigned nblk = (unsigned)((long long)prob.ncosmo * nlt);
+  if (plan.has_rsd) limber_spline_fast_kernel<true><<<nblk, FW * 32, fsm, stream>>>(prob, plan);
+  else limber_spline_fast_kernel<false><<<nblk, FW * 32, fsm, stream>>>(prob, plan);
   launch_limber_redo(prob, plan, stream);
   return cudaGetLastError();
 }

@@ -143,7 +143,8 @@ struct FastPlan {
   int* gcolls;      // [ncosmo][cstride]
   int* ngrids;      // [ncosmo]
   int gstride, cstride;
-  int ntr_max, pad;  // largest sub-tracer count of any cosmology of the launch (sizes shared memory)
+  int ntr_max;  // largest sub-tracer count of any cosmology of the launch (sizes shared memory)
+  int has_rsd;  // some sub-tracer has der_bessel 1 or 2: launch the kernel variant that handles them
   unsigned long long* redo;  // [0] = count, [1..redo_cap] = task ids left to the general kernel
   unsigned long long redo_cap;
 };

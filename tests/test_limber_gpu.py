@@ -123,12 +123,13 @@ def _oracle_all(bg, pk, subs, colls, pairs, ells, method=oracle.INTEG_SPLINE, lo
     return out, stat
 
 
-@pytest.mark.parametrize("flavour", ["plain", "ia_mag"])
+@pytest.mark.parametrize("flavour", ["plain", "ia_mag", "rsd_ia_mag"])
 def test_batch_fast_path_matches_oracle(flavour):
     """All 120 pairs x 24 ells of two different cosmologies in one launch, against the oracle."""
     import ccl_b200 as cb
     from ccl_b200 import synthetic as S
-    kw = dict(with_ia=True, with_mag=True) if flavour == "ia_mag" else {}
+    kw = {"plain": {}, "ia_mag": dict(with_ia=True, with_mag=True),
+          "rsd_ia_mag": dict(with_ia=True, with_mag=True, with_rsd=True)}[flavour]
     batch = cb.LibBatch(2)
     sets = []
     for ic, (Om, h) in enumerate(((0.3, 0.7), (0.26, 0.64))):
@@ -156,7 +157,7 @@ def test_batch_fast_equals_general_kernel(monkeypatch):
     from ccl_b200 import synthetic as S
     bg = S.background()
     pk = S.power(bg)
-    subs, colls = S.lsst_like_tracers(bg, with_ia=True)
+    subs, colls = S.lsst_like_tracers(bg, with_ia=True, with_rsd=True, with_mag=True)
     pairs = [(i, j) for i in range(len(colls)) for j in range(i, len(colls))]
     ells = np.geomspace(2, 3000, 100)
     batch = cb.LibBatch(1)
