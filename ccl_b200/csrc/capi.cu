@@ -541,6 +541,7 @@ struct ccl_b200_batch {
   TableSet ts;
   unsigned long long last_qag_evals = 0;
   bool last_fast = false;  // the last 'spline' launch used the grid-sharing kernels
+  cudaStream_t stream = nullptr;  // non-blocking: batches driven from different host threads overlap
   DevBuf out;   // device result buffer of the host-buffer entry (kept across calls)
   DevBuf call;  // per-batch call buffers (colls, pairs, ells, counters, outputs)
 };
@@ -988,12 +989,20 @@ ccl_b200_batch* ccl_b200_batch_new(int ncosmo, const ccl_b200_params* params, in
   if (params) b->params = *params; else ccl_b200_default_params(&b->params);
   b->ts.device = current_device();
   b->ts.cosmos.resize(ncosmo);
+  if (!cuda_ok(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "cudaStreamCreate", status)) {
+    delete b;
+    return nullptr;
+  }
   return b;
 }
 
 void ccl_b200_batch_free(ccl_b200_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ts.device);
+  if (b->stream) {
+    cudaStreamSynchronize(b->stream);
+    cudaStreamDestroy(b->stream);
+  }
   delete b;
 }
 
@@ -1152,7 +1161,7 @@ void ccl_b200_batch_reset(ccl_b200_batch* b) { if (b) b->ts.reset(); }
 
 void ccl_b200_batch_commit(ccl_b200_batch* b, int* status) {
   if (*status || !b) return;
-  b->ts.commit(0, status);
+  b->ts.commit(b->stream, status);
 }
 
 unsigned long long ccl_b200_batch_h2d_bytes(const ccl_b200_batch* b) { return b->ts.last_h2d; }
@@ -1245,11 +1254,12 @@ void ccl_b200_batch_angular_cls_limber(ccl_b200_batch* b, int ncoll, const int* 
   double* d_cl = reinterpret_cast<double*>(b->out.p);
   int* d_st = reinterpret_cast<int*>(b->out.p + (ncl * 8 + 255) / 256 * 256);
   ccl_b200_batch_angular_cls_limber_dev(b, ncoll, coll_start, coll_count, npair, pair1, pair2, nl, ell,
-                                        integration_method, d_cl, d_st, nullptr, status);
+                                        integration_method, d_cl, d_st, b->stream, status);
   if (*status) return;
-  if (!cuda_ok(cudaMemcpy(cl_out, d_cl, ncl * 8, cudaMemcpyDeviceToHost), "limber kernel", status)) return;
   std::vector<int> st(nst);
-  cudaMemcpy(st.data(), d_st, nst * sizeof(int), cudaMemcpyDeviceToHost);
+  if (ncl) cudaMemcpyAsync(cl_out, d_cl, ncl * 8, cudaMemcpyDeviceToHost, b->stream);
+  if (nst) cudaMemcpyAsync(st.data(), d_st, nst * sizeof(int), cudaMemcpyDeviceToHost, b->stream);
+  if (!cuda_ok(cudaStreamSynchronize(b->stream), "limber kernel", status)) return;
   bool any = false;
   for (size_t i = 0; i < nst; ++i) {
     if (status_out) status_out[i] = st[i];

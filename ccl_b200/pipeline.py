@@ -1,0 +1,116 @@
+"""Host-buffer entry for large likelihood batches: stage -> upload/prepare -> integrate, pipelined.
+
+`PipelinedBatch.angular_cl(stacked_tables, ...)` splits the batch into chunks of cosmologies, each
+with its own ccl_b200_batch (arena + non-blocking stream), and runs three stages on three host
+threads so that they overlap across chunks:
+  1. staging of the caller's stacked host tables into the chunk's pinned arena (host threads),
+  2. one H2D copy + device table preparation (copy engine + small kernels),
+  3. the Limber kernels + D2H of the chunk's C_ell block (SMs + copy engine).
+The C ABI calls release the GIL, so the stages really run concurrently.  Results are identical to
+a single LibBatch (same kernels on the same tables).  No counterpart in the reference, which has
+no batch axis at all (pairs and cosmologies are Python loops, benchmarks/test_timing.py:31-34).
+"""
+import queue
+import threading
+
+import numpy as np
+
+from . import _lib
+from .lowlevel import LibBatch
+from .sharding import shard_range
+
+__all__ = ("PipelinedBatch", "slice_stacked")
+
+
+def slice_stacked(stk, lo, hi):
+    """Rows [lo, hi) of a stacked-table dict (see LibBatch.set_stacked); shared grids are kept."""
+    def rows(x):
+        x = np.asarray(x)
+        return x[lo:hi]
+
+    n_per, chi, a = stk["achi"]
+    out = dict(count=hi - lo, achi=(rows(n_per), rows(chi), rows(a)), tracers=[])
+    if stk.get("growth") is not None:
+        ag, D = stk["growth"]
+        out["growth"] = (ag if np.ndim(ag) == 1 else rows(ag), rows(D))
+    if stk.get("chi_max_nokernel") is not None:
+        out["chi_max_nokernel"] = rows(stk["chi_max_nokernel"])
+    lk, apk, pk, olo, ohi, islog = stk["pk"]
+    out["pk"] = (lk, apk, rows(pk), olo, ohi, islog)
+    for t in stk["tracers"]:
+        u = dict(t)
+        for key in ("chi", "a"):
+            if t.get(key) is not None and np.ndim(t[key]) == 2:
+                u[key] = rows(t[key])
+        for key in ("w", "fka", "fk", "fa"):
+            if t.get(key) is not None:
+                u[key] = rows(t[key])
+        out["tracers"].append(u)
+    return out
+
+
+class PipelinedBatch:
+    def __init__(self, ncosmo, nchunks=8, params=None):
+        self.ncosmo = int(ncosmo)
+        self.nchunks = max(1, min(int(nchunks), self.ncosmo))
+        self.spans = [shard_range(self.ncosmo, self.nchunks, c) for c in range(self.nchunks)]
+        self.batches = [LibBatch(cnt, params) for _, cnt in self.spans]
+
+    @property
+    def h2d_bytes(self):
+        return sum(int(b.h2d_bytes) for b in self.batches)
+
+    def angular_cl(self, stk, collections, pairs, ells, method=_lib.INTEGRATION_SPLINE, out=None):
+        """cl[ncosmo, npair, nl], status[ncosmo, npair], status -- like LibBatch.angular_cl."""
+        nl = len(np.atleast_1d(ells))
+        shape = (self.ncosmo, len(pairs), nl)
+        if out is None:
+            out = np.empty(shape)
+        assert out.shape == shape and out.dtype == np.float64 and out.flags.c_contiguous
+        stat = np.zeros((self.ncosmo, len(pairs)), dtype=np.int32)
+        staged, ready = queue.Queue(), queue.Queue()
+        errors = []
+
+        def stage():
+            try:
+                for c, (off, cnt) in enumerate(self.spans):
+                    b = self.batches[c]
+                    b.reset()
+                    b.set_stacked(0, slice_stacked(stk, off, off + cnt))
+                    staged.put(c)
+            except BaseException as e:  # noqa: BLE001 -- re-raised on the caller's thread
+                errors.append(e)
+            finally:
+                staged.put(None)
+
+        def commit():
+            try:
+                while True:
+                    c = staged.get()
+                    if c is None:
+                        break
+                    self.batches[c].commit()
+                    ready.put(c)
+            except BaseException as e:  # noqa: BLE001
+                errors.append(e)
+            finally:
+                ready.put(None)
+
+        t1 = threading.Thread(target=stage, daemon=True)
+        t2 = threading.Thread(target=commit, daemon=True)
+        t1.start()
+        t2.start()
+        worst = 0
+        while True:
+            c = ready.get()
+            if c is None:
+                break
+            off, cnt = self.spans[c]
+            _, s_c, st = self.batches[c].angular_cl(collections, pairs, ells, method, out=out[off:off + cnt])
+            stat[off:off + cnt] = s_c
+            worst = worst or st
+        t1.join()
+        t2.join()
+        if errors:
+            raise errors[0]
+        return out, stat, worst

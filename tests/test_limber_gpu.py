@@ -298,3 +298,24 @@ def test_batch_edge_cases(synth):
     assert stq == 0
     for q in range(len(pairs)):
         assert parity_error(clq[0, q], refq[q], None, QAG_RTOL) < QAG_RTOL
+
+
+def test_pipelined_host_entry_equals_single_batch():
+    """PipelinedBatch (chunked stage/commit/compute on three threads) == one LibBatch, bit for bit."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import ccl_b200 as cb
+    tables = bench.build_host_tables(3)
+    colls, pairs, ells = bench.geometry()
+    ells = ells[::7]
+    n = 37                                      # ragged chunks
+    stk = bench.stack_host_tables(tables, n, 2)
+    b1 = cb.LibBatch(n)
+    b1.set_stacked(0, stk)
+    b1.commit()
+    c1, s1, st1 = b1.angular_cl(colls, pairs, ells)
+    pipe = cb.PipelinedBatch(n, nchunks=5)
+    for _ in range(2):                          # arenas are reused from step to step
+        c2, s2, st2 = pipe.angular_cl(stk, colls, pairs, ells)
+        assert np.array_equal(c1, c2) and np.array_equal(s1, s2) and st1 == st2 == 0
