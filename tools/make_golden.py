@@ -35,3 +35,15 @@ for i in (1, 2):
 out["cc"] = np.loadtxt(os.path.join(SRC, "run_log_cl_cc.txt"), unpack=True)[1][ells.astype(int)]
 np.savez_compressed(os.path.join(OUT, "cells_benchmark.npz"), **out)
 print("wrote %d arrays to %s" % (len(out), os.path.join(OUT, "cells_benchmark.npz")))
+
+# Upstream tables the path reads (pins of the host table builders, benchmarks/test_bbks.py 1e-5,
+# test_distances.py 1e-4, test_growth.py 1e-4): independent-code values shipped with the reference.
+up = {}
+for m in (1, 2, 3):
+    up["bbks_model%d_pk" % m] = np.loadtxt(os.path.join(SRC, "model%d_pk.txt" % m))
+up["chi_model1_5"] = np.genfromtxt(os.path.join(SRC, "chi_model1-5.txt"))
+up["growth_model1_5"] = np.genfromtxt(os.path.join(SRC, "growth_model1-5.txt"))
+up["eh_model1_pk"] = np.loadtxt(os.path.join(SRC, "model1_pk_eh.txt"))
+np.savez_compressed(os.path.join(OUT, "upstream_tables.npz"), **up)
+print("wrote %d arrays to %s" % (len(up), os.path.join(OUT, "upstream_tables.npz")))
+
