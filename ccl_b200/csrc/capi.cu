@@ -1303,4 +1303,50 @@ unsigned long long ccl_b200_batch_last_qag_evals(const ccl_b200_batch* b) { retu
 
 int ccl_b200_batch_last_used_fast_path(const ccl_b200_batch* b) { return b->last_fast ? 1 : 0; }
 
+// ---- device builders ----
+void ccl_b200_build_background(int ncosmo, const double* params, int na, const double* a_grid, double dchi,
+                               double root_epsrel, int root_niter, double a_growth_init, int stride, double* E,
+                               double* chi, int* n_achi, double* achi_chi, double* achi_a, double* growth,
+                               double* fgrowth, double* growth0, int* status) {
+  if (*status) return;
+  if (!use_device(status)) return;
+  if (ncosmo <= 0 || na < 5 || stride < 5 || a_grid[na - 1] != 1.0) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200_build_background: need ncosmo > 0, na >= 5, stride >= 5 and an a-grid ending at 1");
+    return;
+  }
+  const size_t nc = (size_t)ncosmo, sna = (size_t)na, sst = (size_t)stride;
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t o_par = 0, o_a = o_par + up(nc * CCL_B200_NPAR * 8), o_E = o_a + up(sna * 8),
+               o_chi = o_E + up(nc * sna * 8), o_n = o_chi + up(nc * sna * 8), o_gx = o_n + up(nc * 4),
+               o_ga = o_gx + up(nc * sst * 8), o_D = o_ga + up(nc * sst * 8), o_f = o_D + up(nc * sna * 8),
+               o_g0 = o_f + up(nc * sna * 8), total = o_g0 + up(nc * 8);
+  DevBuf buf;
+  if (!buf.reserve(total, status)) return;
+  char* d = buf.p;
+  cudaMemcpy(d + o_par, params, nc * CCL_B200_NPAR * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_a, a_grid, sna * 8, cudaMemcpyHostToDevice);
+  cudaMemset(d + o_gx, 0, 2 * up(nc * sst * 8));
+  launch_build_background(ncosmo, na, (double*)(d + o_a), (double*)(d + o_par), dchi, root_epsrel, root_niter,
+                          a_growth_init, stride, (double*)(d + o_E), (double*)(d + o_chi), (int*)(d + o_n),
+                          (double*)(d + o_gx), (double*)(d + o_ga), (double*)(d + o_D), (double*)(d + o_f),
+                          (double*)(d + o_g0), 0);
+  if (!cuda_ok(cudaGetLastError(), "background builder launch", status)) return;
+  if (!cuda_ok(cudaDeviceSynchronize(), "background builder", status)) return;
+  cudaMemcpy(E, d + o_E, nc * sna * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(chi, d + o_chi, nc * sna * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(n_achi, d + o_n, nc * 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(achi_chi, d + o_gx, nc * sst * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(achi_a, d + o_ga, nc * sst * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(growth, d + o_D, nc * sna * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(fgrowth, d + o_f, nc * sna * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(growth0, d + o_g0, nc * 8, cudaMemcpyDeviceToHost);
+  for (int i = 0; i < ncosmo; ++i)
+    if (n_achi[i] < 5) {
+      *status = CCL_B200_ERROR_MEMORY;
+      set_err("ccl_b200_build_background: cosmology %d needs %d a(chi) nodes, stride is %d", i, -n_achi[i], stride);
+      return;
+    }
+}
+
 }  // extern "C"

@@ -191,4 +191,10 @@ void launch_eval_tracer_kernel(const Tracer* d_tr, int n, const double* d_chi, d
 void launch_eval_tracer_transfer(const Tracer* d_tr, int n, const double* d_lk, const double* d_a,
                                  double* d_out, int* d_status, cudaStream_t stream);
 
+// device table builders (builders.cu)
+void launch_build_background(int ncosmo, int na, const double* d_a, const double* d_params, double dchi,
+                             double epsrel, int nmax, double a_init, int stride, double* d_E, double* d_chi,
+                             int* d_n, double* d_achi_chi, double* d_achi_a, double* d_growth, double* d_fgrowth,
+                             double* d_growth0, cudaStream_t stream);
+
 }  // namespace cclb

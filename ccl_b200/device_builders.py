@@ -1,0 +1,53 @@
+"""Batched device builders of the tables the Limber path reads (north-star item 5).
+
+Python front-end of the ``ccl_b200_build_*`` entries: a list of ``Cosmology`` objects (or their
+derived parameter dicts) in, stacked tables out.  The algorithms are those of the host builders
+(``background.py``, ``power.py``, ``tracers.py``), which restate src/ccl_background.c,
+src/ccl_power.c and src/ccl_tracers.c; tests/test_builders_gpu.py compares the two."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .errors import check
+from .synthetic import linlog_spacing
+
+_PAR_KEYS = ("Omega_c", "Omega_b", "Omega_l", "Omega_k", "Omega_g", "Omega_nu_rel", "w0", "wa", "h", "Omega_m",
+             "n_s", "sigma8", "T_CMB", "k_sign", "sqrtk")
+NPAR = 16
+
+
+def pack_params(cosmologies):
+    """[ncosmo, NPAR] parameter matrix (include/ccl_b200.h) from Cosmology objects or parameter dicts."""
+    out = np.zeros((len(cosmologies), NPAR))
+    for i, c in enumerate(cosmologies):
+        p = c._params if hasattr(c, "_params") else c
+        out[i, :len(_PAR_KEYS)] = [float(p[k]) for k in _PAR_KEYS]
+    return out
+
+
+def build_background(cosmologies, spline_params=None, gsl_params=None, stride=8192):
+    """E(a), chi(a), a(chi), D(a), f(a) of every cosmology, built on the device.
+
+    Returns dict(a, E[nc, na], chi[nc, na], n_achi[nc], achi_chi[nc, stride], achi_a[nc, stride],
+    growth[nc, na], fgrowth[nc, na], growth0[nc])."""
+    from .parameters import gsl_params as gp0, spline_params as sp0
+    sp = spline_params if spline_params is not None else sp0
+    gp = gsl_params if gsl_params is not None else gp0
+    par = np.ascontiguousarray(pack_params(cosmologies))
+    a = linlog_spacing(sp["A_SPLINE_MINLOG"], sp["A_SPLINE_MIN"], sp["A_SPLINE_MAX"], sp["A_SPLINE_NLOG"],
+                       sp["A_SPLINE_NA"])
+    nc, na = par.shape[0], a.size
+    out = dict(a=a, E=np.empty((nc, na)), chi=np.empty((nc, na)), n_achi=np.zeros(nc, dtype=np.int32),
+               achi_chi=np.zeros((nc, stride)), achi_a=np.zeros((nc, stride)), growth=np.empty((nc, na)),
+               fgrowth=np.empty((nc, na)), growth0=np.empty(nc))
+    st = C.c_int(0)
+    dp = lambda x: x.ctypes.data_as(_lib._dp)
+    _lib.load().ccl_b200_build_background(nc, dp(par), na, dp(a), float(sp["DCHI_INTEGRATION"]),
+                                          float(gp["ROOT_EPSREL"]), int(gp["ROOT_N_ITERATION"]),
+                                          float(gp["EPS_SCALEFAC_GROWTH"]), stride, dp(out["E"]), dp(out["chi"]),
+                                          out["n_achi"].ctypes.data_as(_lib._ip), dp(out["achi_chi"]),
+                                          dp(out["achi_a"]), dp(out["growth"]), dp(out["fgrowth"]),
+                                          dp(out["growth0"]), C.byref(st))
+    check(st.value)
+    return out

@@ -220,6 +220,23 @@ unsigned long long ccl_b200_batch_last_qag_evals(const ccl_b200_batch *b);
  * environment variable CCL_B200_NO_FAST forces the general kernel. */
 int ccl_b200_batch_last_used_fast_path(const ccl_b200_batch *b);
 
+/* ---- device builders of the tables the path reads (batched over cosmologies) ---- */
+/* One cosmology = CCL_B200_NPAR doubles, derived like pyccl/cosmology.py:398-496 (m_nu = 0):
+ * [0] Omega_c [1] Omega_b [2] Omega_l [3] Omega_k [4] Omega_g [5] Omega_nu_rel [6] w0 [7] wa [8] h
+ * [9] Omega_m [10] n_s [11] sigma8 [12] T_CMB [13] k_sign [14] sqrtk [15] reserved */
+#define CCL_B200_NPAR 16
+/* ccl_cosmology_compute_distances + ccl_cosmology_compute_growth (src/ccl_background.c:417-589,
+ * 763-1002) for ncosmo cosmologies on the device.  a_grid[na] is the shared linlog a-grid ending at
+ * a = 1.  Host outputs, row-major with a leading cosmology axis: E[na] = H/H0, chi[na] (Mpc), the
+ * a(chi) table on a uniform chi grid of step <= dchi (n_achi[i] nodes in rows of `stride`; a negative
+ * count means stride was too small), growth[na] (D, D(1) = 1), fgrowth[na], growth0 (D unnormalised
+ * at a = 1).  root_epsrel / root_niter are ccl_gsl_params.ROOT_EPSREL / ROOT_N_ITERATION (the Newton
+ * stopping rule decides the a(chi) node values), a_growth_init is EPS_SCALEFAC_GROWTH. */
+void ccl_b200_build_background(int ncosmo, const double *params, int na, const double *a_grid, double dchi,
+                               double root_epsrel, int root_niter, double a_growth_init, int stride,
+                               double *E, double *chi, int *n_achi, double *achi_chi, double *achi_a,
+                               double *growth, double *fgrowth, double *growth0, int *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,42 @@
+"""Device table builders against the host builders of this package (which are pinned against the
+reference's benchmark files in tests/test_upstream_tables_cpu.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _cosmologies():
+    import ccl_b200 as ccl
+    rng = np.random.default_rng(11)
+    out = [ccl.Cosmology(Omega_c=0.27, Omega_b=0.045, h=0.67, sigma8=0.8, n_s=0.96, transfer_function='bbks')]
+    for _ in range(5):
+        out.append(ccl.Cosmology(Omega_c=rng.uniform(0.2, 0.35), Omega_b=rng.uniform(0.04, 0.055),
+                                 h=rng.uniform(0.6, 0.8), n_s=rng.uniform(0.92, 1.0), sigma8=rng.uniform(0.7, 0.9),
+                                 w0=rng.uniform(-1.3, -0.7), wa=rng.uniform(-0.5, 0.5),
+                                 transfer_function='eisenstein_hu'))
+    out.append(ccl.Cosmology(Omega_c=0.25, Omega_b=0.05, h=0.7, sigma8=0.8, n_s=0.96, Omega_k=0.05, Neff=0,
+                             Omega_g=0, transfer_function='bbks'))
+    return out
+
+
+def test_background_matches_host_builder():
+    from ccl_b200 import device_builders as db
+    cos = _cosmologies()
+    dev = db.build_background(cos)
+    for i, c in enumerate(cos):
+        c.compute_distances()
+        c.compute_growth()
+        bg = c._bg
+        assert np.array_equal(dev["a"], bg.a)
+        assert np.max(np.abs(dev["E"][i] / bg.E - 1)) < 1e-14
+        assert np.max(np.abs(dev["chi"][i][:-1] / bg.chi[:-1] - 1)) < 1e-13 and dev["chi"][i][-1] == 0
+        n = dev["n_achi"][i]
+        assert n == bg.achi_chi.size
+        assert np.max(np.abs(dev["achi_chi"][i, :n] - bg.achi_chi)) < 1e-9
+        # same Newton chain and stopping rule: the node values agree far below the rule's own 1e-4
+        assert np.max(np.abs(dev["achi_a"][i, :n] / bg.achi_a - 1)) < 1e-11
+        # RK4 at dlna = 2e-3 vs DOP853 at rtol 1e-11 (the reference's RKCK runs at 1e-6)
+        assert np.max(np.abs(dev["growth"][i] / bg.growth - 1)) < 2e-9
+        assert np.max(np.abs(dev["fgrowth"][i] / bg.fgrowth - 1)) < 2e-9
+        assert abs(dev["growth0"][i] / bg.growth0 - 1) < 2e-9
