@@ -172,6 +172,248 @@ __global__ void bg_growth_kernel(int ncosmo, int na, const double* __restrict__ 
     if (a_grid[i] >= a_init) D[i] /= g0;
 }
 
+// ------------------------------------------------------------------------------------------
+// GSL-compatible spline arithmetic evaluated straight from the nodes (no coefficient table): used
+// where a freshly built table is read a handful of times per cosmology.
+// ------------------------------------------------------------------------------------------
+// gsl_interp_bsearch: i with x[i] <= v < x[i+1] (last interval closed)
+__device__ __forceinline__ int bsearch_nodes(const double* x, int n, double v) {
+  int lo = 0, hi = n - 1;
+  while (hi > lo + 1) {
+    const int m = (hi + lo) >> 1;
+    if (x[m] > v) hi = m; else lo = m;
+  }
+  return lo;
+}
+
+// slope m_j of the akima construction, j in [-2, n] (akima_init boundary rules)
+__device__ __forceinline__ double akima_slope(const double* x, const double* y, int n, int j) {
+  auto raw = [&](int q) { return (y[q + 1] - y[q]) / (x[q + 1] - x[q]); };
+  if (j >= 0 && j <= n - 2) return raw(j);
+  if (j == -1) return 2.0 * raw(0) - raw(1);
+  if (j == -2) return 3.0 * raw(0) - 2.0 * raw(1);
+  if (j == n - 1) return 2.0 * raw(n - 2) - raw(n - 3);
+  return 3.0 * raw(n - 2) - 2.0 * raw(n - 3);
+}
+
+// coefficients (b, c, d) of interval i (akima_calc)
+__device__ __forceinline__ void akima_interval(const double* x, const double* y, int n, int i, double& b,
+                                               double& c, double& d) {
+  const double mm2 = akima_slope(x, y, n, i - 2), mm1 = akima_slope(x, y, n, i - 1), m0 = akima_slope(x, y, n, i),
+               mp1 = akima_slope(x, y, n, i + 1), mp2 = akima_slope(x, y, n, i + 2);
+  const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
+  if (NE == 0.0) { b = m0; c = 0.0; d = 0.0; return; }
+  const double h = x[i + 1] - x[i];
+  const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
+  const double alpha = fabs(mm1 - mm2) / NE;
+  double tL;
+  if (NE_next == 0.0) tL = m0;
+  else {
+    const double alpha1 = fabs(m0 - mm1) / NE_next;
+    tL = (1.0 - alpha1) * m0 + alpha1 * mp1;
+  }
+  b = (1.0 - alpha) * mm1 + alpha * m0;
+  c = (3.0 * m0 - 2.0 * b - tL) / h;
+  d = (b + tL - 2.0 * m0) / (h * h);
+}
+
+__device__ __forceinline__ double akima_eval_direct(const double* x, const double* y, int n, double v) {
+  const int i = bsearch_nodes(x, n, v);
+  double b, c, d;
+  akima_interval(x, y, n, i, b, c, d);
+  const double dx = v - x[i];
+  return y[i] + dx * (b + dx * (c + dx * d));
+}
+
+// ------------------------------------------------------------------------------------------
+// Linear matter power: ccl_compute_linpower_analytic (src/ccl_power.c:28-146) with the BBKS
+// (src/ccl_bbks.c:10-26) or Eisenstein-Hu (src/ccl_eh.c:9-204) transfer function and the sigma8
+// normalisation (ccl_sigmaR, src/ccl_power.c:390-454).  One CTA per cosmology.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct EHConst {
+  double h, th2p7, keq, rsound, kSilk, alphac, betac, alphab, betab, bnode, rsound_approx, b_frac, OMh2, Om;
+};
+
+__device__ EHConst eh_constants(const double* p) {
+  EHConst e;
+  const double h = p[P_H];
+  const double OMh2 = p[P_OM] * h * h, OBh2 = p[P_OB] * h * h;
+  const double th2p7 = p[P_TCMB] / 2.7;
+  const double zeq = 2.5E4 * OMh2 / pow(th2p7, 4);
+  const double keq = 0.0746 * OMh2 / (h * th2p7 * th2p7);
+  const double b1 = 0.313 * pow(OMh2, -0.419) * (1 + 0.607 * pow(OMh2, 0.674));
+  const double b2 = 0.238 * pow(OMh2, 0.223);
+  const double zdrag = 1291 * pow(OMh2, 0.251) * (1 + b1 * pow(OBh2, b2)) / (1 + 0.659 * pow(OMh2, 0.828));
+  const double Req = 31.5 * OBh2 * 1000. / (zeq * pow(th2p7, 4));
+  const double Rd = 31.5 * OBh2 * 1000. / ((1 + zdrag) * pow(th2p7, 4));
+  e.rsound = 2 / (3 * keq) * sqrt(6 / Req) * log((sqrt(1 + Rd) + sqrt(Rd + Req)) / (1 + sqrt(Req)));
+  e.kSilk = 1.6 * pow(OBh2, 0.52) * pow(OMh2, 0.73) * (1 + pow(10.4 * OMh2, -0.95)) / h;
+  const double a1 = pow(46.9 * OMh2, 0.670) * (1 + pow(32.1 * OMh2, -0.532));
+  const double a2 = pow(12.0 * OMh2, 0.424) * (1 + pow(45.0 * OMh2, -0.582));
+  const double b_frac = OBh2 / OMh2;
+  e.alphac = pow(a1, -b_frac) * pow(a2, -(b_frac * b_frac * b_frac));
+  const double bb1 = 0.944 / (1 + pow(458 * OMh2, -0.708));
+  const double bb2 = pow(0.395 * OMh2, -0.0266);
+  e.betac = 1 / (1 + bb1 * (pow(1 - b_frac, bb2) - 1));
+  const double y = zeq / (1 + zdrag);
+  const double sqy = sqrt(1 + y);
+  const double gy = y * (-6 * sqy + (2 + 3 * y) * log((sqy + 1) / (sqy - 1)));
+  e.alphab = 2.07 * keq * e.rsound * pow(1 + Rd, -0.75) * gy;
+  e.betab = 0.5 + b_frac + (3 - 2 * b_frac) * sqrt((17.2 * OMh2) * (17.2 * OMh2) + 1);
+  e.bnode = 8.41 * pow(OMh2, 0.435);
+  e.rsound_approx = h * 44.5 * log(9.83 / OMh2) / sqrt(1 + 10 * pow(OBh2, 0.75));
+  e.h = h; e.th2p7 = th2p7; e.keq = keq; e.b_frac = b_frac; e.OMh2 = OMh2; e.Om = p[P_OM];
+  return e;
+}
+
+__device__ __forceinline__ double eh_tk0(const EHConst& e, double kk, double a, double b) {
+  const double q = kk / (13.41 * e.keq);
+  const double c = 14.2 / a + 386. / (1 + 69.9 * pow(q, 1.08));
+  const double l = log(M_E + 1.8 * b * q);
+  return l / (l + c * q * q);
+}
+
+// k^ns T(k)^2, k in 1/Mpc
+__device__ double analytic_pk(const double* p, const EHConst& e, int model, double k) {
+  if (model == 0) {  // BBKS
+    const double tfac = p[P_TCMB] / 2.7;
+    const double q = tfac * tfac * k / (p[P_OM] * p[P_H] * p[P_H] * exp(-p[P_OB] * (1.0 + sqrt(2. * p[P_H]) / p[P_OM])));
+    const double lg = log(1. + 2.34 * q) / (2.34 * q);
+    const double t2 = lg * lg / sqrt(1. + 3.89 * q + (16.1 * q) * (16.1 * q) + (5.46 * q) * (5.46 * q) * (5.46 * q) +
+                                     (6.71 * q) * (6.71 * q) * (6.71 * q) * (6.71 * q));
+    return pow(k, p[P_NS]) * t2;
+  }
+  const double kh = k / e.h;
+  double tk;
+  if (model == 1) {
+    const double f = 1 / (1 + pow(kh * e.rsound / 5.4, 4));
+    const double tc = f * eh_tk0(e, kh, 1, e.betac) + (1 - f) * eh_tk0(e, kh, e.alphac, e.betac);
+    const double x = kh * e.rsound;
+    const double x_bessel = x * pow(1 + e.bnode * e.bnode * e.bnode / (x * x * x), -1. / 3.);
+    const double part1 = eh_tk0(e, kh, 1, 1) / (1 + (x / 5.2) * (x / 5.2));
+    const double part2 = e.alphab / (1 + pow(e.betab / x, 3)) * exp(-pow(kh / e.kSilk, 1.4));
+    const double ax2 = x_bessel * x_bessel;
+    const double jl = (ax2 < 1e-4) ? 1 - ax2 * (1 - ax2 / 20.) / 6. : sin(x_bessel) / x_bessel;
+    const double tb = jl * (part1 + part2);
+    tk = e.b_frac * tb + (1 - e.b_frac) * tc;
+  } else {
+    const double alpha_gamma = 1 - 0.328 * log(431 * e.OMh2) * e.b_frac + 0.38 * log(22.3 * e.OMh2) * e.b_frac * e.b_frac;
+    const double gamma_eff = e.Om * e.h * (alpha_gamma + (1 - alpha_gamma) / (1 + pow(0.43 * kh * e.rsound_approx, 4)));
+    const double q = kh * e.th2p7 * e.th2p7 / gamma_eff;
+    const double l0 = log(2 * M_E + 1.8 * q);
+    const double c0 = 14.2 + 731 / (1 + 62.5 * q);
+    tk = l0 / (l0 + c0 * q * q);
+  }
+  return pow(k, p[P_NS]) * tk * tk;
+}
+
+// w_tophat (src/ccl_power.c:390-404)
+__device__ __forceinline__ double w_tophat(double kR) {
+  if (kR < 0.1) {
+    const double kR2 = kR * kR;
+    return 1. + kR2 * (-1.0 / 10.0 + kR2 * (1.0 / 280.0 + kR2 * (-1.0 / 15120.0 + kR2 * (1.0 / 1330560.0 +
+                                                                                     kR2 * (-1.0 / 172972800.0)))));
+  }
+  return 3. * (sin(kR) - kR * cos(kR)) / (kR * kR * kR);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256)
+linpower_kernel(int nk, const double* __restrict__ k_grid, int na_pk, const double* __restrict__ a_pk,
+                int na_bg, const double* __restrict__ a_bg, const double* __restrict__ growth,
+                const double* __restrict__ params, int model, double lg_kmin, double lg_kmax, int npanel,
+                double* __restrict__ logp, double* __restrict__ sigma8_unnorm) {
+  extern __shared__ double sm[];
+  double* lk = sm;          // [nk]
+  double* row = lk + nk;    // log P at a = 1
+  double* cc = row + nk;    // natural-spline c at the nodes
+  double* tmp = cc + nk;    // forward-sweep scratch
+  __shared__ double red[256];
+  const int ic = blockIdx.x;
+  const double* p = params + (size_t)ic * CCL_B200_NPAR;
+  const EHConst e = eh_constants(p);
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+    lk[i] = log(k_grid[i]);
+    row[i] = log(analytic_pk(p, e, model, k_grid[i]));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // natural cubic spline of the a = 1 row (gsl cspline_init): tridiagonal solve for c_1..c_{n-2}
+    const int N = nk - 2;
+    cc[0] = 0.0;
+    cc[nk - 1] = 0.0;
+    auto hh = [&](int i) { return lk[i + 1] - lk[i]; };
+    auto g = [&](int i) { return 3.0 * ((row[i + 2] - row[i + 1]) / hh(i + 1) - (row[i + 1] - row[i]) / hh(i)); };
+    // Thomas algorithm: tmp = modified upper diagonal, cc[1..] = modified rhs
+    double beta = 2.0 * (hh(0) + hh(1));
+    tmp[0] = hh(1) / beta;
+    cc[1] = g(0) / beta;
+    for (int i = 1; i < N; ++i) {
+      beta = 2.0 * (hh(i) + hh(i + 1)) - hh(i) * tmp[i - 1];
+      tmp[i] = hh(i + 1) / beta;
+      cc[i + 1] = (g(i) - hh(i) * cc[i]) / beta;
+    }
+    for (int i = N - 2; i >= 0; --i) cc[i + 1] -= tmp[i] * cc[i + 2];
+  }
+  __syncthreads();
+  // sigma_R at R = 8/h: composite 16-point Gauss-Legendre in log10 k over the spline of the table row
+  const double R = 8.0 / p[P_H];
+  const double step = (lg_kmax - lg_kmin) / npanel;
+  const double inv_dlk = (nk - 1) / (lk[nk - 1] - lk[0]);
+  double acc = 0.0;
+  for (int t = threadIdx.x; t < npanel * 16; t += blockDim.x) {
+    const int j = t >> 4, q = t & 15;
+    const double e0 = lg_kmin + j * step, e1 = (j == npanel - 1) ? lg_kmax : lg_kmin + (j + 1) * step;
+    const double mid = 0.5 * (e1 + e0), half = 0.5 * (e1 - e0);
+    const double x = mid + half * GL16_X[q];
+    const double k = pow(10., x);
+    const double lkq = fmin(fmax(x * log(10.), lk[0]), lk[nk - 1]);
+    int i = (int)((lkq - lk[0]) * inv_dlk);
+    i = min(max(i, 0), nk - 2);
+    while (i > 0 && lkq < lk[i]) --i;
+    while (i < nk - 2 && lkq >= lk[i + 1]) ++i;
+    const double h = lk[i + 1] - lk[i], dy = row[i + 1] - row[i];
+    const double b = dy / h - h * (cc[i + 1] + 2.0 * cc[i]) / 3.0;
+    const double d = (cc[i + 1] - cc[i]) / (3.0 * h);
+    const double dx = lkq - lk[i];
+    const double pk = exp(row[i] + dx * (b + dx * (cc[i] + dx * d)));
+    const double w = w_tophat(k * R);
+    acc += half * GL16_W[q] * pk * k * k * k * w * w;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double sigma8 = sqrt(red[0] * log(10.) / (2 * M_PI * M_PI));
+  if (threadIdx.x == 0) sigma8_unnorm[ic] = sigma8;
+  const double shift = 2 * (log(p[P_S8]) - log(sigma8));
+  // log P(k, a) = log(k^ns T^2) + 2 log D(a) + 2 log(sigma8_in / sigma8) (src/ccl_power.c:99-130)
+  const double* D = growth + (size_t)ic * na_bg;
+  for (int ja = 0; ja < na_pk; ++ja) {
+    const double a = a_pk[ja];
+    const double Da = (a == 1.0) ? 1.0 : akima_eval_direct(a_bg, D, na_bg, a);
+    const double g2 = 2. * log(Da);
+    for (int i = threadIdx.x; i < nk; i += blockDim.x)
+      logp[((size_t)ic * na_pk + ja) * nk + i] = row[i] + g2 + shift;
+  }
+}
+
+void launch_build_linpower(int ncosmo, int nk, const double* d_k, int na_pk, const double* d_apk, int na_bg,
+                           const double* d_abg, const double* d_growth, const double* d_params, int model,
+                           double lg_kmin, double lg_kmax, double* d_logp, double* d_sigma8, cudaStream_t stream) {
+  if (ncosmo <= 0) return;
+  const size_t smem = sizeof(double) * 4 * (size_t)nk;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(linpower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  linpower_kernel<<<ncosmo, 256, smem, stream>>>(nk, d_k, na_pk, d_apk, na_bg, d_abg, d_growth, d_params, model,
+                                                 lg_kmin, lg_kmax, 600, d_logp, d_sigma8);
+}
+
 void launch_build_background(int ncosmo, int na, const double* d_a, const double* d_params, double dchi,
                              double epsrel, int nmax, double a_init, int stride, double* d_E, double* d_chi,
                              int* d_n, double* d_achi_chi, double* d_achi_a, double* d_growth, double* d_fgrowth,

@@ -1349,4 +1349,37 @@ void ccl_b200_build_background(int ncosmo, const double* params, int na, const d
     }
 }
 
+void ccl_b200_build_linear_power(int ncosmo, const double* params, int model, int nk, const double* k_grid,
+                                 int na_pk, const double* a_pk, int na_bg, const double* a_bg,
+                                 const double* growth, double k_min, double k_max, double* logp,
+                                 double* sigma8_unnorm, int* status) {
+  if (*status) return;
+  if (!use_device(status)) return;
+  if (ncosmo <= 0 || nk < 4 || na_pk < 1 || na_bg < 5 || model < 0 || model > 2) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200_build_linear_power: inconsistent arguments");
+    return;
+  }
+  const size_t nc = (size_t)ncosmo;
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t o_par = 0, o_k = o_par + up(nc * CCL_B200_NPAR * 8), o_apk = o_k + up((size_t)nk * 8),
+               o_abg = o_apk + up((size_t)na_pk * 8), o_D = o_abg + up((size_t)na_bg * 8),
+               o_lp = o_D + up(nc * na_bg * 8), o_s8 = o_lp + up(nc * na_pk * nk * 8), total = o_s8 + up(nc * 8);
+  DevBuf buf;
+  if (!buf.reserve(total, status)) return;
+  char* d = buf.p;
+  cudaMemcpy(d + o_par, params, nc * CCL_B200_NPAR * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_k, k_grid, (size_t)nk * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_apk, a_pk, (size_t)na_pk * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_abg, a_bg, (size_t)na_bg * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_D, growth, nc * na_bg * 8, cudaMemcpyHostToDevice);
+  launch_build_linpower(ncosmo, nk, (double*)(d + o_k), na_pk, (double*)(d + o_apk), na_bg, (double*)(d + o_abg),
+                        (double*)(d + o_D), (double*)(d + o_par), model, log10(k_min), log10(k_max),
+                        (double*)(d + o_lp), (double*)(d + o_s8), 0);
+  if (!cuda_ok(cudaGetLastError(), "linear power builder launch", status)) return;
+  if (!cuda_ok(cudaDeviceSynchronize(), "linear power builder", status)) return;
+  cudaMemcpy(logp, d + o_lp, nc * na_pk * nk * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(sigma8_unnorm, d + o_s8, nc * 8, cudaMemcpyDeviceToHost);
+}
+
 }  // extern "C"

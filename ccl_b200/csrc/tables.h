@@ -197,4 +197,8 @@ void launch_build_background(int ncosmo, int na, const double* d_a, const double
                              int* d_n, double* d_achi_chi, double* d_achi_a, double* d_growth, double* d_fgrowth,
                              double* d_growth0, cudaStream_t stream);
 
+void launch_build_linpower(int ncosmo, int nk, const double* d_k, int na_pk, const double* d_apk, int na_bg,
+                           const double* d_abg, const double* d_growth, const double* d_params, int model,
+                           double lg_kmin, double lg_kmax, double* d_logp, double* d_sigma8, cudaStream_t stream);
+
 }  // namespace cclb

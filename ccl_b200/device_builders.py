@@ -51,3 +51,30 @@ def build_background(cosmologies, spline_params=None, gsl_params=None, stride=81
                                           dp(out["growth0"]), C.byref(st))
     check(st.value)
     return out
+
+
+_MODELS = {"bbks": 0, "eisenstein_hu": 1, "eisenstein_hu_nowiggles": 2}
+
+
+def build_linear_power(cosmologies, model, background, spline_params=None):
+    """log P_lin(k, a) tables [nc, na_pk, nk] on the default (k, a) grids, sigma8-normalised, built on the
+    device from the device-built growth tables.  Returns dict(lk, a, logp, sigma8_unnorm)."""
+    from .parameters import spline_params as sp0
+    from .power import pk_grids
+    sp = spline_params if spline_params is not None else sp0
+    par = np.ascontiguousarray(pack_params(cosmologies))
+    if np.any(~np.isfinite(par[:, 11])):
+        raise ValueError("sigma8 not set, required for analytic power spectra")
+    k, a_pk = pk_grids(sp)
+    nc = par.shape[0]
+    a_bg = np.ascontiguousarray(background["a"])
+    D = np.ascontiguousarray(background["growth"])
+    logp = np.empty((nc, a_pk.size, k.size))
+    s8 = np.empty(nc)
+    st = C.c_int(0)
+    dp = lambda x: x.ctypes.data_as(_lib._dp)
+    _lib.load().ccl_b200_build_linear_power(nc, dp(par), _MODELS[model], k.size, dp(k), a_pk.size, dp(a_pk),
+                                            a_bg.size, dp(a_bg), dp(D), float(sp["K_MIN"]), float(sp["K_MAX"]),
+                                            dp(logp), dp(s8), C.byref(st))
+    check(st.value)
+    return dict(lk=np.log(k), a=a_pk, logp=logp, sigma8_unnorm=s8)

@@ -237,6 +237,18 @@ void ccl_b200_build_background(int ncosmo, const double *params, int na, const d
                                double *E, double *chi, int *n_achi, double *achi_chi, double *achi_a,
                                double *growth, double *fgrowth, double *growth0, int *status);
 
+/* ccl_compute_linpower_analytic (src/ccl_power.c:28-146) on the device for ncosmo cosmologies:
+ * log P(k, a) = log(k^ns T(k)^2) + 2 log D(a) + 2 log(sigma8 / sigma8_unnormalised) on the shared grids
+ * k_grid[nk] (1/Mpc) x a_pk[na_pk].  model: 0 = BBKS (src/ccl_bbks.c), 1 = Eisenstein-Hu,
+ * 2 = Eisenstein-Hu without wiggles (src/ccl_eh.c).  growth[ncosmo][na_bg] is D(a) on a_bg[na_bg]
+ * (e.g. from ccl_b200_build_background), read through its Akima spline like ccl_growth_factor.
+ * sigma8 of the unnormalised table is integrated over [k_min, k_max] like ccl_sigmaR
+ * (src/ccl_power.c:390-454).  Host outputs: logp[ncosmo][na_pk][nk], sigma8_unnorm[ncosmo]. */
+void ccl_b200_build_linear_power(int ncosmo, const double *params, int model, int nk, const double *k_grid,
+                                 int na_pk, const double *a_pk, int na_bg, const double *a_bg,
+                                 const double *growth, double k_min, double k_max, double *logp,
+                                 double *sigma8_unnorm, int *status);
+
 #ifdef __cplusplus
 }
 #endif
