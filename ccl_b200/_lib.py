@@ -97,6 +97,8 @@ SIGNATURES = {
     "ccl_b200_batch_last_used_fast_path": (C.c_int, [_vp]),
     "ccl_b200_build_linear_power": (None, [C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp,
                                            C.c_double, C.c_double, _dp, _dp, _ip]),
+    "ccl_b200_build_tracer_kernels": (None, [C.c_int, _dp, C.c_int, _dp, _dp, _ip, C.c_int, _dp, _dp, C.c_int, _dp,
+                                             C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _ip]),
     "ccl_b200_build_background": (None, [C.c_int, _dp, C.c_int, _dp, C.c_double, C.c_double, C.c_int, C.c_double,
                                          C.c_int, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _ip]),
 }

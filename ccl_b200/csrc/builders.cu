@@ -414,6 +414,142 @@ void launch_build_linpower(int ncosmo, int nk, const double* d_k, int na_pk, con
                                                  lg_kmin, lg_kmax, 600, d_logp, d_sigma8);
 }
 
+// ------------------------------------------------------------------------------------------
+// Tracer radial kernels from n(z): number counts p(z) H(z) (ccl_get_number_counts_kernel,
+// src/ccl_tracers.c:121-160) and the lensing / magnification kernel by Akima-spline integration
+// with the reference's trapezoid edge term (integrate_lensing_kernel_spline, :347-454; node
+// placement ccl_get_chis_lensing_kernel, :470-479).  One CTA per (cosmology, n(z)); one thread per
+// lensing-kernel node walks the n(z) grid with a sliding window of Akima slopes.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ double sinn(const double* p, double chi) {  // ccl_sinn, src/ccl_background.c:107-131
+  const double ks = p[P_KSIGN], sk = p[P_SQRTK];
+  if (ks == -1.0) return sinh(sk * chi) / sk;
+  if (ks == 1.0) return sin(sk * chi) / sk;
+  return chi;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256)
+tracer_kernel_builder(int na, const double* __restrict__ a_bg, const double* __restrict__ chi_bg,
+                      const int* __restrict__ n_achi, int stride, const double* __restrict__ achi_chi,
+                      const double* __restrict__ achi_a, const double* __restrict__ params, int nz,
+                      const double* __restrict__ z, int ntr, const double* __restrict__ nz_arr,
+                      const double* __restrict__ sz_arr, const double* __restrict__ inv_norm, int nchi,
+                      double* __restrict__ chi_z_out, double* __restrict__ w_nc, double* __restrict__ chi_l_out,
+                      double* __restrict__ w_l) {
+  extern __shared__ double sm[];
+  double* chz = sm;        // chi at the n(z) nodes
+  double* nq = chz + nz;   // n(z) (1 - 2.5 s(z))
+  double* snz = nq + nz;   // sinn(chi(z))
+  const int ic = blockIdx.x, it = blockIdx.y;
+  const double* p = params + (size_t)ic * CCL_B200_NPAR;
+  const double* chi_a = chi_bg + (size_t)ic * na;
+  const double* nzv = nz_arr + (size_t)it * nz;
+  const double inorm = inv_norm[it];
+  for (int j = threadIdx.x; j < nz; j += blockDim.x) {
+    const double a = 1. / (1 + z[j]);
+    // ccl_comoving_radial_distance: Akima spline of chi(a), 0 at a = 1
+    const double c = (a == 1.0) ? 0.0 : akima_eval_direct(a_bg, chi_a, na, a);
+    chz[j] = c;
+    snz[j] = sinn(p, c);
+    nq[j] = nzv[j] * (sz_arr ? 1 - 2.5 * sz_arr[(size_t)it * nz + j] : 1.0);
+    if (it == 0) chi_z_out[(size_t)ic * nz + j] = c;
+    // H(z) p(z): h E(a) / c * n(z) / norm
+    w_nc[((size_t)ic * ntr + it) * nz + j] = p[P_H] * h_over_h0(p, a) / CLIGHT_HMPC * nzv[j] * inorm;
+  }
+  __syncthreads();
+  const int ik = threadIdx.x;
+  if (ik >= nchi) return;
+  const double z_k = (z[nz - 1] / nchi) * ik + 1E-15;
+  const double ak0 = 1. / (1 + z_k);
+  const double chi_end = (ak0 == 1.0) ? 0.0 : akima_eval_direct(a_bg, chi_a, na, ak0);
+  // ccl_scale_factor_of_chi on the freshly built a(chi) table
+  const double a_k = (chi_end < 1e-8) ? 1.0
+                                      : akima_eval_direct(achi_chi + (size_t)ic * stride, achi_a + (size_t)ic * stride,
+                                                          n_achi[ic], chi_end);
+  const double z_end = 1. / a_k - 1;
+  // integrand on the n(z) grid: 0 below chi_end, n q sinn(chi - chi_end) / sinn(chi) above
+  auto yv = [&](int j) -> double {
+    const double c = chz[j];
+    if (c < chi_end) return 0.0;
+    if (c == 0.0) return nq[j];
+    return nq[j] * sinn(p, c - chi_end) / snz[j];
+  };
+  int i_end = 0;  // chi(z) is increasing: number of nodes below chi_end
+  {
+    int lo = 0, hi = nz;
+    while (lo < hi) {
+      const int m = (lo + hi) >> 1;
+      if (chz[m] < chi_end) lo = m + 1; else hi = m;
+    }
+    i_end = lo;
+  }
+  auto raw = [&](int q) { return (yv(q + 1) - yv(q)) / (z[q + 1] - z[q]); };
+  auto slope = [&](int j) -> double {
+    if (j >= 0 && j <= nz - 2) return raw(j);
+    if (j == -1) return 2.0 * raw(0) - raw(1);
+    if (j == -2) return 3.0 * raw(0) - 2.0 * raw(1);
+    if (j == nz - 1) return 2.0 * raw(nz - 2) - raw(nz - 3);
+    return 3.0 * raw(nz - 2) - 2.0 * raw(nz - 3);
+  };
+  double res = 0.0;
+  if (i_end <= nz - 2) {
+    // gsl_spline_eval_integ from the node z[i_end] to z[nz-1]: whole intervals of the Akima spline
+    double mm2 = slope(i_end - 2), mm1 = slope(i_end - 1), m0 = slope(i_end), mp1 = slope(i_end + 1),
+           mp2 = slope(i_end + 2);
+    double y_i = yv(i_end);
+    for (int i = i_end; i <= nz - 2; ++i) {
+      const double h = z[i + 1] - z[i];
+      const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
+      double b, c, d;
+      if (NE == 0.0) { b = m0; c = 0.0; d = 0.0; }
+      else {
+        const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
+        const double alpha = fabs(mm1 - mm2) / NE;
+        double tL;
+        if (NE_next == 0.0) tL = m0;
+        else {
+          const double alpha1 = fabs(m0 - mm1) / NE_next;
+          tL = (1.0 - alpha1) * m0 + alpha1 * mp1;
+        }
+        b = (1.0 - alpha) * mm1 + alpha * m0;
+        c = (3.0 * m0 - 2.0 * b - tL) / h;
+        d = (b + tL - 2.0 * m0) / (h * h);
+      }
+      // (x2 - x1) (y + b r12/2 + c (r1^2 + r2^2 + r1 r2)/3 + d r12 (r1^2 + r2^2)/4) with r1 = 0, r2 = h
+      res += h * (y_i + 0.5 * b * h + (1. / 3.) * c * (h * h) + 0.25 * d * h * (h * h));
+      // slide the window
+      y_i = yv(i + 1);
+      mm2 = mm1; mm1 = m0; m0 = mp1; mp1 = mp2;
+      mp2 = slope(i + 3);
+    }
+  }
+  const double y_end = (i_end < nz) ? yv(i_end) : 0.0;
+  if (z_end > z[0] && i_end < nz) res += 0.5 * (z[i_end] - z_end) * y_end;
+  const double hub = p[P_H] / CLIGHT_HMPC;
+  const double pref = 1.5 * hub * hub * p[P_OM];  // get_lensing_prefactor, src/ccl_tracers.c:163-166
+  if (it == 0) chi_l_out[(size_t)ic * nchi + ik] = chi_end;
+  w_l[((size_t)ic * ntr + it) * nchi + ik] = res * pref * inorm * chi_end / a_k;
+}
+
+void launch_build_tracer_kernels(int ncosmo, int na, const double* d_abg, const double* d_chibg, const int* d_nachi,
+                                 int stride, const double* d_achi_chi, const double* d_achi_a, const double* d_params,
+                                 int nz, const double* d_z, int ntr, const double* d_nz, const double* d_sz,
+                                 const double* d_inv_norm, int nchi, double* d_chi_z, double* d_w_nc, double* d_chi_l,
+                                 double* d_w_l, cudaStream_t stream) {
+  if (ncosmo <= 0 || ntr <= 0) return;
+  const size_t smem = sizeof(double) * 3 * (size_t)nz;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(tracer_kernel_builder, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(ncosmo, ntr);
+  tracer_kernel_builder<<<grid, 256, smem, stream>>>(na, d_abg, d_chibg, d_nachi, stride, d_achi_chi, d_achi_a,
+                                                     d_params, nz, d_z, ntr, d_nz, d_sz, d_inv_norm, nchi, d_chi_z,
+                                                     d_w_nc, d_chi_l, d_w_l);
+}
+
 void launch_build_background(int ncosmo, int na, const double* d_a, const double* d_params, double dchi,
                              double epsrel, int nmax, double a_init, int stride, double* d_E, double* d_chi,
                              int* d_n, double* d_achi_chi, double* d_achi_a, double* d_growth, double* d_fgrowth,

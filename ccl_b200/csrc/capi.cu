@@ -1382,4 +1382,49 @@ void ccl_b200_build_linear_power(int ncosmo, const double* params, int model, in
   cudaMemcpy(sigma8_unnorm, d + o_s8, nc * 8, cudaMemcpyDeviceToHost);
 }
 
+void ccl_b200_build_tracer_kernels(int ncosmo, const double* params, int na, const double* a_bg,
+                                   const double* chi_bg, const int* n_achi, int stride, const double* achi_chi,
+                                   const double* achi_a, int nz, const double* z, int ntr, const double* nz_arr,
+                                   const double* sz_arr, const double* inv_norm, int nchi, double* chi_z,
+                                   double* w_nc, double* chi_l, double* w_l, int* status) {
+  if (*status) return;
+  if (!use_device(status)) return;
+  if (ncosmo <= 0 || ntr <= 0 || nz < 5 || na < 5 || nchi < 1 || nchi > 256 || ntr > 65535) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200_build_tracer_kernels: need nz >= 5, 1 <= nchi <= 256, ntr <= 65535");
+    return;
+  }
+  const size_t nc = (size_t)ncosmo, snz = (size_t)nz, st = (size_t)stride, nt = (size_t)ntr;
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += up(bytes); return o; };
+  const size_t o_par = take(nc * CCL_B200_NPAR * 8), o_a = take((size_t)na * 8), o_chi = take(nc * na * 8),
+               o_n = take(nc * 4), o_gx = take(nc * st * 8), o_ga = take(nc * st * 8), o_z = take(snz * 8),
+               o_nz = take(nt * snz * 8), o_sz = take(nt * snz * 8), o_in = take(nt * 8), o_cz = take(nc * snz * 8),
+               o_wn = take(nc * nt * snz * 8), o_cl = take(nc * nchi * 8), o_wl = take(nc * nt * nchi * 8);
+  DevBuf buf;
+  if (!buf.reserve(off, status)) return;
+  char* d = buf.p;
+  cudaMemcpy(d + o_par, params, nc * CCL_B200_NPAR * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_a, a_bg, (size_t)na * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_chi, chi_bg, nc * na * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_n, n_achi, nc * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_gx, achi_chi, nc * st * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_ga, achi_a, nc * st * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_z, z, snz * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_nz, nz_arr, nt * snz * 8, cudaMemcpyHostToDevice);
+  if (sz_arr) cudaMemcpy(d + o_sz, sz_arr, nt * snz * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_in, inv_norm, nt * 8, cudaMemcpyHostToDevice);
+  launch_build_tracer_kernels(ncosmo, na, (double*)(d + o_a), (double*)(d + o_chi), (int*)(d + o_n), stride,
+                              (double*)(d + o_gx), (double*)(d + o_ga), (double*)(d + o_par), nz, (double*)(d + o_z),
+                              ntr, (double*)(d + o_nz), sz_arr ? (double*)(d + o_sz) : nullptr, (double*)(d + o_in),
+                              nchi, (double*)(d + o_cz), (double*)(d + o_wn), (double*)(d + o_cl), (double*)(d + o_wl), 0);
+  if (!cuda_ok(cudaGetLastError(), "tracer kernel builder launch", status)) return;
+  if (!cuda_ok(cudaDeviceSynchronize(), "tracer kernel builder", status)) return;
+  cudaMemcpy(chi_z, d + o_cz, nc * snz * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(w_nc, d + o_wn, nc * nt * snz * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(chi_l, d + o_cl, nc * nchi * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(w_l, d + o_wl, nc * nt * nchi * 8, cudaMemcpyDeviceToHost);
+}
+
 }  // extern "C"

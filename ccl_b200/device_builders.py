@@ -78,3 +78,34 @@ def build_linear_power(cosmologies, model, background, spline_params=None):
                                             dp(logp), dp(s8), C.byref(st))
     check(st.value)
     return dict(lk=np.log(k), a=a_pk, logp=logp, sigma8_unnorm=s8)
+
+
+def build_tracer_kernels(cosmologies, background, z, nz_list, mag_bias_list=None, n_chi=256):
+    """Number-counts and lensing kernels of every (cosmology, n(z)) on the device.
+
+    z[nz] is shared; nz_list is a sequence of n(z) arrays on it; mag_bias_list (optional) the
+    magnification-bias functions s(z) on the same grid.  Returns dict(chi_z[nc, nz], w_nc[nc, ntr, nz],
+    chi_l[nc, n_chi], w_l[nc, ntr, n_chi])."""
+    from ._hostspline import Akima
+    par = np.ascontiguousarray(pack_params(cosmologies))
+    z = np.ascontiguousarray(z, dtype=float)
+    nzs = np.ascontiguousarray(np.stack([np.asarray(n, dtype=float) for n in nz_list]))
+    szs = None if mag_bias_list is None else np.ascontiguousarray(np.stack([np.asarray(s_, dtype=float) for s_ in mag_bias_list]))
+    inv_norm = np.array([1.0 / float(Akima(z, n).integrate_nodes()) for n in nzs])   # get_nz_norm, spline mode
+    nc, ntr = par.shape[0], nzs.shape[0]
+    a_bg = np.ascontiguousarray(background["a"])
+    out = dict(chi_z=np.empty((nc, z.size)), w_nc=np.empty((nc, ntr, z.size)), chi_l=np.empty((nc, n_chi)),
+               w_l=np.empty((nc, ntr, n_chi)))
+    st = C.c_int(0)
+    dp = lambda x: None if x is None else x.ctypes.data_as(_lib._dp)
+    chi_bg = np.ascontiguousarray(background["chi"])
+    n_achi = np.ascontiguousarray(background["n_achi"], dtype=np.int32)
+    gx = np.ascontiguousarray(background["achi_chi"])
+    ga = np.ascontiguousarray(background["achi_a"])
+    _lib.load().ccl_b200_build_tracer_kernels(nc, dp(par), a_bg.size, dp(a_bg), dp(chi_bg),
+                                              n_achi.ctypes.data_as(_lib._ip), gx.shape[1], dp(gx), dp(ga), z.size,
+                                              dp(z), ntr, dp(nzs), dp(szs), dp(inv_norm), int(n_chi),
+                                              dp(out["chi_z"]), dp(out["w_nc"]), dp(out["chi_l"]), dp(out["w_l"]),
+                                              C.byref(st))
+    check(st.value)
+    return out

@@ -249,6 +249,22 @@ void ccl_b200_build_linear_power(int ncosmo, const double *params, int model, in
                                  const double *growth, double k_min, double k_max, double *logp,
                                  double *sigma8_unnorm, int *status);
 
+/* Radial kernels of n(z)-defined tracers for ncosmo cosmologies on the device.  Shared by all
+ * cosmologies: the redshift grid z[nz], ntr distributions nz_arr[ntr][nz], optional magnification
+ * bias sz_arr[ntr][nz] on the same grid (NULL: none) and inv_norm[ntr] = 1 / integral of n(z)
+ * (get_nz_norm, src/ccl_tracers.c:60-119; cosmology-independent).  Per cosmology: params, the chi(a)
+ * table chi_bg[ncosmo][na] on a_bg[na] and the a(chi) table (n_achi, stride, achi_chi, achi_a), e.g.
+ * from ccl_b200_build_background.  Host outputs: chi_z[ncosmo][nz] (chi at the n(z) nodes = abscissa
+ * of the number-counts kernels), w_nc[ncosmo][ntr][nz] = p(z) H(z) (ccl_get_number_counts_kernel,
+ * src/ccl_tracers.c:121-160), chi_l[ncosmo][nchi] and w_l[ncosmo][ntr][nchi]: the lensing kernel
+ * nodes (ccl_get_chis_lensing_kernel, :470-479) and values by Akima-spline integration with the
+ * trapezoid edge term (integrate_lensing_kernel_spline, :347-454).  nchi <= 256. */
+void ccl_b200_build_tracer_kernels(int ncosmo, const double *params, int na, const double *a_bg,
+                                   const double *chi_bg, const int *n_achi, int stride, const double *achi_chi,
+                                   const double *achi_a, int nz, const double *z, int ntr, const double *nz_arr,
+                                   const double *sz_arr, const double *inv_norm, int nchi, double *chi_z,
+                                   double *w_nc, double *chi_l, double *w_l, int *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,3 +55,27 @@ def test_linear_power_matches_host_builder(model):
         assert np.array_equal(a, dev["a"]) and np.max(np.abs(lk - dev["lk"])) < 1e-14
         # log P agrees to the growth tables' agreement (2e-9 relative in D -> 4e-9 absolute in log P)
         assert np.max(np.abs(dev["logp"][i] - tab)) < 2e-8, (model, i, np.max(np.abs(dev["logp"][i] - tab)))
+
+
+def test_tracer_kernels_match_host_builder():
+    import ccl_b200 as ccl
+    from ccl_b200 import device_builders as db
+    from ccl_b200 import synthetic as S
+    cos = _cosmologies()
+    z = np.linspace(0.0, 3.5, 500)
+    nzs = S.smail_bins(z, 0.26, 0.94, edges=np.arange(0.2, 1.2 + 1e-9, 0.2), sigma_z=0.03)[:2] + \
+        S.smail_bins(z, 0.13, 0.78, nbins=10, sigma_z=0.05)[::4]
+    sz = [0.4 + 0.1 * z for _ in nzs]
+    bgd = db.build_background(cos)
+    for mag in (None, sz):
+        dev = db.build_tracer_kernels(cos, bgd, z, nzs, mag)
+        for i, c in enumerate(cos):
+            for t, n in enumerate(nzs):
+                chi, w = ccl.get_density_kernel(c, dndz=(z, n))
+                assert np.max(np.abs(dev["chi_z"][i] - chi)) < 1e-7 * chi.max()
+                assert np.max(np.abs(dev["w_nc"][i, t] - w)) < 1e-12 * np.max(np.abs(w))
+                ck, wk = ccl.get_lensing_kernel(c, dndz=(z, n), mag_bias=None if mag is None else (z, mag[t]),
+                                                n_chi=256)
+                assert np.max(np.abs(dev["chi_l"][i] - ck)) < 1e-7 * ck.max()
+                # same Akima integral and edge term on tables that agree to ~1e-11
+                assert np.max(np.abs(dev["w_l"][i, t] - wk)) < 1e-8 * np.max(np.abs(wk)), (i, t)
