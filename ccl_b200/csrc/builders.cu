@@ -550,6 +550,197 @@ void launch_build_tracer_kernels(int ncosmo, int na, const double* d_abg, const 
                                                      d_w_nc, d_chi_l, d_w_l);
 }
 
+// ------------------------------------------------------------------------------------------
+// Halofit (Takahashi et al. 2012 with the Bird et al. 2012 neutrino terms at f_nu = 0):
+// ccl_apply_halofit (src/ccl_power.c:171-232) = per scale factor the non-linear scale sigma(R) = 1
+// (get_rsigma, src/ccl_halofit.c:259-315), n_eff and C from the first two derivatives (:322-554),
+// then ccl_halofit_power (:828-930) on every k.  One CTA per (cosmology, a-node): the row's natural
+// cubic spline is built once, the Gaussian-filtered moments are 16-point Gauss-Legendre sums over
+// ln k spread over the CTA, the root is found by bracketed Newton iterations on ln R.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double* __restrict__ a_grid,
+               const double* __restrict__ logplin, const double* __restrict__ params, double* __restrict__ logpnl,
+               double* __restrict__ rsigma_out, int* __restrict__ fail) {
+  extern __shared__ double sm[];
+  double* lk = sm;
+  double* row = lk + nk;
+  double* cc = row + nk;
+  double* tmp = cc + nk;
+  __shared__ double red[3][256];
+  const int ic = blockIdx.x, ia = blockIdx.y;
+  const double* p = params + (size_t)ic * CCL_B200_NPAR;
+  const double* src = logplin + ((size_t)ic * na + ia) * nk;
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+    lk[i] = lk_grid[i];
+    row[i] = src[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int N = nk - 2;
+    cc[0] = 0.0;
+    cc[nk - 1] = 0.0;
+    auto hh = [&](int i) { return lk[i + 1] - lk[i]; };
+    auto g = [&](int i) { return 3.0 * ((row[i + 2] - row[i + 1]) / hh(i + 1) - (row[i + 1] - row[i]) / hh(i)); };
+    double beta = 2.0 * (hh(0) + hh(1));
+    tmp[0] = hh(1) / beta;
+    cc[1] = g(0) / beta;
+    for (int i = 1; i < N; ++i) {
+      beta = 2.0 * (hh(i) + hh(i + 1)) - hh(i) * tmp[i - 1];
+      tmp[i] = hh(i + 1) / beta;
+      cc[i + 1] = (g(i) - hh(i) * cc[i]) / beta;
+    }
+    for (int i = N - 2; i >= 0; --i) cc[i + 1] -= tmp[i] * cc[i + 2];
+  }
+  __syncthreads();
+  const double lnkmin = lk[0], lnkmax_t = lk[nk - 1];
+  const double inv_dlk = (nk - 1) / (lnkmax_t - lnkmin);
+  // edge derivatives for the ln k extrapolation of ccl_f2d_t_eval (order 1 below, order 2 above)
+  double d1_lo, d1_hi, d2_hi;
+  {
+    const double h0 = lk[1] - lk[0];
+    d1_lo = (row[1] - row[0]) / h0 - h0 * (cc[1] + 2.0 * cc[0]) / 3.0;
+    const int i = nk - 2;
+    const double h = lk[i + 1] - lk[i];
+    const double b = (row[i + 1] - row[i]) / h - h * (cc[i + 1] + 2.0 * cc[i]) / 3.0;
+    const double d = (cc[i + 1] - cc[i]) / (3.0 * h);
+    d1_hi = b + h * (2.0 * cc[i] + 3.0 * d * h);
+    d2_hi = 2.0 * cc[i] + 6.0 * d * h;
+  }
+  auto plin = [&](double x) -> double {
+    const double xi = fmin(fmax(x, lnkmin), lnkmax_t);
+    int i = (int)((xi - lnkmin) * inv_dlk);
+    i = min(max(i, 0), nk - 2);
+    while (i > 0 && xi < lk[i]) --i;
+    while (i < nk - 2 && xi >= lk[i + 1]) ++i;
+    const double h = lk[i + 1] - lk[i];
+    const double b = (row[i + 1] - row[i]) / h - h * (cc[i + 1] + 2.0 * cc[i]) / 3.0;
+    const double d = (cc[i + 1] - cc[i]) / (3.0 * h);
+    const double dx = xi - lk[i];
+    double val = row[i] + dx * (b + dx * (cc[i] + dx * d));
+    const double dlk = x - xi;
+    if (dlk > 0) val += d1_hi * dlk + 0.5 * d2_hi * dlk * dlk;
+    else if (dlk < 0) val += d1_lo * dlk;
+    return exp(val);
+  };
+  // moments of Delta^2(k) exp(-k^2 R^2): m0 = sigma^2, m1 = d sigma^2 / dR, m2 = d2 sigma^2 / dR2
+  auto moments = [&](double R, double& m0, double& m1, double& m2) {
+    const double lnkmax = fmax(lnkmax_t, log(30. / R));
+    const int npanel = (int)(400 * fmax(1.0, (lnkmax - lnkmin) / 25.0));
+    const double step = (lnkmax - lnkmin) / npanel;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int t = threadIdx.x; t < npanel * 16; t += blockDim.x) {
+      const int j = t >> 4, q = t & 15;
+      const double e0 = lnkmin + j * step, e1 = (j == npanel - 1) ? lnkmax : lnkmin + (j + 1) * step;
+      const double mid = 0.5 * (e1 + e0), half = 0.5 * (e1 - e0);
+      const double x = mid + half * GL16_X[q];
+      const double kk = exp(x), k2 = kk * kk;
+      const double base = half * GL16_W[q] * plin(x) * kk * k2 / 2.0 / M_PI / M_PI * exp(-k2 * R * R);
+      a0 += base;
+      a1 += base * (-k2 * 2.0 * R);
+      a2 += base * (-2.0 * k2 + 4.0 * k2 * k2 * R * R);
+    }
+    red[0][threadIdx.x] = a0; red[1][threadIdx.x] = a1; red[2][threadIdx.x] = a2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        red[0][threadIdx.x] += red[0][threadIdx.x + o];
+        red[1][threadIdx.x] += red[1][threadIdx.x + o];
+        red[2][threadIdx.x] += red[2][threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+    m0 = red[0][0]; m1 = red[1][0]; m2 = red[2][0];
+    __syncthreads();
+  };
+  // ---- sigma(R) = 1: bracket in ln R like the reference ([1e-64, 1e16], src/ccl_halofit.c:260),
+  //      then Newton steps on f(ln R) = sigma^2 - 1 (f' = R d sigma^2/dR) kept inside the bracket ----
+  double m0, m1, m2;
+  double lo = log(1e-6), hi = log(1e4);
+  moments(exp(lo), m0, m1, m2);
+  double flo = m0 - 1.0;
+  while (flo < 0 && lo > log(1e-64)) {
+    lo = fmax(lo - log(1e4), log(1e-64));
+    moments(exp(lo), m0, m1, m2);
+    flo = m0 - 1.0;
+  }
+  moments(exp(hi), m0, m1, m2);
+  double fhi = m0 - 1.0;
+  const size_t oidx = (size_t)ic * na + ia;
+  if (!(flo > 0 && fhi < 0)) {
+    if (threadIdx.x == 0) { rsigma_out[oidx] = -1.0; atomicExch(fail, 1); }
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) logpnl[oidx * nk + i] = nan("");
+    return;
+  }
+  double x = 0.5 * (lo + hi);
+  for (int it = 0; it < 200; ++it) {
+    const double R = exp(x);
+    moments(R, m0, m1, m2);
+    const double f = m0 - 1.0;
+    if (f == 0.0) break;
+    if (f > 0) lo = x; else hi = x;
+    double xn = x - f / (R * m1);            // Newton
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    if (fabs(xn - x) <= 1e-14 * fabs(x) + 1e-15 || (hi - lo) <= 2e-14 * fabs(x)) { x = xn; break; }
+    x = xn;
+  }
+  const double R = exp(x);
+  moments(R, m0, m1, m2);
+  const double sigma2 = m0;
+  const double neff = -R / sigma2 * m1 - 3.0;
+  const double ds = (neff + 3.0) / (-R / sigma2);
+  const double Cc = -1.0 * (m2 * R * R / sigma2 + ds * R / sigma2 - ds * ds * R * R / sigma2 / sigma2);
+  if (threadIdx.x == 0) rsigma_out[oidx] = R;
+  // ---- ccl_halofit_power (src/ccl_halofit.c:828-930), f_nu = 0 ----
+  const double a = a_grid[ia];
+  const double hn = h_over_h0(p, a);
+  const double om = (p[P_OC] + p[P_OB]) / (a * a * a) / hn / hn;
+  const double ode = p[P_OL] * pow(a, -3 * (1 + p[P_W0] + p[P_WA])) * exp(3 * p[P_WA] * (a - 1)) / hn / hn;
+  const double weffa = p[P_W0];
+  const double ksigma = 1.0 / R;
+  const double n1 = neff, n2 = n1 * n1, n3 = n2 * n1, n4 = n2 * n2;
+  const double an = pow(10.0, 1.5222 + 2.8553 * n1 + 2.3706 * n2 + 0.9903 * n3 + 0.2250 * n4 - 0.6038 * Cc +
+                                  0.1749 * ode * (1.0 + weffa));
+  const double bn = pow(10.0, -0.5642 + 0.5864 * n1 + 0.5716 * n2 - 1.5474 * Cc + 0.2279 * ode * (1.0 + weffa));
+  const double cn = pow(10.0, 0.3698 + 2.0404 * n1 + 0.8161 * n2 + 0.5869 * Cc);
+  const double gamman = 0.1971 - 0.0843 * n1 + 0.8460 * Cc;
+  const double alphan = fabs(6.0835 + 1.3373 * n1 - 0.1959 * n2 - 5.5274 * Cc);
+  const double betan = 2.0379 - 0.7354 * n1 + 0.3157 * n2 + 1.2490 * n3 + 0.3980 * n4 - 0.1682 * Cc;
+  const double nun = pow(10.0, 5.2105 + 3.6902 * n1);
+  double f1 = 1.0, f2 = 1.0, f3 = 1.0;
+  if (fabs(1.0 - om) > 0.01) {
+    const double f1a = pow(om, -0.0732), f2a = pow(om, -0.1423), f3a = pow(om, 0.0725);
+    const double f1b = pow(om, -0.0307), f2b = pow(om, -0.0585), f3b = pow(om, 0.0743);
+    const double fb = ode / (1.0 - om);
+    f1 = fb * f1b + (1.0 - fb) * f1a;
+    f2 = fb * f2b + (1.0 - fb) * f2a;
+    f3 = fb * f3b + (1.0 - fb) * f3a;
+  }
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+    const double k = exp(lk[i]);
+    const double delta2_norm = k * k * k / 2.0 / M_PI / M_PI;
+    const double PkL = exp(row[i]);
+    const double y = k / ksigma, y2 = y * y;
+    const double fy = y / 4.0 + y2 / 8.0;
+    const double DeltakL = PkL * delta2_norm;
+    const double DeltakQ = DeltakL * pow(1.0 + DeltakL, betan) / (1.0 + alphan * DeltakL) * exp(-fy);
+    const double DeltakHprime = an * pow(y, 3.0 * f1) / (1.0 + bn * pow(y, f2) + pow(cn * f3 * y, 3.0 - gamman));
+    const double DeltakH = DeltakHprime / (1.0 + nun / y2);
+    logpnl[oidx * nk + i] = log((DeltakQ + DeltakH) / delta2_norm);
+  }
+}
+
+void launch_build_halofit(int ncosmo, int nk, const double* d_lk, int na, const double* d_a, const double* d_logplin,
+                          const double* d_params, double* d_logpnl, double* d_rsigma, int* d_fail,
+                          cudaStream_t stream) {
+  if (ncosmo <= 0) return;
+  const size_t smem = sizeof(double) * 4 * (size_t)nk;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(halofit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(ncosmo, na);
+  halofit_kernel<<<grid, 256, smem, stream>>>(nk, d_lk, na, d_a, d_logplin, d_params, d_logpnl, d_rsigma, d_fail);
+}
+
 void launch_build_background(int ncosmo, int na, const double* d_a, const double* d_params, double dchi,
                              double epsrel, int nmax, double a_init, int stride, double* d_E, double* d_chi,
                              int* d_n, double* d_achi_chi, double* d_achi_a, double* d_growth, double* d_fgrowth,

@@ -1427,4 +1427,37 @@ void ccl_b200_build_tracer_kernels(int ncosmo, const double* params, int na, con
   cudaMemcpy(w_l, d + o_wl, nc * nt * nchi * 8, cudaMemcpyDeviceToHost);
 }
 
+void ccl_b200_build_halofit(int ncosmo, const double* params, int nk, const double* lk, int na, const double* a,
+                            const double* logplin, double* logpnl, double* rsigma, int* status) {
+  if (*status) return;
+  if (!use_device(status)) return;
+  if (ncosmo <= 0 || nk < 4 || na < 1) { *status = CCL_B200_ERROR_INCONSISTENT; return; }
+  const size_t nc = (size_t)ncosmo, tab = nc * na * nk * 8;
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += up(bytes); return o; };
+  const size_t o_par = take(nc * CCL_B200_NPAR * 8), o_lk = take((size_t)nk * 8), o_a = take((size_t)na * 8),
+               o_in = take(tab), o_out = take(tab), o_rs = take(nc * na * 8), o_f = take(4);
+  DevBuf buf;
+  if (!buf.reserve(off, status)) return;
+  char* d = buf.p;
+  cudaMemcpy(d + o_par, params, nc * CCL_B200_NPAR * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_lk, lk, (size_t)nk * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_a, a, (size_t)na * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + o_in, logplin, tab, cudaMemcpyHostToDevice);
+  cudaMemset(d + o_f, 0, 4);
+  launch_build_halofit(ncosmo, nk, (double*)(d + o_lk), na, (double*)(d + o_a), (double*)(d + o_in),
+                       (double*)(d + o_par), (double*)(d + o_out), (double*)(d + o_rs), (int*)(d + o_f), 0);
+  if (!cuda_ok(cudaGetLastError(), "halofit builder launch", status)) return;
+  if (!cuda_ok(cudaDeviceSynchronize(), "halofit builder", status)) return;
+  cudaMemcpy(logpnl, d + o_out, tab, cudaMemcpyDeviceToHost);
+  cudaMemcpy(rsigma, d + o_rs, nc * na * 8, cudaMemcpyDeviceToHost);
+  int failed = 0;
+  cudaMemcpy(&failed, d + o_f, 4, cudaMemcpyDeviceToHost);
+  if (failed) {
+    *status = CCL_B200_ERROR_INTEG;
+    set_err("ccl_halofit.c: could not solve for non-linear scale for halofit");
+  }
+}
+
 }  // extern "C"

@@ -207,4 +207,8 @@ void launch_build_tracer_kernels(int ncosmo, int na, const double* d_abg, const 
                                  const double* d_inv_norm, int nchi, double* d_chi_z, double* d_w_nc, double* d_chi_l,
                                  double* d_w_l, cudaStream_t stream);
 
+void launch_build_halofit(int ncosmo, int nk, const double* d_lk, int na, const double* d_a, const double* d_logplin,
+                          const double* d_params, double* d_logpnl, double* d_rsigma, int* d_fail,
+                          cudaStream_t stream);
+
 }  // namespace cclb

@@ -109,3 +109,20 @@ def build_tracer_kernels(cosmologies, background, z, nz_list, mag_bias_list=None
                                               C.byref(st))
     check(st.value)
     return out
+
+
+def build_halofit(cosmologies, linear):
+    """log P_NL tables [nc, na, nk] from the linear tables of build_linear_power (or any stacked log P)."""
+    par = np.ascontiguousarray(pack_params(cosmologies))
+    lk = np.ascontiguousarray(linear["lk"])
+    a = np.ascontiguousarray(linear["a"])
+    lin = np.ascontiguousarray(linear["logp"])
+    nc = par.shape[0]
+    out = np.empty_like(lin)
+    rs = np.empty((nc, a.size))
+    st = C.c_int(0)
+    dp = lambda x: x.ctypes.data_as(_lib._dp)
+    _lib.load().ccl_b200_build_halofit(nc, dp(par), lk.size, dp(lk), a.size, dp(a), dp(lin), dp(out), dp(rs),
+                                       C.byref(st))
+    check(st.value)
+    return dict(lk=lk, a=a, logp=out, rsigma=rs)

@@ -265,6 +265,13 @@ void ccl_b200_build_tracer_kernels(int ncosmo, const double *params, int na, con
                                    const double *sz_arr, const double *inv_norm, int nchi, double *chi_z,
                                    double *w_nc, double *chi_l, double *w_l, int *status);
 
+/* ccl_apply_halofit (src/ccl_power.c:171-232; src/ccl_halofit.c) on the device: log P_NL on the grid of
+ * the linear table logplin[ncosmo][na][nk] (natural log of P, ln k grid lk[nk], scale factors a[na]).
+ * Host outputs: logpnl[ncosmo][na][nk] and the non-linear scales rsigma[ncosmo][na] (Mpc).  *status is
+ * CCL_B200_ERROR_INTEG (and the row NaN) where sigma(R) = 1 has no root in [1e-64, 1e4] Mpc. */
+void ccl_b200_build_halofit(int ncosmo, const double *params, int nk, const double *lk, int na, const double *a,
+                            const double *logplin, double *logpnl, double *rsigma, int *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,3 +79,18 @@ def test_tracer_kernels_match_host_builder():
                 assert np.max(np.abs(dev["chi_l"][i] - ck)) < 1e-7 * ck.max()
                 # same Akima integral and edge term on tables that agree to ~1e-11
                 assert np.max(np.abs(dev["w_l"][i, t] - wk)) < 1e-8 * np.max(np.abs(wk)), (i, t)
+
+
+def test_halofit_matches_host_builder():
+    import ccl_b200 as ccl
+    from ccl_b200 import device_builders as db
+    from ccl_b200.power import halofit_table
+    cos = _cosmologies()[:4]
+    bgd = db.build_background(cos)
+    lin = db.build_linear_power(cos, "eisenstein_hu", bgd)
+    dev = db.build_halofit(cos, lin)
+    for i, c in enumerate(cos):
+        ref, diag = halofit_table(c._params, lin["a"], lin["lk"], lin["logp"][i])
+        assert np.max(np.abs(dev["rsigma"][i] / diag["rsigma"] - 1)) < 1e-9
+        # both integrate the same spline with the same nodes; the roots agree to the solvers' 1e-13
+        assert np.max(np.abs(dev["logp"][i] - ref)) < 1e-8, np.max(np.abs(dev["logp"][i] - ref))
