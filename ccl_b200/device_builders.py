@@ -126,3 +126,43 @@ def build_halofit(cosmologies, linear):
                                        C.byref(st))
     check(st.value)
     return dict(lk=lk, a=a, logp=out, rsigma=rs)
+
+
+def build_3x2pt_stacked(cosmologies, z, lens_nz, source_nz, lens_bias=None, model="eisenstein_hu", halofit=True,
+                        n_chi=256, spline_params=None, gsl_params=None):
+    """Every table of a 3x2pt likelihood batch from cosmological parameters, built on the device.
+
+    `cosmologies`: Cosmology objects (only their parameters are read); `z`: shared redshift grid;
+    `lens_nz` / `source_nz`: n(z) arrays of the NumberCounts (density term, constant bias
+    `lens_bias[i]`, no RSD) and WeakLensing (shear) tracers.  Returns (stk, collections) for
+    LibBatch.set_stacked / PipelinedBatch: the same tables NumberCountsTracer(has_rsd=False, bias=...) and
+    WeakLensingTracer(...) would hand to the C layer (pyccl/tracers.py:831-988), for all cosmologies.
+    """
+    from .parameters import spline_params as sp0
+    sp = spline_params if spline_params is not None else sp0
+    z = np.ascontiguousarray(z, dtype=float)
+    nl, ns = len(lens_nz), len(source_nz)
+    if lens_bias is None:
+        lens_bias = np.ones(nl)
+    bgd = build_background(cosmologies, sp, gsl_params)
+    lin = build_linear_power(cosmologies, model, bgd, sp)
+    pk = build_halofit(cosmologies, lin) if halofit else lin
+    trk = build_tracer_kernels(cosmologies, bgd, z, list(lens_nz) + list(source_nz), None, n_chi)
+    nc = len(cosmologies)
+    from ._hostspline import Akima
+    # chi(A_SPLINE_MIN): chi_max of kernel-less tracers (not used by these tracers, kept for completeness)
+    cmax = np.array([float(Akima(bgd["a"], bgd["chi"][i])(sp["A_SPLINE_MIN"])) for i in range(nc)])
+    nmax = int(bgd["n_achi"].max())
+    stk = dict(count=nc, achi=(bgd["n_achi"], np.ascontiguousarray(bgd["achi_chi"][:, :nmax]),
+                               np.ascontiguousarray(bgd["achi_a"][:, :nmax])),
+               growth=(bgd["a"], bgd["growth"]), chi_max_nokernel=cmax,
+               pk=(pk["lk"], pk["a"], pk["logp"], 1, 2, True), tracers=[])
+    a_rev = np.ascontiguousarray(1. / (1 + z[::-1]))
+    for i in range(nl):   # density term: kernel p(z) H(z), transfer b(a) (pyccl/tracers.py:879-886)
+        stk["tracers"].append(dict(der_bessel=0, der_angles=0, chi=trk["chi_z"], w=np.ascontiguousarray(trk["w_nc"][:, i]),
+                                   a=a_rev, fa=np.full((nc, z.size), float(lens_bias[i]))))
+    for j in range(ns):   # shear: lensing kernel, der_bessel -1, der_angles 2 (pyccl/tracers.py:952-957)
+        stk["tracers"].append(dict(der_bessel=-1, der_angles=2, chi=trk["chi_l"],
+                                   w=np.ascontiguousarray(trk["w_l"][:, nl + j])))
+    collections = [(i, 1) for i in range(nl + ns)]
+    return stk, collections
