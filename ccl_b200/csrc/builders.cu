@@ -741,6 +741,67 @@ void launch_build_halofit(int ncosmo, int nk, const double* d_lk, int na, const 
   halofit_kernel<<<grid, 256, smem, stream>>>(nk, d_lk, na, d_a, d_logplin, d_params, d_logpnl, d_rsigma, d_fail);
 }
 
+// chi_min / chi_max rule of ccl_cl_tracer_t_new (src/ccl_tracers.c:626-666) for device-built kernels, and
+// the end nodes of their abscissae: out[(ic*ntr + it)*4] = {chi_min, chi_max, x[0], x[n-1]}.
+__global__ void tracer_range_kernel(int ncosmo, int ntr, int n, const double* __restrict__ x, int x_per_tracer,
+                                    const double* __restrict__ w, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncosmo * ntr) return;
+  const int ic = t / ntr;
+  const double* xx = x + (size_t)(x_per_tracer ? t : ic) * n;
+  const double* ww = w + (size_t)t * n;
+  double w_max = fabs(ww[0]);
+  for (int i = 0; i < n; ++i)
+    if (fabs(ww[i]) >= w_max) w_max = fabs(ww[i]);
+  w_max *= 5E-4;  // CCL_FRAC_RELEVANT
+  double lo = xx[0], hi = xx[n - 1];
+  for (int i = 0; i < n - 1; ++i)
+    if (fabs(ww[i + 1]) >= w_max) { lo = xx[i]; break; }
+  for (int i = n - 1; i >= 1; --i)
+    if (fabs(ww[i - 1]) >= w_max) { hi = xx[i]; break; }
+  out[(size_t)t * 4 + 0] = lo;
+  out[(size_t)t * 4 + 1] = hi;
+  out[(size_t)t * 4 + 2] = xx[0];
+  out[(size_t)t * 4 + 3] = xx[n - 1];
+}
+
+// chi(a_eval) through the Akima spline of the chi(a) table: chi_max of kernel-less tracers
+__global__ void chi_at_kernel(int ncosmo, int na, const double* __restrict__ a_bg, const double* __restrict__ chi,
+                              double a_eval, double* __restrict__ out) {
+  const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ic >= ncosmo) return;
+  out[ic] = (a_eval == 1.0) ? 0.0 : akima_eval_direct(a_bg, chi + (size_t)ic * na, na, a_eval);
+}
+
+__global__ void log_kernel(int n, const double* __restrict__ x, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = log(x[i]);
+}
+
+__global__ void scale_rows_kernel(int ncosmo, int ntr, int n, double* __restrict__ w, const double* __restrict__ scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)ncosmo * ntr * n) return;
+  w[i] *= scale[(i / n) % ntr];
+}
+
+void launch_scale_rows(int ncosmo, int ntr, int n, double* d_w, const double* d_scale, cudaStream_t stream) {
+  const size_t tot = (size_t)ncosmo * ntr * n;
+  if (tot) scale_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ncosmo, ntr, n, d_w, d_scale);
+}
+
+void launch_tracer_ranges(int ncosmo, int ntr, int n, const double* d_x, int x_per_tracer, const double* d_w,
+                          double* d_out, cudaStream_t stream) {
+  const int tot = ncosmo * ntr;
+  if (tot > 0) tracer_range_kernel<<<(tot + 127) / 128, 128, 0, stream>>>(ncosmo, ntr, n, d_x, x_per_tracer, d_w, d_out);
+}
+void launch_chi_at(int ncosmo, int na, const double* d_abg, const double* d_chi, double a_eval, double* d_out,
+                   cudaStream_t stream) {
+  if (ncosmo > 0) chi_at_kernel<<<(ncosmo + 127) / 128, 128, 0, stream>>>(ncosmo, na, d_abg, d_chi, a_eval, d_out);
+}
+void launch_log(int n, const double* d_x, double* d_out, cudaStream_t stream) {
+  if (n > 0) log_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, d_x, d_out);
+}
+
 void launch_build_background(int ncosmo, int na, const double* d_a, const double* d_params, double dchi,
                              double epsrel, int nmax, double a_init, int stride, double* d_E, double* d_chi,
                              int* d_n, double* d_achi_chi, double* d_achi_a, double* d_growth, double* d_fgrowth,

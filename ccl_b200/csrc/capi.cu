@@ -62,6 +62,9 @@ struct S1Plan {
   size_t x_off = 0, y_off = 0;               // raw region, in doubles
   size_t co_off = 0, lut_off = 0, scr_off = 0;  // derived region, in bytes
   double x0 = 0, xn = 0;
+  // tables built on the device (ccl_b200_tables) are read in place by the preparation kernels
+  const double* x_dev = nullptr;
+  const double* y_dev = nullptr;
 };
 
 struct F2DPlan {
@@ -69,6 +72,7 @@ struct F2DPlan {
   S1Plan fk, fa, gk, ga;
   size_t z_off = 0, tab_off = 0, scr_off = 0;
   int nk = 0, na = 0;
+  const double* z_dev = nullptr;
 };
 
 struct TracerPlan {
@@ -192,6 +196,7 @@ struct TableSet {
   static int lut_size(int n) { return std::min(std::max(n > 1000 ? 2 * n : 4 * n, 64), 1 << 15); }
 
   bool plan_s1(S1Plan& s, int kind, int n, const double* x, const double* y, int* status) {
+    s = S1Plan();
     s.present = true; s.kind = kind; s.n = n;
     s.x_off = raw.put(x, n);
     if (y) s.y_off = raw.put(y, n);
@@ -216,12 +221,52 @@ struct TableSet {
     return true;
   }
 
+  // Same bookkeeping as plan_s1 for a table that already sits in device memory: the host only needs
+  // its size, end nodes and whether its grid is quasi-uniform.
+  void plan_s1_dev(S1Plan& s, int kind, int n, double x0, double xn, int uniform, const double* d_x,
+                   const double* d_y) {
+    s = S1Plan();
+    s.present = true; s.kind = kind; s.n = n; s.x0 = x0; s.xn = xn; s.uniform = uniform;
+    s.x_dev = d_x; s.y_dev = d_y;
+    s.nlut = lut_size(n);
+    s.lut_off = derive(sizeof(int) * s.nlut);
+    if (kind != 2) s.co_off = derive(sizeof(Rec1) * (n - 1));
+    else s.co_off = derive(sizeof(AxisRec) * (n - 1));
+    if (kind == 1) s.scr_off = derive(sizeof(double) * 3 * n);
+  }
+
+  static int quasi_uniform(const double* x, int n) {
+    const double step = (x[n - 1] - x[0]) / (n - 1.);
+    for (int i = 0; i < n; ++i)
+      if (fabs(x[i] - (x[0] + step * i)) > 0.3 * step) return 0;
+    return 1;
+  }
+
+  // set_pk2d_new_from_arrays flags on a device-resident log P(k,a) table with shared grids
+  void plan_psp_dev(F2DPlan& f, int nk, const double* h_lk, const double* d_lk, int na, const double* h_a,
+                    const double* d_a, const double* d_z, int order_lok, int order_hik, int is_log) {
+    memset(&f.flags, 0, sizeof(F2D));
+    F2D& g = f.flags;
+    g.extrap_order_lok = order_lok; g.extrap_order_hik = order_hik;
+    g.extrap_linear_growth = GROWTH_CCL; g.is_log = is_log; g.growth_factor_0 = 0; g.growth_exponent = 2;
+    g.lkmin = h_lk[0]; g.lkmax = h_lk[nk - 1]; g.amin = h_a[0]; g.amax = h_a[na - 1];
+    plan_s1_dev(f.gk, 2, nk, h_lk[0], h_lk[nk - 1], quasi_uniform(h_lk, nk), d_lk, nullptr);
+    plan_s1_dev(f.ga, 2, na, h_a[0], h_a[na - 1], quasi_uniform(h_a, na), d_a, nullptr);
+    f.fk = S1Plan(); f.fa = S1Plan();
+    f.nk = nk; f.na = na;
+    f.z_dev = d_z;
+    f.tab_off = derive(sizeof(double4) * (size_t)nk * na);
+    f.scr_off = derive(sizeof(double) * 2 * (size_t)(nk + na));
+    g.has_fka = 1;
+  }
+
   // ccl_f2d_t_new (src/ccl_f2d.c:92-201)
   bool plan_f2d(F2DPlan& f, int na, const double* a_arr, int nk, const double* lk_arr,
                 const double* fka_arr, const double* fk_arr, const double* fa_arr, int is_factorizable,
                 int extrap_order_lok, int extrap_order_hik, int extrap_linear_growth, int is_fka_log,
                 double growth_factor_0, int growth_exponent, int* status) {
     memset(&f.flags, 0, sizeof(F2D));
+    f.z_dev = nullptr;
     F2D& g = f.flags;
     is_factorizable = is_factorizable || (a_arr == nullptr) || (lk_arr == nullptr) || (fka_arr == nullptr);
     g.is_factorizable = is_factorizable;
@@ -365,8 +410,8 @@ struct TableSet {
   void jobs_s1(const S1Plan& s, char* br, char* bd, std::vector<AkimaJob>& ak, std::vector<CsplineJob>& cs,
                std::vector<LutJob>& lu) {
     if (!s.present) return;
-    const double* x = reinterpret_cast<const double*>(br) + s.x_off;
-    const double* y = reinterpret_cast<const double*>(br) + s.y_off;
+    const double* x = s.x_dev ? s.x_dev : reinterpret_cast<const double*>(br) + s.x_off;
+    const double* y = s.y_dev ? s.y_dev : reinterpret_cast<const double*>(br) + s.y_off;
     if (!s.uniform) lu.push_back(LutJob{x, reinterpret_cast<int*>(bd + s.lut_off), s.n, s.nlut});
     if (s.kind == 0) ak.push_back(AkimaJob{x, y, reinterpret_cast<Rec1*>(bd + s.co_off), s.n});
     else if (s.kind == 1)
@@ -385,9 +430,9 @@ struct TableSet {
     jobs_s1(f.gk, br, bd, ak, cs, lu);
     jobs_s1(f.ga, br, bd, ak, cs, lu);
     if (f.flags.has_fka) {
-      bc.push_back(BicubicJob{reinterpret_cast<const double*>(br) + f.gk.x_off,
-                              reinterpret_cast<const double*>(br) + f.ga.x_off,
-                              reinterpret_cast<const double*>(br) + f.z_off,
+      bc.push_back(BicubicJob{f.gk.x_dev ? f.gk.x_dev : reinterpret_cast<const double*>(br) + f.gk.x_off,
+                              f.ga.x_dev ? f.ga.x_dev : reinterpret_cast<const double*>(br) + f.ga.x_off,
+                              f.z_dev ? f.z_dev : reinterpret_cast<const double*>(br) + f.z_off,
                               reinterpret_cast<double4*>(bd + f.tab_off),
                               reinterpret_cast<double*>(bd + f.scr_off), f.nk, f.na});
       max_nk = std::max(max_nk, f.nk);
@@ -544,6 +589,22 @@ struct ccl_b200_batch {
   cudaStream_t stream = nullptr;  // non-blocking: batches driven from different host threads overlap
   DevBuf out;   // device result buffer of the host-buffer entry (kept across calls)
   DevBuf call;  // per-batch call buffers (colls, pairs, ells, counters, outputs)
+};
+
+struct ccl_b200_tables {
+  int device = 0;
+  int ncosmo = 0, na = 0, stride = 0, nk = 0, na_pk = 0, nz = 0, ntr = 0, nchi = 0;
+  bool has_nl = false;
+  DevBuf buf;
+  double *d_par = nullptr, *d_a = nullptr, *d_E = nullptr, *d_chi = nullptr, *d_gx = nullptr, *d_ga = nullptr,
+         *d_D = nullptr, *d_f = nullptr, *d_g0 = nullptr, *d_k = nullptr, *d_lk = nullptr, *d_apk = nullptr,
+         *d_lin = nullptr, *d_nl = nullptr, *d_s8 = nullptr, *d_rs = nullptr, *d_z = nullptr, *d_nz = nullptr,
+         *d_sz = nullptr, *d_in = nullptr, *d_chiz = nullptr, *d_wnc = nullptr, *d_chil = nullptr,
+         *d_wl = nullptr, *d_rng = nullptr, *d_cmax = nullptr;
+  int *d_nachi = nullptr, *d_fail = nullptr;
+  // host-side metadata the arena planner needs (sizes and end nodes; never the tables themselves)
+  std::vector<double> h_a, h_lk, h_apk, h_chi_amin, h_cmax, h_rng_nc, h_rng_l;
+  std::vector<int> h_nachi;
 };
 
 static void cosmology_rebuild(ccl_b200_cosmology* c, const double* chi, const double* a, int n,
@@ -1458,6 +1519,186 @@ void ccl_b200_build_halofit(int ncosmo, const double* params, int nk, const doub
     *status = CCL_B200_ERROR_INTEG;
     set_err("ccl_halofit.c: could not solve for non-linear scale for halofit");
   }
+}
+
+// ---- device-resident tables ----
+ccl_b200_tables* ccl_b200_tables_build(int ncosmo, const double* params, int na, const double* a_grid, double dchi,
+                                       double root_epsrel, int root_niter, double a_growth_init, int achi_stride,
+                                       double a_spline_min, int model, int halofit, int nk, const double* k_grid,
+                                       const double* lk_grid, int na_pk, const double* a_pk, double k_min,
+                                       double k_max, int nz,
+                                       const double* z, int ntr, const double* nz_arr, const double* sz_arr,
+                                       const double* inv_norm, const double* lens_scale, int nchi, int* status) {
+  if (*status) return nullptr;
+  if (!use_device(status)) return nullptr;
+  if (ncosmo <= 0 || na < 5 || achi_stride < 5 || a_grid[na - 1] != 1.0 || nk < 4 || na_pk < 4 || model < 0 ||
+      model > 2 || (ntr > 0 && (nz < 5 || nchi < 5 || nchi > 256)) || ntr < 0 || ntr > 65535) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200_tables_build: inconsistent arguments");
+    return nullptr;
+  }
+  auto* t = new ccl_b200_tables();
+  t->device = current_device();
+  t->ncosmo = ncosmo; t->na = na; t->stride = achi_stride; t->nk = nk; t->na_pk = na_pk; t->nz = nz; t->ntr = ntr;
+  t->nchi = nchi; t->has_nl = halofit != 0;
+  const size_t nc = (size_t)ncosmo, sna = (size_t)na, sst = (size_t)achi_stride, tab = nc * na_pk * nk, nt = (size_t)ntr;
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += up(bytes); return o; };
+  const size_t o_par = take(nc * CCL_B200_NPAR * 8), o_a = take(sna * 8), o_E = take(nc * sna * 8),
+               o_chi = take(nc * sna * 8), o_n = take(nc * 4), o_gx = take(nc * sst * 8), o_ga = take(nc * sst * 8),
+               o_D = take(nc * sna * 8), o_f = take(nc * sna * 8), o_g0 = take(nc * 8), o_k = take((size_t)nk * 8),
+               o_lk = take((size_t)nk * 8), o_apk = take((size_t)na_pk * 8), o_lin = take(tab * 8),
+               o_nl = take(halofit ? tab * 8 : 8), o_s8 = take(nc * 8), o_rs = take(nc * na_pk * 8), o_fail = take(4),
+               o_z = take((size_t)nz * 8), o_nz = take(nt * nz * 8), o_sz = take(nt * nz * 8), o_in = take(nt * 8),
+               o_cz = take(nc * nz * 8), o_wn = take(nc * nt * nz * 8), o_cl = take(nc * nchi * 8),
+               o_wl = take(nc * nt * nchi * 8), o_rng = take(nc * (nt ? nt : 1) * 4 * 8 * 2), o_cm = take(nc * 8);
+  if (!t->buf.reserve(off, status)) { delete t; return nullptr; }
+  char* d = t->buf.p;
+  auto D = [&](size_t o) { return reinterpret_cast<double*>(d + o); };
+  t->d_par = D(o_par); t->d_a = D(o_a); t->d_E = D(o_E); t->d_chi = D(o_chi); t->d_nachi = (int*)(d + o_n);
+  t->d_gx = D(o_gx); t->d_ga = D(o_ga); t->d_D = D(o_D); t->d_f = D(o_f); t->d_g0 = D(o_g0); t->d_k = D(o_k);
+  t->d_lk = D(o_lk); t->d_apk = D(o_apk); t->d_lin = D(o_lin); t->d_nl = D(o_nl); t->d_s8 = D(o_s8); t->d_rs = D(o_rs);
+  t->d_fail = (int*)(d + o_fail); t->d_z = D(o_z); t->d_nz = D(o_nz); t->d_sz = D(o_sz); t->d_in = D(o_in);
+  t->d_chiz = D(o_cz); t->d_wnc = D(o_wn); t->d_chil = D(o_cl); t->d_wl = D(o_wl); t->d_rng = D(o_rng); t->d_cmax = D(o_cm);
+  cudaStream_t st = 0;
+  cudaMemcpyAsync(t->d_par, params, nc * CCL_B200_NPAR * 8, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(t->d_a, a_grid, sna * 8, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(t->d_k, k_grid, (size_t)nk * 8, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(t->d_apk, a_pk, (size_t)na_pk * 8, cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(t->d_fail, 0, 4, st);
+  cudaMemcpyAsync(t->d_lk, lk_grid, (size_t)nk * 8, cudaMemcpyHostToDevice, st);  // the caller's ln k nodes, verbatim
+  launch_build_background(ncosmo, na, t->d_a, t->d_par, dchi, root_epsrel, root_niter, a_growth_init, achi_stride,
+                          t->d_E, t->d_chi, t->d_nachi, t->d_gx, t->d_ga, t->d_D, t->d_f, t->d_g0, st);
+  launch_chi_at(ncosmo, na, t->d_a, t->d_chi, a_spline_min, t->d_cmax, st);
+  launch_build_linpower(ncosmo, nk, t->d_k, na_pk, t->d_apk, na, t->d_a, t->d_D, t->d_par, model, log10(k_min),
+                        log10(k_max), t->d_lin, t->d_s8, st);
+  if (halofit)
+    launch_build_halofit(ncosmo, nk, t->d_lk, na_pk, t->d_apk, t->d_lin, t->d_par, t->d_nl, t->d_rs, t->d_fail, st);
+  if (ntr > 0) {
+    cudaMemcpyAsync(t->d_z, z, (size_t)nz * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(t->d_nz, nz_arr, nt * nz * 8, cudaMemcpyHostToDevice, st);
+    if (sz_arr) cudaMemcpyAsync(t->d_sz, sz_arr, nt * nz * 8, cudaMemcpyHostToDevice, st);
+    std::vector<double> eff(nt);
+    for (size_t i = 0; i < nt; ++i) eff[i] = inv_norm[i];
+    cudaMemcpy(t->d_in, eff.data(), nt * 8, cudaMemcpyHostToDevice);
+    launch_build_tracer_kernels(ncosmo, na, t->d_a, t->d_chi, t->d_nachi, achi_stride, t->d_gx, t->d_ga, t->d_par, nz,
+                                t->d_z, ntr, t->d_nz, sz_arr ? t->d_sz : nullptr, t->d_in, nchi, t->d_chiz, t->d_wnc,
+                                t->d_chil, t->d_wl, st);
+    if (lens_scale) {
+      // fold the per-distribution factor (e.g. -2 for magnification) into the lensing kernels
+      std::vector<double> sc(lens_scale, lens_scale + nt);
+      double* d_sc = t->d_rng;  // scratch until the ranges are computed
+      cudaMemcpy(d_sc, sc.data(), nt * 8, cudaMemcpyHostToDevice);
+      launch_scale_rows(ncosmo, ntr, nchi, t->d_wl, d_sc, st);
+    }
+    launch_tracer_ranges(ncosmo, ntr, nz, t->d_chiz, 0, t->d_wnc, t->d_rng, st);
+    launch_tracer_ranges(ncosmo, ntr, nchi, t->d_chil, 0, t->d_wl, t->d_rng + nc * nt * 4, st);
+  }
+  if (!cuda_ok(cudaGetLastError(), "table builder launch", status)) { delete t; return nullptr; }
+  if (!cuda_ok(cudaStreamSynchronize(st), "table builders", status)) { delete t; return nullptr; }
+  // host metadata (small): sizes and end nodes
+  t->h_a.assign(a_grid, a_grid + na);
+  t->h_apk.assign(a_pk, a_pk + na_pk);
+  t->h_lk.assign(lk_grid, lk_grid + nk);
+  t->h_nachi.resize(nc);
+  cudaMemcpy(t->h_nachi.data(), t->d_nachi, nc * 4, cudaMemcpyDeviceToHost);
+  t->h_chi_amin.resize(nc);
+  cudaMemcpy2D(t->h_chi_amin.data(), 8, t->d_chi, sna * 8, 8, nc, cudaMemcpyDeviceToHost);  // chi(a_grid[0])
+  t->h_cmax.resize(nc);
+  cudaMemcpy(t->h_cmax.data(), t->d_cmax, nc * 8, cudaMemcpyDeviceToHost);
+  if (ntr > 0) {
+    t->h_rng_nc.resize(nc * nt * 4);
+    t->h_rng_l.resize(nc * nt * 4);
+    cudaMemcpy(t->h_rng_nc.data(), t->d_rng, nc * nt * 4 * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(t->h_rng_l.data(), t->d_rng + nc * nt * 4, nc * nt * 4 * 8, cudaMemcpyDeviceToHost);
+  }
+  int failed = 0;
+  cudaMemcpy(&failed, t->d_fail, 4, cudaMemcpyDeviceToHost);
+  for (size_t i = 0; i < nc; ++i)
+    if (t->h_nachi[i] < 5) {
+      *status = CCL_B200_ERROR_MEMORY;
+      set_err("ccl_b200_tables_build: cosmology %zu needs %d a(chi) nodes, stride is %d", i, -t->h_nachi[i], achi_stride);
+      delete t;
+      return nullptr;
+    }
+  if (failed) {
+    *status = CCL_B200_ERROR_INTEG;
+    set_err("ccl_halofit.c: could not solve for non-linear scale for halofit");
+    delete t;
+    return nullptr;
+  }
+  return t;
+}
+
+void ccl_b200_tables_free(ccl_b200_tables* t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  delete t;
+}
+
+void ccl_b200_batch_set_from_tables(ccl_b200_batch* b, int first, const ccl_b200_tables* t, int order_lok,
+                                    int order_hik, int use_linear, int* status) {
+  if (*status) return;
+  if (!b || !t || first < 0 || first + t->ncosmo > (int)b->ts.cosmos.size() || b->ts.device != t->device) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200_batch_set_from_tables: slot range or device mismatch");
+    return;
+  }
+  const double* pk = (t->has_nl && !use_linear) ? t->d_nl : t->d_lin;
+  const int gu = TableSet::quasi_uniform(t->h_a.data(), t->na);
+  for (int i = 0; i < t->ncosmo; ++i) {
+    CosmoPlan& p = b->ts.cosmos[first + i];
+    const size_t si = (size_t)i;
+    // a(chi): uniform grid from chi(a = 1) = 0 to chi(a_min)
+    b->ts.plan_s1_dev(p.achi, 0, t->h_nachi[i], 0.0, t->h_chi_amin[i], 1, t->d_gx + si * t->stride, t->d_ga + si * t->stride);
+    b->ts.plan_s1_dev(p.growth, 0, t->na, t->h_a[0], t->h_a[t->na - 1], gu, t->d_a, t->d_D + si * t->na);
+    p.chi_max_nokernel = t->h_cmax[i];
+    b->ts.plan_psp_dev(p.psp, t->nk, t->h_lk.data(), t->d_lk, t->na_pk, t->h_apk.data(), t->d_apk,
+                       pk + si * t->na_pk * t->nk, order_lok, order_hik, 1);
+    p.has_psp = true;
+  }
+  b->ts.committed = false;
+}
+
+int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch* b, int first, const ccl_b200_tables* t, int kind, int itr,
+                                          int der_bessel, int der_angles, int na_ka, const double* a_ka,
+                                          const double* fa_arr, int* status) {
+  if (*status) return -1;
+  if (!b || !t || first < 0 || first + t->ncosmo > (int)b->ts.cosmos.size() || itr < 0 || itr >= t->ntr ||
+      (kind != 0 && kind != 1) || der_angles < 0 || der_angles > 2 || der_bessel < -1 || der_bessel > 2) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200_batch_add_tracer_from_tables: inconsistent arguments");
+    return -1;
+  }
+  const int n = kind ? t->nchi : t->nz;
+  const std::vector<double>& rng = kind ? t->h_rng_l : t->h_rng_nc;
+  int idx = -1;
+  b->ts.raw.defer = true;
+  for (int i = 0; i < t->ncosmo && !*status; ++i) {
+    CosmoPlan& p = b->ts.cosmos[first + i];
+    const size_t si = (size_t)i, ti = si * t->ntr + itr;
+    TracerPlan tp;
+    tp.der_bessel = der_bessel;
+    tp.der_angles = der_angles;
+    tp.chi_min = rng[ti * 4 + 0];
+    tp.chi_max = rng[ti * 4 + 1];
+    const double* d_x = kind ? t->d_chil + si * n : t->d_chiz + si * n;
+    const double* d_w = (kind ? t->d_wl : t->d_wnc) + ti * n;
+    b->ts.plan_s1_dev(tp.kernel, 0, n, rng[ti * 4 + 2], rng[ti * 4 + 3], 0, d_x, d_w);
+    if (fa_arr != nullptr && a_ka != nullptr) {
+      tp.has_transfer = true;
+      if (!b->ts.plan_f2d(tp.transfer, na_ka, a_ka, 0, nullptr, nullptr, nullptr, fa_arr, 1, 0, 2, GROWTH_CONST, 0, 1.0,
+                          0, status))
+        break;
+    }
+    p.tracers.push_back(tp);
+    idx = (int)p.tracers.size() - 1;
+  }
+  b->ts.raw.defer = false;
+  b->ts.raw.flush();
+  b->ts.committed = false;
+  return *status ? -1 : idx;
 }
 
 }  // extern "C"

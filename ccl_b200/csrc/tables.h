@@ -211,4 +211,12 @@ void launch_build_halofit(int ncosmo, int nk, const double* d_lk, int na, const 
                           const double* d_params, double* d_logpnl, double* d_rsigma, int* d_fail,
                           cudaStream_t stream);
 
+void launch_tracer_ranges(int ncosmo, int ntr, int n, const double* d_x, int x_per_tracer, const double* d_w,
+                          double* d_out, cudaStream_t stream);
+void launch_chi_at(int ncosmo, int na, const double* d_abg, const double* d_chi, double a_eval, double* d_out,
+                   cudaStream_t stream);
+void launch_log(int n, const double* d_x, double* d_out, cudaStream_t stream);
+
+void launch_scale_rows(int ncosmo, int ntr, int n, double* d_w, const double* d_scale, cudaStream_t stream);
+
 }  // namespace cclb

@@ -166,3 +166,91 @@ def build_3x2pt_stacked(cosmologies, z, lens_nz, source_nz, lens_bias=None, mode
                                    w=np.ascontiguousarray(trk["w_l"][:, nl + j])))
     collections = [(i, 1) for i in range(nl + ns)]
     return stk, collections
+
+
+class DeviceTables:
+    """ccl_b200_tables: every table of a batch of cosmologies built and kept in HBM."""
+
+    def __init__(self, cosmologies, z=None, nz_list=(), mag_bias_list=None, lens_scale=None, model="eisenstein_hu",
+                 halofit=True, n_chi=256, spline_params=None, gsl_params=None, achi_stride=8192):
+        from ._hostspline import Akima
+        from .parameters import gsl_params as gp0, spline_params as sp0
+        from .power import pk_grids
+        sp = spline_params if spline_params is not None else sp0
+        gp = gsl_params if gsl_params is not None else gp0
+        par = np.ascontiguousarray(pack_params(cosmologies))
+        a = linlog_spacing(sp["A_SPLINE_MINLOG"], sp["A_SPLINE_MIN"], sp["A_SPLINE_MAX"], sp["A_SPLINE_NLOG"],
+                           sp["A_SPLINE_NA"])
+        k, a_pk = pk_grids(sp)
+        ntr = len(nz_list)
+        dp = lambda x: None if x is None else x.ctypes.data_as(_lib._dp)
+        zz = nzs = szs = inorm = lsc = None
+        if ntr:
+            zz = np.ascontiguousarray(z, dtype=float)
+            nzs = np.ascontiguousarray(np.stack([np.asarray(n, dtype=float) for n in nz_list]))
+            if mag_bias_list is not None:
+                szs = np.ascontiguousarray(np.stack([np.asarray(s_, dtype=float) for s_ in mag_bias_list]))
+            inorm = np.array([1.0 / float(Akima(zz, n).integrate_nodes()) for n in nzs])
+            if lens_scale is not None:
+                lsc = np.ascontiguousarray(lens_scale, dtype=float)
+        self.ncosmo, self.ntr, self.z = par.shape[0], ntr, zz
+        st = C.c_int(0)
+        self.h = _lib.load().ccl_b200_tables_build(
+            self.ncosmo, dp(par), a.size, dp(a), float(sp["DCHI_INTEGRATION"]), float(gp["ROOT_EPSREL"]),
+            int(gp["ROOT_N_ITERATION"]), float(gp["EPS_SCALEFAC_GROWTH"]), int(achi_stride), float(sp["A_SPLINE_MIN"]),
+            _MODELS[model], int(bool(halofit)), k.size, dp(k), dp(np.log(k)), a_pk.size, dp(a_pk), float(sp["K_MIN"]),
+            float(sp["K_MAX"]), 0 if zz is None else zz.size, dp(zz), ntr, dp(nzs), dp(szs), dp(inorm), dp(lsc),
+            int(n_chi), C.byref(st))
+        check(st.value)
+
+    def fill(self, batch, first=0, order_lok=1, order_hik=2, use_linear=False):
+        """a(chi), growth, chi(A_SPLINE_MIN) and P(k,a) of every cosmology into batch slots [first, ...)."""
+        st = C.c_int(0)
+        _lib.load().ccl_b200_batch_set_from_tables(batch.h, int(first), self.h, order_lok, order_hik, int(use_linear),
+                                                   C.byref(st))
+        check(st.value)
+        batch._tables_ref = self   # the tables must outlive the batch's commit
+
+    def add_tracer(self, batch, kind, itr, der_bessel=0, der_angles=0, transfer_a=None, first=0):
+        """One sub-tracer per slot from a device-built kernel: kind 'nc' (p(z) H(z)) or 'lensing'."""
+        a_ka = fa = None
+        if transfer_a is not None:
+            a_ka = np.ascontiguousarray(transfer_a[0], dtype=float)
+            fa = np.ascontiguousarray(transfer_a[1], dtype=float)
+        st = C.c_int(0)
+        dp = lambda x: None if x is None else x.ctypes.data_as(_lib._dp)
+        idx = _lib.load().ccl_b200_batch_add_tracer_from_tables(
+            batch.h, int(first), self.h, {"nc": 0, "lensing": 1}[kind], int(itr), int(der_bessel), int(der_angles),
+            0 if a_ka is None else a_ka.size, dp(a_ka), dp(fa), C.byref(st))
+        check(st.value)
+        return idx
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib._LIB is not None:
+            _lib._LIB.ccl_b200_tables_free(self.h)
+            self.h = None
+
+
+def build_3x2pt_batch(cosmologies, z, lens_nz, source_nz, lens_bias=None, model="eisenstein_hu", halofit=True,
+                      n_chi=256, batch=None):
+    """Parameters -> committed LibBatch with no table ever visiting the host (north-star item 5).
+
+    Same content as build_3x2pt_stacked + LibBatch.set_stacked.  Returns (batch, collections, tables)."""
+    from .lowlevel import LibBatch
+    nl, ns = len(lens_nz), len(source_nz)
+    if lens_bias is None:
+        lens_bias = np.ones(nl)
+    tabs = DeviceTables(cosmologies, z, list(lens_nz) + list(source_nz), model=model, halofit=halofit, n_chi=n_chi)
+    if batch is None:
+        batch = LibBatch(tabs.ncosmo)
+    else:
+        batch.reset()
+    tabs.fill(batch)
+    z = np.asarray(z, dtype=float)
+    a_rev = np.ascontiguousarray(1. / (1 + z[::-1]))
+    for i in range(nl):
+        tabs.add_tracer(batch, "nc", i, 0, 0, transfer_a=(a_rev, np.full(z.size, float(lens_bias[i]))))
+    for j in range(ns):
+        tabs.add_tracer(batch, "lensing", nl + j, -1, 2)
+    batch.commit()
+    return batch, [(i, 1) for i in range(nl + ns)], tabs

@@ -272,6 +272,33 @@ void ccl_b200_build_tracer_kernels(int ncosmo, const double *params, int na, con
 void ccl_b200_build_halofit(int ncosmo, const double *params, int nk, const double *lk, int na, const double *a,
                             const double *logplin, double *logpnl, double *rsigma, int *status);
 
+/* ---- device-resident tables: parameters -> tables -> batch without a host round trip ---- */
+typedef struct ccl_b200_tables ccl_b200_tables;
+/* Runs the four builders above for ncosmo cosmologies and keeps every table in HBM.  Arguments as in the
+ * host-in/out entries; halofit != 0 also builds the non-linear P(k); nz_arr / sz_arr / inv_norm / lens_scale
+ * describe ntr redshift distributions (lens_scale[ntr], may be NULL, multiplies the lensing kernel, e.g.
+ * -2 for a magnification term).  The object must outlive ccl_b200_batch_commit of every batch filled
+ * from it (the preparation kernels read its tables in place). */
+ccl_b200_tables *ccl_b200_tables_build(int ncosmo, const double *params, int na, const double *a_grid,
+                                       double dchi, double root_epsrel, int root_niter, double a_growth_init,
+                                       int achi_stride, double a_spline_min, int model, int halofit, int nk,
+                                       const double *k_grid, const double *lk_grid /* ln k_grid */, int na_pk,
+                                       const double *a_pk, double k_min, double k_max, int nz, const double *z, int ntr, const double *nz_arr,
+                                       const double *sz_arr, const double *inv_norm, const double *lens_scale,
+                                       int nchi, int *status);
+void ccl_b200_tables_free(ccl_b200_tables *t);
+/* Fill batch slots [first, first + ncosmo) with the a(chi) and growth tables, chi(A_SPLINE_MIN) and the
+ * P(k,a) of the tables object (non-linear if built, unless use_linear != 0). */
+void ccl_b200_batch_set_from_tables(ccl_b200_batch *b, int first, const ccl_b200_tables *t, int order_lok,
+                                    int order_hik, int use_linear, int *status);
+/* Add one sub-tracer per slot whose radial kernel is a device-built one: kind 0 = number-counts kernel of
+ * distribution itr (abscissa chi(z)), kind 1 = its lensing kernel.  Optional a-only transfer shared by all
+ * cosmologies (a_ka[na_ka], fa_arr[na_ka]; NULL = none), e.g. a galaxy bias b(a).  Returns the index of
+ * the new sub-tracer (same in every slot) or -1. */
+int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch *b, int first, const ccl_b200_tables *t, int kind,
+                                          int itr, int der_bessel, int der_angles, int na_ka, const double *a_ka,
+                                          const double *fa_arr, int *status);
+
 #ifdef __cplusplus
 }
 #endif
