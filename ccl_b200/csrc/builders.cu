@@ -71,11 +71,15 @@ __global__ void bg_distance_kernel(int na, const double* __restrict__ a_grid, co
 
 // a(chi) on a uniform chi grid of step <= dchi: Newton iterations seeded by the previous node's root
 // and stopped when |da| < epsrel |a| (a_of_chi, src/ccl_background.c:370-410, 498-571).  The chain is
-// sequential by construction; one thread per cosmology.
-__global__ void bg_achi_kernel(int ncosmo, int na, const double* __restrict__ a_grid, const double* __restrict__ params,
-                               const double* __restrict__ chi, double dchi, double epsrel, int nmax, int stride,
-                               int* __restrict__ n_out, double* __restrict__ achi_chi, double* __restrict__ achi_a) {
-  const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+// sequential by construction; a half-warp per cosmology spreads the 12 quadrature nodes of every
+// chi(a) evaluation over its lanes.
+__global__ void __launch_bounds__(128)
+bg_achi_kernel(int ncosmo, int na, const double* __restrict__ a_grid, const double* __restrict__ params,
+               const double* __restrict__ chi, double dchi, double epsrel, int nmax, int stride,
+               int* __restrict__ n_out, double* __restrict__ achi_chi, double* __restrict__ achi_a) {
+  const int sub = threadIdx.x & 15;                                  // lane within the half-warp
+  const int ic = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;       // one cosmology per half-warp
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);              // the half-warp's lanes
   if (ic >= ncosmo) return;
   const double* p = params + (size_t)ic * CCL_B200_NPAR;
   const double* ch = chi + (size_t)ic * na;
@@ -85,18 +89,27 @@ __global__ void bg_achi_kernel(int ncosmo, int na, const double* __restrict__ a_
   const double a0 = a_grid[na - 1], af = a_grid[0];
   int n = (int)((chif - chi0) / dchi);
   if (n > stride) n = -n;  // reported to the host: the caller's stride is too small
-  n_out[ic] = n;
+  if (sub == 0) n_out[ic] = n;
   if (n < 5) return;
   const double dx = (chif - chi0) / (n - 1.);
+  // 12-point panel with one node per lane, summed in node order by lane 0's shuffle chain so that the
+  // value does not depend on the lane layout
+  auto panel = [&](double lo, double hi) -> double {
+    const double mid = 0.5 * (hi + lo), half = 0.5 * (hi - lo);
+    const double term = (sub < 12) ? GL12_W[sub] * chi_integrand(p, mid + half * GL12_X[sub]) : 0.0;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) s += __shfl_sync(hmask, term, q, 16);
+    return half * s;
+  };
   int j = na - 1;  // a_grid[j-1] <= cur < a_grid[j], hunted downwards as chi grows
   auto chi_of = [&](double a) -> double {
-    if (a >= 1.0) return (a > 1.0) ? -chi_panel(p, 1.0, a) : 0.0;
+    if (a >= 1.0) return (a > 1.0) ? -panel(1.0, a) : 0.0;
     while (j > 1 && a < a_grid[j - 1]) --j;
     while (j < na - 1 && a >= a_grid[j]) ++j;
-    return ch[j] + chi_panel(p, a, a_grid[j]);
+    return ch[j] + panel(a, a_grid[j]);
   };
-  gx[0] = chi0;
-  ga[0] = a0;
+  if (sub == 0) { gx[0] = chi0; ga[0] = a0; }
   double cur = a0;
   for (int i = 1; i < n - 1; ++i) {
     const double target = chi0 + dx * i;
@@ -111,11 +124,9 @@ __global__ void bg_achi_kernel(int ncosmo, int na, const double* __restrict__ a_
       df = chi_integrand(p, cur);
       if (fabs(cur - prev) < epsrel * fabs(cur) || cur == prev || it > nmax) break;
     }
-    gx[i] = target;
-    ga[i] = cur;
+    if (sub == 0) { gx[i] = target; ga[i] = cur; }
   }
-  gx[n - 1] = chif;
-  ga[n - 1] = af;
+  if (sub == 0) { gx[n - 1] = chif; ga[n - 1] = af; }
 }
 
 // Linear growth: y0' = y1 / (a^3 E), y1' = 1.5 E a Omega_m(a) y0 from a_i with y0 = a_i, y1 = a_i^3 E(a_i)
@@ -500,7 +511,9 @@ tracer_kernel_builder(int na, const double* __restrict__ a_bg, const double* __r
     // gsl_spline_eval_integ from the node z[i_end] to z[nz-1]: whole intervals of the Akima spline
     double mm2 = slope(i_end - 2), mm1 = slope(i_end - 1), m0 = slope(i_end), mp1 = slope(i_end + 1),
            mp2 = slope(i_end + 2);
-    double y_i = yv(i_end);
+    // integrand values y_i .. y_{i+3}: one new evaluation per interval as the window slides
+    double q0 = yv(i_end), q1 = yv(min(i_end + 1, nz - 1)), q2 = yv(min(i_end + 2, nz - 1)),
+           q3 = yv(min(i_end + 3, nz - 1));
     for (int i = i_end; i <= nz - 2; ++i) {
       const double h = z[i + 1] - z[i];
       const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
@@ -520,11 +533,19 @@ tracer_kernel_builder(int na, const double* __restrict__ a_bg, const double* __r
         d = (b + tL - 2.0 * m0) / (h * h);
       }
       // (x2 - x1) (y + b r12/2 + c (r1^2 + r2^2 + r1 r2)/3 + d r12 (r1^2 + r2^2)/4) with r1 = 0, r2 = h
-      res += h * (y_i + 0.5 * b * h + (1. / 3.) * c * (h * h) + 0.25 * d * h * (h * h));
-      // slide the window
-      y_i = yv(i + 1);
+      res += h * (q0 + 0.5 * b * h + (1. / 3.) * c * (h * h) + 0.25 * d * h * (h * h));
+      // slide: slopes m_{i-1} .. m_{i+3}
       mm2 = mm1; mm1 = m0; m0 = mp1; mp1 = mp2;
-      mp2 = slope(i + 3);
+      const int jn = i + 3;  // index of the new slope
+      if (jn <= nz - 2) {
+        const double ynew = yv(jn + 1);
+        mp2 = (ynew - q3) / (z[jn + 1] - z[jn]);
+        q0 = q1; q1 = q2; q2 = q3; q3 = ynew;
+      } else {
+        if (jn == nz - 1) mp2 = 2.0 * mp1 - m0;        // 2 m_{n-2} - m_{n-3}
+        else if (jn == nz) mp2 = 3.0 * m0 - 2.0 * mm1;  // 3 m_{n-2} - 2 m_{n-3}
+        q0 = q1; q1 = q2; q2 = q3;
+      }
     }
   }
   const double y_end = (i_end < nz) ? yv(i_end) : 0.0;
@@ -558,7 +579,9 @@ void launch_build_tracer_kernels(int ncosmo, int na, const double* d_abg, const 
 // cubic spline is built once, the Gaussian-filtered moments are 16-point Gauss-Legendre sums over
 // ln k spread over the CTA, the root is found by bracketed Newton iterations on ln R.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int HF_GROUP = 10;
+
+__global__ void __launch_bounds__(256, 3)
 halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double* __restrict__ a_grid,
                const double* __restrict__ logplin, const double* __restrict__ params, double* __restrict__ logpnl,
                double* __restrict__ rsigma_out, int* __restrict__ fail) {
@@ -566,11 +589,18 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
   double* lk = sm;
   double* row = lk + nk;
   double* cc = row + nk;
-  double* tmp = cc + nk;
+  double* tmp = cc + nk;   // forward-sweep scratch, then the b coefficients
+  double* dco = tmp + nk;  // d coefficients
   __shared__ double red[3][256];
-  const int ic = blockIdx.x, ia = blockIdx.y;
+  __shared__ double glx[16], glw[16];  // lane-varying node index: shared memory, not the constant cache
+  if (threadIdx.x < 16) { glx[threadIdx.x] = GL16_X[threadIdx.x]; glw[threadIdx.x] = GL16_W[threadIdx.x]; }
+  const int ic = blockIdx.x;
   const double* p = params + (size_t)ic * CCL_B200_NPAR;
+  // a CTA walks HF_GROUP consecutive scale factors; each root search starts from the previous root
+  double x = log(1.0);
+  for (int ia = blockIdx.y * HF_GROUP; ia < min(na, (int)(blockIdx.y + 1) * HF_GROUP); ++ia) {
   const double* src = logplin + ((size_t)ic * na + ia) * nk;
+  __syncthreads();
   for (int i = threadIdx.x; i < nk; i += blockDim.x) {
     lk[i] = lk_grid[i];
     row[i] = src[i];
@@ -593,19 +623,22 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
     for (int i = N - 2; i >= 0; --i) cc[i + 1] -= tmp[i] * cc[i + 2];
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < nk - 1; i += blockDim.x) {  // per-interval b and d (gsl cspline coeff_calc)
+    const double h = lk[i + 1] - lk[i];
+    tmp[i] = (row[i + 1] - row[i]) / h - h * (cc[i + 1] + 2.0 * cc[i]) / 3.0;
+    dco[i] = (cc[i + 1] - cc[i]) / (3.0 * h);
+  }
+  __syncthreads();
   const double lnkmin = lk[0], lnkmax_t = lk[nk - 1];
   const double inv_dlk = (nk - 1) / (lnkmax_t - lnkmin);
   // edge derivatives for the ln k extrapolation of ccl_f2d_t_eval (order 1 below, order 2 above)
   double d1_lo, d1_hi, d2_hi;
   {
-    const double h0 = lk[1] - lk[0];
-    d1_lo = (row[1] - row[0]) / h0 - h0 * (cc[1] + 2.0 * cc[0]) / 3.0;
+    d1_lo = tmp[0];
     const int i = nk - 2;
     const double h = lk[i + 1] - lk[i];
-    const double b = (row[i + 1] - row[i]) / h - h * (cc[i + 1] + 2.0 * cc[i]) / 3.0;
-    const double d = (cc[i + 1] - cc[i]) / (3.0 * h);
-    d1_hi = b + h * (2.0 * cc[i] + 3.0 * d * h);
-    d2_hi = 2.0 * cc[i] + 6.0 * d * h;
+    d1_hi = tmp[i] + h * (2.0 * cc[i] + 3.0 * dco[i] * h);
+    d2_hi = 2.0 * cc[i] + 6.0 * dco[i] * h;
   }
   auto plin = [&](double x) -> double {
     const double xi = fmin(fmax(x, lnkmin), lnkmax_t);
@@ -613,11 +646,8 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
     i = min(max(i, 0), nk - 2);
     while (i > 0 && xi < lk[i]) --i;
     while (i < nk - 2 && xi >= lk[i + 1]) ++i;
-    const double h = lk[i + 1] - lk[i];
-    const double b = (row[i + 1] - row[i]) / h - h * (cc[i + 1] + 2.0 * cc[i]) / 3.0;
-    const double d = (cc[i + 1] - cc[i]) / (3.0 * h);
     const double dx = xi - lk[i];
-    double val = row[i] + dx * (b + dx * (cc[i] + dx * d));
+    double val = row[i] + dx * (tmp[i] + dx * (cc[i] + dx * dco[i]));
     const double dlk = x - xi;
     if (dlk > 0) val += d1_hi * dlk + 0.5 * d2_hi * dlk * dlk;
     else if (dlk < 0) val += d1_lo * dlk;
@@ -633,9 +663,9 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
       const int j = t >> 4, q = t & 15;
       const double e0 = lnkmin + j * step, e1 = (j == npanel - 1) ? lnkmax : lnkmin + (j + 1) * step;
       const double mid = 0.5 * (e1 + e0), half = 0.5 * (e1 - e0);
-      const double x = mid + half * GL16_X[q];
+      const double x = mid + half * glx[q];
       const double kk = exp(x), k2 = kk * kk;
-      const double base = half * GL16_W[q] * plin(x) * kk * k2 / 2.0 / M_PI / M_PI * exp(-k2 * R * R);
+      const double base = half * glw[q] * plin(x) * kk * k2 * (0.5 / (M_PI * M_PI)) * exp(-k2 * R * R);
       a0 += base;
       a1 += base * (-k2 * 2.0 * R);
       a2 += base * (-2.0 * k2 + 4.0 * k2 * k2 * R * R);
@@ -653,39 +683,44 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
     m0 = red[0][0]; m1 = red[1][0]; m2 = red[2][0];
     __syncthreads();
   };
-  // ---- sigma(R) = 1: bracket in ln R like the reference ([1e-64, 1e16], src/ccl_halofit.c:260),
-  //      then Newton steps on f(ln R) = sigma^2 - 1 (f' = R d sigma^2/dR) kept inside the bracket ----
-  double m0, m1, m2;
-  double lo = log(1e-6), hi = log(1e4);
-  moments(exp(lo), m0, m1, m2);
-  double flo = m0 - 1.0;
-  while (flo < 0 && lo > log(1e-64)) {
-    lo = fmax(lo - log(1e4), log(1e-64));
-    moments(exp(lo), m0, m1, m2);
-    flo = m0 - 1.0;
-  }
-  moments(exp(hi), m0, m1, m2);
-  double fhi = m0 - 1.0;
+  // ---- sigma(R) = 1 (get_rsigma, src/ccl_halofit.c:259-315, root searched in [1e-64, 1e16] Mpc there):
+  //      Newton steps on ln sigma^2 as a function of ln R (slope -(n_eff + 3), nearly constant), kept
+  //      inside the bracket found so far; bisection whenever a step leaves it.  The moments of the last
+  //      evaluation are the ones at the returned R. ----
+  double m0 = 0, m1 = 0, m2 = 0;
+  const double X_MIN = log(1e-64), X_MAX = log(1e4);
+  double lo = X_MIN, hi = X_MAX;      // sigma^2 > 1 at lo, < 1 at hi once seen
+  bool have_lo = false, have_hi = false;
   const size_t oidx = (size_t)ic * na + ia;
-  if (!(flo > 0 && fhi < 0)) {
-    if (threadIdx.x == 0) { rsigma_out[oidx] = -1.0; atomicExch(fail, 1); }
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) logpnl[oidx * nk + i] = nan("");
-    return;
-  }
-  double x = 0.5 * (lo + hi);
+  bool ok = false;
   for (int it = 0; it < 200; ++it) {
     const double R = exp(x);
     moments(R, m0, m1, m2);
-    const double f = m0 - 1.0;
-    if (f == 0.0) break;
-    if (f > 0) lo = x; else hi = x;
-    double xn = x - f / (R * m1);            // Newton
-    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-    if (fabs(xn - x) <= 1e-14 * fabs(x) + 1e-15 || (hi - lo) <= 2e-14 * fabs(x)) { x = xn; break; }
+    const double f = log(m0);
+    if (f > 0) { lo = x; have_lo = true; } else if (f < 0) { hi = x; have_hi = true; }
+    if (f == 0.0) { ok = true; break; }
+    double step = -f / (R * m1 / m0);                     // Newton on ln sigma^2
+    if (!(fabs(step) <= 8.0)) step = (f > 0) ? 8.0 : -8.0;   // also catches NaN / zero slope
+    double xn = x + step;
+    if (have_lo && have_hi) {
+      if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    } else if (xn < X_MIN || xn > X_MAX) {
+      xn = fmin(fmax(xn, X_MIN), X_MAX);
+      if (xn == x) break;  // pinned at an end of the search range: no root
+    }
+    if (fabs(xn - x) <= 1e-13 * (1.0 + fabs(x)) || (have_lo && have_hi && (hi - lo) <= 1e-13 * (1.0 + fabs(x)))) {
+      ok = true;  // the step is below the resolution of R: keep this evaluation's moments
+      break;
+    }
     x = xn;
   }
+  if (!ok) {
+    if (threadIdx.x == 0) { rsigma_out[oidx] = -1.0; atomicExch(fail, 1); }
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) logpnl[oidx * nk + i] = nan("");
+    x = log(1.0);
+    continue;
+  }
   const double R = exp(x);
-  moments(R, m0, m1, m2);
   const double sigma2 = m0;
   const double neff = -R / sigma2 * m1 - 3.0;
   const double ds = (neff + 3.0) / (-R / sigma2);
@@ -728,16 +763,17 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
     const double DeltakH = DeltakHprime / (1.0 + nun / y2);
     logpnl[oidx * nk + i] = log((DeltakQ + DeltakH) / delta2_norm);
   }
+  }  // scale factors of the group
 }
 
 void launch_build_halofit(int ncosmo, int nk, const double* d_lk, int na, const double* d_a, const double* d_logplin,
                           const double* d_params, double* d_logpnl, double* d_rsigma, int* d_fail,
                           cudaStream_t stream) {
   if (ncosmo <= 0) return;
-  const size_t smem = sizeof(double) * 4 * (size_t)nk;
-  if (smem > 48 * 1024)
+  const size_t smem = sizeof(double) * 5 * (size_t)nk;
+  if (smem + (3 * 256 + 32) * sizeof(double) > 48 * 1024)  // dynamic + the static buffers
     cudaFuncSetAttribute(halofit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid(ncosmo, na);
+  dim3 grid(ncosmo, (na + HF_GROUP - 1) / HF_GROUP);
   halofit_kernel<<<grid, 256, smem, stream>>>(nk, d_lk, na, d_a, d_logplin, d_params, d_logpnl, d_rsigma, d_fail);
 }
 
@@ -808,7 +844,7 @@ void launch_build_background(int ncosmo, int na, const double* d_a, const double
                              double* d_growth0, cudaStream_t stream) {
   if (ncosmo <= 0) return;
   bg_distance_kernel<<<ncosmo, 128, sizeof(double) * na, stream>>>(na, d_a, d_params, d_E, d_chi);
-  bg_achi_kernel<<<(ncosmo + 31) / 32, 32, 0, stream>>>(ncosmo, na, d_a, d_params, d_chi, dchi, epsrel, nmax, stride,
+  bg_achi_kernel<<<(ncosmo * 16 + 127) / 128, 128, 0, stream>>>(ncosmo, na, d_a, d_params, d_chi, dchi, epsrel, nmax, stride,
                                                          d_n, d_achi_chi, d_achi_a);
   bg_growth_kernel<<<(ncosmo + 31) / 32, 32, 0, stream>>>(ncosmo, na, d_a, d_params, a_init, 2.0e-3, d_growth,
                                                            d_fgrowth, d_growth0);
