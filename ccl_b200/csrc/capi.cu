@@ -65,6 +65,7 @@ struct S1Plan {
   // tables built on the device (ccl_b200_tables) are read in place by the preparation kernels
   const double* x_dev = nullptr;
   const double* y_dev = nullptr;
+  int check_id = -1;  // stacked setters: node checks deferred to TableSet::run_checks (host threads)
 };
 
 struct F2DPlan {
@@ -193,6 +194,62 @@ struct TableSet {
     return off;
   }
 
+  // deferred node checks of the stacked setters (strictly increasing nodes; quasi-uniform grid)
+  struct NodeCheck { size_t x_off; int n; int uniform; int ok; };
+  std::vector<NodeCheck> checks;
+  size_t checks_done = 0;
+
+  void run_checks() {
+    const size_t lo = checks_done, hi = checks.size();
+    if (hi == lo) return;
+    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (hi - lo < 64) nt = 1;
+    auto work = [&](unsigned t) {
+      for (size_t c = lo + t; c < hi; c += nt) {
+        NodeCheck& k = checks[c];
+        const double* x = raw.p + k.x_off;
+        k.ok = 1;
+        for (int i = 1; i < k.n; ++i)
+          if (!(x[i] > x[i - 1])) { k.ok = 0; break; }
+        k.uniform = k.ok ? quasi_uniform(x, k.n) : 0;
+      }
+    };
+    if (nt == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+      for (auto& x : th) x.join();
+    }
+    checks_done = hi;
+  }
+
+  bool resolve(S1Plan& s, int* status) {
+    if (!s.present || s.check_id < 0) return true;
+    const NodeCheck& k = checks[s.check_id];
+    s.check_id = -1;
+    if (!k.ok) {
+      set_err("ccl_b200: spline nodes must be strictly increasing");
+      *status = CCL_B200_ERROR_SPLINE;
+      return false;
+    }
+    s.uniform = k.uniform;
+    return true;
+  }
+  bool resolve_f2d(F2DPlan& f, int* status) {
+    return resolve(f.fk, status) && resolve(f.fa, status) && resolve(f.gk, status) && resolve(f.ga, status);
+  }
+  bool resolve_all(int* status) {
+    for (CosmoPlan& c : cosmos) {
+      if (!resolve(c.achi, status) || !resolve(c.growth, status)) return false;
+      if (c.has_psp && !resolve_f2d(c.psp, status)) return false;
+      for (TracerPlan& t : c.tracers) {
+        if (!resolve(t.kernel, status)) return false;
+        if (t.has_transfer && !resolve_f2d(t.transfer, status)) return false;
+      }
+    }
+    return true;
+  }
+
   static int lut_size(int n) { return std::min(std::max(n > 1000 ? 2 * n : 4 * n, 64), 1 << 15); }
 
   bool plan_s1(S1Plan& s, int kind, int n, const double* x, const double* y, int* status) {
@@ -202,17 +259,20 @@ struct TableSet {
     if (y) s.y_off = raw.put(y, n);
     if (s.x_off == (size_t)-1 || s.y_off == (size_t)-1) { *status = CCL_B200_ERROR_MEMORY; return false; }
     s.x0 = x[0]; s.xn = x[n - 1];
-    for (int i = 1; i < n; ++i)
-      if (!(x[i] > x[i - 1])) {  // gsl_spline_init requires strictly increasing x
-        set_err("ccl_b200: spline nodes must be strictly increasing");
-        *status = CCL_B200_ERROR_SPLINE;
-        return false;
-      }
-    // quasi-uniform grid: the analytic index guess is within +-1 interval of the true one
-    const double step = (s.xn - s.x0) / (n - 1.);
-    s.uniform = 1;
-    for (int i = 0; i < n; ++i)
-      if (fabs(x[i] - (s.x0 + step * i)) > 0.3 * step) { s.uniform = 0; break; }
+    if (raw.defer) {
+      // stacked setters: the O(n) node checks run on several host threads after staging
+      s.check_id = (int)checks.size();
+      checks.push_back(NodeCheck{s.x_off, n, 0, 1});
+    } else {
+      for (int i = 1; i < n; ++i)
+        if (!(x[i] > x[i - 1])) {  // gsl_spline_init requires strictly increasing x
+          set_err("ccl_b200: spline nodes must be strictly increasing");
+          *status = CCL_B200_ERROR_SPLINE;
+          return false;
+        }
+      // quasi-uniform grid: the analytic index guess is within +-1 interval of the true one
+      s.uniform = quasi_uniform(x, n);
+    }
     s.nlut = lut_size(n);
     s.lut_off = derive(sizeof(int) * s.nlut);
     if (kind != 2) s.co_off = derive(sizeof(Rec1) * (n - 1));
@@ -368,6 +428,8 @@ struct TableSet {
   void reset() {
     raw.size = 0;
     derived = 0;
+    checks.clear();
+    checks_done = 0;
     for (auto& c : cosmos) c = CosmoPlan();
     committed = false;
   }
@@ -442,6 +504,9 @@ struct TableSet {
 
   bool commit(cudaStream_t stream, int* status) {
     if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice", status)) return false;
+    raw.flush();
+    run_checks();
+    if (!resolve_all(status)) return false;
     raw_bytes = (raw.size * sizeof(double) + 255) / 256 * 256;
     const size_t der_bytes = (derived + 255) / 256 * 256;
     size_t ntr = 0;
@@ -1143,6 +1208,7 @@ void ccl_b200_batch_set_achi_stacked(ccl_b200_batch* b, int first, int count, co
   }
   b->ts.raw.defer = false;
   b->ts.raw.flush();
+  b->ts.run_checks();
   b->ts.committed = false;
 }
 
@@ -1155,6 +1221,7 @@ void ccl_b200_batch_set_growth_stacked(ccl_b200_batch* b, int first, int count, 
     b->ts.plan_s1(b->ts.cosmos[first + i].growth, 0, n, a + (size_t)i * stride_a, growth + (size_t)i * n, status);
   b->ts.raw.defer = false;
   b->ts.raw.flush();
+  b->ts.run_checks();
   b->ts.committed = false;
 }
 
@@ -1175,6 +1242,7 @@ void ccl_b200_batch_set_pk2d_stacked(ccl_b200_batch* b, int first, int count, co
   }
   b->ts.raw.defer = false;
   b->ts.raw.flush();
+  b->ts.run_checks();
   b->ts.committed = false;
 }
 
@@ -1207,6 +1275,7 @@ int ccl_b200_batch_add_tracer_stacked(ccl_b200_batch* b, int first, int count, i
   }
   b->ts.raw.defer = false;
   b->ts.raw.flush();
+  b->ts.run_checks();
   b->ts.committed = false;
   return *status ? -1 : idx;
 }
@@ -1697,6 +1766,7 @@ int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch* b, int first, const cc
   }
   b->ts.raw.defer = false;
   b->ts.raw.flush();
+  b->ts.run_checks();
   b->ts.committed = false;
   return *status ? -1 : idx;
 }
