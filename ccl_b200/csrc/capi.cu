@@ -474,7 +474,8 @@ struct TableSet {
     if (!s.present) return;
     const double* x = s.x_dev ? s.x_dev : reinterpret_cast<const double*>(br) + s.x_off;
     const double* y = s.y_dev ? s.y_dev : reinterpret_cast<const double*>(br) + s.y_off;
-    if (!s.uniform) lu.push_back(LutJob{x, reinterpret_cast<int*>(bd + s.lut_off), s.n, s.nlut});
+    // the LUT is built for every grid: the fast kernel indexes tracer splines through it only
+    lu.push_back(LutJob{x, reinterpret_cast<int*>(bd + s.lut_off), s.n, s.nlut});
     if (s.kind == 0) ak.push_back(AkimaJob{x, y, reinterpret_cast<Rec1*>(bd + s.co_off), s.n});
     else if (s.kind == 1)
       cs.push_back(CsplineJob{x, y, reinterpret_cast<Rec1*>(bd + s.co_off),

@@ -43,12 +43,54 @@ constexpr int LPC = CCLB_LPC;   // ells per CTA (descriptor staging is amortised
 constexpr int NSG = 2 * CCLB_NCG;  // sub-tracers per grid task
 constexpr int GB = 64;          // (ell, grid) tasks whose limits are precomputed per CTA pass
 
-struct FastTr {
-  Spline1D kernel;
-  Spline1D fa;
+// Compact lookup descriptor of one 1-D spline, laid out so that a lookup reads it with three 16-byte
+// shared-memory loads: {x0, xn}, {inv_bin, rec}, {lut, nlut - 1, n - 2}.
+struct __align__(16) FastS1 {
+  double x0, xn;
+  double inv_bin;
+  const Rec1* rec;
+  const int* lut;
+  int nlutm1, last;
+};
+
+struct __align__(16) FastTr {
+  FastS1 kernel;
+  FastS1 fa;
   double pref[LPC];  // f_ell (/(l+1/2)^2 when der_bessel == -1) for each ell of this CTA
   int has_fa, der_bessel;
+  int pad[2];
 };
+
+__device__ __forceinline__ FastS1 pack_s1(const Spline1D& s) {
+  FastS1 f;
+  f.x0 = s.x0; f.xn = s.xn; f.inv_bin = s.inv_bin; f.rec = s.rec; f.lut = s.lut; f.nlutm1 = s.nlut - 1; f.last = s.n - 2;
+  return f;
+}
+
+// find_rec through the LUT only (built for every grid): the entry is the interval of a point just
+// left of the bin, so the walk goes right only.
+__device__ __forceinline__ Rec1 find_rec_lut(const FastS1& s, double v) {
+  int j = (int)((v - s.x0) * s.inv_bin);
+  j = min(max(j, 0), s.nlutm1);
+  int i = __ldg(s.lut + j);
+  const int last = s.last;
+  Rec1 r = load_rec(s.rec + i);
+  int steps = 0;
+  while (v >= r.x1 && i < last) {
+    if (++steps > 4) {  // strongly non-uniform grid: finish by bisection on the interval starts
+      int lo = i, hi = last + 1;
+      while (hi > lo + 1) {
+        const int m = (hi + lo) >> 1;
+        if (__ldg(&s.rec[m].x0) > v) hi = m; else lo = m;
+      }
+      i = lo;
+      r = load_rec(s.rec + i);
+      break;
+    }
+    r = load_rec(s.rec + (++i));
+  }
+  return r;
+}
 
 // ln k limits and node spacing of one (ell, grid) task (get_k_interval + ccl_linear_spacing)
 struct GridPar {
@@ -65,8 +107,9 @@ struct FastCta {
   int next_task, pad;
 };
 
+__host__ __device__ inline size_t fast_tr_offset() { return (sizeof(FastCta) + 15) & ~size_t(15); }
 __host__ __device__ inline size_t fast_warp_offset(int ntr_max) {
-  return (sizeof(FastCta) + (size_t)ntr_max * sizeof(FastTr) + 15) & ~size_t(15);
+  return (fast_tr_offset() + (size_t)ntr_max * sizeof(FastTr) + 15) & ~size_t(15);
 }
 
 // sub-tracer list entry of a grid task: tracer index | collection slot << 8 | first << 16 | last << 17
@@ -271,7 +314,7 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   FastCta& S = *reinterpret_cast<FastCta*>(smraw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  FastTr* const s_tr = reinterpret_cast<FastTr*>(smraw + sizeof(FastCta));
+  FastTr* const s_tr = reinterpret_cast<FastTr*>(smraw + fast_tr_offset());
   FastWarp& W = reinterpret_cast<FastWarp*>(smraw + fast_warp_offset(G.ntr_max))[warp];
   const int nlt = (P.nl + LPC - 1) / LPC;
   const int il0 = (blockIdx.x % nlt) * LPC;
@@ -282,8 +325,8 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
   // ---- per-CTA staging of the descriptors this (cosmology, ell tile) needs ----
   for (int t = threadIdx.x; t < cs->ntracers; t += blockDim.x) {
     const Tracer& tr = cs->tracers[t];
-    s_tr[t].kernel = tr.kernel;
-    s_tr[t].fa = tr.transfer.fa;
+    s_tr[t].kernel = pack_s1(tr.kernel);
+    s_tr[t].fa = pack_s1(tr.transfer.fa);
     s_tr[t].has_fa = tr.has_transfer;
     s_tr[t].der_bessel = tr.der_bessel;
     for (int ls = 0; ls < nls; ++ls) s_tr[t].pref[ls] = tracer_prefactor(tr, P.ells[il0 + ls]);
@@ -428,10 +471,10 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
             const unsigned ent = W.subs[e];
             const FastTr& tr = s_tr[ent & 0xffu];
             const bool inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
-            double wt = rec_value(find_rec(tr.kernel, chi), chi);  // index clamped inside; dropped if outside
+            double wt = rec_value(find_rec_lut(tr.kernel, chi), chi);  // index clamped inside; dropped if outside
             if (tr.has_fa) {
               const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
-              wt *= rec_value(find_rec(tr.fa, a_ev), a_ev);
+              wt *= rec_value(find_rec_lut(tr.fa, a_ev), a_ev);
             }
             double val = inside ? wt * tr.pref[ls] : 0.0;
             if (RSD && tr.der_bessel >= 1) {
@@ -439,10 +482,10 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
               const double l = lp1h - 0.5, lp3h = lp1h + 1.0;
               const double w_t = inside ? wt : 0.0;
               const bool inside_p = (chi_lp > tr.kernel.x0) && (chi_lp < tr.kernel.xn);
-              double wt_p = rec_value(find_rec(tr.kernel, chi_lp), chi_lp);
+              double wt_p = rec_value(find_rec_lut(tr.kernel, chi_lp), chi_lp);
               if (tr.has_fa) {
                 const double a_ev = fmin(fmax(a_lp, tr.fa.x0), tr.fa.xn);
-                wt_p *= rec_value(find_rec(tr.fa, a_ev), a_ev);
+                wt_p *= rec_value(find_rec_lut(tr.fa, a_ev), a_ev);
               }
               if (!inside_p) wt_p = 0.0;
               double dd;
