@@ -16,4 +16,34 @@ from .pk2d import Pk2D, parse_pk2d  # noqa: F401,E402
 from .tracers import (CMBLensingTracer, ISWTracer, NumberCountsTracer, NzTracer, Tracer,  # noqa: F401,E402
                       WeakLensingTracer, get_density_kernel, get_kappa_kernel, get_lensing_kernel)
 
+
+
+def linear_matter_power(cosmo, k, a):
+    return cosmo.linear_matter_power(k, a)
+
+
+def nonlin_matter_power(cosmo, k, a):
+    return cosmo.nonlin_matter_power(k, a)
+
+
+def comoving_radial_distance(cosmo, a):
+    return cosmo.comoving_radial_distance(a)
+
+
+def scale_factor_of_chi(cosmo, chi):
+    return cosmo.scale_factor_of_chi(chi)
+
+
+def growth_factor(cosmo, a):
+    return cosmo.growth_factor(a)
+
+
+def growth_rate(cosmo, a):
+    return cosmo.growth_rate(a)
+
+
+def h_over_h0(cosmo, a):
+    return cosmo.h_over_h0(a)
+
+
 __version__ = "0.1.0"

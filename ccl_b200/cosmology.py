@@ -242,6 +242,14 @@ class Cosmology:
         out = self._splines["f"](np.asarray(a, dtype=float))
         return out if out.ndim else float(out)
 
+    def linear_matter_power(self, k, a):
+        """pyccl.linear_matter_power (pyccl/power.py): evaluated on the device."""
+        return self.get_linear_power()(k, a, self)
+
+    def nonlin_matter_power(self, k, a):
+        """pyccl.nonlin_matter_power (pyccl/power.py): evaluated on the device."""
+        return self.get_nonlin_power()(k, a, self)
+
     def sigma8(self, p_of_k_a=DEFAULT_POWER_SPECTRUM):
         pk = self.parse_pk2d(p_of_k_a, is_linear=True)
         from .power import sigmaR_from_table
