@@ -30,7 +30,7 @@ namespace {
 #define CCLB_NPG 10
 #endif
 #ifndef CCLB_LPC
-#define CCLB_LPC 4
+#define CCLB_LPC 1
 #endif
 #ifndef CCLB_MINB
 #define CCLB_MINB 3
