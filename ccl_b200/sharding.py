@@ -69,3 +69,33 @@ def gather_blocks(local, sizes, dst=0, group=None):
     if sizes[rank] > 0:
         dist.send(local.contiguous(), dst=dst, group=group)
     return None
+
+
+def interleaved_indices(n, world, rank):
+    """Indices rank::world of an axis of length n: the ell-tile shard of a single-cosmology problem
+    (BASELINE configs[4]); interleaving balances the slowly varying work per ell (nk grows with ell)."""
+    return np.arange(int(rank), int(n), int(world))
+
+
+def gather_interleaved(local, n, dst=0, group=None):
+    """Reassemble an axis-(-1) interleaved shard: local[..., j] holds global index rank + j * world.
+
+    Shards may differ by one element; they are padded to a common length for ONE gather and the
+    padding is dropped on `dst`.  Returns the full [..., n] tensor on `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nmax = (n + world - 1) // world
+    pad = torch.zeros(tuple(local.shape[:-1]) + (nmax,), dtype=local.dtype, device=local.device)
+    pad[..., :local.shape[-1]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = torch.empty(tuple(local.shape[:-1]) + (n,), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        idx = interleaved_indices(n, world, r)
+        out[..., idx] = parts[r][..., :idx.size]
+    return out

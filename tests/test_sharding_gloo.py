@@ -72,3 +72,38 @@ def test_balance_tiles_on_nodes():
     assert sorted(np.concatenate(parts).tolist()) == list(range(w.size))
     loads = np.array([w[p].sum() for p in parts])
     assert loads.max() / loads.mean() < 1.01
+
+
+def _worker_ell(rank, world, port, npair, nl, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        idx = sharding.interleaved_indices(nl, world, rank)
+        ip = torch.arange(npair, dtype=torch.float64)[:, None]
+        local = ip * 1e4 + torch.as_tensor(idx, dtype=torch.float64)[None, :]   # stand-in for cl[pair, ell shard]
+        out = sharding.gather_interleaved(local, nl, dst=0)
+        if rank == 0:
+            q.put(out.numpy())
+        else:
+            assert out is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nl", [10, 11])
+def test_gather_by_ell_tile_world2(nl):
+    """Single-cosmology problems (BASELINE configs[4]) shard the ell axis; one gather reassembles it."""
+    world, npair = 2, 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ell, args=(r, world, port, npair, nl, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ip, il = np.meshgrid(np.arange(npair), np.arange(nl), indexing="ij")
+    assert np.array_equal(got, ip * 1e4 + il)
