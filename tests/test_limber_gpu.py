@@ -319,3 +319,46 @@ def test_pipelined_host_entry_equals_single_batch():
     for _ in range(2):                          # arenas are reused from step to step
         c2, s2, st2 = pipe.angular_cl(stk, colls, pairs, ells)
         assert np.array_equal(c1, c2) and np.array_equal(s1, s2) and st1 == st2 == 0
+
+
+def test_batch_fallbacks_to_general_kernel(synth):
+    """(i) a collection with more sub-tracers than a fast-path task holds goes through the redo list;
+    (ii) a table form outside the fast path (2-D k-a transfer) sends the whole batch to the general
+    kernel.  Both must still match the oracle."""
+    import ccl_b200 as cb
+    from ccl_b200 import synthetic as S
+    bg, pk = synth["bg"], synth["pk"]
+    subs0, colls0 = S.lsst_like_tracers(bg, n_lens=2, n_src=2)
+    cmax = chi_max_nokernel(bg)
+    ells = ELLS[::3]
+    # (i) one collection made of 25 copies of a shear kernel scaled by 1/25 each: same C_ell as one
+    big = [dict(subs0[2], w=subs0[2]["w"] / 25.0) for _ in range(25)]
+    subs = subs0 + big
+    colls = colls0 + [(len(subs0), 25)]
+    pairs = [(0, 4), (2, 4), (4, 4), (2, 2), (1, 3)]
+    batch = cb.LibBatch(1)
+    _fill(batch, 0, bg, pk, subs, cmax)
+    batch.commit()
+    cl, stat, st = batch.angular_cl(colls, pairs, ells)
+    assert batch.last_used_fast_path and st == 0
+    ref, _ = _oracle_all(bg, pk, subs, colls, pairs, ells)
+    for q in range(len(pairs)):
+        redo = lambda: _oracle_all(bg, pk, subs, colls, [pairs[q]], ells)[0][0]
+        assert parity_error(cl[0, q], ref[q], redo, SPLINE_RTOL) < SPLINE_RTOL, pairs[q]
+    assert np.max(np.abs(cl[0, 2] / cl[0, 3] - 1)) < 1e-12          # 25 x (w/25) == w
+    # (ii) a k-dependent 2-D transfer on one sub-tracer
+    lk_t = np.linspace(np.log(1e-4), np.log(50.0), 40)
+    a_t = np.linspace(0.2, 1.0, 16)
+    tka = (1.0 + 0.1 * np.tanh(lk_t))[None, :] * (0.5 + a_t)[:, None]
+    subs2 = [dict(s) for s in subs0]
+    subs2[0] = dict(der_bessel=0, der_angles=0, chi=subs0[0]["chi"], w=subs0[0]["w"], a=a_t, lk=lk_t, fka=tka)
+    batch2 = cb.LibBatch(1)
+    _fill(batch2, 0, bg, pk, subs2, cmax)
+    batch2.commit()
+    pairs2 = [(0, 0), (0, 2), (1, 3)]
+    cl2, stat2, st2 = batch2.angular_cl(colls0, pairs2, ells)
+    assert not batch2.last_used_fast_path and st2 == 0
+    ref2, _ = _oracle_all(bg, pk, subs2, colls0, pairs2, ells)
+    for q in range(len(pairs2)):
+        redo = lambda: _oracle_all(bg, pk, subs2, colls0, [pairs2[q]], ells)[0][0]
+        assert parity_error(cl2[0, q], ref2[q], redo, SPLINE_RTOL) < SPLINE_RTOL, pairs2[q]
