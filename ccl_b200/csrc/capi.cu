@@ -82,6 +82,8 @@ struct TracerPlan {
   S1Plan kernel;
   bool has_transfer = false;
   F2DPlan transfer;
+  bool const_transfer = false;  // factorised, a-only, linear, all samples equal
+  double const_transfer_value = 0;
 };
 
 struct CosmoPlan {
@@ -421,6 +423,13 @@ struct TableSet {
       if (!plan_f2d(t.transfer, na_ka, a_ka, nk_ka, lk_ka, fka_arr, fk_arr, fa_arr, is_factorizable,
                     extrap_order_lok, extrap_order_hik, GROWTH_CONST, is_fka_log, 1.0, 0, status))
         return false;
+      const F2D& g = t.transfer.flags;
+      if (g.is_factorizable && !g.has_fk && g.has_fa && !g.is_log && fa_arr != nullptr) {
+        bool same = true;
+        for (int i = 1; i < na_ka && same; ++i) same = (fa_arr[i] == fa_arr[0]);
+        t.const_transfer = same;
+        t.const_transfer_value = fa_arr[0];
+      }
     }
     return true;
   }
@@ -563,6 +572,7 @@ struct TableSet {
         td.der_bessel = t.der_bessel; td.der_angles = t.der_angles;
         td.has_kernel = t.kernel.present; td.has_transfer = t.has_transfer;
         td.chi_min = t.chi_min; td.chi_max = t.chi_max;
+        td.const_transfer = t.const_transfer; td.const_transfer_value = t.const_transfer_value;
         td.kernel = mk_s1(t.kernel, br, bd);
         jobs_s1(t.kernel, br, bd, ak, cs, lu);
         if (t.has_transfer) {
@@ -1761,6 +1771,10 @@ int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch* b, int first, const cc
       if (!b->ts.plan_f2d(tp.transfer, na_ka, a_ka, 0, nullptr, nullptr, nullptr, fa_arr, 1, 0, 2, GROWTH_CONST, 0, 1.0,
                           0, status))
         break;
+      bool same = true;
+      for (int j = 1; j < na_ka && same; ++j) same = (fa_arr[j] == fa_arr[0]);
+      tp.const_transfer = same;
+      tp.const_transfer_value = fa_arr[0];
     }
     p.tracers.push_back(tp);
     idx = (int)p.tracers.size() - 1;

@@ -327,9 +327,13 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
     const Tracer& tr = cs->tracers[t];
     s_tr[t].kernel = pack_s1(tr.kernel);
     s_tr[t].fa = pack_s1(tr.transfer.fa);
-    s_tr[t].has_fa = tr.has_transfer;
+    // a constant a-only transfer is folded into the prefactor: (w * t) * pref == w * (t * pref) up to
+    // one rounding, and its spline evaluates to exactly the constant
+    const bool fold = tr.has_transfer && tr.const_transfer;
+    s_tr[t].has_fa = tr.has_transfer && !fold;
     s_tr[t].der_bessel = tr.der_bessel;
-    for (int ls = 0; ls < nls; ++ls) s_tr[t].pref[ls] = tracer_prefactor(tr, P.ells[il0 + ls]);
+    for (int ls = 0; ls < nls; ++ls)
+      s_tr[t].pref[ls] = tracer_prefactor(tr, P.ells[il0 + ls]) * (fold ? tr.const_transfer_value : 1.0);
   }
   for (int c = threadIdx.x; c < P.ncoll; c += blockDim.x) S.colls[c] = P.colls[c];
   if (threadIdx.x == 32) S.achi = cs->achi;

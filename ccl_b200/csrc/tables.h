@@ -90,6 +90,10 @@ struct F2D {
 struct Tracer {
   int der_bessel, der_angles, has_kernel, has_transfer;
   double chi_min, chi_max;
+  // an a-only transfer whose samples are all equal (a constant galaxy bias) evaluates to exactly that
+  // constant through its natural cubic spline: the fast kernel folds it into the ell prefactor
+  int const_transfer, pad0;
+  double const_transfer_value;
   Spline1D kernel;  // Akima W(chi); value 0 at and outside the end nodes (src/ccl_f1d.c:137-161)
   F2D transfer;
 };
