@@ -191,7 +191,7 @@ struct TableSet {
   unsigned long long last_h2d = 0;
 
   size_t derive(size_t bytes) {
-    size_t off = (derived + 31) / 32 * 32;
+    size_t off = (derived + 63) / 64 * 64;
     derived = off + bytes;
     return off;
   }

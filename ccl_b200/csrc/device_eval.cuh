@@ -17,10 +17,18 @@ __device__ __forceinline__ Rec1 load_rec(const Rec1* p) {
   return r;
 }
 
+// One 32-byte table node with a single 256-bit read-only load (LDG.E.256 on sm_100a); every double4
+// table is carved on a 32-byte boundary (BatchPlan::derive, Arena).
 __device__ __forceinline__ double4 ldg4(const double4* p) {
+#ifdef CCLB_NO_LDG256
   const double2* q = reinterpret_cast<const double2*>(p);
   const double2 a = __ldg(q), b = __ldg(q + 1);
   return make_double4(a.x, a.y, b.x, b.y);
+#else
+  double4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+#endif
 }
 
 // Record of the interval gsl_interp_bsearch(x, v, 0, n-1) would return, for x[0] <= v <= x[n-1].
