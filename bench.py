@@ -237,6 +237,9 @@ def _main(json_out):
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--from-parameters", type=int, default=0, metavar="N",
                     help="also time parameters -> device-built tables -> C_ell for N cosmologies (extra key)")
+    ap.add_argument("--e2e-trace", action="store_true", help="print the per-chunk stage timeline of one e2e step to stderr")
+    ap.add_argument("--e2e-pageable", action="store_true",
+                    help="keep the e2e input tables in pageable host memory (staged through pinned arenas by host threads)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="cosmology chunks of the pipelined host-buffer entry")
     args = ap.parse_args()
 
@@ -366,6 +369,9 @@ def _main(json_out):
 
         parts = {"stage_host_tables_ms": 0.0, "h2d_and_table_prep_ms": 0.0, "limber_and_d2h_ms": 0.0}
         stk = stack_host_tables(tables, nloc, off)              # the caller's host buffers
+        if not args.e2e_pageable:
+            # page-locked, as the contract asks: the library then DMAs straight from these arrays
+            stk = cb.pin_stacked(stk)
         cl_pinned = torch.empty((nloc, npair, nl), dtype=torch.float64, pin_memory=True).numpy()
 
         def serial_step():
@@ -396,6 +402,15 @@ def _main(json_out):
 
         e2e_step()
         sync_all()
+        if args.e2e_trace and rank == 0:
+            pipe.trace = []
+            t_ref = time.perf_counter()
+            e2e_step()
+            for name, c, ta, tb in sorted(pipe.trace, key=lambda r: r[2]):
+                print("e2e-trace %-8s chunk %2d  %8.2f -> %8.2f ms (%6.2f)" % (name, c, (ta - t_ref) * 1e3, (tb - t_ref) * 1e3,
+                                                                         (tb - ta) * 1e3), file=sys.stderr)
+            pipe.trace = None
+            sync_all()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             cl_host, stat_host, _ = e2e_step()
@@ -409,11 +424,13 @@ def _main(json_out):
         d2h = int(cl_host.nbytes + stat_host.nbytes)
         e2e = {"value": n_cl_total / dt, "unit": "C_ell/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": dt * 1e3,
-               "chunks": pipe.nchunks, "serial_breakdown_rank0": dict(parts),
+               "chunks": pipe.nchunks, "host_inputs": "pageable" if args.e2e_pageable else "pinned",
+               "serial_breakdown_rank0": dict(parts),
                "identical_to_resident_path": bool(np.array_equal(cl_host, d_cl.cpu().numpy())),
-               "note": "per step through the host-buffer entry (PipelinedBatch over the C ABI): stacked host tables -> "
-                       "pinned staging arenas (host threads), H2D copies, device table prep, Limber kernels, D2H of "
-                       "all C_ell into pinned memory; the three stages overlap across chunks of cosmologies"}
+               "note": "per step through the host-buffer entry (PipelinedBatch over the C ABI): stacked host tables "
+                       "(pinned: one DMA per stacked array straight from the caller's buffers; pageable: staged "
+                       "into pinned arenas by host threads) -> H2D copies, device table prep, Limber kernels, D2H "
+                       "of all C_ell into pinned memory; the three stages overlap across chunks of cosmologies"}
 
     # ---- optional: the whole likelihood step from cosmological parameters (device-built tables) ----
     from_parameters = None

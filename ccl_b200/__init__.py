@@ -11,7 +11,7 @@ from .cells import angular_cl  # noqa: F401,E402
 from .cosmology import Cosmology, CosmologyCalculator, CosmologyVanillaLCDM  # noqa: F401,E402
 from .errors import CCLError, CCLWarning, update_warning_verbosity  # noqa: F401,E402
 from .parameters import gsl_params, physical_constants, spline_params  # noqa: F401,E402
-from .pipeline import PipelinedBatch  # noqa: F401,E402
+from .pipeline import PipelinedBatch, pin_stacked, slice_stacked  # noqa: F401,E402
 from .pk2d import Pk2D, parse_pk2d  # noqa: F401,E402
 from .tracers import (CMBLensingTracer, ISWTracer, NumberCountsTracer, NzTracer, Tracer,  # noqa: F401,E402
                       WeakLensingTracer, get_density_kernel, get_kappa_kernel, get_lensing_kernel)

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -55,6 +56,8 @@ bool use_device(int* status) {
 constexpr size_t ALIGN_D = 4;  // raw region alignment in doubles (32 B)
 
 // ---- plans: offsets into the arena, turned into device descriptors at commit ----
+constexpr size_t NO_LAND = (size_t)-1;
+
 struct S1Plan {
   bool present = false;
   int kind = 0;  // 0 akima, 1 natural cspline, 2 bicubic axis (nodes + LUT)
@@ -65,6 +68,9 @@ struct S1Plan {
   // tables built on the device (ccl_b200_tables) are read in place by the preparation kernels
   const double* x_dev = nullptr;
   const double* y_dev = nullptr;
+  // stacked setters on pinned host arrays: the whole stacked array is copied by ONE DMA into the
+  // landing region at commit and the table is read there (offset in doubles; NO_LAND = staged)
+  size_t x_land = NO_LAND, y_land = NO_LAND;
   int check_id = -1;  // stacked setters: node checks deferred to TableSet::run_checks (host threads)
 };
 
@@ -74,6 +80,12 @@ struct F2DPlan {
   size_t z_off = 0, tab_off = 0, scr_off = 0;
   int nk = 0, na = 0;
   const double* z_dev = nullptr;
+  size_t z_land = NO_LAND;
+};
+
+// Where the arrays of one stacked-setter slot sit in the landing region (NO_LAND: stage through raw)
+struct Lands {
+  size_t chi = NO_LAND, w = NO_LAND, a = NO_LAND, lk = NO_LAND, fka = NO_LAND, fk = NO_LAND, fa = NO_LAND;
 };
 
 struct TracerPlan {
@@ -179,6 +191,36 @@ struct TableSet {
   std::vector<CosmoPlan> cosmos;
   DevBuf dev;          // [raw | derived | descriptors]
   DevBuf jobs;         // prep job arrays
+  // Landing region: stacked arrays that live in pinned host memory are not staged; commit() copies
+  // each of them with one DMA straight from the caller's buffer (which must stay valid until
+  // commit returns).  Small shared grids are kept in `owned` so that they take the same route.
+  struct DirectCopy { size_t off; const double* src; size_t n; bool done; };
+  DevBuf landing;
+  size_t land_size = 0;  // doubles
+  std::vector<DirectCopy> direct;
+  std::deque<std::vector<double>> owned;
+
+  static bool is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  }
+  size_t land_put(const double* src, size_t n) {
+    const size_t off = (land_size + ALIGN_D - 1) / ALIGN_D * ALIGN_D;
+    direct.push_back(DirectCopy{off, src, n, false});
+    land_size = off + n;
+    return off;
+  }
+  size_t land_put_owned(const double* src, size_t n) {
+    owned.emplace_back(src, src + n);
+    return land_put(owned.back().data(), n);
+  }
+  // landing offset of a stacked array if it is pinned, else NO_LAND
+  size_t land_if_pinned(const double* src, size_t n) {
+    static const bool off = getenv("CCL_B200_NO_DIRECT") != nullptr;
+    return (src && n && !off && is_pinned(src)) ? land_put(src, n) : NO_LAND;
+  }
   size_t raw_bytes = 0, desc_off = 0;
   Cosmo* d_cosmos = nullptr;
   F2D* d_psp = nullptr;
@@ -197,19 +239,22 @@ struct TableSet {
   }
 
   // deferred node checks of the stacked setters (strictly increasing nodes; quasi-uniform grid)
-  struct NodeCheck { size_t x_off; int n; int uniform; int ok; };
+  struct NodeCheck { size_t x_off; const double* xsrc; int n; int uniform; int ok; };
   std::vector<NodeCheck> checks;
   size_t checks_done = 0;
 
   void run_checks() {
     const size_t lo = checks_done, hi = checks.size();
     if (hi == lo) return;
+    size_t nodes = 0;
+    for (size_t c = lo; c < hi; ++c) nodes += (size_t)checks[c].n;
+    // a thread is worth spawning per ~256k nodes (a stacked call on a few hundred slots stays inline)
     unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    if (hi - lo < 64) nt = 1;
+    nt = (unsigned)std::min<size_t>(nt, nodes / (size_t(1) << 18) + 1);
     auto work = [&](unsigned t) {
       for (size_t c = lo + t; c < hi; c += nt) {
         NodeCheck& k = checks[c];
-        const double* x = raw.p + k.x_off;
+        const double* x = k.xsrc ? k.xsrc : raw.p + k.x_off;
         k.ok = 1;
         for (int i = 1; i < k.n; ++i)
           if (!(x[i] > x[i - 1])) { k.ok = 0; break; }
@@ -254,17 +299,22 @@ struct TableSet {
 
   static int lut_size(int n) { return std::min(std::max(n > 1000 ? 2 * n : 4 * n, 64), 1 << 15); }
 
-  bool plan_s1(S1Plan& s, int kind, int n, const double* x, const double* y, int* status) {
+  bool plan_s1(S1Plan& s, int kind, int n, const double* x, const double* y, int* status,
+               size_t x_land = NO_LAND, size_t y_land = NO_LAND) {
     s = S1Plan();
     s.present = true; s.kind = kind; s.n = n;
-    s.x_off = raw.put(x, n);
-    if (y) s.y_off = raw.put(y, n);
+    s.x_land = x_land;
+    if (x_land == NO_LAND) s.x_off = raw.put(x, n);
+    if (y) {
+      s.y_land = y_land;
+      if (y_land == NO_LAND) s.y_off = raw.put(y, n);
+    }
     if (s.x_off == (size_t)-1 || s.y_off == (size_t)-1) { *status = CCL_B200_ERROR_MEMORY; return false; }
     s.x0 = x[0]; s.xn = x[n - 1];
     if (raw.defer) {
       // stacked setters: the O(n) node checks run on several host threads after staging
       s.check_id = (int)checks.size();
-      checks.push_back(NodeCheck{s.x_off, n, 0, 1});
+      checks.push_back(NodeCheck{s.x_off, x_land == NO_LAND ? nullptr : x, n, 0, 1});
     } else {
       for (int i = 1; i < n; ++i)
         if (!(x[i] > x[i - 1])) {  // gsl_spline_init requires strictly increasing x
@@ -326,9 +376,10 @@ struct TableSet {
   bool plan_f2d(F2DPlan& f, int na, const double* a_arr, int nk, const double* lk_arr,
                 const double* fka_arr, const double* fk_arr, const double* fa_arr, int is_factorizable,
                 int extrap_order_lok, int extrap_order_hik, int extrap_linear_growth, int is_fka_log,
-                double growth_factor_0, int growth_exponent, int* status) {
+                double growth_factor_0, int growth_exponent, int* status, const Lands& L = Lands()) {
     memset(&f.flags, 0, sizeof(F2D));
     f.z_dev = nullptr;
+    f.z_land = NO_LAND;
     F2D& g = f.flags;
     is_factorizable = is_factorizable || (a_arr == nullptr) || (lk_arr == nullptr) || (fka_arr == nullptr);
     g.is_factorizable = is_factorizable;
@@ -351,12 +402,12 @@ struct TableSet {
     if (g.is_factorizable) {
       if (!g.is_k_constant) {
         if (nk < 3) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: cspline needs >= 3 nodes"); return false; }
-        if (!plan_s1(f.fk, 1, nk, lk_arr, fk_arr, status)) return false;
+        if (!plan_s1(f.fk, 1, nk, lk_arr, fk_arr, status, L.lk, L.fk)) return false;
         g.has_fk = 1;
       }
       if (!g.is_a_constant) {
         if (na < 3) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: cspline needs >= 3 nodes"); return false; }
-        if (!plan_s1(f.fa, 1, na, a_arr, fa_arr, status)) return false;
+        if (!plan_s1(f.fa, 1, na, a_arr, fa_arr, status, L.a, L.fa)) return false;
         g.has_fa = 1;
       }
     } else if (!(g.is_k_constant || g.is_a_constant)) {
@@ -365,10 +416,11 @@ struct TableSet {
         set_err("ccl_b200: bicubic interpolation needs >= 4 nodes per axis");
         return false;
       }
-      if (!plan_s1(f.gk, 2, nk, lk_arr, nullptr, status)) return false;
-      if (!plan_s1(f.ga, 2, na, a_arr, nullptr, status)) return false;
+      if (!plan_s1(f.gk, 2, nk, lk_arr, nullptr, status, L.lk)) return false;
+      if (!plan_s1(f.ga, 2, na, a_arr, nullptr, status, L.a)) return false;
       f.nk = nk; f.na = na;
-      f.z_off = raw.put(fka_arr, (size_t)nk * na);
+      f.z_land = L.fka;
+      if (L.fka == NO_LAND) f.z_off = raw.put(fka_arr, (size_t)nk * na);
       if (f.z_off == (size_t)-1) { *status = CCL_B200_ERROR_MEMORY; return false; }
       f.tab_off = derive(sizeof(double4) * (size_t)nk * na);
       f.scr_off = derive(sizeof(double) * 2 * (size_t)(nk + na));
@@ -382,7 +434,7 @@ struct TableSet {
                    const double* chi_w, const double* w_w, int na_ka, const double* a_ka, int nk_ka,
                    const double* lk_ka, const double* fka_arr, const double* fk_arr, const double* fa_arr,
                    int is_fka_log, int is_factorizable, int extrap_order_lok, int extrap_order_hik,
-                   int* status) {
+                   int* status, const Lands& L = Lands()) {
     if ((der_angles < 0) || (der_angles > 2)) {
       *status = CCL_B200_ERROR_INCONSISTENT;
       set_err("ccl_tracers.c: ccl_cl_tracer_new(): der_angles must be between 0 and 2\n");
@@ -403,7 +455,7 @@ struct TableSet {
         set_err("ccl_b200: tracer kernel needs >= 5 nodes (akima)");
         return false;
       }
-      if (!plan_s1(t.kernel, 0, n_w, chi_w, w_w, status)) return false;
+      if (!plan_s1(t.kernel, 0, n_w, chi_w, w_w, status, L.chi, L.w)) return false;
       double w_max = fabs(w_w[0]);
       for (int i = 0; i < n_w; ++i)
         if (fabs(w_w[i]) >= w_max) w_max = fabs(w_w[i]);
@@ -421,7 +473,7 @@ struct TableSet {
     if ((fka_arr != nullptr) || (fk_arr != nullptr) || (fa_arr != nullptr)) {
       t.has_transfer = true;
       if (!plan_f2d(t.transfer, na_ka, a_ka, nk_ka, lk_ka, fka_arr, fk_arr, fa_arr, is_factorizable,
-                    extrap_order_lok, extrap_order_hik, GROWTH_CONST, is_fka_log, 1.0, 0, status))
+                    extrap_order_lok, extrap_order_hik, GROWTH_CONST, is_fka_log, 1.0, 0, status, L))
         return false;
       const F2D& g = t.transfer.flags;
       if (g.is_factorizable && !g.has_fk && g.has_fa && !g.is_log && fa_arr != nullptr) {
@@ -437,6 +489,9 @@ struct TableSet {
   void reset() {
     raw.size = 0;
     derived = 0;
+    land_size = 0;
+    direct.clear();
+    owned.clear();
     checks.clear();
     checks_done = 0;
     for (auto& c : cosmos) c = CosmoPlan();
@@ -478,11 +533,19 @@ struct TableSet {
     return d;
   }
 
+  const double* land_base() const { return reinterpret_cast<const double*>(landing.p); }
+  const double* xptr(const S1Plan& s, char* br) const {
+    return s.x_dev ? s.x_dev
+                   : (s.x_land != NO_LAND ? land_base() + s.x_land : reinterpret_cast<const double*>(br) + s.x_off);
+  }
+
   void jobs_s1(const S1Plan& s, char* br, char* bd, std::vector<AkimaJob>& ak, std::vector<CsplineJob>& cs,
                std::vector<LutJob>& lu) {
     if (!s.present) return;
-    const double* x = s.x_dev ? s.x_dev : reinterpret_cast<const double*>(br) + s.x_off;
-    const double* y = s.y_dev ? s.y_dev : reinterpret_cast<const double*>(br) + s.y_off;
+    const double* x = xptr(s, br);
+    const double* y = s.y_dev ? s.y_dev
+                              : (s.y_land != NO_LAND ? land_base() + s.y_land
+                                                     : reinterpret_cast<const double*>(br) + s.y_off);
     // the LUT is built for every grid: the fast kernel indexes tracer splines through it only
     lu.push_back(LutJob{x, reinterpret_cast<int*>(bd + s.lut_off), s.n, s.nlut});
     if (s.kind == 0) ak.push_back(AkimaJob{x, y, reinterpret_cast<Rec1*>(bd + s.co_off), s.n});
@@ -502,9 +565,10 @@ struct TableSet {
     jobs_s1(f.gk, br, bd, ak, cs, lu);
     jobs_s1(f.ga, br, bd, ak, cs, lu);
     if (f.flags.has_fka) {
-      bc.push_back(BicubicJob{f.gk.x_dev ? f.gk.x_dev : reinterpret_cast<const double*>(br) + f.gk.x_off,
-                              f.ga.x_dev ? f.ga.x_dev : reinterpret_cast<const double*>(br) + f.ga.x_off,
-                              f.z_dev ? f.z_dev : reinterpret_cast<const double*>(br) + f.z_off,
+      bc.push_back(BicubicJob{xptr(f.gk, br), xptr(f.ga, br),
+                              f.z_dev ? f.z_dev
+                                      : (f.z_land != NO_LAND ? land_base() + f.z_land
+                                                             : reinterpret_cast<const double*>(br) + f.z_off),
                               reinterpret_cast<double4*>(bd + f.tab_off),
                               reinterpret_cast<double*>(bd + f.scr_off), f.nk, f.na});
       max_nk = std::max(max_nk, f.nk);
@@ -535,6 +599,28 @@ struct TableSet {
                  "H2D(raw tables)", status))
       return false;
     last_h2d = raw.size * sizeof(double);
+    if (land_size) {
+      const size_t need = land_size * sizeof(double);
+      if (need > landing.cap && landing.p) {
+        // growing after an earlier commit: blocks already landed are kept (their sources may be gone)
+        DevBuf grown;
+        if (!grown.reserve(need, status)) return false;
+        if (!cuda_ok(cudaMemcpyAsync(grown.p, landing.p, landing.cap, cudaMemcpyDeviceToDevice, stream),
+                     "D2D(landing)", status) ||
+            !cuda_ok(cudaStreamSynchronize(stream), "D2D(landing)", status))
+          return false;
+        std::swap(grown.p, landing.p);
+        std::swap(grown.cap, landing.cap);
+      } else if (!landing.reserve(need, status))
+        return false;
+      for (DirectCopy& c : direct) {
+        if (c.done) continue;
+        if (!cuda_ok(cudaMemcpyAsync(landing.p + c.off * sizeof(double), c.src, c.n * sizeof(double),
+                                     cudaMemcpyHostToDevice, stream), "H2D(pinned stacked tables)", status))
+          return false;
+        last_h2d += c.n * sizeof(double);
+      }
+    }
     // descriptors + jobs
     h_cosmos.assign(nc, Cosmo());
     h_psp.assign(nc, F2D());
@@ -611,10 +697,14 @@ struct TableSet {
     BicubicJob* d_bc = (BicubicJob*)up(bc.data(), bc.size() * sizeof(BicubicJob));
     AxisJob* d_ax = (AxisJob*)up(ax_jobs.data(), ax_jobs.size() * sizeof(AxisJob));
     last_h2d += jb - 2048;
+    int max_ncs = 0;
+    for (const CsplineJob& j : cs) max_ncs = std::max(max_ncs, j.n);
     launch_prep(d_ak, (int)ak.size(), d_cs, (int)cs.size(), d_lu, (int)lu.size(), d_ax, (int)ax_jobs.size(),
-                d_bc, (int)bc.size(), max_nk, max_na, stream);
+                d_bc, (int)bc.size(), max_nk, max_na, max_ncs, stream);
     if (!cuda_ok(cudaGetLastError(), "table preparation launch", status)) return false;
     if (!cuda_ok(cudaStreamSynchronize(stream), "table preparation", status)) return false;
+    for (DirectCopy& c : direct) c.done = true;  // the callers' pinned buffers are no longer needed
+    owned.clear();
     committed = true;
     return true;
   }
@@ -663,6 +753,10 @@ struct ccl_b200_batch {
   unsigned long long last_qag_evals = 0;
   bool last_fast = false;  // the last 'spline' launch used the grid-sharing kernels
   cudaStream_t stream = nullptr;  // non-blocking: batches driven from different host threads overlap
+  // commit() runs on its own high-priority stream: while another batch's Limber grid (tens of
+  // thousands of CTAs) is being dispatched, the small table-preparation kernels of this batch are
+  // scheduled ahead of its remaining CTAs instead of behind its last wave (PipelinedBatch)
+  cudaStream_t prep_stream = nullptr;
   DevBuf out;   // device result buffer of the host-buffer entry (kept across calls)
   DevBuf call;  // per-batch call buffers (colls, pairs, ells, counters, outputs)
 };
@@ -1126,8 +1220,12 @@ ccl_b200_batch* ccl_b200_batch_new(int ncosmo, const ccl_b200_params* params, in
   if (params) b->params = *params; else ccl_b200_default_params(&b->params);
   b->ts.device = current_device();
   b->ts.cosmos.resize(ncosmo);
-  if (!cuda_ok(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "cudaStreamCreate", status)) {
-    delete b;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (!cuda_ok(cudaStreamCreateWithPriority(&b->stream, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate", status) ||
+      !cuda_ok(cudaStreamCreateWithPriority(&b->prep_stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate",
+               status)) {
+    ccl_b200_batch_free(b);
     return nullptr;
   }
   return b;
@@ -1139,6 +1237,10 @@ void ccl_b200_batch_free(ccl_b200_batch* b) {
   if (b->stream) {
     cudaStreamSynchronize(b->stream);
     cudaStreamDestroy(b->stream);
+  }
+  if (b->prep_stream) {
+    cudaStreamSynchronize(b->prep_stream);
+    cudaStreamDestroy(b->prep_stream);
   }
   delete b;
 }
@@ -1212,10 +1314,14 @@ void ccl_b200_batch_set_achi_stacked(ccl_b200_batch* b, int first, int count, co
                                      const double* chi, const double* a, int* status) {
   BATCH_RANGE(b, first, count);
   b->ts.raw.defer = true;
+  const size_t tot = (size_t)count * stride;
+  const size_t l_chi = b->ts.land_if_pinned(chi, tot), l_a = b->ts.land_if_pinned(a, tot);
+  auto at = [](size_t base, size_t d) { return base == NO_LAND ? NO_LAND : base + d; };
   for (int i = 0; i < count && !*status; ++i) {
     const int n = n_per ? n_per[i] : stride;
     if (n < 5 || n > stride) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: a(chi) spline needs 5 <= n <= stride"); break; }
-    b->ts.plan_s1(b->ts.cosmos[first + i].achi, 0, n, chi + (size_t)i * stride, a + (size_t)i * stride, status);
+    const size_t d = (size_t)i * stride;
+    b->ts.plan_s1(b->ts.cosmos[first + i].achi, 0, n, chi + d, a + d, status, at(l_chi, d), at(l_a, d));
   }
   b->ts.raw.defer = false;
   b->ts.raw.flush();
@@ -1228,8 +1334,13 @@ void ccl_b200_batch_set_growth_stacked(ccl_b200_batch* b, int first, int count, 
   BATCH_RANGE(b, first, count);
   if (n < 5) { *status = CCL_B200_ERROR_MEMORY; set_err("ccl_b200: growth spline needs >= 5 nodes"); return; }
   b->ts.raw.defer = true;
+  // stride_a == 0: one scale-factor grid shared by every slot
+  const size_t l_a = stride_a ? b->ts.land_if_pinned(a, (size_t)count * stride_a) : b->ts.land_put_owned(a, n);
+  const size_t l_g = b->ts.land_if_pinned(growth, (size_t)count * n);
+  auto at = [](size_t base, size_t d) { return base == NO_LAND ? NO_LAND : base + d; };
   for (int i = 0; i < count && !*status; ++i)
-    b->ts.plan_s1(b->ts.cosmos[first + i].growth, 0, n, a + (size_t)i * stride_a, growth + (size_t)i * n, status);
+    b->ts.plan_s1(b->ts.cosmos[first + i].growth, 0, n, a + (size_t)i * stride_a, growth + (size_t)i * n, status,
+                  at(l_a, (size_t)i * stride_a), at(l_g, (size_t)i * n));
   b->ts.raw.defer = false;
   b->ts.raw.flush();
   b->ts.run_checks();
@@ -1246,10 +1357,16 @@ void ccl_b200_batch_set_pk2d_stacked(ccl_b200_batch* b, int first, int count, co
                                      int order_hik, int is_logp, int* status) {
   BATCH_RANGE(b, first, count);
   b->ts.raw.defer = true;
+  // the ln k and a grids are shared by every slot: landed once instead of once per cosmology
+  Lands L;
+  if (lk_arr && nk > 0) L.lk = b->ts.land_put_owned(lk_arr, nk);
+  if (a_arr && na > 0) L.a = b->ts.land_put_owned(a_arr, na);
+  const size_t l_pk = b->ts.land_if_pinned(pk_arr, (size_t)count * na * nk);
   for (int i = 0; i < count && !*status; ++i) {
     CosmoPlan& p = b->ts.cosmos[first + i];
+    L.fka = l_pk == NO_LAND ? NO_LAND : l_pk + (size_t)i * na * nk;
     p.has_psp = b->ts.plan_f2d(p.psp, na, a_arr, nk, lk_arr, pk_arr + (size_t)i * na * nk, nullptr, nullptr, 0,
-                               order_lok, order_hik, GROWTH_CCL, is_logp, 0, 2, status);
+                               order_lok, order_hik, GROWTH_CCL, is_logp, 0, 2, status, L);
   }
   b->ts.raw.defer = false;
   b->ts.raw.flush();
@@ -1270,16 +1387,35 @@ int ccl_b200_batch_add_tracer_stacked(ccl_b200_batch* b, int first, int count, i
   }
   int idx = -1;
   b->ts.raw.defer = true;
+  const size_t cnt = (size_t)count;
+  const bool has_kernel = n_w > 0 && chi_w && w_w;
+  // stride 0: one grid shared by every slot (landed once)
+  const size_t l_chi = !has_kernel ? NO_LAND
+                       : stride_chi ? b->ts.land_if_pinned(chi_w, cnt * stride_chi)
+                                    : b->ts.land_put_owned(chi_w, n_w);
+  const size_t l_w = has_kernel ? b->ts.land_if_pinned(w_w, cnt * n_w) : NO_LAND;
+  const size_t l_a = !(a_ka && na_ka > 0) ? NO_LAND
+                     : stride_a ? b->ts.land_if_pinned(a_ka, cnt * stride_a)
+                                : b->ts.land_put_owned(a_ka, na_ka);
+  const size_t l_lk = (lk_ka && nk_ka > 0) ? b->ts.land_put_owned(lk_ka, nk_ka) : NO_LAND;
+  const size_t l_fka = fka_arr ? b->ts.land_if_pinned(fka_arr, cnt * na_ka * nk_ka) : NO_LAND;
+  const size_t l_fk = fk_arr ? b->ts.land_if_pinned(fk_arr, cnt * nk_ka) : NO_LAND;
+  const size_t l_fa = fa_arr ? b->ts.land_if_pinned(fa_arr, cnt * na_ka) : NO_LAND;
+  auto at = [](size_t base, size_t d) { return base == NO_LAND ? NO_LAND : base + d; };
   for (int i = 0; i < count && !*status; ++i) {
     CosmoPlan& p = b->ts.cosmos[first + i];
+    if (p.tracers.capacity() < 16) p.tracers.reserve(16);
     TracerPlan t;
     const size_t si = (size_t)i;
+    Lands L;
+    L.chi = at(l_chi, si * stride_chi); L.w = at(l_w, si * n_w); L.a = at(l_a, si * stride_a); L.lk = l_lk;
+    L.fka = at(l_fka, si * na_ka * nk_ka); L.fk = at(l_fk, si * nk_ka); L.fa = at(l_fa, si * na_ka);
     if (!b->ts.plan_tracer(t, p.chi_max_nokernel, der_bessel, der_angles, n_w,
                            chi_w ? chi_w + si * stride_chi : nullptr, w_w ? w_w + si * n_w : nullptr, na_ka,
                            a_ka ? a_ka + si * stride_a : nullptr, nk_ka, lk_ka,
                            fka_arr ? fka_arr + si * na_ka * nk_ka : nullptr, fk_arr ? fk_arr + si * nk_ka : nullptr,
                            fa_arr ? fa_arr + si * na_ka : nullptr, is_fka_log, is_factorizable, extrap_order_lok,
-                           extrap_order_hik, status))
+                           extrap_order_hik, status, L))
       break;
     p.tracers.push_back(t);
     idx = (int)p.tracers.size() - 1;
@@ -1302,7 +1438,7 @@ void ccl_b200_batch_reset(ccl_b200_batch* b) { if (b) b->ts.reset(); }
 
 void ccl_b200_batch_commit(ccl_b200_batch* b, int* status) {
   if (*status || !b) return;
-  b->ts.commit(b->stream, status);
+  b->ts.commit(b->prep_stream, status);
 }
 
 unsigned long long ccl_b200_batch_h2d_bytes(const ccl_b200_batch* b) { return b->ts.last_h2d; }

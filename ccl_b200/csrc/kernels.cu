@@ -102,63 +102,143 @@ __device__ void tridiag_factor(const double* x, int n, double* alpha, double* ga
 }
 
 // Solve for the natural-spline c_i of data y(stride) on nodes x and emit, per node, the
-// first derivative gsl_spline_eval_deriv(spline, x_i) into out(stride).  `tmp` (same
-// indexing as out) is used as scratch for the forward sweep, so out may alias nothing
-// else.  Mirrors cspline_init + cspline_eval_deriv.
+// first derivative gsl_spline_eval_deriv(spline, x_i) into out(stride).  out is also the scratch
+// of the forward sweep.  Mirrors cspline_init + cspline_eval_deriv (same operations in the same
+// order).  One thread runs the two serial sweeps; their only true dependence is one FMA per node,
+// so the table reads of PF nodes are issued together ahead of the chain (the loop is otherwise
+// bound by one exposed L2/HBM latency per node: out aliases y's buffer, nothing can be hoisted by
+// the compiler).
+constexpr int PF = 8;
+
 __device__ void natural_spline_node_derivs(const double* x, int n, const double* y, size_t ystride,
                                            double* out, size_t ostride, const double* alpha,
                                            const double* gamma) {
   const int N = n - 2;
   auto Y = [&](int i) { return y[(size_t)i * ystride]; };
-  auto G = [&](int i) {
-    const double h_i = x[i + 1] - x[i];
-    const double h_ip1 = x[i + 2] - x[i + 1];
-    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0;
-    const double g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
-    return 3.0 * ((Y(i + 2) - Y(i + 1)) * g_ip1 - (Y(i + 1) - Y(i)) * g_i);
-  };
-  // forward sweep: z_i, then c~_i = z_i / alpha_i stored at node i+1
+  auto inv = [](double h) { return (h != 0.0) ? 1.0 / h : 0.0; };
+  // forward sweep: z_i = G_i - gamma_{i-1} z_{i-1}, c~_i = z_i / alpha_i stored at node i+1, with
+  // G_i = 3 ((y_{i+2} - y_{i+1}) / h_{i+1} - (y_{i+1} - y_i) / h_i)
   if (N == 1) {
-    out[ostride] = G(0) / (2.0 * ((x[2] - x[1]) + (x[1] - x[0])));
+    const double G0 = 3.0 * ((Y(2) - Y(1)) * inv(x[2] - x[1]) - (Y(1) - Y(0)) * inv(x[1] - x[0]));
+    out[ostride] = G0 / (2.0 * ((x[2] - x[1]) + (x[1] - x[0])));
   } else {
-    double z = G(0);
-    out[ostride] = z / alpha[0];
-    for (int i = 1; i < N; ++i) {
-      z = G(i) - gamma[i - 1] * z;
-      out[(size_t)(i + 1) * ostride] = z / alpha[i];
+    double xa = x[1], ya = Y(1);
+    double slope = (ya - Y(0)) * inv(xa - x[0]);  // (y_{i+1} - y_i) / h_i of the current i
+    double z = 0.0;
+    for (int i0 = 0; i0 < N; i0 += PF) {
+      double xb[PF], yb[PF], al[PF], gm[PF];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int i = min(i0 + u, N - 1);
+        xb[u] = x[i + 2];
+        yb[u] = Y(i + 2);
+        al[u] = alpha[i];
+        gm[u] = gamma[max(i - 1, 0)];
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int i = i0 + u;
+        if (i < N) {
+          const double snext = (yb[u] - ya) * inv(xb[u] - xa);
+          const double G = 3.0 * (snext - slope);
+          z = (i == 0) ? G : G - gm[u] * z;
+          out[(size_t)(i + 1) * ostride] = z / al[u];
+          slope = snext; xa = xb[u]; ya = yb[u];
+        }
+      }
     }
   }
   // back substitution fused with the derivative evaluation.  c_node[n-1] = 0.
   double c_next = 0.0;  // c at node i+1
-  // last node: derivative of the last interval at its right end
-  // first get c at node n-2
-  double c_cur;
+  double c_cur = out[(size_t)(n - 2) * ostride];  // node n-2 <-> system index N-1: c = c~
+  double xr = x[n - 1], yr = Y(n - 1);            // right end of the current interval
+  double xl = x[n - 2], yl = Y(n - 2);
   {
-    // node n-2 corresponds to system index N-1
-    c_cur = out[(size_t)(n - 2) * ostride];  // x[N-1] = c~[N-1]
-    const double h = x[n - 1] - x[n - 2];
-    const double dyv = Y(n - 1) - Y(n - 2);
+    const double h = xr - xl;
+    const double dyv = yr - yl;
     const double b = (dyv / h) - h * (c_next + 2.0 * c_cur) / 3.0;
     const double d = (c_next - c_cur) / (3.0 * h);
     out[(size_t)(n - 1) * ostride] = b + h * (2.0 * c_cur + 3.0 * d * h);
     out[(size_t)(n - 2) * ostride] = b;
   }
   c_next = c_cur;
-  for (int node = n - 3; node >= 0; --node) {
-    if (node >= 1) {
-      const int i = node - 1;  // system index
-      c_cur = out[(size_t)node * ostride] - gamma[i] * c_next;
-    } else
-      c_cur = 0.0;
-    const double h = x[node + 1] - x[node];
-    const double dyv = Y(node + 1) - Y(node);
-    out[(size_t)node * ostride] = (dyv / h) - h * (c_next + 2.0 * c_cur) / 3.0;
-    c_next = c_cur;
+  xr = xl; yr = yl;
+  for (int node0 = n - 3; node0 >= 0; node0 -= PF) {
+    double xb[PF], yb[PF], ct[PF], gm[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int node = max(node0 - u, 0);
+      xb[u] = x[node];
+      yb[u] = Y(node);
+      ct[u] = out[(size_t)node * ostride];
+      gm[u] = gamma[max(node - 1, 0)];
+    }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int node = node0 - u;
+      if (node >= 0) {
+        c_cur = (node >= 1) ? ct[u] - gm[u] * c_next : 0.0;
+        const double h = xr - xb[u];
+        const double dyv = yr - yb[u];
+        out[(size_t)node * ostride] = (dyv / h) - h * (c_next + 2.0 * c_cur) / 3.0;
+        c_next = c_cur;
+        xr = xb[u]; yr = yb[u];
+      }
+    }
   }
 }
 
 // Factorised-transfer splines: natural cspline coefficients {y, b, c, d} per interval
-// (cspline_init + coeff_calc of interpolation/cspline.c).  One thread per job.
+// (cspline_init + coeff_calc of interpolation/cspline.c).  One warp per job: the nodes are staged in
+// shared memory with coalesced loads, lane 0 runs the three serial sweeps there (same operations in
+// the same order as GSL), all lanes write the interval records.  Layout of the dynamic shared
+// memory: x[n] y[n] alpha[n] gamma[n] c[n].
+__global__ void cspline_coef_smem_kernel(const CsplineJob* jobs, int max_n) {
+  extern __shared__ double csm[];
+  const CsplineJob jb = jobs[blockIdx.x];
+  const int n = jb.n, lane = threadIdx.x;
+  double* x = csm;
+  double* y = x + max_n;
+  double* alpha = y + max_n;
+  double* gamma = alpha + max_n;
+  double* c = gamma + max_n;
+  for (int i = lane; i < n; i += 32) { x[i] = jb.x[i]; y[i] = jb.y[i]; }
+  __syncwarp();
+  if (lane == 0) {
+    const int N = n - 2;
+    c[0] = 0.0;
+    c[n - 1] = 0.0;
+    auto G = [&](int i) {
+      const double h_i = x[i + 1] - x[i];
+      const double h_ip1 = x[i + 2] - x[i + 1];
+      const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0;
+      const double g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+      return 3.0 * ((y[i + 2] - y[i + 1]) * g_ip1 - (y[i + 1] - y[i]) * g_i);
+    };
+    if (N == 1) {
+      c[1] = G(0) / (2.0 * ((x[2] - x[1]) + (x[1] - x[0])));
+    } else {
+      tridiag_factor(x, n, alpha, gamma);
+      double z = G(0);
+      c[1] = z / alpha[0];
+      for (int i = 1; i < N; ++i) {
+        z = G(i) - gamma[i - 1] * z;
+        c[i + 1] = z / alpha[i];
+      }
+      for (int i = N - 2; i >= 0; --i) c[i + 1] = c[i + 1] - gamma[i] * c[i + 2];
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < n - 1; i += 32) {
+    const double dx = x[i + 1] - x[i];
+    const double dy = y[i + 1] - y[i];
+    const double b = (dy / dx) - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
+    const double d = (c[i + 1] - c[i]) / (3.0 * dx);
+    jb.rec[i] = Rec1{x[i], x[i + 1], y[i], b, c[i], d};
+  }
+}
+
+// Same for splines too long for shared memory: one thread per job on global scratch.
 __global__ void cspline_coef_kernel(const CsplineJob* jobs, int njobs) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= njobs) return;
@@ -244,11 +324,19 @@ __global__ void bicubic_deriv_kernel(const BicubicJob* jobs, int pass) {
 
 void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs, const LutJob* d_lut,
                  int nlut, const AxisJob* d_ax, int nax, const BicubicJob* d_bc, int nbc, int max_nk,
-                 int max_na, cudaStream_t stream) {
+                 int max_na, int max_ncs, cudaStream_t stream) {
   if (nak > 0) akima_coef_kernel<<<nak, 128, 0, stream>>>(d_ak);
   if (nlut > 0) lut_kernel<<<nlut, 128, 0, stream>>>(d_lut);
   if (nax > 0) axis_kernel<<<nax, 128, 0, stream>>>(d_ax);
-  if (ncs > 0) cspline_coef_kernel<<<(ncs + 63) / 64, 64, 0, stream>>>(d_cs, ncs);
+  if (ncs > 0) {
+    const size_t csm = sizeof(double) * 5 * (size_t)max_ncs;
+    if (csm <= 200 * 1024) {
+      if (csm > 48 * 1024)
+        cudaFuncSetAttribute(cspline_coef_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
+      cspline_coef_smem_kernel<<<ncs, 32, csm, stream>>>(d_cs, max_ncs);
+    } else
+      cspline_coef_kernel<<<(ncs + 63) / 64, 64, 0, stream>>>(d_cs, ncs);
+  }
   if (nbc > 0) {
     bicubic_factor_kernel<<<nbc, 256, 0, stream>>>(d_bc);
     dim3 g1((max_na + max_nk + 63) / 64, nbc), g2((max_na + 63) / 64, nbc);

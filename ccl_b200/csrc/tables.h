@@ -170,7 +170,7 @@ struct BicubicJob {
 // launchers (kernels.cu)
 void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs, const LutJob* d_lut,
                  int nlut, const AxisJob* d_ax, int nax, const BicubicJob* d_bc, int nbc, int max_nk,
-                 int max_na, cudaStream_t stream);
+                 int max_na, int max_ncs, cudaStream_t stream);
 cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws, size_t qag_ws_bytes,
                           cudaStream_t stream);
 size_t limber_qag_workspace_bytes(int n_iteration);

@@ -206,6 +206,7 @@ class LibBatch:
         self._geom = None
 
     def reset(self):
+        self._sources = []
         _lib.load().ccl_b200_batch_reset(self.h)
 
     def set_cosmology(self, ic, chi, a, a_growth=None, growth=None, chi_max_nokernel=None):
@@ -250,6 +251,9 @@ class LibBatch:
         L = _lib.load()
         st = C.c_int(0)
         count = int(stk["count"])
+        # pinned source arrays are read by commit(), not here: keep them alive until then
+        self._sources = getattr(self, "_sources", [])
+        self._sources.append(stk)
         n_per, chi, a = stk["achi"]
         kn, pn = iarr(n_per)
         kc, pc = darr(chi)
@@ -303,6 +307,7 @@ class LibBatch:
     def commit(self):
         st = C.c_int(0)
         _lib.load().ccl_b200_batch_commit(self.h, C.byref(st))
+        self._sources = []
         _check(st.value, "batch_commit")
 
     @property

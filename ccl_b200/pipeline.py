@@ -3,8 +3,11 @@
 `PipelinedBatch.angular_cl(stacked_tables, ...)` splits the batch into chunks of cosmologies, each
 with its own ccl_b200_batch (arena + non-blocking stream), and runs three stages on three host
 threads so that they overlap across chunks:
-  1. staging of the caller's stacked host tables into the chunk's pinned arena (host threads),
-  2. one H2D copy + device table preparation (copy engine + small kernels),
+  1. planning, and for pageable inputs staging of the caller's stacked host tables into the chunk's
+     pinned arena (host threads); stacked arrays that already live in pinned memory (pin_stacked)
+     are not staged at all,
+  2. H2D copies (one DMA per pinned stacked array, one for the staged arena) + device table
+     preparation (copy engine + small kernels),
   3. the Limber kernels + D2H of the chunk's C_ell block (SMs + copy engine).
 The C ABI calls release the GIL, so the stages really run concurrently.  Results are identical to
 a single LibBatch (same kernels on the same tables).  No counterpart in the reference, which has
@@ -12,14 +15,14 @@ no batch axis at all (pairs and cosmologies are Python loops, benchmarks/test_ti
 """
 import queue
 import threading
+import time
 
 import numpy as np
 
 from . import _lib
 from .lowlevel import LibBatch
-from .sharding import shard_range
 
-__all__ = ("PipelinedBatch", "slice_stacked")
+__all__ = ("PipelinedBatch", "slice_stacked", "pin_stacked")
 
 
 def slice_stacked(stk, lo, hi):
@@ -49,12 +52,55 @@ def slice_stacked(stk, lo, hi):
     return out
 
 
+def pin_stacked(stk):
+    """Copy of a stacked-table dict whose float64 arrays live in pinned (page-locked) host memory.
+
+    The stacked setters recognise pinned sources (cudaPointerGetAttributes) and skip the staging
+    copy: commit() moves each stacked array with one DMA straight from the caller's buffer, which
+    therefore has to stay alive and unchanged until commit() returns (LibBatch keeps a reference)."""
+    import torch
+
+    def pin(x):
+        if x is None or np.ndim(x) == 0:
+            return x
+        x = np.asarray(x)
+        if x.dtype != np.float64:
+            return x
+        t = torch.empty(x.shape, dtype=torch.float64, pin_memory=True)
+        v = t.numpy()
+        v[...] = x
+        return v
+
+    out = dict(stk)
+    n_per, chi, a = stk["achi"]
+    out["achi"] = (n_per, pin(chi), pin(a))
+    if stk.get("growth") is not None:
+        out["growth"] = tuple(pin(x) for x in stk["growth"])
+    lk, apk, pk, olo, ohi, islog = stk["pk"]
+    out["pk"] = (lk, apk, pin(pk), olo, ohi, islog)
+    out["tracers"] = [{k: (pin(v) if k in ("chi", "w", "a", "fka", "fk", "fa") else v) for k, v in t.items()}
+                      for t in stk["tracers"]]
+    return out
+
+
 class PipelinedBatch:
     def __init__(self, ncosmo, nchunks=8, params=None):
         self.ncosmo = int(ncosmo)
         self.nchunks = max(1, min(int(nchunks), self.ncosmo))
-        self.spans = [shard_range(self.ncosmo, self.nchunks, c) for c in range(self.nchunks)]
+        # chunk sizes ramp up (x1.5 from a quarter of the regular size): the first chunk reaches the
+        # SMs after a quarter of the regular stage + upload time, later chunks amortise launch overheads
+        base = -(-self.ncosmo // self.nchunks)
+        sizes, size, rem = [], max(1, base // 4), self.ncosmo
+        while rem > 0:
+            take = min(size, base, rem)
+            sizes.append(take)
+            rem -= take
+            size = -(-size * 3 // 2)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        self.spans = [(int(offs[c]), int(sizes[c])) for c in range(len(sizes))]
+        self.nchunks = len(sizes)
         self.batches = [LibBatch(cnt, params) for _, cnt in self.spans]
+        self.trace = None     # set to [] to collect (stage, chunk, t_start, t_end) of the next call
 
     @property
     def h2d_bytes(self):
@@ -70,13 +116,22 @@ class PipelinedBatch:
         stat = np.zeros((self.ncosmo, len(pairs)), dtype=np.int32)
         staged, ready = queue.Queue(), queue.Queue()
         errors = []
+        trace = self.trace
+
+        def timed(name, c, fn, *a, **k):
+            if trace is None:
+                return fn(*a, **k)
+            t0 = time.perf_counter()
+            r = fn(*a, **k)
+            trace.append((name, c, t0, time.perf_counter()))
+            return r
 
         def stage():
             try:
                 for c, (off, cnt) in enumerate(self.spans):
                     b = self.batches[c]
                     b.reset()
-                    b.set_stacked(0, slice_stacked(stk, off, off + cnt))
+                    timed("stage", c, b.set_stacked, 0, slice_stacked(stk, off, off + cnt))
                     staged.put(c)
             except BaseException as e:  # noqa: BLE001 -- re-raised on the caller's thread
                 errors.append(e)
@@ -89,7 +144,7 @@ class PipelinedBatch:
                     c = staged.get()
                     if c is None:
                         break
-                    self.batches[c].commit()
+                    timed("commit", c, self.batches[c].commit)
                     ready.put(c)
             except BaseException as e:  # noqa: BLE001
                 errors.append(e)
@@ -106,7 +161,8 @@ class PipelinedBatch:
             if c is None:
                 break
             off, cnt = self.spans[c]
-            _, s_c, st = self.batches[c].angular_cl(collections, pairs, ells, method, out=out[off:off + cnt])
+            _, s_c, st = timed("compute", c, self.batches[c].angular_cl, collections, pairs, ells, method,
+                               out=out[off:off + cnt])
             stat[off:off + cnt] = s_c
             worst = worst or st
         t1.join()

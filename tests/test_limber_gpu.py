@@ -321,6 +321,50 @@ def test_pipelined_host_entry_equals_single_batch():
         assert np.array_equal(c1, c2) and np.array_equal(s1, s2) and st1 == st2 == 0
 
 
+def test_pinned_stacked_inputs_are_not_staged():
+    """Stacked arrays in page-locked memory are DMA'd straight from the caller's buffers (landing
+    region) instead of being staged: same C_ell bit for bit, through LibBatch and PipelinedBatch; the
+    landed tables survive a second commit after the sources are gone and a later per-slot addition."""
+    import sys, os, gc
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import ccl_b200 as cb
+    tables = bench.build_host_tables(3)
+    colls, pairs, ells = bench.geometry()
+    ells = ells[::7]
+    n = 21
+    stk = bench.stack_host_tables(tables, n, 1)
+    b1 = cb.LibBatch(n)
+    b1.set_stacked(0, stk)
+    b1.commit()
+    c1, s1, _ = b1.angular_cl(colls, pairs, ells)
+    pinned = cb.pin_stacked(stk)
+    b2 = cb.LibBatch(n)
+    b2.set_stacked(0, pinned)
+    b2.commit()
+    c2, s2, _ = b2.angular_cl(colls, pairs, ells)
+    assert np.array_equal(c1, c2) and np.array_equal(s1, s2)
+    assert [b1.tracer_chi_range(4, t) for t in range(15)] == [b2.tracer_chi_range(4, t) for t in range(15)]
+    pipe = cb.PipelinedBatch(n, nchunks=4)
+    for _ in range(2):
+        c3, s3, st3 = pipe.angular_cl(pinned, colls, pairs, ells)
+        assert np.array_equal(c1, c3) and np.array_equal(s1, s3) and st3 == 0
+    # sources released, then one more sub-tracer added per slot and a second commit
+    for t in pinned["tracers"]:
+        for k in ("chi", "w", "fa"):
+            if t.get(k) is not None:
+                t[k][...] = np.nan
+    pinned["pk"][2][...] = np.nan
+    del pinned
+    gc.collect()
+    sub = tables[0]["subs"][7]
+    for ic in range(n):
+        b2.add_tracer(ic, chi=sub["chi"], w=sub["w"])
+    b2.commit()
+    c4, s4, _ = b2.angular_cl(colls, pairs, ells)
+    assert np.array_equal(c1, c4) and np.array_equal(s1, s4)
+
+
 def test_batch_fallbacks_to_general_kernel(synth):
     """(i) a collection with more sub-tracers than a fast-path task holds goes through the redo list;
     (ii) a table form outside the fast path (2-D k-a transfer) sends the whole batch to the general
