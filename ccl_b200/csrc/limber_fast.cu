@@ -302,6 +302,62 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int s, int base,
   }
 }
 
+// Interior chunks (every lane holds a node in 4..nk-6 of the uniform part of the grid): the same sums
+// without the shared-memory window.  The left neighbour's value and first difference come from two
+// warp shuffles; the tie flags follow from ONE ballot of E_s = (d_s == d_{s-1}), d_s = f_s - f_{s-1}:
+// z_c = E_{c+2} && E_c.  The previous chunk's last four values (W.fc, also what the edge form reads)
+// supply lane 0's neighbour and the two carried E bits.
+__device__ __forceinline__ void pair_phase_interior(FastWarp& W, int np, int lane, double kp, double dx,
+                                                    double inv_dx, unsigned& zdirty) {
+  const unsigned FULL = 0xffffffffu;
+  const double wtrap = 0.5 * dx;
+#pragma unroll 1
+  for (int q = 0; q < np; ++q) {
+    const int2 po = W.po[q];
+    const double f4 = kp * W.dflat[po.x + lane] * W.dflat[po.y + lane];
+    const double2 ca = *reinterpret_cast<const double2*>(&W.fc[q][0]);  // f at nodes base-4, base-3
+    const double2 cb = *reinterpret_cast<const double2*>(&W.fc[q][2]);  // f at nodes base-2, base-1
+    const double cd1 = cb.y - cb.x, cd2 = cb.x - ca.y, cd3 = ca.y - ca.x;  // d at base-1, base-2, base-3
+    double f3 = __shfl_up_sync(FULL, f4, 1);
+    if (lane == 0) f3 = cb.y;
+    const double dd = f4 - f3;
+    double dc = __shfl_up_sync(FULL, dd, 1);
+    if (lane == 0) dc = cd1;
+    const unsigned em = __ballot_sync(FULL, dd == dc);
+    const unsigned ec = (cd2 == cd3 ? 1u : 0u) | (cd1 == cd2 ? 2u : 0u);  // E at nodes base-2, base-1
+    const unsigned zm = em & ((em << 2) | ec);  // bit lane: tie flag of node c = base + lane - 2
+    __syncwarp();  // every lane has read W.fc
+    if (lane >= 28) W.fc[q][lane - 28] = f4;
+    const unsigned carry = (zdirty >> q) & 1u;
+    const unsigned trans = zm ^ ((zm << 1) | carry);
+    double add = wtrap * (f3 + f4);
+    if (trans != 0u) {
+      // ---- a tie transition in this chunk: per-node form (see pair_phase) ----
+      double db = __shfl_up_sync(FULL, dd, 2), da = __shfl_up_sync(FULL, dd, 3);
+      if (lane < 2) db = (lane == 1) ? cd1 : cd2;
+      if (lane < 3) da = (lane == 2) ? cd1 : ((lane == 1) ? cd2 : cd3);
+      if (((trans >> lane) & 1u) != 0u) {
+        const double mm2 = da * inv_dx, mm1 = db * inv_dx, m0 = dc * inv_dx, mp1 = dd * inv_dx;
+        const bool z = ((zm >> lane) & 1u) != 0u;
+        const bool zprev = lane ? (((zm >> (lane - 1)) & 1u) != 0u) : (carry != 0u);
+        const double d12 = fabs(mm1 - mm2);
+        const double NE = fabs(mp1 - m0) + d12;
+        double tc = 0.0;
+        if (!z && NE != 0.0) {
+          const double alpha = d12 / NE;
+          tc = (1.0 - alpha) * mm1 + alpha * m0;
+        }
+        double cc = z ? 0.0 : tc;
+        if (!zprev) cc -= (z ? mm1 : tc);
+        add += cc * (dx * dx * (1.0 / 12.0));
+      }
+    }
+    W.acc[q][lane] += add;
+    const unsigned top = (zm >> 31) & 1u;
+    if ((carry | top) != 0u) zdirty = (zdirty & ~(1u << q)) | (top << q);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // The fast integrator.
 // ------------------------------------------------------------------------------------------
@@ -508,7 +564,7 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
         if ((base == 0) || (base + 31 >= nk - 5))
           pair_phase<true>(W, np, s, base, nk, lane, kp, dx, inv_dx, inv_hl, zdirty);
         else
-          pair_phase<false>(W, np, s, base, nk, lane, kp, dx, inv_dx, inv_hl, zdirty);
+          pair_phase_interior(W, np, lane, kp, dx, inv_dx, zdirty);
         __syncwarp();
       }
 
