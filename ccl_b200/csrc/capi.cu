@@ -368,7 +368,7 @@ struct TableSet {
     f.nk = nk; f.na = na;
     f.z_dev = d_z;
     f.tab_off = derive(sizeof(double4) * (size_t)nk * na);
-    f.scr_off = derive(sizeof(double) * 2 * (size_t)(nk + na));
+    f.scr_off = derive(sizeof(double) * 4 * (size_t)(nk + na));
     g.has_fka = 1;
   }
 
@@ -423,7 +423,7 @@ struct TableSet {
       if (L.fka == NO_LAND) f.z_off = raw.put(fka_arr, (size_t)nk * na);
       if (f.z_off == (size_t)-1) { *status = CCL_B200_ERROR_MEMORY; return false; }
       f.tab_off = derive(sizeof(double4) * (size_t)nk * na);
-      f.scr_off = derive(sizeof(double) * 2 * (size_t)(nk + na));
+      f.scr_off = derive(sizeof(double) * 4 * (size_t)(nk + na));
       g.has_fka = 1;
     }
     return true;
@@ -565,12 +565,20 @@ struct TableSet {
     jobs_s1(f.gk, br, bd, ak, cs, lu);
     jobs_s1(f.ga, br, bd, ak, cs, lu);
     if (f.flags.has_fka) {
-      bc.push_back(BicubicJob{xptr(f.gk, br), xptr(f.ga, br),
+      // tables on the same pair of grids (same device arrays) share one set of axis factors
+      const double* xk = xptr(f.gk, br);
+      const double* ya = xptr(f.ga, br);
+      double* scratch = reinterpret_cast<double*>(bd + f.scr_off);
+      int factor = 1;
+      if (!bc.empty() && bc.back().xk == xk && bc.back().ya == ya && bc.back().nk == f.nk && bc.back().na == f.na) {
+        scratch = bc.back().scratch;
+        factor = 0;
+      }
+      bc.push_back(BicubicJob{xk, ya,
                               f.z_dev ? f.z_dev
                                       : (f.z_land != NO_LAND ? land_base() + f.z_land
                                                              : reinterpret_cast<const double*>(br) + f.z_off),
-                              reinterpret_cast<double4*>(bd + f.tab_off),
-                              reinterpret_cast<double*>(bd + f.scr_off), f.nk, f.na});
+                              reinterpret_cast<double4*>(bd + f.tab_off), scratch, f.nk, f.na, factor});
       max_nk = std::max(max_nk, f.nk);
       max_na = std::max(max_na, f.na);
     }

@@ -101,88 +101,127 @@ __device__ void tridiag_factor(const double* x, int n, double* alpha, double* ga
   if (N > 1) alpha[N - 1] = diag(N - 1) - off(N - 2) * gamma[N - 2];
 }
 
-// Solve for the natural-spline c_i of data y(stride) on nodes x and emit, per node, the
-// first derivative gsl_spline_eval_deriv(spline, x_i) into out(stride).  out is also the scratch
-// of the forward sweep.  Mirrors cspline_init + cspline_eval_deriv (same operations in the same
-// order).  One thread runs the two serial sweeps; their only true dependence is one FMA per node,
-// so the table reads of PF nodes are issued together ahead of the chain (the loop is otherwise
-// bound by one exposed L2/HBM latency per node: out aliases y's buffer, nothing can be hoisted by
-// the compiler).
+// Solve for the natural-spline c_i of NP data planes y_p(stride) on the same nodes x and emit, per
+// node, the first derivative gsl_spline_eval_deriv(spline, x_i) into out_p(stride); plane p has its
+// data at base + yoff[p] and its output at base + ooff[p].  out is also the scratch of the forward
+// sweep.  Mirrors cspline_init + cspline_eval_deriv operation by operation, except that the grid-only
+// reciprocals are precomputed once per grid (AxisFactors: 1/h_i as in GSL, 1/alpha_i and 1/3 replacing
+// three divisions by multiplications: a last-bit difference).  One thread runs the two serial sweeps;
+// their only true dependence is one FMA per node and plane, so the strided table reads of PF nodes are
+// issued together ahead of the chain (out aliases y's buffer: the compiler cannot hoist them), and the
+// planes of one node share its cache line.
 constexpr int PF = 8;
 
-__device__ void natural_spline_node_derivs(const double* x, int n, const double* y, size_t ystride,
-                                           double* out, size_t ostride, const double* alpha,
-                                           const double* gamma) {
+struct AxisFactors {
+  const double* alpha;   // LDL^T diagonal
+  const double* gamma;   // LDL^T off-diagonal factor
+  const double* inv_h;   // 1 / (x_{i+1} - x_i), 0 for a zero interval
+  const double* inv_al;  // 1 / alpha_i
+};
+
+__device__ __forceinline__ AxisFactors axis_factors(double* scratch, int n) {
+  return AxisFactors{scratch, scratch + n, scratch + 2 * n, scratch + 3 * n};
+}
+
+template <int NP>
+__device__ __forceinline__ void natural_spline_node_derivs(const double* x, int n, double* base, size_t stride,
+                                                           const int (&yoff)[NP], const int (&ooff)[NP],
+                                                           const AxisFactors F) {
   const int N = n - 2;
-  auto Y = [&](int i) { return y[(size_t)i * ystride]; };
-  auto inv = [](double h) { return (h != 0.0) ? 1.0 / h : 0.0; };
+  const double third = 1.0 / 3.0;
+  auto Y = [&](int p, int i) { return base[(size_t)i * stride + yoff[p]]; };
+  auto O = [&](int p, int i) -> double& { return base[(size_t)i * stride + ooff[p]]; };
   // forward sweep: z_i = G_i - gamma_{i-1} z_{i-1}, c~_i = z_i / alpha_i stored at node i+1, with
   // G_i = 3 ((y_{i+2} - y_{i+1}) / h_{i+1} - (y_{i+1} - y_i) / h_i)
   if (N == 1) {
-    const double G0 = 3.0 * ((Y(2) - Y(1)) * inv(x[2] - x[1]) - (Y(1) - Y(0)) * inv(x[1] - x[0]));
-    out[ostride] = G0 / (2.0 * ((x[2] - x[1]) + (x[1] - x[0])));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const double G0 = 3.0 * ((Y(p, 2) - Y(p, 1)) * F.inv_h[1] - (Y(p, 1) - Y(p, 0)) * F.inv_h[0]);
+      O(p, 1) = G0 / (2.0 * ((x[2] - x[1]) + (x[1] - x[0])));
+    }
   } else {
-    double xa = x[1], ya = Y(1);
-    double slope = (ya - Y(0)) * inv(xa - x[0]);  // (y_{i+1} - y_i) / h_i of the current i
-    double z = 0.0;
+    const double g0 = F.inv_h[0];
+    double ya[NP], slope[NP], z[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      ya[p] = Y(p, 1);
+      slope[p] = (ya[p] - Y(p, 0)) * g0;  // (y_{i+1} - y_i) / h_i of the current i
+      z[p] = 0.0;
+    }
     for (int i0 = 0; i0 < N; i0 += PF) {
-      double xb[PF], yb[PF], al[PF], gm[PF];
+      double yb[NP][PF];
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         const int i = min(i0 + u, N - 1);
-        xb[u] = x[i + 2];
-        yb[u] = Y(i + 2);
-        al[u] = alpha[i];
-        gm[u] = gamma[max(i - 1, 0)];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) yb[p][u] = Y(p, i + 2);
       }
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         const int i = i0 + u;
         if (i < N) {
-          const double snext = (yb[u] - ya) * inv(xb[u] - xa);
-          const double G = 3.0 * (snext - slope);
-          z = (i == 0) ? G : G - gm[u] * z;
-          out[(size_t)(i + 1) * ostride] = z / al[u];
-          slope = snext; xa = xb[u]; ya = yb[u];
+          const double g = F.inv_h[i + 1];
+          const double ial = F.inv_al[i], gm = F.gamma[max(i - 1, 0)];
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const double snext = (yb[p][u] - ya[p]) * g;
+            const double G = 3.0 * (snext - slope[p]);
+            z[p] = (i == 0) ? G : G - gm * z[p];
+            O(p, i + 1) = z[p] * ial;
+            slope[p] = snext;
+            ya[p] = yb[p][u];
+          }
         }
       }
     }
   }
   // back substitution fused with the derivative evaluation.  c_node[n-1] = 0.
-  double c_next = 0.0;  // c at node i+1
-  double c_cur = out[(size_t)(n - 2) * ostride];  // node n-2 <-> system index N-1: c = c~
-  double xr = x[n - 1], yr = Y(n - 1);            // right end of the current interval
-  double xl = x[n - 2], yl = Y(n - 2);
+  double c_next[NP], yr[NP];
+  double xr = x[n - 1];
   {
-    const double h = xr - xl;
-    const double dyv = yr - yl;
-    const double b = (dyv / h) - h * (c_next + 2.0 * c_cur) / 3.0;
-    const double d = (c_next - c_cur) / (3.0 * h);
-    out[(size_t)(n - 1) * ostride] = b + h * (2.0 * c_cur + 3.0 * d * h);
-    out[(size_t)(n - 2) * ostride] = b;
+    const double xl = x[n - 2];
+    const double h = xr - xl, g = F.inv_h[n - 2];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const double c_cur = O(p, n - 2);  // node n-2 <-> system index N-1: c = c~
+      const double yl = Y(p, n - 2);
+      const double dyv = Y(p, n - 1) - yl;
+      const double b = (dyv * g) - h * (0.0 + 2.0 * c_cur) * third;
+      const double d = (0.0 - c_cur) * (third * g);
+      O(p, n - 1) = b + h * (2.0 * c_cur + 3.0 * d * h);
+      O(p, n - 2) = b;
+      c_next[p] = c_cur;
+      yr[p] = yl;
+    }
+    xr = xl;
   }
-  c_next = c_cur;
-  xr = xl; yr = yl;
   for (int node0 = n - 3; node0 >= 0; node0 -= PF) {
-    double xb[PF], yb[PF], ct[PF], gm[PF];
+    double yb[NP][PF], ct[NP][PF];
 #pragma unroll
     for (int u = 0; u < PF; ++u) {
       const int node = max(node0 - u, 0);
-      xb[u] = x[node];
-      yb[u] = Y(node);
-      ct[u] = out[(size_t)node * ostride];
-      gm[u] = gamma[max(node - 1, 0)];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        yb[p][u] = Y(p, node);
+        ct[p][u] = O(p, node);
+      }
     }
 #pragma unroll
     for (int u = 0; u < PF; ++u) {
       const int node = node0 - u;
       if (node >= 0) {
-        c_cur = (node >= 1) ? ct[u] - gm[u] * c_next : 0.0;
-        const double h = xr - xb[u];
-        const double dyv = yr - yb[u];
-        out[(size_t)node * ostride] = (dyv / h) - h * (c_next + 2.0 * c_cur) / 3.0;
-        c_next = c_cur;
-        xr = xb[u]; yr = yb[u];
+        const double xl = x[node];
+        const double gm = F.gamma[max(node - 1, 0)];
+        const double h = xr - xl, g = F.inv_h[node];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const double c_cur = (node >= 1) ? ct[p][u] - gm * c_next[p] : 0.0;
+          const double dyv = yr[p] - yb[p][u];
+          O(p, node) = (dyv * g) - h * (c_next[p] + 2.0 * c_cur) * third;
+          c_next[p] = c_cur;
+          yr[p] = yb[p][u];
+        }
+        xr = xl;
       }
     }
   }
@@ -192,7 +231,7 @@ __device__ void natural_spline_node_derivs(const double* x, int n, const double*
 // (cspline_init + coeff_calc of interpolation/cspline.c).  One warp per job: the nodes are staged in
 // shared memory with coalesced loads, lane 0 runs the three serial sweeps there (same operations in
 // the same order as GSL), all lanes write the interval records.  Layout of the dynamic shared
-// memory: x[n] y[n] alpha[n] gamma[n] c[n].
+// memory: x[n] y[n] alpha[n] gamma[n] c[n] 1/h[n].
 __global__ void cspline_coef_smem_kernel(const CsplineJob* jobs, int max_n) {
   extern __shared__ double csm[];
   const CsplineJob jb = jobs[blockIdx.x];
@@ -202,31 +241,36 @@ __global__ void cspline_coef_smem_kernel(const CsplineJob* jobs, int max_n) {
   double* alpha = y + max_n;
   double* gamma = alpha + max_n;
   double* c = gamma + max_n;
+  double* ih = c + max_n;
+  const int N = n - 2;
   for (int i = lane; i < n; i += 32) { x[i] = jb.x[i]; y[i] = jb.y[i]; }
   __syncwarp();
-  if (lane == 0) {
-    const int N = n - 2;
-    c[0] = 0.0;
-    c[n - 1] = 0.0;
-    auto G = [&](int i) {
-      const double h_i = x[i + 1] - x[i];
-      const double h_ip1 = x[i + 2] - x[i + 1];
-      const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0;
-      const double g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
-      return 3.0 * ((y[i + 2] - y[i + 1]) * g_ip1 - (y[i + 1] - y[i]) * g_i);
-    };
-    if (N == 1) {
-      c[1] = G(0) / (2.0 * ((x[2] - x[1]) + (x[1] - x[0])));
-    } else {
+  // everything without a serial dependence runs on all lanes: 1/h_i, the right-hand side G_i (kept in
+  // c[i+1] until the forward sweep overwrites it), the division by alpha_i and the interval records
+  for (int i = lane; i < n - 1; i += 32) {
+    const double h = x[i + 1] - x[i];
+    ih[i] = (h != 0.0) ? 1.0 / h : 0.0;
+  }
+  __syncwarp();
+  for (int i = lane; i < N; i += 32) c[i + 1] = 3.0 * ((y[i + 2] - y[i + 1]) * ih[i + 1] - (y[i + 1] - y[i]) * ih[i]);
+  if (lane == 0) { c[0] = 0.0; c[n - 1] = 0.0; }
+  __syncwarp();
+  if (N == 1) {
+    if (lane == 0) c[1] = c[1] / (2.0 * ((x[2] - x[1]) + (x[1] - x[0])));
+  } else {
+    if (lane == 0) {
       tridiag_factor(x, n, alpha, gamma);
-      double z = G(0);
-      c[1] = z / alpha[0];
-      for (int i = 1; i < N; ++i) {
-        z = G(i) - gamma[i - 1] * z;
-        c[i + 1] = z / alpha[i];
+      double z = c[1];
+      for (int i = 1; i < N; ++i) {  // z_i = G_i - gamma_{i-1} z_{i-1}
+        z = c[i + 1] - gamma[i - 1] * z;
+        c[i + 1] = z;
       }
-      for (int i = N - 2; i >= 0; --i) c[i + 1] = c[i + 1] - gamma[i] * c[i + 2];
     }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) c[i + 1] = c[i + 1] / alpha[i];
+    __syncwarp();
+    if (lane == 0)
+      for (int i = N - 2; i >= 0; --i) c[i + 1] = c[i + 1] - gamma[i] * c[i + 2];
   }
   __syncwarp();
   for (int i = lane; i < n - 1; i += 32) {
@@ -280,44 +324,46 @@ __global__ void cspline_coef_kernel(const CsplineJob* jobs, int njobs) {
   }
 }
 
-// bicubic_init (interp2d/bicubic.c).  Pass 0: tridiagonal factors of both axes + copy z.
+// bicubic_init (interp2d/bicubic.c).  Pass 0: axis factors (once per distinct pair of grids) + copy z.
 __global__ void bicubic_factor_kernel(const BicubicJob* jobs) {
   const BicubicJob jb = jobs[blockIdx.x];
-  double* ak = jb.scratch;
-  double* gk = ak + jb.nk;
-  double* aa = gk + jb.nk;
-  double* ga = aa + jb.na;
-  if (threadIdx.x == 0) tridiag_factor(jb.xk, jb.nk, ak, gk);
-  if (threadIdx.x == 32) tridiag_factor(jb.ya, jb.na, aa, ga);
-  const int nn = jb.nk * jb.na;
+  const int nk = jb.nk, na = jb.na;
+  const int nn = nk * na;
   for (int i = threadIdx.x; i < nn; i += blockDim.x) jb.tab[i].x = jb.z[i];
+  if (!jb.factor) return;
+  double* sk = jb.scratch;
+  double* sa = jb.scratch + 4 * nk;
+  if (threadIdx.x == 0) tridiag_factor(jb.xk, nk, sk, sk + nk);
+  if (threadIdx.x == 32) tridiag_factor(jb.ya, na, sa, sa + na);
+  auto invh = [](const double* x, int i) {
+    const double h = x[i + 1] - x[i];
+    return (h != 0.0) ? 1.0 / h : 0.0;
+  };
+  for (int i = threadIdx.x; i < nk - 1; i += blockDim.x) sk[2 * nk + i] = invh(jb.xk, i);
+  for (int i = threadIdx.x; i < na - 1; i += blockDim.x) sa[2 * na + i] = invh(jb.ya, i);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nk - 2; i += blockDim.x) sk[3 * nk + i] = 1.0 / sk[i];
+  for (int i = threadIdx.x; i < na - 2; i += blockDim.x) sa[3 * na + i] = 1.0 / sa[i];
 }
 
-// Pass 1: zx (rows, spline along ln k) and zy (columns, spline along a).
-// Pass 2: zxy = d/dx of the zy plane (rows).
+// Pass 1: zy (columns, spline along a).  Pass 2: zx and zxy = d/dx of the z and zy planes (rows, spline
+// along ln k; one thread carries both planes of its row through the same sweeps).
 __global__ void bicubic_deriv_kernel(const BicubicJob* jobs, int pass) {
   const BicubicJob jb = jobs[blockIdx.y];
   const int nk = jb.nk, na = jb.na;
-  const double* ak = jb.scratch;
-  const double* gk = ak + nk;
-  const double* aa = gk + nk;
-  const double* ga = aa + na;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   double* tab = reinterpret_cast<double*>(jb.tab);
   if (pass == 1) {
-    if (t < na) {
-      // row t: y = z[t][*] (slot .x), out = zx (slot .y)
-      double* row = tab + (size_t)t * nk * 4;
-      natural_spline_node_derivs(jb.xk, nk, row + 0, 4, row + 1, 4, ak, gk);
-    } else if (t < na + nk) {
-      const int ik = t - na;
-      double* col = tab + (size_t)ik * 4;
-      natural_spline_node_derivs(jb.ya, na, col + 0, (size_t)nk * 4, col + 2, (size_t)nk * 4, aa, ga);
+    if (t < nk) {
+      const int yoff[1] = {0}, ooff[1] = {2};
+      natural_spline_node_derivs<1>(jb.ya, na, tab + (size_t)t * 4, (size_t)nk * 4, yoff, ooff,
+                                    axis_factors(jb.scratch + 4 * nk, na));
     }
   } else {
     if (t < na) {
-      double* row = tab + (size_t)t * nk * 4;
-      natural_spline_node_derivs(jb.xk, nk, row + 2, 4, row + 3, 4, ak, gk);
+      const int yoff[2] = {0, 2}, ooff[2] = {1, 3};
+      natural_spline_node_derivs<2>(jb.xk, nk, tab + (size_t)t * nk * 4, 4, yoff, ooff,
+                                    axis_factors(jb.scratch, nk));
     }
   }
 }
@@ -329,7 +375,7 @@ void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs,
   if (nlut > 0) lut_kernel<<<nlut, 128, 0, stream>>>(d_lut);
   if (nax > 0) axis_kernel<<<nax, 128, 0, stream>>>(d_ax);
   if (ncs > 0) {
-    const size_t csm = sizeof(double) * 5 * (size_t)max_ncs;
+    const size_t csm = sizeof(double) * 6 * (size_t)max_ncs;
     if (csm <= 200 * 1024) {
       if (csm > 48 * 1024)
         cudaFuncSetAttribute(cspline_coef_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
@@ -339,9 +385,9 @@ void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs,
   }
   if (nbc > 0) {
     bicubic_factor_kernel<<<nbc, 256, 0, stream>>>(d_bc);
-    dim3 g1((max_na + max_nk + 63) / 64, nbc), g2((max_na + 63) / 64, nbc);
+    dim3 g1((max_nk + 63) / 64, nbc), g2((max_na + 31) / 32, nbc);
     bicubic_deriv_kernel<<<g1, 64, 0, stream>>>(d_bc, 1);
-    bicubic_deriv_kernel<<<g2, 64, 0, stream>>>(d_bc, 2);
+    bicubic_deriv_kernel<<<g2, 32, 0, stream>>>(d_bc, 2);
   }
 }
 

@@ -163,8 +163,9 @@ struct BicubicJob {
   const double* ya;  // [na]
   const double* z;   // [na*nk]
   double4* tab;      // [na*nk]
-  double* scratch;   // [2*(nk+na)] alpha/gamma of both axes
+  double* scratch;   // [4*(nk+na)] alpha, gamma, 1/h, 1/alpha of both axes (shared by jobs on the same grids)
   int nk, na;
+  int factor;        // this job computes the axis factors (the first job of each distinct grid pair)
 };
 
 // launchers (kernels.cu)
