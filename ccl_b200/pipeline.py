@@ -84,6 +84,8 @@ def pin_stacked(stk):
 
 
 class PipelinedBatch:
+    NSTAGE = 2   # host threads planning/staging chunks concurrently
+
     def __init__(self, ncosmo, nchunks=8, params=None):
         self.ncosmo = int(ncosmo)
         self.nchunks = max(1, min(int(nchunks), self.ncosmo))
@@ -114,7 +116,7 @@ class PipelinedBatch:
             out = np.empty(shape)
         assert out.shape == shape and out.dtype == np.float64 and out.flags.c_contiguous
         stat = np.zeros((self.ncosmo, len(pairs)), dtype=np.int32)
-        staged, ready = queue.Queue(), queue.Queue()
+        ready = queue.Queue()
         errors = []
         trace = self.trace
 
@@ -126,35 +128,45 @@ class PipelinedBatch:
             trace.append((name, c, t0, time.perf_counter()))
             return r
 
-        def stage():
+        nchunks = len(self.spans)
+        staged = [threading.Event() for _ in range(nchunks)]
+        failed = threading.Event()
+
+        def stage(first):
+            # planning is serial host work per chunk: NSTAGE threads take alternate chunks
             try:
-                for c, (off, cnt) in enumerate(self.spans):
+                for c in range(first, nchunks, self.NSTAGE):
+                    if failed.is_set():
+                        break
+                    off, cnt = self.spans[c]
                     b = self.batches[c]
                     b.reset()
                     timed("stage", c, b.set_stacked, 0, slice_stacked(stk, off, off + cnt))
-                    staged.put(c)
+                    staged[c].set()
             except BaseException as e:  # noqa: BLE001 -- re-raised on the caller's thread
                 errors.append(e)
-            finally:
-                staged.put(None)
+                failed.set()
+                for ev in staged:
+                    ev.set()
 
         def commit():
             try:
-                while True:
-                    c = staged.get()
-                    if c is None:
+                for c in range(nchunks):
+                    staged[c].wait()
+                    if failed.is_set():
                         break
                     timed("commit", c, self.batches[c].commit)
                     ready.put(c)
             except BaseException as e:  # noqa: BLE001
                 errors.append(e)
+                failed.set()
             finally:
                 ready.put(None)
 
-        t1 = threading.Thread(target=stage, daemon=True)
-        t2 = threading.Thread(target=commit, daemon=True)
-        t1.start()
-        t2.start()
+        threads = [threading.Thread(target=stage, args=(k,), daemon=True) for k in range(self.NSTAGE)]
+        threads.append(threading.Thread(target=commit, daemon=True))
+        for t in threads:
+            t.start()
         worst = 0
         while True:
             c = ready.get()
@@ -165,8 +177,8 @@ class PipelinedBatch:
                                out=out[off:off + cnt])
             stat[off:off + cnt] = s_c
             worst = worst or st
-        t1.join()
-        t2.join()
+        for t in threads:
+            t.join()
         if errors:
             raise errors[0]
         return out, stat, worst
