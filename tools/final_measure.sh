@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round-end measurement batch on one B200 (run through gpurun); outputs under gpurun_out/.
+# usage: bash tools/final_measure.sh [tag]
+TAG=${1:-final}
+O=gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > $O/pytest_gpu_$TAG.txt; cat $O/pytest_gpu_$TAG.txt
+python __graft_entry__.py --smoke > $O/smoke_$TAG.txt 2>&1; tail -2 $O/smoke_$TAG.txt
+python bench.py --steps 5 --warmup 3 --from-parameters 4096 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; cut -c1-400 $O/bench_$TAG.json
+python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$TAG.json 2> $O/bench_ref_$TAG.err; cut -c1-300 $O/bench_ref_$TAG.json
+python bench.py --steps 3 --warmup 3 --method qag_quad --ncosmo 64 --no-e2e > $O/bench_qag_$TAG.json 2> $O/bench_qag_$TAG.err; cut -c1-300 $O/bench_qag_$TAG.json
+bash tools/ncu_traffic.sh 4096 | tail -1
+ncu --set full --clock-control none --import-source on -k regex:limber_spline_fast -c 1 -f -o $O/prof_$TAG \
+    python bench.py --ncosmo 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/ncu_$TAG.log 2>&1; echo ncu-full rc=$?
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
+    python bench.py --ncosmo 512 --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_launches_$TAG.log 2>&1; echo ncu-launches rc=$?
