@@ -167,7 +167,10 @@ int ccl_b200_batch_add_tracer(ccl_b200_batch *b, int icosmo, int der_bessel, int
  * carry a leading cosmology axis ([count][n] row-major); abscissa arrays have a stride between
  * consecutive cosmologies, 0 meaning one grid shared by all.  Same per-slot semantics as the
  * single-slot setters above (and as ccl_cl_tracer_t_new / set_pk2d_new_from_arrays); the copies into
- * the pinned staging arena run on several host threads. */
+ * the pinned staging arena run on several host threads.  A stacked array that lives in page-locked
+ * host memory (cudaHostAlloc / cudaHostRegister) is not staged: ccl_b200_batch_commit copies it with
+ * one DMA straight from the caller's buffer, which must then stay valid and unchanged until commit
+ * returns (pageable arrays are only borrowed for the call, like every other input). */
 void ccl_b200_batch_set_achi_stacked(ccl_b200_batch *b, int first, int count, const int *n_per /* NULL: stride */,
                                      int stride, const double *chi, const double *a, int *status);
 void ccl_b200_batch_set_growth_stacked(ccl_b200_batch *b, int first, int count, int n, int stride_a,
