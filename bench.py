@@ -240,7 +240,7 @@ def _main(json_out):
     ap.add_argument("--e2e-trace", action="store_true", help="print the per-chunk stage timeline of one e2e step to stderr")
     ap.add_argument("--e2e-pageable", action="store_true",
                     help="keep the e2e input tables in pageable host memory (staged through pinned arenas by host threads)")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="cosmology chunks of the pipelined host-buffer entry")
+    ap.add_argument("--e2e-chunks", type=int, default=None, help="cosmology chunks of the pipelined host-buffer entry")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -86,13 +86,17 @@ def pin_stacked(stk):
 class PipelinedBatch:
     NSTAGE = 2   # host threads planning/staging chunks concurrently
 
-    def __init__(self, ncosmo, nchunks=8, params=None):
+    def __init__(self, ncosmo, nchunks=None, params=None):
         self.ncosmo = int(ncosmo)
+        if nchunks is None:
+            # regular chunks of >= 256 cosmologies (fewer Limber CTAs than ~60 waves cost tail time and
+            # every chunk costs ~1 ms of launches and synchronisation), at most 8 of them
+            nchunks = max(1, min(8, self.ncosmo // 256))
         self.nchunks = max(1, min(int(nchunks), self.ncosmo))
-        # chunk sizes ramp up (x1.5 from a quarter of the regular size): the first chunk reaches the
-        # SMs after a quarter of the regular stage + upload time, later chunks amortise launch overheads
+        # chunk sizes ramp up (x1.5 from a quarter of the regular size, not below 64): the first chunk
+        # reaches the SMs after a fraction of the regular stage + upload time
         base = -(-self.ncosmo // self.nchunks)
-        sizes, size, rem = [], max(1, base // 4), self.ncosmo
+        sizes, size, rem = [], max(1, base // 4, min(64, base)), self.ncosmo
         while rem > 0:
             take = min(size, base, rem)
             sizes.append(take)
