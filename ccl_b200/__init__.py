@@ -10,7 +10,7 @@ from .lowlevel import (CCLB200Error, LibBatch, LibCosmology, LibF2D, LibTracer, 
 from .cells import angular_cl  # noqa: F401,E402
 from .cosmology import Cosmology, CosmologyCalculator, CosmologyVanillaLCDM  # noqa: F401,E402
 from .errors import CCLError, CCLWarning, update_warning_verbosity  # noqa: F401,E402
-from .parameters import gsl_params, physical_constants, spline_params  # noqa: F401,E402
+from .parameters import DEFAULT_POWER_SPECTRUM, gsl_params, physical_constants, spline_params  # noqa: F401,E402
 from .pipeline import PipelinedBatch, pin_stacked, slice_stacked  # noqa: F401,E402
 from .pk2d import Pk2D, parse_pk2d  # noqa: F401,E402
 from .tracers import (CMBLensingTracer, ISWTracer, NumberCountsTracer, NzTracer, Tracer,  # noqa: F401,E402

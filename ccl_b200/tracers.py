@@ -55,7 +55,12 @@ def _lensing_prefactor(cosmo):
 
 
 def _nz_norm(cosmo, z, n):
-    """get_nz_norm (src/ccl_tracers.c:60-119)."""
+    """get_nz_norm (src/ccl_tracers.c:60-119).  Returned as a numpy scalar: an identically zero n(z)
+    gives 1/0 = inf and NaN kernels downstream, like the C arithmetic, not a Python exception."""
+    return np.float64(_nz_norm_value(cosmo, z, n))
+
+
+def _nz_norm_value(cosmo, z, n):
     if cosmo._gsl_params["NZ_NORM_SPLINE_INTEGRATION"]:
         return float(Akima(z, n).integrate_nodes())
     f = F1D(z, n)
@@ -72,9 +77,11 @@ def get_density_kernel(cosmo, *, dndz):
     chi = cosmo.comoving_radial_distance(1. / (1. + z_n))
     a = 1. / (1 + z_n)
     hz = cosmo["h"] * cosmo.h_over_h0(a) / physical_constants.CLIGHT_HMPC
-    return chi, hz * n * (1. / _nz_norm(cosmo, z_n, n))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return chi, hz * n * (1. / _nz_norm(cosmo, z_n, n))
 
 
+@np.errstate(divide='ignore', invalid='ignore')   # an identically zero n(z): inf / NaN like the C code
 def get_lensing_kernel(cosmo, *, dndz, mag_bias=None, n_chi=None):
     """chi, W_L(chi) (pyccl/tracers.py:114-172; ccl_get_lensing_mag_kernel, src/ccl_tracers.c:485-550)."""
     cosmo.compute_distances()

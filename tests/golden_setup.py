@@ -92,8 +92,8 @@ def set_up(nztyp):
     return _cache[nztyp]
 
 
-def oracle_objects(cosmo, trc):
-    """Oracle twins of the API objects (same flat tables)."""
+def oracle_objects(cosmo, trc, pk=None):
+    """Oracle twins of the API objects (same flat tables); `pk`: a Pk2D instead of the cosmology's own."""
     import oracle
     from common import oracle_tracer
     bg = cosmo._bg
@@ -102,7 +102,8 @@ def oracle_objects(cosmo, trc):
     oc = oracle.Cosmo(bg.achi_chi, bg.achi_a, bg.a, bg.growth, K_MAX=sp["K_MAX"], K_MIN=sp["K_MIN"],
                       DLOGK=sp["DLOGK_INTEGRATION"], LIMBER_EPSREL=gp["INTEGRATION_LIMBER_EPSREL"],
                       N_ITERATION=gp["N_ITERATION"])
-    pk = cosmo.get_nonlin_power()
+    if pk is None:
+        pk = cosmo.get_nonlin_power()
     op = oracle.F2D(a=pk._a, lk=pk._lk, fka=pk._tab, is_factorizable=False, extrap_order_lok=pk.extrap_order_lok,
                     extrap_order_hik=pk.extrap_order_hik, extrap_linear_growth=oracle.F2D_CCLGROWTH,
                     is_log=pk.is_logp, growth_factor_0=0.0, growth_exponent=2)

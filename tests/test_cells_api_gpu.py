@@ -1,0 +1,119 @@
+"""The reference's own unit tests of the path (pyccl/tests/test_cells.py, Limber cases), run against
+the pyccl-compatible API of this package on the GPU; every curve is also checked against the oracle.
+
+  test_cells_smoke               pyccl/tests/test_cells.py:25-81   six tracer flavours x four ell forms x
+                                                                    three p_of_k_a forms, symmetry, invalid dndz
+  test_cells_raise_ell_reversed  :84-87
+  test_cells_raise_integ_method  :90-101
+  test_cells_raise_nonlimber     :104-120 (Limber-only build: unknown method names still raise)
+  test_cells_raise_weird_pk      :123-126
+  test_cells_calculator          :380-409 without modified gravity: a Calculator fed the P(k,a) arrays of
+                                  another cosmology returns the same C_ell to 1e-10
+"""
+import numpy as np
+import pytest
+
+import oracle
+from common import parity_error
+from golden_setup import oracle_objects
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import ccl_b200 as ccl
+    cosmo = ccl.Cosmology(Omega_c=0.27, Omega_b=0.045, h=0.67, sigma8=0.8, n_s=0.96,
+                          transfer_function="bbks", matter_power_spectrum="linear")
+    zz = np.linspace(0.0, 1.0, 200)
+    nn = np.exp(-(((zz - 0.5) / 0.1) ** 2))
+    lens = ccl.WeakLensingTracer(cosmo, dndz=(zz, nn))
+    pka = ccl.Pk2D.from_function(pkfunc=lambda k, a: np.log(a / k))
+    return dict(ccl=ccl, cosmo=cosmo, zz=zz, nn=nn, lens=lens, pka=pka)
+
+
+@pytest.mark.parametrize("p_of_k_a", ["default", "pk2d", None])
+def test_cells_smoke(env, p_of_k_a):
+    ccl, cosmo = env["ccl"], env["cosmo"]
+    pk = {"default": ccl.DEFAULT_POWER_SPECTRUM, "pk2d": env["pka"], None: None}[p_of_k_a]
+    z = np.linspace(0.0, 1.0, 200)
+    n = np.exp(-(((z - 0.5) / 0.1) ** 2))
+    b = np.sqrt(1.0 + z)
+    lens1 = ccl.WeakLensingTracer(cosmo, dndz=(z, n))
+    lens2 = ccl.WeakLensingTracer(cosmo, dndz=(z, n), ia_bias=(z, n))
+    nc1 = ccl.NumberCountsTracer(cosmo, has_rsd=False, dndz=(z, n), bias=(z, b))
+    nc2 = ccl.NumberCountsTracer(cosmo, has_rsd=True, dndz=(z, n), bias=(z, b))
+    nc3 = ccl.NumberCountsTracer(cosmo, has_rsd=True, dndz=(z, n), bias=(z, b), mag_bias=(z, b))
+    cmbl = ccl.CMBLensingTracer(cosmo, z_source=1100.0)
+    tracers = [lens1, lens2, nc1, nc2, nc3, cmbl]
+    ells = [4, 4.0, [2, 3, 4, 5], np.arange(2, 5)]
+    kw = {} if pk is None else {"p_of_k_a": pk}
+    # the oracle on the same host tables (the explicit Pk2D has its own table)
+    pk_obj = env["pka"] if p_of_k_a == "pk2d" else None
+    oc, op, otr = oracle_objects(cosmo, dict(enumerate(tracers)), pk=pk_obj)
+    ell_chk = np.array([2., 3., 4., 5.])
+    for i in range(len(tracers)):
+        for j in range(i, len(tracers)):
+            for ell in ells:
+                corr = ccl.angular_cl(cosmo, tracers[i], tracers[j], ell, **kw)
+                assert np.all(np.isfinite(corr))
+                assert np.shape(corr) == np.shape(ell)
+                corr_rev = ccl.angular_cl(cosmo, tracers[j], tracers[i], ell, **kw)
+                assert np.allclose(corr, corr_rev)
+            # default method (qag_quad) and 'spline' against the oracle
+            cq = ccl.angular_cl(cosmo, tracers[i], tracers[j], ell_chk, **kw)
+            rq = oracle.angular_cl(oc, otr[i], otr[j], op, ell_chk, oracle.INTEG_QAG)[0]
+            assert parity_error(cq, rq, None, 1e-5) < 1e-5, (i, j)
+            cs = ccl.angular_cl(cosmo, tracers[i], tracers[j], ell_chk, limber_integration_method="spline", **kw)
+            redo = lambda: oracle.angular_cl(oc, otr[i], otr[j], op, ell_chk, oracle.INTEG_SPLINE)[0]  # noqa: E731
+            assert parity_error(cs, redo(), redo, 1e-10) < 1e-10, (i, j)
+    # invalid dndz
+    for bad in (z, (z, n, n), (z,), (1, 2)):
+        with pytest.raises(ValueError):
+            ccl.NumberCountsTracer(cosmo, has_rsd=False, dndz=bad, bias=(z, b))
+        with pytest.raises(ValueError):
+            ccl.WeakLensingTracer(cosmo, dndz=bad)
+
+
+@pytest.mark.parametrize("ells", [[3, 2, 1], [1, 3, 2], [2, 3, 1]])
+def test_cells_raise_ell_reversed(env, ells):
+    with pytest.raises(ValueError):
+        env["ccl"].angular_cl(env["cosmo"], env["lens"], env["lens"], ells)
+
+
+def test_cells_raise_integ_method(env):
+    ccl, cosmo, lens = env["ccl"], env["cosmo"], env["lens"]
+    with pytest.raises(ValueError):
+        ccl.angular_cl(cosmo, lens, lens, [10, 11], limber_integration_method="guad")
+    with pytest.raises(ValueError):
+        lens2 = ccl.WeakLensingTracer(cosmo, dndz=(env["zz"], np.zeros(len(env["zz"]))))
+        ccl.angular_cl(cosmo, lens, lens2, [10, 11], limber_integration_method="quad")
+
+
+def test_cells_raise_nonlimber(env):
+    ccl, cosmo, lens = env["ccl"], env["cosmo"], env["lens"]
+    with pytest.raises(ValueError):
+        ccl.angular_cl(cosmo, lens, lens, [10, 11], non_limber_integration_method="FEKM")
+    with pytest.raises(ValueError):
+        ccl.angular_cl(cosmo, lens, lens, [10, 11], l_limber="auoto", non_limber_integration_method="FKEM")
+
+
+def test_cells_raise_weird_pk(env):
+    with pytest.raises(ValueError):
+        env["ccl"].angular_cl(env["cosmo"], env["lens"], env["lens"], [10, 11], p_of_k_a=lambda k, a: 10)
+
+
+def test_cells_calculator(env):
+    ccl = env["ccl"]
+    cosmo = ccl.CosmologyVanillaLCDM(transfer_function="bbks", matter_power_spectrum="linear")
+    cosmo.compute_nonlin_power()
+    a, lk, pk = cosmo.get_nonlin_power().get_spline_arrays()
+    calc = ccl.CosmologyCalculator(Omega_c=0.25, Omega_b=0.05, h=0.67, n_s=0.96, sigma8=0.81,
+                                   pk_nonlin={"a": a, "k": np.exp(lk), "delta_matter:delta_matter": pk})
+    ell = np.geomspace(2, 2000, 128)
+    tr0 = ccl.CMBLensingTracer(cosmo, z_source=1100.0)
+    tr1 = ccl.CMBLensingTracer(calc, z_source=1100.0)
+    cl0 = ccl.angular_cl(cosmo, tr0, tr0, ell)
+    calc.compute_growth()
+    cl1 = ccl.angular_cl(calc, tr1, tr1, ell)
+    assert np.all(np.fabs(1 - cl1 / cl0) < 1e-10)
