@@ -589,38 +589,61 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
   double* lk = sm;
   double* row = lk + nk;
   double* cc = row + nk;
-  double* tmp = cc + nk;   // forward-sweep scratch, then the b coefficients
+  double* tmp = cc + nk;   // right-hand side of the spline system, then the b coefficients
   double* dco = tmp + nk;  // d coefficients
+  double* alpha = dco + nk;  // LDL^T factors of the natural-spline system of the ln k grid: the same
+  double* gamma = alpha + nk;  // for every scale factor of the group, computed once per CTA
   __shared__ double red[3][256];
   __shared__ double glx[16], glw[16];  // lane-varying node index: shared memory, not the constant cache
   if (threadIdx.x < 16) { glx[threadIdx.x] = GL16_X[threadIdx.x]; glw[threadIdx.x] = GL16_W[threadIdx.x]; }
   const int ic = blockIdx.x;
   const double* p = params + (size_t)ic * CCL_B200_NPAR;
-  // a CTA walks HF_GROUP consecutive scale factors; each root search starts from the previous root
-  double x = log(1.0);
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) lk[i] = lk_grid[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {  // gsl solve_tridiag (linalg/tridiag.c): alpha_i, gamma_i of diag 2(h_i + h_{i+1}), offdiag h_{i+1}
+    const int N = nk - 2;
+    auto hh = [&](int i) { return lk[i + 1] - lk[i]; };
+    alpha[0] = 2.0 * (hh(0) + hh(1));
+    gamma[0] = hh(1) / alpha[0];
+    for (int i = 1; i < N; ++i) {
+      alpha[i] = 2.0 * (hh(i) + hh(i + 1)) - hh(i) * gamma[i - 1];
+      gamma[i] = hh(i + 1) / alpha[i];
+    }
+  }
+  // a CTA walks HF_GROUP consecutive scale factors; each root search starts from the linear
+  // extrapolation of the previous two roots (ln R_sigma is smooth in a)
+  double x = log(1.0), x_prev = 0.0, a_prev = 0.0, a_prev2 = 0.0, x_prev2 = 0.0;
+  int nroots = 0;
   for (int ia = blockIdx.y * HF_GROUP; ia < min(na, (int)(blockIdx.y + 1) * HF_GROUP); ++ia) {
   const double* src = logplin + ((size_t)ic * na + ia) * nk;
+  if (nroots >= 2) x = x_prev + (x_prev - x_prev2) * (a_grid[ia] - a_prev) / (a_prev - a_prev2);
   __syncthreads();
-  for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-    lk[i] = lk_grid[i];
-    row[i] = src[i];
-  }
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) row[i] = src[i];
   __syncthreads();
-  if (threadIdx.x == 0) {
+  {
+    // natural cubic spline of the row (gsl cspline_init): everything without a serial dependence runs
+    // on all threads; thread 0 only carries the two first-order recurrences (one FMA per node each)
     const int N = nk - 2;
-    cc[0] = 0.0;
-    cc[nk - 1] = 0.0;
-    auto hh = [&](int i) { return lk[i + 1] - lk[i]; };
-    auto g = [&](int i) { return 3.0 * ((row[i + 2] - row[i + 1]) / hh(i + 1) - (row[i + 1] - row[i]) / hh(i)); };
-    double beta = 2.0 * (hh(0) + hh(1));
-    tmp[0] = hh(1) / beta;
-    cc[1] = g(0) / beta;
-    for (int i = 1; i < N; ++i) {
-      beta = 2.0 * (hh(i) + hh(i + 1)) - hh(i) * tmp[i - 1];
-      tmp[i] = hh(i + 1) / beta;
-      cc[i + 1] = (g(i) - hh(i) * cc[i]) / beta;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const double h0 = lk[i + 1] - lk[i], h1 = lk[i + 2] - lk[i + 1];
+      tmp[i] = 3.0 * ((row[i + 2] - row[i + 1]) / h1 - (row[i + 1] - row[i]) / h0);
     }
-    for (int i = N - 2; i >= 0; --i) cc[i + 1] -= tmp[i] * cc[i + 2];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      cc[0] = 0.0;
+      cc[nk - 1] = 0.0;
+      double z = tmp[0];
+      cc[1] = z;
+      for (int i = 1; i < N; ++i) {
+        z = tmp[i] - gamma[i - 1] * z;
+        cc[i + 1] = z;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) cc[i + 1] = cc[i + 1] / alpha[i];
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int i = N - 2; i >= 0; --i) cc[i + 1] -= gamma[i] * cc[i + 2];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nk - 1; i += blockDim.x) {  // per-interval b and d (gsl cspline coeff_calc)
@@ -659,13 +682,20 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
     const int npanel = (int)(400 * fmax(1.0, (lnkmax - lnkmin) / 25.0));
     const double step = (lnkmax - lnkmin) / npanel;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int t = threadIdx.x; t < npanel * 16; t += blockDim.x) {
-      const int j = t >> 4, q = t & 15;
+    // a thread keeps its Gauss-Legendre index q (blockDim is a multiple of 16) and visits every
+    // (blockDim/16)-th panel: k = exp(panel start) * exp(offset of node q) advances by a constant ratio,
+    // so the node's exp(ln k) costs one multiplication
+    const int q = threadIdx.x & 15, jstride = blockDim.x >> 4;
+    const double gx = glx[q], gw = glw[q];
+    const double fq = exp(0.5 * step * (1.0 + gx));
+    const double eratio = exp(step * jstride);
+    double ej = exp(lnkmin + (threadIdx.x >> 4) * step);
+    for (int j = threadIdx.x >> 4; j < npanel; j += jstride, ej *= eratio) {
       const double e0 = lnkmin + j * step, e1 = (j == npanel - 1) ? lnkmax : lnkmin + (j + 1) * step;
       const double mid = 0.5 * (e1 + e0), half = 0.5 * (e1 - e0);
-      const double x = mid + half * glx[q];
-      const double kk = exp(x), k2 = kk * kk;
-      const double base = half * glw[q] * plin(x) * kk * k2 * (0.5 / (M_PI * M_PI)) * exp(-k2 * R * R);
+      const double x = mid + half * gx;
+      const double kk = ej * fq, k2 = kk * kk;
+      const double base = half * gw * plin(x) * kk * k2 * (0.5 / (M_PI * M_PI)) * exp(-k2 * R * R);
       a0 += base;
       a1 += base * (-k2 * 2.0 * R);
       a2 += base * (-2.0 * k2 + 4.0 * k2 * k2 * R * R);
@@ -699,7 +729,13 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
     const double f = log(m0);
     if (f > 0) { lo = x; have_lo = true; } else if (f < 0) { hi = x; have_hi = true; }
     if (f == 0.0) { ok = true; break; }
-    double step = -f / (R * m1 / m0);                     // Newton on ln sigma^2
+    // Halley step on ln sigma^2(ln R): f' = R m1 / m0, f'' = f' + R^2 m2 / m0 - f'^2 (falls back to Newton
+    // when the correction is not a modest one)
+    const double f1 = R * m1 / m0;
+    const double f2 = f1 + R * R * m2 / m0 - f1 * f1;
+    double den = f1 - 0.5 * f * f2 / f1;
+    if (!(den * f1 > 0.25 * f1 * f1)) den = f1;
+    double step = -f / den;
     if (!(fabs(step) <= 8.0)) step = (f > 0) ? 8.0 : -8.0;   // also catches NaN / zero slope
     double xn = x + step;
     if (have_lo && have_hi) {
@@ -718,9 +754,13 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
     if (threadIdx.x == 0) { rsigma_out[oidx] = -1.0; atomicExch(fail, 1); }
     for (int i = threadIdx.x; i < nk; i += blockDim.x) logpnl[oidx * nk + i] = nan("");
     x = log(1.0);
+    nroots = 0;
     continue;
   }
   const double R = exp(x);
+  x_prev2 = x_prev; a_prev2 = a_prev;
+  x_prev = x; a_prev = a_grid[ia];
+  ++nroots;
   const double sigma2 = m0;
   const double neff = -R / sigma2 * m1 - 3.0;
   const double ds = (neff + 3.0) / (-R / sigma2);
@@ -770,7 +810,7 @@ void launch_build_halofit(int ncosmo, int nk, const double* d_lk, int na, const 
                           const double* d_params, double* d_logpnl, double* d_rsigma, int* d_fail,
                           cudaStream_t stream) {
   if (ncosmo <= 0) return;
-  const size_t smem = sizeof(double) * 5 * (size_t)nk;
+  const size_t smem = sizeof(double) * 7 * (size_t)nk;
   if (smem + (3 * 256 + 32) * sizeof(double) > 48 * 1024)  // dynamic + the static buffers
     cudaFuncSetAttribute(halofit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ncosmo, (na + HF_GROUP - 1) / HF_GROUP);

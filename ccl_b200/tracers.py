@@ -175,6 +175,21 @@ def _chi_range(sub, chi_max_nokernel):
     return float(lo), float(hi)
 
 
+class SubTracer(dict):
+    """One sub-tracer: the keyword arguments of lowlevel.LibTracer (= ccl_cl_tracer_t_new), with the
+    fields of the reference's C struct readable as attributes (include/ccl_tracers.h:15-22)."""
+    chi_min = 0.0
+    chi_max = 1e15
+
+    @property
+    def der_bessel(self):
+        return self.get("der_bessel", 0)
+
+    @property
+    def der_angles(self):
+        return self.get("der_angles", 0)
+
+
 class Tracer:
     """Container of sub-tracers (pyccl/tracers.py:199-828, hot-path subset)."""
 
@@ -184,6 +199,7 @@ class Tracer:
         self.avg_weighted_a = []
         self._dev_key = None
         self._dev_objs = None
+        self._cosmo = None      # the cosmology the sub-tracers were built with
 
     def __bool__(self):
         return bool(self._trc)
@@ -209,8 +225,8 @@ class Tracer:
         is_k_constant = (transfer_ka is None) and (transfer_k is None)
         is_a_constant = (transfer_ka is None) and (transfer_a is None)
         chi_s, wchi_s = _check_array_params(kernel, 'kernel')
-        sub = dict(der_bessel=int(der_bessel), der_angles=int(der_angles), is_logt=bool(is_logt),
-                   extrap_order_lok=int(extrap_order_lok), extrap_order_hik=int(extrap_order_hik))
+        sub = SubTracer(der_bessel=int(der_bessel), der_angles=int(der_angles), is_logt=bool(is_logt),
+                        extrap_order_lok=int(extrap_order_lok), extrap_order_hik=int(extrap_order_hik))
         a_s = None
         if is_factorizable:
             a_s, ta_s = _check_array_params(transfer_a, 'transfer_a')
@@ -244,7 +260,9 @@ class Tracer:
             raise CCLError("Error CCL_ERROR_MEMORY: tracer kernels are Akima splines and need >= 5 nodes")
         self._trc.append(sub)
         self._chi_range.append(_chi_range(sub, cosmo.chi_max_nokernel()))
+        sub.chi_min, sub.chi_max = self._chi_range[-1]
         self._dev_objs = None
+        self._cosmo = cosmo
         # kernel-weighted mean scale factor (pyccl/tracers.py:755-766)
         if chi_s is None:
             self.avg_weighted_a.append(1.0)
@@ -263,26 +281,46 @@ class Tracer:
             self._dev_key = dev
         return self._dev_objs
 
-    def _need_cosmo(self):
-        if self._dev_objs is None:
-            raise CCLError("tracer accessors run on the device: call them after the tracer was used with a "
-                           "cosmology (or pass through angular_cl first)")
-        return self._dev_objs
+    def _need_cosmo(self, cosmo=None):
+        """Device twins; without an explicit cosmology the one the sub-tracers were built with is used
+        (the reference keeps the C structs it made at add_tracer time)."""
+        if cosmo is None:
+            cosmo = self._cosmo
+        if cosmo is None:
+            return []
+        return self._device(cosmo)
 
     def get_kernel(self, chi=None, *, cosmo=None):
-        """W(chi) of every sub-tracer, evaluated on the device (ccl_cl_tracer_t_get_kernel)."""
-        objs = self._device(cosmo) if cosmo is not None else self._need_cosmo()
+        """W(chi) of every sub-tracer that has a kernel, evaluated on the device
+        (pyccl/tracers.py:331-368 -> ccl_cl_tracer_t_get_kernel); `chi=None` returns the spline nodes."""
         if chi is None:
-            return [sub.get("w") for sub in self._trc], [sub.get("chi") for sub in self._trc]
-        return np.array([o.kernel(chi) for o in objs])
+            subs = [sub for sub in self._trc if sub.get("w") is not None]
+            return [sub["w"] for sub in subs], [sub["chi"] for sub in subs]
+        objs = self._need_cosmo(cosmo)
+        kernels = np.array([o.kernel(chi) for o, sub in zip(objs, self._trc) if sub.get("w") is not None])
+        if np.ndim(chi) == 0 and kernels.shape != (0,):
+            kernels = np.squeeze(kernels, axis=-1)
+        return kernels
 
     def get_f_ell(self, ell, *, cosmo=None):
-        objs = self._device(cosmo) if cosmo is not None else self._need_cosmo()
-        return np.array([o.f_ell(ell) for o in objs])
+        """pyccl/tracers.py:370-398 -> ccl_cl_tracer_t_get_f_ell."""
+        f_ells = np.array([o.f_ell(ell) for o in self._need_cosmo(cosmo)])
+        if np.ndim(ell) == 0 and f_ells.shape != (0,):
+            f_ells = np.squeeze(f_ells, axis=-1)
+        return f_ells
 
     def get_transfer(self, lk, a, *, cosmo=None):
-        objs = self._device(cosmo) if cosmo is not None else self._need_cosmo()
-        return np.array([o.transfer(lk, a) for o in objs])
+        """pyccl/tracers.py:400-438 -> ccl_cl_tracer_t_get_transfer: shape (n_tracer, lk.size, a.size),
+        scalar inputs squeezed."""
+        transfers = np.array([o.transfer(lk, a) for o in self._need_cosmo(cosmo)])
+        if transfers.shape != (0,):
+            if np.ndim(a) == 0:
+                transfers = np.squeeze(transfers, axis=-1)
+                if np.ndim(lk) == 0:
+                    transfers = np.squeeze(transfers, axis=-1)
+            elif np.ndim(lk) == 0:
+                transfers = np.squeeze(transfers, axis=-2)
+        return transfers
 
 
 class NzTracer(Tracer):
