@@ -32,6 +32,8 @@ sys.path.insert(0, ROOT)
 NCOSMO_TOTAL = 4096
 N_DISTINCT = 8          # distinct synthetic cosmologies; slots cycle through them with a P(k) offset
 NL = 100
+REF_SAMPLE = 64         # cosmologies per step of the CPU reference arm (~2 s on 16 host threads)
+CPU_SAMPLE_S = 10.0     # seconds of CPU work of the cpu_baseline leg of the default run
 # algorithmic flops per integrand node: base + per-sub-tracer + Akima integral
 F_BASE, F_AKIMA = 81.0, 33.0
 F_SUB = {"wl": 10.0, "nc": 26.0}
@@ -174,18 +176,21 @@ def run_reference(args, rank, json_out=sys.stdout):
     import oracle
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from common import oracle_cosmo, oracle_pk, oracle_tracer
-    tables = build_host_tables(1)
-    t = tables[0]
+    tables = build_host_tables(N_DISTINCT)
     colls, pairs, ells = geometry()
-    oc, op = oracle_cosmo(t["bg"]), oracle_pk(t["pk"])
-    otr = [oracle_tracer(s, t["cmax"]) for s in t["subs"]]
+    objs = []
+    for t in tables:
+        objs.append((oracle_cosmo(t["bg"]), oracle_pk(t["pk"]), [oracle_tracer(s, t["cmax"]) for s in t["subs"]]))
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
     oracle.set_num_threads(len(os.sched_getaffinity(0)))
     cores = oracle.num_threads()
+    nsample = min(REF_SAMPLE, args.ncosmo)
 
     def one_pass():
-        for (i, j) in pairs:
-            oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, oracle.INTEG_SPLINE)
+        for ic in range(nsample):   # the batch cycles through N_DISTINCT table sets, like the GPU arm's
+            oc, op, otr = objs[ic % len(objs)]
+            for (i, j) in pairs:
+                oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, oracle.INTEG_SPLINE)
 
     for _ in range(max(args.warmup, 1)):
         one_pass()
@@ -193,9 +198,10 @@ def run_reference(args, rank, json_out=sys.stdout):
     for _ in range(args.steps):
         one_pass()
     dt = (time.perf_counter() - t0) / args.steps
-    n_cl = len(pairs) * len(ells)
+    n_cl = nsample * len(pairs) * len(ells)
     val = n_cl / dt
-    sample = "1 of 4096 cosmologies x 120 pairs x 100 ells per step ('spline'), pairs serial, OpenMP over ell"
+    sample = ("%d of %d cosmologies x 120 pairs x 100 ells per step ('spline'), pairs serial, OpenMP over ell"
+              % (nsample, args.ncosmo))
     print(json.dumps({
         "impl": "reference", "metric": "3x2pt C_ell/s (pair x ell), Limber 'spline'", "value": val,
         "unit": "C_ell/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -207,7 +213,7 @@ def run_reference(args, rank, json_out=sys.stdout):
                    "reference_impl": "oracle/ CPU restatement of src/ccl_cls.c + GSL (the GSL-based reference "
                                      "is not buildable in this image: DESIGN.md section 3)"},
         "cpu_baseline": {"value": val, "unit": "C_ell/s", "cores": cores, "kind": "port", "sample": sample,
-                         "cosmologies_per_s": 1.0 / dt},
+                         "cosmologies_per_s": nsample / dt},
         "e2e": {"value": val, "unit": "C_ell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), file=json_out)
 
@@ -472,21 +478,33 @@ def _main(json_out):
         import oracle
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from common import oracle_cosmo, oracle_pk, oracle_tracer
-        t = tables[off % len(tables)]
         oracle.set_num_threads(len(os.sched_getaffinity(0)))
-        oc, op = oracle_cosmo(t["bg"]), oracle_pk(t["pk"])
-        otr = [oracle_tracer(s, t["cmax"]) for s in t["subs"]]
-        t0 = time.perf_counter()
-        ref = np.empty((npair, nl))
-        for q, (i, j) in enumerate(pairs):
-            ref[q], _ = oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, oracle.INTEG_SPLINE)
-        dtc = time.perf_counter() - t0
-        got = d_cl[0].cpu().numpy()
-        err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
-        cpu_baseline = {"value": npair * nl / dtc, "unit": "C_ell/s", "cores": oracle.num_threads(),
-                        "kind": "port", "cosmologies_per_s": 1.0 / dtc,
-                        "sample": "1 of %d cosmologies x 120 pairs x 100 ells, 'spline', pairs serial, "
-                                  "OpenMP over ell (oracle restatement of src/ccl_cls.c)" % args.ncosmo,
+        # bounded sample: cosmologies of the batch, in slot order, until ~CPU_SAMPLE_S seconds of CPU work
+        # (the first N_DISTINCT slots are also the parity check of the GPU result)
+        integ = oracle.INTEG_SPLINE if args.method == "spline" else oracle.INTEG_QAG
+        objs = {}
+        ndone, err = 0, 0.0
+        t_cpu = 0.0
+        while ndone < nloc and t_cpu < CPU_SAMPLE_S:
+            key = (off + ndone) % len(tables)
+            if key not in objs:
+                t = tables[key]
+                objs[key] = (oracle_cosmo(t["bg"]), oracle_pk(t["pk"]), [oracle_tracer(s, t["cmax"]) for s in t["subs"]])
+            oc, op, otr = objs[key]
+            t0 = time.perf_counter()
+            ref = np.empty((npair, nl))
+            for q, (i, j) in enumerate(pairs):
+                ref[q], _ = oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, integ)
+            t_cpu += time.perf_counter() - t0
+            if (off + ndone) < len(tables):   # unshifted slots: same tables on both sides
+                got = d_cl[ndone].cpu().numpy()
+                err = max(err, float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))))
+            ndone += 1
+        cpu_baseline = {"value": ndone * npair * nl / t_cpu, "unit": "C_ell/s", "cores": oracle.num_threads(),
+                        "kind": "port", "cosmologies_per_s": ndone / t_cpu,
+                        "sample": "%d of %d cosmologies x 120 pairs x 100 ells (%.1f s of CPU work), '%s', pairs "
+                                  "serial, OpenMP over ell (oracle restatement of src/ccl_cls.c)"
+                                  % (ndone, args.ncosmo, t_cpu, args.method),
                         "max_rel_err_gpu_vs_cpu_on_sample": err}
 
     if rank == 0:
