@@ -448,7 +448,8 @@ tracer_kernel_builder(int na, const double* __restrict__ a_bg, const double* __r
                       const int* __restrict__ n_achi, int stride, const double* __restrict__ achi_chi,
                       const double* __restrict__ achi_a, const double* __restrict__ params, int nz,
                       const double* __restrict__ z, int ntr, const double* __restrict__ nz_arr,
-                      const double* __restrict__ sz_arr, const double* __restrict__ inv_norm, int nchi,
+                      const double* __restrict__ sz_arr, const double* __restrict__ inv_norm,
+                      const double* __restrict__ lens_scale, int nchi,
                       double* __restrict__ chi_z_out, double* __restrict__ w_nc, double* __restrict__ chi_l_out,
                       double* __restrict__ w_l) {
   extern __shared__ double sm[];
@@ -477,6 +478,11 @@ tracer_kernel_builder(int na, const double* __restrict__ a_bg, const double* __r
   const double z_k = (z[nz - 1] / nchi) * ik + 1E-15;
   const double ak0 = 1. / (1 + z_k);
   const double chi_end = (ak0 == 1.0) ? 0.0 : akima_eval_direct(a_bg, chi_a, na, ak0);
+  if (lens_scale && lens_scale[it] == 0.0) {  // this distribution's lensing kernel is not used (pure number counts)
+    if (it == 0) chi_l_out[(size_t)ic * nchi + ik] = chi_end;
+    w_l[((size_t)ic * ntr + it) * nchi + ik] = 0.0;
+    return;
+  }
   // ccl_scale_factor_of_chi on the freshly built a(chi) table
   const double a_k = (chi_end < 1e-8) ? 1.0
                                       : akima_eval_direct(achi_chi + (size_t)ic * stride, achi_a + (size_t)ic * stride,
@@ -559,16 +565,16 @@ tracer_kernel_builder(int na, const double* __restrict__ a_bg, const double* __r
 void launch_build_tracer_kernels(int ncosmo, int na, const double* d_abg, const double* d_chibg, const int* d_nachi,
                                  int stride, const double* d_achi_chi, const double* d_achi_a, const double* d_params,
                                  int nz, const double* d_z, int ntr, const double* d_nz, const double* d_sz,
-                                 const double* d_inv_norm, int nchi, double* d_chi_z, double* d_w_nc, double* d_chi_l,
-                                 double* d_w_l, cudaStream_t stream) {
+                                 const double* d_inv_norm, const double* d_lens_scale, int nchi, double* d_chi_z,
+                                 double* d_w_nc, double* d_chi_l, double* d_w_l, cudaStream_t stream) {
   if (ncosmo <= 0 || ntr <= 0) return;
   const size_t smem = sizeof(double) * 3 * (size_t)nz;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(tracer_kernel_builder, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ncosmo, ntr);
   tracer_kernel_builder<<<grid, 256, smem, stream>>>(na, d_abg, d_chibg, d_nachi, stride, d_achi_chi, d_achi_a,
-                                                     d_params, nz, d_z, ntr, d_nz, d_sz, d_inv_norm, nchi, d_chi_z,
-                                                     d_w_nc, d_chi_l, d_w_l);
+                                                     d_params, nz, d_z, ntr, d_nz, d_sz, d_inv_norm, d_lens_scale, nchi,
+                                                     d_chi_z, d_w_nc, d_chi_l, d_w_l);
 }
 
 // ------------------------------------------------------------------------------------------

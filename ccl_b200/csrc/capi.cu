@@ -1703,7 +1703,7 @@ void ccl_b200_build_tracer_kernels(int ncosmo, const double* params, int na, con
   launch_build_tracer_kernels(ncosmo, na, (double*)(d + o_a), (double*)(d + o_chi), (int*)(d + o_n), stride,
                               (double*)(d + o_gx), (double*)(d + o_ga), (double*)(d + o_par), nz, (double*)(d + o_z),
                               ntr, (double*)(d + o_nz), sz_arr ? (double*)(d + o_sz) : nullptr, (double*)(d + o_in),
-                              nchi, (double*)(d + o_cz), (double*)(d + o_wn), (double*)(d + o_cl), (double*)(d + o_wl), 0);
+                              nullptr, nchi, (double*)(d + o_cz), (double*)(d + o_wn), (double*)(d + o_cl), (double*)(d + o_wl), 0);
   if (!cuda_ok(cudaGetLastError(), "tracer kernel builder launch", status)) return;
   if (!cuda_ok(cudaDeviceSynchronize(), "tracer kernel builder", status)) return;
   cudaMemcpy(chi_z, d + o_cz, nc * snz * 8, cudaMemcpyDeviceToHost);
@@ -1806,16 +1806,17 @@ ccl_b200_tables* ccl_b200_tables_build(int ncosmo, const double* params, int na,
     std::vector<double> eff(nt);
     for (size_t i = 0; i < nt; ++i) eff[i] = inv_norm[i];
     cudaMemcpy(t->d_in, eff.data(), nt * 8, cudaMemcpyHostToDevice);
-    launch_build_tracer_kernels(ncosmo, na, t->d_a, t->d_chi, t->d_nachi, achi_stride, t->d_gx, t->d_ga, t->d_par, nz,
-                                t->d_z, ntr, t->d_nz, sz_arr ? t->d_sz : nullptr, t->d_in, nchi, t->d_chiz, t->d_wnc,
-                                t->d_chil, t->d_wl, st);
+    // per-distribution factor of the lensing kernels (e.g. -2 for magnification); 0 = kernel not needed,
+    // its integrals are skipped
+    double* d_sc = nullptr;
     if (lens_scale) {
-      // fold the per-distribution factor (e.g. -2 for magnification) into the lensing kernels
-      std::vector<double> sc(lens_scale, lens_scale + nt);
-      double* d_sc = t->d_rng;  // scratch until the ranges are computed
-      cudaMemcpy(d_sc, sc.data(), nt * 8, cudaMemcpyHostToDevice);
-      launch_scale_rows(ncosmo, ntr, nchi, t->d_wl, d_sc, st);
+      d_sc = t->d_rng;  // scratch until the ranges are computed
+      cudaMemcpy(d_sc, lens_scale, nt * 8, cudaMemcpyHostToDevice);
     }
+    launch_build_tracer_kernels(ncosmo, na, t->d_a, t->d_chi, t->d_nachi, achi_stride, t->d_gx, t->d_ga, t->d_par, nz,
+                                t->d_z, ntr, t->d_nz, sz_arr ? t->d_sz : nullptr, t->d_in, d_sc, nchi, t->d_chiz,
+                                t->d_wnc, t->d_chil, t->d_wl, st);
+    if (lens_scale) launch_scale_rows(ncosmo, ntr, nchi, t->d_wl, d_sc, st);
     launch_tracer_ranges(ncosmo, ntr, nz, t->d_chiz, 0, t->d_wnc, t->d_rng, st);
     launch_tracer_ranges(ncosmo, ntr, nchi, t->d_chil, 0, t->d_wl, t->d_rng + nc * nt * 4, st);
   }

@@ -209,7 +209,7 @@ void launch_build_linpower(int ncosmo, int nk, const double* d_k, int na_pk, con
 void launch_build_tracer_kernels(int ncosmo, int na, const double* d_abg, const double* d_chibg, const int* d_nachi,
                                  int stride, const double* d_achi_chi, const double* d_achi_a, const double* d_params,
                                  int nz, const double* d_z, int ntr, const double* d_nz, const double* d_sz,
-                                 const double* d_inv_norm, int nchi, double* d_chi_z, double* d_w_nc, double* d_chi_l,
+                                 const double* d_inv_norm, const double* d_lens_scale, int nchi, double* d_chi_z, double* d_w_nc, double* d_chi_l,
                                  double* d_w_l, cudaStream_t stream);
 
 void launch_build_halofit(int ncosmo, int nk, const double* d_lk, int na, const double* d_a, const double* d_logplin,

@@ -240,7 +240,9 @@ def build_3x2pt_batch(cosmologies, z, lens_nz, source_nz, lens_bias=None, model=
     nl, ns = len(lens_nz), len(source_nz)
     if lens_bias is None:
         lens_bias = np.ones(nl)
-    tabs = DeviceTables(cosmologies, z, list(lens_nz) + list(source_nz), model=model, halofit=halofit, n_chi=n_chi)
+    # lens bins are pure number counts here: their lensing (magnification) kernels are not built
+    tabs = DeviceTables(cosmologies, z, list(lens_nz) + list(source_nz), lens_scale=[0.0] * nl + [1.0] * ns,
+                        model=model, halofit=halofit, n_chi=n_chi)
     if batch is None:
         batch = LibBatch(tabs.ncosmo)
     else:

@@ -279,7 +279,7 @@ void ccl_b200_build_halofit(int ncosmo, const double *params, int nk, const doub
 typedef struct ccl_b200_tables ccl_b200_tables;
 /* Runs the four builders above for ncosmo cosmologies and keeps every table in HBM.  Arguments as in the
  * host-in/out entries; halofit != 0 also builds the non-linear P(k); nz_arr / sz_arr / inv_norm / lens_scale
- * describe ntr redshift distributions (lens_scale[ntr], may be NULL, multiplies the lensing kernel, e.g.
+ * describe ntr redshift distributions (lens_scale[ntr], may be NULL, multiplies the lensing kernel; 0 = not built; e.g.
  * -2 for a magnification term).  The object must outlive ccl_b200_batch_commit of every batch filled
  * from it (the preparation kernels read its tables in place). */
 ccl_b200_tables *ccl_b200_tables_build(int ncosmo, const double *params, int na, const double *a_grid,
