@@ -734,6 +734,7 @@ LimberParams to_limber_params(const ccl_b200_params& p) {
   lp.K_MAX = p.K_MAX; lp.K_MIN = p.K_MIN; lp.DLOGK_INTEGRATION = p.DLOGK_INTEGRATION;
   lp.LIMBER_EPSREL = p.INTEGRATION_LIMBER_EPSREL; lp.N_ITERATION = p.N_ITERATION;
   lp.nk_cap = limber_nk_cap(lp);
+  lp.force_cquad = getenv("CCL_B200_FORCE_CQUAD") != nullptr;
   return lp;
 }
 

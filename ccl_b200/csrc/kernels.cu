@@ -5,6 +5,7 @@
 // One warp owns one (cosmology, pair, ell) C_ell: lanes walk the ln k sample axis, the
 // integrand samples live in shared memory, the Akima / Gauss-Kronrod sums are reduced with
 // warp shuffles.  Bound: fp64 DFMA pipe.
+#include <math_constants.h>
 #include <cfloat>
 #include <cstdio>
 
@@ -736,11 +737,277 @@ __device__ __forceinline__ bool subinterval_too_small(double a1, double a2, doub
   return fabs(a1) <= tmp && fabs(b2) <= tmp;
 }
 
+// ------------------------------------------------------------------------------------------
+// gsl_integration_cquad (GSL 2.x integration/cquad.c; Gonnet 2010): the reference's fallback after
+// gsl_integration_qag reports GSL_EROUND (src/ccl_cls.c:245-259).  Doubly-adaptive Clenshaw-Curtis
+// on nested 5/9/17/33 Chebyshev nodes, interpolants kept in an orthonormal Legendre basis, interval
+// heap ordered by error.  One warp per C_ell: integrand evaluations and the matrix-vector products
+// are spread over the lanes (each coefficient is still ONE sequential sum, as in GSL), the scalar
+// bookkeeping is executed redundantly by every lane on data that lane 0 writes to the warp's slice of
+// the workspace.  GSL's removal of non-finite samples (`downdate`) is not restated: a non-finite
+// integrand fails the C_ell.  Constant tables: tools/gen_cquad.py.
+// ------------------------------------------------------------------------------------------
+#define CQUAD_TABLE __device__ const
+#include "cquad_tables.h"
+
+struct CqIval {
+  double a, b, igral, err;
+  double c[64];
+  double fx[33];
+  int depth, rdepth, ndiv, pad;
+};
+
+constexpr int CQ_WARPS = 64;          // warps of the fallback kernel (it is a rare path)
+constexpr unsigned long long CQ_LIST_CAP = 1ull << 20;
+
+__device__ __forceinline__ void cq_vinvfx(const double* fx, double* c, int d, int lane) {
+  const int m = (4 << d) + 1, skip = 8 >> d;
+  const double* V = d == 0 ? CQ_V1INV : d == 1 ? CQ_V2INV : d == 2 ? CQ_V3INV : CQ_V4INV;
+  for (int i = lane; i < m; i += 32) {
+    double acc = 0.0;
+    for (int j = 0; j < m; ++j) acc += V[i * m + j] * fx[j * skip];
+    c[i] = acc;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void cq_sift_down(const CqIval* ivals, int* heap, int i, int n) {
+  while (2 * i + 1 < n) {
+    int j = 2 * i + 1;
+    if (j + 1 < n && ivals[heap[j + 1]].err >= ivals[heap[j]].err) j++;
+    if (ivals[heap[j]].err <= ivals[heap[i]].err) break;
+    const int t = heap[j]; heap[j] = heap[i]; heap[i] = t;
+    i = j;
+  }
+}
+
+// Returns the GSL status; every lane returns the same values.
+__device__ int cquad_warp(const TaskCtx& c, const double* pref, double a, double b, double epsabs, double epsrel,
+                          int wsize, CqIval* ivals, int* heap, int lane, double& result, int& st,
+                          unsigned long long& nev) {
+  const int n[4] = {4, 8, 16, 32};
+  const int skip[4] = {8, 4, 2, 1};
+  const int idx[4] = {0, 5, 14, 31};
+  const double w = 0.70710678118654752440;  // M_SQRT2 / 2
+  const int ndiv_max = 20;
+  const double* xi = CQ_XI;
+  if (epsabs < 0.0 || epsrel < 0.0) return ST_GSL_EBADTOL;
+  if (epsabs <= 0 && epsrel < DBL_EPSILON) return ST_GSL_EBADTOL;
+  if (wsize < 3) return ST_GSL_EDOM;
+  bool bad = false;
+  auto feval = [&](double x) {
+    int s1 = 0;
+    const double v = cl_integrand(c, pref, pref + MAX_SUB, x, s1);
+    if (s1 && !st) st = s1;
+    if (!isfinite(v)) bad = true;
+    return v;
+  };
+  auto settle = [&]() {  // every lane leaves with the same status / bad flag
+    st = warp_first_nonzero(st);
+    bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+  };
+  double nc, ncdiff, temp;
+  CqIval* iv = &ivals[0];
+  double m = (a + b) / 2, h = (b - a) / 2;
+  for (int i = lane; i <= n[3]; i += 32) iv->fx[i] = feval(m + xi[i] * h);
+  nev += 33;
+  settle();
+  cq_vinvfx(iv->fx, &iv->c[idx[0]], 0, lane);
+  cq_vinvfx(iv->fx, &iv->c[idx[3]], 3, lane);
+  cq_vinvfx(iv->fx, &iv->c[idx[2]], 2, lane);
+  nc = 0.0;
+  for (int i = n[2] + 1; i <= n[3]; i++) { temp = iv->c[idx[3] + i]; nc += temp * temp; }
+  ncdiff = nc;
+  for (int i = 0; i <= n[2]; i++) {
+    temp = iv->c[idx[2] + i] - iv->c[idx[3] + i];
+    ncdiff += temp * temp;
+    nc += iv->c[idx[3] + i] * iv->c[idx[3] + i];
+  }
+  ncdiff = sqrt(ncdiff);
+  nc = sqrt(nc);
+  {
+    const double ig0 = 2 * h * iv->c[idx[3]] * w;
+    double er0 = ncdiff * 2 * h;
+    if (ncdiff / nc > 0.1 && er0 < 2 * h * nc) er0 = 2 * h * nc;
+    __syncwarp();
+    if (lane == 0) {
+      iv->a = a; iv->b = b; iv->depth = 3; iv->rdepth = 1; iv->ndiv = 0;
+      iv->igral = ig0; iv->err = er0;
+    }
+  }
+  for (int i = lane; i < wsize; i += 32) heap[i] = i;
+  __syncwarp();
+  double igral = iv->igral, err = iv->err, igral_final = 0.0, err_final = 0.0;
+  int nivals = 1, status = 0;
+
+  while (!bad && !st && nivals > 0 && err > 0.0 && !(err <= fabs(igral) * epsrel || err <= epsabs) &&
+         !(err_final > fabs(igral) * epsrel || err - err_final < fabs(igral) * epsrel)) {
+    int split, d;
+    iv = &ivals[heap[0]];  // the interval with the largest error
+    m = (iv->a + iv->b) / 2;
+    h = (iv->b - iv->a) / 2;
+    double iv_err = iv->err, iv_igral = iv->igral;
+    if (iv->depth < 3) {  // raise the degree first
+      d = iv->depth + 1;
+      const int nnew = 16 / skip[d];  // samples at i = skip, 3 skip, 5 skip, ...
+      if (lane < nnew) {
+        const int i = skip[d] * (2 * lane + 1);
+        iv->fx[i] = feval(m + xi[i] * h);
+      }
+      nev += nnew;
+      settle();
+      cq_vinvfx(iv->fx, &iv->c[idx[d]], d, lane);
+      nc = 0.0;
+      for (int i = n[d - 1] + 1; i <= n[d]; i++) { temp = iv->c[idx[d] + i]; nc += temp * temp; }
+      ncdiff = nc;
+      for (int i = 0; i <= n[d - 1]; i++) {
+        temp = iv->c[idx[d - 1] + i] - iv->c[idx[d] + i];
+        ncdiff += temp * temp;
+        nc += iv->c[idx[d] + i] * iv->c[idx[d] + i];
+      }
+      ncdiff = 2 * h * sqrt(ncdiff);
+      nc = sqrt(nc);
+      iv_err = ncdiff;
+      iv_igral = 2 * h * w * iv->c[idx[d]];
+      __syncwarp();
+      if (lane == 0) { iv->depth = d; iv->err = iv_err; iv->igral = iv_igral; }
+      __syncwarp();
+      split = (nc > 0 && ncdiff / nc > 0.1);
+    } else
+      split = 1;  // maximum degree reached
+
+    if ((m + h * xi[0]) >= (m + h * xi[1]) || (m + h * xi[31]) >= (m + h * xi[32]) ||
+        iv_err < fabs(iv_igral) * DBL_EPSILON * 10) {
+      // drop the interval: keep its contribution
+      err_final += iv_err;
+      igral_final += iv_igral;
+      if (lane == 0) {
+        const int t = heap[nivals - 1]; heap[nivals - 1] = heap[0]; heap[0] = t;
+        cq_sift_down(ivals, heap, 0, nivals - 1);
+      }
+      nivals--;
+      __syncwarp();
+    } else if (split) {
+      d = iv->depth;
+      CqIval* ch[2] = {&ivals[heap[nivals]], &ivals[heap[nivals + 1]]};
+      // the six new samples of both children in one pass (i = 8, 16, 24 of each)
+      if (lane < 6) {
+        const int side = lane / 3, i = 8 * (lane % 3 + 1);
+        const double ca = side ? m : iv->a, cb = side ? iv->b : m;
+        ch[side]->fx[i] = feval((ca + cb) / 2 + xi[i] * h / 2);
+      } else if (lane == 6) { ch[0]->fx[0] = iv->fx[0]; ch[0]->fx[32] = iv->fx[16]; }
+      else if (lane == 7) { ch[1]->fx[0] = iv->fx[16]; ch[1]->fx[32] = iv->fx[32]; }
+      nev += 6;
+      settle();
+      bool diverged = false;
+      for (int side = 0; side < 2; ++side) {
+        CqIval* ic = ch[side];
+        const double* T = side == 0 ? CQ_TLEFT : CQ_TRIGHT;
+        cq_vinvfx(ic->fx, ic->c, 0, lane);
+        for (int i = lane; i <= n[d]; i += 32) {
+          double acc = 0.0;
+          for (int j = i; j <= n[d]; ++j) acc += T[i * 33 + j] * iv->c[idx[d] + j];
+          ic->c[idx[d] + i] = acc;
+        }
+        __syncwarp();
+        ncdiff = 0.0;
+        for (int i = 0; i <= n[0]; i++) { temp = ic->c[i] - ic->c[idx[d] + i]; ncdiff += temp * temp; }
+        for (int i = n[0] + 1; i <= n[d]; i++) { temp = ic->c[idx[d] + i]; ncdiff += temp * temp; }
+        ncdiff = sqrt(ncdiff);
+        const int ndiv = iv->ndiv + (fabs(iv->c[0]) > 0 && ic->c[0] / iv->c[0] > 2);
+        const int rdepth = iv->rdepth + 1;
+        const double cig = h * w * ic->c[0];
+        __syncwarp();
+        if (lane == 0) {
+          ic->a = side ? m : iv->a; ic->b = side ? iv->b : m;
+          ic->depth = 0; ic->rdepth = rdepth; ic->ndiv = ndiv;
+          ic->err = ncdiff * h; ic->igral = cig;
+        }
+        __syncwarp();
+        if (ndiv > ndiv_max && 2 * ndiv > rdepth) { diverged = true; break; }
+      }
+      if (diverged) {
+        result = (igral >= 0) ? CUDART_INF : -CUDART_INF;
+        return ST_GSL_EDIVERGE;
+      }
+      nivals += 2;
+      // the parent leaves the heap; the right child takes its place, the left one is the last entry
+      if (lane == 0) {
+        int t = heap[nivals - 1]; heap[nivals - 1] = heap[0]; heap[0] = t;
+        cq_sift_down(ivals, heap, 0, nivals - 2);
+        int i = nivals - 2;
+        while (i > 0) {
+          const int j = (i - 1) / 2;
+          if (ivals[heap[j]].err < ivals[heap[i]].err) {
+            t = heap[j]; heap[j] = heap[i]; heap[i] = t;
+            i = j;
+          } else
+            break;
+        }
+      }
+      nivals--;
+      __syncwarp();
+    } else {
+      if (lane == 0) cq_sift_down(ivals, heap, 0, nivals);
+      __syncwarp();
+    }
+    // heap about to overflow: retire the last intervals
+    while (nivals > wsize - 2) {
+      const CqIval* il = &ivals[heap[nivals - 1]];
+      err_final += il->err;
+      igral_final += il->igral;
+      nivals--;
+    }
+    igral = igral_final;
+    err = err_final;
+    for (int i = 0; i < nivals; i++) { igral += ivals[heap[i]].igral; err += ivals[heap[i]].err; }
+  }
+  result = igral;
+  if (bad && !st) return ST_GSL_EFAILED;
+  return status;
+}
+
+// Tasks the QAG kernel handed over (list[0] = count, list[1] = next, entries from list[2]).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+limber_cquad_kernel(const LimberProblem P, unsigned long long* list, CqIval* pool, int* heaps) {
+  __shared__ double s_pref[WARPS_PER_CTA][2 * MAX_SUB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * WARPS_PER_CTA + warp;
+  const int wsize = P.par.N_ITERATION;
+  CqIval* ivals = pool + (size_t)gw * wsize;
+  int* heap = heaps + (size_t)gw * wsize;
+  double* pref = s_pref[warp];
+  const unsigned long long count = min(list[0], CQ_LIST_CAP);
+  for (;;) {
+    unsigned long long i = 0;
+    if (lane == 0) i = atomicAdd(&list[1], 1ull);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= count) break;
+    const long long t = (long long)list[2 + i];
+    TaskCtx c;
+    int ic, ip, il;
+    setup_task(P, t, c, ic, ip, il);
+    double lkmin, lkmax;
+    get_k_interval(c, P.par, lkmin, lkmax);
+    __syncwarp();
+    setup_prefactors(c, pref, lane);
+    int st = 0;
+    unsigned long long nev = 0;
+    double result = 0.0;
+    const int gsl = cquad_warp(c, pref, lkmin, lkmax, 0.0, P.par.LIMBER_EPSREL, wsize, ivals, heap, lane, result, st, nev);
+    if (P.counters && lane == 0) atomicAdd(P.counters, nev);
+    finish_task(P, ic, ip, il, result, st ? st : gsl, lane);
+    __syncwarp();
+  }
+}
+
 // integ_cls_limber_qag_quad (src/ccl_cls.c:227-263): gsl_integration_qag(F, lkmin, lkmax, 0,
 // epsrel, limit, GSL_INTEG_GAUSS41).  Persistent warps pull tasks from a counter; the
 // interval list (a, b, r, e) of the warp lives in its slice of a global workspace.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned long long* next_task) {
+limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned long long* next_task,
+                  unsigned long long* cq_list) {
   __shared__ double s_fv[WARPS_PER_CTA][2 * 41];
   __shared__ double s_pref[WARPS_PER_CTA][2 * MAX_SUB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -773,6 +1040,9 @@ limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned 
     double result = 0.0;
     if (epsabs <= 0 && (epsrel < 50 * DBL_EPSILON || epsrel < 0.5e-28)) {
       gsl = ST_GSL_EBADTOL;
+    } else if (P.par.force_cquad) {
+      gsl = ST_GSL_EROUND;  // tests of the fallback branch: skip QAG
+      nev = 0;
     } else {
       double r0[1], e0[1], ab0[1], as0[1];
       const double pa0[1] = {lkmin}, pb0[1] = {lkmax};
@@ -850,8 +1120,17 @@ limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned 
       }
     }
     if (P.counters && lane == 0) atomicAdd(P.counters, nev);
-    // GSL_EROUND would switch the reference to CQUAD (src/ccl_cls.c:245-259); that branch is
-    // not implemented on the device and is reported as a failed C_ell with detail GSL_EROUND.
+    // GSL_EROUND switches the reference to CQUAD (src/ccl_cls.c:245-259): the task is handed to
+    // limber_cquad_kernel, which runs after this kernel in the same stream
+    if (gsl == ST_GSL_EROUND && !st && cq_list) {
+      unsigned long long at = CQ_LIST_CAP;
+      if (lane == 0) {
+        at = atomicAdd(&cq_list[0], 1ull);
+        if (at < CQ_LIST_CAP) cq_list[2 + at] = t;
+      }
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (at < CQ_LIST_CAP) continue;
+    }
     finish_task(P, ic, ip, il, result, st ? st : gsl, lane);
   }
 }
@@ -900,12 +1179,21 @@ double measure_fp64_peak_tflops(cudaStream_t stream) {
   return best;
 }
 
+// workspace layout: [QAG interval lists | task counter (64 B) | CQUAD task list | CQUAD interval pool | heaps]
+static size_t up256(size_t b) { return (b + 255) / 256 * 256; }
+static size_t qag_region_bytes(size_t warps, int n_iteration) {
+  return up256(warps * 4 * (size_t)n_iteration * sizeof(double)) + 256;
+}
+static size_t cq_list_bytes() { return up256((2 + CQ_LIST_CAP) * sizeof(unsigned long long)); }
+static size_t cq_pool_bytes(int n_iteration) { return up256((size_t)CQ_WARPS * n_iteration * sizeof(CqIval)); }
+static size_t cq_heap_bytes(int n_iteration) { return up256((size_t)CQ_WARPS * n_iteration * sizeof(int)); }
+
 size_t limber_qag_workspace_bytes(int n_iteration) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t warps = (size_t)sms * 8 * WARPS_PER_CTA;
-  return warps * 4 * (size_t)n_iteration * sizeof(double) + 64;  // + task counter
+  return qag_region_bytes(warps, n_iteration) + cq_list_bytes() + cq_pool_bytes(n_iteration) + cq_heap_bytes(n_iteration);
 }
 
 int limber_nk_cap(const LimberParams& par) {
@@ -949,12 +1237,19 @@ cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws,
       g_gk_uploaded[dev & 63] = true;
     }
     const int nblk = sms * 8;
-    if ((size_t)nblk * WARPS_PER_CTA * 4 * (size_t)prob.par.N_ITERATION * sizeof(double) + 64 > qag_ws_bytes)
-      return cudaErrorInvalidValue;
-    unsigned long long* next =
-        reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(qag_ws) + qag_ws_bytes - 64);
+    const int nit = prob.par.N_ITERATION;
+    const size_t o_next = qag_region_bytes((size_t)nblk * WARPS_PER_CTA, nit) - 256;
+    const size_t o_list = o_next + 256, o_pool = o_list + cq_list_bytes(), o_heap = o_pool + cq_pool_bytes(nit);
+    if (o_heap + cq_heap_bytes(nit) > qag_ws_bytes) return cudaErrorInvalidValue;
+    char* wsb = reinterpret_cast<char*>(qag_ws);
+    unsigned long long* next = reinterpret_cast<unsigned long long*>(wsb + o_next);
+    unsigned long long* cq_list = reinterpret_cast<unsigned long long*>(wsb + o_list);
     cudaMemsetAsync(next, 0, sizeof(unsigned long long), stream);
-    limber_qag_kernel<<<nblk, WARPS_PER_CTA * 32, 0, stream>>>(prob, ntasks, qag_ws, next);
+    cudaMemsetAsync(cq_list, 0, 2 * sizeof(unsigned long long), stream);
+    limber_qag_kernel<<<nblk, WARPS_PER_CTA * 32, 0, stream>>>(prob, ntasks, qag_ws, next, cq_list);
+    // the reference's fallback for GSL_EROUND; its warps exit at once when the list is empty
+    limber_cquad_kernel<<<CQ_WARPS / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, stream>>>(
+        prob, cq_list, reinterpret_cast<CqIval*>(wsb + o_pool), reinterpret_cast<int*>(wsb + o_heap));
   }
   return cudaGetLastError();
 }

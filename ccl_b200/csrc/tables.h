@@ -25,6 +25,7 @@ enum : int {
   ST_GSL_EBADTOL = 13,
   ST_GSL_EROUND = 18,
   ST_GSL_ESING = 21,
+  ST_GSL_EDIVERGE = 22,
   ST_ERR_MEMORY = 1025,
   ST_ERR_INCONSISTENT = 1027,
   ST_ERR_SPLINE = 1028,
@@ -112,6 +113,7 @@ struct LimberParams {
   double K_MAX, K_MIN, DLOGK_INTEGRATION, LIMBER_EPSREL;
   int N_ITERATION;
   int nk_cap;  // capacity (nodes) of the per-warp integrand buffer
+  int force_cquad;  // tests: send every 'qag_quad' C_ell through the CQUAD fallback (CCL_B200_FORCE_CQUAD)
 };
 
 // One launch: cl[(ic*npair + ip)*nl + il]

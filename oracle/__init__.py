@@ -94,7 +94,10 @@ def lib():
         L.o_integ_spline.argtypes = [C.c_int, _dp, _dp, C.c_double, C.c_double, _dp, _ip]
         L.o_qag41_test.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                    C.c_int, _dp, _dp, _ip]
+        L.o_cquad_test.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_int, _dp, _dp, _ip]
         L.o_set_num_threads.argtypes = [C.c_int]
+        L.o_set_force_cquad.argtypes = [C.c_int]
         L.o_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -346,6 +349,14 @@ def qag41_test(kind, p, a, b, epsabs=0.0, epsrel=1e-4, limit=1000):
     return r.value, e.value, n.value, st
 
 
+def cquad_test(kind, p, a, b, epsabs=0.0, epsrel=1e-4, wsize=1000):
+    """gsl_integration_cquad restatement on the test functions of qag41_test: result, abserr, nevals, status."""
+    r, e = C.c_double(), C.c_double()
+    n = C.c_int()
+    st = lib().o_cquad_test(kind, p, a, b, epsabs, epsrel, wsize, C.byref(r), C.byref(e), C.byref(n))
+    return r.value, e.value, n.value, st
+
+
 def set_num_threads(n):
     """Use n OpenMP threads (launchers such as torchrun export OMP_NUM_THREADS=1)."""
     lib().o_set_num_threads(int(n))
@@ -353,3 +364,8 @@ def set_num_threads(n):
 
 def num_threads():
     return lib().o_num_threads()
+
+
+def set_force_cquad(on):
+    """Send every 'qag_quad' C_ell through the CQUAD fallback (src/ccl_cls.c:245-259) instead of QAG."""
+    lib().o_set_force_cquad(int(bool(on)))

@@ -11,7 +11,8 @@
  * not vendored under /root/reference and is not installed in the build container, so the
  * reference itself is unbuildable here.  The GSL algorithms (interpolation/akima.c,
  * cspline.c, linalg/tridiag.c, interpolation/bsearch.h, integ_eval.h, interp2d/bicubic.c,
- * integration/qag.c, qk.c, qk41.c, qpsrt.c, util.c) are restated from their published
+ * integration/qag.c, qk.c, qk41.c, qpsrt.c, util.c, cquad.c with its constant tables
+ * regenerated from their definitions by tools/gen_cquad.py) are restated from their published
  * sources.  Pins: scipy Akima1DInterpolator / CubicSpline(natural) (tests/test_oracle.py),
  * the reference's 23 golden C_ell benchmark curves (benchmarks/data/run_*_log_cl_*.txt via
  * tests/golden/), the closed-form power-law C_ell of benchmarks/test_tracers.py:6-18.
@@ -56,10 +57,6 @@
 #define O_ERR_NOT_IMPLEMENTED 1040
 #define O_ERR_GROWTH_INIT 1058
 #define O_ERR_DISTANCES_INIT 1059
-/* oracle-only: GSL_EROUND in QAG would make the reference retry with CQUAD
- * (src/ccl_cls.c:245-259); CQUAD is not restated, the case is flagged instead. */
-#define O_ERR_CQUAD_NEEDED 9001
-
 #define O_F2D_CCLGROWTH 401
 #define O_F2D_CONSTGROWTH 403
 #define O_F2D_NOEXTRAPOL 404
@@ -1173,12 +1170,217 @@ int o_qag41(o_func f, void *par, double a, double b, double epsabs, double epsre
   return O_GSL_EFAILED;
 }
 
+/* --------------------------------------------------------------------------------------------
+ * gsl_integration_cquad (GSL 2.x integration/cquad.c; P. Gonnet, "Increasing the reliability of
+ * adaptive quadrature using explicit interpolants", ACM TOMS 37 (2010)): doubly-adaptive
+ * Clenshaw-Curtis quadrature on nested 5/9/17/33 Chebyshev nodes with the interpolants kept in an
+ * orthonormal Legendre basis.  Restated from the published algorithm and GSL's routine; the constant
+ * tables are regenerated from their definitions (tools/gen_cquad.py).  The reference calls it only
+ * after gsl_integration_qag returned GSL_EROUND (src/ccl_cls.c:245-259).  GSL's removal of
+ * non-finite function values (`downdate`) is not restated: a non-finite integrand is an error here.
+ * parity unpinned: no reference vector exercises this branch.
+ * ------------------------------------------------------------------------------------------ */
+#define CQUAD_TABLE static const
+#include "cquad_tables.h"
+#define O_GSL_EDIVERGE 22
+
+typedef struct {
+  double a, b;
+  double c[64];
+  double fx[33];
+  double igral, err;
+  int depth, rdepth, ndiv;
+} o_cquad_ival;
+
+static void o_cq_vinvfx(const double *fx, double *c, int d) {
+  static const int nn[4] = {4, 8, 16, 32}, skip[4] = {8, 4, 2, 1};
+  const double *V = d == 0 ? CQ_V1INV : d == 1 ? CQ_V2INV : d == 2 ? CQ_V3INV : CQ_V4INV;
+  const int m = nn[d] + 1;
+  for (int i = 0; i < m; i++) {
+    c[i] = 0.0;
+    for (int j = 0; j < m; j++) c[i] += V[i * m + j] * fx[j * skip[d]];
+  }
+}
+
+static void o_cq_sift_down(const o_cquad_ival *ivals, size_t *heap, int i, int n) {
+  while (2 * i + 1 < n) {
+    int j = 2 * i + 1;
+    if (j + 1 < n && ivals[heap[j + 1]].err >= ivals[heap[j]].err) j++;
+    if (ivals[heap[j]].err <= ivals[heap[i]].err) break;
+    size_t t = heap[j]; heap[j] = heap[i]; heap[i] = t;
+    i = j;
+  }
+}
+
+static int o_cquad(o_func f, void *par, double a, double b, double epsabs, double epsrel, size_t wsize,
+                   double *result, double *abserr, size_t *nevals) {
+  static const int n[4] = {4, 8, 16, 32};
+  static const int skip[4] = {8, 4, 2, 1};
+  static const int idx[4] = {0, 5, 14, 31};
+  const double w = M_SQRT2 / 2;
+  const int ndiv_max = 20;
+  const double *xi = CQ_XI;
+  if (epsabs < 0.0 || epsrel < 0.0) return O_GSL_EBADTOL;
+  if (epsabs <= 0 && epsrel < DBL_EPSILON) return O_GSL_EBADTOL;
+  if (wsize < 3) return O_GSL_EDOM;
+  o_cquad_ival *ivals = (o_cquad_ival *)malloc(sizeof(o_cquad_ival) * wsize);
+  size_t *heap = (size_t *)malloc(sizeof(size_t) * wsize);
+  if (!ivals || !heap) { free(ivals); free(heap); return O_ERR_MEMORY; }
+  int neval = 0, bad = 0;
+  double nc, ncdiff, temp;
+
+  /* first interval: the 33-point rule straight away */
+  o_cquad_ival *iv = &ivals[0], *ivl, *ivr;
+  double m = (a + b) / 2, h = (b - a) / 2;
+  for (int i = 0; i <= n[3]; i++) {
+    iv->fx[i] = f(m + xi[i] * h, par);
+    neval++;
+    if (!isfinite(iv->fx[i])) bad = 1;
+  }
+  o_cq_vinvfx(iv->fx, &iv->c[idx[0]], 0);
+  o_cq_vinvfx(iv->fx, &iv->c[idx[3]], 3);
+  o_cq_vinvfx(iv->fx, &iv->c[idx[2]], 2);
+  iv->a = a; iv->b = b; iv->depth = 3; iv->rdepth = 1; iv->ndiv = 0;
+  iv->igral = 2 * h * iv->c[idx[3]] * w;
+  nc = 0.0;
+  for (int i = n[2] + 1; i <= n[3]; i++) { temp = iv->c[idx[3] + i]; nc += temp * temp; }
+  ncdiff = nc;
+  for (int i = 0; i <= n[2]; i++) {
+    temp = iv->c[idx[2] + i] - iv->c[idx[3] + i];
+    ncdiff += temp * temp;
+    nc += iv->c[idx[3] + i] * iv->c[idx[3] + i];
+  }
+  ncdiff = sqrt(ncdiff);
+  nc = sqrt(nc);
+  iv->err = ncdiff * 2 * h;
+  if (ncdiff / nc > 0.1 && iv->err < 2 * h * nc) iv->err = 2 * h * nc;
+  for (size_t i = 0; i < wsize; i++) heap[i] = i;
+  double igral = iv->igral, err = iv->err, igral_final = 0.0, err_final = 0.0;
+  int nivals = 1, status = O_SUCCESS;
+
+  while (!bad && nivals > 0 && err > 0.0 && !(err <= fabs(igral) * epsrel || err <= epsabs) &&
+         !(err_final > fabs(igral) * epsrel || err - err_final < fabs(igral) * epsrel)) {
+    int split, d;
+    iv = &ivals[heap[0]];  /* the interval with the largest error */
+    m = (iv->a + iv->b) / 2;
+    h = (iv->b - iv->a) / 2;
+    if (iv->depth < 3) {  /* raise the degree first */
+      d = ++iv->depth;
+      for (int i = skip[d]; i <= 32; i += 2 * skip[d]) {
+        iv->fx[i] = f(m + xi[i] * h, par);
+        neval++;
+        if (!isfinite(iv->fx[i])) bad = 1;
+      }
+      o_cq_vinvfx(iv->fx, &iv->c[idx[d]], d);
+      nc = 0.0;
+      for (int i = n[d - 1] + 1; i <= n[d]; i++) { temp = iv->c[idx[d] + i]; nc += temp * temp; }
+      ncdiff = nc;
+      for (int i = 0; i <= n[d - 1]; i++) {
+        temp = iv->c[idx[d - 1] + i] - iv->c[idx[d] + i];
+        ncdiff += temp * temp;
+        nc += iv->c[idx[d] + i] * iv->c[idx[d] + i];
+      }
+      ncdiff = 2 * h * sqrt(ncdiff);
+      nc = sqrt(nc);
+      iv->err = ncdiff;
+      iv->igral = 2 * h * w * iv->c[idx[d]];
+      split = (nc > 0 && ncdiff / nc > 0.1);
+    } else
+      split = 1;  /* maximum degree reached */
+
+    if ((m + h * xi[0]) >= (m + h * xi[1]) || (m + h * xi[31]) >= (m + h * xi[32]) ||
+        iv->err < fabs(iv->igral) * DBL_EPSILON * 10) {
+      /* drop the interval: keep its contribution */
+      err_final += iv->err;
+      igral_final += iv->igral;
+      size_t t = heap[nivals - 1]; heap[nivals - 1] = heap[0]; heap[0] = t;
+      nivals--;
+      o_cq_sift_down(ivals, heap, 0, nivals);
+    } else if (split) {
+      d = iv->depth;
+      for (int side = 0; side < 2; side++) {
+        o_cquad_ival *ic = &ivals[heap[nivals++]];
+        const double *T = side == 0 ? CQ_TLEFT : CQ_TRIGHT;
+        if (side == 0) { ivl = ic; ic->a = iv->a; ic->b = m; ic->fx[0] = iv->fx[0]; ic->fx[32] = iv->fx[16]; }
+        else { ivr = ic; ic->a = m; ic->b = iv->b; ic->fx[0] = iv->fx[16]; ic->fx[32] = iv->fx[32]; }
+        ic->depth = 0;
+        ic->rdepth = iv->rdepth + 1;
+        for (int i = skip[0]; i < 32; i += skip[0]) {
+          ic->fx[i] = f((ic->a + ic->b) / 2 + xi[i] * h / 2, par);
+          neval++;
+          if (!isfinite(ic->fx[i])) bad = 1;
+        }
+        o_cq_vinvfx(ic->fx, ic->c, 0);
+        for (int i = 0; i <= n[d]; i++) {
+          ic->c[idx[d] + i] = 0.0;
+          for (int j = i; j <= n[d]; j++) ic->c[idx[d] + i] += T[i * 33 + j] * iv->c[idx[d] + j];
+        }
+        ncdiff = 0.0;
+        for (int i = 0; i <= n[0]; i++) { temp = ic->c[i] - ic->c[idx[d] + i]; ncdiff += temp * temp; }
+        for (int i = n[0] + 1; i <= n[d]; i++) { temp = ic->c[idx[d] + i]; ncdiff += temp * temp; }
+        ncdiff = sqrt(ncdiff);
+        ic->err = ncdiff * h;
+        ic->ndiv = iv->ndiv + (fabs(iv->c[0]) > 0 && ic->c[0] / iv->c[0] > 2);
+        if (ic->ndiv > ndiv_max && 2 * ic->ndiv > ic->rdepth) {
+          *result = (igral >= 0) ? INFINITY : -INFINITY;
+          status = O_GSL_EDIVERGE;
+          goto done;
+        }
+        ic->igral = h * w * ic->c[0];
+      }
+      (void)ivl; (void)ivr;
+      /* the parent leaves the heap; the right child takes its place, the left one is the last entry */
+      size_t t = heap[nivals - 1]; heap[nivals - 1] = heap[0]; heap[0] = t;
+      nivals--;
+      o_cq_sift_down(ivals, heap, 0, nivals - 1);
+      int i = nivals - 1;
+      while (i > 0) {
+        int j = (i - 1) / 2;
+        if (ivals[heap[j]].err < ivals[heap[i]].err) {
+          t = heap[j]; heap[j] = heap[i]; heap[i] = t;
+          i = j;
+        } else
+          break;
+      }
+    } else
+      o_cq_sift_down(ivals, heap, 0, nivals);
+
+    /* heap about to overflow: retire the last intervals */
+    while (nivals > (int)wsize - 2) {
+      iv = &ivals[heap[nivals - 1]];
+      err_final += iv->err;
+      igral_final += iv->igral;
+      nivals--;
+    }
+    igral = igral_final;
+    err = err_final;
+    for (int i = 0; i < nivals; i++) { igral += ivals[heap[i]].igral; err += ivals[heap[i]].err; }
+  }
+  *result = igral;
+done:
+  if (abserr) *abserr = err;
+  if (nevals) *nevals = (size_t)neval;
+  free(ivals);
+  free(heap);
+  if (bad) { *result = NAN; return O_GSL_EFAILED; }
+  return status;
+}
+
+static int o_force_cquad = 0;
+/* oracle-only: send every 'qag_quad' C_ell through CQUAD (tests of the fallback branch) */
+void o_set_force_cquad(int on) { o_force_cquad = on; }
+
 static void o_integ_cls_limber_qag_quad(const o_cosmo *cosmo, o_integ_par *ipar, double lkmin,
                                         double lkmax, double *result, double *eresult,
                                         int *status) {
-  int gslstatus = o_qag41(o_cl_integrand, ipar, lkmin, lkmax, 0, cosmo->LIMBER_EPSREL,
-                          cosmo->N_ITERATION, result, eresult, NULL);
-  if (gslstatus == O_GSL_EROUND) gslstatus = O_ERR_CQUAD_NEEDED;
+  int gslstatus = o_force_cquad ? O_GSL_EROUND
+                                : o_qag41(o_cl_integrand, ipar, lkmin, lkmax, 0, cosmo->LIMBER_EPSREL,
+                                          cosmo->N_ITERATION, result, eresult, NULL);
+  if (gslstatus == O_GSL_EROUND) {  /* src/ccl_cls.c:245-259 */
+    size_t nevals = 0;
+    gslstatus = o_cquad(o_cl_integrand, ipar, lkmin, lkmax, 0, cosmo->LIMBER_EPSREL,
+                        (size_t)cosmo->N_ITERATION, result, eresult, &nevals);
+  }
   if (*status == 0) *status = gslstatus;
 }
 
@@ -1261,6 +1463,15 @@ int o_qag41_test(int kind, double p, double a, double b, double epsabs, double e
                  double *result, double *abserr, int *nint) {
   o_testf_par par = {kind, p};
   return o_qag41(o_testf, &par, a, b, epsabs, epsrel, limit, result, abserr, nint);
+}
+
+int o_cquad_test(int kind, double p, double a, double b, double epsabs, double epsrel, int wsize,
+                 double *result, double *abserr, int *nevals) {
+  o_testf_par par = {kind, p};
+  size_t ne = 0;
+  const int st = o_cquad(o_testf, &par, a, b, epsabs, epsrel, (size_t)wsize, result, abserr, &ne);
+  *nevals = (int)ne;
+  return st;
 }
 
 void o_set_num_threads(int n) {

@@ -75,6 +75,37 @@ def test_single_pair_qag(setup, pair):
     assert np.max(_rel(cl, ref, ref)) < QAG_RTOL
 
 
+@pytest.mark.parametrize("pair", PAIRS)
+def test_single_pair_cquad_fallback(setup, pair, monkeypatch):
+    """The reference retries with gsl_integration_cquad when QAG reports GSL_EROUND
+    (src/ccl_cls.c:245-259).  That branch is forced on both sides (no synthetic input of this suite
+    triggers it): device CQUAD == oracle CQUAD to the 'qag_quad' tolerance, and both agree with
+    QAG-GK41 to its own epsrel."""
+    import ccl_b200 as cb
+    s = setup
+    c1, c2 = s["colls"][pair[0]], s["colls"][pair[1]]
+    args = (s["ocos"], _coll(s["otr"], c1), _coll(s["otr"], c2), s["opk"], ELLS, oracle.INTEG_QAG)
+    ref_qag, _ = oracle.angular_cl(*args)
+    oracle.set_force_cquad(True)
+    try:
+        ref, st_ref = oracle.angular_cl(*args)
+    finally:
+        oracle.set_force_cquad(False)
+    monkeypatch.setenv("CCL_B200_FORCE_CQUAD", "1")
+    cl, st = cb.angular_cls_limber(s["cos"], _coll(s["ltr"], c1), _coll(s["ltr"], c2), s["psp"], ELLS,
+                                   cb._lib.INTEGRATION_QAG_QUAD)
+    monkeypatch.delenv("CCL_B200_FORCE_CQUAD")
+    assert st == st_ref == 0 and np.all(np.isfinite(cl))
+    assert np.max(_rel(cl, ref, ref)) < QAG_RTOL
+    # two integrators at epsrel = 1e-4, where the curve is not a near-cancellation of disjoint kernels
+    big = np.abs(ref_qag) > 1e-3 * np.max(np.abs(ref_qag))
+    assert np.max(np.abs(cl[big] / ref_qag[big] - 1)) < 5e-4
+    # and the normal path is back afterwards
+    cl2, _ = cb.angular_cls_limber(s["cos"], _coll(s["ltr"], c1), _coll(s["ltr"], c2), s["psp"], ELLS,
+                                   cb._lib.INTEGRATION_QAG_QUAD)
+    assert np.max(_rel(cl2, ref_qag, ref_qag)) < QAG_RTOL
+
+
 def test_accessors_match_oracle(setup):
     s = setup
     chi = np.linspace(0.0, 9000.0, 301)
@@ -298,6 +329,32 @@ def test_batch_edge_cases(synth):
     assert stq == 0
     for q in range(len(pairs)):
         assert parity_error(clq[0, q], refq[q], None, QAG_RTOL) < QAG_RTOL
+
+
+def test_batch_cquad_fallback(synth, monkeypatch):
+    """The CQUAD hand-over list through the batched entry: forced on both sides, every C_ell of the batch
+    goes QAG kernel -> list -> limber_cquad_kernel and matches the oracle's CQUAD."""
+    import ccl_b200 as cb
+    bg, pk = synth["bg"], synth["pk"]
+    from ccl_b200 import synthetic as S
+    subs, colls = S.lsst_like_tracers(bg)
+    batch = cb.LibBatch(2)
+    for ic in range(2):
+        _fill(batch, ic, bg, pk, subs, chi_max_nokernel(bg))
+    batch.commit()
+    pairs = [(0, 0), (2, 9), (7, 9), (14, 14)]
+    ells = ELLS[::3]
+    oracle.set_force_cquad(True)
+    try:
+        ref, _ = _oracle_all(bg, pk, subs, colls, pairs, ells, oracle.INTEG_QAG)
+    finally:
+        oracle.set_force_cquad(False)
+    monkeypatch.setenv("CCL_B200_FORCE_CQUAD", "1")
+    cl, stat, st = batch.angular_cl(colls, pairs, ells, cb._lib.INTEGRATION_QAG_QUAD)
+    monkeypatch.delenv("CCL_B200_FORCE_CQUAD")
+    assert st == 0 and not stat.any() and np.array_equal(cl[0], cl[1])
+    for q in range(len(pairs)):
+        assert parity_error(cl[0, q], ref[q], None, QAG_RTOL) < QAG_RTOL, pairs[q]
 
 
 def test_pipelined_host_entry_equals_single_batch():

@@ -128,6 +128,37 @@ def test_qag41_known_integrals():
     assert st == 0 and n > 1 and abs(r - 2 / 3.) < 1e-8
 
 
+def test_cquad_known_integrals():
+    """gsl_integration_cquad restatement (the reference's fallback after GSL_EROUND, src/ccl_cls.c:245-259)."""
+    from scipy.integrate import quad
+    # polynomials the 17-point rule already reproduces: the first 33 evaluations settle it
+    for p in (0, 1, 7):
+        r, e, n, st = oracle.cquad_test(1, float(p), 0.0, 1.5)
+        assert st == 0 and n == 33
+        assert abs(r - 1.5 ** (p + 1) / (p + 1)) < 1e-12 * max(1, 1.5 ** (p + 1))
+    # degree 30: the 17- and 33-point interpolants differ, the interval is refined until epsrel holds
+    r, e, n, st = oracle.cquad_test(1, 30.0, 0.0, 1.5)
+    assert st == 0 and n > 33 and abs(r / (1.5 ** 31 / 31) - 1) < 1e-4
+    # smooth rational function against the arctangent
+    r, e, n, st = oracle.cquad_test(2, 4.0, -1.0, 2.0, epsrel=1e-10)
+    assert st == 0 and abs(r - (np.arctan(4.0) + np.arctan(2.0)) / 2.0) < 1e-11
+    # oscillatory integrand: intervals are split, the error estimate bounds the true error
+    r, e, n, st = oracle.cquad_test(0, 40.0, -3.0, 5.0, epsrel=1e-8)
+    ref = quad(lambda x: np.exp(-x * x) * np.cos(40.0 * x), -3.0, 5.0, epsabs=1e-15, epsrel=1e-13, limit=400)[0]
+    assert st == 0 and n > 33
+    assert abs(r - ref) <= max(e, 1e-8 * abs(ref)) + 1e-14
+    # end-point singularity in the derivative: sqrt(x) on [0, 1]
+    r, e, n, st = oracle.cquad_test(1, 0.5, 0.0, 1.0, epsrel=1e-9)
+    assert st == 0 and n > 33 and abs(r - 2 / 3.) < 1e-9
+    # the same accuracy class as QAG at the Limber tolerance
+    rq = oracle.qag41_test(0, 12.0, -2.0, 3.0, epsrel=1e-4)[0]
+    rc = oracle.cquad_test(0, 12.0, -2.0, 3.0, epsrel=1e-4)[0]
+    ref = quad(lambda x: np.exp(-x * x) * np.cos(12.0 * x), -2.0, 3.0, epsabs=1e-15, epsrel=1e-13)[0]
+    assert abs(rq - ref) < 1e-4 * abs(ref) + 1e-12 and abs(rc - ref) < 1e-4 * abs(ref) + 1e-12
+    # bad tolerance: GSL_EBADTOL
+    assert oracle.cquad_test(2, 1.0, 0.0, 1.0, epsrel=1e-20)[3] == 13
+
+
 def test_f_ell_values():
     # ccl_cl_tracer_t_get_f_ell (src/ccl_tracers.c:703-726)
     t0 = oracle.Tracer(der_angles=0)
