@@ -1901,8 +1901,18 @@ int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch* b, int first, const cc
   const std::vector<double>& rng = kind ? t->h_rng_l : t->h_rng_nc;
   int idx = -1;
   b->ts.raw.defer = true;
+  // the a-only transfer is shared by every slot: landed once, its constancy checked once
+  Lands L;
+  bool same = false;
+  if (fa_arr != nullptr && a_ka != nullptr && na_ka > 0) {
+    L.a = b->ts.land_put_owned(a_ka, na_ka);
+    L.fa = b->ts.land_put_owned(fa_arr, na_ka);
+    same = true;
+    for (int j = 1; j < na_ka && same; ++j) same = (fa_arr[j] == fa_arr[0]);
+  }
   for (int i = 0; i < t->ncosmo && !*status; ++i) {
     CosmoPlan& p = b->ts.cosmos[first + i];
+    if (p.tracers.capacity() < 16) p.tracers.reserve(16);
     const size_t si = (size_t)i, ti = si * t->ntr + itr;
     TracerPlan tp;
     tp.der_bessel = der_bessel;
@@ -1915,10 +1925,8 @@ int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch* b, int first, const cc
     if (fa_arr != nullptr && a_ka != nullptr) {
       tp.has_transfer = true;
       if (!b->ts.plan_f2d(tp.transfer, na_ka, a_ka, 0, nullptr, nullptr, nullptr, fa_arr, 1, 0, 2, GROWTH_CONST, 0, 1.0,
-                          0, status))
+                          0, status, L))
         break;
-      bool same = true;
-      for (int j = 1; j < na_ka && same; ++j) same = (fa_arr[j] == fa_arr[0]);
       tp.const_transfer = same;
       tp.const_transfer_value = fa_arr[0];
     }
