@@ -871,6 +871,40 @@ void launch_scale_rows(int ncosmo, int ntr, int n, double* d_w, const double* d_
   if (tot) scale_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ncosmo, ntr, n, d_w, d_scale);
 }
 
+// ccl_get_kappa_kernel (src/ccl_tracers.c:554-567) on chi = linspace(0, chi(z_source), n) (pyccl/tracers.py:189-190)
+// for every cosmology: one CTA per cosmology, one thread per node.
+__global__ void kappa_kernel_builder(int na, const double* __restrict__ a_bg, const double* __restrict__ chi_bg,
+                                     const int* __restrict__ n_achi, int stride, const double* __restrict__ achi_chi,
+                                     const double* __restrict__ achi_a, const double* __restrict__ params,
+                                     double z_source, int n, double* __restrict__ chi_out, double* __restrict__ w_out) {
+  const int ic = blockIdx.x;
+  const double* p = params + (size_t)ic * CCL_B200_NPAR;
+  const double a_s = 1. / (1. + z_source);
+  const double chi_s = (a_s == 1.0) ? 0.0 : akima_eval_direct(a_bg, chi_bg + (size_t)ic * na, na, a_s);
+  const double hub = p[P_H] / CLIGHT_HMPC;
+  const double pref = 1.5 * hub * hub * p[P_OM] / sinn(p, chi_s);  // get_lensing_prefactor / sinn(chi_source)
+  const double step = chi_s / (n - 1.);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double chi = (i == n - 1) ? chi_s : step * i;  // numpy.linspace: start + step * i, last = stop
+    const double a = (chi < 1e-8) ? 1.0
+                                  : akima_eval_direct(achi_chi + (size_t)ic * stride, achi_a + (size_t)ic * stride,
+                                                      n_achi[ic], chi);
+    double w;
+    if (chi != 0.0) w = pref * sinn(p, chi_s - chi) * chi * chi / a / sinn(p, chi);
+    else w = pref * sinn(p, chi_s - chi) * chi / a;
+    chi_out[(size_t)ic * n + i] = chi;
+    w_out[(size_t)ic * n + i] = w;
+  }
+}
+
+void launch_build_kappa_kernel(int ncosmo, int na, const double* d_abg, const double* d_chibg, const int* d_nachi,
+                               int stride, const double* d_achi_chi, const double* d_achi_a, const double* d_params,
+                               double z_source, int n, double* d_chi, double* d_w, cudaStream_t stream) {
+  if (ncosmo > 0)
+    kappa_kernel_builder<<<ncosmo, 128, 0, stream>>>(na, d_abg, d_chibg, d_nachi, stride, d_achi_chi, d_achi_a, d_params,
+                                                     z_source, n, d_chi, d_w);
+}
+
 void launch_tracer_ranges(int ncosmo, int ntr, int n, const double* d_x, int x_per_tracer, const double* d_w,
                           double* d_out, cudaStream_t stream) {
   const int tot = ncosmo * ntr;

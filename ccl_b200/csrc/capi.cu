@@ -784,6 +784,8 @@ struct ccl_b200_tables {
   // host-side metadata the arena planner needs (sizes and end nodes; never the tables themselves)
   std::vector<double> h_a, h_lk, h_apk, h_chi_amin, h_cmax, h_rng_nc, h_rng_l;
   std::vector<int> h_nachi;
+  // kernels built after the object (CMB-lensing kappa kernels): kept until the object is freed
+  std::deque<DevBuf> extras;
 };
 
 static void cosmology_rebuild(ccl_b200_cosmology* c, const double* chi, const double* a, int n,
@@ -1938,6 +1940,53 @@ int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch* b, int first, const cc
   b->ts.run_checks();
   b->ts.committed = false;
   return *status ? -1 : idx;
+}
+
+int ccl_b200_batch_add_kappa_tracer_from_tables(ccl_b200_batch* b, int first, ccl_b200_tables* t, double z_source,
+                                                int n_samples, int* status) {
+  if (*status) return -1;
+  if (!b || !t || first < 0 || first + t->ncosmo > (int)b->ts.cosmos.size() || n_samples < 5 || !(z_source > 0)) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200_batch_add_kappa_tracer_from_tables: inconsistent arguments (n_samples >= 5, z_source > 0)");
+    return -1;
+  }
+  if (1. / (1. + z_source) < t->h_a.front()) {  // pyccl: _check_background_spline_compatibility
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200: tracer defined over wider redshift range than the background a-spline");
+    return -1;
+  }
+  if (!cuda_ok(cudaSetDevice(t->device), "cudaSetDevice", status)) return -1;
+  const size_t nc = (size_t)t->ncosmo, n = (size_t)n_samples;
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  t->extras.emplace_back();
+  DevBuf& buf = t->extras.back();
+  const size_t o_chi = 0, o_w = up(nc * n * 8), o_rng = o_w + up(nc * n * 8);
+  if (!buf.reserve(o_rng + up(nc * 4 * 8), status)) return -1;
+  double* d_chi = reinterpret_cast<double*>(buf.p + o_chi);
+  double* d_w = reinterpret_cast<double*>(buf.p + o_w);
+  double* d_rng = reinterpret_cast<double*>(buf.p + o_rng);
+  launch_build_kappa_kernel(t->ncosmo, t->na, t->d_a, t->d_chi, t->d_nachi, t->stride, t->d_gx, t->d_ga, t->d_par,
+                            z_source, n_samples, d_chi, d_w, 0);
+  launch_tracer_ranges(t->ncosmo, 1, n_samples, d_chi, 1, d_w, d_rng, 0);
+  if (!cuda_ok(cudaGetLastError(), "kappa kernel builder launch", status)) return -1;
+  std::vector<double> rng(nc * 4);
+  if (!cuda_ok(cudaMemcpy(rng.data(), d_rng, nc * 4 * 8, cudaMemcpyDeviceToHost), "kappa kernel builder", status))
+    return -1;
+  int idx = -1;
+  for (size_t i = 0; i < nc; ++i) {
+    CosmoPlan& p = b->ts.cosmos[first + i];
+    if (p.tracers.capacity() < 16) p.tracers.reserve(16);
+    TracerPlan tp;
+    tp.der_bessel = -1;   // pyccl/tracers.py:1009-1013
+    tp.der_angles = 1;
+    tp.chi_min = rng[i * 4 + 0];
+    tp.chi_max = rng[i * 4 + 1];
+    b->ts.plan_s1_dev(tp.kernel, 0, n_samples, rng[i * 4 + 2], rng[i * 4 + 3], 1, d_chi + i * n, d_w + i * n);
+    p.tracers.push_back(tp);
+    idx = (int)p.tracers.size() - 1;
+  }
+  b->ts.committed = false;
+  return idx;
 }
 
 }  // extern "C"

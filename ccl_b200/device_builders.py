@@ -225,6 +225,14 @@ class DeviceTables:
         check(st.value)
         return idx
 
+    def add_kappa_tracer(self, batch, z_source, n_samples=100, first=0):
+        """One CMB-lensing sub-tracer per slot (CMBLensingTracer): kappa kernel built on the device."""
+        st = C.c_int(0)
+        idx = _lib.load().ccl_b200_batch_add_kappa_tracer_from_tables(batch.h, int(first), self.h, float(z_source),
+                                                                      int(n_samples), C.byref(st))
+        check(st.value)
+        return idx
+
     def __del__(self):
         if getattr(self, "h", None) and _lib._LIB is not None:
             _lib._LIB.ccl_b200_tables_free(self.h)

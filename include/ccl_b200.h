@@ -302,6 +302,13 @@ int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch *b, int first, const cc
                                           int itr, int der_bessel, int der_angles, int na_ka, const double *a_ka,
                                           const double *fa_arr, int *status);
 
+/* One CMB-lensing sub-tracer per slot (pyccl CMBLensingTracer, pyccl/tracers.py:991-1014): the kappa kernel
+ * of ccl_get_kappa_kernel (src/ccl_tracers.c:554-567) on linspace(0, chi(z_source), n_samples) is built on
+ * the device from the object's chi(a) and a(chi) tables and kept by the object; der_bessel = -1,
+ * der_angles = 1.  Returns the index of the new sub-tracer or -1. */
+int ccl_b200_batch_add_kappa_tracer_from_tables(ccl_b200_batch *b, int first, ccl_b200_tables *t, double z_source,
+                                                int n_samples, int *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -131,6 +131,38 @@ def test_3x2pt_from_parameters_matches_api_path():
             assert err < 5e-7, (ic, (i, j), err)
 
 
+def test_kappa_tracer_from_device_tables():
+    """CMB-lensing kappa kernels built on the device (ccl_get_kappa_kernel) from device-built background
+    tables: kappa x kappa, kappa x shear and kappa x counts agree with the pyccl-compatible classes; kappa
+    reaches a < a_min of P(k,a), so these C_ell also take the growth-extrapolation (redo) route."""
+    import ccl_b200 as ccl
+    from ccl_b200 import device_builders as db
+    from ccl_b200 import synthetic as S
+    cos = _cosmologies()[1:4]
+    z = np.linspace(0.0, 3.5, 500)
+    lens = S.smail_bins(z, 0.26, 0.94, edges=np.arange(0.2, 0.6 + 1e-9, 0.2), sigma_z=0.03)
+    src = S.smail_bins(z, 0.13, 0.78, nbins=2, sigma_z=0.05)
+    batch, colls, tabs = db.build_3x2pt_batch(cos, z, lens, src, [1.3, 1.5], model="eisenstein_hu", halofit=True)
+    ik = tabs.add_kappa_tracer(batch, 1100.0)
+    colls = list(colls) + [(ik, 1)]
+    batch.commit()
+    nk = len(colls) - 1
+    pairs = [(nk, nk), (0, nk), (3, nk), (1, 2)]
+    ells = np.unique(np.geomspace(2, 2000, 12).astype(int)).astype(float)
+    cl, stat, st = batch.angular_cl(colls, pairs, ells)
+    assert st == 0 and not stat.any()
+    for ic, c in enumerate(cos):
+        c2 = ccl.Cosmology(**{**c._params_init_kwargs, "transfer_function": "eisenstein_hu",
+                              "matter_power_spectrum": "halofit"})
+        trs = [ccl.NumberCountsTracer(c2, dndz=(z, n), bias=(z, b * np.ones_like(z)), has_rsd=False)
+               for n, b in zip(lens, [1.3, 1.5])] + [ccl.WeakLensingTracer(c2, dndz=(z, n)) for n in src]
+        trs.append(ccl.CMBLensingTracer(c2, z_source=1100.0))
+        for q, (i, j) in enumerate(pairs):
+            ref = ccl.angular_cl(c2, trs[i], trs[j], ells, limber_integration_method='spline')
+            err = np.max(np.abs(cl[ic, q] / ref - 1))
+            assert err < 5e-7, (ic, (i, j), err)
+
+
 def test_device_resident_pipeline_equals_round_trip():
     """Tables handed from the builders to the batch inside HBM give the same C_ell, bit for bit, as the
     same tables taken through the host (build_3x2pt_stacked + set_stacked)."""
