@@ -106,6 +106,8 @@ SIGNATURES = {
     "ccl_b200_batch_set_from_tables": (None, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _ip]),
     "ccl_b200_batch_add_tracer_from_tables": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                         _dp, _dp, _ip]),
+    "ccl_b200_batch_add_tracer_from_tables_bg": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                           C.c_int, _dp, _dp, _ip]),
     "ccl_b200_batch_add_kappa_tracer_from_tables": (C.c_int, [_vp, C.c_int, _vp, C.c_double, C.c_int, _ip]),
     "ccl_b200_build_halofit": (None, [C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, _ip]),
     "ccl_b200_build_background": (None, [C.c_int, _dp, C.c_int, _dp, C.c_double, C.c_double, C.c_int, C.c_double,

@@ -897,6 +897,36 @@ __global__ void kappa_kernel_builder(int na, const double* __restrict__ a_bg, co
   }
 }
 
+// a-only transfer functions that depend on the cosmology through its growth tables, on shared nodes a_ka[n]:
+// kind 1 = redshift-space distortions, -f(a) (pyccl/tracers.py:895-899: transfer_a = (a, -growth_rate(a)));
+// kind 2 = intrinsic alignments, -amp_j Omega_m / D(a_j) with amp_j = A_IA(z_j) 5e-14 rho_crit
+// (pyccl/tracers.py:967-987).  D and f are read through their Akima splines like ccl_growth_factor /
+// ccl_growth_rate (src/ccl_background.c:1290-1352).
+__global__ void bg_transfer_kernel(int ncosmo, int na, const double* __restrict__ a_bg, const double* __restrict__ D,
+                                   const double* __restrict__ f, const double* __restrict__ params, int kind, int n,
+                                   const double* __restrict__ a_ka, const double* __restrict__ amp,
+                                   double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncosmo * n) return;
+  const int ic = t / n, j = t - ic * n;
+  const double a = a_ka[j];
+  if (kind == 1) {
+    out[t] = -akima_eval_direct(a_bg, f + (size_t)ic * na, na, a);
+  } else {
+    const double Da = (a == 1.0) ? 1.0 : akima_eval_direct(a_bg, D + (size_t)ic * na, na, a);
+    out[t] = -amp[j] * params[(size_t)ic * CCL_B200_NPAR + P_OM] / Da;
+  }
+}
+
+void launch_build_bg_transfer(int ncosmo, int na, const double* d_abg, const double* d_D, const double* d_f,
+                              const double* d_params, int kind, int n, const double* d_a_ka, const double* d_amp,
+                              double* d_out, cudaStream_t stream) {
+  const int tot = ncosmo * n;
+  if (tot > 0)
+    bg_transfer_kernel<<<(tot + 127) / 128, 128, 0, stream>>>(ncosmo, na, d_abg, d_D, d_f, d_params, kind, n, d_a_ka,
+                                                             d_amp, d_out);
+}
+
 void launch_build_kappa_kernel(int ncosmo, int na, const double* d_abg, const double* d_chibg, const int* d_nachi,
                                int stride, const double* d_achi_chi, const double* d_achi_a, const double* d_params,
                                double z_source, int n, double* d_chi, double* d_w, cudaStream_t stream) {

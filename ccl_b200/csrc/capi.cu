@@ -1942,6 +1942,77 @@ int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch* b, int first, const cc
   return *status ? -1 : idx;
 }
 
+int ccl_b200_batch_add_tracer_from_tables_bg(ccl_b200_batch* b, int first, ccl_b200_tables* t, int kind, int itr,
+                                             int der_bessel, int der_angles, int bg_kind, int na_ka,
+                                             const double* a_ka, const double* amp, int* status) {
+  if (*status) return -1;
+  if (!b || !t || first < 0 || first + t->ncosmo > (int)b->ts.cosmos.size() || itr < 0 || itr >= t->ntr ||
+      (kind != 0 && kind != 1) || der_angles < 0 || der_angles > 2 || der_bessel < -1 || der_bessel > 2 ||
+      (bg_kind != 1 && bg_kind != 2) || na_ka < 3 || !a_ka || (bg_kind == 2 && !amp)) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200_batch_add_tracer_from_tables_bg: inconsistent arguments");
+    return -1;
+  }
+  for (int j = 1; j < na_ka; ++j)
+    if (!(a_ka[j] > a_ka[j - 1])) {
+      *status = CCL_B200_ERROR_SPLINE;
+      set_err("ccl_b200: spline nodes must be strictly increasing");
+      return -1;
+    }
+  if (a_ka[0] < t->h_a.front() || a_ka[na_ka - 1] > t->h_a.back()) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200: transfer nodes outside the background a-spline");
+    return -1;
+  }
+  if (!cuda_ok(cudaSetDevice(t->device), "cudaSetDevice", status)) return -1;
+  const size_t nc = (size_t)t->ncosmo, n = (size_t)na_ka;
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  t->extras.emplace_back();
+  DevBuf& buf = t->extras.back();
+  const size_t o_a = 0, o_amp = up(n * 8), o_fa = o_amp + up(n * 8);
+  if (!buf.reserve(o_fa + up(nc * n * 8), status)) return -1;
+  double* d_a = reinterpret_cast<double*>(buf.p + o_a);
+  double* d_amp = reinterpret_cast<double*>(buf.p + o_amp);
+  double* d_fa = reinterpret_cast<double*>(buf.p + o_fa);
+  cudaMemcpy(d_a, a_ka, n * 8, cudaMemcpyHostToDevice);
+  if (amp) cudaMemcpy(d_amp, amp, n * 8, cudaMemcpyHostToDevice);
+  launch_build_bg_transfer(t->ncosmo, t->na, t->d_a, t->d_D, t->d_f, t->d_par, bg_kind, na_ka, d_a, d_amp, d_fa, 0);
+  if (!cuda_ok(cudaGetLastError(), "transfer builder launch", status)) return -1;
+  if (!cuda_ok(cudaDeviceSynchronize(), "transfer builder", status)) return -1;
+  const int nk = kind ? t->nchi : t->nz;
+  const std::vector<double>& rng = kind ? t->h_rng_l : t->h_rng_nc;
+  const int a_uniform = TableSet::quasi_uniform(a_ka, na_ka);
+  int idx = -1;
+  for (size_t i = 0; i < nc; ++i) {
+    CosmoPlan& p = b->ts.cosmos[first + i];
+    if (p.tracers.capacity() < 16) p.tracers.reserve(16);
+    const size_t ti = i * t->ntr + itr;
+    TracerPlan tp;
+    tp.der_bessel = der_bessel;
+    tp.der_angles = der_angles;
+    tp.chi_min = rng[ti * 4 + 0];
+    tp.chi_max = rng[ti * 4 + 1];
+    const double* d_x = kind ? t->d_chil + i * nk : t->d_chiz + i * nk;
+    const double* d_w = (kind ? t->d_wl : t->d_wnc) + ti * nk;
+    b->ts.plan_s1_dev(tp.kernel, 0, nk, rng[ti * 4 + 2], rng[ti * 4 + 3], 0, d_x, d_w);
+    // the flags ccl_f2d_t_new gives a factorised a-only transfer (ccl_cl_tracer_t_new, src/ccl_tracers.c:670-684)
+    tp.has_transfer = true;
+    F2DPlan& f = tp.transfer;
+    memset(&f.flags, 0, sizeof(F2D));
+    F2D& g = f.flags;
+    g.is_factorizable = 1; g.is_k_constant = 1; g.is_a_constant = 0;
+    g.extrap_order_lok = 0; g.extrap_order_hik = 2; g.extrap_linear_growth = GROWTH_CONST;
+    g.is_log = 0; g.growth_factor_0 = 1.0; g.growth_exponent = 0;
+    g.amin = a_ka[0]; g.amax = a_ka[na_ka - 1];
+    g.has_fa = 1;
+    b->ts.plan_s1_dev(f.fa, 1, na_ka, a_ka[0], a_ka[na_ka - 1], a_uniform, d_a, d_fa + i * n);
+    p.tracers.push_back(tp);
+    idx = (int)p.tracers.size() - 1;
+  }
+  b->ts.committed = false;
+  return idx;
+}
+
 int ccl_b200_batch_add_kappa_tracer_from_tables(ccl_b200_batch* b, int first, ccl_b200_tables* t, double z_source,
                                                 int n_samples, int* status) {
   if (*status) return -1;

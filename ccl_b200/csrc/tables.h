@@ -208,6 +208,9 @@ void launch_build_linpower(int ncosmo, int nk, const double* d_k, int na_pk, con
                            const double* d_abg, const double* d_growth, const double* d_params, int model,
                            double lg_kmin, double lg_kmax, double* d_logp, double* d_sigma8, cudaStream_t stream);
 
+void launch_build_bg_transfer(int ncosmo, int na, const double* d_abg, const double* d_D, const double* d_f,
+                              const double* d_params, int kind, int n, const double* d_a_ka, const double* d_amp,
+                              double* d_out, cudaStream_t stream);
 void launch_build_kappa_kernel(int ncosmo, int na, const double* d_abg, const double* d_chibg, const int* d_nachi,
                                int stride, const double* d_achi_chi, const double* d_achi_a, const double* d_params,
                                double z_source, int n, double* d_chi, double* d_w, cudaStream_t stream);

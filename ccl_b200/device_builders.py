@@ -209,7 +209,13 @@ class DeviceTables:
         _lib.load().ccl_b200_batch_set_from_tables(batch.h, int(first), self.h, order_lok, order_hik, int(use_linear),
                                                    C.byref(st))
         check(st.value)
-        batch._tables_ref = self   # the tables must outlive the batch's commit
+        self._keep(batch)
+
+    def _keep(self, batch):
+        """The tables object must outlive the batch's commit (its buffers are read in place)."""
+        refs = batch.__dict__.setdefault("_tables_refs", [])
+        if self not in refs:
+            refs.append(self)
 
     def add_tracer(self, batch, kind, itr, der_bessel=0, der_angles=0, transfer_a=None, first=0):
         """One sub-tracer per slot from a device-built kernel: kind 'nc' (p(z) H(z)) or 'lensing'."""
@@ -223,6 +229,22 @@ class DeviceTables:
             batch.h, int(first), self.h, {"nc": 0, "lensing": 1}[kind], int(itr), int(der_bessel), int(der_angles),
             0 if a_ka is None else a_ka.size, dp(a_ka), dp(fa), C.byref(st))
         check(st.value)
+        self._keep(batch)
+        return idx
+
+    def add_tracer_bg(self, batch, kind, itr, der_bessel, der_angles, bg_kind, a_nodes, amp=None, first=0):
+        """One sub-tracer per slot whose a-only transfer is built on the device from each cosmology's growth
+        tables: bg_kind 'rsd' -> -f(a) (use der_bessel=2), 'ia' -> -amp Omega_m / D(a) with
+        amp = A_IA(z) 5e-14 rho_crit on the same nodes (use der_bessel=-1, der_angles=2)."""
+        a_ka = np.ascontiguousarray(a_nodes, dtype=float)
+        am = None if amp is None else np.ascontiguousarray(amp, dtype=float)
+        st = C.c_int(0)
+        dp = lambda x: None if x is None else x.ctypes.data_as(_lib._dp)
+        idx = _lib.load().ccl_b200_batch_add_tracer_from_tables_bg(
+            batch.h, int(first), self.h, {"nc": 0, "lensing": 1}[kind], int(itr), int(der_bessel), int(der_angles),
+            {"rsd": 1, "ia": 2}[bg_kind], a_ka.size, dp(a_ka), dp(am), C.byref(st))
+        check(st.value)
+        self._keep(batch)
         return idx
 
     def add_kappa_tracer(self, batch, z_source, n_samples=100, first=0):
@@ -231,6 +253,7 @@ class DeviceTables:
         idx = _lib.load().ccl_b200_batch_add_kappa_tracer_from_tables(batch.h, int(first), self.h, float(z_source),
                                                                       int(n_samples), C.byref(st))
         check(st.value)
+        self._keep(batch)
         return idx
 
     def __del__(self):

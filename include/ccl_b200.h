@@ -302,6 +302,13 @@ int ccl_b200_batch_add_tracer_from_tables(ccl_b200_batch *b, int first, const cc
                                           int itr, int der_bessel, int der_angles, int na_ka, const double *a_ka,
                                           const double *fa_arr, int *status);
 
+/* Same with an a-only transfer that depends on the cosmology through its growth tables, built on the device
+ * on the shared nodes a_ka[na_ka]: bg_kind 1 = redshift-space distortions, -f(a) (pyccl/tracers.py:895-899, use
+ * with der_bessel = 2); bg_kind 2 = intrinsic alignments, -amp[j] Omega_m / D(a_ka[j]) with
+ * amp[j] = A_IA(z_j) 5e-14 rho_crit (pyccl/tracers.py:967-987, use with der_bessel = -1, der_angles = 2). */
+int ccl_b200_batch_add_tracer_from_tables_bg(ccl_b200_batch *b, int first, ccl_b200_tables *t, int kind, int itr,
+                                             int der_bessel, int der_angles, int bg_kind, int na_ka,
+                                             const double *a_ka, const double *amp, int *status);
 /* One CMB-lensing sub-tracer per slot (pyccl CMBLensingTracer, pyccl/tracers.py:991-1014): the kappa kernel
  * of ccl_get_kappa_kernel (src/ccl_tracers.c:554-567) on linspace(0, chi(z_source), n_samples) is built on
  * the device from the object's chi(a) and a(chi) tables and kept by the object; der_bessel = -1,
