@@ -12,6 +12,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ccl_b200.h"
@@ -242,10 +243,11 @@ struct TableSet {
   struct NodeCheck { size_t x_off; const double* xsrc; int n; int uniform; int ok; };
   std::vector<NodeCheck> checks;
   size_t checks_done = 0;
+  std::unordered_map<const double*, int> shared_checks;  // source pointer -> check, within one setter call
 
   void run_checks() {
     const size_t lo = checks_done, hi = checks.size();
-    if (hi == lo) return;
+    if (hi == lo) { shared_checks.clear(); return; }
     size_t nodes = 0;
     for (size_t c = lo; c < hi; ++c) nodes += (size_t)checks[c].n;
     // a thread is worth spawning per ~256k nodes (a stacked call on a few hundred slots stays inline)
@@ -268,6 +270,7 @@ struct TableSet {
       for (auto& x : th) x.join();
     }
     checks_done = hi;
+    shared_checks.clear();
   }
 
   bool resolve(S1Plan& s, int* status) {
@@ -313,8 +316,15 @@ struct TableSet {
     s.x0 = x[0]; s.xn = x[n - 1];
     if (raw.defer) {
       // stacked setters: the O(n) node checks run on several host threads after staging
-      s.check_id = (int)checks.size();
-      checks.push_back(NodeCheck{s.x_off, x_land == NO_LAND ? nullptr : x, n, 0, 1});
+      // (a grid shared by the slots of one stacked call is checked once)
+      auto seen = x_land == NO_LAND ? shared_checks.end() : shared_checks.find(x);
+      if (seen != shared_checks.end() && checks[seen->second].n == n) {
+        s.check_id = seen->second;
+      } else {
+        s.check_id = (int)checks.size();
+        checks.push_back(NodeCheck{s.x_off, x_land == NO_LAND ? nullptr : x, n, 0, 1});
+        if (x_land != NO_LAND) shared_checks[x] = s.check_id;
+      }
     } else {
       for (int i = 1; i < n; ++i)
         if (!(x[i] > x[i - 1])) {  // gsl_spline_init requires strictly increasing x
@@ -493,6 +503,7 @@ struct TableSet {
     direct.clear();
     owned.clear();
     checks.clear();
+    shared_checks.clear();
     checks_done = 0;
     for (auto& c : cosmos) c = CosmoPlan();
     committed = false;
