@@ -264,6 +264,9 @@ __device__ __forceinline__ double tracer_kernel(const Tracer& tr, double chi) {
 // (galaxy bias, IA amplitude, growth rate) is the common case and is inlined.
 __device__ __forceinline__ double tracer_transfer(const Tracer& tr, double lk, double a, int& st) {
   if (!tr.has_transfer) return 1;
+  // all samples of an a-only transfer equal (a constant galaxy bias): its natural cubic spline is that
+  // constant exactly (every c_i, b_i, d_i is 0), inside and, through the clamp below, outside the table
+  if (tr.const_transfer) return tr.const_transfer_value;
   const F2D& f = tr.transfer;
   if (f.is_factorizable && !f.has_fk && f.has_fa && !f.is_log) {
     // constant in k, clamped in a (growth_factor_0 = 1, exponent 0: src/ccl_tracers.c:670-684)
