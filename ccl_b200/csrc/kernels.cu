@@ -1005,7 +1005,10 @@ limber_cquad_kernel(const LimberProblem P, unsigned long long* list, CqIval* poo
 // integ_cls_limber_qag_quad (src/ccl_cls.c:227-263): gsl_integration_qag(F, lkmin, lkmax, 0,
 // epsrel, limit, GSL_INTEG_GAUSS41).  Persistent warps pull tasks from a counter; the
 // interval list (a, b, r, e) of the warp lives in its slice of a global workspace.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+#ifndef CCLB_QAG_MINB
+#define CCLB_QAG_MINB 5
+#endif
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CCLB_QAG_MINB)
 limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned long long* next_task,
                   unsigned long long* cq_list) {
   __shared__ double s_fv[WARPS_PER_CTA][2 * 41];
