@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib
 from .lowlevel import LibBatch
 
-__all__ = ("PipelinedBatch", "slice_stacked", "pin_stacked")
+__all__ = ("PipelinedBatch", "slice_stacked", "pin_stacked", "chunk_sizes")
 
 
 def slice_stacked(stk, lo, hi):
@@ -83,25 +83,35 @@ def pin_stacked(stk):
     return out
 
 
+def chunk_sizes(ncosmo, nchunks=None):
+    """Cosmologies per chunk of the pipelined entry.
+
+    Regular chunks hold >= 256 cosmologies (fewer Limber CTAs than ~60 waves cost tail time and every chunk
+    costs ~1 ms of launches and synchronisation), at most 8 of them unless `nchunks` says otherwise; the sizes
+    ramp up x1.5 from a quarter of the regular size (not below 64) so that the first chunk reaches the SMs
+    after a fraction of the regular plan + upload time."""
+    ncosmo = int(ncosmo)
+    if ncosmo <= 0:
+        return []
+    if nchunks is None:
+        nchunks = max(1, min(8, ncosmo // 256))
+    nchunks = max(1, min(int(nchunks), ncosmo))
+    base = -(-ncosmo // nchunks)
+    sizes, size, rem = [], max(1, base // 4, min(64, base)), ncosmo
+    while rem > 0:
+        take = min(size, base, rem)
+        sizes.append(take)
+        rem -= take
+        size = -(-size * 3 // 2)
+    return sizes
+
+
 class PipelinedBatch:
     NSTAGE = 2   # host threads planning/staging chunks concurrently
 
     def __init__(self, ncosmo, nchunks=None, params=None):
         self.ncosmo = int(ncosmo)
-        if nchunks is None:
-            # regular chunks of >= 256 cosmologies (fewer Limber CTAs than ~60 waves cost tail time and
-            # every chunk costs ~1 ms of launches and synchronisation), at most 8 of them
-            nchunks = max(1, min(8, self.ncosmo // 256))
-        self.nchunks = max(1, min(int(nchunks), self.ncosmo))
-        # chunk sizes ramp up (x1.5 from a quarter of the regular size, not below 64): the first chunk
-        # reaches the SMs after a fraction of the regular stage + upload time
-        base = -(-self.ncosmo // self.nchunks)
-        sizes, size, rem = [], max(1, base // 4, min(64, base)), self.ncosmo
-        while rem > 0:
-            take = min(size, base, rem)
-            sizes.append(take)
-            rem -= take
-            size = -(-size * 3 // 2)
+        sizes = chunk_sizes(self.ncosmo, nchunks)
         offs = np.concatenate([[0], np.cumsum(sizes)])
         self.spans = [(int(offs[c]), int(sizes[c])) for c in range(len(sizes))]
         self.nchunks = len(sizes)

@@ -107,3 +107,32 @@ def test_gather_by_ell_tile_world2(nl):
         assert p.exitcode == 0
     ip, il = np.meshgrid(np.arange(npair), np.arange(nl), indexing="ij")
     assert np.array_equal(got, ip * 1e4 + il)
+
+
+def test_pipeline_chunk_sizes_and_slices():
+    """Host logic of the pipelined host-buffer entry: chunk sizes cover the batch, ramp up, respect the
+    regular size; slice_stacked cuts every per-cosmology array and keeps shared grids."""
+    from ccl_b200.pipeline import chunk_sizes, slice_stacked
+    assert chunk_sizes(0) == []
+    for n in (1, 37, 100, 256, 512, 1000, 4096, 5000):
+        for k in (None, 1, 4, 8, 16):
+            sz = chunk_sizes(n, k)
+            assert sum(sz) == n and min(sz) >= 1
+            base = max(sz)
+            assert all(b >= a or b == sz[-1] for a, b in zip(sz, sz[1:]))      # non-decreasing but the tail
+            if k is None:
+                assert len(sz) <= 8 + 5 and (n < 1024 or base >= 256)
+    assert chunk_sizes(4096) == [128, 192, 288, 432, 512, 512, 512, 512, 512, 496]
+    n, nz = 6, 4
+    stk = dict(count=n, achi=(np.arange(n), np.arange(n * 5.).reshape(n, 5), np.ones((n, 5))),
+               growth=(np.linspace(0.1, 1, 3), np.arange(n * 3.).reshape(n, 3)), chi_max_nokernel=np.arange(n, dtype=float),
+               pk=(np.zeros(7), np.zeros(2), np.arange(n * 14.).reshape(n, 2, 7), 1, 2, True),
+               tracers=[dict(der_bessel=0, chi=np.arange(n * nz, dtype=float).reshape(n, nz), w=np.ones((n, nz)),
+                             a=np.linspace(0.5, 1, 3), fa=np.arange(n * 3.).reshape(n, 3))])
+    cut = slice_stacked(stk, 2, 5)
+    assert cut["count"] == 3 and cut["achi"][1].shape == (3, 5) and cut["achi"][1][0, 0] == 10.0
+    assert cut["growth"][0].shape == (3,) and cut["growth"][1][0, 0] == 6.0           # shared a grid kept
+    assert cut["pk"][2].shape == (3, 2, 7) and cut["pk"][0] is stk["pk"][0]
+    t = cut["tracers"][0]
+    assert t["chi"].shape == (3, nz) and t["chi"][0, 0] == 2 * nz and t["a"].shape == (3,) and t["fa"][0, 0] == 6.0
+    assert np.shares_memory(cut["pk"][2], stk["pk"][2])                                # views, no copies
