@@ -301,6 +301,25 @@ __device__ __forceinline__ double tracer_prefactor(const Tracer& tr, double l) {
 
 // transfer_limber_single + transfer_limber_wrap (src/ccl_cls.c:102-164).
 // pref[itr] = f_ell (/ (l+1/2)^2 when der_bessel == -1), hoisted out of the node loop.
+// der_bessel 1 / 2 terms of transfer_limber_single (src/ccl_cls.c:121-145): the second evaluation point
+// chi' = (l + 3/2) / k.  Kept out of line: it is the larger half of the integrand's code and only
+// redshift-space-distortion sub-tracers reach it (the adaptive integrators are instruction-fetch bound).
+static __device__ __noinline__ double rsd_term(const TaskCtx& c, const Tracer& tr, double lk, double k, double a,
+                                               double w, double t, int& st) {
+  const double l = c.l;
+  const double lp1h = l + 0.5;
+  const double lp3h = l + 1.5;
+  const double chi_lp = lp3h / k;
+  const double a_lp = scale_factor_of_chi(*c.cs, chi_lp, st);
+  const double pk_ratio =
+      fabs(psp_eval(*c.cs->psp, lk, a_lp, c.cs, st) / psp_eval(*c.cs->psp, lk, a, c.cs, st));
+  const double w_p = tracer_kernel(tr, chi_lp);
+  const double t_p = tracer_transfer(tr, lk, a_lp, st);
+  const double sqell = sqrt(lp1h * pk_ratio / lp3h);
+  if (tr.der_bessel == 1) return l * w * t / lp1h - sqell * w_p * t_p;
+  return sqell * 2 * w_p * t_p / lp3h - (0.25 + 2 * l) * w * t / (lp1h * lp1h);
+}
+
 __device__ __forceinline__ double transfer_limber_wrap(const TaskCtx& c, const Tracer* trs, int n,
                                                        const double* pref, double lk, double k, double chi,
                                                        double a, int& st) {
@@ -311,21 +330,8 @@ __device__ __forceinline__ double transfer_limber_wrap(const TaskCtx& c, const T
     double dd;
     const double w = tracer_kernel(tr, chi);
     const double t = tracer_transfer(tr, lk, a, st);
-    if (tr.der_bessel < 1) {
-      dd = w * t;
-    } else {
-      const double lp1h = l + 0.5;
-      const double lp3h = l + 1.5;
-      const double chi_lp = lp3h / k;
-      const double a_lp = scale_factor_of_chi(*c.cs, chi_lp, st);
-      const double pk_ratio =
-          fabs(psp_eval(*c.cs->psp, lk, a_lp, c.cs, st) / psp_eval(*c.cs->psp, lk, a, c.cs, st));
-      const double w_p = tracer_kernel(tr, chi_lp);
-      const double t_p = tracer_transfer(tr, lk, a_lp, st);
-      const double sqell = sqrt(lp1h * pk_ratio / lp3h);
-      if (tr.der_bessel == 1) dd = l * w * t / lp1h - sqell * w_p * t_p;
-      else dd = sqell * 2 * w_p * t_p / lp3h - (0.25 + 2 * l) * w * t / (lp1h * lp1h);
-    }
+    if (tr.der_bessel < 1) dd = w * t;
+    else dd = rsd_term(c, tr, lk, k, a, w, t, st);
     transfer += dd * (itr < MAX_SUB ? pref[itr] : tracer_prefactor(tr, l));
     if (st != 0) return -1;
   }

@@ -617,7 +617,7 @@ __device__ __forceinline__ void spline_task(const LimberProblem& P, long long ta
 }
 
 // General 'spline' kernel: one warp per (cosmology, pair, ell), every tracer / P(k) form.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)   // 128 registers: 16 warps per SM
 limber_spline_kernel(const LimberProblem P, long long ntasks) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
