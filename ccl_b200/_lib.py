@@ -30,7 +30,7 @@ class Params(C.Structure):
     """ccl_b200_params: the spline/gsl parameters the path reads (include/ccl_core.h:94-178)."""
     _fields_ = [("K_MAX", C.c_double), ("K_MIN", C.c_double), ("DLOGK_INTEGRATION", C.c_double),
                 ("INTEGRATION_LIMBER_EPSREL", C.c_double), ("N_ITERATION", C.c_int),
-                ("A_SPLINE_MIN", C.c_double)]
+                ("INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS", C.c_int), ("A_SPLINE_MIN", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/ccl_b200.h

@@ -40,9 +40,17 @@ def angular_cl(cosmo, tracer1, tracer2, ell, *, p_of_k_a=DEFAULT_POWER_SPECTRUM,
         raise ValueError("ell values must be monotonically increasing")
     if ell_use[0] < l_limber:
         raise NotImplementedError("the FKEM non-Limber integrator is outside the Limber hot path (SURVEY.md 2b)")
-    # growth is only read when P(k,a) is evaluated below its a-range (src/ccl_f2d.c:351-370)
-    need_growth = any(r[1] > cosmo.comoving_radial_distance(max(psp._a[0], cosmo._bg.a[0]))
-                      for t in (tracer1, tracer2) for r in t._chi_range) if psp._a[0] > cosmo._bg.a[0] else False
+    # growth is only read when P(k,a) is evaluated below its a-range (src/ccl_f2d.c:351-370): at the node
+    # chi = (l+1/2)/k <= chi_max and, for der_bessel 1/2 sub-tracers, at the second point chi' = (l+3/2)/k
+    # (src/ccl_cls.c:121-145), which reaches chi_max (l+3/2)/(l+1/2)
+    need_growth = False
+    if psp._a[0] > cosmo._bg.a[0]:
+        chi_tab = cosmo.comoving_radial_distance(max(psp._a[0], cosmo._bg.a[0]))
+        lmin = float(ell_use[0])
+        for t in (tracer1, tracer2):
+            for sub, r in zip(t._trc, t._chi_range):
+                reach = r[1] * ((lmin + 1.5) / (lmin + 0.5) if sub.get("der_bessel", 0) >= 1 else 1.0)
+                need_growth = need_growth or reach > chi_tab
     dev = cosmo._device(need_growth=need_growth)
     trs1 = tracer1._device(cosmo)
     trs2 = trs1 if tracer2 is tracer1 else tracer2._device(cosmo)

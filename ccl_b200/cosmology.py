@@ -263,7 +263,9 @@ class Cosmology:
         sp, gp = self._spline_params, self._gsl_params
         return lowlevel.make_params(K_MAX=sp["K_MAX"], K_MIN=sp["K_MIN"], DLOGK_INTEGRATION=sp["DLOGK_INTEGRATION"],
                                     INTEGRATION_LIMBER_EPSREL=gp["INTEGRATION_LIMBER_EPSREL"],
-                                    N_ITERATION=gp["N_ITERATION"], A_SPLINE_MIN=sp["A_SPLINE_MIN"])
+                                    N_ITERATION=gp["N_ITERATION"], A_SPLINE_MIN=sp["A_SPLINE_MIN"],
+                                    INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS=gp[
+                                        "INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS"])
 
     def chi_max_nokernel(self):
         """chi(A_SPLINE_MIN): chi_max of kernel-less tracers (src/ccl_tracers.c:632)."""

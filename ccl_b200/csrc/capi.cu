@@ -300,6 +300,10 @@ struct TableSet {
     return true;
   }
 
+  // interval records of an n-node spline: {x0, x1}[n-1] then, on a 32-byte boundary, {y, b, c, d}[n-1]
+  static size_t rec_x_bytes(int n) { return ((size_t)(n - 1) * sizeof(double2) + 31) / 32 * 32; }
+  static size_t rec_bytes(int n) { return rec_x_bytes(n) + (size_t)(n - 1) * sizeof(double4); }
+
   static int lut_size(int n) { return std::min(std::max(n > 1000 ? 2 * n : 4 * n, 64), 1 << 15); }
 
   bool plan_s1(S1Plan& s, int kind, int n, const double* x, const double* y, int* status,
@@ -337,7 +341,7 @@ struct TableSet {
     }
     s.nlut = lut_size(n);
     s.lut_off = derive(sizeof(int) * s.nlut);
-    if (kind != 2) s.co_off = derive(sizeof(Rec1) * (n - 1));
+    if (kind != 2) s.co_off = derive(rec_bytes(n));
     else s.co_off = derive(sizeof(AxisRec) * (n - 1));
     if (kind == 1) s.scr_off = derive(sizeof(double) * 3 * n);
     return true;
@@ -352,7 +356,7 @@ struct TableSet {
     s.x_dev = d_x; s.y_dev = d_y;
     s.nlut = lut_size(n);
     s.lut_off = derive(sizeof(int) * s.nlut);
-    if (kind != 2) s.co_off = derive(sizeof(Rec1) * (n - 1));
+    if (kind != 2) s.co_off = derive(rec_bytes(n));
     else s.co_off = derive(sizeof(AxisRec) * (n - 1));
     if (kind == 1) s.scr_off = derive(sizeof(double) * 3 * n);
   }
@@ -514,7 +518,8 @@ struct TableSet {
     Spline1D d;
     memset(&d, 0, sizeof(d));
     if (!s.present) return d;
-    d.rec = reinterpret_cast<const Rec1*>(base_der + s.co_off);
+    d.xr = reinterpret_cast<const double2*>(base_der + s.co_off);
+    d.cr = reinterpret_cast<const double4*>(base_der + s.co_off + rec_x_bytes(s.n));
     d.lut = reinterpret_cast<const int*>(base_der + s.lut_off);
     d.n = s.n; d.nlut = s.nlut; d.uniform = s.uniform; d.x0 = s.x0; d.xn = s.xn;
     d.inv_step = (s.n - 1) / (s.xn - s.x0);
@@ -559,10 +564,11 @@ struct TableSet {
                                                      : reinterpret_cast<const double*>(br) + s.y_off);
     // the LUT is built for every grid: the fast kernel indexes tracer splines through it only
     lu.push_back(LutJob{x, reinterpret_cast<int*>(bd + s.lut_off), s.n, s.nlut});
-    if (s.kind == 0) ak.push_back(AkimaJob{x, y, reinterpret_cast<Rec1*>(bd + s.co_off), s.n});
+    double2* xr = reinterpret_cast<double2*>(bd + s.co_off);
+    double4* cr = reinterpret_cast<double4*>(bd + s.co_off + rec_x_bytes(s.n));
+    if (s.kind == 0) ak.push_back(AkimaJob{x, y, xr, cr, s.n});
     else if (s.kind == 1)
-      cs.push_back(CsplineJob{x, y, reinterpret_cast<Rec1*>(bd + s.co_off),
-                              reinterpret_cast<double*>(bd + s.scr_off), s.n});
+      cs.push_back(CsplineJob{x, y, xr, cr, reinterpret_cast<double*>(bd + s.scr_off), s.n});
     else
       ax_jobs.push_back(AxisJob{x, reinterpret_cast<AxisRec*>(bd + s.co_off), s.n});
   }
@@ -943,6 +949,16 @@ double ccl_b200_measure_fp64_peak(int* status) {
 void ccl_b200_default_params(ccl_b200_params* p) {
   p->K_MAX = 1e3; p->K_MIN = 5e-5; p->DLOGK_INTEGRATION = 0.025;
   p->INTEGRATION_LIMBER_EPSREL = 1e-4; p->N_ITERATION = 1000; p->A_SPLINE_MIN = 0.1;
+  p->INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS = 4;  // GSL_INTEG_GAUSS41 (src/ccl_core.c:40)
+}
+
+// gsl_integration_qag takes the rule key from the parameters (src/ccl_cls.c:240); the device has GK41 only
+static bool qag_rule_ok(const ccl_b200_params& p, int* status) {
+  if (p.INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS == 4) return true;
+  *status = CCL_B200_ERROR_NOT_IMPLEMENTED;
+  set_err("ccl_b200: INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS = %d: only GSL_INTEG_GAUSS41 (4) is implemented "
+          "for limber_integration_method='qag_quad'", p.INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS);
+  return false;
 }
 
 // ---- cosmology ----
@@ -1173,6 +1189,10 @@ void ccl_b200_angular_cls_limber(ccl_b200_cosmology* cosmo, ccl_b200_collection*
     set_err("ccl_cls.c: ccl_angular_cls_limber(); integration error\n");
     return;
   }
+  if (integration_method == INTEG_QAG && !qag_rule_ok(cosmo->params, status)) {
+    for (int i = 0; i < nl_out; ++i) cl_out[i] = NAN;
+    return;
+  }
   const int device = cosmo->ts.device;
   if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice", status)) return;
   DeviceScratch& sc = scratch_for(device);
@@ -1330,7 +1350,10 @@ int ccl_b200_batch_add_tracer(ccl_b200_batch* b, int icosmo, int der_bessel, int
     *status = CCL_B200_ERROR_INCONSISTENT;                                                  \
     set_err("ccl_b200: batch slots [%d, %d) out of range", (first), (first) + (count));    \
     return;                                                                                 \
-  }
+  }                                                                                         \
+  /* staging threads start with no current device: pinned-memory queries and allocations of   \
+     this call must bind to the batch's own GPU, not create a context on device 0 */         \
+  cudaSetDevice((b)->ts.device);
 
 void ccl_b200_batch_set_achi_stacked(ccl_b200_batch* b, int first, int count, const int* n_per, int stride,
                                      const double* chi, const double* a, int* status) {
@@ -1407,6 +1430,7 @@ int ccl_b200_batch_add_tracer_stacked(ccl_b200_batch* b, int first, int count, i
     *status = CCL_B200_ERROR_INCONSISTENT;
     return -1;
   }
+  cudaSetDevice(b->ts.device);  // see BATCH_RANGE
   int idx = -1;
   b->ts.raw.defer = true;
   const size_t cnt = (size_t)count;
@@ -1456,7 +1480,11 @@ void ccl_b200_batch_tracer_chi_range(const ccl_b200_batch* b, int icosmo, int it
   *chi_max = t.chi_max;
 }
 
-void ccl_b200_batch_reset(ccl_b200_batch* b) { if (b) b->ts.reset(); }
+void ccl_b200_batch_reset(ccl_b200_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ts.device);
+  b->ts.reset();
+}
 
 void ccl_b200_batch_commit(ccl_b200_batch* b, int* status) {
   if (*status || !b) return;
@@ -1477,6 +1505,7 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
     *status = CCL_B200_ERROR_NOT_IMPLEMENTED;
     return;
   }
+  if (integration_method == INTEG_QAG && !qag_rule_ok(b->params, status)) return;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   if (!cuda_ok(cudaSetDevice(b->ts.device), "cudaSetDevice", status)) return;
   const int nc = (int)b->ts.cosmos.size();

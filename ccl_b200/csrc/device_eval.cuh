@@ -9,14 +9,6 @@
 
 namespace cclb {
 
-__device__ __forceinline__ Rec1 load_rec(const Rec1* p) {
-  const double2* q = reinterpret_cast<const double2*>(p);
-  const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-  Rec1 r;
-  r.x0 = a.x; r.x1 = a.y; r.y = b.x; r.b = b.y; r.c = c.x; r.d = c.y;
-  return r;
-}
-
 // One 32-byte table node with a single 256-bit read-only load (LDG.E.256 on sm_100a); every double4
 // table is carved on a 32-byte boundary (BatchPlan::derive, Arena).
 __device__ __forceinline__ double4 ldg4(const double4* p) {
@@ -31,6 +23,15 @@ __device__ __forceinline__ double4 ldg4(const double4* p) {
 #endif
 }
 
+// Interval i of a 1-D spline: end points (LDG.128) and coefficients (LDG.256), issued together.
+__device__ __forceinline__ Rec1 load_rec(const Spline1D& s, int i) {
+  const double2 a = __ldg(s.xr + i);
+  const double4 c = ldg4(s.cr + i);
+  Rec1 r;
+  r.x0 = a.x; r.x1 = a.y; r.y = c.x; r.b = c.y; r.c = c.z; r.d = c.w;
+  return r;
+}
+
 // Record of the interval gsl_interp_bsearch(x, v, 0, n-1) would return, for x[0] <= v <= x[n-1].
 __device__ __forceinline__ Rec1 find_rec(const Spline1D& s, double v) {
   int i;
@@ -43,23 +44,23 @@ __device__ __forceinline__ Rec1 find_rec(const Spline1D& s, double v) {
   }
   const int last = s.n - 2;
   i = min(max(i, 0), last);
-  Rec1 r = load_rec(s.rec + i);
+  Rec1 r = load_rec(s, i);
   // the LUT entry is the interval of a point just left of the bin (lut_kernel): never past the target
   if (s.uniform)
-    while (v < r.x0 && i > 0) r = load_rec(s.rec + (--i));
+    while (v < r.x0 && i > 0) r = load_rec(s, --i);
   int steps = 0;
   while (v >= r.x1 && i < last) {
     if (++steps > 4) {  // strongly non-uniform grid: finish by bisection on the interval starts
       int lo = i, hi = last + 1;
       while (hi > lo + 1) {
         const int m = (hi + lo) >> 1;  // m <= last
-        if (__ldg(&s.rec[m].x0) > v) hi = m; else lo = m;
+        if (__ldg(&s.xr[m].x) > v) hi = m; else lo = m;
       }
       i = lo;
-      r = load_rec(s.rec + i);
+      r = load_rec(s, i);
       break;
     }
-    r = load_rec(s.rec + (++i));
+    r = load_rec(s, ++i);
   }
   return r;
 }

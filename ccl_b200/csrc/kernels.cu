@@ -53,7 +53,8 @@ __global__ void akima_coef_kernel(const AkimaJob* jobs) {
       c = (3.0 * m0 - 2.0 * b - tL_ip1) / h_i;
       d = (b + tL_ip1 - 2.0 * m0) / (h_i * h_i);
     }
-    jb.rec[i] = Rec1{x[i], x[i + 1], y[i], b, c, d};
+    jb.xr[i] = make_double2(x[i], x[i + 1]);
+    jb.cr[i] = make_double4(y[i], b, c, d);
   }
 }
 
@@ -279,7 +280,8 @@ __global__ void cspline_coef_smem_kernel(const CsplineJob* jobs, int max_n) {
     const double dy = y[i + 1] - y[i];
     const double b = (dy / dx) - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
     const double d = (c[i + 1] - c[i]) / (3.0 * dx);
-    jb.rec[i] = Rec1{x[i], x[i + 1], y[i], b, c[i], d};
+    jb.xr[i] = make_double2(x[i], x[i + 1]);
+    jb.cr[i] = make_double4(y[i], b, c[i], d);
   }
 }
 
@@ -321,7 +323,8 @@ __global__ void cspline_coef_kernel(const CsplineJob* jobs, int njobs) {
     const double dy = y[i + 1] - y[i];
     const double b = (dy / dx) - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
     const double d = (c[i + 1] - c[i]) / (3.0 * dx);
-    jb.rec[i] = Rec1{x[i], x[i + 1], y[i], b, c[i], d};
+    jb.xr[i] = make_double2(x[i], x[i + 1]);
+    jb.cr[i] = make_double4(y[i], b, c[i], d);
   }
 }
 

@@ -1,4 +1,4 @@
-// Fast 'spline' Limber kernels (sm_100a): ln k node grids shared across tracer pairs.
+// Fast 'spline' Limber kernels (sm_100a): ln k node grids shared across tracer pairs, 64-node chunks.
 //
 // Reference path: integ_cls_limber_spline (src/ccl_cls.c:189-225) -> cl_integrand (:166-187)
 // -> ccl_integ_spline (src/ccl_utils.c:274-345).  The reference evaluates the integrand
@@ -8,20 +8,32 @@
 // remainder is one product plus the Akima integral.  Node values and the
 // integrand's arithmetic are exactly those of the general kernel (kernels.cu, spline_task).
 //
-// Work decomposition: one CTA per (cosmology, ell); its 8 warps pull that cosmology's grids from
-// a shared-memory counter.  A warp streams a grid in chunks of 32 nodes (lane = node): phase 1
-// fills a 36-column shared-memory window (4 carried + 32 new) with k P and the collections' D,
-// phase 2 forms each pair's integrand over the window and advances its Akima integral, which
-// needs only f_{j-2..j+2} per node.  Anything the fast path does not cover (a node outside the
-// a(chi) or P(k,a) tables, ...) is pushed to a redo list for the general kernel.
+// Work decomposition: one CTA per (cosmology, ell); its warps pull that cosmology's grid tasks from
+// a shared-memory counter.  A warp streams a grid in chunks of CH = 32 * NPL nodes:
+//   phase 1 (lane = node, NPL sub-chunks of 32): a(chi), k P(k,a) and every collection's D into
+//     shared memory.  The task's sub-tracers arrive ordered by spline grid (limber_group_kernel), so
+//     splines on identical grids -- the lensing kernels of all source bins, the bias / alignment
+//     transfers -- share ONE interval search per node and then read only their 32-byte coefficient
+//     records;
+//   phase 2 (lane = NPL consecutive nodes): each pair's integrand and its Akima integral in streaming
+//     form; the per-pair cost (two vector loads, two shuffles, NPL ballots) is paid once per CH nodes.
+// Anything the fast path does not cover (a node outside the a(chi) or P(k,a) tables, ...) is pushed
+// to a redo list for the general kernel.
+#include <cstdlib>
+
 #include "device_eval.cuh"
 
 namespace cclb {
+
+cudaError_t launch_limber_fast_v1(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream);
 
 namespace {
 
 #ifndef CCLB_FW
 #define CCLB_FW 8
+#endif
+#ifndef CCLB_NPL
+#define CCLB_NPL 2
 #endif
 #ifndef CCLB_NCG
 #define CCLB_NCG 10
@@ -33,24 +45,38 @@ namespace {
 #define CCLB_LPC 1
 #endif
 #ifndef CCLB_MINB
-#define CCLB_MINB 3
+#define CCLB_MINB 2
+#endif
+#ifndef CCLB_TR_UNROLL
+#define CCLB_TR_UNROLL 1
 #endif
 constexpr int FW = CCLB_FW;     // warps per CTA
+constexpr int NPL = CCLB_NPL;   // nodes per lane in phase 2
+constexpr int CH = 32 * NPL;    // nodes per chunk
 constexpr int NCG = CCLB_NCG;   // collections per grid task
 constexpr int NPG = CCLB_NPG;   // pairs per grid task
-static_assert(CCLB_NPG <= 16, "pair flags are packed two bits per pair");
+static_assert(NPL == 2 || NPL == 4, "phase 2 is written for 2 or 4 nodes per lane");
+static_assert(CCLB_NPG <= 32 && CCLB_NCG <= 16, "carry bits are one per pair; collection slots are 4 bits");
 constexpr int LPC = CCLB_LPC;   // ells per CTA (descriptor staging is amortised over them)
 constexpr int NSG = 2 * CCLB_NCG;  // sub-tracers per grid task
+constexpr int TRU = CCLB_TR_UNROLL;  // unroll factor of the sub-tracer loop
 constexpr int GB = 64;          // (ell, grid) tasks whose limits are precomputed per CTA pass
 
-// Compact lookup descriptor of one 1-D spline, laid out so that a lookup reads it with three 16-byte
-// shared-memory loads: {x0, xn}, {inv_bin, rec}, {lut, nlut - 1, n - 2}.
+// sub-tracer list entry of a grid task:
+//   tracer index | collection slot << 8 | FIRST << 12 | NEWK << 13 | NEWA << 14
+// FIRST: first entry of its collection (store instead of accumulate); NEWK / NEWA: the kernel / the
+// a-only transfer sits on a different grid than the previous entry's (search the interval again).
+constexpr unsigned SUB_FIRST = 1u << 12, SUB_NEWK = 1u << 13, SUB_NEWA = 1u << 14;
+
+// Lookup descriptor of one 1-D spline, read with 16-byte shared-memory loads.
 struct __align__(16) FastS1 {
   double x0, xn;
   double inv_bin;
-  const Rec1* rec;
+  const double2* xr;
+  const double4* cr;
   const int* lut;
   int nlutm1, last;
+  int pad[2];
 };
 
 struct __align__(16) FastTr {
@@ -58,39 +84,44 @@ struct __align__(16) FastTr {
   FastS1 fa;
   double pref[LPC];  // f_ell (/(l+1/2)^2 when der_bessel == -1) for each ell of this CTA
   int has_fa, der_bessel;
-  int pad[2];
 };
 
 __device__ __forceinline__ FastS1 pack_s1(const Spline1D& s) {
   FastS1 f;
-  f.x0 = s.x0; f.xn = s.xn; f.inv_bin = s.inv_bin; f.rec = s.rec; f.lut = s.lut; f.nlutm1 = s.nlut - 1; f.last = s.n - 2;
+  f.x0 = s.x0; f.xn = s.xn; f.inv_bin = s.inv_bin; f.xr = s.xr; f.cr = s.cr; f.lut = s.lut;
+  f.nlutm1 = s.nlut - 1; f.last = s.n - 2;
+  f.pad[0] = f.pad[1] = 0;
   return f;
 }
 
-// find_rec through the LUT only (built for every grid): the entry is the interval of a point just
-// left of the bin, so the walk goes right only.
-__device__ __forceinline__ Rec1 find_rec_lut(const FastS1& s, double v) {
+// Interval gsl_interp_bsearch would return, through the LUT (built for every grid): the entry is the
+// interval of a point just left of the bin, so the walk goes right only.  Returns the index and the
+// interval's left node.  Abscissae outside the grid land on the first / last interval.
+__device__ __forceinline__ int find_interval(const FastS1& s, double v, double& x0) {
   int j = (int)((v - s.x0) * s.inv_bin);
   j = min(max(j, 0), s.nlutm1);
   int i = __ldg(s.lut + j);
   const int last = s.last;
-  Rec1 r = load_rec(s.rec + i);
+  double2 r = __ldg(s.xr + i);
   int steps = 0;
-  while (v >= r.x1 && i < last) {
+  while (v >= r.y && i < last) {
     if (++steps > 4) {  // strongly non-uniform grid: finish by bisection on the interval starts
       int lo = i, hi = last + 1;
       while (hi > lo + 1) {
         const int m = (hi + lo) >> 1;
-        if (__ldg(&s.rec[m].x0) > v) hi = m; else lo = m;
+        if (__ldg(&s.xr[m].x) > v) hi = m; else lo = m;
       }
       i = lo;
-      r = load_rec(s.rec + i);
+      r = __ldg(s.xr + i);
       break;
     }
-    r = load_rec(s.rec + (++i));
+    r = __ldg(s.xr + (++i));
   }
-  return r;
+  x0 = r.x;
+  return i;
 }
+
+__device__ __forceinline__ double cubic(const double4 c, double d) { return c.x + d * (c.y + d * (c.z + d * c.w)); }
 
 // ln k limits and node spacing of one (ell, grid) task (get_k_interval + ccl_linear_spacing)
 struct GridPar {
@@ -102,7 +133,6 @@ struct GridPar {
 struct FastCta {
   Spline1D achi;
   F2D psp;
-  int2 colls[FAST_MAX_COLLS];
   GridPar gp[GB];
   int next_task, pad;
 };
@@ -112,17 +142,13 @@ __host__ __device__ inline size_t fast_warp_offset(int ntr_max) {
   return (fast_tr_offset() + (size_t)ntr_max * sizeof(FastTr) + 15) & ~size_t(15);
 }
 
-// sub-tracer list entry of a grid task: tracer index | collection slot << 8 | first << 16 | last << 17
-constexpr unsigned SUB_FIRST = 1u << 16, SUB_LAST = 1u << 17;
-
-struct FastWarp {
-  double dflat[NCG * 32]; // D of the grid's collection c at this lane's node: [c * 32 + lane]
-  double sf[2][36];       // integrand of the current pair: 4 carried + 32 new nodes (double-buffered)
-  double fc[NPG][4];      // last 4 integrand values of the previous chunk, per pair
-  double fe[NPG][8];      // f_0..f_2 and f_{nk-5}..f_{nk-1} per pair (end-node terms)
-  int2 po[NPG];           // offsets of the pair's two collections in dflat
-  double acc[NPG][32];    // per-lane partial integrals
-  GridPair prs[NPG];
+struct __align__(16) FastWarp {
+  double dflat[NCG * CH];  // D of the grid's collection slot c at chunk node j: [c * CH + j]
+  double kp[CH];           // k P(k, a) at chunk node j
+  double acc[NPG][32];     // per-lane partial integrals
+  double fc[NPG][4];       // integrand at the last 4 nodes of the previous chunk, per pair
+  double fe[NPG][8];       // f_0..f_2 and f_{nk-5}..f_{nk-1} per pair (end-node terms)
+  int2 po[NPG];            // offsets of the pair's two collections in dflat
   unsigned subs[NSG];
 };
 
@@ -132,18 +158,15 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__device__ __forceinline__ double rec_value(const Rec1& r, double v) {
-  const double d = v - r.x0;
-  return r.y + d * (r.b + d * (r.c + d * r.d));
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-// Grouping: one CTA per cosmology builds its grid descriptors.
+// Grouping: one CTA per cosmology builds its grid tasks: pairs with equal (chi_min, chi_max), their
+// collections, and the flattened sub-tracer list ordered by spline grid.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P, const FastPlan G) {
   extern __shared__ double gsm[];
+  __shared__ int s_kgrp[FAST_MAX_TRACERS], s_agrp[FAST_MAX_TRACERS];
   const int ic = blockIdx.x;
   const int ncoll = P.ncoll, npair = P.npair;
   double* cmin = gsm;
@@ -152,6 +175,7 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
   double* pmax = pmin + npair;
   int* leader = reinterpret_cast<int*>(pmax + npair);
   const Cosmo* cs = P.cosmos + ic;
+  const int ntr = cs->ntracers;
   for (int c = threadIdx.x; c < ncoll; c += blockDim.x) {
     const int2 cr = P.colls[c];
     double lo = 1E15, hi = -1E15;  // get_k_interval (src/ccl_cls.c:70-90)
@@ -176,15 +200,88 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
       if (pmin[q] == a && pmax[q] == b) { ld = q; break; }
     leader[p] = ld;
   }
-  __syncthreads();
+  // Spline grids: kgrp[t] / agrp[t] = first sub-tracer whose kernel / a-only transfer has exactly the
+  // same nodes (every interval record {x_i, x_{i+1}} equal).  agrp = -1: no transfer lookup.
+  for (int t = 0; t < ntr; ++t) {
+    const Tracer& tr = cs->tracers[t];
+    int kg = t, ag = -1;
+    for (int u = 0; u < t; ++u) {
+      if (s_kgrp[u] != u) continue;
+      const Spline1D& a = tr.kernel;
+      const Spline1D& b = cs->tracers[u].kernel;
+      bool same = (a.n == b.n) && (a.x0 == b.x0) && (a.xn == b.xn);
+      if (same)
+        for (int i = threadIdx.x; i < a.n - 1; i += blockDim.x) {
+          const double2 p = a.xr[i], q = b.xr[i];
+          if (p.x != q.x || p.y != q.y) same = false;
+        }
+      if (__syncthreads_and(same)) { kg = u; break; }
+    }
+    const bool fold = tr.has_transfer && tr.const_transfer;
+    if (tr.has_transfer && !fold) {
+      ag = t;
+      for (int u = 0; u < t; ++u) {
+        if (s_agrp[u] != u) continue;
+        const Spline1D& a = tr.transfer.fa;
+        const Spline1D& b = cs->tracers[u].transfer.fa;
+        bool same = (a.n == b.n) && (a.x0 == b.x0) && (a.xn == b.xn);
+        if (same)
+          for (int i = threadIdx.x; i < a.n - 1; i += blockDim.x) {
+            const double2 p = a.xr[i], q = b.xr[i];
+            if (p.x != q.x || p.y != q.y) same = false;
+          }
+        if (__syncthreads_and(same)) { ag = u; break; }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { s_kgrp[t] = kg; s_agrp[t] = ag; }
+    __syncthreads();
+  }
   if (threadIdx.x != 0) return;
   GridDesc* grids = G.grids + (size_t)ic * G.gstride;
   GridPair* gp = G.gpairs + (size_t)ic * G.gstride;
   int* gc = G.gcolls + (size_t)ic * G.cstride;
+  unsigned* gs = G.gsubs + (size_t)ic * G.sstride;
   int ng = 0, npw = 0, ncw = 0;
+  auto close_task = [&](GridDesc& cur) {
+    // flatten the task's collections into one sub-tracer list, ordered by kernel grid (stable)
+    unsigned* out = gs + (size_t)ng * NSG;
+    int key[NSG];
+    int n = 0, rsd = 0;
+    for (int s = 0; s < cur.ncoll; ++s) {
+      const int2 cr = P.colls[gc[cur.coll_begin + s]];
+      for (int j = 0; j < cr.y; ++j) {
+        const int t = cr.x + j;
+        if (n < NSG) {
+          int at = n;
+          while (at > 0 && key[at - 1] > s_kgrp[t]) { key[at] = key[at - 1]; out[at] = out[at - 1]; --at; }
+          key[at] = s_kgrp[t];
+          out[at] = (unsigned)t | ((unsigned)s << 8);
+        }
+        ++n;
+        rsd |= (cs->tracers[t].der_bessel >= 1);
+      }
+    }
+    cur.nsub = n;  // n > NSG: the fast kernel leaves the task to the general kernel
+    cur.has_rsd = rsd;
+    cur.sub_begin = ng * NSG;
+    unsigned seen = 0u;
+    int last_k = -1, last_a = -2;
+    for (int e = 0; e < min(n, NSG); ++e) {
+      unsigned ent = out[e];
+      const int t = (int)(ent & 0xffu), s = (int)((ent >> 8) & 0xfu);
+      if (!((seen >> s) & 1u)) { ent |= SUB_FIRST; seen |= 1u << s; }
+      if (s_kgrp[t] != last_k) { ent |= SUB_NEWK; last_k = s_kgrp[t]; }
+      if (s_agrp[t] >= 0 && s_agrp[t] != last_a) { ent |= SUB_NEWA; last_a = s_agrp[t]; }
+      out[e] = ent;
+    }
+    grids[ng++] = cur;
+    ncw += cur.ncoll;
+    npw += cur.npair;
+  };
   for (int p = 0; p < npair; ++p) {
     if (leader[p] != p) continue;
-    GridDesc cur{pmin[p], pmax[p], ncw, 0, npw, 0};
+    GridDesc cur{pmin[p], pmax[p], ncw, 0, npw, 0, 0, 0, 0, 0};
     int cur_nsub = 0;
     for (int q = p; q < npair; ++q) {
       if (leader[q] != p) continue;
@@ -199,10 +296,8 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
       const int need_sub = (sa < 0 ? P.colls[pr.x].y : 0) + (new_b ? P.colls[pr.y].y : 0);
       if (cur.npair > 0 && (cur.ncoll + need > NCG || cur.npair + 1 > NPG || cur_nsub + need_sub > NSG)) {
         // close this task, open another on the same grid
-        grids[ng++] = cur;
-        ncw += cur.ncoll;
-        npw += cur.npair;
-        cur = GridDesc{pmin[p], pmax[p], ncw, 0, npw, 0};
+        close_task(cur);
+        cur = GridDesc{pmin[p], pmax[p], ncw, 0, npw, 0, 0, 0, 0, 0};
         cur_nsub = 0;
         sa = sb = -1;
       }
@@ -211,9 +306,7 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
       else if (sb < 0) { sb = cur.ncoll; gc[cur.coll_begin + cur.ncoll++] = pr.y; cur_nsub += P.colls[pr.y].y; }
       gp[cur.pair_begin + cur.npair++] = GridPair{q, (short)sa, (short)sb};
     }
-    grids[ng++] = cur;
-    ncw += cur.ncoll;
-    npw += cur.npair;
+    close_task(cur);
   }
   G.ngrids[ic] = ng;
 }
@@ -223,138 +316,177 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
 //
 // With m_j the slopes and t_j the Akima node derivatives, GSL's piecewise cubic integrates to
 //   sum_i h_i (f_i + f_{i+1}) / 2  +  (1/12) sum_{i: NE_i != 0} h_i^2 (t_i - tL_{i+1}),
-// tL_{i+1} = t_{i+1} unless NE_{i+1} == 0 (then m_i).  Per node c the second sum contributes
-// h^2 ([!z_c] t_c - [!z_{c-1}] (z_c ? m_{c-1} : t_c)) with z_c = (NE_c == 0): on the uniform part of the
-// grid that vanishes unless z_c != z_{c-1}.  The chunk loop therefore adds trapezoids and tests for
-// tie transitions (NE_c == 0 <=> m_{c+1} == m_c and m_{c-1} == m_{c-2}, i.e. equal consecutive first
-// differences); only a chunk holding a transition evaluates the per-node form, for the interior
-// nodes 1..nk-3.  The three end-node terms (nodes 0, nk-2, nk-1) are added once per pair after the
-// loop from the saved values fe.  Lane `lane` holds node s = base + lane and owns the trapezoid of
-// interval (s-1, s) and the correction term of node c = s - 2.
+// tL_{i+1} = t_{i+1} unless NE_{i+1} == 0 (then m_i).  The first sum is a node-weighted sum (weights
+// dx inside, half intervals at the two ends, the last interval with its own width).  Per node c the
+// second sum contributes h^2 ([!z_c] t_c - [!z_{c-1}] (z_c ? m_{c-1} : t_c)) with z_c = (NE_c == 0): on
+// the uniform part of the grid that vanishes unless z_c != z_{c-1}.  The chunk loop therefore adds
+// weighted node values and tests for tie transitions (NE_c == 0 <=> m_{c+1} == m_c and m_{c-1} ==
+// m_{c-2}, i.e. E_{c+2} && E_c with E_s = (d_s == d_{s-1}), d_s = f_s - f_{s-1}); only a chunk holding
+// a transition evaluates the per-node form, for the interior nodes 1..nk-3.  The three end-node
+// terms (nodes 0, nk-2, nk-1) are added once per pair after the loop from the saved values fe.
+//
+// Lane `lane` holds the chunk nodes n = NPL*lane + r (r < NPL) and owns the correction term of node
+// c = base + n - 2.  The left neighbours of a lane's first node come from two shuffles; the previous
+// chunk's last four values (W.fc) supply lane 0, and three carried bits per pair (E at the last two
+// nodes, z at the last owned node) connect the tie flags across chunks.
 // ------------------------------------------------------------------------------------------
 template <bool EDGE>
-__device__ __forceinline__ void pair_phase(FastWarp& W, int np, int s, int base, int nk, int lane, double kp,
-                                           double dx, double inv_dx, double inv_hl, unsigned& zdirty) {
+__device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk, int lane, double dx, double hl,
+                                           double inv_dx, double inv_hl, unsigned& cE1, unsigned& cE2,
+                                           unsigned& cZ) {
   const unsigned FULL = 0xffffffffu;
-  const bool valid = s < nk;
-  const double wtrap = (s >= 1 && valid) ? 0.5 * dx : 0.0;  // the last interval is fixed up after the loop
-  const int cn = s - 2;
-  const bool cvalid = EDGE ? ((cn >= 0) && (cn <= nk - 3)) : true;
-#pragma unroll 1
-  for (int q = 0; q < np; ++q) {
-    const int2 po = W.po[q];
-    double* sf = W.sf[q & 1];
-    // cl_integrand (src/ccl_cls.c:166-187): k P d1 d2, exactly 0 when either transfer vanishes
-    // (lanes past the last node read stale shared memory: select, do not multiply by zero)
-    const double f4 = valid ? kp * W.dflat[po.x + lane] * W.dflat[po.y + lane] : 0.0;
-    sf[4 + lane] = f4;
-    if (lane < 4) sf[lane] = W.fc[q][lane];
-    if (EDGE) {  // f_0..f_2 and f_{nk-5}..f_{nk-1} feed the end-node terms
-      if (s < 3) W.fe[q][s] = f4;
-      const int r = s - (nk - 5);
-      if (r >= 0 && valid) W.fe[q][3 + r] = f4;
-    }
-    __syncwarp();
-    const double f0 = sf[lane], f1 = sf[lane + 1], f2 = sf[lane + 2], f3 = sf[lane + 3];
-    if (lane >= 28) W.fc[q][lane - 28] = f4;
-    const double da = f1 - f0, db = f2 - f1, dc = f3 - f2, dd = f4 - f3;
-    bool z = (dd == dc) && (db == da);  // tie flag of node c
-    if (EDGE) {
-      // boundary slopes repeat the first difference of slopes: z_0 <=> m_1 == m_0; z_1 <=> m_2 == m_1 == m_0
-      if (cn == 0) z = (dd == dc);
-      if (cn == 1) z = (dd == dc) && (dc == db);
-      z = z && cvalid;
-    }
-    const unsigned zm = __ballot_sync(FULL, z);
-    const unsigned carry = (zdirty >> q) & 1u;
-    unsigned trans = (zm ^ ((zm << 1) | carry));
-    if (EDGE) {
-      unsigned m = (base == 0) ? ~7u : ~0u;  // node 0 has no left neighbour term; nodes 1..nk-3 only
-      if (nk - base < 32) m &= (1u << (nk - base)) - 1u;
-      trans &= m;
-    }
-    double add = wtrap * (f3 + f4);
-    if (trans != 0u) {
-      // ---- a tie transition in this chunk: per-node form for its interior nodes ----
-      double mm2 = da * inv_dx, mm1 = db * inv_dx, m0 = dc * inv_dx, mp1 = dd * inv_dx;
-      if (EDGE) {
-        if (cn == nk - 3) mp1 = dd * inv_hl;
-        if (cn == 1) mm2 = 2.0 * mm1 - m0;
-        if (cn == 0) { mm1 = 2.0 * m0 - mp1; mm2 = 3.0 * m0 - 2.0 * mp1; }
-      }
-      const bool zprev = lane ? ((zm >> (lane - 1)) & 1u) : (carry != 0u);
-      if (((trans >> lane) & 1u) != 0u) {
-        const double d12 = fabs(mm1 - mm2);
-        const double NE = fabs(mp1 - m0) + d12;
-        double tc = 0.0;
-        if (!z && NE != 0.0) {
-          const double alpha = d12 / NE;
-          tc = (1.0 - alpha) * mm1 + alpha * m0;
-        }
-        double cc = z ? 0.0 : tc;
-        if (!zprev) cc -= (z ? mm1 : tc);
-        add += cc * (dx * dx * (1.0 / 12.0));
-      }
-    }
-    W.acc[q][lane] += add;
-    const unsigned top = (zm >> 31) & 1u;  // tie flag of this chunk's last node, carried to the next chunk
-    if ((carry | top) != 0u) zdirty = (zdirty & ~(1u << q)) | (top << q);
+  const int n0 = NPL * lane;
+  double kpv[NPL], wn[NPL];
+  unsigned vmask[NPL];
+  if (NPL == 2) {
+    const double2 k2 = *reinterpret_cast<const double2*>(&W.kp[n0]);
+    kpv[0] = k2.x; kpv[1] = k2.y;
+  } else {
+    const double2 k2 = *reinterpret_cast<const double2*>(&W.kp[n0]);
+    const double2 k3 = *reinterpret_cast<const double2*>(&W.kp[n0 + 2]);
+    kpv[0] = k2.x; kpv[1] = k2.y; kpv[NPL - 2] = k3.x; kpv[NPL - 1] = k3.y;
   }
-}
-
-// Interior chunks (every lane holds a node in 4..nk-6 of the uniform part of the grid): the same sums
-// without the shared-memory window.  The left neighbour's value and first difference come from two
-// warp shuffles; the tie flags follow from ONE ballot of E_s = (d_s == d_{s-1}), d_s = f_s - f_{s-1}:
-// z_c = E_{c+2} && E_c.  The previous chunk's last four values (W.fc, also what the edge form reads)
-// supply lane 0's neighbour and the two carried E bits.
-__device__ __forceinline__ void pair_phase_interior(FastWarp& W, int np, int lane, double kp, double dx,
-                                                    double inv_dx, unsigned& zdirty) {
-  const unsigned FULL = 0xffffffffu;
-  const double wtrap = 0.5 * dx;
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) {
+    if (EDGE) {
+      const int s = base + n0 + r;
+      double w = dx;
+      if (s == 0) w = 0.5 * dx;
+      if (s == nk - 2) w = 0.5 * dx + 0.5 * hl;  // the last interval ends on lkmax itself (ccl_linear_spacing)
+      if (s == nk - 1) w = 0.5 * hl;
+      if (s >= nk) w = 0.0;
+      wn[r] = w;
+      vmask[r] = __ballot_sync(FULL, s >= 3 && s <= nk - 1);  // owned correction node c = s - 2 in 1..nk-3
+    } else {
+      wn[r] = dx;
+      vmask[r] = FULL;
+    }
+  }
+  const bool first = EDGE && (base == 0);
 #pragma unroll 1
   for (int q = 0; q < np; ++q) {
     const int2 po = W.po[q];
-    const double f4 = kp * W.dflat[po.x + lane] * W.dflat[po.y + lane];
-    const double2 ca = *reinterpret_cast<const double2*>(&W.fc[q][0]);  // f at nodes base-4, base-3
-    const double2 cb = *reinterpret_cast<const double2*>(&W.fc[q][2]);  // f at nodes base-2, base-1
-    const double cd1 = cb.y - cb.x, cd2 = cb.x - ca.y, cd3 = ca.y - ca.x;  // d at base-1, base-2, base-3
-    double f3 = __shfl_up_sync(FULL, f4, 1);
-    if (lane == 0) f3 = cb.y;
-    const double dd = f4 - f3;
-    double dc = __shfl_up_sync(FULL, dd, 1);
-    if (lane == 0) dc = cd1;
-    const unsigned em = __ballot_sync(FULL, dd == dc);
-    const unsigned ec = (cd2 == cd3 ? 1u : 0u) | (cd1 == cd2 ? 2u : 0u);  // E at nodes base-2, base-1
-    const unsigned zm = em & ((em << 2) | ec);  // bit lane: tie flag of node c = base + lane - 2
-    __syncwarp();  // every lane has read W.fc
-    if (lane >= 28) W.fc[q][lane - 28] = f4;
-    const unsigned carry = (zdirty >> q) & 1u;
-    const unsigned trans = zm ^ ((zm << 1) | carry);
-    double add = wtrap * (f3 + f4);
-    if (trans != 0u) {
-      // ---- a tie transition in this chunk: per-node form (see pair_phase) ----
-      double db = __shfl_up_sync(FULL, dd, 2), da = __shfl_up_sync(FULL, dd, 3);
-      if (lane < 2) db = (lane == 1) ? cd1 : cd2;
-      if (lane < 3) da = (lane == 2) ? cd1 : ((lane == 1) ? cd2 : cd3);
-      if (((trans >> lane) & 1u) != 0u) {
-        const double mm2 = da * inv_dx, mm1 = db * inv_dx, m0 = dc * inv_dx, mp1 = dd * inv_dx;
-        const bool z = ((zm >> lane) & 1u) != 0u;
-        const bool zprev = lane ? (((zm >> (lane - 1)) & 1u) != 0u) : (carry != 0u);
-        const double d12 = fabs(mm1 - mm2);
-        const double NE = fabs(mp1 - m0) + d12;
-        double tc = 0.0;
-        if (!z && NE != 0.0) {
-          const double alpha = d12 / NE;
-          tc = (1.0 - alpha) * mm1 + alpha * m0;
-        }
-        double cc = z ? 0.0 : tc;
-        if (!zprev) cc -= (z ? mm1 : tc);
-        add += cc * (dx * dx * (1.0 / 12.0));
+    // cl_integrand (src/ccl_cls.c:166-187): k P d1 d2 (nodes past the end hold zeros)
+    double f[NPL], d[NPL];
+    {
+      const double2 a0 = *reinterpret_cast<const double2*>(&W.dflat[po.x + n0]);
+      const double2 b0 = *reinterpret_cast<const double2*>(&W.dflat[po.y + n0]);
+      f[0] = kpv[0] * a0.x * b0.x;
+      f[1] = kpv[1] * a0.y * b0.y;
+      if (NPL == 4) {
+        const double2 a1 = *reinterpret_cast<const double2*>(&W.dflat[po.x + n0 + 2]);
+        const double2 b1 = *reinterpret_cast<const double2*>(&W.dflat[po.y + n0 + 2]);
+        f[NPL - 2] = kpv[NPL - 2] * a1.x * b1.x;
+        f[NPL - 1] = kpv[NPL - 1] * a1.y * b1.y;
       }
     }
-    W.acc[q][lane] += add;
-    const unsigned top = (zm >> 31) & 1u;
-    if ((carry | top) != 0u) zdirty = (zdirty & ~(1u << q)) | (top << q);
+    const double2 c01 = *reinterpret_cast<const double2*>(&W.fc[q][0]);  // f at nodes base-4, base-3
+    const double2 c23 = *reinterpret_cast<const double2*>(&W.fc[q][2]);  // f at nodes base-2, base-1
+    const double cd1 = c23.y - c23.x;                                      // d at node base-1
+    double pf = __shfl_up_sync(FULL, f[NPL - 1], 1);
+    if (lane == 0) pf = c23.y;
+    d[0] = f[0] - pf;
+#pragma unroll
+    for (int r = 1; r < NPL; ++r) d[r] = f[r] - f[r - 1];
+    double pd = __shfl_up_sync(FULL, d[NPL - 1], 1);
+    if (lane == 0) pd = cd1;
+    unsigned m[NPL], zm[NPL], tr[NPL];
+    m[0] = __ballot_sync(FULL, d[0] == pd);
+#pragma unroll
+    for (int r = 1; r < NPL; ++r) m[r] = __ballot_sync(FULL, d[r] == d[r - 1]);
+    if (first) {
+      // boundary slopes repeat the first difference of slopes (gsl akima_init): z_0 <=> m_1 == m_0 and
+      // z_1 <=> m_2 == m_1 == m_0, i.e. E_0 := true, E_1 := E_2
+      const unsigned e2 = (NPL == 2) ? ((m[0] >> 1) & 1u) : (m[NPL - 2] & 1u);
+      m[0] |= 1u;
+      m[1] = (m[1] & ~1u) | e2;
+    }
+    const unsigned qE1 = (cE1 >> q) & 1u, qE2 = (cE2 >> q) & 1u, qZ = (cZ >> q) & 1u;
+    if (NPL == 2) {
+      zm[0] = m[0] & ((m[0] << 1) | qE2);
+      zm[1] = m[1] & ((m[1] << 1) | qE1);
+    } else {
+      zm[NPL - 2] = m[NPL - 2] & m[0];
+      zm[NPL - 1] = m[NPL - 1] & m[1];
+      zm[0] = m[0] & ((m[NPL - 2] << 1) | qE2);
+      zm[1] = m[1] & ((m[NPL - 1] << 1) | qE1);
+    }
+    tr[0] = (zm[0] ^ ((zm[NPL - 1] << 1) | qZ)) & vmask[0];
+    unsigned any = tr[0];
+#pragma unroll
+    for (int r = 1; r < NPL; ++r) {
+      tr[r] = (zm[r] ^ zm[r - 1]) & vmask[r];
+      any |= tr[r];
+    }
+    double acc = W.acc[q][lane];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) acc = fma(wn[r], f[r], acc);
+    if (EDGE) {  // f_0..f_2 and f_{nk-5}..f_{nk-1} feed the end-node terms
+#pragma unroll
+      for (int r = 0; r < NPL; ++r) {
+        const int s = base + n0 + r;
+        if (s < 3) W.fe[q][s] = f[r];
+        const int e = s - (nk - 5);
+        if (e >= 0 && s < nk) W.fe[q][3 + e] = f[r];
+      }
+    }
+    if (any != 0u) {
+      // ---- a tie transition in this chunk: per-node form for the flagged nodes ----
+      const double cd2 = c23.x - c01.y, cd3 = c01.y - c01.x;  // d at nodes base-2, base-3
+      double w4[NPL + 3];  // d at chunk nodes n0-3 .. n0+NPL-1
+      if (NPL == 2) {
+        double p0 = __shfl_up_sync(FULL, d[0], 1), pp1 = __shfl_up_sync(FULL, d[1], 2);
+        if (lane == 0) { p0 = cd2; pp1 = cd3; }
+        if (lane == 1) pp1 = cd1;
+        w4[0] = pp1; w4[1] = p0;
+      } else {
+        double p1 = __shfl_up_sync(FULL, d[1], 1), p2 = __shfl_up_sync(FULL, d[NPL - 2], 1);
+        if (lane == 0) { p1 = cd3; p2 = cd2; }
+        w4[0] = p1; w4[1] = p2;
+      }
+      w4[2] = pd;
+#pragma unroll
+      for (int r = 0; r < NPL; ++r) w4[3 + r] = d[r];
+#pragma unroll
+      for (int r = 0; r < NPL; ++r) {
+        if (((tr[r] >> lane) & 1u) != 0u) {
+          const int cn = base + n0 + r - 2;
+          double mm2 = w4[r] * inv_dx, mm1 = w4[r + 1] * inv_dx, m0 = w4[r + 2] * inv_dx, mp1 = w4[r + 3] * inv_dx;
+          if (EDGE) {
+            if (cn == nk - 3) mp1 = w4[r + 3] * inv_hl;
+            if (cn == 1) mm2 = 2.0 * mm1 - m0;
+          }
+          const bool z = ((zm[r] >> lane) & 1u) != 0u;
+          bool zprev;
+          if (r > 0) zprev = ((zm[r > 0 ? r - 1 : 0] >> lane) & 1u) != 0u;
+          else zprev = lane ? (((zm[NPL - 1] >> (lane - 1)) & 1u) != 0u) : (qZ != 0u);
+          const double d12 = fabs(mm1 - mm2);
+          const double NE = fabs(mp1 - m0) + d12;
+          double tc = 0.0;
+          if (!z && NE != 0.0) {
+            const double alpha = d12 / NE;
+            tc = (1.0 - alpha) * mm1 + alpha * m0;
+          }
+          double cc = z ? 0.0 : tc;
+          if (!zprev) cc -= (z ? mm1 : tc);
+          acc += cc * (dx * dx * (1.0 / 12.0));
+        }
+      }
+    }
+    W.acc[q][lane] = acc;
+    __syncwarp();  // every lane has read W.fc
+    if (NPL == 2) {
+      if (lane >= 30) *reinterpret_cast<double2*>(&W.fc[q][2 * (lane - 30)]) = make_double2(f[0], f[1]);
+    } else {
+      if (lane == 31) {
+        *reinterpret_cast<double2*>(&W.fc[q][0]) = make_double2(f[0], f[1]);
+        *reinterpret_cast<double2*>(&W.fc[q][2]) = make_double2(f[NPL - 2], f[NPL - 1]);
+      }
+    }
+    const unsigned bit = 1u << q;
+    cE1 = (cE1 & ~bit) | ((m[NPL - 1] >> 31) << q);
+    cE2 = (cE2 & ~bit) | ((m[NPL - 2] >> 31) << q);
+    cZ = (cZ & ~bit) | ((zm[NPL - 1] >> 31) << q);
   }
 }
 
@@ -391,13 +523,12 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
     for (int ls = 0; ls < nls; ++ls)
       s_tr[t].pref[ls] = tracer_prefactor(tr, P.ells[il0 + ls]) * (fold ? tr.const_transfer_value : 1.0);
   }
-  for (int c = threadIdx.x; c < P.ncoll; c += blockDim.x) S.colls[c] = P.colls[c];
   if (threadIdx.x == 32) S.achi = cs->achi;
   if (threadIdx.x == 64) S.psp = *cs->psp;
 
   const GridDesc* grids = G.grids + (size_t)ic * G.gstride;
   const GridPair* gpairs = G.gpairs + (size_t)ic * G.gstride;
-  const int* gcolls = G.gcolls + (size_t)ic * G.cstride;
+  const unsigned* gsubs = G.gsubs + (size_t)ic * G.sstride;
   const unsigned FULL = 0xffffffffu;
   const int ngrids = G.ngrids[ic];
   const int ntasks = ngrids * nls;  // task = (ell of the tile, grid)
@@ -440,40 +571,19 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
       const int ls = S.gp[gl].ls;
       const int il = il0 + ls;
       const double lp1h = P.ells[il] + 0.5;
-      const int ncoll = gd.ncoll, np = gd.npair;
+      const int ncoll = gd.ncoll, np = gd.npair, nsub = gd.nsub;
       __syncwarp();
       if (lane < np) {
         const GridPair pr = gpairs[gd.pair_begin + lane];
-        W.prs[lane] = pr;
-        W.po[lane] = make_int2(pr.a * 32, pr.b * 32);
+        W.po[lane] = make_int2(pr.a * CH, pr.b * CH);
       }
-      // flatten the grid's collections into one sub-tracer list (lane c expands collection c)
-      int2 cr = make_int2(0, 0);
-      if (lane < ncoll) cr = S.colls[gcolls[gd.coll_begin + lane]];
-      int off = cr.y;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL, off, o);
-        if (lane >= o) off += v;
-      }
-      bool task_rsd = false;
-      if (RSD) {
-        bool mine = false;
-        for (int j = 0; j < cr.y; ++j) mine = mine || (s_tr[cr.x + j].der_bessel >= 1);
-        task_rsd = __any_sync(FULL, mine);
-      }
-      const int nsub = __shfl_sync(FULL, off, 31);
-      off -= cr.y;
-      if (nsub <= NSG)
-        for (int j = 0; j < cr.y; ++j)
-          W.subs[off + j] = (unsigned)(cr.x + j) | ((unsigned)lane << 8) | (j == 0 ? SUB_FIRST : 0u) |
-                            (j == cr.y - 1 ? SUB_LAST : 0u);
+      if (lane < min(nsub, NSG)) W.subs[lane] = gsubs[gd.sub_begin + lane];
+      const bool task_rsd = RSD && gd.has_rsd;
       const int nk = S.gp[gl].nk;
       const double lkmin = S.gp[gl].lkmin, lkmax = S.gp[gl].lkmax;
-      __syncwarp();
       if (nk < 5) {  // gsl_spline_alloc(akima, n < 5) fails: NaN + CCL_ERROR_INTEG
         if (lane < np) {
-          const int ip = W.prs[lane].out;
+          const int ip = gpairs[gd.pair_begin + lane].out;
           const size_t s = (size_t)ic * P.npair + ip;
           P.cl[s * P.nl + il] = nan("");
           P.status[s] = ST_ERR_INTEG;
@@ -484,94 +594,127 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
       // outside the P(k,a) table in ln k, or more sub-tracers than the list holds: general kernel
       bool redo = !(lkmin >= S.psp.lkmin && lkmax <= S.psp.lkmax) || nsub > NSG;
       const double dx = S.gp[gl].dx, hl = S.gp[gl].hl, inv_dx = S.gp[gl].inv_dx, inv_hl = S.gp[gl].inv_hl;
-      // k and chi advance by constant ratios from chunk to chunk (one exp per lane per grid)
+      // k and chi advance by constant ratios from one 32-node sub-chunk to the next (one exp per lane per grid)
       double k = exp(lkmin + dx * lane);
       double chi = lp1h / k;
-      unsigned zdirty = 0u;  // bit q: the last node of pair q's previous chunk was an Akima tie
+      unsigned cE1 = 0u, cE2 = 0u, cZ = 0u;  // bit q: carried tie flags of pair q (see pair_phase)
       for (int i = lane; i < NPG * 4; i += 32) (&W.fc[0][0])[i] = 0.0;  // f at nodes -4..-1: finite placeholders
 #pragma unroll 1
       for (int q = 0; q < np; ++q) W.acc[q][lane] = 0.0;
+      __syncwarp();
 
 #pragma unroll 1
-      for (int base = 0; base < nk && !redo; base += 32) {
-        // ---------------- phase 1: node quantities (lane = node base + lane) ----------------
-        const int s = base + lane;
+      for (int base = 0; base < nk && !redo; base += CH) {
+        // ---------------- phase 1: node quantities (lane = node base + 32 u + lane) ----------------
         bool bad = false;
-        double kp = 0.0;
-        if (s < nk) {
-          const double lk = (s == 0) ? lkmin : ((s == nk - 1) ? lkmax : lkmin + dx * s);
-          // ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277); chi > 0 here
-          double a = 1.0;
-          if (!(chi < 1.e-8)) {
-            if (chi >= S.achi.x0 && chi <= S.achi.xn) a = rec_value(find_rec(S.achi, chi), chi);
-            else bad = true;  // GSL_EDOM: the general kernel reports it
-          }
-          if (!(a >= S.psp.amin && a <= S.psp.amax)) bad = true;  // growth extrapolation: general kernel
-          double pk = 0.0;
-          if (!bad) pk = exp(bicubic_eval(S.psp, lk, a, 0));
-          kp = k * pk;
-          double chi_lp = 0.0, a_lp = 1.0, sqell = 0.0;
-          if (RSD && task_rsd) {
-            const double lp3h = lp1h + 1.0;
-            chi_lp = lp3h / k;
-            if (!(chi_lp < 1.e-8)) {
-              if (chi_lp >= S.achi.x0 && chi_lp <= S.achi.xn) a_lp = rec_value(find_rec(S.achi, chi_lp), chi_lp);
-              else bad = true;
+#pragma unroll 1
+        for (int u = 0; u < NPL; ++u) {
+          const int j = 32 * u + lane;
+          const int s = base + j;
+          double kp = 0.0;
+          if (s < nk) {
+            const double lk = (s == 0) ? lkmin : ((s == nk - 1) ? lkmax : lkmin + dx * s);
+            // ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277); chi > 0 here
+            double a = 1.0;
+            if (!(chi < 1.e-8)) {
+              if (chi >= S.achi.x0 && chi <= S.achi.xn) {
+                const Rec1 r = find_rec(S.achi, chi);
+                a = cubic(make_double4(r.y, r.b, r.c, r.d), chi - r.x0);
+              } else
+                bad = true;  // GSL_EDOM: the general kernel reports it
             }
-            if (!(a_lp >= S.psp.amin && a_lp <= S.psp.amax)) bad = true;
-            if (!bad) sqell = sqrt(lp1h * fabs(exp(bicubic_eval(S.psp, lk, a_lp, 0)) / pk) / lp3h);
-          }
-          // transfer_limber_wrap (src/ccl_cls.c:150-164) for every collection of the grid, as one
-          // branch-free loop over the flattened sub-tracer list so that independent table lookups
-          // overlap.  Outside a kernel's support the lookup runs on the clamped abscissa and the
-          // term is dropped (ccl_f1d_t_eval: the end nodes count as outside, src/ccl_f1d.c:137-161).
-          double D = 0.0;
-#pragma unroll 2
-          for (int e = 0; e < nsub; ++e) {
-            const unsigned ent = W.subs[e];
-            const FastTr& tr = s_tr[ent & 0xffu];
-            const bool inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
-            double wt = rec_value(find_rec_lut(tr.kernel, chi), chi);  // index clamped inside; dropped if outside
-            if (tr.has_fa) {
-              const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
-              wt *= rec_value(find_rec_lut(tr.fa, a_ev), a_ev);
-            }
-            double val = inside ? wt * tr.pref[ls] : 0.0;
-            if (RSD && tr.der_bessel >= 1) {
-              // w t at chi is `inside ? wt : 0`; the second point has its own support test
-              const double l = lp1h - 0.5, lp3h = lp1h + 1.0;
-              const double w_t = inside ? wt : 0.0;
-              const bool inside_p = (chi_lp > tr.kernel.x0) && (chi_lp < tr.kernel.xn);
-              double wt_p = rec_value(find_rec_lut(tr.kernel, chi_lp), chi_lp);
-              if (tr.has_fa) {
-                const double a_ev = fmin(fmax(a_lp, tr.fa.x0), tr.fa.xn);
-                wt_p *= rec_value(find_rec_lut(tr.fa, a_ev), a_ev);
+            if (!(a >= S.psp.amin && a <= S.psp.amax)) bad = true;  // growth extrapolation: general kernel
+            double pk = 0.0;
+            if (!bad) pk = exp(bicubic_eval(S.psp, lk, a, 0));
+            kp = k * pk;
+            double chi_lp = 0.0, a_lp = 1.0, sqell = 0.0;
+            if (RSD && task_rsd) {
+              const double lp3h = lp1h + 1.0;
+              chi_lp = lp3h / k;
+              if (!(chi_lp < 1.e-8)) {
+                if (chi_lp >= S.achi.x0 && chi_lp <= S.achi.xn) {
+                  const Rec1 r = find_rec(S.achi, chi_lp);
+                  a_lp = cubic(make_double4(r.y, r.b, r.c, r.d), chi_lp - r.x0);
+                } else
+                  bad = true;
               }
-              if (!inside_p) wt_p = 0.0;
-              double dd;
-              if (tr.der_bessel == 1) dd = l * w_t / lp1h - sqell * wt_p;
-              else dd = sqell * 2 * wt_p / lp3h - (0.25 + 2 * l) * w_t / (lp1h * lp1h);
-              val = dd * tr.pref[ls];
+              if (!(a_lp >= S.psp.amin && a_lp <= S.psp.amax)) bad = true;
+              if (!bad) sqell = sqrt(lp1h * fabs(exp(bicubic_eval(S.psp, lk, a_lp, 0)) / pk) / lp3h);
             }
-            D = (ent & SUB_FIRST) ? val : D + val;
-            if (ent & SUB_LAST) W.dflat[((ent >> 8) & 0xffu) * 32 + lane] = D;
+            // transfer_limber_wrap (src/ccl_cls.c:150-164) for every collection of the grid, as one loop
+            // over the task's sub-tracer list.  Entries on the same spline grid share the interval search
+            // (ki, kdel for the kernels in chi; ai, adel for the a-only transfers); each then reads its own
+            // 32-byte coefficient record.  Outside a kernel's support the lookup runs on the first / last
+            // interval and the term is dropped (ccl_f1d_t_eval: the end nodes count as outside,
+            // src/ccl_f1d.c:137-161).
+            int ki = 0, ai = 0;
+            double kdel = 0.0, adel = 0.0;
+            bool inside = false;
+#pragma unroll TRU
+            for (int e = 0; e < nsub; ++e) {
+              const unsigned ent = W.subs[e];
+              const FastTr& tr = s_tr[ent & 0xffu];
+              if (ent & SUB_NEWK) {
+                double x0;
+                ki = find_interval(tr.kernel, chi, x0);
+                kdel = chi - x0;
+                inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
+              }
+              double wt = cubic(ldg4(tr.kernel.cr + ki), kdel);
+              if (tr.has_fa) {
+                if (ent & SUB_NEWA) {
+                  const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
+                  double x0;
+                  ai = find_interval(tr.fa, a_ev, x0);
+                  adel = a_ev - x0;
+                }
+                wt *= cubic(ldg4(tr.fa.cr + ai), adel);
+              }
+              double val = inside ? wt * tr.pref[ls] : 0.0;
+              if (RSD && tr.der_bessel >= 1) {
+                // w t at chi is `inside ? wt : 0`; the second point has its own support test
+                const double l = lp1h - 0.5, lp3h = lp1h + 1.0;
+                const double w_t = inside ? wt : 0.0;
+                const bool inside_p = (chi_lp > tr.kernel.x0) && (chi_lp < tr.kernel.xn);
+                double x0;
+                const int ip = find_interval(tr.kernel, chi_lp, x0);
+                double wt_p = cubic(ldg4(tr.kernel.cr + ip), chi_lp - x0);
+                if (tr.has_fa) {
+                  const double a_ev = fmin(fmax(a_lp, tr.fa.x0), tr.fa.xn);
+                  const int ia = find_interval(tr.fa, a_ev, x0);
+                  wt_p *= cubic(ldg4(tr.fa.cr + ia), a_ev - x0);
+                }
+                if (!inside_p) wt_p = 0.0;
+                double dd;
+                if (tr.der_bessel == 1) dd = l * w_t / lp1h - sqell * wt_p;
+                else dd = sqell * 2 * wt_p / lp3h - (0.25 + 2 * l) * w_t / (lp1h * lp1h);
+                val = dd * tr.pref[ls];
+              }
+              double* dp = &W.dflat[((ent >> 8) & 0xfu) * CH + j];
+              if (!(ent & SUB_FIRST)) val += *dp;
+              *dp = val;
+            }
+            k *= S.gp[gl].ratio;
+            chi *= S.gp[gl].iratio;
+          } else {
+            for (int c = 0; c < ncoll; ++c) W.dflat[c * CH + j] = 0.0;  // nodes past the end: f = 0
           }
-          k *= S.gp[gl].ratio;
-          chi *= S.gp[gl].iratio;
+          W.kp[j] = kp;
         }
         if (__any_sync(FULL, bad)) { redo = true; break; }
+        __syncwarp();
         // ---------------- phase 2: per-pair integrand and Akima integral ----------------
-        if ((base == 0) || (base + 31 >= nk - 5))
-          pair_phase<true>(W, np, s, base, nk, lane, kp, dx, inv_dx, inv_hl, zdirty);
+        if ((base == 0) || (base + CH - 1 >= nk - 5))
+          pair_phase<true>(W, np, base, nk, lane, dx, hl, inv_dx, inv_hl, cE1, cE2, cZ);
         else
-          pair_phase_interior(W, np, lane, kp, dx, inv_dx, zdirty);
+          pair_phase<false>(W, np, base, nk, lane, dx, hl, inv_dx, inv_hl, cE1, cE2, cZ);
         __syncwarp();
       }
 
       if (redo) {
         if (lane < np) {
           const unsigned long long task =
-              ((unsigned long long)ic * P.npair + W.prs[lane].out) * P.nl + il;
+              ((unsigned long long)ic * P.npair + gpairs[gd.pair_begin + lane].out) * P.nl + il;
           const unsigned long long at = atomicAdd(G.redo, 1ull);
           if (at < G.redo_cap) G.redo[1 + at] = task;
         }
@@ -579,7 +722,9 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
       }
       // ---- end-node terms, one lane per pair (nodes 0, nk-2, nk-1; gsl akima_init boundary slopes) ----
       double endc = 0.0;
+      int out = 0;
       if (lane < np) {
+        out = gpairs[gd.pair_begin + lane].out;
         const double* e = W.fe[lane];
         auto blend = [](double d12, double NE, double ml, double mr) {
           const double alpha = d12 / NE;
@@ -608,12 +753,13 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
           const double t1 = z1 ? 0.0 : blend(e12, NE1, md, me);
           if (!z2) endc -= hl * hl * (z1 ? md : t1);
         }
-        endc = endc * (1.0 / 12.0) + 0.5 * (hl - dx) * (g3 + g4);
+        endc = endc * (1.0 / 12.0);
       }
 #pragma unroll 1
       for (int q = 0; q < np; ++q) {
         const double v = warp_sum(W.acc[q][lane]) + __shfl_sync(FULL, endc, q);
-        if (lane == 0) P.cl[((size_t)ic * P.npair + W.prs[q].out) * P.nl + il] = v / lp1h;  // src/ccl_cls.c:340
+        const int o = __shfl_sync(FULL, out, q);
+        if (lane == 0) P.cl[((size_t)ic * P.npair + o) * P.nl + il] = v / lp1h;  // src/ccl_cls.c:340
       }
     }
   }
@@ -623,7 +769,8 @@ size_t limber_fast_plan_bytes(int ncosmo, int npair, unsigned long long redo_cap
   auto up = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t nc = (size_t)ncosmo, np = (size_t)npair;
   return up(nc * np * sizeof(GridDesc)) + up(nc * np * sizeof(GridPair)) + up(nc * 2 * np * sizeof(int)) +
-         up(nc * sizeof(int)) + up((redo_cap + 1) * sizeof(unsigned long long));
+         up(nc * sizeof(int)) + up(nc * np * 2 * 16 * sizeof(unsigned)) +
+         up((redo_cap + 1) * sizeof(unsigned long long));
 }
 
 FastPlan limber_fast_plan_carve(void* base, int ncosmo, int npair, unsigned long long redo_cap) {
@@ -635,9 +782,11 @@ FastPlan limber_fast_plan_carve(void* base, int ncosmo, int npair, unsigned long
   G.gpairs = reinterpret_cast<GridPair*>(p); p += up(nc * np * sizeof(GridPair));
   G.gcolls = reinterpret_cast<int*>(p); p += up(nc * 2 * np * sizeof(int));
   G.ngrids = reinterpret_cast<int*>(p); p += up(nc * sizeof(int));
+  G.gsubs = reinterpret_cast<unsigned*>(p); p += up(nc * np * 2 * 16 * sizeof(unsigned));
   G.redo = reinterpret_cast<unsigned long long*>(p);
   G.gstride = npair;
   G.cstride = 2 * npair;
+  G.sstride = npair * 2 * 16;
   G.redo_cap = redo_cap;
   G.ntr_max = FAST_MAX_TRACERS;
   G.has_rsd = 1;
@@ -645,11 +794,13 @@ FastPlan limber_fast_plan_carve(void* base, int ncosmo, int npair, unsigned long
 }
 
 cudaError_t launch_limber_fast(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream) {
+  static const bool use_v1 = getenv("CCL_B200_FAST_V1") != nullptr;
+  if (use_v1) return launch_limber_fast_v1(prob, plan, stream);
   if (prob.ncosmo == 0 || prob.npair == 0 || prob.nl == 0) return cudaSuccess;
   if ((long long)prob.ncosmo * prob.nl > 0x7fffffffLL) return cudaErrorInvalidValue;
   cudaMemsetAsync(plan.redo, 0, sizeof(unsigned long long), stream);
   const size_t gsm = sizeof(double) * 2 * ((size_t)prob.ncoll + prob.npair) + sizeof(int) * (size_t)prob.npair;
-  if (gsm > 48 * 1024)
+  if (gsm > 40 * 1024)
     cudaFuncSetAttribute(limber_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
   limber_group_kernel<<<prob.ncosmo, 128, gsm, stream>>>(prob, plan);
   const size_t fsm = fast_warp_offset(plan.ntr_max) + FW * sizeof(FastWarp);

@@ -42,9 +42,12 @@ enum : int { INTEG_QAG = 500, INTEG_SPLINE = 501 };                      // incl
 
 // One interval of a piecewise-cubic 1-D interpolant: p(x) = y + dx (b + dx (c + dx d)),
 // dx = x - x0, valid for x0 <= x < x1 (GSL's interval convention; last interval closed).
-// The interval's own end points travel with the coefficients so that a lookup is ONE 48-byte
-// record fetch: the index guess is verified against (x0, x1) without touching a node array.
-struct __align__(16) Rec1 {
+// Stored as two parallel arrays: the interval's end points {x0, x1} (16 B, one LDG.128) and its
+// coefficients {y, b, c, d} (32 B on a 32-byte boundary, one LDG.256).  An index guess is verified
+// against the interval's own end points without touching a node array, and splines on identical
+// grids (the lensing kernels of all source bins, the bias transfers of all lens bins) can share one
+// interval search and then read only their 32-byte coefficient records (limber_fast.cu).
+struct Rec1 {
   double x0, x1, y, b, c, d;
 };
 
@@ -59,7 +62,8 @@ struct __align__(32) AxisRec {
 // followed by a +-1 walk on the records until x0 <= x < x1, which reproduces
 // gsl_interp_bsearch exactly for any grid.
 struct Spline1D {
-  const Rec1* rec;  // [n-1]
+  const double2* xr;  // [n-1] {x_i, x_{i+1}}
+  const double4* cr;  // [n-1] {y_i, b_i, c_i, d_i}
   const int* lut;   // [nlut] (unused when uniform)
   int n, nlut, uniform, pad;
   double x0, xn;     // x[0], x[n-1]
@@ -138,6 +142,8 @@ struct GridDesc {
   double chi_min, chi_max;
   int coll_begin, ncoll;  // into gcolls (collection indices used by this grid's pairs)
   int pair_begin, npair;  // into gpairs
+  int sub_begin, nsub;    // into gsubs: the task's flattened sub-tracer list, ordered by spline grid
+  int has_rsd, pad;       // some sub-tracer of the task has der_bessel 1 or 2
 };
 struct GridPair {
   int out;     // pair index in the caller's list
@@ -148,7 +154,8 @@ struct FastPlan {
   GridPair* gpairs; // [ncosmo][gstride]
   int* gcolls;      // [ncosmo][cstride]
   int* ngrids;      // [ncosmo]
-  int gstride, cstride;
+  unsigned* gsubs;  // [ncosmo][sstride] sub-tracer entries of every grid task (limber_fast.cu)
+  int gstride, cstride, sstride;
   int ntr_max;  // largest sub-tracer count of any cosmology of the launch (sizes shared memory)
   int has_rsd;  // some sub-tracer has der_bessel 1 or 2: launch the kernel variant that handles them
   unsigned long long* redo;  // [0] = count, [1..redo_cap] = task ids left to the general kernel
@@ -156,8 +163,8 @@ struct FastPlan {
 };
 
 // ---- table-preparation jobs (device kernels fill the derived regions of the arena) ----
-struct AkimaJob { const double* x; const double* y; Rec1* rec; int n; };
-struct CsplineJob { const double* x; const double* y; Rec1* rec; double* scratch; int n; };
+struct AkimaJob { const double* x; const double* y; double2* xr; double4* cr; int n; };
+struct CsplineJob { const double* x; const double* y; double2* xr; double4* cr; double* scratch; int n; };
 struct LutJob { const double* x; int* lut; int n; int nlut; };
 struct AxisJob { const double* x; AxisRec* rec; int n; };
 struct BicubicJob {

@@ -21,8 +21,9 @@ def _check(status, where=""):
 
 
 def make_params(K_MAX=1e3, K_MIN=5e-5, DLOGK_INTEGRATION=0.025, INTEGRATION_LIMBER_EPSREL=1e-4,
-                N_ITERATION=1000, A_SPLINE_MIN=0.1):
-    return _lib.Params(K_MAX, K_MIN, DLOGK_INTEGRATION, INTEGRATION_LIMBER_EPSREL, N_ITERATION, A_SPLINE_MIN)
+                N_ITERATION=1000, A_SPLINE_MIN=0.1, INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS=4):
+    return _lib.Params(K_MAX, K_MIN, DLOGK_INTEGRATION, INTEGRATION_LIMBER_EPSREL, N_ITERATION,
+                       INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS, A_SPLINE_MIN)
 
 
 def _tracer_args(sub):

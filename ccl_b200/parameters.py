@@ -78,10 +78,15 @@ class SplineParams(CCLParameters):
 
 
 class GSLParams(CCLParameters):
-    """ccl_gsl_params (src/ccl_core.c:67-82)."""
+    """ccl_gsl_params (src/ccl_core.c:67-82).
+
+    The Gauss-Kronrod entries hold GSL's rule key like the reference (GSL_INTEG_GAUSS41 = 4,
+    src/ccl_core.c:40), not a node count.  Only GK41 exists on the device: a 'qag_quad' angular_cl
+    call on a cosmology created with another INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS raises CCLError
+    (CCL_ERROR_NOT_IMPLEMENTED) instead of silently using GK41."""
     _defaults = dict(
-        N_ITERATION=1000, INTEGRATION_GAUSS_KRONROD_POINTS=41, INTEGRATION_EPSREL=1E-4,
-        INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS=41, INTEGRATION_LIMBER_EPSREL=1E-4,
+        N_ITERATION=1000, INTEGRATION_GAUSS_KRONROD_POINTS=4, INTEGRATION_EPSREL=1E-4,
+        INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS=4, INTEGRATION_LIMBER_EPSREL=1E-4,
         INTEGRATION_DISTANCE_EPSREL=1E-6, INTEGRATION_SIGMAR_EPSREL=1E-5,
         INTEGRATION_KNL_EPSREL=1E-5, ROOT_EPSREL=1E-4, ROOT_N_ITERATION=1000,
         ODE_GROWTH_EPSREL=1E-6, EPS_SCALEFAC_GROWTH=1E-6, NZ_NORM_SPLINE_INTEGRATION=True,

@@ -36,6 +36,20 @@ def balance_tiles(weights, world):
     return [np.flatnonzero(owner == r) for r in range(world)]
 
 
+def make_tiles(npair, nl, pair_tile=32, ell_tile=128):
+    """Rectangular (pair, ell) tiles covering an [npair, nl] C_ell block: list of (p0, p1, l0, l1)."""
+    return [(p0, min(p0 + pair_tile, npair), l0, min(l0 + ell_tile, nl))
+            for p0 in range(0, int(npair), int(pair_tile)) for l0 in range(0, int(nl), int(ell_tile))]
+
+
+def tile_weights(batch, collections, pairs, ells, tiles):
+    """Integrand nodes (sum of nk over the tile's (pair, ell) entries, first cosmology of the batch) of every
+    tile: the work measure balance_tiles partitions on (nk varies 17..600 per C_ell)."""
+    ells = np.asarray(ells, dtype=np.float64)
+    return np.array([batch.spline_nodes(collections, list(pairs[p0:p1]), ells[l0:l1]) for p0, p1, l0, l1 in tiles],
+                    dtype=np.float64)
+
+
 def gather_blocks(local, sizes, dst=0, group=None):
     """Assemble per-rank blocks [sizes[r], ...] on rank `dst` with one collective.
 

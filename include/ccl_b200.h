@@ -57,6 +57,11 @@ typedef struct {
   double DLOGK_INTEGRATION;         /* 0.025 */
   double INTEGRATION_LIMBER_EPSREL; /* 1e-4  */
   int N_ITERATION;                  /* 1000  */
+  /* GSL key of the Gauss-Kronrod rule of 'qag_quad' (src/ccl_cls.c:240; gsl_integration.h: 1..6 = GK15, 21,
+   * 31, 41, 51, 61).  Default GSL_INTEG_GAUSS41 = 4 (src/ccl_core.c:40,71), the only rule built on the
+   * device: any other value makes a 'qag_quad' call fail with CCL_B200_ERROR_NOT_IMPLEMENTED instead of
+   * silently integrating with GK41. */
+  int INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS;
   double A_SPLINE_MIN;              /* 0.1: chi_max of kernel-less tracers = chi(A_SPLINE_MIN) */
 } ccl_b200_params;
 

@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 import oracle
-from common import chi_max_nokernel, oracle_cosmo, oracle_pk, oracle_tracer, parity_error
+from common import (chi_max_nokernel, edge_mask, edge_mask_subs, oracle_cosmo, oracle_pk, oracle_tracer,
+                    parity_error)
 
 pytestmark = pytest.mark.gpu
 
@@ -59,7 +60,8 @@ def test_single_pair_spline(setup, pair):
     assert np.all(np.isfinite(cl))
     redo = lambda: oracle.angular_cl(s["ocos"], _coll(s["otr"], c1), _coll(s["otr"], c2), s["opk"], ELLS,
                                      oracle.INTEG_SPLINE)[0]
-    assert parity_error(cl, ref, redo, SPLINE_RTOL) < SPLINE_RTOL
+    edge = edge_mask(_coll(s["otr"], c1), _coll(s["otr"], c2), ELLS)
+    assert parity_error(cl, ref, redo, SPLINE_RTOL, edge) < SPLINE_RTOL
 
 
 @pytest.mark.parametrize("pair", PAIRS[:5])
@@ -179,7 +181,8 @@ def test_batch_fast_path_matches_oracle(flavour):
         ref, _ = _oracle_all(bg, pk, subs, colls_i, pairs, ELLS, logp_shift=0.01 * ic)
         for q in range(len(pairs)):
             redo = lambda: _oracle_all(bg, pk, subs, colls_i, [pairs[q]], ELLS, logp_shift=0.01 * ic)[0][0]
-            assert parity_error(cl[ic, q], ref[q], redo, SPLINE_RTOL) < SPLINE_RTOL, (ic, pairs[q])
+            edge = edge_mask_subs(subs, colls_i, pairs[q], ELLS, chi_max_nokernel(bg))
+            assert parity_error(cl[ic, q], ref[q], redo, SPLINE_RTOL, edge) < SPLINE_RTOL, (ic, pairs[q])
 
 
 def test_batch_fast_equals_general_kernel(monkeypatch):
@@ -233,7 +236,8 @@ def test_batch_fast_redo_and_failures():
     for q in range(len(pairs)):
         if ok[q].any():
             redo = lambda: _oracle_all(bg, pk_cut, subs, colls, [pairs[q]], ELLS)[0][0][ok[q]]
-            assert parity_error(cl[0, q][ok[q]], ref[q][ok[q]], redo, SPLINE_RTOL) < SPLINE_RTOL, pairs[q]
+            edge = edge_mask_subs(subs, colls, pairs[q], ELLS, chi_max_nokernel(bg))[ok[q]]
+            assert parity_error(cl[0, q][ok[q]], ref[q][ok[q]], redo, SPLINE_RTOL, edge) < SPLINE_RTOL, pairs[q]
 
 
 def test_batch_stacked_setters_equal_per_slot():
@@ -296,7 +300,8 @@ def test_full_size_batch_properties():
         t = tables[ic % nd]
         shift = 1e-3 * (ic // nd)
         redo = lambda: _oracle_all(t["bg"], t["pk"], t["subs"], t["colls"], [pairs[q]], ells, logp_shift=shift)[0][0]
-        assert parity_error(cl[ic, q], redo(), redo, SPLINE_RTOL) < SPLINE_RTOL, (ic, pairs[q])
+        edge = edge_mask_subs(t["subs"], t["colls"], pairs[q], ells, t["cmax"])
+        assert parity_error(cl[ic, q], redo(), redo, SPLINE_RTOL, edge) < SPLINE_RTOL, (ic, pairs[q])
 
 
 def test_batch_edge_cases(synth):
@@ -323,7 +328,8 @@ def test_batch_edge_cases(synth):
     ref, rstat = _oracle_all(bg, pk, subs, colls, pairs, ells)
     for q in range(len(pairs)):
         redo = lambda: _oracle_all(bg, pk, subs, colls, [pairs[q]], ells)[0][0]
-        assert parity_error(cl[0, q], ref[q], redo, SPLINE_RTOL) < SPLINE_RTOL, pairs[q]
+        edge = edge_mask_subs(subs, colls, pairs[q], ells, chi_max_nokernel(bg))
+        assert parity_error(cl[0, q], ref[q], redo, SPLINE_RTOL, edge) < SPLINE_RTOL, pairs[q]
     clq, statq, stq = batch.angular_cl(colls, pairs, ells[2:7], cb._lib.INTEGRATION_QAG_QUAD)
     refq, _ = _oracle_all(bg, pk, subs, colls, pairs, ells[2:7], oracle.INTEG_QAG)
     assert stq == 0
@@ -445,7 +451,8 @@ def test_batch_fallbacks_to_general_kernel(synth):
     ref, _ = _oracle_all(bg, pk, subs, colls, pairs, ells)
     for q in range(len(pairs)):
         redo = lambda: _oracle_all(bg, pk, subs, colls, [pairs[q]], ells)[0][0]
-        assert parity_error(cl[0, q], ref[q], redo, SPLINE_RTOL) < SPLINE_RTOL, pairs[q]
+        edge = edge_mask_subs(subs, colls, pairs[q], ells, chi_max_nokernel(bg))
+        assert parity_error(cl[0, q], ref[q], redo, SPLINE_RTOL, edge) < SPLINE_RTOL, pairs[q]
     assert np.max(np.abs(cl[0, 2] / cl[0, 3] - 1)) < 1e-12          # 25 x (w/25) == w
     # (ii) a k-dependent 2-D transfer on one sub-tracer
     lk_t = np.linspace(np.log(1e-4), np.log(50.0), 40)
@@ -462,4 +469,5 @@ def test_batch_fallbacks_to_general_kernel(synth):
     ref2, _ = _oracle_all(bg, pk, subs2, colls0, pairs2, ells)
     for q in range(len(pairs2)):
         redo = lambda: _oracle_all(bg, pk, subs2, colls0, [pairs2[q]], ells)[0][0]
-        assert parity_error(cl2[0, q], ref2[q], redo, SPLINE_RTOL) < SPLINE_RTOL, pairs2[q]
+        edge = edge_mask_subs(subs2, colls0, pairs2[q], ells, cmax)
+        assert parity_error(cl2[0, q], ref2[q], redo, SPLINE_RTOL, edge) < SPLINE_RTOL, pairs2[q]

@@ -1,13 +1,16 @@
-# usage: bash tools/ab.sh [lib names...]; default: the in-tree build
-python -m pytest tests -m gpu -q 2>&1 | tail -3
+# usage: bash tools/ab.sh [lib names...]; default: the in-tree build.  A name "v1" runs the default build with
+# CCL_B200_FAST_V1=1 (round-1 kernel kept for A/B).
+python -m pytest tests -m gpu -q -x 2>&1 | tail -5
 libs="$@"; [ -z "$libs" ] && libs="libccl_b200"
 for v in $libs; do
   echo "== $v"
-  CCL_B200_LIB=$PWD/ccl_b200/$v.so python bench.py --ncosmo 512 --steps 3 --warmup 2 --no-e2e --no-cpu-baseline 2>&1 | python -c "
+  lib=$PWD/ccl_b200/$v.so; extra=""
+  if [ "$v" = "v1" ]; then lib=$PWD/ccl_b200/libccl_b200.so; export CCL_B200_FAST_V1=1; else unset CCL_B200_FAST_V1; fi
+  CCL_B200_LIB=$lib python bench.py --ncosmo ${NCOSMO:-512} --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>&1 | python -c "
 import sys,json
 for ln in sys.stdin:
     if ln.startswith('{'):
-        d=json.loads(ln); print('ms/step %.2f  frac %.4f  value %.3e fail %d'%(d['ms_per_step'],d['roofline']['frac'],d['value'],d['config']['failed_cl_entries']))
+        d=json.loads(ln); print('ms/step %.2f  frac %.4f  value %.3e fail %d maxerr %s'%(d['ms_per_step'],d['roofline']['frac'],d['value'],d['config']['failed_cl_entries'],d['config'].get('max_rel_err_vs_cpu')))
     else: print(ln.rstrip()[:200])
 "
 done

@@ -33,7 +33,7 @@ print("Y10 shear+IA: %d pairs x %d ells, fast path %s, status %d: %.2f ms per ca
       % (len(pairs), len(ells), batch.last_used_fast_path, st, dt * 1e3, len(pairs) * len(ells) / dt))
 if "--check" in sys.argv:
     import oracle
-    from common import oracle_cosmo, oracle_pk, oracle_tracer, parity_error
+    from common import edge_mask, oracle_cosmo, oracle_pk, oracle_tracer, parity_error
     oc, op = oracle_cosmo(bg), oracle_pk(pk)
     otr = [oracle_tracer(s, cmax) for s in subs]
     worst = 0.0
@@ -42,5 +42,5 @@ if "--check" in sys.argv:
         t1 = otr[colls[i][0]:colls[i][0] + colls[i][1]]
         t2 = otr[colls[j][0]:colls[j][0] + colls[j][1]]
         redo = lambda: oracle.angular_cl(oc, t1, t2, op, ells[::25], oracle.INTEG_SPLINE)[0]
-        worst = max(worst, parity_error(cl[0, q][::25], redo(), redo, 1e-10))
+        worst = max(worst, parity_error(cl[0, q][::25], redo(), redo, 1e-10, edge_mask(t1, t2, ells[::25])))
     print("max rel err vs oracle on a sample: %.3e" % worst)

@@ -47,3 +47,15 @@ up["eh_model1_pk"] = np.loadtxt(os.path.join(SRC, "model1_pk_eh.txt"))
 np.savez_compressed(os.path.join(OUT, "upstream_tables.npz"), **up)
 print("wrote %d arrays to %s" % (len(up), os.path.join(OUT, "upstream_tables.npz")))
 
+
+# ---- halofit pin: the reference's 3-D correlation benchmark of BBKS + halofit P(k) ----
+# benchmarks/data/model{1,2,3}_xi.txt: xi(r) at z = 0..5 from an independent code, asserted by the
+# reference at |r^2 dxi| < 3e-2 (benchmarks/test_correlation_3d.py:6-54, matter_power_spectrum='halofit').
+xi = {}
+for m in (1, 2, 3):
+    f = os.path.join(SRC, "model%d_xi.txt" % m)
+    if os.path.exists(f):
+        xi["model%d" % m] = np.loadtxt(f)
+if xi:
+    np.savez_compressed(os.path.join(OUT, "halofit_xi.npz"), **xi)
+    print("halofit_xi.npz:", {k: v.shape for k, v in xi.items()})
