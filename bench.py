@@ -2,16 +2,20 @@
 """bench.py -- Limber C_ell throughput of the B200 path (driver contract).
 
 Workload (BASELINE.json configs[3], the configuration the metric is quoted on):
-  4096 cosmologies x LSST-Y1-like 3x2pt (5 NumberCounts + 10 WeakLensing -> 120 pairs) x 100
-  log-spaced ells 2..3000, 'spline' Limber integration, fp64.  The batch is sharded by
-  cosmology over the N ranks (strong scaling of the 4096-cosmology job) and the C_ell blocks
+  4096 DISTINCT w0-wa cosmologies (Latin hypercube, seed 0) x LSST-Y1-like 3x2pt
+  (5 NumberCounts + 10 WeakLensing -> 120 pairs) x 100 log-spaced ells 2..3000, 'spline' Limber
+  integration, fp64.  Every table (E, chi(a), a(chi), growth, Eisenstein-Hu P(k) + sigma8, halofit, the 15
+  tracer kernels) is built by the device builders from the 7 parameters of each cosmology.  The batch is
+  sharded by cosmology over the N ranks (strong scaling of the 4096-cosmology job) and the C_ell blocks
   are gathered to rank 0 with one NCCL gather inside the timed region.
 
 One "step" = one pass of the hot path (ccl_angular_cls_limber for every cosmology, pair, ell)
 over the resident batch.  `value` is C_ell/s with all tables already in HBM; `e2e` times the
-host-buffer C-ABI path per step: staging of the flat host tables, one H2D copy, the device
-table preparation (spline coefficients / bicubic planes), the Limber kernel and the D2H copy
-of every C_ell.
+host-buffer C-ABI path per step: the caller's stacked host tables (pinned) -> H2D copies, the device
+table preparation (spline coefficients / bicubic planes), the Limber kernels and the D2H copy of every
+C_ell; `from_parameters` times parameters -> device-built tables -> C_ell with no table on the host;
+`qag` is the same resident pass with limber_integration_method='qag_quad' (pyccl's default) on a bounded
+number of cosmologies.
 
 `--impl reference` times the CPU restatement of the reference (oracle/, OpenMP over ell like
 src/ccl_cls.c:282-356, pairs serial like benchmarks/test_timing.py:31-34) on a bounded sample
@@ -32,7 +36,8 @@ sys.path.insert(0, ROOT)
 NCOSMO_TOTAL = 4096
 N_DISTINCT = 8          # distinct synthetic cosmologies; slots cycle through them with a P(k) offset
 NL = 100
-REF_SAMPLE = 64         # cosmologies per step of the CPU reference arm (~2 s on 16 host threads)
+REF_SAMPLE = 8          # cosmologies per step of the CPU reference arm (their host-built tables take ~5 s each)
+QAG_SAMPLE = 512        # cosmologies of the 'qag_quad' leg of the default run
 CPU_SAMPLE_S = 10.0     # seconds of CPU work of the cpu_baseline leg of the default run
 # algorithmic flops per integrand node: base + per-sub-tracer + Akima integral
 F_BASE, F_AKIMA = 81.0, 33.0
@@ -100,30 +105,24 @@ def stack_host_tables(tables, nslots, offset0=0):
     return stk
 
 
-def algorithmic_flops(batch, tables, nslots, colls, pairs, ells, offset0=0):
-    """Sum over (cosmology, pair, ell) of nk * (F_base + sum F_tracer + F_akima)."""
-    kinds = ["nc" if t[0] < 5 else "wl" for t in enumerate(colls)]
-    per_distinct = {}
-    nodes_tot, flops_tot = 0, 0.0
-    for ic in range(nslots):
-        key = (ic + offset0) % len(tables)
-        if key not in per_distinct:
-            rng_ = [batch.tracer_chi_range(ic, c[0]) for c in colls]   # one sub-tracer per collection here
-            nodes, flops = 0, 0.0
-            for (i, j) in pairs:
-                chi_min = max(rng_[i][0], rng_[j][0])
-                chi_max = min(rng_[i][1], rng_[j][1])
-                cm = np.where(chi_min <= 0, 0.5 * (ells + 0.5) / 1e3, chi_min)
-                lkmax = np.log(np.minimum(1e3, 2 * (ells + 0.5) / cm))
-                lkmin = np.log(np.maximum(5e-5, (ells + 0.5) / chi_max))
-                nk = (np.maximum((lkmax - lkmin) / 0.025 + 0.5, 1.0)).astype(int) + 1
-                nk = np.where(nk >= 5, nk, 0)
-                nodes += int(nk.sum())
-                flops += float(nk.sum()) * (F_BASE + F_SUB[kinds[i]] + F_SUB[kinds[j]] + F_AKIMA)
-            per_distinct[key] = (nodes, flops)
-        nodes_tot += per_distinct[key][0]
-        flops_tot += per_distinct[key][1]
-    return nodes_tot, flops_tot
+def algorithmic_flops(batch, colls, pairs, ells):
+    """Sum over (cosmology, pair, ell) of nk * (F_base + sum F_tracer + F_akima), exact: the node
+    counts come from ccl_b200_batch_spline_nodes (get_k_interval + the nk rule on every cosmology's own chi
+    ranges).  Collections 0..4 are NumberCounts (constant bias counted as the a-only cspline it is in the
+    reference, although the kernel folds it into the ell prefactor), 5..14 WeakLensing.
+    Returns (nodes, flops, mean flop per node without the Akima term)."""
+    kind = lambda c: "nc" if c < 5 else "wl"   # noqa: E731
+    nodes_tot, flops_tot, fl_noak = 0, 0.0, 0.0
+    for k1 in ("nc", "wl"):
+        for k2 in ("nc", "wl"):
+            sub = [p for p in pairs if (kind(p[0]), kind(p[1])) == (k1, k2)]
+            if not sub:
+                continue
+            n = int(batch.spline_nodes(colls, sub, ells))
+            nodes_tot += n
+            flops_tot += n * (F_BASE + F_SUB[k1] + F_SUB[k2] + F_AKIMA)
+            fl_noak += n * (F_BASE + F_SUB[k1] + F_SUB[k2])
+    return nodes_tot, flops_tot, fl_noak / max(nodes_tot, 1)
 
 
 class ClockSampler(threading.Thread):
@@ -169,28 +168,109 @@ def geometry():
     return colls, pairs, ells
 
 
+def lhs_cosmologies(n, seed=0):
+    """n derived-parameter dicts on a Latin hypercube (seed 0) over the SURVEY 8d config-4 ranges:
+    Omega_c [0.2, 0.35], Omega_b [0.04, 0.055], h [0.6, 0.8], n_s [0.92, 1.0], sigma8 [0.7, 0.9],
+    w0 [-1.3, -0.7], wa [-0.5, 0.5]."""
+    from ccl_b200.cosmology import Cosmology
+    rng = np.random.default_rng(seed)
+    lo = np.array([0.2, 0.04, 0.6, 0.92, 0.7, -1.3, -0.5])
+    hi = np.array([0.35, 0.055, 0.8, 1.0, 0.9, -0.7, 0.5])
+    u = np.stack([(rng.permutation(n) + rng.random(n)) / n for _ in range(7)], axis=1)
+    v = lo + u * (hi - lo)
+    return [Cosmology._build_parameters(Omega_c=r[0], Omega_b=r[1], h=r[2], n_s=r[3], sigma8=r[4], A_s=None,
+                                        Omega_k=0., Omega_g=None, Neff=3.044, m_nu=0., mass_split='normal',
+                                        w0=r[5], wa=r[6], T_CMB=2.7255, T_ncdm=0.71611) for r in v]
+
+
+LENS_BIAS = 1.0 + 0.2 * np.arange(5)
+
+
+def survey_nz():
+    """z grid and the 5 lens / 10 source n(z) of the LSST-Y1-like set."""
+    from ccl_b200 import synthetic as S
+    zz = np.linspace(0.0, 3.5, 500)
+    lens = S.smail_bins(zz, 0.26, 0.94, edges=np.arange(0.2, 1.2 + 1e-9, 0.2), sigma_z=0.03)
+    src = S.smail_bins(zz, 0.13, 0.78, nbins=10, sigma_z=0.05)
+    return zz, lens, src
+
+
+def stacked_row(stk, ic):
+    """Cosmology ic of a stacked-table dict as the flat per-cosmology tables the oracle helpers take:
+    (bg, pk, subs, chi_max_nokernel)."""
+    n_per, chi, a = stk["achi"]
+    n = int(n_per[ic])
+    ag, D = stk["growth"]
+    bg = dict(chi=np.ascontiguousarray(chi[ic, :n]), a=np.ascontiguousarray(a[ic, :n]),
+              a_growth=np.asarray(ag if np.ndim(ag) == 1 else ag[ic]), growth=np.ascontiguousarray(D[ic]))
+    lk, apk, pk, olo, ohi, islog = stk["pk"]
+    subs = []
+    for t in stk["tracers"]:
+        s = dict(der_bessel=t.get("der_bessel", 0), der_angles=t.get("der_angles", 0),
+                 chi=np.ascontiguousarray(t["chi"] if np.ndim(t["chi"]) == 1 else t["chi"][ic]),
+                 w=np.ascontiguousarray(t["w"][ic]))
+        if t.get("fa") is not None:
+            s["a"] = np.asarray(t["a"] if np.ndim(t["a"]) == 1 else t["a"][ic])
+            s["fa"] = np.ascontiguousarray(t["fa"][ic])
+        subs.append(s)
+    return bg, dict(lk=lk, a=apk, logp=pk[ic]), subs, float(stk["chi_max_nokernel"][ic])
+
+
+def host_tables_from_parameters(p):
+    """The same flat tables for one parameter set through the pyccl-compatible host classes (numpy twins of
+    the device builders): the inputs of the CPU reference arm, which must not touch the GPU."""
+    import ccl_b200 as ccl
+    zz, lens, src = survey_nz()
+    cosmo = ccl.Cosmology(Omega_c=p["Omega_c"], Omega_b=p["Omega_b"], h=p["h"], n_s=p["n_s"], sigma8=p["sigma8"],
+                          w0=p["w0"], wa=p["wa"], transfer_function='eisenstein_hu', matter_power_spectrum='halofit')
+    trc = [ccl.NumberCountsTracer(cosmo, has_rsd=False, dndz=(zz, n), bias=(zz, LENS_BIAS[i] * np.ones_like(zz)))
+           for i, n in enumerate(lens)]
+    trc += [ccl.WeakLensingTracer(cosmo, dndz=(zz, n)) for n in src]
+    cosmo.compute_growth()
+    b = cosmo._bg
+    pk = cosmo.get_nonlin_power()
+    bg = dict(chi=b.achi_chi, a=b.achi_a, a_growth=b.a, growth=b.growth)
+    subs = [t._trc[0] for t in trc]
+    return bg, dict(lk=pk._lk, a=pk._a, logp=pk._tab), subs, cosmo.chi_max_nokernel()
+
+
+def workload_config(ncosmo, method):
+    """The `config` object of the JSON line: identical in the B200 arm and the reference arm."""
+    return {"workload": "LSST-Y1-like 3x2pt likelihood batch (BASELINE configs[3]): %d cosmologies x 120 pairs "
+                        "(5 NumberCounts + 10 WeakLensing) x 100 log-spaced ells 2..3000" % ncosmo,
+            "method": method, "cosmologies": ncosmo, "distinct_cosmologies": ncosmo,
+            "parameters": "Latin hypercube (seed 0): Omega_c 0.2-0.35, Omega_b 0.04-0.055, h 0.6-0.8, n_s 0.92-1.0, "
+                          "sigma8 0.7-0.9, w0 -1.3--0.7, wa -0.5-0.5 (SURVEY 8d config 4)",
+            "tables": "per cosmology: E, chi(a), a(chi), growth, Eisenstein-Hu P(k) + sigma8, halofit, "
+                      "5 number-counts + 10 lensing kernels",
+            "sharding": "by cosmology, contiguous blocks, one gather",
+            "l2": "inputs larger than L2 (3.4 MB of tables per cosmology, 14 GB per 4096 cosmologies)"}
+
+
 def run_reference(args, rank, json_out=sys.stdout):
-    """CPU restatement of the reference on a bounded sample: 1 cosmology x 120 pairs x 100 ells."""
+    """CPU restatement of the reference on a bounded sample: REF_SAMPLE cosmologies x 120 pairs x 100 ells.
+    Pure host code: the sample's tables come from the numpy twins of the device builders."""
     if rank != 0:
         return
     import oracle
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from common import oracle_cosmo, oracle_pk, oracle_tracer
-    tables = build_host_tables(N_DISTINCT)
     colls, pairs, ells = geometry()
+    nsample = min(REF_SAMPLE, args.ncosmo)
+    plist = lhs_cosmologies(args.ncosmo)[:nsample]      # the first cosmologies of the same hypercube
+    integ = oracle.INTEG_SPLINE if args.method == "spline" else oracle.INTEG_QAG
     objs = []
-    for t in tables:
-        objs.append((oracle_cosmo(t["bg"]), oracle_pk(t["pk"]), [oracle_tracer(s, t["cmax"]) for s in t["subs"]]))
+    for p in plist:
+        bg, pk, subs, cmax = host_tables_from_parameters(p)
+        objs.append((oracle_cosmo(bg), oracle_pk(pk), [oracle_tracer(s_, cmax) for s_ in subs]))
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
     oracle.set_num_threads(len(os.sched_getaffinity(0)))
     cores = oracle.num_threads()
-    nsample = min(REF_SAMPLE, args.ncosmo)
 
     def one_pass():
-        for ic in range(nsample):   # the batch cycles through N_DISTINCT table sets, like the GPU arm's
-            oc, op, otr = objs[ic % len(objs)]
+        for oc, op, otr in objs:
             for (i, j) in pairs:
-                oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, oracle.INTEG_SPLINE)
+                oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, integ)
 
     for _ in range(max(args.warmup, 1)):
         one_pass()
@@ -200,18 +280,17 @@ def run_reference(args, rank, json_out=sys.stdout):
     dt = (time.perf_counter() - t0) / args.steps
     n_cl = nsample * len(pairs) * len(ells)
     val = n_cl / dt
-    sample = ("%d of %d cosmologies x 120 pairs x 100 ells per step ('spline'), pairs serial, OpenMP over ell"
-              % (nsample, args.ncosmo))
+    sample = ("%d of %d cosmologies x 120 pairs x 100 ells per step ('%s'), pairs serial, OpenMP over ell"
+              % (nsample, args.ncosmo, args.method))
     print(json.dumps({
-        "impl": "reference", "metric": "3x2pt C_ell/s (pair x ell), Limber 'spline'", "value": val,
+        "impl": "reference", "metric": "3x2pt C_ell/s (pair x ell), Limber '%s'" % args.method, "value": val,
         "unit": "C_ell/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "LSST-Y1-like 3x2pt likelihood batch (BASELINE configs[3]): %d cosmologies x "
-                               "120 pairs (5 NumberCounts + 10 WeakLensing) x 100 log-spaced ells 2..3000" % args.ncosmo,
-                   "method": "spline",
-                   "reference_impl": "oracle/ CPU restatement of src/ccl_cls.c + GSL (the GSL-based reference "
-                                     "is not buildable in this image: DESIGN.md section 3)"},
+        "config": workload_config(args.ncosmo, args.method),
+        "run": {"reference_impl": "oracle/ CPU restatement of src/ccl_cls.c + GSL, gcc -O3 -fomit-frame-pointer like "
+                                  "CMakeLists.txt:63 (the GSL-based reference is not buildable in this image: "
+                                  "DESIGN.md section 3)", "sample": sample},
         "cpu_baseline": {"value": val, "unit": "C_ell/s", "cores": cores, "kind": "port", "sample": sample,
                          "cosmologies_per_s": nsample / dt},
         "e2e": {"value": val, "unit": "C_ell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -241,8 +320,11 @@ def _main(json_out):
     ap.add_argument("--method", default="spline", choices=["spline", "qag_quad"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--from-parameters", type=int, default=0, metavar="N",
-                    help="also time parameters -> device-built tables -> C_ell for N cosmologies (extra key)")
+    ap.add_argument("--from-parameters", type=int, default=None, metavar="N",
+                    help="cosmologies of the parameters -> device-built tables -> C_ell leg (default: this rank's "
+                         "share of the batch; 0 skips it)")
+    ap.add_argument("--qag-sample", type=int, default=QAG_SAMPLE, metavar="N",
+                    help="cosmologies of the 'qag_quad' leg of a 'spline' run (0 skips it)")
     ap.add_argument("--e2e-trace", action="store_true", help="print the per-chunk stage timeline of one e2e step to stderr")
     ap.add_argument("--e2e-pageable", action="store_true",
                     help="keep the e2e input tables in pageable host memory (staged through pinned arenas by host threads)")
@@ -279,11 +361,21 @@ def _main(json_out):
     nloc = base + (1 if rank < rem else 0)
     off = rank * base + min(rank, rem)
 
-    tables = build_host_tables(N_DISTINCT)
+    # ---- the stated workload: nloc DISTINCT Latin-hypercube cosmologies, every table device-built ----
+    from ccl_b200 import device_builders as db
+    from ccl_b200.pipeline import slice_stacked
+    plist = lhs_cosmologies(args.ncosmo)
+    mine = plist[off:off + nloc]
+    zz, lens_nz, src_nz = survey_nz()
+    t_b = time.perf_counter()
+    stk, _ = db.build_3x2pt_stacked(mine, zz, lens_nz, src_nz, LENS_BIAS)   # device builders -> the caller's host tables
+    build_s = time.perf_counter() - t_b
+    if not args.e2e_pageable:
+        stk = cb.pin_stacked(stk)       # page-locked, as the contract asks: the library DMAs straight from these
     batch = cb.LibBatch(nloc)
-    fill_batch(batch, tables, nloc, off)
+    batch.set_stacked(0, stk)
     batch.commit()
-    nodes, flops = algorithmic_flops(batch, tables, nloc, colls, pairs, ells, off)
+    nodes, flops, f_node_noakima = algorithmic_flops(batch, colls, pairs, ells)
 
     d_cl = torch.empty((nloc, npair, nl), dtype=torch.float64, device="cuda")
     d_st = torch.zeros((2, nloc, npair), dtype=torch.int32, device="cuda")
@@ -352,18 +444,28 @@ def _main(json_out):
     # ---- fp64 roofline of the dominant kernel (this rank's launch) ----
     st = C.c_int(0)
     peak = _lib.load().ccl_b200_measure_fp64_peak(C.byref(st))
+    if args.method == "qag_quad":
+        # unit = one GK41 evaluation: the kernel counts them; same per-node costs, no Akima term
+        nodes = int(batch.last_qag_evals)
+        flops = nodes * f_node_noakima
     achieved = flops / (kern_ms * 1e-3) / 1e12
-    traffic = None
-    tfile = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes of one ncu capture (tools/ncu_traffic.sh)
+    traffic = executed = None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")   # one ncu capture of this launch (tools/ncu_traffic.sh)
     if os.path.exists(tfile):
         tj = json.load(open(tfile))
         if tj.get("ncosmo") == nloc and tj.get("method") == args.method:
             traffic = tj.get("dram_bytes_per_launch")
+            executed = tj.get("executed_fp64_flops_per_launch")
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak and peak > 0 else None, "traffic": traffic,
                 "kernel": ("limber_spline_fast_kernel" if batch.last_used_fast_path else "limber_spline_kernel")
-                if args.method == "spline" else "limber_qag_kernel",
+                if args.method == "spline" else "limber_qag_fast_kernel",
                 "kernel_ms": kern_ms, "algorithmic_flops_per_launch": flops, "integrand_nodes_per_launch": nodes,
+                "executed_fp64_flops_per_launch": executed,
+                "flop_model": "SURVEY 8d per node: 81 (k, chi, a(chi), bicubic P, product) + per sub-tracer (WL 10, "
+                              "NC 26 incl. its constant-bias a-only cspline, which the kernel folds into the ell "
+                              "prefactor) + 33 Akima; executed < algorithmic because a(chi), P and every "
+                              "collection's transfer are evaluated once per shared node grid",
                 "peak_source": "measured in-run: DFMA microbenchmark ccl_b200_measure_fp64_peak "
                                "(MEASURED_PEAKS.json holds no fp64 figure)"}
 
@@ -374,10 +476,6 @@ def _main(json_out):
         e2e_steps = max(1, min(args.steps, 3))
 
         parts = {"stage_host_tables_ms": 0.0, "h2d_and_table_prep_ms": 0.0, "limber_and_d2h_ms": 0.0}
-        stk = stack_host_tables(tables, nloc, off)              # the caller's host buffers
-        if not args.e2e_pageable:
-            # page-locked, as the contract asks: the library then DMAs straight from these arrays
-            stk = cb.pin_stacked(stk)
         cl_pinned = torch.empty((nloc, npair, nl), dtype=torch.float64, pin_memory=True).numpy()
 
         def serial_step():
@@ -438,40 +536,64 @@ def _main(json_out):
                        "into pinned arenas by host threads) -> H2D copies, device table prep, Limber kernels, D2H "
                        "of all C_ell into pinned memory; the three stages overlap across chunks of cosmologies"}
 
-    # ---- optional: the whole likelihood step from cosmological parameters (device-built tables) ----
+    # ---- the whole likelihood step from cosmological parameters (device-built tables, nothing on the host) ----
     from_parameters = None
-    if args.from_parameters and rank == 0:
-        from ccl_b200 import device_builders as db, synthetic as S
-        from ccl_b200.cosmology import Cosmology
-        nfp = min(nloc, args.from_parameters)
-        rng = np.random.default_rng(0)   # SURVEY 8d config 4 ranges
-        u = rng.random((nfp, 7))
-        lo = np.array([0.2, 0.04, 0.6, 0.92, 0.7, -1.3, -0.5])
-        hi = np.array([0.35, 0.055, 0.8, 1.0, 0.9, -0.7, 0.5])
-        v = lo + u * (hi - lo)
-        plist = [Cosmology._build_parameters(Omega_c=r[0], Omega_b=r[1], h=r[2], n_s=r[3], sigma8=r[4], A_s=None,
-                                             Omega_k=0., Omega_g=None, Neff=3.044, m_nu=0., mass_split='normal',
-                                             w0=r[5], wa=r[6], T_CMB=2.7255, T_ncdm=0.71611) for r in v]
-        zz = np.linspace(0.0, 3.5, 500)
-        lens = S.smail_bins(zz, 0.26, 0.94, edges=np.arange(0.2, 1.2 + 1e-9, 0.2), sigma_z=0.03)
-        src = S.smail_bins(zz, 0.13, 0.78, nbins=10, sigma_z=0.05)
-        fp_batch, fp_colls, fp_tabs = db.build_3x2pt_batch(plist, zz, lens, src, np.ones(5))   # warm-up
+    nfp = nloc if args.from_parameters is None else min(nloc, args.from_parameters)
+    if nfp and rank == 0:
+        fp_list = mine[:nfp]
+        fp_batch, fp_colls, fp_tabs = db.build_3x2pt_batch(fp_list, zz, lens_nz, src_nz, LENS_BIAS)   # warm-up
         d_cl2 = torch.empty((nfp, npair, nl), dtype=torch.float64, device="cuda")
         d_st2 = torch.zeros((2, nfp, npair), dtype=torch.int32, device="cuda")
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        fp_batch, fp_colls, fp_tabs = db.build_3x2pt_batch(plist, zz, lens, src, np.ones(5), batch=fp_batch)
+        fp_batch, fp_colls, fp_tabs = db.build_3x2pt_batch(fp_list, zz, lens_nz, src_nz, LENS_BIAS, batch=fp_batch)
         t1 = time.perf_counter()
         fp_batch.angular_cl_dev(fp_colls, pairs, ells, d_cl2.data_ptr(), d_st2.data_ptr(), method, stream)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
+        same = float(torch.max(torch.abs(d_cl2 - d_cl[:nfp]) / torch.clamp(torch.abs(d_cl[:nfp]), min=1e-300)).item())
         from_parameters = {"cosmologies": nfp, "cosmologies_per_s": nfp / (t2 - t0), "C_ell_per_s": nfp * npair * nl / (t2 - t0),
                            "build_tables_ms": (t1 - t0) * 1e3, "limber_ms": (t2 - t1) * 1e3,
                            "failed_cl_entries": int((d_st2[0] != 0).sum().item()), "fast_path": bool(fp_batch.last_used_fast_path),
-                           "note": "7-parameter w0-wa cosmologies (Latin-hypercube-like, seed 0) -> E, chi(a), a(chi), growth, "
-                                   "Eisenstein-Hu P(k) + sigma8, halofit, 5 number-counts + 10 lensing kernels -> 120 x 100 "
-                                   "C_ell, every table built and kept on the device"}
+                           "max_rel_diff_vs_host_buffer_tables": same,
+                           "note": "the batch's own 7-parameter cosmologies -> E, chi(a), a(chi), growth, Eisenstein-Hu P(k) + "
+                                   "sigma8, halofit, 5 number-counts + 10 lensing kernels -> 120 x 100 C_ell, every table "
+                                   "built and kept on the device"}
         del fp_batch, fp_tabs, d_cl2, d_st2
+
+    # ---- 'qag_quad' (pyccl's default method) on the first cosmologies of the same batch ----
+    qag = None
+    nq = min(nloc, args.qag_sample)
+    if nq and rank == 0 and world == 1 and args.method == "spline":
+        qb = cb.LibBatch(nq)
+        qb.set_stacked(0, slice_stacked(stk, 0, nq))
+        qb.commit()
+        d_clq = torch.empty((nq, npair, nl), dtype=torch.float64, device="cuda")
+        d_stq = torch.zeros((2, nq, npair), dtype=torch.int32, device="cuda")
+        qm = _lib.INTEGRATION_QAG_QUAD
+        for _ in range(2):
+            qb.angular_cl_dev(colls, pairs, ells, d_clq.data_ptr(), d_stq.data_ptr(), qm, stream)
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = 2
+        q0.record()
+        for _ in range(nrep):
+            qb.angular_cl_dev(colls, pairs, ells, d_clq.data_ptr(), d_stq.data_ptr(), qm, stream)
+        q1.record()
+        torch.cuda.synchronize()
+        q_ms = q0.elapsed_time(q1) / nrep
+        q_evals = int(qb.last_qag_evals)
+        q_comp = int(qb.last_qag_nodes_computed)
+        q_flops = q_evals * f_node_noakima
+        q_ach = q_flops / (q_ms * 1e-3) / 1e12
+        qag = {"value": nq * npair * nl / (q_ms * 1e-3), "unit": "C_ell/s", "cosmologies": nq, "ms_per_pass": q_ms,
+               "integrand_evaluations": q_evals, "evaluations_per_cl": q_evals / (nq * npair * nl),
+               "abscissae_computed": q_comp,
+               "achieved": q_ach, "frac": q_ach / peak if peak and peak > 0 else None,
+               "failed_cl_entries": int((d_stq[0] != 0).sum().item()),
+               "max_rel_err": None}
+        q_host = d_clq[:2].cpu().numpy()
+        del qb, d_stq
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -479,27 +601,31 @@ def _main(json_out):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from common import oracle_cosmo, oracle_pk, oracle_tracer
         oracle.set_num_threads(len(os.sched_getaffinity(0)))
-        # bounded sample: cosmologies of the batch, in slot order, until ~CPU_SAMPLE_S seconds of CPU work
-        # (the first N_DISTINCT slots are also the parity check of the GPU result)
+        # bounded sample: cosmologies of the batch, in slot order, until ~CPU_SAMPLE_S seconds of CPU work; every one
+        # of them is also a parity check of the GPU result (same tables on both sides)
         integ = oracle.INTEG_SPLINE if args.method == "spline" else oracle.INTEG_QAG
-        objs = {}
-        ndone, err = 0, 0.0
-        t_cpu = 0.0
+        ndone, err, t_cpu = 0, 0.0, 0.0
+        err_q = 0.0
         while ndone < nloc and t_cpu < CPU_SAMPLE_S:
-            key = (off + ndone) % len(tables)
-            if key not in objs:
-                t = tables[key]
-                objs[key] = (oracle_cosmo(t["bg"]), oracle_pk(t["pk"]), [oracle_tracer(s, t["cmax"]) for s in t["subs"]])
-            oc, op, otr = objs[key]
+            bg_i, pk_i, subs_i, cmax_i = stacked_row(stk, ndone)
+            oc, op = oracle_cosmo(bg_i), oracle_pk(pk_i)
+            otr = [oracle_tracer(s_, cmax_i) for s_ in subs_i]
             t0 = time.perf_counter()
             ref = np.empty((npair, nl))
             for q, (i, j) in enumerate(pairs):
                 ref[q], _ = oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, integ)
             t_cpu += time.perf_counter() - t0
-            if (off + ndone) < len(tables):   # unshifted slots: same tables on both sides
-                got = d_cl[ndone].cpu().numpy()
-                err = max(err, float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))))
+            got = d_cl[ndone].cpu().numpy()
+            scale = np.maximum(np.abs(ref), 1e-6 * np.max(np.abs(ref), axis=1, keepdims=True))
+            err = max(err, float(np.max(np.abs(got - ref) / np.maximum(scale, 1e-300))))
+            if qag is not None and ndone < 2:      # 'qag_quad' leg: GPU vs oracle on the first two cosmologies
+                for q, (i, j) in enumerate(pairs):
+                    rq, _ = oracle.angular_cl(oc, [otr[i]], [otr[j]], op, ells, oracle.INTEG_QAG)
+                    sc = np.maximum(np.abs(rq), 1e-6 * np.max(np.abs(rq)))
+                    err_q = max(err_q, float(np.max(np.abs(q_host[ndone, q] - rq) / np.maximum(sc, 1e-300))))
             ndone += 1
+        if qag is not None:
+            qag["max_rel_err"] = err_q
         cpu_baseline = {"value": ndone * npair * nl / t_cpu, "unit": "C_ell/s", "cores": oracle.num_threads(),
                         "kind": "port", "cosmologies_per_s": ndone / t_cpu,
                         "sample": "%d of %d cosmologies x 120 pairs x 100 ells (%.1f s of CPU work), '%s', pairs "
@@ -513,14 +639,14 @@ def _main(json_out):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "LSST-Y1-like 3x2pt likelihood batch (BASELINE configs[3]): %d cosmologies x "
-                                   "120 pairs (5 NumberCounts + 10 WeakLensing) x 100 log-spaced ells 2..3000"
-                                   % args.ncosmo,
-                       "method": args.method, "sharding": "by cosmology, contiguous blocks, one NCCL gather",
-                       "cosmologies_per_s": value / (npair * nl),
-                       "l2": "inputs larger than L2 (%.1f GB of tables per rank)" % (batch.arena_bytes / 1e9),
-                       "distinct_cosmologies": N_DISTINCT, "failed_cl_entries": n_fail},
+            "config": workload_config(args.ncosmo, args.method),
+            "run": {"cosmologies_per_s": value / (npair * nl), "failed_cl_entries": n_fail,
+                    "tables_gb_per_rank": batch.arena_bytes / 1e9, "gather": "one NCCL gather to rank 0" if world > 1 else None,
+                    "device_table_build_s_rank0": build_s,
+                    "fast_path": bool(fast_path),
+                    "qag_abscissae_computed": int(batch.last_qag_nodes_computed) if args.method == "qag_quad" else None},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "from_parameters": from_parameters,
+            "qag": qag,
             # fast 'spline' path: grouping + integrator + redo kernels per step; otherwise one kernel
             "gpu_launches": args.steps * (3 if fast_path else 1), "clocks": clocks,
         }), file=json_out)

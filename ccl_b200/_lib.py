@@ -94,6 +94,7 @@ SIGNATURES = {
                                                      C.c_int, _vp, _vp, _vp, _ip]),
     "ccl_b200_batch_spline_nodes": (C.c_ulonglong, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp]),
     "ccl_b200_batch_last_qag_evals": (C.c_ulonglong, [_vp]),
+    "ccl_b200_batch_last_qag_nodes_computed": (C.c_ulonglong, [_vp]),
     "ccl_b200_batch_last_used_fast_path": (C.c_int, [_vp]),
     "ccl_b200_build_linear_power": (None, [C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp,
                                            C.c_double, C.c_double, _dp, _dp, _ip]),

@@ -776,7 +776,7 @@ struct ccl_b200_collection { std::vector<ccl_b200_tracer*> ts; };
 struct ccl_b200_batch {
   ccl_b200_params params;
   TableSet ts;
-  unsigned long long last_qag_evals = 0;
+  unsigned long long last_qag_evals = 0, last_qag_nodes = 0;
   bool last_fast = false;  // the last 'spline' launch used the grid-sharing kernels
   cudaStream_t stream = nullptr;  // non-blocking: batches driven from different host threads overlap
   // commit() runs on its own high-priority stream: while another batch's Limber grid (tens of
@@ -1517,7 +1517,8 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
   const size_t o_el = o_pr + ((size_t)npair * 8 + 255) / 256 * 256;
   const size_t o_ct = o_el + ((size_t)nl * 8 + 255) / 256 * 256;
   const size_t o_fp = o_ct + 256;
-  const bool fast = (integration_method == INTEG_SPLINE) && fast_eligible(b, ncoll, npair);
+  static const bool no_qag_fast = getenv("CCL_B200_NO_QAG_FAST") != nullptr;
+  const bool fast = fast_eligible(b, ncoll, npair) && (integration_method == INTEG_SPLINE || !no_qag_fast);
   const unsigned long long redo_cap = 1ull << 20;
   const size_t total = o_fp + (fast ? limber_fast_plan_bytes(nc, npair, redo_cap) : 0);
   if (!b->call.reserve(total, status)) return;
@@ -1545,7 +1546,7 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
   std::unique_lock<std::mutex> lk(sc.mu, std::defer_lock);
   if (integration_method == INTEG_QAG) {
     lk.lock();
-    wsb = limber_qag_workspace_bytes(P.par.N_ITERATION);
+    wsb = limber_qag_workspace_bytes(P.par.N_ITERATION) + (fast ? limber_qag_fast_workspace_bytes(P.par.N_ITERATION) : 0);
     if (!sc.qag.reserve(wsb, status)) return;
     ws = reinterpret_cast<double*>(sc.qag.p);
   }
@@ -1558,14 +1559,21 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
       plan.ntr_max = std::max(plan.ntr_max, (int)c.tracers.size());
       for (const TracerPlan& t : c.tracers) plan.has_rsd |= (t.der_bessel > 0);
     }
-    if (!cuda_ok(launch_limber_fast(P, plan, stream), "limber fast launch", status)) return;
+    if (integration_method == INTEG_SPLINE) {
+      if (!cuda_ok(launch_limber_fast(P, plan, stream), "limber fast launch", status)) return;
+      return;
+    }
+    // 'qag_quad': grid-sharing panels, then the general kernel over the redo list, then CQUAD
+    if (!cuda_ok(launch_limber_qag_fast(P, plan, ws, wsb, stream), "limber qag fast launch", status)) return;
+  } else if (!cuda_ok(launch_limber(P, integration_method, ws, wsb, stream), "limber launch", status))
     return;
-  }
-  if (!cuda_ok(launch_limber(P, integration_method, ws, wsb, stream), "limber launch", status)) return;
   if (integration_method == INTEG_QAG) {
     // the shared workspace must not be reused before this launch has drained
     cuda_ok(cudaStreamSynchronize(stream), "limber qag kernel", status);
-    cudaMemcpy(&b->last_qag_evals, P.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    unsigned long long cnt[2] = {0, 0};
+    cudaMemcpy(cnt, P.counters, sizeof(cnt), cudaMemcpyDeviceToHost);
+    b->last_qag_evals = cnt[0];
+    b->last_qag_nodes = fast ? cnt[1] : cnt[0];
   }
 }
 
@@ -1628,6 +1636,7 @@ unsigned long long ccl_b200_batch_spline_nodes(const ccl_b200_batch* b, int ncol
 }
 
 unsigned long long ccl_b200_batch_last_qag_evals(const ccl_b200_batch* b) { return b->last_qag_evals; }
+unsigned long long ccl_b200_batch_last_qag_nodes_computed(const ccl_b200_batch* b) { return b->last_qag_nodes; }
 
 int ccl_b200_batch_last_used_fast_path(const ccl_b200_batch* b) { return b->last_fast ? 1 : 0; }
 

@@ -1013,7 +1013,7 @@ limber_cquad_kernel(const LimberProblem P, unsigned long long* list, CqIval* poo
 #endif
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CCLB_QAG_MINB)
 limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned long long* next_task,
-                  unsigned long long* cq_list) {
+                  unsigned long long* cq_list, const unsigned long long* list, unsigned long long list_cap) {
   __shared__ double s_fv[WARPS_PER_CTA][2 * 41];
   __shared__ double s_pref[WARPS_PER_CTA][2 * MAX_SUB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1024,11 +1024,16 @@ limber_qag_kernel(const LimberProblem P, long long ntasks, double* ws, unsigned 
   double* elist = rlist + limit;
   double* fv = s_fv[warp];
   double* pref = s_pref[warp];
+  // list mode (redo list of the grid-sharing kernel): list[0] = count, tasks from list[1]; an overflowed
+  // list means every task is recomputed
+  const bool listed = list != nullptr && list[0] <= list_cap;
+  if (list != nullptr) ntasks = listed ? (long long)list[0] : ntasks;
   for (;;) {
     unsigned long long t = 0;
     if (lane == 0) t = atomicAdd(next_task, 1ull);
     t = __shfl_sync(0xffffffffu, t, 0);
     if ((long long)t >= ntasks) break;
+    if (listed) t = list[1 + t];
     TaskCtx c;
     int ic, ip, il;
     setup_task(P, (long long)t, c, ic, ip, il);
@@ -1220,6 +1225,49 @@ void launch_limber_redo(const LimberProblem& prob, const FastPlan& plan, cudaStr
   limber_spline_redo_kernel<<<sms * 4, WARPS_PER_CTA * 32, smem, stream>>>(prob, ntasks, plan.redo, plan.redo_cap);
 }
 
+// The CQUAD hand-over list inside the QAG workspace (zeroed here: call once per angular_cl call, before the
+// integrators that append to it).
+void limber_qag_cq_list(double* qag_ws, int n_iteration, unsigned long long** list, unsigned long long* cap,
+                        cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t o_next = qag_region_bytes((size_t)sms * 8 * WARPS_PER_CTA, n_iteration) - 256;
+  char* wsb = reinterpret_cast<char*>(qag_ws);
+  *list = reinterpret_cast<unsigned long long*>(wsb + o_next + 256);
+  *cap = CQ_LIST_CAP;
+  cudaMemsetAsync(*list, 0, 2 * sizeof(unsigned long long), stream);
+}
+
+// General QAG kernel over every task (list == nullptr) or over a redo list, then the CQUAD fallback over the
+// hand-over list (which the caller zeroed with limber_qag_cq_list before the first integrator ran).
+void launch_limber_qag_list(const LimberProblem& prob, double* qag_ws, size_t qag_ws_bytes,
+                            const unsigned long long* list, unsigned long long cap, cudaStream_t stream) {
+  const long long ntasks = (long long)prob.ncosmo * prob.npair * prob.nl;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (!g_gk_uploaded[dev & 63]) {
+    cudaMemcpyToSymbol(c_xgk, GK41_XGK, sizeof(double) * 21);
+    cudaMemcpyToSymbol(c_wgk, GK41_WGK, sizeof(double) * 21);
+    cudaMemcpyToSymbol(c_wg, GK41_WG, sizeof(double) * 10);
+    g_gk_uploaded[dev & 63] = true;
+  }
+  const int nblk = sms * 8;
+  const int nit = prob.par.N_ITERATION;
+  const size_t o_next = qag_region_bytes((size_t)nblk * WARPS_PER_CTA, nit) - 256;
+  const size_t o_list = o_next + 256, o_pool = o_list + cq_list_bytes(), o_heap = o_pool + cq_pool_bytes(nit);
+  (void)qag_ws_bytes;
+  char* wsb = reinterpret_cast<char*>(qag_ws);
+  unsigned long long* next = reinterpret_cast<unsigned long long*>(wsb + o_next);
+  unsigned long long* cq_list = reinterpret_cast<unsigned long long*>(wsb + o_list);
+  cudaMemsetAsync(next, 0, sizeof(unsigned long long), stream);
+  limber_qag_kernel<<<nblk, WARPS_PER_CTA * 32, 0, stream>>>(prob, ntasks, qag_ws, next, cq_list, list, cap);
+  // the reference's fallback for GSL_EROUND; its warps exit at once when the list is empty
+  limber_cquad_kernel<<<CQ_WARPS / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, stream>>>(
+      prob, cq_list, reinterpret_cast<CqIval*>(wsb + o_pool), reinterpret_cast<int*>(wsb + o_heap));
+}
+
 cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws, size_t qag_ws_bytes,
                           cudaStream_t stream) {
   const long long ntasks = (long long)prob.ncosmo * prob.npair * prob.nl;
@@ -1233,29 +1281,11 @@ cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws,
     if (nblk > 0x7fffffffLL) return cudaErrorInvalidValue;
     limber_spline_kernel<<<(unsigned)nblk, WARPS_PER_CTA * 32, smem, stream>>>(prob, ntasks);
   } else {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (!g_gk_uploaded[dev & 63]) {
-      cudaMemcpyToSymbol(c_xgk, GK41_XGK, sizeof(double) * 21);
-      cudaMemcpyToSymbol(c_wgk, GK41_WGK, sizeof(double) * 21);
-      cudaMemcpyToSymbol(c_wg, GK41_WG, sizeof(double) * 10);
-      g_gk_uploaded[dev & 63] = true;
-    }
-    const int nblk = sms * 8;
-    const int nit = prob.par.N_ITERATION;
-    const size_t o_next = qag_region_bytes((size_t)nblk * WARPS_PER_CTA, nit) - 256;
-    const size_t o_list = o_next + 256, o_pool = o_list + cq_list_bytes(), o_heap = o_pool + cq_pool_bytes(nit);
-    if (o_heap + cq_heap_bytes(nit) > qag_ws_bytes) return cudaErrorInvalidValue;
-    char* wsb = reinterpret_cast<char*>(qag_ws);
-    unsigned long long* next = reinterpret_cast<unsigned long long*>(wsb + o_next);
-    unsigned long long* cq_list = reinterpret_cast<unsigned long long*>(wsb + o_list);
-    cudaMemsetAsync(next, 0, sizeof(unsigned long long), stream);
-    cudaMemsetAsync(cq_list, 0, 2 * sizeof(unsigned long long), stream);
-    limber_qag_kernel<<<nblk, WARPS_PER_CTA * 32, 0, stream>>>(prob, ntasks, qag_ws, next, cq_list);
-    // the reference's fallback for GSL_EROUND; its warps exit at once when the list is empty
-    limber_cquad_kernel<<<CQ_WARPS / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, stream>>>(
-        prob, cq_list, reinterpret_cast<CqIval*>(wsb + o_pool), reinterpret_cast<int*>(wsb + o_heap));
+    if (limber_qag_workspace_bytes(prob.par.N_ITERATION) > qag_ws_bytes) return cudaErrorInvalidValue;
+    unsigned long long* cq_list = nullptr;
+    unsigned long long cq_cap = 0;
+    limber_qag_cq_list(qag_ws, prob.par.N_ITERATION, &cq_list, &cq_cap, stream);
+    launch_limber_qag_list(prob, qag_ws, qag_ws_bytes, nullptr, 0, stream);
   }
   return cudaGetLastError();
 }

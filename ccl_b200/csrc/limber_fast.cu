@@ -19,9 +19,10 @@
 //     form; the per-pair cost (two vector loads, two shuffles, NPL ballots) is paid once per CH nodes.
 // Anything the fast path does not cover (a node outside the a(chi) or P(k,a) tables, ...) is pushed
 // to a redo list for the general kernel.
+#include <cstddef>
 #include <cstdlib>
 
-#include "device_eval.cuh"
+#include "fast_common.cuh"
 
 namespace cclb {
 
@@ -35,17 +36,8 @@ namespace {
 #ifndef CCLB_NPL
 #define CCLB_NPL 2
 #endif
-#ifndef CCLB_NCG
-#define CCLB_NCG 10
-#endif
-#ifndef CCLB_NPG
-#define CCLB_NPG 10
-#endif
-#ifndef CCLB_LPC
-#define CCLB_LPC 1
-#endif
 #ifndef CCLB_MINB
-#define CCLB_MINB 2
+#define CCLB_MINB 3
 #endif
 #ifndef CCLB_TR_UNROLL
 #define CCLB_TR_UNROLL 1
@@ -57,77 +49,17 @@ constexpr int NCG = CCLB_NCG;   // collections per grid task
 constexpr int NPG = CCLB_NPG;   // pairs per grid task
 static_assert(NPL == 2 || NPL == 4, "phase 2 is written for 2 or 4 nodes per lane");
 static_assert(CCLB_NPG <= 32 && CCLB_NCG <= 16, "carry bits are one per pair; collection slots are 4 bits");
-constexpr int LPC = CCLB_LPC;   // ells per CTA (descriptor staging is amortised over them)
 constexpr int NSG = 2 * CCLB_NCG;  // sub-tracers per grid task
 constexpr int TRU = CCLB_TR_UNROLL;  // unroll factor of the sub-tracer loop
-constexpr int GB = 64;          // (ell, grid) tasks whose limits are precomputed per CTA pass
-
-// sub-tracer list entry of a grid task:
-//   tracer index | collection slot << 8 | FIRST << 12 | NEWK << 13 | NEWA << 14
-// FIRST: first entry of its collection (store instead of accumulate); NEWK / NEWA: the kernel / the
-// a-only transfer sits on a different grid than the previous entry's (search the interval again).
-constexpr unsigned SUB_FIRST = 1u << 12, SUB_NEWK = 1u << 13, SUB_NEWA = 1u << 14;
-
-// Lookup descriptor of one 1-D spline, read with 16-byte shared-memory loads.
-struct __align__(16) FastS1 {
-  double x0, xn;
-  double inv_bin;
-  const double2* xr;
-  const double4* cr;
-  const int* lut;
-  int nlutm1, last;
-  int pad[2];
-};
-
-struct __align__(16) FastTr {
-  FastS1 kernel;
-  FastS1 fa;
-  double pref[LPC];  // f_ell (/(l+1/2)^2 when der_bessel == -1) for each ell of this CTA
-  int has_fa, der_bessel;
-};
-
-__device__ __forceinline__ FastS1 pack_s1(const Spline1D& s) {
-  FastS1 f;
-  f.x0 = s.x0; f.xn = s.xn; f.inv_bin = s.inv_bin; f.xr = s.xr; f.cr = s.cr; f.lut = s.lut;
-  f.nlutm1 = s.nlut - 1; f.last = s.n - 2;
-  f.pad[0] = f.pad[1] = 0;
-  return f;
-}
-
-// Interval gsl_interp_bsearch would return, through the LUT (built for every grid): the entry is the
-// interval of a point just left of the bin, so the walk goes right only.  Returns the index and the
-// interval's left node.  Abscissae outside the grid land on the first / last interval.
-__device__ __forceinline__ int find_interval(const FastS1& s, double v, double& x0) {
-  int j = (int)((v - s.x0) * s.inv_bin);
-  j = min(max(j, 0), s.nlutm1);
-  int i = __ldg(s.lut + j);
-  const int last = s.last;
-  double2 r = __ldg(s.xr + i);
-  int steps = 0;
-  while (v >= r.y && i < last) {
-    if (++steps > 4) {  // strongly non-uniform grid: finish by bisection on the interval starts
-      int lo = i, hi = last + 1;
-      while (hi > lo + 1) {
-        const int m = (hi + lo) >> 1;
-        if (__ldg(&s.xr[m].x) > v) hi = m; else lo = m;
-      }
-      i = lo;
-      r = __ldg(s.xr + i);
-      break;
-    }
-    r = __ldg(s.xr + (++i));
-  }
-  x0 = r.x;
-  return i;
-}
-
-__device__ __forceinline__ double cubic(const double4 c, double d) { return c.x + d * (c.y + d * (c.z + d * c.w)); }
+constexpr int GB = 56;          // (ell, grid) tasks whose limits are precomputed per CTA pass
 
 // ln k limits and node spacing of one (ell, grid) task (get_k_interval + ccl_linear_spacing)
-struct GridPar {
-  double lkmin, lkmax, dx, hl, inv_dx, inv_hl, ratio, iratio;
+struct __align__(16) GridPar {
+  double lkmin, lkmax, dx, inv_dx, ratio, iratio;
   int nk, grid, ls, pad;
 };
+// the last interval ends on lkmax itself (ccl_linear_spacing overwrites the end node)
+__device__ __forceinline__ double last_interval(const GridPar& g) { return g.lkmax - (g.lkmin + g.dx * (g.nk - 2)); }
 
 // Per-CTA shared state; followed in shared memory by FastTr tr[ntr_max] and the per-warp blocks.
 struct FastCta {
@@ -137,19 +69,22 @@ struct FastCta {
   int next_task, pad;
 };
 
-__host__ __device__ inline size_t fast_tr_offset() { return (sizeof(FastCta) + 15) & ~size_t(15); }
-__host__ __device__ inline size_t fast_warp_offset(int ntr_max) {
-  return (fast_tr_offset() + (size_t)ntr_max * sizeof(FastTr) + 15) & ~size_t(15);
-}
 
 struct __align__(16) FastWarp {
+  FastEnt ents[NSG];       // the task's sub-tracers, ordered by spline grid (first: FastEnt offsets are positive)
   double dflat[NCG * CH];  // D of the grid's collection slot c at chunk node j: [c * CH + j]
   double kp[CH];           // k P(k, a) at chunk node j
-  double acc[NPG][32];     // per-lane partial integrals
+  double acc[NPG][16];     // partial integrals: lanes l and l + 16 share an entry
   double fc[NPG][4];       // integrand at the last 4 nodes of the previous chunk, per pair
   double fe[NPG][8];       // f_0..f_2 and f_{nk-5}..f_{nk-1} per pair (end-node terms)
   int2 po[NPG];            // offsets of the pair's two collections in dflat
-  unsigned subs[NSG];
+};
+
+// Layout of the CTA's dynamic shared memory; tr[] really holds FastPlan::ntr_max entries.
+struct __align__(16) FastSmem {
+  FastCta cta;
+  FastWarp warps[FW];
+  FastTr tr[1];
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -331,11 +266,12 @@ __global__ void __launch_bounds__(128) limber_group_kernel(const LimberProblem P
 // nodes, z at the last owned node) connect the tie flags across chunks.
 // ------------------------------------------------------------------------------------------
 template <bool EDGE>
-__device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk, int lane, double dx, double hl,
-                                           double inv_dx, double inv_hl, unsigned& cE1, unsigned& cE2,
-                                           unsigned& cZ) {
+__device__ __forceinline__ void pair_phase(FastWarp& W, const GridPar& gp, int np, int base, int lane,
+                                           unsigned& cE1, unsigned& cE2, unsigned& cZ) {
   const unsigned FULL = 0xffffffffu;
   const int n0 = NPL * lane;
+  const int nk = gp.nk;
+  const double dx = gp.dx;
   double kpv[NPL], wn[NPL];
   unsigned vmask[NPL];
   if (NPL == 2) {
@@ -350,9 +286,10 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk
   for (int r = 0; r < NPL; ++r) {
     if (EDGE) {
       const int s = base + n0 + r;
+      const double hl = last_interval(gp);
       double w = dx;
       if (s == 0) w = 0.5 * dx;
-      if (s == nk - 2) w = 0.5 * dx + 0.5 * hl;  // the last interval ends on lkmax itself (ccl_linear_spacing)
+      if (s == nk - 2) w = 0.5 * dx + 0.5 * hl;
       if (s == nk - 1) w = 0.5 * hl;
       if (s >= nk) w = 0.0;
       wn[r] = w;
@@ -380,16 +317,16 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk
         f[NPL - 1] = kpv[NPL - 1] * a1.y * b1.y;
       }
     }
-    const double2 c01 = *reinterpret_cast<const double2*>(&W.fc[q][0]);  // f at nodes base-4, base-3
-    const double2 c23 = *reinterpret_cast<const double2*>(&W.fc[q][2]);  // f at nodes base-2, base-1
-    const double cd1 = c23.y - c23.x;                                      // d at node base-1
     double pf = __shfl_up_sync(FULL, f[NPL - 1], 1);
-    if (lane == 0) pf = c23.y;
-    d[0] = f[0] - pf;
 #pragma unroll
     for (int r = 1; r < NPL; ++r) d[r] = f[r] - f[r - 1];
     double pd = __shfl_up_sync(FULL, d[NPL - 1], 1);
-    if (lane == 0) pd = cd1;
+    if (lane == 0) {  // the previous chunk's last values: f at nodes base-2, base-1
+      const double2 c23 = *reinterpret_cast<const double2*>(&W.fc[q][2]);
+      pf = c23.y;
+      pd = c23.y - c23.x;
+    }
+    d[0] = f[0] - pf;
     unsigned m[NPL], zm[NPL], tr[NPL];
     m[0] = __ballot_sync(FULL, d[0] == pd);
 #pragma unroll
@@ -401,7 +338,8 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk
       m[0] |= 1u;
       m[1] = (m[1] & ~1u) | e2;
     }
-    const unsigned qE1 = (cE1 >> q) & 1u, qE2 = (cE2 >> q) & 1u, qZ = (cZ >> q) & 1u;
+    // carried flags of this pair sit in bit 0; the new ones enter at bit 31 and the words rotate right once per pair
+    const unsigned qE1 = cE1 & 1u, qE2 = cE2 & 1u, qZ = cZ & 1u;
     if (NPL == 2) {
       zm[0] = m[0] & ((m[0] << 1) | qE2);
       zm[1] = m[1] & ((m[1] << 1) | qE1);
@@ -418,7 +356,7 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk
       tr[r] = (zm[r] ^ zm[r - 1]) & vmask[r];
       any |= tr[r];
     }
-    double acc = W.acc[q][lane];
+    double acc = 0.0;
 #pragma unroll
     for (int r = 0; r < NPL; ++r) acc = fma(wn[r], f[r], acc);
     if (EDGE) {  // f_0..f_2 and f_{nk-5}..f_{nk-1} feed the end-node terms
@@ -432,7 +370,10 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk
     }
     if (any != 0u) {
       // ---- a tie transition in this chunk: per-node form for the flagged nodes ----
-      const double cd2 = c23.x - c01.y, cd3 = c01.y - c01.x;  // d at nodes base-2, base-3
+      const double2 c01 = *reinterpret_cast<const double2*>(&W.fc[q][0]);  // f at nodes base-4, base-3
+      const double2 c23 = *reinterpret_cast<const double2*>(&W.fc[q][2]);  // f at nodes base-2, base-1
+      const double cd1 = c23.y - c23.x, cd2 = c23.x - c01.y, cd3 = c01.y - c01.x;  // d at nodes base-1, -2, -3
+      const double inv_dx = gp.inv_dx;
       double w4[NPL + 3];  // d at chunk nodes n0-3 .. n0+NPL-1
       if (NPL == 2) {
         double p0 = __shfl_up_sync(FULL, d[0], 1), pp1 = __shfl_up_sync(FULL, d[1], 2);
@@ -453,7 +394,7 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk
           const int cn = base + n0 + r - 2;
           double mm2 = w4[r] * inv_dx, mm1 = w4[r + 1] * inv_dx, m0 = w4[r + 2] * inv_dx, mp1 = w4[r + 3] * inv_dx;
           if (EDGE) {
-            if (cn == nk - 3) mp1 = w4[r + 3] * inv_hl;
+            if (cn == nk - 3) mp1 = w4[r + 3] / last_interval(gp);
             if (cn == 1) mm2 = 2.0 * mm1 - m0;
           }
           const bool z = ((zm[r] >> lane) & 1u) != 0u;
@@ -473,7 +414,8 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk
         }
       }
     }
-    W.acc[q][lane] = acc;
+    acc += __shfl_down_sync(FULL, acc, 16);
+    if (lane < 16) W.acc[q][lane] += acc;
     __syncwarp();  // every lane has read W.fc
     if (NPL == 2) {
       if (lane >= 30) *reinterpret_cast<double2*>(&W.fc[q][2 * (lane - 30)]) = make_double2(f[0], f[1]);
@@ -483,11 +425,14 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk
         *reinterpret_cast<double2*>(&W.fc[q][2]) = make_double2(f[NPL - 2], f[NPL - 1]);
       }
     }
-    const unsigned bit = 1u << q;
-    cE1 = (cE1 & ~bit) | ((m[NPL - 1] >> 31) << q);
-    cE2 = (cE2 & ~bit) | ((m[NPL - 2] >> 31) << q);
-    cZ = (cZ & ~bit) | ((zm[NPL - 1] >> 31) << q);
+    cE1 = (cE1 >> 1) | (m[NPL - 1] & 0x80000000u);
+    cE2 = (cE2 >> 1) | (m[NPL - 2] & 0x80000000u);
+    cZ = (cZ >> 1) | (zm[NPL - 1] & 0x80000000u);
   }
+  // after np pairs the flags occupy bits 32-np..31: pair 0 back to bit 0 for the next chunk
+  cE1 >>= (32 - np);
+  cE2 >>= (32 - np);
+  cZ >>= (32 - np);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -499,11 +444,12 @@ __device__ __forceinline__ void pair_phase(FastWarp& W, int np, int base, int nk
 template <bool RSD>
 __global__ void __launch_bounds__(FW * 32, CCLB_MINB)
 limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  FastCta& S = *reinterpret_cast<FastCta*>(smraw);
+  // one typed view of the dynamic shared memory: every access stays a direct shared-space access
+  extern __shared__ __align__(16) FastSmem fsm[];
+  FastCta& S = fsm[0].cta;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  FastTr* const s_tr = reinterpret_cast<FastTr*>(smraw + fast_tr_offset());
-  FastWarp& W = reinterpret_cast<FastWarp*>(smraw + fast_warp_offset(G.ntr_max))[warp];
+  FastTr* const s_tr = fsm[0].tr;
+  FastWarp& W = fsm[0].warps[warp];
   const int nlt = (P.nl + LPC - 1) / LPC;
   const int il0 = (blockIdx.x % nlt) * LPC;
   const int ic = blockIdx.x / nlt;
@@ -551,9 +497,7 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
       q.lkmin = log(fmax(P.par.K_MIN, lp1h / gd.chi_max));
       q.nk = (int)(fmax((q.lkmax - q.lkmin) / P.par.DLOGK_INTEGRATION + 0.5, 1.0)) + 1;
       q.dx = (q.lkmax - q.lkmin) / (q.nk - 1.);
-      q.hl = q.lkmax - (q.lkmin + q.dx * (q.nk - 2));  // last interval (end node overwritten)
       q.inv_dx = 1.0 / q.dx;
-      q.inv_hl = 1.0 / q.hl;
       q.ratio = exp(32.0 * q.dx);
       q.iratio = 1.0 / q.ratio;
       q.pad = 0;
@@ -577,7 +521,19 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
         const GridPair pr = gpairs[gd.pair_begin + lane];
         W.po[lane] = make_int2(pr.a * CH, pr.b * CH);
       }
-      if (lane < min(nsub, NSG)) W.subs[lane] = gsubs[gd.sub_begin + lane];
+      if (lane < min(nsub, NSG)) {
+        const unsigned ent = gsubs[gd.sub_begin + lane];
+        const FastTr& tr = s_tr[ent & 0xffu];
+        FastEnt en;
+        en.kcr = tr.kernel.cr;
+        en.pref = tr.pref[ls];
+        en.acr = tr.has_fa ? tr.fa.cr : nullptr;
+        const char* self = reinterpret_cast<const char*>(&W.ents[lane]);
+        const unsigned drow = (unsigned)(reinterpret_cast<const char*>(&W.dflat[((ent >> 8) & 0xfu) * CH]) - self) >> 4;
+        en.flags = (ent & 0xffffu) | ((RSD && tr.der_bessel >= 1) ? SUB_RSD : 0u) | (drow << 16);
+        en.troff = (int)(reinterpret_cast<const char*>(&tr) - self);
+        W.ents[lane] = en;
+      }
       const bool task_rsd = RSD && gd.has_rsd;
       const int nk = S.gp[gl].nk;
       const double lkmin = S.gp[gl].lkmin, lkmax = S.gp[gl].lkmax;
@@ -593,14 +549,15 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
       }
       // outside the P(k,a) table in ln k, or more sub-tracers than the list holds: general kernel
       bool redo = !(lkmin >= S.psp.lkmin && lkmax <= S.psp.lkmax) || nsub > NSG;
-      const double dx = S.gp[gl].dx, hl = S.gp[gl].hl, inv_dx = S.gp[gl].inv_dx, inv_hl = S.gp[gl].inv_hl;
+      const double dx = S.gp[gl].dx;
       // k and chi advance by constant ratios from one 32-node sub-chunk to the next (one exp per lane per grid)
       double k = exp(lkmin + dx * lane);
       double chi = lp1h / k;
-      unsigned cE1 = 0u, cE2 = 0u, cZ = 0u;  // bit q: carried tie flags of pair q (see pair_phase)
+      unsigned cE1 = 0u, cE2 = 0u, cZ = 0u;  // bit q: carried tie flags of pair q (see pair_phase); np >= 1
       for (int i = lane; i < NPG * 4; i += 32) (&W.fc[0][0])[i] = 0.0;  // f at nodes -4..-1: finite placeholders
 #pragma unroll 1
-      for (int q = 0; q < np; ++q) W.acc[q][lane] = 0.0;
+      for (int q = 0; q < np; ++q)
+        if (lane < 16) W.acc[q][lane] = 0.0;
       __syncwarp();
 
 #pragma unroll 1
@@ -613,7 +570,7 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
           const int s = base + j;
           double kp = 0.0;
           if (s < nk) {
-            const double lk = (s == 0) ? lkmin : ((s == nk - 1) ? lkmax : lkmin + dx * s);
+            const double lk = (s == 0) ? lkmin : ((s == nk - 1) ? S.gp[gl].lkmax : lkmin + dx * s);
             // ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277); chi > 0 here
             double a = 1.0;
             if (!(chi < 1.e-8)) {
@@ -625,7 +582,7 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
             }
             if (!(a >= S.psp.amin && a <= S.psp.amax)) bad = true;  // growth extrapolation: general kernel
             double pk = 0.0;
-            if (!bad) pk = exp(bicubic_eval(S.psp, lk, a, 0));
+            if (!bad) pk = fast_exp(bicubic_eval(S.psp, lk, a, 0));
             kp = k * pk;
             double chi_lp = 0.0, a_lp = 1.0, sqell = 0.0;
             if (RSD && task_rsd) {
@@ -639,7 +596,7 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
                   bad = true;
               }
               if (!(a_lp >= S.psp.amin && a_lp <= S.psp.amax)) bad = true;
-              if (!bad) sqell = sqrt(lp1h * fabs(exp(bicubic_eval(S.psp, lk, a_lp, 0)) / pk) / lp3h);
+              if (!bad) sqell = sqrt(lp1h * fabs(fast_exp(bicubic_eval(S.psp, lk, a_lp, 0)) / pk) / lp3h);
             }
             // transfer_limber_wrap (src/ccl_cls.c:150-164) for every collection of the grid, as one loop
             // over the task's sub-tracer list.  Entries on the same spline grid share the interval search
@@ -650,28 +607,32 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
             int ki = 0, ai = 0;
             double kdel = 0.0, adel = 0.0;
             bool inside = false;
+            const FastEnt* ep = W.ents;
 #pragma unroll TRU
-            for (int e = 0; e < nsub; ++e) {
-              const unsigned ent = W.subs[e];
-              const FastTr& tr = s_tr[ent & 0xffu];
-              if (ent & SUB_NEWK) {
+            for (int e = 0; e < nsub; ++e, ++ep) {
+              const FastEnt en = *ep;
+              const unsigned ent = en.flags;
+              if (__builtin_expect((ent & SUB_NEWK) != 0u, 0)) {
+                const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
                 double x0;
                 ki = find_interval(tr.kernel, chi, x0);
                 kdel = chi - x0;
                 inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
               }
-              double wt = cubic(ldg4(tr.kernel.cr + ki), kdel);
-              if (tr.has_fa) {
-                if (ent & SUB_NEWA) {
+              double wt = cubic(ldg4(en.kcr + ki), kdel);
+              if (en.acr != nullptr) {
+                if (__builtin_expect((ent & SUB_NEWA) != 0u, 0)) {
+                  const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
                   const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
                   double x0;
                   ai = find_interval(tr.fa, a_ev, x0);
                   adel = a_ev - x0;
                 }
-                wt *= cubic(ldg4(tr.fa.cr + ai), adel);
+                wt *= cubic(ldg4(en.acr + ai), adel);
               }
-              double val = inside ? wt * tr.pref[ls] : 0.0;
-              if (RSD && tr.der_bessel >= 1) {
+              double val = inside ? wt * en.pref : 0.0;
+              if (RSD && (ent & SUB_RSD)) {
+                const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
                 // w t at chi is `inside ? wt : 0`; the second point has its own support test
                 const double l = lp1h - 0.5, lp3h = lp1h + 1.0;
                 const double w_t = inside ? wt : 0.0;
@@ -688,9 +649,10 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
                 double dd;
                 if (tr.der_bessel == 1) dd = l * w_t / lp1h - sqell * wt_p;
                 else dd = sqell * 2 * wt_p / lp3h - (0.25 + 2 * l) * w_t / (lp1h * lp1h);
-                val = dd * tr.pref[ls];
+                val = dd * en.pref;
               }
-              double* dp = &W.dflat[((ent >> 8) & 0xfu) * CH + j];
+              double* dp = reinterpret_cast<double*>(const_cast<char*>(reinterpret_cast<const char*>(ep)) +
+                                                     ((ent >> 16) << 4)) + j;
               if (!(ent & SUB_FIRST)) val += *dp;
               *dp = val;
             }
@@ -705,9 +667,9 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
         __syncwarp();
         // ---------------- phase 2: per-pair integrand and Akima integral ----------------
         if ((base == 0) || (base + CH - 1 >= nk - 5))
-          pair_phase<true>(W, np, base, nk, lane, dx, hl, inv_dx, inv_hl, cE1, cE2, cZ);
+          pair_phase<true>(W, S.gp[gl], np, base, lane, cE1, cE2, cZ);
         else
-          pair_phase<false>(W, np, base, nk, lane, dx, hl, inv_dx, inv_hl, cE1, cE2, cZ);
+          pair_phase<false>(W, S.gp[gl], np, base, lane, cE1, cE2, cZ);
         __syncwarp();
       }
 
@@ -726,6 +688,7 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
       if (lane < np) {
         out = gpairs[gd.pair_begin + lane].out;
         const double* e = W.fe[lane];
+        const double hl = last_interval(S.gp[gl]), inv_hl = 1.0 / hl, inv_dx = S.gp[gl].inv_dx;
         auto blend = [](double d12, double NE, double ml, double mr) {
           const double alpha = d12 / NE;
           return (1.0 - alpha) * ml + alpha * mr;
@@ -757,7 +720,7 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
       }
 #pragma unroll 1
       for (int q = 0; q < np; ++q) {
-        const double v = warp_sum(W.acc[q][lane]) + __shfl_sync(FULL, endc, q);
+        const double v = warp_sum(lane < 16 ? W.acc[q][lane] : 0.0) + __shfl_sync(FULL, endc, q);
         const int o = __shfl_sync(FULL, out, q);
         if (lane == 0) P.cl[((size_t)ic * P.npair + o) * P.nl + il] = v / lp1h;  // src/ccl_cls.c:340
       }
@@ -793,17 +756,22 @@ FastPlan limber_fast_plan_carve(void* base, int ncosmo, int npair, unsigned long
   return G;
 }
 
-cudaError_t launch_limber_fast(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream) {
-  static const bool use_v1 = getenv("CCL_B200_FAST_V1") != nullptr;
-  if (use_v1) return launch_limber_fast_v1(prob, plan, stream);
-  if (prob.ncosmo == 0 || prob.npair == 0 || prob.nl == 0) return cudaSuccess;
-  if ((long long)prob.ncosmo * prob.nl > 0x7fffffffLL) return cudaErrorInvalidValue;
+// grid tasks of every cosmology (shared by the 'spline' and 'qag_quad' grid-sharing integrators)
+void launch_limber_group(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream) {
   cudaMemsetAsync(plan.redo, 0, sizeof(unsigned long long), stream);
   const size_t gsm = sizeof(double) * 2 * ((size_t)prob.ncoll + prob.npair) + sizeof(int) * (size_t)prob.npair;
   if (gsm > 40 * 1024)
     cudaFuncSetAttribute(limber_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
   limber_group_kernel<<<prob.ncosmo, 128, gsm, stream>>>(prob, plan);
-  const size_t fsm = fast_warp_offset(plan.ntr_max) + FW * sizeof(FastWarp);
+}
+
+cudaError_t launch_limber_fast(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream) {
+  static const bool use_v1 = getenv("CCL_B200_FAST_V1") != nullptr;
+  if (use_v1) return launch_limber_fast_v1(prob, plan, stream);
+  if (prob.ncosmo == 0 || prob.npair == 0 || prob.nl == 0) return cudaSuccess;
+  if ((long long)prob.ncosmo * prob.nl > 0x7fffffffLL) return cudaErrorInvalidValue;
+  launch_limber_group(prob, plan, stream);
+  const size_t fsm = offsetof(FastSmem, tr) + (size_t)plan.ntr_max * sizeof(FastTr);
   static size_t attr_set[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);

@@ -184,6 +184,12 @@ void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs,
 cudaError_t launch_limber(const LimberProblem& prob, int method, double* qag_ws, size_t qag_ws_bytes,
                           cudaStream_t stream);
 size_t limber_qag_workspace_bytes(int n_iteration);
+// grid-sharing 'qag_quad' (limber_qag_fast.cu): its workspace follows the general kernel's in the same buffer
+size_t limber_qag_fast_workspace_bytes(int n_iteration);
+void limber_qag_cq_list(double* qag_ws, int n_iteration, unsigned long long** list, unsigned long long* cap,
+                        cudaStream_t stream);
+void launch_limber_qag_list(const LimberProblem& prob, double* qag_ws, size_t qag_ws_bytes,
+                            const unsigned long long* list, unsigned long long cap, cudaStream_t stream);
 // fast path (limber_fast.cu): eligibility limits, plan sizing, launch (group + fast + redo kernels)
 constexpr int FAST_MAX_TRACERS = 48;  // sub-tracers per cosmology
 constexpr int FAST_MAX_COLLS = 48;    // collections per call
@@ -191,6 +197,9 @@ constexpr int FAST_MAX_PAIRS = 2048;  // pairs per call
 size_t limber_fast_plan_bytes(int ncosmo, int npair, unsigned long long redo_cap);
 FastPlan limber_fast_plan_carve(void* base, int ncosmo, int npair, unsigned long long redo_cap);
 cudaError_t launch_limber_fast(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream);
+void launch_limber_group(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream);
+cudaError_t launch_limber_qag_fast(const LimberProblem& prob, const FastPlan& plan, double* ws, size_t ws_bytes,
+                                   cudaStream_t stream);
 // the general one-warp-per-C_ell kernel over the plan's redo list (kernels.cu)
 void launch_limber_redo(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream);
 int limber_nk_cap(const LimberParams& par);

@@ -366,6 +366,10 @@ class LibBatch:
     def last_qag_evals(self):
         return _lib.load().ccl_b200_batch_last_qag_evals(self.h)
 
+    @property
+    def last_qag_nodes_computed(self):
+        return _lib.load().ccl_b200_batch_last_qag_nodes_computed(self.h)
+
     def __del__(self):
         if getattr(self, "h", None) and _lib._LIB is not None:
             _lib._LIB.ccl_b200_batch_free(self.h)

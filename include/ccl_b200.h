@@ -222,6 +222,9 @@ unsigned long long ccl_b200_batch_spline_nodes(const ccl_b200_batch *b, int ncol
                                                const int *pair2, int nl, const double *ell);
 /* Integrand evaluations of the last qag_quad launch on this batch. */
 unsigned long long ccl_b200_batch_last_qag_evals(const ccl_b200_batch *b);
+/* Integrand abscissae the last 'qag_quad' launch actually evaluated: smaller than last_qag_evals when the
+ * grid-sharing kernel served panels from its cache (pairs with equal chi ranges request the same panels). */
+unsigned long long ccl_b200_batch_last_qag_nodes_computed(const ccl_b200_batch *b);
 /* 1 if the last 'spline' launch ran the grid-sharing kernels (pairs of one cosmology whose
  * get_k_interval ranges coincide share a(chi), k P(k,a) and tracer evaluations; same node values
  * and integrand arithmetic as src/ccl_cls.c:166-225), 0 if it ran the general kernel.  Setting the

@@ -27,11 +27,12 @@ def build(force=False):
     """Compile liblimber_oracle.so with the committed Makefile (gcc, OpenMP if available)."""
     so = os.path.join(_HERE, "liblimber_oracle.so")
     src = os.path.join(_HERE, "limber_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    mk = os.path.join(_HERE, "Makefile")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(mk)):
         r = subprocess.run(["make", "-C", _HERE, "-B"], capture_output=True, text=True)
         if r.returncode != 0:
             # no OpenMP runtime: scalar build
-            r = subprocess.run(["gcc", "-O2", "-fPIC", "-std=gnu99", "-ffp-contract=off", "-shared",
+            r = subprocess.run(["gcc", "-O3", "-fomit-frame-pointer", "-fPIC", "-std=gnu99", "-ffp-contract=off", "-shared",
                                 "-o", so, src, "-lm"], capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("oracle build failed:\n" + r.stderr)

@@ -49,6 +49,10 @@ def test_default_params_match_reference_defaults(lib):
     lib.ccl_b200_default_params(C.byref(p))
     assert (p.K_MAX, p.K_MIN, p.DLOGK_INTEGRATION) == (1e3, 5e-5, 0.025)
     assert (p.INTEGRATION_LIMBER_EPSREL, p.N_ITERATION, p.A_SPLINE_MIN) == (1e-4, 1000, 0.1)
+    # the Gauss-Kronrod entries hold GSL's rule key like the reference: GSL_INTEG_GAUSS41 = 4 (src/ccl_core.c:40)
+    assert p.INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS == 4
+    import ccl_b200 as ccl
+    assert ccl.gsl_params.INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS == 4
     assert b"sm_100a" in lib.ccl_b200_version()
 
 

@@ -117,3 +117,45 @@ def test_cells_calculator(env):
     calc.compute_growth()
     cl1 = ccl.angular_cl(calc, tr1, tr1, ell)
     assert np.all(np.fabs(1 - cl1 / cl0) < 1e-10)
+
+
+def test_limber_gauss_kronrod_rule_is_honoured_or_rejected():
+    """gsl_params.INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS is the GSL rule key gsl_integration_qag receives
+    (src/ccl_cls.c:240).  Only GK41 (key 4) exists on the device: any other key must raise for
+    'qag_quad' instead of silently integrating with GK41; 'spline' does not read it."""
+    import ccl_b200 as ccl
+    z = np.linspace(0., 1., 200)
+    n = np.ones_like(z)
+    ell = np.array([10., 100.])
+    try:
+        ccl.gsl_params.INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS = 6      # GSL_INTEG_GAUSS61
+        cosmo = ccl.Cosmology(Omega_c=0.27, Omega_b=0.045, h=0.67, sigma8=0.8, n_s=0.96, transfer_function='bbks')
+    finally:
+        ccl.gsl_params.reload()
+    t = ccl.WeakLensingTracer(cosmo, dndz=(z, n))
+    with pytest.raises(ccl.CCLError, match="GAUSS_KRONROD"):
+        ccl.angular_cl(cosmo, t, t, ell, limber_integration_method='qag_quad')
+    cs = ccl.angular_cl(cosmo, t, t, ell, limber_integration_method='spline')
+    assert np.all(np.isfinite(cs)) and np.all(cs > 0)
+    # a cosmology created with the default key integrates
+    cosmo2 = ccl.Cosmology(Omega_c=0.27, Omega_b=0.045, h=0.67, sigma8=0.8, n_s=0.96, transfer_function='bbks')
+    t2 = ccl.WeakLensingTracer(cosmo2, dndz=(z, n))
+    cq = ccl.angular_cl(cosmo2, t2, t2, ell, limber_integration_method='qag_quad')
+    assert np.max(np.abs(cq / cs - 1)) < 1e-3
+
+
+def test_distances_not_computed_is_error_1059():
+    """src/ccl_cls.c:274-280: a cosmology without the a(chi) table fails with CCL_ERROR_DISTANCES_INIT."""
+    import ccl_b200 as cb
+    from ccl_b200 import synthetic as S
+    bg = S.background()
+    pk = S.power(bg)
+    subs, colls = S.lsst_like_tracers(bg, n_lens=1, n_src=1)
+    full = cb.LibCosmology()
+    full.set_achi(bg["chi"], bg["a"])
+    ltr = [cb.LibTracer(full, **s) for s in subs]
+    psp = cb.LibF2D(a=pk["a"], lk=pk["lk"], fka=pk["logp"], extrap_order_lok=1, extrap_order_hik=2, is_log=True,
+                    growth_exponent=2, growth_factor_0=0.0)
+    empty = cb.LibCosmology()           # no distances injected or computed
+    cl, st = cb.angular_cls_limber(empty, ltr[:1], ltr[1:2], psp, np.array([10., 20.]), cb._lib.INTEGRATION_SPLINE)
+    assert st == 1059       # the output array is left untouched, like the reference's early return
