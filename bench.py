@@ -220,6 +220,7 @@ def host_tables_from_parameters(p):
     """The same flat tables for one parameter set through the pyccl-compatible host classes (numpy twins of
     the device builders): the inputs of the CPU reference arm, which must not touch the GPU."""
     import ccl_b200 as ccl
+    ccl.set_table_builder("host")      # numpy twins: this arm is pure CPU
     zz, lens, src = survey_nz()
     cosmo = ccl.Cosmology(Omega_c=p["Omega_c"], Omega_b=p["Omega_b"], h=p["h"], n_s=p["n_s"], sigma8=p["sigma8"],
                           w0=p["w0"], wa=p["wa"], transfer_function='eisenstein_hu', matter_power_spectrum='halofit')
@@ -320,6 +321,7 @@ def _main(json_out):
     ap.add_argument("--method", default="spline", choices=["spline", "qag_quad"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-y10", action="store_true", help="skip the LSST-Y10 single-cosmology leg (configs[4])")
     ap.add_argument("--from-parameters", type=int, default=None, metavar="N",
                     help="cosmologies of the parameters -> device-built tables -> C_ell leg (default: this rank's "
                          "share of the batch; 0 skips it)")
@@ -345,6 +347,13 @@ def _main(json_out):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    if world > 1:
+        # one core set per rank (like numactl in a launcher): the staging / planning threads of the ranks of one
+        # box must not fight over the same cores
+        cores = sorted(os.sched_getaffinity(0))
+        lw = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        per = max(1, len(cores) // lw)
+        os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per] or cores)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -379,26 +388,15 @@ def _main(json_out):
 
     d_cl = torch.empty((nloc, npair, nl), dtype=torch.float64, device="cuda")
     d_st = torch.zeros((2, nloc, npair), dtype=torch.int32, device="cuda")
-    gather_list = None
-    if world > 1 and rank == 0:
-        sizes = [base + (1 if r < rem else 0) for r in range(world)]
-        gather_list = [torch.empty((s, npair, nl), dtype=torch.float64, device="cuda") for s in sizes]
     stream = torch.cuda.current_stream().cuda_stream
 
+    from ccl_b200 import sharding
+    sizes = sharding.shard_sizes(args.ncosmo, world)
+    assert sizes[rank] == nloc and sharding.shard_range(args.ncosmo, world, rank)[0] == off
+
     def step():
-        batch.angular_cl_dev(colls, pairs, ells, d_cl.data_ptr(), d_st.data_ptr(), method, stream)
-        if world > 1:
-            # equal-sized shards go through one NCCL gather; ragged ones through send/recv
-            if rem == 0:
-                dist.gather(d_cl, gather_list, dst=0)
-            else:
-                if rank == 0:
-                    gather_list[0].copy_(d_cl)
-                    reqs = [dist.irecv(gather_list[r], src=r) for r in range(1, world)]
-                    for q in reqs:
-                        q.wait()
-                else:
-                    dist.send(d_cl, dst=0)
+        # this rank's block of cosmologies, then ONE gather of the C_ell blocks to rank 0 (product code)
+        return sharding.angular_cl_by_cosmology(batch, colls, pairs, ells, sizes, method, out=d_cl, d_status=d_st, dst=0)
 
     def sync_all():
         if world > 1:
@@ -418,14 +416,7 @@ def _main(json_out):
         batch.angular_cl_dev(colls, pairs, ells, d_cl.data_ptr(), d_st.data_ptr(), method, stream)
         kev[i][1].record()
         if world > 1:
-            if rem == 0:
-                dist.gather(d_cl, gather_list, dst=0)
-            elif rank == 0:
-                gather_list[0].copy_(d_cl)
-                for q in [dist.irecv(gather_list[r], src=r) for r in range(1, world)]:
-                    q.wait()
-            else:
-                dist.send(d_cl, dst=0)
+            sharding.gather_blocks(d_cl, sizes, dst=0)
     ev1.record()
     sync_all()
     clocks = sampler.stop()
@@ -595,6 +586,54 @@ def _main(json_out):
         q_host = d_clq[:2].cpu().numpy()
         del qb, d_stq
 
+    # ---- BASELINE configs[4]: LSST-Y10 shear + IA, ONE cosmology, 210 pairs x 1000 ells, sharded by ell tile ----
+    y10 = None
+    if not args.no_y10:
+        from ccl_b200 import synthetic as S
+        y_stk = None
+        y_bg = S.background()
+        y_subs, y_colls = S.lsst_like_tracers(y_bg, n_lens=0, n_src=20, with_ia=True)
+        y_pairs = S.all_pairs(len(y_colls))
+        y_ells = np.geomspace(2, 5000, 1000)
+        if rank == 0:      # the table pack lives on rank 0 and is broadcast once
+            a_, chi_ = y_bg["chi_of_a"]
+            y_tab = dict(bg=y_bg, pk=S.power(y_bg), subs=y_subs, colls=y_colls, cmax=float(np.interp(0.1, a_, chi_)))
+            y_stk = stack_host_tables([y_tab], 1)
+        tsl = sharding.TileShardedLimber(y_stk, y_colls, y_pairs, y_ells, src=0)
+        for _ in range(3):
+            y_out = tsl.angular_cl(method)
+        sync_all()
+        y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = 10
+        y0.record()
+        for _ in range(nrep):
+            y_out = tsl.angular_cl(method)
+        y1.record()
+        sync_all()
+        y_ms = y0.elapsed_time(y1) / nrep
+        if world > 1:
+            tt = torch.tensor([y_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            y_ms = float(tt.item())
+        if rank == 0:
+            loads = nodes_loads = None
+            w_ell = sharding.nodes_per_ell(tsl.batch, y_colls, y_pairs, y_ells)
+            loads = [float(w_ell[p].sum()) for p in tsl.plan]
+            same = None
+            if world > 1:   # the split reproduces the unsplit single-GPU result bit for bit
+                full = torch.empty((1, len(y_pairs), len(y_ells)), dtype=torch.float64, device="cuda")
+                stf = torch.zeros((2, 1, len(y_pairs)), dtype=torch.int32, device="cuda")
+                tsl.batch.angular_cl_dev(y_colls, y_pairs, y_ells, full.data_ptr(), stf.data_ptr(), method, stream)
+                torch.cuda.synchronize()
+                same = bool(torch.equal(full, y_out))
+            y10 = {"value": len(y_pairs) * len(y_ells) / (y_ms * 1e-3), "unit": "C_ell/s", "ms_per_pass": y_ms,
+                   "n_gpus": world, "pairs": len(y_pairs), "ells": len(y_ells), "finite": bool(torch.isfinite(y_out).all().item()),
+                   "nodes_per_rank": loads, "identical_to_unsplit": same,
+                   "note": "one cosmology, 20 IA-augmented source bins; table pack broadcast once, ell tiles (all pairs x the "
+                           "ells of the rank) balanced on integrand nodes, one launch per rank, one gather (ccl_b200.sharding."
+                           "TileShardedLimber)"}
+        del tsl
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
@@ -646,7 +685,7 @@ def _main(json_out):
                     "fast_path": bool(fast_path),
                     "qag_abscissae_computed": int(batch.last_qag_nodes_computed) if args.method == "qag_quad" else None},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "from_parameters": from_parameters,
-            "qag": qag,
+            "qag": qag, "y10": y10,
             # fast 'spline' path: grouping + integrator + redo kernels per step; otherwise one kernel
             "gpu_launches": args.steps * (3 if fast_path else 1), "clocks": clocks,
         }), file=json_out)

@@ -8,7 +8,8 @@ from .lowlevel import (CCLB200Error, LibBatch, LibCosmology, LibF2D, LibTracer, 
                        angular_cls_limber, make_params)
 
 from .cells import angular_cl  # noqa: F401,E402
-from .cosmology import Cosmology, CosmologyCalculator, CosmologyVanillaLCDM  # noqa: F401,E402
+from .cosmology import (Cosmology, CosmologyCalculator, CosmologyVanillaLCDM, get_table_builder,  # noqa: F401,E402
+                        set_table_builder)
 from .errors import CCLError, CCLWarning, update_warning_verbosity  # noqa: F401,E402
 from .parameters import DEFAULT_POWER_SPECTRUM, gsl_params, physical_constants, spline_params  # noqa: F401,E402
 from .pipeline import PipelinedBatch, pin_stacked, slice_stacked  # noqa: F401,E402

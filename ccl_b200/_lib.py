@@ -90,6 +90,9 @@ SIGNATURES = {
     "ccl_b200_batch_arena_bytes": (C.c_ulonglong, [_vp]),
     "ccl_b200_batch_angular_cls_limber": (None, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp,
                                                  C.c_int, _dp, _ip, _ip]),
+    "ccl_b200_batch_angular_cls_limber_start": (None, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp,
+                                                        C.c_int, _dp, _ip]),
+    "ccl_b200_batch_angular_cls_limber_wait": (None, [_vp, _ip, _ip]),
     "ccl_b200_batch_angular_cls_limber_dev": (None, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp,
                                                      C.c_int, _vp, _vp, _vp, _ip]),
     "ccl_b200_batch_spline_nodes": (C.c_ulonglong, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp]),

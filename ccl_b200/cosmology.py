@@ -16,7 +16,27 @@ from .background import Background, h_over_h0, omega_x
 from .errors import CCLError
 from .parameters import DEFAULT_POWER_SPECTRUM, DefaultParams, gsl_params, physical_constants, spline_params
 
-__all__ = ("Cosmology", "CosmologyVanillaLCDM", "CosmologyCalculator")
+__all__ = ("Cosmology", "CosmologyVanillaLCDM", "CosmologyCalculator", "set_table_builder", "get_table_builder")
+
+# Who builds the tables of a Cosmology (background, growth, analytic P(k), halofit, tracer kernels):
+#   "device": the ccl_b200_build_* kernels (csrc/builders.cu), one-cosmology batches -- the product path; it fails
+#             loudly without a CUDA device, like every other compute entry;
+#   "host":   the numpy twins (background.py, power.py, tracers.py).  They are the test oracles of the device
+#             builders (pinned on the reference's benchmark files, tests/test_upstream_tables_cpu.py) and what
+#             the CPU-only test session uses to prepare inputs for the oracle; tests select them explicitly.
+_TABLE_BUILDER = "device"
+
+
+def set_table_builder(which):
+    global _TABLE_BUILDER
+    if which not in ("device", "host"):
+        raise ValueError("table builder must be 'device' or 'host'")
+    _TABLE_BUILDER = which
+
+
+def get_table_builder():
+    return _TABLE_BUILDER
+
 
 _ANALYTIC_TRANSFER = ("bbks", "eisenstein_hu", "eisenstein_hu_nowiggles")
 _TRANSFER_TYPES = _ANALYTIC_TRANSFER + ("boltzmann_camb", "boltzmann_class", "boltzmann_isitgr", "calculator")
@@ -57,6 +77,8 @@ class Cosmology:
         self._has_distances = self._has_growth = False
         self._dev = None
         self._splines = {}
+        self._table_builder = _TABLE_BUILDER   # snapshotted like the accuracy parameters
+        self._bgd = None                        # device-built background tables (device_builders.build_background)
 
     # ---- parameters (pyccl/cosmology.py:398-496, m_nu = 0 branch) ----
     @staticmethod
@@ -136,7 +158,10 @@ class Cosmology:
         """ccl_cosmology_compute_distances (src/ccl_background.c:417-589)."""
         if self._has_distances:
             return
-        self._bg.compute_distances()
+        if self._table_builder == "device":
+            self._device_background()
+        else:
+            self._bg.compute_distances()
         self._splines["chi"] = Akima(self._bg.a, self._bg.chi)
         self._splines["E"] = Akima(self._bg.a, self._bg.E)
         self._splines["achi"] = Akima(self._bg.achi_chi, self._bg.achi_a)
@@ -146,10 +171,27 @@ class Cosmology:
         """ccl_cosmology_compute_growth (src/ccl_background.c:763-1002)."""
         if self._has_growth:
             return
-        self._bg.compute_growth()
+        if self._table_builder == "device":
+            self._device_background()
+        else:
+            self._bg.compute_growth()
         self._splines["D"] = Akima(self._bg.a, self._bg.growth)
         self._splines["f"] = Akima(self._bg.a, self._bg.fgrowth)
         self._has_growth = True
+
+    def _device_background(self):
+        """E(a), chi(a), a(chi), D(a), f(a) in one launch sequence of the device builders
+        (ccl_b200_build_background; src/ccl_background.c:417-589,763-1002)."""
+        if self._bgd is not None:
+            return
+        from . import device_builders as db
+        bgd = db.build_background([self], self._spline_params, self._gsl_params)
+        n = int(bgd["n_achi"][0])
+        b = self._bg
+        b.E, b.chi = bgd["E"][0], bgd["chi"][0]
+        b.achi_chi, b.achi_a = np.ascontiguousarray(bgd["achi_chi"][0, :n]), np.ascontiguousarray(bgd["achi_a"][0, :n])
+        b.growth, b.fgrowth, b.growth0 = bgd["growth"][0], bgd["fgrowth"][0], float(bgd["growth0"][0])
+        self._bgd = bgd
 
     def compute_linear_power(self):
         """pyccl/cosmology.py:558-613 for the analytic transfer functions."""
@@ -161,7 +203,16 @@ class Cosmology:
             raise CCLError("transfer_function=%r needs an external Boltzmann code, which this build does not "
                            "wrap; use 'bbks', 'eisenstein_hu' or 'eisenstein_hu_nowiggles', or a "
                            "CosmologyCalculator / Pk2D with precomputed arrays" % trf)
-        self._pk_lin[DEFAULT_POWER_SPECTRUM] = Pk2D.from_model(self, trf)
+        if self._table_builder == "device":
+            from . import device_builders as db
+            if np.isnan(self["sigma8"]):
+                raise CCLError("Error CCL_ERROR_INCONSISTENT: sigma8 not set, required for analytic power spectra")
+            self.compute_growth()
+            lin = db.build_linear_power([self], trf, self._bgd, self._spline_params)
+            self._pk_lin[DEFAULT_POWER_SPECTRUM] = Pk2D(a_arr=lin["a"], lk_arr=lin["lk"], pk_arr=lin["logp"][0], is_logp=True,
+                                                        extrap_order_lok=1, extrap_order_hik=2)
+        else:
+            self._pk_lin[DEFAULT_POWER_SPECTRUM] = Pk2D.from_model(self, trf)
 
     def compute_nonlin_power(self):
         """pyccl/cosmology.py:622-647."""
@@ -312,6 +363,9 @@ class CosmologyCalculator(Cosmology):
                          Omega_g=Omega_g, Neff=Neff, m_nu=m_nu, mass_split=mass_split, w0=w0, wa=wa,
                          T_CMB=T_CMB, T_ncdm=T_ncdm, transfer_function='calculator',
                          matter_power_spectrum='calculator')
+        # injected tables: whatever is still computed (e.g. growth when only distances are given) must stay consistent
+        # with them, so the calculator keeps the host twins and never overwrites its background from the device
+        self._table_builder = "host"
         self._input_arrays = dict(background=background, growth=growth, pk_linear=pk_linear, pk_nonlin=pk_nonlin,
                                   nonlinear_model=nonlinear_model)
         if background is not None:
@@ -386,6 +440,20 @@ class CosmologyCalculator(Cosmology):
             dev.set_growth(a, self._bg.growth)
             self._dev_has_growth = True
         return dev
+
+    def _device_background(self):
+        """E(a), chi(a), a(chi), D(a), f(a) in one launch sequence of the device builders
+        (ccl_b200_build_background; src/ccl_background.c:417-589,763-1002)."""
+        if self._bgd is not None:
+            return
+        from . import device_builders as db
+        bgd = db.build_background([self], self._spline_params, self._gsl_params)
+        n = int(bgd["n_achi"][0])
+        b = self._bg
+        b.E, b.chi = bgd["E"][0], bgd["chi"][0]
+        b.achi_chi, b.achi_a = np.ascontiguousarray(bgd["achi_chi"][0, :n]), np.ascontiguousarray(bgd["achi_a"][0, :n])
+        b.growth, b.fgrowth, b.growth0 = bgd["growth"][0], bgd["fgrowth"][0], float(bgd["growth0"][0])
+        self._bgd = bgd
 
     def compute_linear_power(self):
         if not self.has_linear_power:

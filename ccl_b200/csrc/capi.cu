@@ -2,6 +2,8 @@
 // arrays are staged into one arena, uploaded with a single copy, and every derived table
 // (Akima / natural-cspline coefficients, bicubic derivative planes, index LUTs) is built by
 // device kernels.  No numerical work of the hot path happens on the CPU.
+#include <sched.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -55,6 +57,25 @@ bool use_device(int* status) {
 }
 
 constexpr size_t ALIGN_D = 4;  // raw region alignment in doubles (32 B)
+
+// Helper threads of the host-side staging / node checks: at most 16, at most the cores this process may run on
+// (sched_getaffinity: a launcher that pins ranks to core sets is respected), divided by the ranks that share
+// the node (LOCAL_WORLD_SIZE, exported by torchrun) so that 8 ranks do not start 128 threads on 32 cores.
+// CCL_B200_HOST_THREADS overrides.
+unsigned host_threads() {
+  static const unsigned n = [] {
+    if (const char* e = getenv("CCL_B200_HOST_THREADS")) return (unsigned)std::max(1, atoi(e));
+    unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = std::max(1, CPU_COUNT(&set));
+    unsigned ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(e));
+    // a rank pinned to its own cores keeps them all; otherwise share the node's cores evenly
+    if (cores >= std::thread::hardware_concurrency()) cores = std::max(1u, cores / ranks);
+    return std::min(16u, cores);
+  }();
+  return n;
+}
 
 // ---- plans: offsets into the arena, turned into device descriptors at commit ----
 constexpr size_t NO_LAND = (size_t)-1;
@@ -154,7 +175,7 @@ struct HostBuf {  // growable host staging; pinned once it is large
     if (pending.empty()) return;
     size_t total = 0;
     for (const Pending& q : pending) total += q.n;
-    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    unsigned nt = host_threads();
     if (total * sizeof(double) < (size_t(8) << 20)) nt = 1;
     auto work = [&](unsigned t) {
       for (size_t i = t; i < pending.size(); i += nt)
@@ -231,6 +252,7 @@ struct TableSet {
   std::vector<Tracer> h_tracers;
   std::vector<size_t> tracer_base;  // first tracer of cosmology i in h_tracers
   bool committed = false;
+  unsigned long long commit_gen = 0;  // bumped by every commit(): invalidates plans derived from the tables
   unsigned long long last_h2d = 0;
 
   size_t derive(size_t bytes) {
@@ -251,7 +273,7 @@ struct TableSet {
     size_t nodes = 0;
     for (size_t c = lo; c < hi; ++c) nodes += (size_t)checks[c].n;
     // a thread is worth spawning per ~256k nodes (a stacked call on a few hundred slots stays inline)
-    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    unsigned nt = host_threads();
     nt = (unsigned)std::min<size_t>(nt, nodes / (size_t(1) << 18) + 1);
     auto work = [&](unsigned t) {
       for (size_t c = lo + t; c < hi; c += nt) {
@@ -731,6 +753,7 @@ struct TableSet {
     for (DirectCopy& c : direct) c.done = true;  // the callers' pinned buffers are no longer needed
     owned.clear();
     committed = true;
+    ++commit_gen;
     return true;
   }
 };
@@ -785,6 +808,15 @@ struct ccl_b200_batch {
   cudaStream_t prep_stream = nullptr;
   DevBuf out;   // device result buffer of the host-buffer entry (kept across calls)
   DevBuf call;  // per-batch call buffers (colls, pairs, ells, counters, outputs)
+  // The grid tasks of the grid-sharing kernels depend only on the committed tables and on (collections, pairs):
+  // they are kept across calls (a likelihood evaluates the same geometry again and again; for one cosmology the
+  // grouping pass would otherwise be half of the call) and rebuilt when either changes.
+  HostBuf host_status;       // pinned landing buffer of the status words of a started call (_start / _wait)
+  size_t pending_status = 0; // entries a started call will deliver
+  DevBuf plan;
+  std::vector<int> plan_key;
+  unsigned long long plan_commit = ~0ull;
+  cudaEvent_t plan_event = nullptr;
 };
 
 struct ccl_b200_tables {
@@ -1280,6 +1312,7 @@ void ccl_b200_batch_free(ccl_b200_batch* b) {
     cudaStreamSynchronize(b->stream);
     cudaStreamDestroy(b->stream);
   }
+  if (b->plan_event) cudaEventDestroy(b->plan_event);
   if (b->prep_stream) {
     cudaStreamSynchronize(b->prep_stream);
     cudaStreamDestroy(b->prep_stream);
@@ -1517,12 +1550,33 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
   const size_t o_el = o_pr + ((size_t)npair * 8 + 255) / 256 * 256;
   const size_t o_ct = o_el + ((size_t)nl * 8 + 255) / 256 * 256;
   const size_t o_fp = o_ct + 256;
-  static const bool no_qag_fast = getenv("CCL_B200_NO_QAG_FAST") != nullptr;
-  const bool fast = fast_eligible(b, ncoll, npair) && (integration_method == INTEG_SPLINE || !no_qag_fast);
+  // 'qag_quad': the grid-sharing panel-cache kernel (limber_qag_fast.cu) is opt-in (CCL_B200_QAG_FAST=1): on the
+  // LSST-Y1 3x2pt batch 41 % of the requested panels are cache hits, which does not yet pay for evaluating every
+  // collection of a task on a miss (2.6e7 vs 2.8e7 C_ell/s)
+  static const bool qag_fast = getenv("CCL_B200_QAG_FAST") != nullptr;
+  const bool fast = fast_eligible(b, ncoll, npair) && (integration_method == INTEG_SPLINE || qag_fast);
   const unsigned long long redo_cap = 1ull << 20;
-  const size_t total = o_fp + (fast ? limber_fast_plan_bytes(nc, npair, redo_cap) : 0);
+  const size_t total = o_fp;
   if (!b->call.reserve(total, status)) return;
   char* base = b->call.p;
+  bool regroup = true;
+  if (fast) {
+    const char* before = b->plan.p;
+    if (!b->plan.reserve(limber_fast_plan_bytes(nc, npair, redo_cap), status)) return;
+    std::vector<int> key;
+    key.reserve(2 * (size_t)(ncoll + npair) + 2);
+    key.push_back(ncoll);
+    for (int i = 0; i < ncoll; ++i) { key.push_back(coll_start[i]); key.push_back(coll_count[i]); }
+    key.push_back(npair);
+    for (int i = 0; i < npair; ++i) { key.push_back(pair1[i]); key.push_back(pair2[i]); }
+    regroup = before != b->plan.p || b->plan_commit != b->ts.commit_gen || key != b->plan_key;
+    if (regroup) {
+      b->plan_key.swap(key);
+      b->plan_commit = b->ts.commit_gen;
+    } else if (b->plan_event) {
+      cudaStreamWaitEvent(stream, b->plan_event, 0);  // the plan was written on the stream of an earlier call
+    }
+  }
   // small pageable copies: the driver stages them before returning
   cudaMemcpyAsync(base + o_co, colls.data(), (size_t)ncoll * 8, cudaMemcpyHostToDevice, stream);
   cudaMemcpyAsync(base + o_pr, pairs.data(), (size_t)npair * 8, cudaMemcpyHostToDevice, stream);
@@ -1552,7 +1606,8 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
   }
   b->last_fast = fast;
   if (fast) {
-    FastPlan plan = limber_fast_plan_carve(base + o_fp, nc, npair, redo_cap);
+    FastPlan plan = limber_fast_plan_carve(b->plan.p, nc, npair, redo_cap);
+    plan.regroup = regroup ? 1 : 0;
     plan.ntr_max = 1;
     plan.has_rsd = 0;
     for (const CosmoPlan& c : b->ts.cosmos) {
@@ -1561,10 +1616,18 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
     }
     if (integration_method == INTEG_SPLINE) {
       if (!cuda_ok(launch_limber_fast(P, plan, stream), "limber fast launch", status)) return;
+      if (regroup) {
+        if (!b->plan_event) cudaEventCreateWithFlags(&b->plan_event, cudaEventDisableTiming);
+        cudaEventRecord(b->plan_event, stream);
+      }
       return;
     }
     // 'qag_quad': grid-sharing panels, then the general kernel over the redo list, then CQUAD
     if (!cuda_ok(launch_limber_qag_fast(P, plan, ws, wsb, stream), "limber qag fast launch", status)) return;
+    if (regroup) {
+      if (!b->plan_event) cudaEventCreateWithFlags(&b->plan_event, cudaEventDisableTiming);
+      cudaEventRecord(b->plan_event, stream);
+    }
   } else if (!cuda_ok(launch_limber(P, integration_method, ws, wsb, stream), "limber launch", status))
     return;
   if (integration_method == INTEG_QAG) {
@@ -1577,34 +1640,64 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
   }
 }
 
-void ccl_b200_batch_angular_cls_limber(ccl_b200_batch* b, int ncoll, const int* coll_start,
-                                       const int* coll_count, int npair, const int* pair1,
-                                       const int* pair2, int nl, const double* ell, int integration_method,
-                                       double* cl_out, int* status_out, int* status) {
+void ccl_b200_batch_angular_cls_limber_start(ccl_b200_batch* b, int ncoll, const int* coll_start,
+                                             const int* coll_count, int npair, const int* pair1,
+                                             const int* pair2, int nl, const double* ell, int integration_method,
+                                             double* cl_out, int* status) {
   if (*status || !b) return;
   if (!cuda_ok(cudaSetDevice(b->ts.device), "cudaSetDevice", status)) return;
   const size_t nc = b->ts.cosmos.size();
   const size_t ncl = nc * npair * (size_t)nl;
   const size_t nst = nc * (size_t)npair;
+  b->pending_status = 0;
   if (!b->out.reserve(ncl * 8 + nst * 2 * sizeof(int) + 512, status)) return;
   double* d_cl = reinterpret_cast<double*>(b->out.p);
   int* d_st = reinterpret_cast<int*>(b->out.p + (ncl * 8 + 255) / 256 * 256);
   ccl_b200_batch_angular_cls_limber_dev(b, ncoll, coll_start, coll_count, npair, pair1, pair2, nl, ell,
                                         integration_method, d_cl, d_st, b->stream, status);
   if (*status) return;
-  std::vector<int> st(nst);
+  // status words land in a page-locked buffer of the batch (2 ints per double slot)
+  if (!b->host_status.pinned || b->host_status.cap * 2 < nst) {
+    b->host_status.release();
+    double* q = nullptr;
+    const size_t nd = std::max<size_t>((nst + 1) / 2, 64);
+    if (cudaHostAlloc((void**)&q, nd * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      *status = CCL_B200_ERROR_MEMORY;
+      set_err("ccl_b200: cudaHostAlloc(status buffer) failed");
+      return;
+    }
+    b->host_status.p = q; b->host_status.cap = nd; b->host_status.pinned = true;
+  }
   if (ncl) cudaMemcpyAsync(cl_out, d_cl, ncl * 8, cudaMemcpyDeviceToHost, b->stream);
-  if (nst) cudaMemcpyAsync(st.data(), d_st, nst * sizeof(int), cudaMemcpyDeviceToHost, b->stream);
+  if (nst) cudaMemcpyAsync(b->host_status.p, d_st, nst * sizeof(int), cudaMemcpyDeviceToHost, b->stream);
+  b->pending_status = nst;
+}
+
+void ccl_b200_batch_angular_cls_limber_wait(ccl_b200_batch* b, int* status_out, int* status) {
+  if (*status || !b) return;
+  if (!cuda_ok(cudaSetDevice(b->ts.device), "cudaSetDevice", status)) return;
   if (!cuda_ok(cudaStreamSynchronize(b->stream), "limber kernel", status)) return;
+  const int* st = reinterpret_cast<const int*>(b->host_status.p);
   bool any = false;
-  for (size_t i = 0; i < nst; ++i) {
+  for (size_t i = 0; i < b->pending_status; ++i) {
     if (status_out) status_out[i] = st[i];
     any = any || st[i];
   }
+  b->pending_status = 0;
   if (any) {
     *status = CCL_B200_ERROR_INTEG;
     set_err("ccl_cls.c: ccl_angular_cls_limber(); integration error\n");
   }
+}
+
+void ccl_b200_batch_angular_cls_limber(ccl_b200_batch* b, int ncoll, const int* coll_start,
+                                       const int* coll_count, int npair, const int* pair1,
+                                       const int* pair2, int nl, const double* ell, int integration_method,
+                                       double* cl_out, int* status_out, int* status) {
+  ccl_b200_batch_angular_cls_limber_start(b, ncoll, coll_start, coll_count, npair, pair1, pair2, nl, ell,
+                                          integration_method, cl_out, status);
+  ccl_b200_batch_angular_cls_limber_wait(b, status_out, status);
 }
 
 unsigned long long ccl_b200_batch_spline_nodes(const ccl_b200_batch* b, int ncoll, const int* coll_start,

@@ -753,12 +753,14 @@ FastPlan limber_fast_plan_carve(void* base, int ncosmo, int npair, unsigned long
   G.redo_cap = redo_cap;
   G.ntr_max = FAST_MAX_TRACERS;
   G.has_rsd = 1;
+  G.regroup = 1;
   return G;
 }
 
 // grid tasks of every cosmology (shared by the 'spline' and 'qag_quad' grid-sharing integrators)
 void launch_limber_group(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream) {
   cudaMemsetAsync(plan.redo, 0, sizeof(unsigned long long), stream);
+  if (!plan.regroup) return;
   const size_t gsm = sizeof(double) * 2 * ((size_t)prob.ncoll + prob.npair) + sizeof(int) * (size_t)prob.npair;
   if (gsm > 40 * 1024)
     cudaFuncSetAttribute(limber_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);

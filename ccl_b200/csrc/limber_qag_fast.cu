@@ -7,11 +7,12 @@
 // ranges (the grid tasks limber_group_kernel builds for the 'spline' integrator) therefore request the SAME
 // panels again and again: the first panel and its two halves always, deeper ones whenever the integrands peak in
 // the same place.  One warp runs the QAG state machines of a task's pairs one after the other over a per-warp
-// PANEL CACHE: a panel's 41 Gauss-Kronrod abscissae are evaluated once -- k, chi, a(chi), k P(k,a) and the
-// transfer D of EVERY collection of the task, with the lean lookups of the 'spline' kernel (sub-tracers on
-// identical grids share one interval search) -- and every pair that asks for the panel again only forms
-// k P D1 D2 and the four GK sums.  Both children of a bisection are evaluated together (82 abscissae over three
-// lane passes).  The bookkeeping (interval list, error sums, round-off counters, stop tests) is GSL's, in the
+// PANEL CACHE, filled lazily at two levels: the node part of a panel (k, chi, a(chi), k P(k,a) at its 41
+// Gauss-Kronrod abscissae) is evaluated the first time ANY pair of the task asks for the panel, the transfer D of a
+// collection on that panel the first time a pair USING that collection asks for it -- with the lean lookups of the
+// 'spline' kernel (32-byte coefficient records, descriptors in shared memory).  A pair that finds everything
+// cached only forms k P D1 D2 and the four GK sums.  Both children of a bisection are evaluated together
+// (82 abscissae over three lane passes).  Nothing is ever evaluated that the reference would not evaluate.  The bookkeeping (interval list, error sums, round-off counters, stop tests) is GSL's, in the
 // form of the general kernel (kernels.cu, limber_qag_kernel), which also serves as the redo path for whatever
 // this kernel does not cover: nodes outside the a(chi) / P(k,a) tables, der_bessel 1/2 sub-tracers, oversize tasks.
 #include <cfloat>
@@ -29,33 +30,31 @@ constexpr int QFW = 8;            // warps per CTA
 constexpr int NCG = CCLB_NCG;     // collections per grid task
 constexpr int NPG = CCLB_NPG;     // pairs per grid task
 constexpr int NSG = 2 * CCLB_NCG; // sub-tracers per grid task
-constexpr int NPC = 24;           // cached panels per warp (the last slot doubles as scratch when the cache is full)
+constexpr int NPC = 24;           // cached panels per warp (the last two slots are scratch once the cache is full)
 constexpr int PN = 41;            // abscissae per panel
 constexpr int PS = 48;            // row stride of a cached panel (doubles)
-constexpr int PROWS = NCG + 1;    // k P row + one D row per collection
-constexpr int QGB = 64;           // grid tasks whose limits are precomputed per CTA pass
+constexpr int PROWS = NCG + 3;    // k P, chi, a rows + one D row per collection
+constexpr int QLB = 10;           // ells per CTA work item
 constexpr int QCTAS_PER_SM = 2;
 
 __constant__ double q_xgk[21];
 __constant__ double q_wgk[21];
 __constant__ double q_wg[10];
 
-struct QPar {
-  double lkmin, lkmax;
-  int grid, pad;
-};
-
 struct QCta {
   Spline1D achi;
   F2D psp;
-  QPar gp[QGB];
+  int der_angles[FAST_MAX_TRACERS];
   int next_task, item;
 };
 
 struct __align__(16) QWarp {
-  FastEnt ents[NSG];  // the task's sub-tracers (doff = collection slot)
-  double2 keys[NPC];  // (a, b) of the cached panels
-  int2 po[NPG];       // collection slots of the task's pairs
+  FastEnt ents[NSG];    // the task's sub-tracers, ordered by collection slot
+  double2 keys[NPC];    // (a, b) of the cached panels
+  int2 po[NPG];         // collection slots of the task's pairs
+  int2 cs[NCG];         // {first entry, entries} of every collection slot
+  unsigned dmask[NPC];  // bit c: the D row of collection slot c is valid in this panel
+  unsigned raw[NSG];    // the task's list entries as limber_group_kernel wrote them
 };
 
 // Layout of the CTA's dynamic shared memory; tr[] really holds FastPlan::ntr_max entries.
@@ -97,8 +96,8 @@ __device__ __forceinline__ bool q_subinterval_too_small(double a1, double a2, do
 __device__ __forceinline__ void panel_sums(const double* panel, int ca, int cb, double a, double b, int lane,
                                            double& result, double& abserr, double& resabs, double& resasc) {
   const double* kp = panel;
-  const double* da = panel + (1 + ca) * PS;
-  const double* db = panel + (1 + cb) * PS;
+  const double* da = panel + (3 + ca) * PS;
+  const double* db = panel + (3 + cb) * PS;
   const double half_length = 0.5 * (b - a);
   const double abs_half_length = fabs(half_length);
   double rk = 0, rg = 0, ra = 0, f1 = 0, f2 = 0;
@@ -151,21 +150,26 @@ limber_qag_fast_kernel(const LimberProblem P, const FastPlan G, double* ws, doub
   double* rlist = blist + limit;
   double* elist = rlist + limit;
   double* pcache = cache + gw * (size_t)NPC * PROWS * PS;
-  const long long nitems = (long long)P.ncosmo * P.nl;
+  // work item of a CTA: one cosmology x a block of QLB ells (its descriptors are staged once, its (ell, grid)
+  // tasks are pulled by the warps from a shared counter: one barrier per few hundred tasks)
+  const int nlb = (P.nl + QLB - 1) / QLB;
+  const long long nitems = (long long)P.ncosmo * nlb;
 
   for (;;) {
     __syncthreads();  // the previous item is drained
-    if (threadIdx.x == 0) S.item = (int)min((unsigned long long)nitems, atomicAdd(next_item, 1ull));
+    if (threadIdx.x == 0) {
+      S.item = (int)min((unsigned long long)nitems, atomicAdd(next_item, 1ull));
+      S.next_task = 0;
+    }
     __syncthreads();
     const long long item = S.item;
     if (item >= nitems) break;
-    const int il = (int)(item % P.nl);
-    const int ic = (int)(item / P.nl);
+    const int il0 = (int)(item % nlb) * QLB;
+    const int nls = min(QLB, P.nl - il0);
+    const int ic = (int)(item / nlb);
     const Cosmo* cs = P.cosmos + ic;
-    const double ell = P.ells[il];
-    const double lp1h = ell + 0.5;
 
-    // ---- per-item staging of the descriptors this (cosmology, ell) needs ----
+    // ---- per-item staging of the descriptors this cosmology needs ----
     for (int t = threadIdx.x; t < cs->ntracers; t += blockDim.x) {
       const Tracer& tr = cs->tracers[t];
       s_tr[t].kernel = pack_s1(tr.kernel);
@@ -173,7 +177,8 @@ limber_qag_fast_kernel(const LimberProblem P, const FastPlan G, double* ws, doub
       const bool fold = tr.has_transfer && tr.const_transfer;  // see limber_fast.cu
       s_tr[t].has_fa = tr.has_transfer && !fold;
       s_tr[t].der_bessel = tr.der_bessel;
-      s_tr[t].pref[0] = tracer_prefactor(tr, ell) * (fold ? tr.const_transfer_value : 1.0);
+      s_tr[t].pref[0] = fold ? tr.const_transfer_value : 1.0;  // the ell prefactor is applied per task
+      S.der_angles[t] = tr.der_angles;
     }
     if (threadIdx.x == 32) S.achi = cs->achi;
     if (threadIdx.x == 64) S.psp = *cs->psp;
@@ -181,239 +186,249 @@ limber_qag_fast_kernel(const LimberProblem P, const FastPlan G, double* ws, doub
     const GridPair* gpairs = G.gpairs + (size_t)ic * G.gstride;
     const unsigned* gsubs = G.gsubs + (size_t)ic * G.sstride;
     const int ngrids = G.ngrids[ic];
+    const int ntasks = ngrids * nls;
+    __syncthreads();
 
-    for (int t0 = 0; t0 < ngrids; t0 += QGB) {
-      __syncthreads();
-      const int nb = min(QGB, ngrids - t0);
-      if (threadIdx.x < nb) {  // get_k_interval (src/ccl_cls.c:91-99) once per grid
-        QPar q;
-        q.grid = t0 + threadIdx.x;
-        const GridDesc gd = grids[q.grid];
-        double chi_min = gd.chi_min;
-        if (chi_min <= 0) chi_min = 0.5 * lp1h / P.par.K_MAX;
-        q.lkmax = log(fmin(P.par.K_MAX, 2 * lp1h / chi_min));
-        q.lkmin = log(fmax(P.par.K_MIN, lp1h / gd.chi_max));
-        q.pad = 0;
-        S.gp[threadIdx.x] = q;
+    for (;;) {
+      int task = 0;
+      if (lane == 0) task = atomicAdd(&S.next_task, 1);
+      task = __shfl_sync(FULL, task, 0);
+      if (task >= ntasks) break;
+      const int il = il0 + task / ngrids;
+      const GridDesc gd = grids[task % ngrids];
+      const double ell = P.ells[il];
+      const double lp1h = ell + 0.5;
+      const int ncoll = gd.ncoll, np = gd.npair, nsub = gd.nsub;
+      // get_k_interval (src/ccl_cls.c:91-99)
+      double chi_min = gd.chi_min;
+      if (chi_min <= 0) chi_min = 0.5 * lp1h / P.par.K_MAX;
+      const double lkmax = log(fmin(P.par.K_MAX, 2 * lp1h / chi_min));
+      const double lkmin = log(fmax(P.par.K_MIN, lp1h / gd.chi_max));
+      __syncwarp();
+      if (lane < np) {
+        const GridPair pr = gpairs[gd.pair_begin + lane];
+        W.po[lane] = make_int2(pr.a, pr.b);
       }
-      if (threadIdx.x == 0) S.next_task = 0;
-      __syncthreads();
-
-      for (;;) {
-        int gl = 0;
-        if (lane == 0) gl = atomicAdd(&S.next_task, 1);
-        gl = __shfl_sync(FULL, gl, 0);
-        if (gl >= nb) break;
-        const GridDesc gd = grids[S.gp[gl].grid];
-        const int ncoll = gd.ncoll, np = gd.npair, nsub = gd.nsub;
-        const double lkmin = S.gp[gl].lkmin, lkmax = S.gp[gl].lkmax;
-        __syncwarp();
-        if (lane < np) {
-          const GridPair pr = gpairs[gd.pair_begin + lane];
-          W.po[lane] = make_int2(pr.a, pr.b);
+      const int nent = min(nsub, NSG);
+      if (lane < nent) W.raw[lane] = gsubs[gd.sub_begin + lane];
+      __syncwarp();
+      if (lane < nent) {
+        // order by collection slot (stable): collections are evaluated one at a time, on demand
+        const unsigned ent = W.raw[lane];
+        const unsigned slot = (ent >> 8) & 0xfu;
+        int rank = 0;
+        for (int j = 0; j < nent; ++j) {
+          const unsigned sj = (W.raw[j] >> 8) & 0xfu;
+          rank += (sj < slot) || (sj == slot && j < lane);
         }
-        if (lane < min(nsub, NSG)) {
-          const unsigned ent = gsubs[gd.sub_begin + lane];
-          const FastTr& tr = s_tr[ent & 0xffu];
-          FastEnt en;
-          en.kcr = tr.kernel.cr;
-          en.pref = tr.pref[0];
-          en.acr = tr.has_fa ? tr.fa.cr : nullptr;
-          en.flags = ent & 0xffffu;
-          en.troff = (int)(reinterpret_cast<const char*>(&tr) - reinterpret_cast<const char*>(&W.ents[lane]));
-          W.ents[lane] = en;
+        const int t = (int)(ent & 0xffu);
+        const FastTr& tr = s_tr[t];
+        // ccl_cl_tracer_t_get_f_ell (src/ccl_tracers.c:703-726), /(l+1/2)^2 for der_bessel == -1 (src/ccl_cls.c:118)
+        double pref = tracer_f_ell(S.der_angles[t], ell);
+        if (tr.der_bessel == -1) pref /= (lp1h * lp1h);
+        FastEnt en;
+        en.kcr = tr.kernel.cr;
+        en.pref = pref * tr.pref[0];
+        en.acr = tr.has_fa ? tr.fa.cr : nullptr;
+        en.flags = ent & 0xfffu;
+        en.troff = (int)(reinterpret_cast<const char*>(&tr) - reinterpret_cast<const char*>(&W.ents[rank]));
+        W.ents[rank] = en;
+      }
+      if (lane < ncoll) {
+        int start = 0, cnt = 0;
+        for (int j = 0; j < nent; ++j) {
+          const unsigned sj = (W.raw[j] >> 8) & 0xfu;
+          start += sj < (unsigned)lane;
+          cnt += sj == (unsigned)lane;
         }
-        __syncwarp();
-        // outside the P(k,a) table in ln k, der_bessel 1/2 sub-tracers, oversize list: general kernel
-        bool redo = !(lkmin >= S.psp.lkmin && lkmax <= S.psp.lkmax) || nsub > NSG || gd.has_rsd;
-        int ncached = 0;
-
-        // Evaluate the abscissae of nmiss (1 or 2) panels into their cache slots.  Returns false when a node
-        // leaves the tables the fast path reads (the task is then redone by the general kernel).
-        auto eval_panels = [&](int nmiss, const double* pa, const double* pb, const int* slot) -> bool {
-          bool bad = false;
-          for (int e = lane; e < PN * nmiss; e += 32) {
-            const int p = e >= PN ? 1 : 0, q = e - p * PN;
-            const double center = 0.5 * (pa[p] + pb[p]);
-            const double half_length = 0.5 * (pb[p] - pa[p]);
-            double lk;  // gsl_integration_qk abscissae
-            if (q == 40) lk = center;
-            else if (q < 20) lk = center - half_length * q_xgk[q];
-            else lk = center + half_length * q_xgk[q - 20];
-            double* row = pcache + (size_t)slot[p] * PROWS * PS + q;
-            const double k = exp(lk);
-            const double chi = lp1h / k;
-            // ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277); chi > 0 here
-            double a = 1.0;
-            if (!(chi < 1.e-8)) {
-              if (chi >= S.achi.x0 && chi <= S.achi.xn) {
-                const Rec1 r = find_rec(S.achi, chi);
-                a = cubic(make_double4(r.y, r.b, r.c, r.d), chi - r.x0);
-              } else
-                bad = true;
-            }
-            if (!(a >= S.psp.amin && a <= S.psp.amax)) bad = true;
-            double pk = 0.0;
-            if (!bad) pk = fast_exp(bicubic_eval(S.psp, lk, a, 0));
-            __stcg(row, k * pk);
-            int ki = 0, ai = 0;
-            double kdel = 0.0, adel = 0.0;
-            bool inside = false;
-            const FastEnt* ep = W.ents;
-#pragma unroll 1
-            for (int s = 0; s < nsub; ++s, ++ep) {
-              const FastEnt en = *ep;
-              const unsigned ent = en.flags;
-              if (__builtin_expect((ent & SUB_NEWK) != 0u, 0)) {
-                const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
-                double x0;
-                ki = find_interval(tr.kernel, chi, x0);
-                kdel = chi - x0;
-                inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
-              }
-              double wt = cubic(ldg4(en.kcr + ki), kdel);
-              if (en.acr != nullptr) {
-                if (__builtin_expect((ent & SUB_NEWA) != 0u, 0)) {
-                  const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
-                  const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
-                  double x0;
-                  ai = find_interval(tr.fa, a_ev, x0);
-                  adel = a_ev - x0;
-                }
-                wt *= cubic(ldg4(en.acr + ai), adel);
-              }
-              double val = inside ? wt * en.pref : 0.0;
-              double* dp = row + (1 + ((ent >> 8) & 0xfu)) * PS;
-              if (!(ent & SUB_FIRST)) val += __ldcg(dp);
-              __stcg(dp, val);
-            }
-          }
-          bad = __any_sync(FULL, bad);
-          __syncwarp();
-          return !bad;
-        };
-
-        // Cache slot of panel (a, b): hit -> its slot; miss -> a fresh slot (or the scratch slot when full),
-        // flagged in `miss`.
-        auto find_panel = [&](double a, double b, bool& miss) -> int {
-          bool hit = false;
-          if (lane < ncached) {
-            const double2 key = W.keys[lane];
-            hit = (key.x == a) && (key.y == b);
-          }
-          const unsigned m = __ballot_sync(FULL, hit);
-          if (m) { miss = false; return __ffs(m) - 1; }
-          miss = true;
-          int slot = NPC - 1;
-          if (ncached < NPC - 1) {
-            slot = ncached++;
-            if (lane == 0) W.keys[slot] = make_double2(a, b);
-          }
-          __syncwarp();
-          return slot;
-        };
+        W.cs[lane] = make_int2(start, cnt);
+      }
+      __syncwarp();
+      // outside the P(k,a) table in ln k, der_bessel 1/2 sub-tracers, oversize list: general kernel
+      bool redo = !(lkmin >= S.psp.lkmin && lkmax <= S.psp.lkmax) || nsub > NSG || gd.has_rsd;
+      int ncached = 0;
+      unsigned long long nodes_done = 0;
 
 #pragma unroll 1
-        for (int q = 0; q < np && !redo; ++q) {
-          const int2 po = W.po[q];
-          const int ipair = gpairs[gd.pair_begin + q].out;
-          const double epsabs = 0.0, epsrel = P.par.LIMBER_EPSREL;
-          int gsl = 0;
-          unsigned long long nev = 41;
-          double result = 0.0;
-          if (epsabs <= 0 && (epsrel < 50 * DBL_EPSILON || epsrel < 0.5e-28)) {
-            gsl = ST_GSL_EBADTOL;
-          } else if (P.par.force_cquad) {
-            gsl = ST_GSL_EROUND;  // tests of the fallback branch: skip QAG
-            nev = 0;
-          } else {
-            bool miss;
-            const int s0 = find_panel(lkmin, lkmax, miss);
-            if (miss && !eval_panels(1, &lkmin, &lkmax, &s0)) { redo = true; break; }
-            double r0, e0, ab0, as0;
-            panel_sums(pcache + (size_t)s0 * PROWS * PS, po.x, po.y, lkmin, lkmax, lane, r0, e0, ab0, as0);
-            double tolerance = fmax(epsabs, epsrel * fabs(r0));
-            const double round_off = 50 * DBL_EPSILON * ab0;
-            result = r0;
-            if (e0 <= round_off && e0 > tolerance) gsl = ST_GSL_EROUND;
-            else if ((e0 <= tolerance && e0 != as0) || e0 == 0.0) gsl = 0;
-            else if (limit == 1) gsl = ST_GSL_EMAXITER;
+      for (int q = 0; q < np && !redo; ++q) {
+        const int2 po = W.po[q];
+        const unsigned pmask = (1u << po.x) | (1u << po.y);  // the two collections of this pair
+        const int ipair = gpairs[gd.pair_begin + q].out;
+        const double epsabs = 0.0, epsrel = P.par.LIMBER_EPSREL;
+        int gsl = 0;
+        unsigned long long nev = 0;
+        double result = 0.0;
+        bool running = true;
+        if (epsabs <= 0 && (epsrel < 50 * DBL_EPSILON || epsrel < 0.5e-28)) {
+          gsl = ST_GSL_EBADTOL;
+          nev = 41;
+          running = false;
+        } else if (P.par.force_cquad) {
+          gsl = ST_GSL_EROUND;  // tests of the fallback branch: skip QAG
+          running = false;
+        }
+        // gsl_integration_qag as ONE loop: step 0 requests the whole interval, every later step the two halves of
+        // the interval with the largest error estimate (one call site each for the cache look-up, the node part,
+        // the transfers and the GK sums keeps the kernel inside the instruction cache)
+        int size = 0, iteration = 0, roundoff_type1 = 0, roundoff_type2 = 0, error_type = 0, imax = 0;
+        double area = 0.0, errsum = 0.0, tolerance = 0.0, r_i = 0.0, e_i = 0.0;
+        double qa[2] = {lkmin, 0.0}, qb[2] = {lkmax, 0.0};
+        int npan = 1;
+        while (running) {
+          // ---- panel cache: hit -> its slot; miss -> a fresh slot, or one of the two scratch slots when full ----
+          int sl[2] = {0, 0};
+          double pa[2], pb[2];
+          int ps[2], nmiss = 0;
+#pragma unroll 1
+          for (int p = 0; p < npan; ++p) {
+            bool hit = false;
+            if (lane < ncached) {
+              const double2 key = W.keys[lane];
+              hit = (key.x == qa[p]) && (key.y == qb[p]);
+            }
+            const unsigned m = __ballot_sync(FULL, hit);
+            int slot;
+            if (m) slot = __ffs(m) - 1;
             else {
-              __syncwarp();
-              if (lane == 0) { alist[0] = lkmin; blist[0] = lkmax; rlist[0] = r0; elist[0] = e0; }
-              __syncwarp();
-              int size = 1;
-              double area = r0, errsum = e0;
-              int iteration = 1, roundoff_type1 = 0, roundoff_type2 = 0, error_type = 0;
-              do {
-                // retrieve(): interval with the largest error estimate
-                double emax = -1.0;
-                int imax = 0;
-                for (int i = lane; i < size; i += 32) {
-                  const double e = elist[i];
-                  if (e > emax) { emax = e; imax = i; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  const double eo = __shfl_xor_sync(FULL, emax, o);
-                  const int io = __shfl_xor_sync(FULL, imax, o);
-                  if (eo > emax || (eo == emax && io < imax)) { emax = eo; imax = io; }
-                }
-                const double a_i = alist[imax], b_i = blist[imax], r_i = rlist[imax], e_i = elist[imax];
-                const double a1 = a_i, b1 = 0.5 * (a_i + b_i), a2 = b1, b2 = b_i;
-                // both children together: hits are read back, misses are evaluated in one pass
-                bool m1, m2;
-                const int sl1 = find_panel(a1, b1, m1);
-                int sl2 = find_panel(a2, b2, m2);
-                if (m1 && m2 && sl1 == sl2) {
-                  // cache full: the scratch slot cannot hold both children; evaluate and reduce one after the other
-                  const int one = sl1;
-                  if (!eval_panels(1, &a1, &b1, &one)) { redo = true; break; }
-                }
-                double ar[2], er[2], rab[2], ras[2];
-                if (m1 && m2 && sl1 == sl2) {
-                  panel_sums(pcache + (size_t)sl1 * PROWS * PS, po.x, po.y, a1, b1, lane, ar[0], er[0], rab[0], ras[0]);
-                  if (!eval_panels(1, &a2, &b2, &sl2)) { redo = true; break; }
-                  panel_sums(pcache + (size_t)sl2 * PROWS * PS, po.x, po.y, a2, b2, lane, ar[1], er[1], rab[1], ras[1]);
-                } else {
-                  const double pa[2] = {m1 ? a1 : a2, a2}, pb[2] = {m1 ? b1 : b2, b2};
-                  const int ps[2] = {m1 ? sl1 : sl2, sl2};
-                  const int nmiss = (m1 ? 1 : 0) + (m2 ? 1 : 0);
-                  if (nmiss && !eval_panels(nmiss, pa, pb, ps)) { redo = true; break; }
-                  panel_sums(pcache + (size_t)sl1 * PROWS * PS, po.x, po.y, a1, b1, lane, ar[0], er[0], rab[0], ras[0]);
-                  panel_sums(pcache + (size_t)sl2 * PROWS * PS, po.x, po.y, a2, b2, lane, ar[1], er[1], rab[1], ras[1]);
-                }
-                nev += 82;
-                const double area12 = ar[0] + ar[1];
-                const double error12 = er[0] + er[1];
-                errsum += (error12 - e_i);
-                area += area12 - r_i;
-                if (ras[0] != er[0] && ras[1] != er[1]) {
-                  const double delta = r_i - area12;
-                  if (fabs(delta) <= 1.0e-5 * fabs(area12) && error12 >= 0.99 * e_i) roundoff_type1++;
-                  if (iteration >= 10 && error12 > e_i) roundoff_type2++;
-                }
-                tolerance = fmax(epsabs, epsrel * fabs(area));
-                if (errsum > tolerance) {
-                  if (roundoff_type1 >= 6 || roundoff_type2 >= 20) error_type = 2;
-                  if (q_subinterval_too_small(a1, a2, b2)) error_type = 3;
-                }
-                // update(): larger-error half stays at imax, the other is appended
-                __syncwarp();
-                if (lane == 0) {
-                  if (er[1] > er[0]) {
-                    alist[imax] = a2; rlist[imax] = ar[1]; elist[imax] = er[1];
-                    alist[size] = a1; blist[size] = b1; rlist[size] = ar[0]; elist[size] = er[0];
-                  } else {
-                    blist[imax] = b1; rlist[imax] = ar[0]; elist[imax] = er[0];
-                    alist[size] = a2; blist[size] = b2; rlist[size] = ar[1]; elist[size] = er[1];
+              slot = NPC - 2 + p;
+              if (ncached < NPC - 2) {
+                slot = ncached++;
+                if (lane == 0) W.keys[slot] = make_double2(qa[p], qb[p]);
+              }
+              pa[nmiss] = qa[p]; pb[nmiss] = qb[p]; ps[nmiss] = slot;
+              ++nmiss;
+            }
+            sl[p] = slot;
+            __syncwarp();
+          }
+          // ---- node part of the missing panels: k P, chi, a at their 41 abscissae each ----
+          if (nmiss) {
+            bool bad = false;
+            for (int e = lane; e < PN * nmiss; e += 32) {
+              const int p = e >= PN ? 1 : 0, j = e - p * PN;
+              const double center = 0.5 * (pa[p] + pb[p]);
+              const double half_length = 0.5 * (pb[p] - pa[p]);
+              double lk;  // gsl_integration_qk abscissae
+              if (j == 40) lk = center;
+              else if (j < 20) lk = center - half_length * q_xgk[j];
+              else lk = center + half_length * q_xgk[j - 20];
+              double* row = pcache + (size_t)ps[p] * PROWS * PS + j;
+              const double k = exp(lk);
+              const double chi = lp1h / k;
+              // ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277); chi > 0 here
+              double a = 1.0;
+              if (!(chi < 1.e-8)) {
+                if (chi >= S.achi.x0 && chi <= S.achi.xn) {
+                  const Rec1 r = find_rec(S.achi, chi);
+                  a = cubic(make_double4(r.y, r.b, r.c, r.d), chi - r.x0);
+                } else
+                  bad = true;  // the general kernel reports it
+              }
+              if (!(a >= S.psp.amin && a <= S.psp.amax)) bad = true;  // growth extrapolation: general kernel
+              double pk = 0.0;
+              if (!bad) pk = fast_exp(bicubic_eval(S.psp, lk, a, 0));
+              __stcg(row, k * pk);
+              __stcg(row + PS, chi);
+              __stcg(row + 2 * PS, a);
+            }
+            if (lane < nmiss) W.dmask[ps[lane]] = 0u;
+            nodes_done += (unsigned long long)PN * nmiss;
+            if (__any_sync(FULL, bad)) { redo = true; break; }
+            __syncwarp();
+          }
+          // ---- transfers of this pair's collections where a panel does not hold them yet ----
+          // transfer_limber_wrap (src/ccl_cls.c:150-164) over the sub-tracers of those collections only.  Outside a
+          // kernel's support the lookup runs on the first / last interval and the term is dropped
+          // (ccl_f1d_t_eval: the end nodes count as outside, src/ccl_f1d.c:137-161).
+          unsigned need[2];
+          need[0] = pmask & ~W.dmask[sl[0]];
+          need[1] = npan > 1 ? (pmask & ~W.dmask[sl[1]]) : 0u;
+          if (need[0] | need[1]) {
+            for (int e = lane; e < PN * npan; e += 32) {
+              const int p = e >= PN ? 1 : 0, j = e - p * PN;
+              unsigned todo = need[p];
+              if (!todo) continue;
+              double* row = pcache + (size_t)sl[p] * PROWS * PS + j;
+              const double chi = __ldcg(row + PS), a = __ldcg(row + 2 * PS);
+              while (todo) {
+                const int c = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int2 cr = W.cs[c];
+                double D = 0.0;
+                const FastEnt* ep = W.ents + cr.x;
+#pragma unroll 1
+                for (int s = 0; s < cr.y; ++s, ++ep) {
+                  const FastEnt en = *ep;
+                  const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
+                  double x0;
+                  const int ki = find_interval(tr.kernel, chi, x0);
+                  const bool inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
+                  double wt = cubic(ldg4(en.kcr + ki), chi - x0);
+                  if (en.acr != nullptr) {
+                    const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
+                    const int ai = find_interval(tr.fa, a_ev, x0);
+                    wt *= cubic(ldg4(en.acr + ai), a_ev - x0);
                   }
+                  D += inside ? wt * en.pref : 0.0;
                 }
-                __syncwarp();
-                size++;
-                iteration++;
-              } while (iteration < limit && !error_type && errsum > tolerance);
-              if (redo) break;
+                __stcg(row + (3 + c) * PS, D);
+              }
+            }
+            if (lane < npan && need[lane]) W.dmask[sl[lane]] |= need[lane];
+            __syncwarp();
+          }
+          // ---- GK41 sums of the requested panels ----
+          double ar[2] = {0, 0}, er[2] = {0, 0}, rab[2] = {0, 0}, ras[2] = {0, 0};
+#pragma unroll 1
+          for (int p = 0; p < npan; ++p)
+            panel_sums(pcache + (size_t)sl[p] * PROWS * PS, po.x, po.y, qa[p], qb[p], lane, ar[p], er[p], rab[p], ras[p]);
+          nev += (unsigned long long)PN * npan;
+          // ---- gsl_integration_qag bookkeeping (integration/qag.c) ----
+          if (iteration == 0) {
+            tolerance = fmax(epsabs, epsrel * fabs(ar[0]));
+            const double round_off = 50 * DBL_EPSILON * rab[0];
+            result = ar[0];
+            if (er[0] <= round_off && er[0] > tolerance) { gsl = ST_GSL_EROUND; break; }
+            if ((er[0] <= tolerance && er[0] != ras[0]) || er[0] == 0.0) { gsl = 0; break; }
+            if (limit == 1) { gsl = ST_GSL_EMAXITER; break; }
+            __syncwarp();
+            if (lane == 0) { alist[0] = lkmin; blist[0] = lkmax; rlist[0] = ar[0]; elist[0] = er[0]; }
+            __syncwarp();
+            size = 1;
+            area = ar[0];
+            errsum = er[0];
+            iteration = 1;
+          } else {
+            const double a1 = qa[0], b1 = qb[0], a2 = qa[1], b2 = qb[1];
+            const double area12 = ar[0] + ar[1];
+            const double error12 = er[0] + er[1];
+            errsum += (error12 - e_i);
+            area += area12 - r_i;
+            if (ras[0] != er[0] && ras[1] != er[1]) {
+              const double delta = r_i - area12;
+              if (fabs(delta) <= 1.0e-5 * fabs(area12) && error12 >= 0.99 * e_i) roundoff_type1++;
+              if (iteration >= 10 && error12 > e_i) roundoff_type2++;
+            }
+            tolerance = fmax(epsabs, epsrel * fabs(area));
+            if (errsum > tolerance) {
+              if (roundoff_type1 >= 6 || roundoff_type2 >= 20) error_type = 2;
+              if (q_subinterval_too_small(a1, a2, b2)) error_type = 3;
+            }
+            // update(): larger-error half stays at imax, the other is appended
+            __syncwarp();
+            if (lane == 0) {
+              if (er[1] > er[0]) {
+                alist[imax] = a2; rlist[imax] = ar[1]; elist[imax] = er[1];
+                alist[size] = a1; blist[size] = b1; rlist[size] = ar[0]; elist[size] = er[0];
+              } else {
+                blist[imax] = b1; rlist[imax] = ar[0]; elist[imax] = er[0];
+                alist[size] = a2; blist[size] = b2; rlist[size] = ar[1]; elist[size] = er[1];
+              }
+            }
+            __syncwarp();
+            size++;
+            iteration++;
+            if (!(iteration < limit && !error_type && errsum > tolerance)) {
               double sum = 0.0;
               for (int i = lane; i < size; i += 32) sum += rlist[i];
               result = qwarp_sum(sum);
@@ -422,44 +437,62 @@ limber_qag_fast_kernel(const LimberProblem P, const FastPlan G, double* ws, doub
               else if (error_type == 3) gsl = ST_GSL_ESING;
               else if (iteration == limit) gsl = ST_GSL_EMAXITER;
               else gsl = ST_GSL_EFAILED;
+              break;
             }
           }
-          if (P.counters && lane == 0) atomicAdd(P.counters, nev);
-          const unsigned long long task = ((unsigned long long)ic * P.npair + ipair) * P.nl + il;
-          // GSL_EROUND switches the reference to CQUAD (src/ccl_cls.c:245-259): handed to limber_cquad_kernel
-          if (gsl == ST_GSL_EROUND && cq_list) {
-            unsigned long long at = cq_cap;
-            if (lane == 0) {
-              at = atomicAdd(&cq_list[0], 1ull);
-              if (at < cq_cap) cq_list[2 + at] = task;
-            }
-            at = __shfl_sync(FULL, at, 0);
-            if (at < cq_cap) continue;
+          // retrieve(): interval with the largest error estimate; its two halves are the next request
+          double emax = -1.0;
+          imax = 0;
+          for (int i = lane; i < size; i += 32) {
+            const double e = elist[i];
+            if (e > emax) { emax = e; imax = i; }
           }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double eo = __shfl_xor_sync(FULL, emax, o);
+            const int io = __shfl_xor_sync(FULL, imax, o);
+            if (eo > emax || (eo == emax && io < imax)) { emax = eo; imax = io; }
+          }
+          const double a_i = alist[imax], b_i = blist[imax];
+          r_i = rlist[imax];
+          e_i = elist[imax];
+          qa[0] = a_i; qb[0] = 0.5 * (a_i + b_i); qa[1] = qb[0]; qb[1] = b_i;
+          npan = 2;
+        }
+        if (redo) break;
+        if (P.counters && lane == 0) atomicAdd(P.counters, nev);
+        const unsigned long long task_id = ((unsigned long long)ic * P.npair + ipair) * P.nl + il;
+        // GSL_EROUND switches the reference to CQUAD (src/ccl_cls.c:245-259): handed to limber_cquad_kernel
+        if (gsl == ST_GSL_EROUND && cq_list) {
+          unsigned long long at = cq_cap;
           if (lane == 0) {
-            const size_t o = (size_t)task;
-            if (gsl == 0) {
-              P.cl[o] = result / lp1h;  // src/ccl_cls.c:340
-            } else {
-              P.cl[o] = nan("");         // src/ccl_cls.c:343-345
-              const size_t sidx = (size_t)ic * P.npair + ipair;
-              P.status[sidx] = ST_ERR_INTEG;
-              atomicCAS(P.status_detail + sidx, 0, gsl);
-            }
+            at = atomicAdd(&cq_list[0], 1ull);
+            if (at < cq_cap) cq_list[2 + at] = task_id;
           }
-          (void)ncoll;
+          at = __shfl_sync(FULL, at, 0);
+          if (at < cq_cap) continue;
         }
-        if (redo) {
-          // every pair of the task goes to the general kernel (pairs already finished are simply recomputed)
-          if (lane < np) {
-            const unsigned long long task =
-                ((unsigned long long)ic * P.npair + gpairs[gd.pair_begin + lane].out) * P.nl + il;
-            const unsigned long long at = atomicAdd(G.redo, 1ull);
-            if (at < G.redo_cap) G.redo[1 + at] = task;
+        if (lane == 0) {
+          if (gsl == 0) {
+            P.cl[task_id] = result / lp1h;  // src/ccl_cls.c:340
+          } else {
+            P.cl[task_id] = nan("");         // src/ccl_cls.c:343-345
+            const size_t sidx = (size_t)ic * P.npair + ipair;
+            P.status[sidx] = ST_ERR_INTEG;
+            atomicCAS(P.status_detail + sidx, 0, gsl);
           }
         }
-        if (P.counters && lane == 0 && ncached) atomicAdd(P.counters + 1, (unsigned long long)ncached * PN);
       }
+      if (redo) {
+        // every pair of the task goes to the general kernel (pairs already finished are simply recomputed)
+        if (lane < np) {
+          const unsigned long long task_id =
+              ((unsigned long long)ic * P.npair + gpairs[gd.pair_begin + lane].out) * P.nl + il;
+          const unsigned long long at = atomicAdd(G.redo, 1ull);
+          if (at < G.redo_cap) G.redo[1 + at] = task_id;
+        }
+      }
+      if (P.counters && lane == 0 && nodes_done) atomicAdd(P.counters + 1, nodes_done);
     }
   }
 }

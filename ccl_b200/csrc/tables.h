@@ -158,6 +158,7 @@ struct FastPlan {
   int gstride, cstride, sstride;
   int ntr_max;  // largest sub-tracer count of any cosmology of the launch (sizes shared memory)
   int has_rsd;  // some sub-tracer has der_bessel 1 or 2: launch the kernel variant that handles them
+  int regroup;  // 0: the grid tasks in this plan are still valid (same tables, collections and pairs): skip the grouping pass
   unsigned long long* redo;  // [0] = count, [1..redo_cap] = task ids left to the general kernel
   unsigned long long redo_cap;
 };

@@ -91,7 +91,8 @@ def build_tracer_kernels(cosmologies, background, z, nz_list, mag_bias_list=None
     z = np.ascontiguousarray(z, dtype=float)
     nzs = np.ascontiguousarray(np.stack([np.asarray(n, dtype=float) for n in nz_list]))
     szs = None if mag_bias_list is None else np.ascontiguousarray(np.stack([np.asarray(s_, dtype=float) for s_ in mag_bias_list]))
-    inv_norm = np.array([1.0 / float(Akima(z, n).integrate_nodes()) for n in nzs])   # get_nz_norm, spline mode
+    with np.errstate(divide='ignore'):   # an identically zero n(z): 1/0 = inf like the C arithmetic
+        inv_norm = np.array([1.0 / np.float64(Akima(z, n).integrate_nodes()) for n in nzs])   # get_nz_norm, spline mode
     nc, ntr = par.shape[0], nzs.shape[0]
     a_bg = np.ascontiguousarray(background["a"])
     out = dict(chi_z=np.empty((nc, z.size)), w_nc=np.empty((nc, ntr, z.size)), chi_l=np.empty((nc, n_chi)),
@@ -190,7 +191,8 @@ class DeviceTables:
             nzs = np.ascontiguousarray(np.stack([np.asarray(n, dtype=float) for n in nz_list]))
             if mag_bias_list is not None:
                 szs = np.ascontiguousarray(np.stack([np.asarray(s_, dtype=float) for s_ in mag_bias_list]))
-            inorm = np.array([1.0 / float(Akima(zz, n).integrate_nodes()) for n in nzs])
+            with np.errstate(divide='ignore'):
+                inorm = np.array([1.0 / np.float64(Akima(zz, n).integrate_nodes()) for n in nzs])
             if lens_scale is not None:
                 lsc = np.ascontiguousarray(lens_scale, dtype=float)
         self.ncosmo, self.ntr, self.z = par.shape[0], ntr, zz

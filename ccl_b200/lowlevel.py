@@ -345,6 +345,32 @@ class LibBatch:
             _check(st.value, "batch_angular_cls_limber")
         return cl, stat, st.value
 
+    def angular_cl_start(self, collections, pairs, ells, method=_lib.INTEGRATION_SPLINE, out=None):
+        """First half of angular_cl: queue the kernels and the copy of every C_ell into `out` (a C-contiguous
+        float64 array, page-locked for a truly asynchronous copy) on the batch's stream and return at once."""
+        keep, g = self._geometry(collections, pairs, ells)
+        shape = (self.ncosmo, len(pairs), len(keep[4]))
+        if out is None:
+            out = np.empty(shape)
+        assert out.shape == shape and out.dtype == np.float64 and out.flags.c_contiguous
+        st = C.c_int(0)
+        _lib.load().ccl_b200_batch_angular_cls_limber_start(self.h, *g, int(method), out.ctypes.data_as(_lib._dp),
+                                                            C.byref(st))
+        _check(st.value, "batch_angular_cls_limber_start")
+        self._started = (out, keep, len(pairs))
+        return out
+
+    def angular_cl_wait(self):
+        """Second half: block until the started call has finished; returns (cl, status[ncosmo, npair], status)."""
+        out, _, npair = self._started
+        self._started = None
+        stat = np.zeros((self.ncosmo, npair), dtype=np.int32)
+        st = C.c_int(0)
+        _lib.load().ccl_b200_batch_angular_cls_limber_wait(self.h, stat.ctypes.data_as(_lib._ip), C.byref(st))
+        if st.value not in (0, 1030):
+            _check(st.value, "batch_angular_cls_limber_wait")
+        return out, stat, st.value
+
     def angular_cl_dev(self, collections, pairs, ells, d_cl, d_status, method=_lib.INTEGRATION_SPLINE, stream=0):
         """Device-buffer entry: d_cl / d_status are raw device pointers (ints), e.g. tensor.data_ptr()."""
         keep, g = self._geometry(collections, pairs, ells)

@@ -86,28 +86,42 @@ def pin_stacked(stk):
 def chunk_sizes(ncosmo, nchunks=None):
     """Cosmologies per chunk of the pipelined entry.
 
-    Regular chunks hold >= 256 cosmologies (fewer Limber CTAs than ~60 waves cost tail time and every chunk
-    costs ~1 ms of launches and synchronisation), at most 8 of them unless `nchunks` says otherwise; the sizes
-    ramp up x1.5 from a quarter of the regular size (not below 64) so that the first chunk reaches the SMs
-    after a fraction of the regular plan + upload time."""
+    Regular chunks hold >= 64 cosmologies, at most 16 of them unless `nchunks` says otherwise (a chunk only
+    reaches the SMs after its own planning + upload + preparation, 6 ms for 200 cosmologies on a busy GPU, so
+    chunks must stay small against the whole batch); the sizes
+    ramp up x1.5 from an eighth of the regular size (not below 32), and down again at the end (chunks are queued
+    asynchronously, so small chunks leave no gaps behind them)."""
     ncosmo = int(ncosmo)
     if ncosmo <= 0:
         return []
     if nchunks is None:
-        nchunks = max(1, min(8, ncosmo // 256))
+        nchunks = max(1, min(16, ncosmo // 64))
     nchunks = max(1, min(int(nchunks), ncosmo))
     base = -(-ncosmo // nchunks)
-    sizes, size, rem = [], max(1, base // 4, min(64, base)), ncosmo
-    while rem > 0:
-        take = min(size, base, rem)
-        sizes.append(take)
-        rem -= take
+    # ramp up x1.5 from `first` to the regular size, plateau, then the same ramp down: a chunk's planning + upload +
+    # preparation latency is only exposed for the first chunk (nothing to overlap it with yet) and for the last
+    # ones (the SMs drain while they are still being committed), so both ends are small
+    first = max(1, base // 8, min(32, base))
+    up, size = [], first
+    while size < base and 2 * (sum(up) + size) <= ncosmo:
+        up.append(size)
         size = -(-size * 3 // 2)
-    return sizes
+    rem = ncosmo - 2 * sum(up)
+    mid = []
+    while rem > 0:
+        take = min(base, rem)
+        mid.append(take)
+        rem -= take
+    if len(mid) > 1 and mid[-1] < first:      # fold a tiny remainder into its neighbour
+        mid[-2] += mid.pop()
+    return up + mid + up[::-1]
 
 
 class PipelinedBatch:
     NSTAGE = 2   # host threads planning/staging chunks concurrently
+    NCOMMIT = 2  # host threads uploading + preparing chunks concurrently: a chunk's ~10 small preparation kernels
+                 # each wait for SM slots while an earlier chunk's Limber grid is running, so one serial commit
+                 # thread is latency-bound (3.9 ms per 64 cosmologies against 1.3 ms on an idle GPU)
 
     def __init__(self, ncosmo, nchunks=None, params=None):
         self.ncosmo = int(ncosmo)
@@ -163,9 +177,9 @@ class PipelinedBatch:
                 for ev in staged:
                     ev.set()
 
-        def commit():
+        def commit(first):
             try:
-                for c in range(nchunks):
+                for c in range(first, nchunks, self.NCOMMIT):
                     staged[c].wait()
                     if failed.is_set():
                         break
@@ -178,17 +192,29 @@ class PipelinedBatch:
                 ready.put(None)
 
         threads = [threading.Thread(target=stage, args=(k,), daemon=True) for k in range(self.NSTAGE)]
-        threads.append(threading.Thread(target=commit, daemon=True))
+        threads += [threading.Thread(target=commit, args=(k,), daemon=True) for k in range(self.NCOMMIT)]
         for t in threads:
             t.start()
-        worst = 0
-        while True:
+        # the Limber kernels and the D2H copy of every chunk are QUEUED as soon as its tables are ready (each chunk
+        # on its own stream) and collected afterwards: the SMs never wait for the host between chunks, and the tail
+        # of one chunk's grid overlaps the head of the next
+        started, done = [], 0
+        while done < self.NCOMMIT:
             c = ready.get()
             if c is None:
-                break
+                done += 1
+                continue
             off, cnt = self.spans[c]
-            _, s_c, st = timed("compute", c, self.batches[c].angular_cl, collections, pairs, ells, method,
-                               out=out[off:off + cnt])
+            try:
+                timed("start", c, self.batches[c].angular_cl_start, collections, pairs, ells, method, out=out[off:off + cnt])
+                started.append(c)
+            except BaseException as e:  # noqa: BLE001
+                errors.append(e)
+                failed.set()
+        worst = 0
+        for c in started:
+            off, cnt = self.spans[c]
+            _, s_c, st = timed("wait", c, self.batches[c].angular_cl_wait)
             stat[off:off + cnt] = s_c
             worst = worst or st
         for t in threads:

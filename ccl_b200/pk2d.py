@@ -61,13 +61,14 @@ class Pk2D:
 
     def apply_halofit(self, cosmo):
         """pyccl/pk2d.py:203-242 (ccl_apply_halofit, src/ccl_power.c:171-232)."""
-        from .power import halofit_table
-        if cosmo['wa'] != 0 or cosmo['w0'] != -1:
-            # the reference maps (w0, wa) to an effective constant w (src/ccl_halofit.c:42-170); the
-            # host builder uses w0 directly, exact for wa = 0
-            pass
         logplin = self._tab if self.is_logp else np.log(self._tab)
-        logpnl, _ = halofit_table(cosmo._params, self._a, self._lk, logplin)
+        if getattr(cosmo, "_table_builder", "host") == "device":
+            # ccl_b200_build_halofit (csrc/builders.cu::halofit_kernel); weffa = w0 like src/ccl_halofit.c:847
+            from . import device_builders as db
+            logpnl = db.build_halofit([cosmo], dict(lk=self._lk, a=self._a, logp=np.ascontiguousarray(logplin)[None]))["logp"][0]
+        else:
+            from .power import halofit_table
+            logpnl, _ = halofit_table(cosmo._params, self._a, self._lk, logplin)
         return Pk2D(a_arr=self._a, lk_arr=self._lk, pk_arr=logpnl, is_logp=True, extrap_order_lok=1,
                     extrap_order_hik=2)
 

@@ -69,11 +69,26 @@ def _nz_norm_value(cosmo, z, n):
     return float(np.sum(0.5 * (hi - lo)[:, None] * _GLW * f(zq)))
 
 
+def _device_kernels(cosmo):
+    """Tracer kernels on the device builders: the product path of a Cosmology built with them (spline-mode
+    n(z) normalisation, the reference's default)."""
+    return getattr(cosmo, "_table_builder", "host") == "device" and bool(cosmo._gsl_params["NZ_NORM_SPLINE_INTEGRATION"])
+
+
+def _device_tracer_kernels(cosmo, z_n, n, s, n_chi):
+    from . import device_builders as db
+    cosmo.compute_distances()
+    return db.build_tracer_kernels([cosmo], cosmo._bgd, z_n, [n], None if s is None else [s], n_chi)
+
+
 def get_density_kernel(cosmo, *, dndz):
     """chi, W(chi) = p(z) H(z) (pyccl/tracers.py:84-111; ccl_get_number_counts_kernel,
     src/ccl_tracers.c:121-160)."""
     z_n, n = _check_array_params(dndz, 'dndz')
     _check_background_spline_compatibility(cosmo, z_n)
+    if _device_kernels(cosmo):
+        out = _device_tracer_kernels(cosmo, z_n, n, None, 8)
+        return out["chi_z"][0], out["w_nc"][0, 0]
     chi = cosmo.comoving_radial_distance(1. / (1. + z_n))
     a = 1. / (1 + z_n)
     hz = cosmo["h"] * cosmo.h_over_h0(a) / physical_constants.CLIGHT_HMPC
@@ -99,6 +114,10 @@ def get_lensing_kernel(cosmo, *, dndz, mag_bias=None, n_chi=None):
                       "lensing kernel (%d). Consider disabling spline integration for the lensing kernel by "
                       "setting gsl_params.LENSING_KERNEL_SPLINE_INTEGRATION = False before instantiating the "
                       "Cosmology passed." % (len(z_n), n_chi), category=CCLWarning, importance='low')
+    if _device_kernels(cosmo) and spline_mode and (s is None or np.array_equal(z_s, z_n)):
+        # integrate_lensing_kernel_spline on the device (csrc/builders.cu::tracer_kernel_builder)
+        out = _device_tracer_kernels(cosmo, z_n, n, s, n_chi)
+        return out["chi_l"][0], out["w_l"][0, 0]
     # ccl_get_chis_lensing_kernel (src/ccl_tracers.c:470-479)
     z_k = (z_n[-1] / n_chi) * np.arange(n_chi) + 1E-15
     chi_k = cosmo.comoving_radial_distance(1. / (1 + z_k))

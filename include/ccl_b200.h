@@ -207,6 +207,15 @@ void ccl_b200_batch_angular_cls_limber(ccl_b200_batch *b, int ncoll, const int *
                                        const int *coll_count, int npair, const int *pair1,
                                        const int *pair2, int nl, const double *ell, int integration_method,
                                        double *cl_out, int *status_out, int *status);
+/* The same call in two halves, so that a host thread can queue the next chunk of a pipelined batch while this
+ * one is still running: _start enqueues the Limber kernels and the device-to-host copy of every C_ell into
+ * cl_out (which should be page-locked and must stay valid) on the batch's own stream and returns; _wait blocks
+ * until they have finished and delivers the per-(cosmology, pair) status words like the synchronous entry. */
+void ccl_b200_batch_angular_cls_limber_start(ccl_b200_batch *b, int ncoll, const int *coll_start,
+                                             const int *coll_count, int npair, const int *pair1,
+                                             const int *pair2, int nl, const double *ell, int integration_method,
+                                             double *cl_out, int *status);
+void ccl_b200_batch_angular_cls_limber_wait(ccl_b200_batch *b, int *status_out, int *status);
 /* Same, asynchronous on `stream` (a cudaStream_t, may be NULL) with DEVICE output buffers;
  * d_status_out holds 2*ncosmo*npair ints (status, then first underlying code). */
 void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch *b, int ncoll, const int *coll_start,

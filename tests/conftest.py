@@ -10,6 +10,17 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # Cosmology objects build their tables with the device builders (the product path).  A test session on a
+    # machine without a GPU prepares oracle inputs with the numpy twins instead -- explicitly, here: the product
+    # default stays "device" and fails loudly without a CUDA device.
+    import ccl_b200
+    from ccl_b200 import _lib
+    try:
+        ngpu = _lib.load().ccl_b200_device_count()
+    except Exception:
+        ngpu = 0
+    if ngpu < 1:
+        ccl_b200.set_table_builder("host")
 
 
 @pytest.fixture(scope="session")

@@ -7,7 +7,17 @@ pytestmark = pytest.mark.gpu
 
 
 def _cosmologies():
+    """Cosmologies whose own tables come from the numpy twins: the host side of every comparison below."""
     import ccl_b200 as ccl
+    prev = ccl.get_table_builder()
+    ccl.set_table_builder("host")
+    try:
+        return _make_cosmologies(ccl)
+    finally:
+        ccl.set_table_builder(prev)
+
+
+def _make_cosmologies(ccl):
     rng = np.random.default_rng(11)
     out = [ccl.Cosmology(Omega_c=0.27, Omega_b=0.045, h=0.67, sigma8=0.8, n_s=0.96, transfer_function='bbks')]
     for _ in range(5):
@@ -244,3 +254,44 @@ def test_device_resident_pipeline_equals_round_trip():
     b3, _, tabs3 = db.build_3x2pt_batch(cos, z, lens, src, bias, batch=b2)
     c3, _, _ = b3.angular_cl(colls, pairs, ells)
     assert np.array_equal(c1, c3)
+
+
+def test_api_objects_on_device_builders_match_host_twins():
+    """Cosmology / tracer objects built by the device builders (the product default) against the same objects
+    built by the numpy twins: tables to the builders' parity tolerances, README-example C_ell to 1e-6."""
+    import time
+    import ccl_b200 as ccl
+    assert ccl.get_table_builder() == "device"
+    kw = dict(Omega_c=0.27, Omega_b=0.045, h=0.67, sigma8=0.8, n_s=0.96, transfer_function='bbks')
+    z = np.linspace(0., 1., 500)
+    n = np.ones_like(z)
+    ell = np.arange(2, 2001).astype(float)
+
+    def run():
+        c = ccl.Cosmology(**kw)
+        t1 = ccl.WeakLensingTracer(c, dndz=(z, n))
+        t2 = ccl.WeakLensingTracer(c, dndz=(z, n), ia_bias=(z, n))
+        g = ccl.NumberCountsTracer(c, has_rsd=True, dndz=(z, n), bias=(z, np.sqrt(1 + z)), mag_bias=(z, 0.4 * n))
+        return c, [ccl.angular_cl(c, a, b, ell, limber_integration_method='spline') for a, b in ((t1, t1), (t1, t2), (g, g), (g, t2))]
+
+    run()                                   # CUDA context, library load
+    t0 = time.perf_counter()
+    c_dev, cl_dev = run()
+    dt_dev = time.perf_counter() - t0
+    assert c_dev._table_builder == "device" and c_dev._bgd is not None
+    ccl.set_table_builder("host")
+    try:
+        t0 = time.perf_counter()
+        c_host, cl_host = run()
+        dt_host = time.perf_counter() - t0
+    finally:
+        ccl.set_table_builder("device")
+    assert c_host._table_builder == "host" and c_host._bgd is None
+    print("setup + 4 angular_cl calls: device builders %.1f ms, numpy twins %.1f ms" % (dt_dev * 1e3, dt_host * 1e3))
+    for k in ("chi", "E", "growth", "fgrowth"):
+        assert np.max(np.abs(getattr(c_dev._bg, k) / np.where(getattr(c_host._bg, k) == 0, 1, getattr(c_host._bg, k)) - 1)[:-1]) < 1e-7, k
+    pd, ph = c_dev.get_nonlin_power(), c_host.get_nonlin_power()
+    assert np.max(np.abs(pd._tab - ph._tab)) < 1e-6
+    for a, b in zip(cl_dev, cl_host):
+        assert np.max(np.abs(a - b) / np.max(np.abs(b))) < 1e-6
+    assert dt_dev < dt_host

@@ -1,8 +1,8 @@
 # 'qag_quad' resident pass at 64 cosmologies: grid-sharing kernel vs the general kernel (CCL_B200_NO_QAG_FAST=1)
 for mode in fast general; do
-  if [ $mode = general ]; then export CCL_B200_NO_QAG_FAST=1; else unset CCL_B200_NO_QAG_FAST; fi
+  if [ $mode = fast ]; then export CCL_B200_QAG_FAST=1; else unset CCL_B200_QAG_FAST; fi
   echo "== qag $mode"
-  python bench.py --method qag_quad --ncosmo ${NCOSMO:-64} --steps 2 --warmup 2 --no-e2e --from-parameters 0 --qag-sample 0 2>&1 | python -c "
+  python bench.py --method qag_quad --ncosmo ${NCOSMO:-64} --steps 2 --warmup 2 --no-e2e --from-parameters 0 --qag-sample 0 --no-y10 2>&1 | python -c "
 import sys,json
 for ln in sys.stdin:
     if ln.startswith('{'):

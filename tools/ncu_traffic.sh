@@ -4,7 +4,7 @@
 NC=${1:-4096}
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum --clock-control none \
     -k regex:limber_spline_fast_kernel -c 1 --csv --log-file gpurun_out/traffic.csv \
-    python bench.py --ncosmo $NC --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --from-parameters 0 --qag-sample 0 > gpurun_out/traffic.log 2>&1
+    python bench.py --ncosmo $NC --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --from-parameters 0 --qag-sample 0 --no-y10 > gpurun_out/traffic.log 2>&1
 python - <<PY
 import csv, json
 rows = [r for r in csv.reader(open("gpurun_out/traffic.csv")) if len(r) > 5]
