@@ -4,10 +4,12 @@ Hot path: ``ccl_angular_cls_limber`` (reference src/ccl_cls.c:265-363) as hand-w
 CUDA kernels in ``libccl_b200.so``, reached through the C ABI of ``include/ccl_b200.h``.
 """
 from . import _lib  # noqa: F401
-from .lowlevel import (CCLB200Error, LibBatch, LibCosmology, LibF2D, LibTracer,  # noqa: F401
+from .lowlevel import (CCLB200Error, LibBatch, LibCosmology, LibF2D, LibF3D, LibTracer,  # noqa: F401
                        angular_cls_limber, make_params)
 
 from .cells import angular_cl  # noqa: F401,E402
+from .covariances import angular_cl_cov_cNG, angular_cl_cov_SSC  # noqa: F401,E402
+from .tk3d import Tk3D  # noqa: F401,E402
 from .cosmology import (Cosmology, CosmologyCalculator, CosmologyVanillaLCDM, get_table_builder,  # noqa: F401,E402
                         set_table_builder)
 from .errors import CCLError, CCLWarning, update_warning_verbosity  # noqa: F401,E402

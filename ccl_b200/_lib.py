@@ -30,7 +30,8 @@ class Params(C.Structure):
     """ccl_b200_params: the spline/gsl parameters the path reads (include/ccl_core.h:94-178)."""
     _fields_ = [("K_MAX", C.c_double), ("K_MIN", C.c_double), ("DLOGK_INTEGRATION", C.c_double),
                 ("INTEGRATION_LIMBER_EPSREL", C.c_double), ("N_ITERATION", C.c_int),
-                ("INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS", C.c_int), ("A_SPLINE_MIN", C.c_double)]
+                ("INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS", C.c_int), ("A_SPLINE_MIN", C.c_double),
+                ("DCHI_INTEGRATION", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/ccl_b200.h
@@ -90,6 +91,11 @@ SIGNATURES = {
     "ccl_b200_batch_arena_bytes": (C.c_ulonglong, [_vp]),
     "ccl_b200_batch_angular_cls_limber": (None, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp,
                                                  C.c_int, _dp, _ip, _ip]),
+    "ccl_b200_f3d_new": (_vp, [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_double, C.c_int, _ip]),
+    "ccl_b200_f3d_free": (None, [_vp]),
+    "ccl_b200_angular_cl_covariance": (None, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int,
+                                              C.c_int, C.c_int, _dp, _dp, C.c_double, _ip]),
     "ccl_b200_batch_angular_cls_limber_start": (None, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp,
                                                         C.c_int, _dp, _ip]),
     "ccl_b200_batch_angular_cls_limber_wait": (None, [_vp, _ip, _ip]),

@@ -316,7 +316,8 @@ class Cosmology:
                                     INTEGRATION_LIMBER_EPSREL=gp["INTEGRATION_LIMBER_EPSREL"],
                                     N_ITERATION=gp["N_ITERATION"], A_SPLINE_MIN=sp["A_SPLINE_MIN"],
                                     INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS=gp[
-                                        "INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS"])
+                                        "INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS"],
+                                    DCHI_INTEGRATION=sp["DCHI_INTEGRATION"])
 
     def chi_max_nokernel(self):
         """chi(A_SPLINE_MIN): chi_max of kernel-less tracers (src/ccl_tracers.c:632)."""

@@ -794,6 +794,10 @@ struct ccl_b200_cosmology {
   bool dirty = true;
 };
 struct ccl_b200_f2d { TableSet ts; };
+struct ccl_b200_f3d {  // ccl_f3d_t: the planes are the P tables of a TableSet with one "cosmology" per plane
+  TableSet ts;
+  F3D desc;
+};
 struct ccl_b200_tracer { TableSet ts; double chi_min, chi_max; int der_bessel, der_angles; };
 struct ccl_b200_collection { std::vector<ccl_b200_tracer*> ts; };
 struct ccl_b200_batch {
@@ -982,6 +986,7 @@ void ccl_b200_default_params(ccl_b200_params* p) {
   p->K_MAX = 1e3; p->K_MIN = 5e-5; p->DLOGK_INTEGRATION = 0.025;
   p->INTEGRATION_LIMBER_EPSREL = 1e-4; p->N_ITERATION = 1000; p->A_SPLINE_MIN = 0.1;
   p->INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS = 4;  // GSL_INTEG_GAUSS41 (src/ccl_core.c:40)
+  p->DCHI_INTEGRATION = 5.0;
 }
 
 // gsl_integration_qag takes the rule key from the parameters (src/ccl_cls.c:240); the device has GK41 only
@@ -1101,6 +1106,171 @@ void ccl_b200_f2d_eval_multi(ccl_b200_f2d* f2d, const double* lk, int nk, double
   });
   if (*status == CCL_B200_ERROR_GROWTH_INIT)
     set_err("ccl_f2d.c: ccl_f2d_t_eval(): growth factor splines have not been precomputed!");
+}
+
+// ---- ccl_f3d_t and the Limber covariance (src/ccl_f3d.c, src/ccl_cls.c:377-612) ----
+ccl_b200_f3d* ccl_b200_f3d_new(int na, const double* a_arr, int nk, const double* lk_arr, const double* tkka_arr,
+                               const double* fka1_arr, const double* fka2_arr, int is_product,
+                               int extrap_order_lok, int extrap_order_hik, int extrap_linear_growth,
+                               int is_tkka_log, double growth_factor_0, int growth_exponent, int* status) {
+  if (*status) return nullptr;
+  if (!use_device(status)) return nullptr;
+  is_product = is_product || (tkka_arr == nullptr);
+  if ((extrap_order_lok > 1) || (extrap_order_lok < 0) || (extrap_order_hik > 1) || (extrap_order_hik < 0) ||
+      ((extrap_linear_growth != GROWTH_CCL) && (extrap_linear_growth != GROWTH_CONST) &&
+       (extrap_linear_growth != GROWTH_NONE)) ||
+      (is_product ? (fka1_arr == nullptr || fka2_arr == nullptr) : (tkka_arr == nullptr)) || na < 1 || nk < 4 ||
+      !a_arr || !lk_arr) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_b200: ccl_f3d_t_new(): inconsistent arguments");
+    return nullptr;
+  }
+  auto* f = new ccl_b200_f3d();
+  f->ts.device = current_device();
+  const int nplanes = is_product ? 2 : na;
+  f->ts.cosmos.resize(nplanes);
+  const size_t a_off = f->ts.raw.put(a_arr, na);
+  bool ok = a_off != (size_t)-1;
+  for (int i = 0; i < nplanes && ok; ++i) {
+    CosmoPlan& c = f->ts.cosmos[i];
+    c.has_psp = true;
+    if (is_product)  // two ccl_f2d_t with half the growth exponent (src/ccl_f3d.c:226-241)
+      ok = f->ts.plan_f2d(c.psp, na, a_arr, nk, lk_arr, i == 0 ? fka1_arr : fka2_arr, nullptr, nullptr, 0,
+                          extrap_order_lok, extrap_order_hik, extrap_linear_growth, is_tkka_log, growth_factor_0,
+                          growth_exponent / 2, status);
+    else  // gsl_spline2d_init(tkka[ia], lk_arr, lk_arr, tkk, nk, nk): a bicubic table on (ln k1, ln k2)
+      ok = f->ts.plan_f2d(c.psp, nk, lk_arr, nk, lk_arr, tkka_arr + (size_t)i * nk * nk, nullptr, nullptr, 0, 0, 0,
+                          GROWTH_CONST, 0, 1.0, 0, status);
+  }
+  if (!ok || !f->ts.commit(0, status)) {
+    if (!*status) *status = CCL_B200_ERROR_MEMORY;
+    delete f;
+    return nullptr;
+  }
+  F3D& d = f->desc;
+  memset(&d, 0, sizeof(d));
+  d.na = na; d.is_product = is_product;
+  d.extrap_order_lok = extrap_order_lok; d.extrap_order_hik = extrap_order_hik;
+  d.extrap_linear_growth = extrap_linear_growth; d.is_log = is_tkka_log; d.growth_exponent = growth_exponent;
+  d.growth_factor_0 = growth_factor_0; d.lkmin = lk_arr[0]; d.lkmax = lk_arr[nk - 1];
+  d.a_arr = reinterpret_cast<const double*>(f->ts.dev.p) + a_off;
+  d.planes = f->ts.d_psp;
+  return f;
+}
+
+void ccl_b200_f3d_free(ccl_b200_f3d* f3d) {
+  if (!f3d) return;
+  cudaSetDevice(f3d->ts.device);
+  delete f3d;
+}
+
+void ccl_b200_angular_cl_covariance(ccl_b200_cosmology* cosmo, ccl_b200_collection* trc1, ccl_b200_collection* trc2,
+                                    ccl_b200_collection* trc3, ccl_b200_collection* trc4, ccl_b200_f3d* tsp,
+                                    int nl1_out, const double* l1_out, int nl2_out, const double* l2_out,
+                                    double* cov_out, int integration_method, int chi_exponent, int n_ker,
+                                    const double* a_ker, const double* f_ker, double prefactor_extra, int* status) {
+  if (!cosmo || !trc1 || !trc2 || !trc3 || !trc4 || !tsp) { *status = CCL_B200_ERROR_INCONSISTENT; return; }
+  std::lock_guard<std::mutex> lk(cosmo->mu);
+  if (!cosmo->ts.committed || !cosmo->ts.cosmos[0].achi.present) {
+    *status = CCL_B200_ERROR_DISTANCES_INIT;
+    set_err("ccl_cls.c: ccl_angular_cl_limber(): distance splines have not been precomputed!");
+    return;
+  }
+  if (*status) return;
+  const size_t nout = (size_t)nl1_out * nl2_out;
+  auto fail_all = [&](int code, const char* msg) {
+    for (size_t i = 0; i < nout; ++i) cov_out[i] = NAN;
+    *status = code;
+    set_err("%s", msg);
+  };
+  if (integration_method != INTEG_QAG && integration_method != INTEG_SPLINE)
+    return fail_all(CCL_B200_ERROR_INTEG, "ccl_cls.c: ccl_angular_cov_limber(); integration error\n");
+  if (integration_method == INTEG_QAG && !qag_rule_ok(cosmo->params, status)) {
+    for (size_t i = 0; i < nout; ++i) cov_out[i] = NAN;
+    return;
+  }
+  const int device = cosmo->ts.device;
+  if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice", status)) return;
+  // kernel_extra: a ccl_f1d_t of (a, f) with constant extrapolation (pyccl/ccl_covs.i:95-118), built like any Akima table
+  TableSet ker;
+  ker.device = device;
+  if (n_ker > 0) {
+    if (n_ker < 5 || !a_ker || !f_ker) {
+      *status = CCL_B200_ERROR_SPLINE;
+      set_err("ccl_b200: kernel_extra needs >= 5 nodes (akima)");
+      return;
+    }
+    ker.cosmos.resize(1);
+    if (!ker.plan_s1(ker.cosmos[0].achi, 0, n_ker, a_ker, f_ker, status) || !ker.commit(0, status)) return;
+  }
+  DeviceScratch& sc = scratch_for(device);
+  std::lock_guard<std::mutex> lk2(sc.mu);
+  // update_chi_limits (src/ccl_cls.c:34-62): union over trc1, then intersections
+  ccl_b200_collection* cols[4] = {trc1, trc2, trc3, trc4};
+  double chimin = 1E15, chimax = -1E15;
+  std::vector<Tracer> trs;
+  int2 coll[4];
+  for (int c = 0; c < 4; ++c) {
+    double lo = 1E15, hi = -1E15;
+    coll[c] = make_int2((int)trs.size(), (int)cols[c]->ts.size());
+    for (auto* t : cols[c]->ts) {
+      lo = std::min(lo, t->chi_min);
+      hi = std::max(hi, t->chi_max);
+      trs.push_back(t->ts.h_tracers[0]);
+    }
+    if (c == 0) { chimin = std::min(chimin, lo); chimax = std::max(chimax, hi); }
+    else { chimin = std::max(chimin, lo); chimax = std::min(chimax, hi); }
+  }
+  const double dchi = cosmo->params.DCHI_INTEGRATION;
+  const int nchi = (int)(fmax((chimax - chimin) / dchi + 0.5, 1)) + 1;
+  const int nit = cosmo->params.N_ITERATION;
+  // call buffer: Tracer[] | Cosmo | F3D | l1 | l2 | cov | status[2] | scratch
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t o_tr = 0;
+  const size_t o_cs = o_tr + up(trs.size() * sizeof(Tracer));
+  const size_t o_f3 = o_cs + up(sizeof(Cosmo));
+  const size_t o_l1 = o_f3 + up(sizeof(F3D));
+  const size_t o_l2 = o_l1 + up((size_t)nl1_out * 8);
+  const size_t o_cv = o_l2 + up((size_t)nl2_out * 8);
+  const size_t o_st = o_cv + up(nout * 8);
+  const size_t o_sc = o_st + 256;
+  const size_t total = o_sc + covariance_scratch_bytes(nchi, nit);
+  if (!sc.call.reserve(total, status)) return;
+  char* base = sc.call.p;
+  Cosmo cd = cosmo->ts.h_cosmos[0];
+  cd.psp = nullptr;
+  cd.tracers = reinterpret_cast<const Tracer*>(base + o_tr);
+  cd.ntracers = (int)trs.size();
+  cudaMemcpyAsync(base + o_tr, trs.data(), trs.size() * sizeof(Tracer), cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_cs, &cd, sizeof(Cosmo), cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_f3, &tsp->desc, sizeof(F3D), cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_l1, l1_out, (size_t)nl1_out * 8, cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_l2, l2_out, (size_t)nl2_out * 8, cudaMemcpyHostToDevice, 0);
+  cudaMemsetAsync(base + o_st, 0, 256, 0);
+  CovProblem P;
+  memset(&P, 0, sizeof(P));
+  P.cosmo = reinterpret_cast<const Cosmo*>(base + o_cs);
+  P.tracers = reinterpret_cast<const Tracer*>(base + o_tr);
+  for (int c = 0; c < 4; ++c) P.coll[c] = coll[c];
+  P.tsp = reinterpret_cast<const F3D*>(base + o_f3);
+  P.l1 = reinterpret_cast<const double*>(base + o_l1);
+  P.l2 = reinterpret_cast<const double*>(base + o_l2);
+  P.nl1 = nl1_out; P.nl2 = nl2_out; P.chipow = chi_exponent;
+  P.has_ker = n_ker > 0;
+  if (n_ker > 0) { P.ker = ker.h_cosmos[0].achi; P.ker_y0 = f_ker[0]; P.ker_yf = f_ker[n_ker - 1]; }
+  P.chimin = chimin; P.chimax = chimax; P.prefactor = prefactor_extra;
+  P.cov = reinterpret_cast<double*>(base + o_cv);
+  P.status = reinterpret_cast<int*>(base + o_st);
+  if (!cuda_ok(launch_covariance(P, integration_method, nchi, nit, cosmo->params.INTEGRATION_LIMBER_EPSREL,
+                                 reinterpret_cast<double*>(base + o_sc), 0), "covariance launch", status))
+    return;
+  int st[2] = {0, 0};
+  if (!cuda_ok(cudaMemcpy(cov_out, P.cov, nout * 8, cudaMemcpyDeviceToHost), "covariance kernel", status)) return;
+  cudaMemcpy(st, P.status, sizeof(st), cudaMemcpyDeviceToHost);
+  if (st[0]) {
+    *status = CCL_B200_ERROR_INTEG;
+    set_err("ccl_cls.c: ccl_angular_cov_limber(); integration error\n");
+  }
 }
 
 // ---- tracers ----
@@ -1550,10 +1720,9 @@ void ccl_b200_batch_angular_cls_limber_dev(ccl_b200_batch* b, int ncoll, const i
   const size_t o_el = o_pr + ((size_t)npair * 8 + 255) / 256 * 256;
   const size_t o_ct = o_el + ((size_t)nl * 8 + 255) / 256 * 256;
   const size_t o_fp = o_ct + 256;
-  // 'qag_quad': the grid-sharing panel-cache kernel (limber_qag_fast.cu) is opt-in (CCL_B200_QAG_FAST=1): on the
-  // LSST-Y1 3x2pt batch 41 % of the requested panels are cache hits, which does not yet pay for evaluating every
-  // collection of a task on a miss (2.6e7 vs 2.8e7 C_ell/s)
-  static const bool qag_fast = getenv("CCL_B200_QAG_FAST") != nullptr;
+  // 'qag_quad': the grid-sharing panel-cache kernel (limber_qag_fast.cu); CCL_B200_NO_QAG_FAST=1 keeps every
+  // C_ell on the general one-warp-per-C_ell kernel (A/B runs)
+  static const bool qag_fast = getenv("CCL_B200_NO_QAG_FAST") == nullptr;
   const bool fast = fast_eligible(b, ncoll, npair) && (integration_method == INTEG_SPLINE || qag_fast);
   const unsigned long long redo_cap = 1ull << 20;
   const size_t total = o_fp;

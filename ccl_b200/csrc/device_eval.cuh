@@ -114,7 +114,7 @@ __device__ __forceinline__ double growth_factor(const Cosmo& cs, double a, int& 
   return D;
 }
 
-// gsl_spline2d_eval_e / _deriv_x_e / _deriv_xx_e with gsl_interp2d_bicubic
+// gsl_spline2d_eval_e / _deriv_x_e / _deriv_xx_e / _deriv_y_e (which = 0 / 1 / 2 / 3) with gsl_interp2d_bicubic
 // (interp2d/bicubic.c).  The bicubic Hermite patch is evaluated in tensor Hermite-basis
 // form (same polynomial as GSL's 16-coefficient expansion, ~45 fp64 instructions).
 __device__ __forceinline__ double bicubic_eval(const F2D& f, double x, double y, int which) {
@@ -130,13 +130,19 @@ __device__ __forceinline__ double bicubic_eval(const F2D& f, double x, double y,
   const double t = (x - ax.x0) * ax.inv_dx, u = (y - ay.x0) * ay.inv_dx;
   const double um = 1.0 - u;
   const double u2 = u * u, um2 = um * um;
-  const double u00 = (1.0 + 2.0 * u) * um2;  // value weight, y-min edge
-  const double u01 = u2 * (3.0 - 2.0 * u);   // value weight, y-max edge
-  const double u10 = u * um2 * dy;           // slope weight, y-min edge
-  const double u11 = -u2 * um * dy;          // slope weight, y-max edge
+  double u00 = (1.0 + 2.0 * u) * um2;  // value weight, y-min edge
+  double u01 = u2 * (3.0 - 2.0 * u);   // value weight, y-max edge
+  double u10 = u * um2 * dy;           // slope weight, y-min edge
+  double u11 = -u2 * um * dy;          // slope weight, y-max edge
+  if (which == 3) {                    // d/dy (gsl bicubic_deriv_y): derivative of the y weights, x weights as for the value
+    u00 = 6.0 * u * (u - 1.0) * ay.inv_dx;
+    u01 = -u00;
+    u10 = (3.0 * u * u - 4.0 * u + 1.0);
+    u11 = (3.0 * u * u - 2.0 * u);
+  }
   double t00, t01, t10, t11;
   const double tm = 1.0 - t;
-  if (which == 0) {
+  if (which == 0 || which == 3) {
     const double t2 = t * t, tm2 = tm * tm;
     t00 = (1.0 + 2.0 * t) * tm2;
     t01 = t2 * (3.0 - 2.0 * t);

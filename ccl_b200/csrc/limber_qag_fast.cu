@@ -26,7 +26,10 @@ namespace cclb {
 
 namespace {
 
-constexpr int QFW = 8;            // warps per CTA
+#ifndef CCLB_QFW
+#define CCLB_QFW 12
+#endif
+constexpr int QFW = CCLB_QFW;      // warps per CTA
 constexpr int NCG = CCLB_NCG;     // collections per grid task
 constexpr int NPG = CCLB_NPG;     // pairs per grid task
 constexpr int NSG = 2 * CCLB_NCG; // sub-tracers per grid task
@@ -35,7 +38,10 @@ constexpr int PN = 41;            // abscissae per panel
 constexpr int PS = 48;            // row stride of a cached panel (doubles)
 constexpr int PROWS = NCG + 3;    // k P, chi, a rows + one D row per collection
 constexpr int QLB = 10;           // ells per CTA work item
-constexpr int QCTAS_PER_SM = 2;
+#ifndef CCLB_QCTAS
+#define CCLB_QCTAS 2
+#endif
+constexpr int QCTAS_PER_SM = CCLB_QCTAS;
 
 __constant__ double q_xgk[21];
 __constant__ double q_wgk[21];
@@ -90,46 +96,77 @@ __device__ __forceinline__ bool q_subinterval_too_small(double a1, double a2, do
   return fabs(a1) <= tmp && fabs(b2) <= tmp;
 }
 
-// gsl_integration_qk with the 41-point rule on a cached panel: lanes 0..19 hold the symmetric pairs of
-// abscissae (e, e + 20), lane 20 the centre; the four sums are shuffle-reduced exactly like the general
-// kernel's qk41_warp.  panel: [PROWS][PS] doubles, row 0 = k P, row 1 + c = D of collection slot c.
-__device__ __forceinline__ void panel_sums(const double* panel, int ca, int cb, double a, double b, int lane,
-                                           double& result, double& abserr, double& resabs, double& resasc) {
+// gsl_integration_qk with the 41-point rule on ONE or TWO cached panels at once: lanes 0..15 work on panel 0,
+// lanes 16..31 on panel 1.  A half-warp lane h holds the symmetric pair of abscissae (h, h + 20) and, for
+// h < 5, also the item h + 16 (pairs 16..19 and the centre, item 20); the four sums are reduced by a 4-step
+// butterfly inside each half-warp (both panels for the price of one), and the halves exchange their results.
+// panel: [PROWS][PS] doubles, row 0 = k P, row 3 + c = D of collection slot c.  Same sums as the general
+// kernel's qk41_warp up to the association of the additions.
+__device__ __forceinline__ void panel_sums2(const double* panel0, const double* panel1, int npan, int ca, int cb,
+                                            const double* qa, const double* qb, int lane, double* result,
+                                            double* abserr, double* resabs, double* resasc) {
+  const unsigned FULL = 0xffffffffu;
+  const int half = lane >> 4, h = lane & 15;
+  const bool active = half < npan;
+  const double* panel = half ? panel1 : panel0;
   const double* kp = panel;
   const double* da = panel + (3 + ca) * PS;
   const double* db = panel + (3 + cb) * PS;
+  const double a = (half && npan > 1) ? qa[1] : qa[0], b = (half && npan > 1) ? qb[1] : qb[0];
   const double half_length = 0.5 * (b - a);
   const double abs_half_length = fabs(half_length);
-  double rk = 0, rg = 0, ra = 0, f1 = 0, f2 = 0;
-  if (lane < 20) {
-    // cl_integrand (src/ccl_cls.c:166-187): k P d1 d2
-    f1 = __ldcg(kp + lane) * __ldcg(da + lane) * __ldcg(db + lane);
-    f2 = __ldcg(kp + lane + 20) * __ldcg(da + lane + 20) * __ldcg(db + lane + 20);
-    const double fsum = f1 + f2;
-    rk = q_wgk[lane] * fsum;
-    ra = q_wgk[lane] * (fabs(f1) + fabs(f2));
-    if (lane & 1) rg = q_wg[lane >> 1] * fsum;
-  } else if (lane == 20) {
-    f1 = __ldcg(kp + 40) * __ldcg(da + 40) * __ldcg(db + 40);
-    rk = f1 * q_wgk[20];
-    ra = fabs(rk);
+  double rk = 0, rg = 0, ra = 0;
+  double f1[2] = {0, 0}, f2[2] = {0, 0};
+  bool centre[2] = {false, false}, used[2] = {false, false};
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = h + 16 * u;  // item: 0..19 symmetric pairs, 20 the centre
+      if (i > 20) continue;
+      used[u] = true;
+      if (i < 20) {
+        // cl_integrand (src/ccl_cls.c:166-187): k P d1 d2
+        f1[u] = __ldcg(kp + i) * __ldcg(da + i) * __ldcg(db + i);
+        f2[u] = __ldcg(kp + i + 20) * __ldcg(da + i + 20) * __ldcg(db + i + 20);
+        const double fsum = f1[u] + f2[u];
+        rk += q_wgk[i] * fsum;
+        ra += q_wgk[i] * (fabs(f1[u]) + fabs(f2[u]));
+        if (i & 1) rg += q_wg[i >> 1] * fsum;
+      } else {
+        centre[u] = true;
+        f1[u] = __ldcg(kp + 40) * __ldcg(da + 40) * __ldcg(db + 40);
+        rk += f1[u] * q_wgk[20];
+        ra += fabs(f1[u] * q_wgk[20]);
+      }
+    }
   }
-  rk = qwarp_sum(rk);
-  rg = qwarp_sum(rg);
-  ra = qwarp_sum(ra);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    rk += __shfl_xor_sync(FULL, rk, o);
+    rg += __shfl_xor_sync(FULL, rg, o);
+    ra += __shfl_xor_sync(FULL, ra, o);
+  }
   const double mean = rk * 0.5;
   double rs = 0;
-  if (lane < 20) rs = q_wgk[lane] * (fabs(f1 - mean) + fabs(f2 - mean));
-  else if (lane == 20) rs = q_wgk[20] * fabs(f1 - mean);
-  rs = qwarp_sum(rs);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (!used[u]) continue;
+    const int i = h + 16 * u;
+    if (centre[u]) rs += q_wgk[20] * fabs(f1[u] - mean);
+    else rs += q_wgk[i] * (fabs(f1[u] - mean) + fabs(f2[u] - mean));
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(FULL, rs, o);
   const double err = (rk - rg) * half_length;
   rk *= half_length;
   ra *= abs_half_length;
   rs *= abs_half_length;
-  result = rk;
-  resabs = ra;
-  resasc = rs;
-  abserr = q_rescale_error(err, ra, rs);
+  const double ae = q_rescale_error(err, ra, rs);
+  // every lane leaves with both panels' results
+  const double ork = __shfl_xor_sync(FULL, rk, 16), ora = __shfl_xor_sync(FULL, ra, 16);
+  const double ors = __shfl_xor_sync(FULL, rs, 16), oae = __shfl_xor_sync(FULL, ae, 16);
+  result[0] = half ? ork : rk; resabs[0] = half ? ora : ra; resasc[0] = half ? ors : rs; abserr[0] = half ? oae : ae;
+  result[1] = half ? rk : ork; resabs[1] = half ? ra : ora; resasc[1] = half ? rs : ors; abserr[1] = half ? ae : oae;
 }
 
 }  // namespace
@@ -313,7 +350,7 @@ limber_qag_fast_kernel(const LimberProblem P, const FastPlan G, double* ws, doub
               else if (j < 20) lk = center - half_length * q_xgk[j];
               else lk = center + half_length * q_xgk[j - 20];
               double* row = pcache + (size_t)ps[p] * PROWS * PS + j;
-              const double k = exp(lk);
+              const double k = fast_exp(lk);
               const double chi = lp1h / k;
               // ccl_scale_factor_of_chi (src/ccl_background.c:1251-1277); chi > 0 here
               double a = 1.0;
@@ -379,9 +416,8 @@ limber_qag_fast_kernel(const LimberProblem P, const FastPlan G, double* ws, doub
           }
           // ---- GK41 sums of the requested panels ----
           double ar[2] = {0, 0}, er[2] = {0, 0}, rab[2] = {0, 0}, ras[2] = {0, 0};
-#pragma unroll 1
-          for (int p = 0; p < npan; ++p)
-            panel_sums(pcache + (size_t)sl[p] * PROWS * PS, po.x, po.y, qa[p], qb[p], lane, ar[p], er[p], rab[p], ras[p]);
+          panel_sums2(pcache + (size_t)sl[0] * PROWS * PS, pcache + (size_t)sl[1] * PROWS * PS, npan, po.x, po.y, qa, qb, lane,
+                      ar, er, rab, ras);
           nev += (unsigned long long)PN * npan;
           // ---- gsl_integration_qag bookkeeping (integration/qag.c) ----
           if (iteration == 0) {
@@ -441,17 +477,22 @@ limber_qag_fast_kernel(const LimberProblem P, const FastPlan G, double* ws, doub
             }
           }
           // retrieve(): interval with the largest error estimate; its two halves are the next request
+          // error estimates are non-negative doubles: their bit patterns order like unsigned integers, so the
+          // maximum of a 32-entry block is two integer warp reductions (high words, then low words) and a ballot
           double emax = -1.0;
           imax = 0;
-          for (int i = lane; i < size; i += 32) {
-            const double e = elist[i];
-            if (e > emax) { emax = e; imax = i; }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double eo = __shfl_xor_sync(FULL, emax, o);
-            const int io = __shfl_xor_sync(FULL, imax, o);
-            if (eo > emax || (eo == emax && io < imax)) { emax = eo; imax = io; }
+          for (int i0 = 0; i0 < size; i0 += 32) {
+            const int i = i0 + lane;
+            const double e = (i < size) ? elist[i] : -1.0;
+            const bool live = (i < size) && (e >= 0.0);
+            const unsigned hi = live ? (unsigned)__double2hiint(e) : 0u, lo = live ? (unsigned)__double2loint(e) : 0u;
+            const unsigned mhi = __reduce_max_sync(FULL, hi);
+            const unsigned mlo = __reduce_max_sync(FULL, (live && hi == mhi) ? lo : 0u);
+            const unsigned who = __ballot_sync(FULL, live && hi == mhi && lo == mlo);
+            if (who) {
+              const double eb = __hiloint2double((int)mhi, (int)mlo);
+              if (eb > emax) { emax = eb; imax = i0 + __ffs(who) - 1; }   // ties: the lowest index, as before
+            }
           }
           const double a_i = alist[imax], b_i = blist[imax];
           r_i = rlist[imax];

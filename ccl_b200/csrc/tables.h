@@ -134,6 +134,34 @@ struct LimberProblem {
   unsigned long long* counters;  // [0] integrand evaluations (qag only)
 };
 
+// ---- Limber covariance (covariance.cu): ccl_f3d_t and one ccl_angular_cl_covariance call ----
+// ccl_f3d_t (include/ccl_f3d.h): product form = two (ln k, a) tables, planes[0] and planes[1]; otherwise na bicubic
+// (ln k1, ln k2) planes, linearly interpolated in a (src/ccl_f3d.c:273-392)
+struct F3D {
+  int na, is_product, extrap_order_lok, extrap_order_hik;
+  int extrap_linear_growth, is_log, growth_exponent, pad;
+  double growth_factor_0, lkmin, lkmax;
+  const double* a_arr;  // [na]
+  const F2D* planes;
+};
+struct CovProblem {
+  const Cosmo* cosmo;
+  const Tracer* tracers;  // the four collections, concatenated
+  int2 coll[4];           // {first, count} of trc1..trc4
+  const F3D* tsp;
+  const double* l1;
+  const double* l2;
+  int nl1, nl2, chipow, has_ker;
+  Spline1D ker;           // kernel_extra: Akima f(a), constant extrapolation (pyccl/ccl_covs.i:95-118)
+  double ker_y0, ker_yf;
+  double chimin, chimax, prefactor;
+  double* cov;            // [nl1 * nl2], cov[l1 + nl1 * l2]
+  int* status;            // [2]: 0 / CCL_ERROR_INTEG, first underlying code
+};
+size_t covariance_scratch_bytes(int nchi, int n_iteration);
+cudaError_t launch_covariance(const CovProblem& prob, int method, int nchi, int n_iteration, double epsrel,
+                              double* scratch, cudaStream_t stream);
+
 // ---- fast 'spline' path: ln k node grids shared by the pairs of one cosmology ----
 // Two pairs of one cosmology share a node grid for every ell when their (chi_min, chi_max) from
 // get_k_interval (src/ccl_cls.c:64-100) coincide; a(chi), k P(k,a) and each collection's

@@ -21,9 +21,10 @@ def _check(status, where=""):
 
 
 def make_params(K_MAX=1e3, K_MIN=5e-5, DLOGK_INTEGRATION=0.025, INTEGRATION_LIMBER_EPSREL=1e-4,
-                N_ITERATION=1000, A_SPLINE_MIN=0.1, INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS=4):
+                N_ITERATION=1000, A_SPLINE_MIN=0.1, INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS=4,
+                DCHI_INTEGRATION=5.0):
     return _lib.Params(K_MAX, K_MIN, DLOGK_INTEGRATION, INTEGRATION_LIMBER_EPSREL, N_ITERATION,
-                       INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS, A_SPLINE_MIN)
+                       INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS, A_SPLINE_MIN, DCHI_INTEGRATION)
 
 
 def _tracer_args(sub):
@@ -193,6 +194,52 @@ def angular_cls_limber(cosmo, trs1, trs2, psp, ells, method=_lib.INTEGRATION_SPL
     if not same:
         L.ccl_b200_cl_tracer_collection_t_free(c2)
     return cl, st.value
+
+
+class LibF3D:
+    """ccl_b200_f3d: a ccl_f3d_t on the device (tk3d_new_from_arrays / tk3d_new_factorizable flags by default)."""
+
+    def __init__(self, a, lk, tkka=None, fka1=None, fka2=None, extrap_order_lok=1, extrap_order_hik=1, is_log=True,
+                 extrap_linear_growth=_lib.F2D_CONSTANTGROWTH, growth_factor_0=1.0, growth_exponent=4):
+        ka, pa = darr(a)
+        kl, pl = darr(lk)
+        kt, pt = darr(None if tkka is None else np.asarray(tkka).ravel())
+        k1, p1 = darr(None if fka1 is None else np.asarray(fka1).ravel())
+        k2, p2 = darr(None if fka2 is None else np.asarray(fka2).ravel())
+        st = C.c_int(0)
+        self.h = _lib.load().ccl_b200_f3d_new(len(ka), pa, len(kl), pl, pt, p1, p2, int(tkka is None),
+                                              int(extrap_order_lok), int(extrap_order_hik), int(extrap_linear_growth),
+                                              int(is_log), float(growth_factor_0), int(growth_exponent), C.byref(st))
+        _check(st.value, "f3d_new")
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib._LIB is not None:
+            _lib._LIB.ccl_b200_f3d_free(self.h)
+            self.h = None
+
+
+def angular_cl_covariance(cosmo, trs1, trs2, trs3, trs4, tsp, ell1, ell2, method=_lib.INTEGRATION_QAG_QUAD,
+                          chi_exponent=6, kernel_extra=None, prefactor=1.0):
+    """ccl_angular_cl_covariance through the C entry.  Returns (cov[nl2, nl1], status)."""
+    L = _lib.load()
+    st = C.c_int(0)
+    colls = []
+    for trs in (trs1, trs2, trs3, trs4):
+        c = L.ccl_b200_cl_tracer_collection_t_new(C.byref(st))
+        for t in trs:
+            L.ccl_b200_add_cl_tracer_to_collection(c, t.h, C.byref(st))
+        colls.append(c)
+    k1, p1 = darr(np.atleast_1d(ell1))
+    k2, p2 = darr(np.atleast_1d(ell2))
+    ka, pa = darr(None if kernel_extra is None else kernel_extra[0])
+    kf, pf = darr(None if kernel_extra is None else kernel_extra[1])
+    out = np.empty(len(k1) * len(k2))
+    L.ccl_b200_angular_cl_covariance(cosmo.h, colls[0], colls[1], colls[2], colls[3], tsp.h, len(k1), p1, len(k2), p2,
+                                     out.ctypes.data_as(_lib._dp), int(method), int(chi_exponent),
+                                     0 if ka is None else len(ka), pa, pf, float(prefactor), C.byref(st))
+    for c in colls:
+        L.ccl_b200_cl_tracer_collection_t_free(c)
+    return out.reshape(len(k2), len(k1)), st.value
 
 
 class LibBatch:

@@ -44,6 +44,7 @@ extern "C" {
 
 typedef struct ccl_b200_cosmology ccl_b200_cosmology;    /* ccl_cosmology, as seen by the path */
 typedef struct ccl_b200_f2d ccl_b200_f2d;                /* ccl_f2d_t */
+typedef struct ccl_b200_f3d ccl_b200_f3d;                /* ccl_f3d_t (Tk3D) */
 typedef struct ccl_b200_tracer ccl_b200_tracer;          /* ccl_cl_tracer_t */
 typedef struct ccl_b200_collection ccl_b200_collection;  /* ccl_cl_tracer_collection_t */
 typedef struct ccl_b200_batch ccl_b200_batch;            /* N cosmologies' table packs in one arena */
@@ -63,6 +64,7 @@ typedef struct {
    * silently integrating with GK41. */
   int INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS;
   double A_SPLINE_MIN;              /* 0.1: chi_max of kernel-less tracers = chi(A_SPLINE_MIN) */
+  double DCHI_INTEGRATION;          /* 5.0: chi sampling of the covariance 'spline' method (src/ccl_cls.c:418) */
 } ccl_b200_params;
 
 /* ---- library ---- */
@@ -149,6 +151,27 @@ void ccl_b200_angular_cls_limber(ccl_b200_cosmology *cosmo, ccl_b200_collection 
                                  int *status);
 
 /* ---- batched entry: (ncosmo, npair, nl) in one launch ---- */
+/* ---- Limber covariance ----
+ * ccl_f3d_t_new (include/ccl_f3d.h, src/ccl_f3d.c:161-271) minus interp_type (bicubic only): tkka_arr[na][nk][nk]
+ * (index [ia][ik2][ik1]) or, in product form, fka1_arr / fka2_arr [na][nk].  pyccl binds it through
+ * tk3d_new_from_arrays / tk3d_new_factorizable (pyccl/ccl_tk3d.i:17-44: constant growth, growth_factor_0 = 1,
+ * exponent 4). */
+ccl_b200_f3d *ccl_b200_f3d_new(int na, const double *a_arr, int nk, const double *lk_arr, const double *tkka_arr,
+                               const double *fka1_arr, const double *fka2_arr, int is_product,
+                               int extrap_order_lok, int extrap_order_hik, int extrap_linear_growth,
+                               int is_tkka_log, double growth_factor_0, int growth_exponent, int *status);
+void ccl_b200_f3d_free(ccl_b200_f3d *f3d);
+/* ccl_angular_cl_covariance (include/ccl_cls.h, src/ccl_cls.c:490-612), argument for argument; kernel_extra (a
+ * ccl_f1d_t in the reference) is passed as the (a, f) arrays angular_cov_ssc_vec builds it from
+ * (pyccl/ccl_covs.i:95-118: Akima, constant extrapolation), n_ker = 0 for none (angular_cov_vec, :53-70).
+ * cov_out[l1 + nl1 * l2]; NaN + CCL_ERROR_INTEG on failure. */
+void ccl_b200_angular_cl_covariance(ccl_b200_cosmology *cosmo, ccl_b200_collection *trc1,
+                                    ccl_b200_collection *trc2, ccl_b200_collection *trc3,
+                                    ccl_b200_collection *trc4, ccl_b200_f3d *tsp, int nl1_out,
+                                    const double *l1_out, int nl2_out, const double *l2_out, double *cov_out,
+                                    int integration_method, int chi_exponent, int n_ker, const double *a_ker,
+                                    const double *f_ker, double prefactor_extra, int *status);
+
 /* A batch owns one HBM arena holding the table packs of ncosmo cosmologies.  Slots are filled
  * with the same flat arrays as the single-object constructors, then committed (one H2D copy of
  * the raw region + device kernels that build every spline coefficient table in place). */

@@ -87,6 +87,15 @@ def lib():
                                            C.c_int, _dp, _dp, C.c_int, C.POINTER(C.c_long), _ip]
         L.o_angular_cls_limber_each.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), vp,
                                                 C.c_int, _dp, _dp, C.c_int, _ip]
+        L.o_f3d_new.restype = vp
+        L.o_f3d_new.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_double, C.c_int, _ip]
+        L.o_f3d_free.argtypes = [vp]
+        L.o_f3d_eval.restype = C.c_double
+        L.o_f3d_eval.argtypes = [vp, C.c_double, C.c_double, C.c_double, vp, _ip]
+        L.o_angular_cl_covariance.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int,
+                                              C.POINTER(vp), C.c_int, C.POINTER(vp), vp, C.c_int, _dp, C.c_int, _dp,
+                                              _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double, _ip]
         L.o_get_k_interval_pub.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp),
                                            C.c_double, _dp, _dp]
         L.o_set_lkmin_ulps.argtypes = [C.c_int]
@@ -230,6 +239,55 @@ class F2D:
     def __del__(self):
         if getattr(self, "h", None):
             lib().o_f2d_free(self.h)
+
+
+class F3D:
+    """ccl_f3d_t (src/ccl_f3d.c:161-271) with the flags of tk3d_new_from_arrays / tk3d_new_factorizable
+    (pyccl/ccl_tk3d.i): constant growth, growth_factor_0 = 1, exponent 4.  tkka is [na, nk, nk]."""
+
+    def __init__(self, a, lk, tkka=None, fka1=None, fka2=None, extrap_order_lok=1, extrap_order_hik=1, is_log=True,
+                 extrap_linear_growth=F2D_CONSTGROWTH, growth_factor_0=1.0, growth_exponent=4):
+        self._a, pa = _arr(a)
+        self._lk, plk = _arr(lk)
+        self._t, pt = _arr(None if tkka is None else np.asarray(tkka).ravel())
+        self._f1, p1 = _arr(None if fka1 is None else np.asarray(fka1).ravel())
+        self._f2, p2 = _arr(None if fka2 is None else np.asarray(fka2).ravel())
+        st = C.c_int(0)
+        self.h = lib().o_f3d_new(len(self._a), pa, len(self._lk), plk, pt, p1, p2, int(tkka is None), extrap_order_lok,
+                                 extrap_order_hik, extrap_linear_growth, int(is_log), growth_factor_0,
+                                 growth_exponent, C.byref(st))
+        self.status = st.value
+
+    def __call__(self, lk1, lk2, a, cosmo=None):
+        st = C.c_int(0)
+        v = lib().o_f3d_eval(self.h, float(lk1), float(lk2), float(a), cosmo.h if cosmo else None, C.byref(st))
+        return v, st.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().o_f3d_free(self.h)
+
+
+def angular_cl_cov(cosmo, trc1, trc2, trc3, trc4, tsp, ell1, ell2, method=INTEG_QAG, chi_exponent=6,
+                   kernel_extra=None, prefactor=1.0, dchi=5.0):
+    """ccl_angular_cl_covariance (src/ccl_cls.c:490-612).  Returns (cov[nl2, nl1], status): the flat output of the
+    reference is cov_out[l1 + nl1 * l2]."""
+    ell1 = np.ascontiguousarray(np.atleast_1d(ell1), dtype=np.float64)
+    ell2 = np.ascontiguousarray(np.atleast_1d(ell2), dtype=np.float64)
+    out = np.full(ell1.size * ell2.size, np.nan)
+    ka = kf = None
+    nker = 0
+    if kernel_extra is not None:
+        (ka, pka), (kf, pkf) = _arr(kernel_extra[0]), _arr(kernel_extra[1])
+        nker = len(ka)
+    else:
+        pka = pkf = None
+    st = C.c_int(0)
+    lib().o_angular_cl_covariance(cosmo.h, len(trc1), _coll(trc1), len(trc2), _coll(trc2), len(trc3), _coll(trc3),
+                                  len(trc4), _coll(trc4), tsp.h, ell1.size, ell1.ctypes.data_as(_dp), ell2.size,
+                                  ell2.ctypes.data_as(_dp), out.ctypes.data_as(_dp), int(method), int(chi_exponent),
+                                  nker, pka, pkf, float(prefactor), float(dchi), C.byref(st))
+    return out.reshape(ell2.size, ell1.size), st.value
 
 
 class Tracer:

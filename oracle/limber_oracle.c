@@ -341,36 +341,13 @@ o_bicubic *o_bicubic_new(int nx, int ny, const double *xa, const double *ya, con
   return s;
 }
 
-/* which: 0 value, 1 d/dx, 2 d2/dx2 */
-int o_bicubic_eval_e(const o_bicubic *s, double x, double y, int which, double *out) {
-  if (x < s->x[0] || x > s->x[s->nx - 1] || y < s->y[0] || y > s->y[s->ny - 1]) {
-    *out = NAN;
-    return O_GSL_EDOM;
-  }
-  const int nx = s->nx;
-  size_t xi = o_bsearch(s->x, x, 0, s->nx - 1);
-  size_t yi = o_bsearch(s->y, y, 0, s->ny - 1);
-  const double xmin = s->x[xi], xmax = s->x[xi + 1];
-  const double ymin = s->y[yi], ymax = s->y[yi + 1];
-  const double zminmin = s->z[IDX2D(xi, yi, nx)];
-  const double zminmax = s->z[IDX2D(xi, yi + 1, nx)];
-  const double zmaxmin = s->z[IDX2D(xi + 1, yi, nx)];
-  const double zmaxmax = s->z[IDX2D(xi + 1, yi + 1, nx)];
-  const double dx = xmax - xmin, dy = ymax - ymin;
-  const double t = (x - xmin) / dx, u = (y - ymin) / dy;
-  const double dt = 1. / dx, du = 1. / dy;
-  const double zxminmin = s->zx[IDX2D(xi, yi, nx)] / dt;
-  const double zxminmax = s->zx[IDX2D(xi, yi + 1, nx)] / dt;
-  const double zxmaxmin = s->zx[IDX2D(xi + 1, yi, nx)] / dt;
-  const double zxmaxmax = s->zx[IDX2D(xi + 1, yi + 1, nx)] / dt;
-  const double zyminmin = s->zy[IDX2D(xi, yi, nx)] / du;
-  const double zyminmax = s->zy[IDX2D(xi, yi + 1, nx)] / du;
-  const double zymaxmin = s->zy[IDX2D(xi + 1, yi, nx)] / du;
-  const double zymaxmax = s->zy[IDX2D(xi + 1, yi + 1, nx)] / du;
-  const double zxyminmin = s->zxy[IDX2D(xi, yi, nx)] / (dt * du);
-  const double zxyminmax = s->zxy[IDX2D(xi, yi + 1, nx)] / (dt * du);
-  const double zxymaxmin = s->zxy[IDX2D(xi + 1, yi, nx)] / (dt * du);
-  const double zxymaxmax = s->zxy[IDX2D(xi + 1, yi + 1, nx)] / (dt * du);
+/* The bicubic patch of GSL's interp2d/bicubic.c on one cell, from its 16 corner values (already scaled by the
+ * cell size).  which: 0 value, 1 d/dx, 2 d2/dx2 (bicubic_eval / _deriv_x / _deriv_xx). */
+static void o_bicubic_cell(double zminmin, double zminmax, double zmaxmin, double zmaxmax, double zxminmin,
+                           double zxminmax, double zxmaxmin, double zxmaxmax, double zyminmin, double zyminmax,
+                           double zymaxmin, double zymaxmax, double zxyminmin, double zxyminmax,
+                           double zxymaxmin, double zxymaxmax, double t, double u, double dt, int which,
+                           double *out) {
   const double t0 = 1, t1 = t, t2 = t * t, t3 = t * t2;
   const double u0 = 1, u1 = u, u2 = u * u, u3 = u * u2;
   double v, z = 0;
@@ -455,6 +432,46 @@ int o_bicubic_eval_e(const o_bicubic *s, double x, double y, int which, double *
     z += 6 * v * t1 * u3;
     *out = z * dt * dt;
   }
+}
+
+
+/* which: 0 value, 1 d/dx, 2 d2/dx2, 3 d/dy (bicubic_deriv_y: the x-derivative of the patch with the roles of
+ * the two axes exchanged) */
+int o_bicubic_eval_e(const o_bicubic *s, double x, double y, int which, double *out) {
+  if (x < s->x[0] || x > s->x[s->nx - 1] || y < s->y[0] || y > s->y[s->ny - 1]) {
+    *out = NAN;
+    return O_GSL_EDOM;
+  }
+  const int nx = s->nx;
+  size_t xi = o_bsearch(s->x, x, 0, s->nx - 1);
+  size_t yi = o_bsearch(s->y, y, 0, s->ny - 1);
+  const double xmin = s->x[xi], xmax = s->x[xi + 1];
+  const double ymin = s->y[yi], ymax = s->y[yi + 1];
+  const double zminmin = s->z[IDX2D(xi, yi, nx)];
+  const double zminmax = s->z[IDX2D(xi, yi + 1, nx)];
+  const double zmaxmin = s->z[IDX2D(xi + 1, yi, nx)];
+  const double zmaxmax = s->z[IDX2D(xi + 1, yi + 1, nx)];
+  const double dx = xmax - xmin, dy = ymax - ymin;
+  const double t = (x - xmin) / dx, u = (y - ymin) / dy;
+  const double dt = 1. / dx, du = 1. / dy;
+  const double zxminmin = s->zx[IDX2D(xi, yi, nx)] / dt;
+  const double zxminmax = s->zx[IDX2D(xi, yi + 1, nx)] / dt;
+  const double zxmaxmin = s->zx[IDX2D(xi + 1, yi, nx)] / dt;
+  const double zxmaxmax = s->zx[IDX2D(xi + 1, yi + 1, nx)] / dt;
+  const double zyminmin = s->zy[IDX2D(xi, yi, nx)] / du;
+  const double zyminmax = s->zy[IDX2D(xi, yi + 1, nx)] / du;
+  const double zymaxmin = s->zy[IDX2D(xi + 1, yi, nx)] / du;
+  const double zymaxmax = s->zy[IDX2D(xi + 1, yi + 1, nx)] / du;
+  const double zxyminmin = s->zxy[IDX2D(xi, yi, nx)] / (dt * du);
+  const double zxyminmax = s->zxy[IDX2D(xi, yi + 1, nx)] / (dt * du);
+  const double zxymaxmin = s->zxy[IDX2D(xi + 1, yi, nx)] / (dt * du);
+  const double zxymaxmax = s->zxy[IDX2D(xi + 1, yi + 1, nx)] / (dt * du);
+  if (which == 3)
+    o_bicubic_cell(zminmin, zmaxmin, zminmax, zmaxmax, zyminmin, zymaxmin, zyminmax, zymaxmax, zxminmin, zxmaxmin,
+                   zxminmax, zxmaxmax, zxyminmin, zxymaxmin, zxyminmax, zxymaxmax, u, t, du, 1, out);
+  else
+    o_bicubic_cell(zminmin, zminmax, zmaxmin, zmaxmax, zxminmin, zxminmax, zxmaxmin, zxmaxmax, zyminmin, zyminmax,
+                   zymaxmin, zymaxmax, zxyminmin, zxyminmax, zxymaxmin, zxymaxmax, t, u, dt, which, out);
   return O_SUCCESS;
 }
 
@@ -1382,6 +1399,295 @@ static void o_integ_cls_limber_qag_quad(const o_cosmo *cosmo, o_integ_par *ipar,
                         (size_t)cosmo->N_ITERATION, result, eresult, &nevals);
   }
   if (*status == 0) *status = gslstatus;
+}
+
+/* ------------------------------------------------------------------ */
+/* ccl_f3d_t (src/ccl_f3d.c) and ccl_angular_cl_covariance (src/ccl_cls.c:377-612) */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  double lkmin, lkmax;
+  int na;
+  double *a_arr;
+  int is_product, extrap_order_lok, extrap_order_hik, extrap_linear_growth, is_log;
+  double growth_factor_0;
+  int growth_exponent;
+  o_f2d *fka_1, *fka_2;
+  o_bicubic **tkka; /* [na] bicubic (lk1, lk2) planes */
+} o_f3d;
+
+void o_f3d_free(o_f3d *f) {
+  if (!f) return;
+  o_f2d_free(f->fka_1);
+  o_f2d_free(f->fka_2);
+  if (f->tkka) {
+    for (int ia = 0; ia < f->na; ia++) o_bicubic_free(f->tkka[ia]);
+    free(f->tkka);
+  }
+  free(f->a_arr);
+  free(f);
+}
+
+/* ccl_f3d_t_new (src/ccl_f3d.c:161-271), interp_type = ccl_f2d_3 */
+o_f3d *o_f3d_new(int na, const double *a_arr, int nk, const double *lk_arr, const double *tkka_arr,
+                 const double *fka1_arr, const double *fka2_arr, int is_product, int extrap_order_lok,
+                 int extrap_order_hik, int extrap_linear_growth, int is_tkka_log, double growth_factor_0,
+                 int growth_exponent, int *status) {
+  o_f3d *f = calloc(1, sizeof(o_f3d));
+  is_product = is_product || (tkka_arr == NULL);
+  f->is_product = is_product;
+  f->extrap_order_lok = extrap_order_lok;
+  f->extrap_order_hik = extrap_order_hik;
+  f->extrap_linear_growth = extrap_linear_growth;
+  f->is_log = is_tkka_log;
+  f->growth_factor_0 = growth_factor_0;
+  f->growth_exponent = growth_exponent;
+  f->lkmin = lk_arr[0];
+  f->lkmax = lk_arr[nk - 1];
+  f->na = na;
+  f->a_arr = malloc(na * sizeof(double));
+  memcpy(f->a_arr, a_arr, na * sizeof(double));
+  if ((extrap_order_lok > 1) || (extrap_order_lok < 0) || (extrap_order_hik > 1) || (extrap_order_hik < 0))
+    *status = O_ERR_INCONSISTENT;
+  if ((extrap_linear_growth != O_F2D_CCLGROWTH) && (extrap_linear_growth != O_F2D_CONSTGROWTH) &&
+      (extrap_linear_growth != O_F2D_NOEXTRAPOL))
+    *status = O_ERR_INCONSISTENT;
+  if (f->is_product) {
+    if ((fka1_arr == NULL) || (fka2_arr == NULL)) *status = O_ERR_INCONSISTENT;
+  } else if (tkka_arr == NULL)
+    *status = O_ERR_INCONSISTENT;
+  if (*status == 0) {
+    if (f->is_product) {
+      f->fka_1 = o_f2d_new(na, a_arr, nk, lk_arr, fka1_arr, NULL, NULL, 0, extrap_order_lok, extrap_order_hik,
+                           extrap_linear_growth, is_tkka_log, growth_factor_0, growth_exponent / 2, status);
+      f->fka_2 = o_f2d_new(na, a_arr, nk, lk_arr, fka2_arr, NULL, NULL, 0, extrap_order_lok, extrap_order_hik,
+                           extrap_linear_growth, is_tkka_log, growth_factor_0, growth_exponent / 2, status);
+    } else {
+      f->tkka = calloc(na, sizeof(o_bicubic *));
+      for (int ia = 0; ia < na; ia++) {
+        f->tkka[ia] = o_bicubic_new(nk, nk, lk_arr, lk_arr, tkka_arr + (size_t)ia * nk * nk);
+        if (!f->tkka[ia]) { *status = O_ERR_SPLINE; break; }
+      }
+    }
+  }
+  return f;
+}
+
+/* ccl_find_a_index (src/ccl_f3d.c:46-88): the interval [a_ia, a_ia+1) holding a; na-1 at and above the last node */
+static int o_find_a_index(const o_f3d *f, double a) {
+  if (a >= f->a_arr[f->na - 1]) return f->na - 1;
+  if (a <= f->a_arr[0]) return 0;
+  int ia = 0;
+  while (ia < f->na - 2 && a >= f->a_arr[ia + 1]) ia++;
+  return ia;
+}
+
+/* ccl_f3d_t_eval (src/ccl_f3d.c:273-392) */
+double o_f3d_eval(const o_f3d *f3d, double lk1, double lk2, double a, const o_cosmo *cosmo, int *status) {
+  double tkka_post = 0;
+  double a_ev = a;
+  int is_hiz = a < f3d->a_arr[0];
+  int is_loz = a > f3d->a_arr[f3d->na - 1];
+  if (is_loz) {
+    if (f3d->extrap_linear_growth == O_F2D_NOEXTRAPOL) { *status = O_ERR_SPLINE_EV; return NAN; }
+    a_ev = f3d->a_arr[f3d->na - 1];
+  } else if (is_hiz) {
+    if (f3d->extrap_linear_growth == O_F2D_NOEXTRAPOL) { *status = O_ERR_SPLINE_EV; return NAN; }
+    a_ev = f3d->a_arr[0];
+  }
+  if (f3d->is_product) {
+    double fka1 = o_f2d_eval(f3d->fka_1, lk1, a_ev, cosmo, status);
+    double fka2 = o_f2d_eval(f3d->fka_2, lk2, a_ev, cosmo, status);
+    if (*status != 0) return NAN;
+    tkka_post = fka1 * fka2;
+  } else {
+    double lk1_ev = lk1;
+    int is_hik1 = lk1 > f3d->lkmax, is_lok1 = lk1 < f3d->lkmin;
+    int extrap_k1 = (is_hik1 & (f3d->extrap_order_hik > 0)) || (is_lok1 & (f3d->extrap_order_lok > 0));
+    if (is_hik1) lk1_ev = f3d->lkmax;
+    else if (is_lok1) lk1_ev = f3d->lkmin;
+    double lk2_ev = lk2;
+    int is_hik2 = lk2 > f3d->lkmax, is_lok2 = lk2 < f3d->lkmin;
+    int extrap_k2 = (is_hik2 & (f3d->extrap_order_hik > 0)) || (is_lok2 & (f3d->extrap_order_lok > 0));
+    if (is_hik2) lk2_ev = f3d->lkmax;
+    else if (is_lok2) lk2_ev = f3d->lkmin;
+    int ia = o_find_a_index(f3d, a_ev);
+    if (*status == 0) {
+      int spstatus = 0;
+      double tkka = 0, dtkka1 = 0, dtkka2 = 0;
+      spstatus |= o_bicubic_eval_e(f3d->tkka[ia], lk1_ev, lk2_ev, 0, &tkka);
+      if (extrap_k1) spstatus |= o_bicubic_eval_e(f3d->tkka[ia], lk1_ev, lk2_ev, 1, &dtkka1);
+      if (extrap_k2) spstatus |= o_bicubic_eval_e(f3d->tkka[ia], lk1_ev, lk2_ev, 3, &dtkka2);
+      if (ia < f3d->na - 1) {
+        double tkka_p1, dtkka1_p1, dtkka2_p1;
+        double h = (a_ev - f3d->a_arr[ia]) / (f3d->a_arr[ia + 1] - f3d->a_arr[ia]);
+        spstatus |= o_bicubic_eval_e(f3d->tkka[ia + 1], lk1_ev, lk2_ev, 0, &tkka_p1);
+        if (!spstatus) tkka = tkka * (1 - h) + tkka_p1 * h;
+        if (extrap_k1) {
+          spstatus |= o_bicubic_eval_e(f3d->tkka[ia + 1], lk1_ev, lk2_ev, 1, &dtkka1_p1);
+          if (!spstatus) dtkka1 = dtkka1 * (1 - h) + dtkka1_p1 * h;
+        }
+        if (extrap_k2) {
+          spstatus |= o_bicubic_eval_e(f3d->tkka[ia + 1], lk1_ev, lk2_ev, 3, &dtkka2_p1);
+          if (!spstatus) dtkka2 = dtkka2 * (1 - h) + dtkka2_p1 * h;
+        }
+      }
+      if (spstatus) { *status = O_ERR_SPLINE_EV; return NAN; }
+      if (extrap_k1) tkka += dtkka1 * (lk1 - lk1_ev);
+      if (extrap_k2) tkka += dtkka2 * (lk2 - lk2_ev);
+      tkka_post = tkka;
+    }
+    if (f3d->is_log) tkka_post = exp(tkka_post);
+  }
+  if (is_hiz) {
+    double gz;
+    if (f3d->extrap_linear_growth == O_F2D_CCLGROWTH) {
+      if (!cosmo || !cosmo->growth) { *status = O_ERR_GROWTH_INIT; return NAN; }
+      gz = o_growth_factor(cosmo, a, status) / o_growth_factor(cosmo, a_ev, status);
+    } else
+      gz = f3d->growth_factor_0;
+    tkka_post *= pow(gz, f3d->growth_exponent);
+  }
+  return tkka_post;
+}
+
+typedef struct {
+  int chipow;
+  double l1, l2;
+  const o_cosmo *cosmo;
+  int n1, n2, n3, n4;
+  o_tracer *const *trc1, *const *trc2, *const *trc3, *const *trc4;
+  const o_f3d *tsp;
+  const o_f1d *ker_extra;
+  int *status;
+} o_cov_par;
+
+/* transfer_limber_wrap(..., psp = NULL, ignore_jbes_deriv = 1) (src/ccl_cls.c:102-164): der_bessel 1/2 terms drop */
+static double o_transfer_limber_noderiv(double l, double lk, double chi, double a, int n, o_tracer *const *trc,
+                                        int *status) {
+  double transfer = 0;
+  for (int itr = 0; itr < n; itr++) {
+    const o_tracer *tr = trc[itr];
+    double dd = 0;
+    double w = o_tracer_kernel(tr, chi);
+    double t = o_tracer_transfer(tr, lk, a, status);
+    double fl = o_tracer_f_ell(tr, l);
+    if (tr->der_bessel < 1) {
+      dd = w * t;
+      if (tr->der_bessel == -1) {
+        double lp1h = l + 0.5;
+        dd /= (lp1h * lp1h);
+      }
+    }
+    transfer += dd * fl;
+    if (*status != 0) return -1;
+  }
+  return transfer;
+}
+
+/* cov_integrand (src/ccl_cls.c:377-411) */
+static double o_cov_integrand(double chi, void *params) {
+  o_cov_par *p = (o_cov_par *)params;
+  double ker = 1;
+  double k1 = (p->l1 + 0.5) / chi, k2 = (p->l2 + 0.5) / chi;
+  double lk1 = log(k1), lk2 = log(k2);
+  double a = o_scale_factor_of_chi(p->cosmo, chi, p->status);
+  double d1 = o_transfer_limber_noderiv(p->l1, lk1, chi, a, p->n1, p->trc1, p->status);
+  if (d1 == 0) return 0;
+  double d2 = o_transfer_limber_noderiv(p->l1, lk1, chi, a, p->n2, p->trc2, p->status);
+  if (d2 == 0) return 0;
+  double d3 = o_transfer_limber_noderiv(p->l2, lk2, chi, a, p->n3, p->trc3, p->status);
+  if (d3 == 0) return 0;
+  double d4 = o_transfer_limber_noderiv(p->l2, lk2, chi, a, p->n4, p->trc4, p->status);
+  if (d4 == 0) return 0;
+  double tkk = o_f3d_eval(p->tsp, lk1, lk2, a, p->cosmo, p->status);
+  if (p->ker_extra != NULL) ker = o_f1d_eval(p->ker_extra, a);
+  return d1 * d2 * d3 * d4 * tkk * ker / pow(chi, p->chipow);
+}
+
+/* update_chi_limits (src/ccl_cls.c:34-62) */
+static void o_update_chi_limits(int n, o_tracer *const *trc, double *chimin, double *chimax, int is_union) {
+  double lo = 1E15, hi = -1E15;
+  for (int i = 0; i < n; i++) {
+    if (trc[i]->chi_min < lo) lo = trc[i]->chi_min;
+    if (trc[i]->chi_max > hi) hi = trc[i]->chi_max;
+  }
+  if (is_union) {
+    if (lo < *chimin) *chimin = lo;
+    if (hi > *chimax) *chimax = hi;
+  } else {
+    if (lo > *chimin) *chimin = lo;
+    if (hi < *chimax) *chimax = hi;
+  }
+}
+
+/* ccl_angular_cl_covariance (src/ccl_cls.c:490-612); kernel_extra as the (a, f) arrays angular_cov_ssc_vec turns into a
+ * ccl_f1d_t with constant extrapolation (pyccl/ccl_covs.i:95-118), n_ker = 0: none.  cov_out[lind1 + nl1 * lind2]. */
+void o_angular_cl_covariance(const o_cosmo *cosmo, int n1, o_tracer *const *trc1, int n2, o_tracer *const *trc2,
+                             int n3, o_tracer *const *trc3, int n4, o_tracer *const *trc4, const o_f3d *tsp,
+                             int nl1, const double *l1_out, int nl2, const double *l2_out, double *cov_out,
+                             int integration_method, int chi_exponent, int n_ker, const double *a_ker,
+                             const double *f_ker, double prefactor_extra, double dchi, int *status) {
+  if (!cosmo->achi) { *status = O_ERR_DISTANCES_INIT; return; }
+  o_f1d *ker = n_ker > 0 ? o_f1d_new(n_ker, a_ker, f_ker, f_ker[0], f_ker[n_ker - 1]) : NULL;
+  double chimin = 1E15, chimax = -1E15;
+  o_update_chi_limits(n1, trc1, &chimin, &chimax, 1);
+  o_update_chi_limits(n2, trc2, &chimin, &chimax, 0);
+  o_update_chi_limits(n3, trc3, &chimin, &chimax, 0);
+  o_update_chi_limits(n4, trc4, &chimin, &chimax, 0);
+#pragma omp parallel
+  {
+    int clastatus = 0;
+    int local_status = *status;
+    o_cov_par ipar;
+    ipar.cosmo = cosmo; ipar.n1 = n1; ipar.n2 = n2; ipar.n3 = n3; ipar.n4 = n4;
+    ipar.trc1 = trc1; ipar.trc2 = trc2; ipar.trc3 = trc3; ipar.trc4 = trc4;
+    ipar.tsp = tsp; ipar.ker_extra = ker; ipar.status = &clastatus; ipar.chipow = chi_exponent;
+#pragma omp for schedule(dynamic)
+    for (int lind1 = 0; lind1 < nl1; ++lind1) {
+      ipar.l1 = l1_out[lind1];
+      for (int lind2 = 0; lind2 < nl2; ++lind2) {
+        if (local_status == 0) {
+          double result = 0, eresult = 0;
+          clastatus = 0;
+          ipar.l2 = l2_out[lind2];
+          if (integration_method == O_INTEG_QAG) {
+            int gslstatus = o_qag41(o_cov_integrand, &ipar, chimin, chimax, 0, cosmo->LIMBER_EPSREL,
+                                    cosmo->N_ITERATION, &result, &eresult, NULL);
+            if (gslstatus == O_GSL_EROUND) {
+              size_t nevals = 0;
+              gslstatus = o_cquad(o_cov_integrand, &ipar, chimin, chimax, 0, cosmo->LIMBER_EPSREL,
+                                  (size_t)cosmo->N_ITERATION, &result, &eresult, &nevals);
+            }
+            if (local_status == 0) local_status = gslstatus;
+          } else if (integration_method == O_INTEG_SPLINE) {
+            /* integ_cov_limber_spline (src/ccl_cls.c:413-452) */
+            int nchi = (int)(fmax((chimax - chimin) / dchi + 0.5, 1)) + 1;
+            double *chi_arr = o_linear_spacing(chimin, chimax, nchi);
+            double *fchi = malloc(nchi * sizeof(double));
+            for (int i = 0; i < nchi; i++) {
+              fchi[i] = o_cov_integrand(chi_arr[i], &ipar);
+              if (clastatus) { local_status = clastatus; break; }
+            }
+            if (local_status == 0) o_integ_spline(nchi, chi_arr, fchi, 1, -1, &result, &local_status);
+            free(fchi);
+            free(chi_arr);
+          } else
+            local_status = O_ERR_NOT_IMPLEMENTED;
+          if ((clastatus == 0) && (local_status == 0)) {
+            cov_out[lind1 + nl1 * lind2] = result * prefactor_extra;
+          } else {
+            cov_out[lind1 + nl1 * lind2] = NAN;
+            local_status = O_ERR_INTEG;
+          }
+        }
+      }
+    }
+    if (local_status) {
+#pragma omp atomic write
+      *status = local_status;
+    }
+  }
+  o_f1d_free(ker);
 }
 
 /* src/ccl_cls.c:265-363.  neval_out (may be NULL) receives the integrand evaluations per ell. */

@@ -1,8 +1,10 @@
-# 'qag_quad' resident pass at 64 cosmologies: grid-sharing kernel vs the general kernel (CCL_B200_NO_QAG_FAST=1)
-for mode in fast general; do
-  if [ $mode = fast ]; then export CCL_B200_QAG_FAST=1; else unset CCL_B200_QAG_FAST; fi
-  echo "== qag $mode"
-  python bench.py --method qag_quad --ncosmo ${NCOSMO:-64} --steps 2 --warmup 2 --no-e2e --from-parameters 0 --qag-sample 0 --no-y10 2>&1 | python -c "
+# 'qag_quad' resident pass: grid-sharing kernel of each library variant, then the general kernel (CCL_B200_NO_QAG_FAST=1)
+# usage: [NCOSMO=64] bash tools/ab_qag.sh [lib names...]
+libs="$@"; [ -z "$libs" ] && libs="libccl_b200"
+for v in $libs general; do
+  if [ $v = general ]; then export CCL_B200_NO_QAG_FAST=1; lib=$PWD/ccl_b200/libccl_b200.so; else unset CCL_B200_NO_QAG_FAST; lib=$PWD/ccl_b200/$v.so; fi
+  echo "== qag $v"
+  CCL_B200_LIB=$lib python bench.py --method qag_quad --ncosmo ${NCOSMO:-64} --steps 2 --warmup 2 --no-e2e --from-parameters 0 --qag-sample 0 --no-y10 ${QAG_EXTRA:---no-cpu-baseline} 2>&1 | python -c "
 import sys,json
 for ln in sys.stdin:
     if ln.startswith('{'):
