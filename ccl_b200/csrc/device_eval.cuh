@@ -23,6 +23,19 @@ __device__ __forceinline__ double4 ldg4(const double4* p) {
 #endif
 }
 
+// The same load without allocating the line in L1 (streamed tables: with 3 CTAs per SM the Limber kernel leaves
+// ~28 KB of L1, which the reusable spline records should keep; CCLB_PK_NOALLOC selects it for the P(k,a) nodes).
+__device__ __forceinline__ double4 ldg4_stream(const double4* p) {
+  double4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+#ifdef CCLB_PK_NOALLOC
+#define CCLB_LDG4_PK ldg4_stream
+#else
+#define CCLB_LDG4_PK ldg4
+#endif
+
 // Interval i of a 1-D spline: end points (LDG.128) and coefficients (LDG.256), issued together.
 __device__ __forceinline__ Rec1 load_rec(const Spline1D& s, int i) {
   const double2 a = __ldg(s.xr + i);
@@ -124,8 +137,8 @@ __device__ __forceinline__ double bicubic_eval(const F2D& f, double x, double y,
   const int nk = f.gk.n;
   const double4* r0 = f.tab + (size_t)yi * nk + xi;
   const double4* r1 = r0 + nk;
-  const double4 c00 = ldg4(r0), c10 = ldg4(r0 + 1);  // (xmin,ymin) (xmax,ymin)
-  const double4 c01 = ldg4(r1), c11 = ldg4(r1 + 1);  // (xmin,ymax) (xmax,ymax)
+  const double4 c00 = CCLB_LDG4_PK(r0), c10 = CCLB_LDG4_PK(r0 + 1);  // (xmin,ymin) (xmax,ymin)
+  const double4 c01 = CCLB_LDG4_PK(r1), c11 = CCLB_LDG4_PK(r1 + 1);  // (xmin,ymax) (xmax,ymax)
   const double dx = ax.x1 - ax.x0, dy = ay.x1 - ay.x0;
   const double t = (x - ax.x0) * ax.inv_dx, u = (y - ay.x0) * ay.inv_dx;
   const double um = 1.0 - u;
