@@ -10,6 +10,7 @@ from .lowlevel import (CCLB200Error, LibBatch, LibCosmology, LibF2D, LibF3D, Lib
 from .cells import angular_cl  # noqa: F401,E402
 from .covariances import angular_cl_cov_cNG, angular_cl_cov_SSC  # noqa: F401,E402
 from .tk3d import Tk3D  # noqa: F401,E402
+from .correlations import CorrelationMethods, CorrelationTypes, correlation  # noqa: F401,E402
 from .cosmology import (Cosmology, CosmologyCalculator, CosmologyVanillaLCDM, get_table_builder,  # noqa: F401,E402
                         set_table_builder)
 from .errors import CCLError, CCLWarning, update_warning_verbosity  # noqa: F401,E402

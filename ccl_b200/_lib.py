@@ -20,6 +20,8 @@ F2D_CCLGROWTH = 401
 F2D_CONSTANTGROWTH = 403
 F2D_NO_EXTRAPOL = 404
 ERROR_CUDA = 2001
+CORR_LGNDRE, CORR_FFTLOG, CORR_BESSEL = 1001, 1002, 1003   # include/ccl_correlation.h:6-8
+CORR_GG, CORR_GL, CORR_LP, CORR_LM = 2001, 2002, 2003, 2004  # :9-12
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -31,7 +33,9 @@ class Params(C.Structure):
     _fields_ = [("K_MAX", C.c_double), ("K_MIN", C.c_double), ("DLOGK_INTEGRATION", C.c_double),
                 ("INTEGRATION_LIMBER_EPSREL", C.c_double), ("N_ITERATION", C.c_int),
                 ("INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS", C.c_int), ("A_SPLINE_MIN", C.c_double),
-                ("DCHI_INTEGRATION", C.c_double)]
+                ("DCHI_INTEGRATION", C.c_double), ("ELL_MIN_CORR", C.c_double), ("ELL_MAX_CORR", C.c_double),
+                ("N_ELL_CORR", C.c_int), ("INTEGRATION_GAUSS_KRONROD_POINTS", C.c_int),
+                ("INTEGRATION_EPSREL", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/ccl_b200.h
@@ -94,6 +98,7 @@ SIGNATURES = {
     "ccl_b200_f3d_new": (_vp, [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_double, C.c_int, _ip]),
     "ccl_b200_f3d_free": (None, [_vp]),
+    "ccl_b200_correlation": (None, [_vp, C.c_int, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, _ip]),
     "ccl_b200_angular_cl_covariance": (None, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int,
                                               C.c_int, C.c_int, _dp, _dp, C.c_double, _ip]),
     "ccl_b200_batch_angular_cls_limber_start": (None, [_vp, C.c_int, _ip, _ip, C.c_int, _ip, _ip, C.c_int, _dp,

@@ -317,7 +317,10 @@ class Cosmology:
                                     N_ITERATION=gp["N_ITERATION"], A_SPLINE_MIN=sp["A_SPLINE_MIN"],
                                     INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS=gp[
                                         "INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS"],
-                                    DCHI_INTEGRATION=sp["DCHI_INTEGRATION"])
+                                    DCHI_INTEGRATION=sp["DCHI_INTEGRATION"], ELL_MIN_CORR=sp["ELL_MIN_CORR"],
+                                    ELL_MAX_CORR=sp["ELL_MAX_CORR"], N_ELL_CORR=sp["N_ELL_CORR"],
+                                    INTEGRATION_GAUSS_KRONROD_POINTS=gp["INTEGRATION_GAUSS_KRONROD_POINTS"],
+                                    INTEGRATION_EPSREL=gp["INTEGRATION_EPSREL"])
 
     def chi_max_nokernel(self):
         """chi(A_SPLINE_MIN): chi_max of kernel-less tracers (src/ccl_tracers.c:632)."""

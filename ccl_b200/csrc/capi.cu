@@ -987,6 +987,8 @@ void ccl_b200_default_params(ccl_b200_params* p) {
   p->INTEGRATION_LIMBER_EPSREL = 1e-4; p->N_ITERATION = 1000; p->A_SPLINE_MIN = 0.1;
   p->INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS = 4;  // GSL_INTEG_GAUSS41 (src/ccl_core.c:40)
   p->DCHI_INTEGRATION = 5.0;
+  p->ELL_MIN_CORR = 0.01; p->ELL_MAX_CORR = 60000; p->N_ELL_CORR = 5000;  // src/ccl_core.c:129-131
+  p->INTEGRATION_GAUSS_KRONROD_POINTS = 4; p->INTEGRATION_EPSREL = 1e-4;  // src/ccl_core.c:69-70
 }
 
 // gsl_integration_qag takes the rule key from the parameters (src/ccl_cls.c:240); the device has GK41 only
@@ -1270,6 +1272,107 @@ void ccl_b200_angular_cl_covariance(ccl_b200_cosmology* cosmo, ccl_b200_collecti
   if (st[0]) {
     *status = CCL_B200_ERROR_INTEG;
     set_err("ccl_cls.c: ccl_angular_cov_limber(); integration error\n");
+  }
+}
+
+// ccl_correlation (src/ccl_correlation.c:410-428)
+void ccl_b200_correlation(ccl_b200_cosmology* cosmo, int n_ell, const double* ell, const double* cls, int n_theta,
+                          const double* theta, double* wtheta, int corr_type, int do_taper_cl,
+                          const double* taper_cl_limits, int flag_method, int* status) {
+  if (!cosmo || !ell || !cls || !theta || !wtheta || (do_taper_cl && !taper_cl_limits)) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    return;
+  }
+  if (*status) return;
+  std::lock_guard<std::mutex> lk(cosmo->mu);
+  const ccl_b200_params& par = cosmo->params;
+  if (flag_method != CORR_FFTLOG && flag_method != CORR_LGNDRE && flag_method != CORR_BESSEL) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("ccl_correlation.c: ccl_correlation(): Unknown algorithm\n");
+    return;
+  }
+  if (flag_method == CORR_LGNDRE && (corr_type == CORR_LM || corr_type == CORR_LP)) {
+    *status = CCL_B200_ERROR_NOT_IMPLEMENTED;
+    set_err("ccl_correlation.c: ccl_tracer_corr_legendre(): CCL does not support full-sky xi+- calcuations.\n");
+    return;
+  }
+  if (flag_method == CORR_BESSEL && par.INTEGRATION_GAUSS_KRONROD_POINTS != 4) {
+    *status = CCL_B200_ERROR_NOT_IMPLEMENTED;
+    set_err("ccl_b200: only the 41-point Gauss-Kronrod rule (GSL_INTEG_GAUSS41 = 4) is built on the device");
+    return;
+  }
+  // ccl_f1d_t_new(n_ell, ell, cls, cls[0], 0, extrap_const, extrap_logx_logy): gsl_spline_alloc(akima) needs 5
+  // nodes; the power-law slope needs a same-sign last pair (src/ccl_f1d.c:97-102).  A missing spline is
+  // CCL_ERROR_SPLINE for FFTLog (its status is tested first, :73-81) and CCL_ERROR_MEMORY otherwise (:190-197)
+  const bool bad_nodes = n_ell < 5;
+  const bool bad_slope = !bad_nodes && ((cls[n_ell - 1] * cls[n_ell - 2] <= 0) || (ell[n_ell - 1] * ell[n_ell - 2] <= 0));
+  if (bad_nodes || bad_slope) {
+    *status = (flag_method == CORR_FFTLOG && !bad_nodes) ? CCL_B200_ERROR_SPLINE : CCL_B200_ERROR_MEMORY;
+    set_err("ccl_correlation.c: ccl_tracer_corr_*(): failed to create spline\n");
+    return;
+  }
+  const int N = par.N_ELL_CORR;
+  std::vector<double> l_arr;
+  double L = 0.0;
+  if (flag_method == CORR_FFTLOG) {
+    // ccl_log_spacing (src/ccl_utils.c:109-148): running product with the end points overwritten
+    if (N < 5 || !(par.ELL_MIN_CORR > 0 && par.ELL_MAX_CORR > 0)) {
+      *status = CCL_B200_ERROR_LINSPACE;
+      set_err("ccl_correlation.c: ccl_tracer_corr_fftlog(): ran out of memory\n");
+      return;
+    }
+    l_arr.resize(N);
+    const double xratio = exp((log(par.ELL_MAX_CORR) - log(par.ELL_MIN_CORR)) / (N - 1.));
+    l_arr[0] = par.ELL_MIN_CORR;
+    for (int i = 1; i < N - 1; ++i) l_arr[i] = l_arr[i - 1] * xratio;
+    l_arr[N - 1] = par.ELL_MAX_CORR;
+    L = log(l_arr[N - 1] / l_arr[0]) * N / (N - 1.);
+  }
+  if (n_theta == 0) return;
+  const int device = cosmo->ts.device;
+  if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice", status)) return;
+  DeviceScratch& sc = scratch_for(device);
+  std::lock_guard<std::mutex> lk2(sc.mu);
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t o_ell = 0;
+  const size_t o_cls = o_ell + up((size_t)n_ell * 8);
+  const size_t o_th = o_cls + up((size_t)n_ell * 8);
+  const size_t o_la = o_th + up((size_t)n_theta * 8);
+  const size_t o_out = o_la + up(l_arr.size() * 8);
+  const size_t o_st = o_out + up((size_t)n_theta * 8);
+  const size_t o_wk = o_st + 256;
+  const size_t total = o_wk + correlation_work_bytes(flag_method, n_ell, n_theta, N, par.ELL_MAX_CORR, par.N_ITERATION);
+  if (!sc.call.reserve(total, status)) return;
+  char* base = sc.call.p;
+  cudaMemcpyAsync(base + o_ell, ell, (size_t)n_ell * 8, cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_cls, cls, (size_t)n_ell * 8, cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(base + o_th, theta, (size_t)n_theta * 8, cudaMemcpyHostToDevice, 0);
+  if (!l_arr.empty()) cudaMemcpyAsync(base + o_la, l_arr.data(), l_arr.size() * 8, cudaMemcpyHostToDevice, 0);
+  cudaMemsetAsync(base + o_st, 0, 256, 0);
+  CorrProblem P;
+  memset(&P, 0, sizeof(P));
+  P.ell = reinterpret_cast<const double*>(base + o_ell);
+  P.cls = reinterpret_cast<const double*>(base + o_cls);
+  P.theta = reinterpret_cast<const double*>(base + o_th);
+  P.l_arr = reinterpret_cast<const double*>(base + o_la);
+  P.n_ell = n_ell; P.n_theta = n_theta; P.n_ell_corr = N; P.corr_type = corr_type; P.method = flag_method;
+  P.do_taper = do_taper_cl ? 1 : 0; P.n_iteration = par.N_ITERATION;
+  if (do_taper_cl) for (int i = 0; i < 4; ++i) P.taper[i] = taper_cl_limits[i];
+  P.ell_max_corr = par.ELL_MAX_CORR; P.epsrel = par.INTEGRATION_EPSREL; P.L = L;
+  P.der_hi = log(cls[n_ell - 1] / cls[n_ell - 2]) / log(ell[n_ell - 1] / ell[n_ell - 2]);
+  P.x_ini = ell[0]; P.x_end = ell[n_ell - 1]; P.y0 = cls[0]; P.y_end = cls[n_ell - 1];
+  P.k0 = l_arr.empty() ? 0.0 : l_arr[0];
+  P.wtheta = reinterpret_cast<double*>(base + o_out);
+  P.status = reinterpret_cast<int*>(base + o_st);
+  P.work = base + o_wk;
+  if (!cuda_ok(launch_correlation(P, 0), "launch_correlation", status)) return;
+  int dst = 0;
+  cudaMemcpyAsync(wtheta, base + o_out, (size_t)n_theta * 8, cudaMemcpyDeviceToHost, 0);
+  cudaMemcpyAsync(&dst, base + o_st, sizeof(int), cudaMemcpyDeviceToHost, 0);
+  if (!cuda_ok(cudaStreamSynchronize(0), "ccl_b200_correlation", status)) return;
+  if (dst) {  // the reference keeps the results and ORs the GSL codes into the status (src/ccl_correlation.c:243-251)
+    *status = dst;
+    set_err("ccl_correlation.c: ccl_tracer_corr_bessel(): GSL integration status %d\n", dst);
   }
 }
 

@@ -12,17 +12,13 @@
 
 #include "akima_integ.cuh"
 #include "device_eval.cuh"
-#include "gk41_table.h"
+#include "qag_warp.cuh"
 
 namespace cclb {
 
 namespace {
 
 constexpr int CW = 4;  // warps per CTA
-
-__constant__ double v_xgk[21];
-__constant__ double v_wgk[21];
-__constant__ double v_wg[10];
 
 // ccl_find_a_index (src/ccl_f3d.c:46-88): interval [a_i, a_{i+1}) holding a; na-1 at and above the last node
 __device__ __forceinline__ int find_a_index(const F3D& f, double a) {
@@ -141,11 +137,6 @@ __device__ double cov_integrand(const CovProblem& P, double l1, double l2, doubl
   return d1 * d2 * d3 * d4 * tkk * ker / pow(chi, (double)P.chipow);
 }
 
-__device__ __forceinline__ int first_nonzero(int st) {
-  const unsigned bad = __ballot_sync(0xffffffffu, st != 0);
-  return bad ? __shfl_sync(0xffffffffu, st, __ffs(bad) - 1) : 0;
-}
-
 __device__ __forceinline__ void cov_finish(const CovProblem& P, int i1, int i2, double result, int st, int lane) {
   if (lane != 0) return;
   const size_t o = (size_t)i1 + (size_t)P.nl1 * i2;  // cov_out[lind1 + nl1 * lind2]
@@ -155,64 +146,6 @@ __device__ __forceinline__ void cov_finish(const CovProblem& P, int i1, int i2, 
     atomicCAS(P.status, 0, (int)ST_ERR_INTEG);
     atomicCAS(P.status + 1, 0, st);
   }
-}
-
-// rescale_error (gsl integration/qk.c)
-__device__ __forceinline__ double c_rescale_error(double err, double result_abs, double result_asc) {
-  err = fabs(err);
-  if (result_asc != 0 && err != 0) {
-    const double scale = pow((200 * err / result_asc), 1.5);
-    err = (scale < 1) ? result_asc * scale : result_asc;
-  }
-  if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
-    const double min_err = 50 * DBL_EPSILON * result_abs;
-    if (min_err > err) err = min_err;
-  }
-  return err;
-}
-
-// gsl_integration_qk with the 41-point rule on [a, b]: the abscissae over the lanes (two passes), four shuffle-reduced sums
-__device__ void cov_qk41(const CovProblem& P, double l1, double l2, double a, double b, double* fv, int lane,
-                         double& result, double& abserr, double& resabs, double& resasc, int& st) {
-  const double center = 0.5 * (a + b), half_length = 0.5 * (b - a);
-  for (int e = lane; e < 41; e += 32) {
-    double xq;
-    if (e == 40) xq = center;
-    else if (e < 20) xq = center - half_length * v_xgk[e];
-    else xq = center + half_length * v_xgk[e - 20];
-    int s1 = 0;
-    fv[e] = cov_integrand(P, l1, l2, xq, s1);
-    if (s1 && !st) st = s1;
-  }
-  st = first_nonzero(st);
-  __syncwarp();
-  double rk = 0, rg = 0, ra = 0, f1 = 0, f2 = 0;
-  if (lane < 20) {
-    f1 = fv[lane];
-    f2 = fv[lane + 20];
-    const double fsum = f1 + f2;
-    rk = v_wgk[lane] * fsum;
-    ra = v_wgk[lane] * (fabs(f1) + fabs(f2));
-    if (lane & 1) rg = v_wg[lane >> 1] * fsum;
-  } else if (lane == 20) {
-    f1 = fv[40];
-    rk = f1 * v_wgk[20];
-    ra = fabs(rk);
-  }
-  rk = warp_sum(rk);
-  rg = warp_sum(rg);
-  ra = warp_sum(ra);
-  const double mean = rk * 0.5;
-  double rs = 0;
-  if (lane < 20) rs = v_wgk[lane] * (fabs(f1 - mean) + fabs(f2 - mean));
-  else if (lane == 20) rs = v_wgk[20] * fabs(f1 - mean);
-  rs = warp_sum(rs);
-  const double err = (rk - rg) * half_length;
-  result = rk * half_length;
-  resabs = ra * fabs(half_length);
-  resasc = rs * fabs(half_length);
-  abserr = c_rescale_error(err, resabs, resasc);
-  __syncwarp();
 }
 
 }  // namespace
@@ -236,7 +169,7 @@ __global__ void __launch_bounds__(CW * 32) cov_spline_kernel(const CovProblem P,
       sf[s] = cov_integrand(P, l1, l2, chi, s1);
       if (s1) st = s1;
     }
-    st = first_nonzero(st);
+    st = qagw_first_nonzero(st);
     __syncwarp();
     double acc = 0.0;
     if (!st) acc = akima_integral_uniform(sf, nchi, P.chimin, P.chimax, dx, lane);
@@ -250,97 +183,15 @@ __global__ void __launch_bounds__(CW * 32) cov_spline_kernel(const CovProblem P,
 __global__ void __launch_bounds__(CW * 32) cov_qag_kernel(const CovProblem P, double* ws, int limit, double epsrel) {
   __shared__ double s_fv[CW][41];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned FULL = 0xffffffffu;
   const long long gw = (long long)blockIdx.x * CW + warp, nw = (long long)gridDim.x * CW;
-  double* alist = ws + (size_t)gw * 4 * limit;
-  double* blist = alist + limit;
-  double* rlist = blist + limit;
-  double* elist = rlist + limit;
-  double* fv = s_fv[warp];
   const long long nel = (long long)P.nl1 * P.nl2;
   for (long long el = gw; el < nel; el += nw) {
     const int i1 = (int)(el % P.nl1), i2 = (int)(el / P.nl1);
     const double l1 = P.l1[i1], l2 = P.l2[i2];
-    const double epsabs = 0.0;
+    auto f = [&](double chi, int& s1) { return cov_integrand(P, l1, l2, chi, s1); };
     int st = 0, gsl = 0;
-    double result = 0.0;
-    if (epsabs <= 0 && (epsrel < 50 * DBL_EPSILON || epsrel < 0.5e-28)) gsl = ST_GSL_EBADTOL;
-    else {
-      double r0, e0, ab0, as0;
-      cov_qk41(P, l1, l2, P.chimin, P.chimax, fv, lane, r0, e0, ab0, as0, st);
-      double tolerance = fmax(epsabs, epsrel * fabs(r0));
-      const double round_off = 50 * DBL_EPSILON * ab0;
-      result = r0;
-      if (e0 <= round_off && e0 > tolerance) gsl = ST_GSL_EROUND;
-      else if ((e0 <= tolerance && e0 != as0) || e0 == 0.0) gsl = 0;
-      else if (limit == 1) gsl = ST_GSL_EMAXITER;
-      else {
-        __syncwarp();
-        if (lane == 0) { alist[0] = P.chimin; blist[0] = P.chimax; rlist[0] = r0; elist[0] = e0; }
-        __syncwarp();
-        int size = 1;
-        double area = r0, errsum = e0;
-        int iteration = 1, roundoff_type1 = 0, roundoff_type2 = 0, error_type = 0;
-        do {
-          // retrieve(): interval with the largest error estimate
-          double emax = -1.0;
-          int imax = 0;
-          for (int i = lane; i < size; i += 32) {
-            const double e = elist[i];
-            if (e > emax) { emax = e; imax = i; }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double eo = __shfl_xor_sync(FULL, emax, o);
-            const int io = __shfl_xor_sync(FULL, imax, o);
-            if (eo > emax || (eo == emax && io < imax)) { emax = eo; imax = io; }
-          }
-          const double a_i = alist[imax], b_i = blist[imax], r_i = rlist[imax], e_i = elist[imax];
-          const double a1 = a_i, b1 = 0.5 * (a_i + b_i), a2 = b1, b2 = b_i;
-          double ar[2], er[2], rab[2], ras[2];
-          cov_qk41(P, l1, l2, a1, b1, fv, lane, ar[0], er[0], rab[0], ras[0], st);
-          cov_qk41(P, l1, l2, a2, b2, fv, lane, ar[1], er[1], rab[1], ras[1], st);
-          const double area12 = ar[0] + ar[1];
-          const double error12 = er[0] + er[1];
-          errsum += (error12 - e_i);
-          area += area12 - r_i;
-          if (ras[0] != er[0] && ras[1] != er[1]) {
-            const double delta = r_i - area12;
-            if (fabs(delta) <= 1.0e-5 * fabs(area12) && error12 >= 0.99 * e_i) roundoff_type1++;
-            if (iteration >= 10 && error12 > e_i) roundoff_type2++;
-          }
-          tolerance = fmax(epsabs, epsrel * fabs(area));
-          if (errsum > tolerance) {
-            if (roundoff_type1 >= 6 || roundoff_type2 >= 20) error_type = 2;
-            const double tmp = (1 + 100 * DBL_EPSILON) * (fabs(a2) + 1000 * DBL_MIN);  // subinterval_too_small
-            if (fabs(a1) <= tmp && fabs(b2) <= tmp) error_type = 3;
-          }
-          // update(): larger-error half stays at imax, the other is appended
-          __syncwarp();
-          if (lane == 0) {
-            if (er[1] > er[0]) {
-              alist[imax] = a2; rlist[imax] = ar[1]; elist[imax] = er[1];
-              alist[size] = a1; blist[size] = b1; rlist[size] = ar[0]; elist[size] = er[0];
-            } else {
-              blist[imax] = b1; rlist[imax] = ar[0]; elist[imax] = er[0];
-              alist[size] = a2; blist[size] = b2; rlist[size] = ar[1]; elist[size] = er[1];
-            }
-          }
-          __syncwarp();
-          size++;
-          iteration++;
-          if (st) break;
-        } while (iteration < limit && !error_type && errsum > tolerance);
-        double sum = 0.0;
-        for (int i = lane; i < size; i += 32) sum += rlist[i];
-        result = warp_sum(sum);
-        if (errsum <= tolerance) gsl = 0;
-        else if (error_type == 2) gsl = ST_GSL_EROUND;
-        else if (error_type == 3) gsl = ST_GSL_ESING;
-        else if (iteration == limit) gsl = ST_GSL_EMAXITER;
-        else gsl = ST_GSL_EFAILED;
-      }
-    }
+    const double result = qagw_qag41(f, P.chimin, P.chimax, 0.0, epsrel, limit, ws + (size_t)gw * 4 * limit,
+                                     s_fv[warp], lane, gsl, st);
     cov_finish(P, i1, i2, result, st ? st : gsl, lane);
     __syncwarp();
   }
@@ -360,13 +211,7 @@ cudaError_t launch_covariance(const CovProblem& prob, int method, int nchi, int 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static bool uploaded[64] = {false};
-  if (!uploaded[dev & 63]) {
-    cudaMemcpyToSymbol(v_xgk, GK41_XGK, sizeof(double) * 21);
-    cudaMemcpyToSymbol(v_wgk, GK41_WGK, sizeof(double) * 21);
-    cudaMemcpyToSymbol(v_wg, GK41_WG, sizeof(double) * 10);
-    uploaded[dev & 63] = true;
-  }
+  qagw_upload_tables();
   const long long nel = (long long)prob.nl1 * prob.nl2;
   const int nblk = (int)std::min<long long>((nel + CW - 1) / CW, (long long)sms * 4);
   if (method == INTEG_SPLINE) cov_spline_kernel<<<nblk, CW * 32, 0, stream>>>(prob, scratch, nchi);

@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <cstdio>
 
+#include "akima_coef.cuh"
 #include "akima_integ.cuh"
 #include "device_eval.cuh"
 #include "gk41_table.h"
@@ -25,37 +26,10 @@ __global__ void akima_coef_kernel(const AkimaJob* jobs) {
   const int n = jb.n;
   const double* x = jb.x;
   const double* y = jb.y;
-  auto slope = [&](int j) -> double {  // m[j], j in [-2, n]
-    auto raw = [&](int q) { return (y[q + 1] - y[q]) / (x[q + 1] - x[q]); };
-    if (j >= 0 && j <= n - 2) return raw(j);
-    if (j == -1) return 2.0 * raw(0) - raw(1);
-    if (j == -2) return 3.0 * raw(0) - 2.0 * raw(1);
-    if (j == n - 1) return 2.0 * raw(n - 2) - raw(n - 3);
-    return 3.0 * raw(n - 2) - 2.0 * raw(n - 3);
-  };
   for (int i = threadIdx.x; i < n - 1; i += blockDim.x) {
-    const double mm2 = slope(i - 2), mm1 = slope(i - 1), m0 = slope(i), mp1 = slope(i + 1),
-                 mp2 = slope(i + 2);
-    const double NE = fabs(mp1 - m0) + fabs(mm1 - mm2);
-    double b, c, d;
-    if (NE == 0.0) {
-      b = m0; c = 0.0; d = 0.0;
-    } else {
-      const double h_i = x[i + 1] - x[i];
-      const double NE_next = fabs(mp2 - mp1) + fabs(m0 - mm1);
-      const double alpha_i = fabs(mm1 - mm2) / NE;
-      double tL_ip1;
-      if (NE_next == 0.0) tL_ip1 = m0;
-      else {
-        const double alpha_ip1 = fabs(m0 - mm1) / NE_next;
-        tL_ip1 = (1.0 - alpha_ip1) * m0 + alpha_ip1 * mp1;
-      }
-      b = (1.0 - alpha_i) * mm1 + alpha_i * m0;
-      c = (3.0 * m0 - 2.0 * b - tL_ip1) / h_i;
-      d = (b + tL_ip1 - 2.0 * m0) / (h_i * h_i);
-    }
+    const double4 c = akima_interval_coef(x, y, n, i);
     jb.xr[i] = make_double2(x[i], x[i + 1]);
-    jb.cr[i] = make_double4(y[i], b, c, d);
+    jb.cr[i] = c;
   }
 }
 

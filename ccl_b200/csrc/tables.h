@@ -162,6 +162,32 @@ size_t covariance_scratch_bytes(int nchi, int n_iteration);
 cudaError_t launch_covariance(const CovProblem& prob, int method, int nchi, int n_iteration, double epsrel,
                               double* scratch, cudaStream_t stream);
 
+// ---- C_ell -> xi(theta): ccl_correlation (src/ccl_correlation.c:14-440), SURVEY 8f-4 ----
+enum CorrKind : int {
+  CORR_LGNDRE = 1001, CORR_FFTLOG = 1002, CORR_BESSEL = 1003,      // include/ccl_correlation.h:6-8
+  CORR_GG = 2001, CORR_GL = 2002, CORR_LP = 2003, CORR_LM = 2004,  // :9-12
+};
+struct CorrProblem {
+  // inputs on the device
+  const double* ell;      // [n_ell]
+  const double* cls;      // [n_ell]
+  const double* theta;    // [n_theta], degrees
+  const double* l_arr;    // [n_ell_corr] ccl_log_spacing(ELL_MIN_CORR, ELL_MAX_CORR, N_ELL_CORR) (FFTLog only)
+  int n_ell, n_theta, n_ell_corr, corr_type, method, do_taper, n_iteration, pad;
+  double taper[4];
+  double ell_max_corr, epsrel;
+  double L;               // log(l_arr[N-1] / l_arr[0]) * N / (N - 1)  (src/ccl_fftlog.c:206)
+  double der_hi;          // logx_logy slope of the C_ell spline above its last node (src/ccl_f1d.c:97-102)
+  double x_ini, x_end, y0, y_end;  // ell[0], ell[n-1], cls[0], cls[n-1] (host copies of the spline's end values)
+  double k0;              // l_arr[0]
+  // outputs / work space on the device
+  double* wtheta;         // [n_theta]
+  int* status;            // [1]: OR of the GSL codes of the 'bessel' integrals
+  char* work;             // correlation_work_bytes()
+};
+size_t correlation_work_bytes(int method, int n_ell, int n_theta, int n_ell_corr, double ell_max_corr, int n_iteration);
+cudaError_t launch_correlation(const CorrProblem& prob, cudaStream_t stream);
+
 // ---- fast 'spline' path: ln k node grids shared by the pairs of one cosmology ----
 // Two pairs of one cosmology share a node grid for every ell when their (chi_min, chi_max) from
 // get_k_interval (src/ccl_cls.c:64-100) coincide; a(chi), k P(k,a) and each collection's

@@ -22,9 +22,11 @@ def _check(status, where=""):
 
 def make_params(K_MAX=1e3, K_MIN=5e-5, DLOGK_INTEGRATION=0.025, INTEGRATION_LIMBER_EPSREL=1e-4,
                 N_ITERATION=1000, A_SPLINE_MIN=0.1, INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS=4,
-                DCHI_INTEGRATION=5.0):
+                DCHI_INTEGRATION=5.0, ELL_MIN_CORR=0.01, ELL_MAX_CORR=60000.0, N_ELL_CORR=5000,
+                INTEGRATION_GAUSS_KRONROD_POINTS=4, INTEGRATION_EPSREL=1e-4):
     return _lib.Params(K_MAX, K_MIN, DLOGK_INTEGRATION, INTEGRATION_LIMBER_EPSREL, N_ITERATION,
-                       INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS, A_SPLINE_MIN, DCHI_INTEGRATION)
+                       INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS, A_SPLINE_MIN, DCHI_INTEGRATION, ELL_MIN_CORR,
+                       ELL_MAX_CORR, int(N_ELL_CORR), int(INTEGRATION_GAUSS_KRONROD_POINTS), INTEGRATION_EPSREL)
 
 
 def _tracer_args(sub):
@@ -240,6 +242,20 @@ def angular_cl_covariance(cosmo, trs1, trs2, trs3, trs4, tsp, ell1, ell2, method
     for c in colls:
         L.ccl_b200_cl_tracer_collection_t_free(c)
     return out.reshape(len(k2), len(k1)), st.value
+
+
+def correlation(cosmo, ell, cls, theta, corr_type, method, taper_cl_limits=None):
+    """ccl_correlation through the C entry (theta in degrees).  Returns (wtheta, status)."""
+    L = _lib.load()
+    st = C.c_int(0)
+    ke, pe = darr(ell)
+    kc, pc = darr(cls)
+    kt, pt = darr(np.atleast_1d(theta))
+    kl, pl = darr(taper_cl_limits)
+    out = np.full(len(kt), np.nan)
+    L.ccl_b200_correlation(cosmo.h, len(ke), pe, pc, len(kt), pt, out.ctypes.data_as(_lib._dp), int(corr_type),
+                           int(kl is not None), pl, int(method), C.byref(st))
+    return out, st.value
 
 
 class LibBatch:

@@ -24,6 +24,7 @@ extern "C" {
 
 /* status codes shared with the reference (include/ccl_error.h:10-48) */
 #define CCL_B200_ERROR_MEMORY 1025
+#define CCL_B200_ERROR_LINSPACE 1026
 #define CCL_B200_ERROR_INCONSISTENT 1027
 #define CCL_B200_ERROR_SPLINE 1028
 #define CCL_B200_ERROR_SPLINE_EV 1029
@@ -65,6 +66,12 @@ typedef struct {
   int INTEGRATION_LIMBER_GAUSS_KRONROD_POINTS;
   double A_SPLINE_MIN;              /* 0.1: chi_max of kernel-less tracers = chi(A_SPLINE_MIN) */
   double DCHI_INTEGRATION;          /* 5.0: chi sampling of the covariance 'spline' method (src/ccl_cls.c:418) */
+  /* read by ccl_b200_correlation (src/ccl_correlation.c:54-57,243-246; defaults src/ccl_core.c:69-70,129-131) */
+  double ELL_MIN_CORR;              /* 0.01  */
+  double ELL_MAX_CORR;              /* 60000 */
+  int N_ELL_CORR;                   /* 5000  */
+  int INTEGRATION_GAUSS_KRONROD_POINTS; /* GSL key of the 'bessel' method's QAG rule; 4 = GK41, the only one built */
+  double INTEGRATION_EPSREL;        /* 1e-4  */
 } ccl_b200_params;
 
 /* ---- library ---- */
@@ -171,6 +178,15 @@ void ccl_b200_angular_cl_covariance(ccl_b200_cosmology *cosmo, ccl_b200_collecti
                                     const double *l1_out, int nl2_out, const double *l2_out, double *cov_out,
                                     int integration_method, int chi_exponent, int n_ker, const double *a_ker,
                                     const double *f_ker, double prefactor_extra, int *status);
+
+/* ---- C_ell -> xi(theta) ----
+ * ccl_correlation (include/ccl_correlation.h:14-44, src/ccl_correlation.c:410-428), argument for argument:
+ * flag_method CCL_CORR_LGNDRE / _FFTLOG / _BESSEL = 1001 / 1002 / 1003, corr_type CCL_CORR_GG / _GL / _LP / _LM =
+ * 2001..2004, theta in degrees.  pyccl binds it through correlation_vec (pyccl/ccl_correlation.i:51-64:
+ * do_taper_cl = 0, taper_cl_limits = NULL).  cosmo supplies the spline / gsl parameters only. */
+void ccl_b200_correlation(ccl_b200_cosmology *cosmo, int n_ell, const double *ell, const double *cls, int n_theta,
+                          const double *theta, double *wtheta, int corr_type, int do_taper_cl,
+                          const double *taper_cl_limits, int flag_method, int *status);
 
 /* A batch owns one HBM arena holding the table packs of ncosmo cosmologies.  Slots are filled
  * with the same flat arrays as the single-object constructors, then committed (one H2D copy of

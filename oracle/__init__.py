@@ -96,6 +96,10 @@ def lib():
         L.o_angular_cl_covariance.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int,
                                               C.POINTER(vp), C.c_int, C.POINTER(vp), vp, C.c_int, _dp, C.c_int, _dp,
                                               _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double, _ip]
+        L.o_correlation.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_double,
+                                    C.c_double, C.c_int, C.c_double, C.c_int, _ip]
+        L.o_lngamma_complex.argtypes = [C.c_double, C.c_double, _dp, _dp]
+        L.o_fftlog_fht.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
         L.o_get_k_interval_pub.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp),
                                            C.c_double, _dp, _dp]
         L.o_set_lkmin_ulps.argtypes = [C.c_int]
@@ -374,6 +378,45 @@ def angular_cl(cosmo, trc1, trc2, psp, ells, method=INTEG_SPLINE, each=False, re
     if return_neval:
         return cl, st.value, nev
     return cl, st.value
+
+
+CORR_LGNDRE, CORR_FFTLOG, CORR_BESSEL = 1001, 1002, 1003       # include/ccl_correlation.h:6-8
+CORR_GG, CORR_GL, CORR_LP, CORR_LM = 2001, 2002, 2003, 2004      # :9-12
+CORR_METHODS = {"fftlog": CORR_FFTLOG, "bessel": CORR_BESSEL, "legendre": CORR_LGNDRE}
+CORR_TYPES = {"NN": CORR_GG, "NG": CORR_GL, "GG+": CORR_LP, "GG-": CORR_LM}
+
+
+def correlation(ell, cls, theta, corr_type="NN", method="fftlog", taper_cl_limits=None, ell_min_corr=0.01,
+                ell_max_corr=60000.0, n_ell_corr=5000, epsrel=1e-4, n_iteration=1000):
+    """ccl_correlation (src/ccl_correlation.c:410-428); theta in degrees.  Returns (wtheta, status)."""
+    ell = np.ascontiguousarray(ell, dtype=np.float64)
+    cls = np.ascontiguousarray(cls, dtype=np.float64)
+    theta = np.ascontiguousarray(np.atleast_1d(theta), dtype=np.float64)
+    out = np.full(theta.size, np.nan)
+    st = C.c_int(0)
+    tl, ptl = _arr(taper_cl_limits)
+    lib().o_correlation(ell.size, ell.ctypes.data_as(_dp), cls.ctypes.data_as(_dp), theta.size,
+                        theta.ctypes.data_as(_dp), out.ctypes.data_as(_dp), CORR_TYPES.get(corr_type, corr_type),
+                        int(taper_cl_limits is not None), ptl, CORR_METHODS.get(method, method), float(ell_min_corr),
+                        float(ell_max_corr), int(n_ell_corr), float(epsrel), int(n_iteration), C.byref(st))
+    return out, st.value
+
+
+def lngamma_complex(zr, zi):
+    """gsl_sf_lngamma_complex_e restated: (ln|Gamma(z)|, arg Gamma(z) in (-pi, pi])."""
+    a, b = C.c_double(0), C.c_double(0)
+    lib().o_lngamma_complex(float(zr), float(zi), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def fftlog_fht(k, pk, dim, mu, q=0.0, kcrc=1.0, noring=1):
+    """fht of src/ccl_fftlog.c:199-328 for one array: returns (r, xi)."""
+    k = np.ascontiguousarray(k, dtype=np.float64)
+    pk = np.ascontiguousarray(pk, dtype=np.float64)
+    r, xi = np.empty_like(k), np.empty_like(k)
+    lib().o_fftlog_fht(k.size, k.ctypes.data_as(_dp), pk.ctypes.data_as(_dp), r.ctypes.data_as(_dp),
+                       xi.ctypes.data_as(_dp), float(dim), float(mu), float(q), float(kcrc), int(noring))
+    return r, xi
 
 
 def set_lkmin_ulps(n):

@@ -1754,6 +1754,367 @@ void o_get_k_interval_pub(const o_cosmo *cosmo, int n1, o_tracer *const *t1, int
   o_get_k_interval(cosmo, n1, t1, n2, t2, l, lkmin, lkmax);
 }
 
+/* ================================================================== */
+/* C_ell -> xi(theta): ccl_correlation (src/ccl_correlation.c:14-440),  */
+/* FFTLog (src/ccl_fftlog.c:53-106,199-328,525-530), SURVEY 8f-4       */
+/* ================================================================== */
+#define O_CORR_LGNDRE 1001
+#define O_CORR_FFTLOG 1002
+#define O_CORR_BESSEL 1003
+#define O_CORR_GG 2001
+#define O_CORR_GL 2002
+#define O_CORR_LP 2003
+#define O_CORR_LM 2004
+#define O_ERR_LINSPACE 1026
+
+/* ccl_f1d_t with the two extrapolation pairs ccl_correlation.c uses (src/ccl_f1d.c:15-191):
+ * below x_ini: constant y0; above x_end: constant yf, or y_end (x/x_end)^der_hi (logx_logy) */
+typedef struct {
+  o_akima *spl;
+  double y0, yf, x_ini, x_end, y_end, der_hi;
+  int hi_loglog;
+} o_f1dx;
+
+static void o_f1dx_free(o_f1dx *f) {
+  if (!f) return;
+  o_akima_free(f->spl);
+  free(f);
+}
+
+static o_f1dx *o_f1dx_new(int n, const double *x, const double *y, double y0, double yf, int hi_loglog,
+                          int *status) {
+  o_akima *s = o_akima_new(n, x, y); /* gsl_spline_alloc(akima, n < 5) fails: CCL_ERROR_MEMORY */
+  if (!s) { *status = O_ERR_MEMORY; return NULL; }
+  o_f1dx *f = calloc(1, sizeof(o_f1dx));
+  f->spl = s; f->y0 = y0; f->yf = yf; f->x_ini = x[0]; f->x_end = x[n - 1]; f->y_end = y[n - 1];
+  f->hi_loglog = hi_loglog;
+  if (hi_loglog) { /* src/ccl_f1d.c:97-102 */
+    if ((y[n - 1] * y[n - 2] <= 0) || (x[n - 1] * x[n - 2] <= 0)) *status = O_ERR_SPLINE;
+    else f->der_hi = log(y[n - 1] / y[n - 2]) / log(x[n - 1] / x[n - 2]);
+  }
+  if (*status) { o_f1dx_free(f); return NULL; }
+  return f;
+}
+
+static double o_f1dx_eval(const o_f1dx *f, double x) {
+  if (x <= f->x_ini) return f->y0;
+  else if (x >= f->x_end) return f->hi_loglog ? f->y_end * pow(x / f->x_end, f->der_hi) : f->yf;
+  double y;
+  if (o_akima_eval_e(f->spl, x, &y) != O_SUCCESS) return NAN;
+  return y;
+}
+
+/* taper_cl (src/ccl_correlation.c:20-39) */
+static void o_taper_cl(int n_ell, const double *ell, double *cl, const double *lim) {
+  for (int i = 0; i < n_ell; i++) {
+    if (ell[i] < lim[0] || ell[i] > lim[3]) { cl[i] = 0; continue; }
+    if (ell[i] >= lim[1] && ell[i] <= lim[2]) continue;
+    if (ell[i] < lim[1]) cl[i] *= cos((ell[i] - lim[1]) / (lim[1] - lim[0]) * M_PI / 2.);
+    if (ell[i] > lim[2]) cl[i] *= cos((ell[i] - lim[2]) / (lim[3] - lim[2]) * M_PI / 2.);
+  }
+}
+
+/* ccl_log_spacing (src/ccl_utils.c:109-148): running product, end points overwritten */
+static double *o_log_spacing(double xmin, double xmax, int N) {
+  if (N < 2 || !(xmin > 0 && xmax > 0)) return NULL;
+  const double dlog_x = (log(xmax) - log(xmin)) / (N - 1.);
+  double *x = malloc(sizeof(double) * N);
+  const double xratio = exp(dlog_x);
+  x[0] = xmin;
+  for (int i = 1; i < N - 1; i++) x[i] = x[i - 1] * xratio;
+  x[N - 1] = xmax;
+  return x;
+}
+
+/* GSL specfunc (not in /root/reference: libgsl >= 2.1, CMakeLists.txt:118), restated from the published
+ * algorithm: gsl_sf_lngamma_complex_e = Lanczos g = 7, 9 terms (gamma.c lngamma_lanczos_complex) for
+ * Re z > 1/2, the reflection formula with gsl_sf_complex_logsin_e (trig.c) otherwise; the phase is
+ * reduced to (-pi, pi]. */
+static const double o_lanczos_7_c[9] = {
+  0.99999999999980993227684700473478, 676.520368121885098567009190444019, -1259.13921672240287047156078755283,
+  771.3234287776530788486528258894, -176.61502916214059906584551354, 12.507343278686904814458936853,
+  -0.13857109526572011689554707, 9.984369578019570859563e-6, 1.50563273514931155834e-7};
+
+static double o_angle_restrict_symm(double theta) {
+  /* gsl_sf_angle_restrict_symm_err_e: 2 pi split in three parts */
+  const double P1 = 4 * 7.8539812564849853515625e-01, P2 = 4 * 3.7748947079307981766760e-08,
+               P3 = 4 * 2.6951514290790594840552e-15, TwoPi = 2 * (P1 + P2 + P3);
+  const double y = (theta >= 0 ? 1 : -1) * 2 * floor(fabs(theta) / TwoPi);
+  double r = ((theta - y * P1) - y * P2) - y * P3;
+  if (r > M_PI) r = (((r - 2 * P1) - 2 * P2) - 2 * P3);
+  else if (r < -M_PI) r = (((r + 2 * P1) + 2 * P2) + 2 * P3);
+  return r;
+}
+
+static void o_complex_log(double zr, double zi, double *lnr, double *theta) {
+  const double ax = fabs(zr), ay = fabs(zi);
+  const double mn = ax < ay ? ax : ay, mx = ax < ay ? ay : ax;
+  *lnr = log(mx) + 0.5 * log(1.0 + (mn / mx) * (mn / mx));
+  *theta = atan2(zi, zr);
+}
+
+static void o_lngamma_lanczos_complex(double zr, double zi, double *yr, double *yi) {
+  zr -= 1.0; /* Lanczos writes z! instead of Gamma(z) */
+  double Ag_r = o_lanczos_7_c[0], Ag_i = 0.0;
+  for (int k = 1; k <= 8; k++) {
+    const double R = zr + k, I = zi;
+    const double a = o_lanczos_7_c[k] / (R * R + I * I);
+    Ag_r += a * R;
+    Ag_i -= a * I;
+  }
+  double log1_r, log1_i, logAg_r, logAg_i;
+  o_complex_log(zr + 7.5, zi, &log1_r, &log1_i);
+  o_complex_log(Ag_r, Ag_i, &logAg_r, &logAg_i);
+  /* (z+0.5)*log(z+7.5) - (z+7.5) + LogRootTwoPi_ + log(Ag(z)) */
+  *yr = (zr + 0.5) * log1_r - zi * log1_i - (zr + 7.5) + 0.9189385332046727418 + logAg_r;
+  *yi = o_angle_restrict_symm(zi * log1_r + (zr + 0.5) * log1_i - zi + logAg_i);
+}
+
+static void o_complex_logsin(double zr, double zi, double *lszr, double *lszi) {
+  if (zi > 60.0) { *lszr = -M_LN2 + zi; *lszi = 0.5 * M_PI - zr; }
+  else if (zi < -60.0) { *lszr = -M_LN2 - zi; *lszi = -0.5 * M_PI + zr; }
+  else o_complex_log(sin(zr) * cosh(zi), cos(zr) * sinh(zi), lszr, lszi);
+  *lszi = o_angle_restrict_symm(*lszi);
+}
+
+void o_lngamma_complex(double zr, double zi, double *lnr, double *arg) {
+  if (zr <= 0.5) { /* reflection to the right half plane, stopping at 1/2 */
+    double a, b, lnsin_r, lnsin_i;
+    o_lngamma_lanczos_complex(1.0 - zr, -zi, &a, &b);
+    o_complex_logsin(M_PI * zr, M_PI * zi, &lnsin_r, &lnsin_i);
+    *lnr = 1.14472988584940017414 - lnsin_r - a; /* M_LNPI */
+    *arg = o_angle_restrict_symm(-lnsin_i - b);
+  } else
+    o_lngamma_lanczos_complex(zr, zi, lnr, arg);
+}
+
+/* goodkr (src/ccl_fftlog.c:72-86) */
+static double o_goodkr(int N, double mu, double q, double L, double kr) {
+  const double xp = (mu + 1 + q) / 2, xm = (mu + 1 - q) / 2, y = M_PI * N / (2 * L);
+  double lnr, argm, argp;
+  o_lngamma_complex(xp, y, &lnr, &argp);
+  o_lngamma_complex(xm, y, &lnr, &argm);
+  const double arg = log(2 / kr) * N / L + (argp + argm) / M_PI;
+  const double iarg = round(arg);
+  if (arg != iarg) kr *= exp((arg - iarg) * L / N);
+  return kr;
+}
+
+/* compute_u_coefficients (src/ccl_fftlog.c:95-125), q == 0 branch and the general one; u as (re, im) pairs */
+static void o_compute_u(int N, double mu, double q, double L, double kcrc, double *u) {
+  const double y = M_PI / L, k0r0 = kcrc * exp(-L), t = -2 * y * log(k0r0 / 2);
+  if (q == 0) {
+    const double x = (mu + 1) / 2;
+    for (int m = 0; m <= N / 2; m++) {
+      double lnr, phi;
+      o_lngamma_complex(x, m * y, &lnr, &phi);
+      u[2 * m] = 1.0 * cos(m * t + 2 * phi);
+      u[2 * m + 1] = 1.0 * sin(m * t + 2 * phi);
+    }
+  } else {
+    const double xp = (mu + 1 + q) / 2, xm = (mu + 1 - q) / 2;
+    for (int m = 0; m <= N / 2; m++) {
+      double lnrp, phip, lnrm, phim;
+      o_lngamma_complex(xp, m * y, &lnrp, &phip);
+      o_lngamma_complex(xm, -m * y, &lnrm, &phim);
+      const double r = exp(q * M_LN2 + lnrp - lnrm), ph = m * t + phip - phim;
+      u[2 * m] = r * cos(ph);
+      u[2 * m + 1] = r * sin(ph);
+    }
+  }
+  for (int m = N / 2 + 1; m < N; m++) { u[2 * m] = u[2 * (N - m)]; u[2 * m + 1] = -u[2 * (N - m) + 1]; }
+  if ((N % 2) == 0) u[2 * (N / 2) + 1] = 0.0;
+}
+
+/* fht (src/ccl_fftlog.c:199-328) for one input array.  FFTW (absent here) is replaced by the O(N^2)
+ * definition of the two DFTs it computes (forward sign -1, backward sign +1, unnormalised), with the
+ * twiddle factors tabulated once. */
+void o_fftlog_fht(int N, const double *k, const double *pk, double *r, double *xi, double dim, double mu,
+                  double q, double kcrc, int noring) {
+  const double L = log(k[N - 1] / k[0]) * N / (N - 1.);
+  if (noring) kcrc = o_goodkr(N, mu, q, L, kcrc);
+  double *u = malloc(sizeof(double) * 2 * N), *w = malloc(sizeof(double) * 2 * N);
+  double *a = malloc(sizeof(double) * N), *b = malloc(sizeof(double) * 2 * N), *c = malloc(sizeof(double) * N);
+  o_compute_u(N, mu, q, L, kcrc, u);
+  for (int j = 0; j < N; j++) { w[2 * j] = cos(2 * M_PI * j / N); w[2 * j + 1] = sin(2 * M_PI * j / N); }
+  const double k0r0 = kcrc * exp(-L);
+  r[0] = k0r0 / k[0];
+  for (int n = 1; n < N; n++) r[n] = r[0] * exp(n * L / N);
+  const double one_over_2pi_dhalf = pow(2 * M_PI, -dim / 2);
+  for (int i = 0; i < N; i++) a[i] = pow(k[i], dim / 2 - q) * pk[i];
+#pragma omp parallel for schedule(static)
+  for (int m = 0; m < N; m++) { /* b[m] = sum_i a[i] exp(-2 pi i m i / N), times u[m] / N */
+    double sr = 0, si = 0;
+    long idx = 0;
+    for (int i = 0; i < N; i++) {
+      sr += a[i] * w[2 * idx];
+      si -= a[i] * w[2 * idx + 1];
+      idx += m; if (idx >= N) idx -= N;
+    }
+    const double ur = u[2 * m] / (double)N, ui = u[2 * m + 1] / (double)N;
+    b[2 * m] = sr * ur - si * ui;
+    b[2 * m + 1] = sr * ui + si * ur;
+  }
+#pragma omp parallel for schedule(static)
+  for (int n = 0; n < N; n++) { /* Re sum_m b[m] exp(+2 pi i m n / N) */
+    double sr = 0;
+    long idx = 0;
+    for (int m = 0; m < N; m++) {
+      sr += b[2 * m] * w[2 * idx] - b[2 * m + 1] * w[2 * idx + 1];
+      idx += n; if (idx >= N) idx -= N;
+    }
+    c[n] = sr;
+  }
+  for (int i = 0; i < N; i++) /* reversed array, prefactor */
+    xi[i] = one_over_2pi_dhalf * pow(r[i], -dim / 2 - q) * c[N - 1 - i];
+  free(u); free(w); free(a); free(b); free(c);
+}
+
+static int o_corr_bessel_order(int corr_type) {
+  if (corr_type == O_CORR_GL) return 2;
+  if (corr_type == O_CORR_LM) return 4;
+  return 0;
+}
+
+/* ccl_tracer_corr_fftlog (src/ccl_correlation.c:47-162) */
+static void o_corr_fftlog(int n_ell, const double *ell, const double *cls, int n_theta, const double *theta,
+                          double *wtheta, int corr_type, int do_taper_cl, const double *taper_cl_limits,
+                          double ell_min_corr, double ell_max_corr, int n_ell_corr, int *status) {
+  double *l_arr = o_log_spacing(ell_min_corr, ell_max_corr, n_ell_corr);
+  if (!l_arr) { *status = O_ERR_LINSPACE; return; }
+  o_f1dx *cl_spl = o_f1dx_new(n_ell, ell, cls, cls[0], 0, 1, status);
+  if (*status || !cl_spl) { free(l_arr); if (!*status) *status = O_ERR_MEMORY; return; }
+  double *cl_arr = malloc(sizeof(double) * n_ell_corr), *th_arr = malloc(sizeof(double) * n_ell_corr),
+         *wth_arr = malloc(sizeof(double) * n_ell_corr);
+  for (int i = 0; i < n_ell_corr; i++) cl_arr[i] = o_f1dx_eval(cl_spl, l_arr[i]);
+  o_f1dx_free(cl_spl);
+  if (do_taper_cl) o_taper_cl(n_ell_corr, l_arr, cl_arr, taper_cl_limits);
+  /* ccl_fftlog_ComputeXi2D(i_bessel, 0, ...) = fht(dim 2, mu, q 0, kcrc 1, noring 1) */
+  o_fftlog_fht(n_ell_corr, l_arr, cl_arr, th_arr, wth_arr, 2., (double)o_corr_bessel_order(corr_type), 0., 1., 1);
+  o_f1dx *wth_spl = o_f1dx_new(n_ell_corr, th_arr, wth_arr, wth_arr[0], 0, 0, status);
+  if (wth_spl) {
+    for (int i = 0; i < n_theta; i++) wtheta[i] = o_f1dx_eval(wth_spl, theta[i] * M_PI / 180.);
+    o_f1dx_free(wth_spl);
+  } else
+    *status = O_ERR_MEMORY;
+  free(l_arr); free(cl_arr); free(th_arr); free(wth_arr);
+}
+
+typedef struct { const o_f1dx *cl_spl; int i_bessel; double th; } o_corr_int_par;
+
+/* corr_bessel_integrand (src/ccl_correlation.c:170-181); gsl_sf_bessel_Jn -> libm jn */
+static double o_corr_bessel_integrand(double l, void *params) {
+  const o_corr_int_par *p = (const o_corr_int_par *)params;
+  return l * jn(p->i_bessel, l * p->th) * o_f1dx_eval(p->cl_spl, l);
+}
+
+/* ccl_tracer_corr_bessel (src/ccl_correlation.c:183-262) */
+static void o_corr_bessel(int n_ell, const double *ell, const double *cls, int n_theta, const double *theta,
+                          double *wtheta, int corr_type, double ell_max_corr, double epsrel, int n_iteration,
+                          int *status) {
+  o_f1dx *cl_spl = o_f1dx_new(n_ell, ell, cls, cls[0], 0, 1, status);
+  if (!cl_spl) { *status = O_ERR_MEMORY; return; }
+  int st_all = *status;
+#pragma omp parallel for schedule(dynamic)
+  for (int ith = 0; ith < n_theta; ith++) {
+    o_corr_int_par cp = {cl_spl, o_corr_bessel_order(corr_type), theta[ith] * M_PI / 180};
+    double result, eresult;
+    const int gslstatus = o_qag41(o_corr_bessel_integrand, &cp, 0, ell_max_corr, 0, epsrel, (size_t)n_iteration,
+                                  &result, &eresult, NULL);
+    if (gslstatus != O_SUCCESS) {
+#pragma omp atomic
+      st_all |= gslstatus;
+    }
+    wtheta[ith] = result / (2 * M_PI);
+  }
+  *status = st_all;
+  o_f1dx_free(cl_spl);
+}
+
+/* ccl_compute_legendre_polynomial (src/ccl_correlation.c:269-291): gsl_sf_legendre_Pl_array and
+ * gsl_sf_legendre_Plm(j, 2, x) are the upward recurrences in l (legendre_poly.c); Plm restarts at P_2^2 =
+ * 3 (1-x)(1+x) for every j, which produces the same values as one pass */
+static void o_legendre_polynomial(int corr_type, double theta, int ell_max, double *Pl_theta) {
+  const double cth = cos(theta * M_PI / 180);
+  for (int j = 0; j <= ell_max; j++) Pl_theta[j] = 0.;
+  if (corr_type == O_CORR_GG) {
+    double p_ellm2 = 1.0, p_ellm1 = cth;
+    Pl_theta[0] = 1.0;
+    if (ell_max >= 1) Pl_theta[1] = cth;
+    for (int ell = 2; ell <= ell_max; ell++) {
+      const double p_ell = (cth * (2 * ell - 1) * p_ellm1 - (ell - 1) * p_ellm2) / ell;
+      p_ellm2 = p_ellm1; p_ellm1 = p_ell;
+      Pl_theta[ell] = p_ell;
+    }
+    for (int j = 0; j <= ell_max; j++) Pl_theta[j] *= (2 * j + 1);
+  } else if (corr_type == O_CORR_GL) {
+    const double root_factor = sqrt(1.0 - cth) * sqrt(1.0 + cth);
+    double p_mm = 1.0, fact_coeff = 1.0;
+    for (int i = 1; i <= 2; i++) { p_mm *= -fact_coeff * root_factor; fact_coeff += 2.0; }
+    double p_ellm2 = p_mm, p_ellm1 = cth * 5 * p_mm;
+    for (int j = 2; j <= ell_max; j++) {
+      double p;
+      if (j == 2) p = p_mm;
+      else if (j == 3) p = p_ellm1;
+      else {
+        p = (cth * (2 * j - 1) * p_ellm1 - (j + 1) * p_ellm2) / (j - 2);
+        p_ellm2 = p_ellm1; p_ellm1 = p;
+      }
+      Pl_theta[j] = p * ((2 * j + 1.) / ((j + 0.) * (j + 1.)));
+    }
+  }
+}
+
+/* ccl_tracer_corr_legendre (src/ccl_correlation.c:298-400) */
+static void o_corr_legendre(int n_ell, const double *ell, const double *cls, int n_theta, const double *theta,
+                            double *wtheta, int corr_type, int do_taper_cl, const double *taper_cl_limits,
+                            double ell_max_corr, int *status) {
+  if (corr_type == O_CORR_LM || corr_type == O_CORR_LP) { *status = O_ERR_NOT_IMPLEMENTED; return; }
+  const int lmax = (int)ell_max_corr;
+  o_f1dx *cl_spl = o_f1dx_new(n_ell, ell, cls, cls[0], 0, 1, status);
+  if (!cl_spl) { *status = O_ERR_MEMORY; return; }
+  double *l_arr = malloc(sizeof(double) * (lmax + 1)), *cl_arr = malloc(sizeof(double) * (lmax + 1));
+  for (int i = 0; i <= lmax; i++) { l_arr[i] = (double)i; cl_arr[i] = o_f1dx_eval(cl_spl, l_arr[i]); }
+  o_f1dx_free(cl_spl);
+  if (do_taper_cl) o_taper_cl(lmax + 1, l_arr, cl_arr, taper_cl_limits);
+#pragma omp parallel
+  {
+    double *Pl_theta = malloc(sizeof(double) * (lmax + 1));
+#pragma omp for schedule(dynamic)
+    for (int i = 0; i < n_theta; i++) {
+      wtheta[i] = 0;
+      o_legendre_polynomial(corr_type, theta[i], lmax, Pl_theta);
+      for (int i_L = 1; i_L < lmax; i_L += 1) wtheta[i] += cl_arr[i_L] * Pl_theta[i_L];
+      wtheta[i] /= (M_PI * 4);
+    }
+    free(Pl_theta);
+  }
+  free(l_arr); free(cl_arr);
+}
+
+/* ccl_correlation (src/ccl_correlation.c:410-440); the spline/gsl parameters it reads from cosmo are arguments */
+void o_correlation(int n_ell, const double *ell, const double *cls, int n_theta, const double *theta,
+                   double *wtheta, int corr_type, int do_taper_cl, const double *taper_cl_limits,
+                   int flag_method, double ell_min_corr, double ell_max_corr, int n_ell_corr, double epsrel,
+                   int n_iteration, int *status) {
+  switch (flag_method) {
+    case O_CORR_FFTLOG:
+      o_corr_fftlog(n_ell, ell, cls, n_theta, theta, wtheta, corr_type, do_taper_cl, taper_cl_limits,
+                    ell_min_corr, ell_max_corr, n_ell_corr, status);
+      break;
+    case O_CORR_LGNDRE:
+      o_corr_legendre(n_ell, ell, cls, n_theta, theta, wtheta, corr_type, do_taper_cl, taper_cl_limits,
+                      ell_max_corr, status);
+      break;
+    case O_CORR_BESSEL:
+      o_corr_bessel(n_ell, ell, cls, n_theta, theta, wtheta, corr_type, ell_max_corr, epsrel, n_iteration,
+                    status);
+      break;
+    default:
+      *status = O_ERR_INCONSISTENT;
+  }
+}
+
 /* test helper: integrate exp(-x^2) * cos(w x) type functions through the qag restatement */
 typedef struct { int kind; double p; } o_testf_par;
 static double o_testf(double x, void *v) {

@@ -59,3 +59,26 @@ for m in (1, 2, 3):
 if xi:
     np.savez_compressed(os.path.join(OUT, "halofit_xi.npz"), **xi)
     print("halofit_xi.npz:", {k: v.shape for k, v in xi.items()})
+
+
+# ---- C_ell -> xi(theta) pin: the reference's angular correlation benchmark ----
+# benchmarks/data/run_{b1b1,..}{analytic,histo}_log_wt_{dd,dl,di,ll_pp,ll_mm,li_pp,li_mm,ii_pp,ii_mm}.txt:
+# xi(theta) of 28 tracer-pair cases at 15 angles from an independent code, asserted by the reference at 0.2
+# (fftlog) / 0.1 (bessel) of the LSST error bars in sigma_{clustering,ggl,xi+,xi-}_Nbin5
+# (benchmarks/test_correlation.py:12-231).
+wt = {}
+for nztyp in ("analytic", "histo"):
+    for b in ("b1b1", "b1b2", "b2b1", "b2b2"):
+        for kind in ("dd", "dl", "di", "ll_pp", "ll_mm", "li_pp", "li_mm", "ii_pp", "ii_mm"):
+            f = os.path.join(SRC, "run_%s%s_log_wt_%s.txt" % (b, nztyp, kind))
+            if os.path.exists(f):
+                th, xi_ = np.loadtxt(f, unpack=True)
+                wt["%s_%s_%s" % (nztyp, b, kind)] = xi_
+                wt["theta"] = th
+for name in ("clustering", "ggl", "xi+", "xi-"):
+    f = os.path.join(SRC, "sigma_%s_Nbin5" % name)
+    if os.path.exists(f):
+        wt["sigma_" + name] = np.loadtxt(f, unpack=True)
+if wt:
+    np.savez_compressed(os.path.join(OUT, "correlation_benchmark.npz"), **wt)
+    print("correlation_benchmark.npz: %d arrays" % len(wt))
