@@ -98,6 +98,8 @@ SIGNATURES = {
     "ccl_b200_f3d_new": (_vp, [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_double, C.c_int, _ip]),
     "ccl_b200_f3d_free": (None, [_vp]),
+    "ccl_b200_fftlog_transform_general": (None, [C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_double, C.c_int,
+                                                 C.c_double, C.c_double, _dp, _ip]),
     "ccl_b200_correlation": (None, [_vp, C.c_int, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, _ip]),
     "ccl_b200_angular_cl_covariance": (None, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int,
                                               C.c_int, C.c_int, _dp, _dp, C.c_double, _ip]),

@@ -1275,6 +1275,40 @@ void ccl_b200_angular_cl_covariance(ccl_b200_cosmology* cosmo, ccl_b200_collecti
   }
 }
 
+// fftlog_transform_general (pyccl/ccl_fftlog.i:63-90), batched over mu
+void ccl_b200_fftlog_transform_general(int nmu, const double* mu, int npk, const double* k_in, int n_in_k,
+                                       const double* fk_in, double q, int spherical_bessel, double bessel_deriv,
+                                       double plaw, double* output, int* status) {
+  if (*status) return;
+  if (!mu || !k_in || !fk_in || !output || nmu < 1 || npk < 1 || n_in_k < 2) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    return;
+  }
+  if (round(bessel_deriv) != bessel_deriv || bessel_deriv < 0) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("bessel_deriv must be a non-negative integer in a floating-point format.");
+    return;
+  }
+  if (spherical_bessel != 0 && spherical_bessel != 1) {
+    *status = CCL_B200_ERROR_INCONSISTENT;
+    set_err("0 and 1 are the only valid values of spherical_bessel.");
+    return;
+  }
+  if (!use_device(status)) return;
+  int device = 0;
+  cudaGetDevice(&device);
+  DeviceScratch& sc = scratch_for(device);
+  std::lock_guard<std::mutex> lk2(sc.mu);
+  if (!sc.call.reserve(fftlog_general_work_bytes(nmu, npk, n_in_k), status)) return;
+  double* out_dev = nullptr;
+  if (!cuda_ok(launch_fftlog_general(nmu, mu, npk, n_in_k, k_in, fk_in, q, spherical_bessel, bessel_deriv, plaw,
+                                     sc.call.p, &out_dev, 0),
+               "launch_fftlog_general", status))
+    return;
+  cudaMemcpyAsync(output, out_dev, (size_t)nmu * (npk + 1) * n_in_k * 8, cudaMemcpyDeviceToHost, 0);
+  cuda_ok(cudaStreamSynchronize(0), "ccl_b200_fftlog_transform_general", status);
+}
+
 // ccl_correlation (src/ccl_correlation.c:410-428)
 void ccl_b200_correlation(ccl_b200_cosmology* cosmo, int n_ell, const double* ell, const double* cls, int n_theta,
                           const double* theta, double* wtheta, int corr_type, int do_taper_cl,

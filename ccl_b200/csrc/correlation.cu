@@ -287,6 +287,129 @@ __global__ void corr_legendre_kernel(int lmax, const double* cl_arr, CorrProblem
   P.wtheta[ith] = sum / (PI * 4);
 }
 
+// ---- generalised FFTLog: ccl_fftlog_ComputeXi_general = general_fht (src/ccl_fftlog.c:330-503), batched over mu ----
+__device__ __forceinline__ void cmul(double& ar, double& ai, double br, double bi) {
+  const double r = ar * br - ai * bi, i = ar * bi + ai * br;
+  ar = r; ai = i;
+}
+
+// u = 2^(q + sph + 2 i y - deriv) [k0r0^(-2 i y)] Gamma(xp + i y) / Gamma(xm - i y) prod_j (q + 2 i y - (j - sph)) (-1)^deriv
+// (compute_u_coefficients_new_deriv :171-197; goodkr_new_deriv :134-164 without the k0r0 factor); q includes plaw
+__device__ void general_coef(double mu, double q, int sph, double deriv, double y, double lnk0r0, int with_k0r0,
+                             double& ur, double& ui) {
+  const double xp = (mu + 1 + q - deriv - 0.5 * sph) / 2, xm = (mu + 1 - q + deriv + 0.5 * sph) / 2;
+  double lnrp, phip, lnrm, phim;
+  lngamma_complex(xp, y, lnrp, phip);
+  lngamma_complex(xm, -y, lnrm, phim);
+  const double mod2 = pow(2.0, q + 1.0 * sph - deriv);
+  double ph = 2 * y * 0.69314718055994530942;
+  if (with_k0r0) ph += -2 * y * lnk0r0;
+  double r = mod2 * cos(ph), i = mod2 * sin(ph);
+  const double g = exp(lnrp - lnrm);
+  cmul(r, i, g * cos(phip - phim), g * sin(phip - phim));
+  for (int j = 1; j <= (int)deriv; j++) cmul(r, i, q - (j - sph), 2 * y);
+  const double sgn = ((int)deriv & 1) ? -1.0 : 1.0;  // pow(-1, deriv) for the integer orders the wrapper admits
+  ur = r * sgn; ui = i * sgn;
+}
+
+struct FGProblem {
+  int nmu, npk, N, sph;
+  double q, deriv, plaw, L;  // q = q_in - sph (general_fht :351)
+  const double* mu;          // [nmu] as passed (before + sph / 2)
+  const double* k;           // [N]
+  const double* f;           // [npk][N]
+  double* a;                 // [npk][N] k^(-sph - q) f
+  double2* w;                // [N]
+  double2* u;                // [nmu][N/2 + 1]
+  double2* B;                // [npk][N/2 + 1]
+  double* kcrc;              // [nmu]
+  double* out;               // [nmu][npk + 1][N]
+};
+
+__global__ void fg_setup_kernel(FGProblem P) {
+  const int N = P.N, imu = blockIdx.x;
+  const double mu = P.mu[imu] + 0.5 * P.sph;
+  __shared__ double s_kcrc;
+  if (threadIdx.x == 0) {
+    double pr, pi_;
+    general_coef(mu, P.q + P.plaw, P.sph, P.deriv, PI * N / (2 * P.L), 0.0, 0, pr, pi_);
+    const double arg = atan2(pi_, pr) / PI;
+    const double iarg = round(arg);
+    double kr = P.mu[imu] + 1.0;
+    if (arg != iarg) kr *= exp((arg - iarg) * P.L / N);
+    s_kcrc = kr;
+    P.kcrc[imu] = kr;
+  }
+  __syncthreads();
+  const double y = PI / P.L, lnk0r0 = log(s_kcrc * exp(-P.L));
+  for (int m = threadIdx.x; m <= N / 2; m += blockDim.x) {
+    double ur, ui;
+    general_coef(mu, P.q + P.plaw, P.sph, P.deriv, m * y, lnk0r0, 1, ur, ui);
+    if ((N % 2) == 0 && m == N / 2) ui = 0.0;
+    P.u[(size_t)imu * (N / 2 + 1) + m] = make_double2(ur, ui);
+  }
+  if (imu == 0) {
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      double sn, cs;
+      sincospi(2.0 * j / N, &sn, &cs);
+      P.w[j] = make_double2(cs, sn);
+    }
+    for (int i = threadIdx.x; i < P.npk * N; i += blockDim.x)
+      P.a[i] = pow(P.k[i % N], -1.0 * P.sph - P.q) * P.f[i];
+  }
+}
+
+// B[t][m] = sum_i a[t][i] exp(-2 pi i m i / N): one warp per (t, m)
+__global__ void fg_forward_kernel(FGProblem P) {
+  const int N = P.N, nh = N / 2 + 1;
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= (long long)P.npk * nh) return;
+  const int t = (int)(gw / nh), m = (int)(gw % nh);
+  const double* a = P.a + (size_t)t * N;
+  double sr = 0.0, si = 0.0;
+  for (int i = lane; i < N; i += 32) {
+    const double2 tw = P.w[(int)(((long long)i * m) % N)];
+    sr += a[i] * tw.x;
+    si -= a[i] * tw.y;
+  }
+  sr = warp_sum(sr);
+  si = warp_sum(si);
+  if (lane == 0) P.B[(size_t)t * nh + m] = make_double2(sr, si);
+}
+
+// out[imu][1 + t][i] = r_i^(-sph - q) (sqrt(pi) / 4)^sph Re sum_m B[t][m] u[imu][m] / N exp(+2 pi i m n / N), n = N-1-i;
+// out[imu][0][i] = r_i = kcrc / k[N-1-i]: one warp per (imu, t, n)
+__global__ void fg_backward_kernel(FGProblem P) {
+  const int N = P.N, nh = N / 2 + 1, half = (N - 1) / 2;
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= (long long)P.nmu * P.npk * N) return;
+  const int n = (int)(gw % N), t = (int)((gw / N) % P.npk), imu = (int)(gw / ((long long)N * P.npk));
+  const double2* B = P.B + (size_t)t * nh;
+  const double2* u = P.u + (size_t)imu * nh;
+  double sr = 0.0;
+  for (int m = 1 + lane; m <= half; m += 32) {
+    const double2 tw = P.w[(int)(((long long)m * n) % N)];
+    double br = B[m].x, bi = B[m].y;
+    cmul(br, bi, u[m].x / (double)N, u[m].y / (double)N);
+    sr += br * tw.x - bi * tw.y;
+  }
+  sr = warp_sum(sr);
+  if (lane == 0) {
+    double c = B[0].x * (u[0].x / (double)N) - B[0].y * (u[0].y / (double)N) + 2.0 * sr;
+    if ((N % 2) == 0) {
+      const double bn = B[N / 2].x * (u[N / 2].x / (double)N);  // both factors are real at the Nyquist frequency
+      c += (n & 1) ? -bn : bn;
+    }
+    const int i = N - 1 - n;
+    const double r = P.kcrc[imu] / P.k[N - 1 - i];
+    double* o = P.out + (size_t)imu * (P.npk + 1) * N;
+    if (t == 0) o[i] = r;
+    o[(size_t)(1 + t) * N + i] = pow(r, -1.0 * P.sph - P.q) * c * (P.sph ? 0.44311346272637900682 : 1.0);
+  }
+}
+
 inline size_t up256(size_t b) { return (b + 255) / 256 * 256; }
 
 }  // namespace
@@ -304,6 +427,44 @@ size_t correlation_work_bytes(int method, int n_ell, int n_theta, int n_ell_corr
     b += up256(((size_t)ell_max_corr + 1) * 8);
   }
   return b;
+}
+
+size_t fftlog_general_work_bytes(int nmu, int npk, int N) {
+  const size_t nh = (size_t)N / 2 + 1;
+  return up256((size_t)nmu * 8) + up256((size_t)N * 8) + up256((size_t)npk * N * 8) * 2 + up256((size_t)N * 16) +
+         up256((size_t)nmu * nh * 16) + up256((size_t)npk * nh * 16) + up256((size_t)nmu * 8) +
+         up256((size_t)nmu * (npk + 1) * N * 8);
+}
+
+// work: fftlog_general_work_bytes(); the inputs are copied from the host here, the result stays at *out_dev
+cudaError_t launch_fftlog_general(int nmu, const double* mu, int npk, int N, const double* k, const double* f, double q,
+                                  int sph, double deriv, double plaw, char* work, double** out_dev,
+                                  cudaStream_t stream) {
+  FGProblem P;
+  char* p = work;
+  double* d_mu = reinterpret_cast<double*>(p); p += up256((size_t)nmu * 8);
+  double* d_k = reinterpret_cast<double*>(p); p += up256((size_t)N * 8);
+  double* d_f = reinterpret_cast<double*>(p); p += up256((size_t)npk * N * 8);
+  P.a = reinterpret_cast<double*>(p); p += up256((size_t)npk * N * 8);
+  P.w = reinterpret_cast<double2*>(p); p += up256((size_t)N * 16);
+  const size_t nh = (size_t)N / 2 + 1;
+  P.u = reinterpret_cast<double2*>(p); p += up256((size_t)nmu * nh * 16);
+  P.B = reinterpret_cast<double2*>(p); p += up256((size_t)npk * nh * 16);
+  P.kcrc = reinterpret_cast<double*>(p); p += up256((size_t)nmu * 8);
+  P.out = reinterpret_cast<double*>(p);
+  cudaMemcpyAsync(d_mu, mu, (size_t)nmu * 8, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(d_k, k, (size_t)N * 8, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(d_f, f, (size_t)npk * N * 8, cudaMemcpyHostToDevice, stream);
+  P.nmu = nmu; P.npk = npk; P.N = N; P.sph = sph;
+  P.q = q - 1.0 * sph; P.deriv = deriv; P.plaw = plaw;
+  P.L = log(k[N - 1] / k[0]) * N / (N - 1.);
+  P.mu = d_mu; P.k = d_k; P.f = d_f;
+  fg_setup_kernel<<<nmu, 128, 0, stream>>>(P);
+  const long long wf = (long long)npk * (long long)nh, wb = (long long)nmu * npk * N;
+  fg_forward_kernel<<<(unsigned)((wf * 32 + 255) / 256), 256, 0, stream>>>(P);
+  fg_backward_kernel<<<(unsigned)((wb * 32 + 255) / 256), 256, 0, stream>>>(P);
+  *out_dev = P.out;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_correlation(const CorrProblem& P, cudaStream_t stream) {

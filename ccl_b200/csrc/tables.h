@@ -187,6 +187,10 @@ struct CorrProblem {
 };
 size_t correlation_work_bytes(int method, int n_ell, int n_theta, int n_ell_corr, double ell_max_corr, int n_iteration);
 cudaError_t launch_correlation(const CorrProblem& prob, cudaStream_t stream);
+// generalised FFTLog (ccl_fftlog_ComputeXi_general, src/ccl_fftlog.c:330-503, 525-535), batched over mu
+size_t fftlog_general_work_bytes(int nmu, int npk, int N);
+cudaError_t launch_fftlog_general(int nmu, const double* mu, int npk, int N, const double* k, const double* f, double q,
+                                  int sph, double deriv, double plaw, char* work, double** out_dev, cudaStream_t stream);
 
 // ---- fast 'spline' path: ln k node grids shared by the pairs of one cosmology ----
 // Two pairs of one cosmology share a node grid for every ell when their (chi_min, chi_max) from

@@ -244,6 +244,39 @@ def angular_cl_covariance(cosmo, trs1, trs2, trs3, trs4, tsp, ell1, ell2, method
     return out.reshape(len(k2), len(k1)), st.value
 
 
+def fftlog_transform_general(rs, frs, mu, q, spherical_bessel, bessel_deriv, plaw):
+    """_fftlog_transform_general (pyccl/pyutils.py:567-603) on the device.  `mu` may be an array: the same
+    input arrays are then transformed for every mu in one call.  Returns (ks, fks): [N] and frs.shape for a
+    scalar mu, with a leading mu axis otherwise."""
+    if np.ndim(rs) != 1:
+        raise ValueError("rs should be a 1D array")
+    if np.ndim(frs) < 1 or np.ndim(frs) > 2:
+        raise ValueError("frs should be a 1D or 2D array")
+    f2 = np.ascontiguousarray(np.atleast_2d(frs), dtype=np.float64)
+    n_transforms, n_r = f2.shape
+    if len(rs) != n_r:
+        raise ValueError("rs should have %d elements" % n_r)
+    if round(bessel_deriv) != bessel_deriv or bessel_deriv < 0:
+        raise CCLB200Error("bessel_deriv must be a non-negative integer in a floating-point format.")
+    if spherical_bessel not in (0, 1):
+        raise CCLB200Error("0 and 1 are the only valid values of spherical_bessel.")
+    mus = np.ascontiguousarray(np.atleast_1d(mu), dtype=np.float64)
+    kr, pr = darr(rs)
+    out = np.empty((mus.size, n_transforms + 1, n_r))
+    st = C.c_int(0)
+    _lib.load().ccl_b200_fftlog_transform_general(mus.size, mus.ctypes.data_as(_lib._dp), n_transforms, pr, n_r,
+                                                  f2.ctypes.data_as(_lib._dp), float(q), int(spherical_bessel),
+                                                  float(bessel_deriv), float(plaw), out.ctypes.data_as(_lib._dp),
+                                                  C.byref(st))
+    _check(st.value, "ccl_b200_fftlog_transform_general")
+    ks, fks = out[:, 0, :], out[:, 1:, :]
+    if np.ndim(frs) == 1:
+        fks = fks[:, 0, :]
+    if np.ndim(mu) == 0:
+        ks, fks = ks[0], fks[0]
+    return ks, fks
+
+
 def correlation(cosmo, ell, cls, theta, corr_type, method, taper_cl_limits=None):
     """ccl_correlation through the C entry (theta in degrees).  Returns (wtheta, status)."""
     L = _lib.load()

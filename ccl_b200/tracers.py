@@ -234,6 +234,10 @@ class Tracer:
     def get_bessel_derivative(self):
         return np.array([t.get("der_bessel", 0) for t in self._trc])
 
+    def get_avg_weighted_a(self):
+        """Kernel-averaged scale factor of every sub-tracer (pyccl/tracers.py:523-531)."""
+        return np.array(self.avg_weighted_a)
+
     def get_angles_derivative(self):
         return np.array([t.get("der_angles", 0) for t in self._trc])
 

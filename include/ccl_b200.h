@@ -188,6 +188,15 @@ void ccl_b200_correlation(ccl_b200_cosmology *cosmo, int n_ell, const double *el
                           const double *theta, double *wtheta, int corr_type, int do_taper_cl,
                           const double *taper_cl_limits, int flag_method, int *status);
 
+/* Generalised FFTLog: fftlog_transform_general (pyccl/ccl_fftlog.i:63-90) -> ccl_fftlog_ComputeXi_general
+ * (include/ccl_fftlog.h, src/ccl_fftlog.c:330-503,532-535), with one addition: a leading batch over mu, because
+ * its caller (the FKEM non-Limber integrator, pyccl/nonlimber/_nonlimber_FKEM.py:140-151) transforms the same
+ * arrays for every multipole.  For each mu: output[imu][0][:] = k, output[imu][1 + j][:] = transform of
+ * fk_in[j][:]; nmu = 1 is the reference's call. */
+void ccl_b200_fftlog_transform_general(int nmu, const double *mu, int npk, const double *k_in, int n_in_k,
+                                       const double *fk_in, double q, int spherical_bessel, double bessel_deriv,
+                                       double plaw, double *output, int *status);
+
 /* A batch owns one HBM arena holding the table packs of ncosmo cosmologies.  Slots are filled
  * with the same flat arrays as the single-object constructors, then committed (one H2D copy of
  * the raw region + device kernels that build every spline coefficient table in place). */

@@ -100,6 +100,8 @@ def lib():
                                     C.c_double, C.c_int, C.c_double, C.c_int, _ip]
         L.o_lngamma_complex.argtypes = [C.c_double, C.c_double, _dp, _dp]
         L.o_fftlog_fht.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.o_fftlog_general.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int,
+                                       C.c_double, C.c_double]
         L.o_get_k_interval_pub.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp),
                                            C.c_double, _dp, _dp]
         L.o_set_lkmin_ulps.argtypes = [C.c_int]
@@ -417,6 +419,17 @@ def fftlog_fht(k, pk, dim, mu, q=0.0, kcrc=1.0, noring=1):
     lib().o_fftlog_fht(k.size, k.ctypes.data_as(_dp), pk.ctypes.data_as(_dp), r.ctypes.data_as(_dp),
                        xi.ctypes.data_as(_dp), float(dim), float(mu), float(q), float(kcrc), int(noring))
     return r, xi
+
+
+def fftlog_transform_general(rs, frs, mu, q, spherical_bessel, bessel_deriv, plaw):
+    """_fftlog_transform_general (pyccl/pyutils.py:567-603) -> ccl_fftlog_ComputeXi_general: returns (ks, fks)."""
+    rs = np.ascontiguousarray(rs, dtype=np.float64)
+    f2 = np.ascontiguousarray(np.atleast_2d(frs), dtype=np.float64)
+    ks, fks = np.empty_like(rs), np.empty_like(f2)
+    lib().o_fftlog_general(f2.shape[0], rs.size, rs.ctypes.data_as(_dp), f2.ctypes.data_as(_dp),
+                           ks.ctypes.data_as(_dp), fks.ctypes.data_as(_dp), float(mu), float(q),
+                           int(spherical_bessel), float(bessel_deriv), float(plaw))
+    return ks, (fks[0] if np.ndim(frs) == 1 else fks)
 
 
 def set_lkmin_ulps(n):

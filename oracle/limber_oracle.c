@@ -1970,6 +1970,93 @@ void o_fftlog_fht(int N, const double *k, const double *pk, double *r, double *x
   free(u); free(w); free(a); free(b); free(c);
 }
 
+/* goodkr_new_deriv (src/ccl_fftlog.c:134-164): low-ringing kr of the generalised transform.  cpow(2, z) and the
+ * complex products are written out in (modulus, phase) / (re, im) form. */
+static void o_cmul(double *ar, double *ai, double br, double bi) {
+  const double r = *ar * br - *ai * bi, i = *ar * bi + *ai * br;
+  *ar = r; *ai = i;
+}
+
+static void o_general_coef(double mu, double q, int sph, double deriv, double y, double lnk0r0, int with_k0r0,
+                           double *ur, double *ui) {
+  /* u = 2^(q + sph + 2 i y - deriv) [k0r0^(-2 i y)] Gamma(xp + i y) / Gamma(xm - i y)
+   *     prod_{j=1..deriv} (q + 2 i y - (j - sph)) (-1)^deriv          (src/ccl_fftlog.c:146-156,181-192) */
+  const double xp = (mu + 1 + q - deriv - 0.5 * sph) / 2, xm = (mu + 1 - q + deriv + 0.5 * sph) / 2;
+  double lnrp, phip, lnrm, phim;
+  o_lngamma_complex(xp, y, &lnrp, &phip);
+  o_lngamma_complex(xm, -y, &lnrm, &phim);
+  const double mod2 = pow(2.0, q + 1.0 * sph - deriv);
+  double ph = 2 * y * M_LN2;
+  if (with_k0r0) ph += -2 * y * lnk0r0;
+  double r = mod2 * cos(ph), i = mod2 * sin(ph);
+  const double g = exp(lnrp - lnrm);
+  o_cmul(&r, &i, g * cos(phip - phim), g * sin(phip - phim));
+  for (int j = 1; j <= (int)deriv; j++) o_cmul(&r, &i, q - (j - sph), 2 * y);
+  const double sgn = pow(-1.0, deriv);
+  *ur = r * sgn; *ui = i * sgn;
+}
+
+static double o_goodkr_new_deriv(int N, double mu, double q, double L, int sph, double deriv, double plaw, double kr) {
+  q += plaw;
+  double pr, pi_;
+  o_general_coef(mu, q, sph, deriv, M_PI * N / (2 * L), 0.0, 0, &pr, &pi_);
+  const double arg = atan2(pi_, pr) / M_PI; /* cimag(clog(prefac)) / pi */
+  const double iarg = round(arg);
+  if (arg != iarg) kr *= exp((arg - iarg) * L / N);
+  return kr;
+}
+
+/* general_fht (src/ccl_fftlog.c:345-503) = ccl_fftlog_ComputeXi_general: for each of the npk input arrays
+ *   xi(r_n) = int dk/k?  -- in the reference's words: a~(k) = int dr / (x k)^plaw a(r) (J / j)^(deriv)_mu(x k)
+ * on the low-ringing output grid r_n = kcrc / k_{N-1-n}.  DFTs from their definition as in o_fftlog_fht. */
+void o_fftlog_general(int npk, int N, const double *k, const double *pk, double *r, double *xi, double mu, double q,
+                      int sph, double deriv, double plaw) {
+  q = q - 1.0 * sph;
+  double kcrc = mu + 1.0;
+  mu = mu + 0.5 * sph;
+  const double L = log(k[N - 1] / k[0]) * N / (N - 1.);
+  kcrc = o_goodkr_new_deriv(N, mu, q, L, sph, deriv, plaw, kcrc);
+  double *u = malloc(sizeof(double) * 2 * N), *w = malloc(sizeof(double) * 2 * N);
+  double *a = malloc(sizeof(double) * N), *b = malloc(sizeof(double) * 2 * N), *c = malloc(sizeof(double) * N);
+  { /* compute_u_coefficients_new_deriv (src/ccl_fftlog.c:171-197) */
+    const double y = M_PI / L, lnk0r0 = log(kcrc * exp(-L));
+    for (int m = 0; m <= N / 2; m++) o_general_coef(mu, q + plaw, sph, deriv, m * y, lnk0r0, 1, &u[2 * m], &u[2 * m + 1]);
+    for (int m = N / 2 + 1; m < N; m++) { u[2 * m] = u[2 * (N - m)]; u[2 * m + 1] = -u[2 * (N - m) + 1]; }
+    if ((N % 2) == 0) u[2 * (N / 2) + 1] = 0.0;
+  }
+  for (int j = 0; j < N; j++) { w[2 * j] = cos(2 * M_PI * j / N); w[2 * j + 1] = sin(2 * M_PI * j / N); }
+  for (int n = 0; n < N; n++) r[n] = kcrc / k[N - 1 - n];
+  for (int t = 0; t < npk; t++) {
+    for (int i = 0; i < N; i++) a[i] = pow(k[i], -1 * sph - q) * pk[(size_t)t * N + i];
+#pragma omp parallel for schedule(static)
+    for (int m = 0; m < N; m++) {
+      double sr = 0, si = 0;
+      long idx = 0;
+      for (int i = 0; i < N; i++) {
+        sr += a[i] * w[2 * idx];
+        si -= a[i] * w[2 * idx + 1];
+        idx += m; if (idx >= N) idx -= N;
+      }
+      const double ur = u[2 * m] / (double)N, ui = u[2 * m + 1] / (double)N;
+      b[2 * m] = sr * ur - si * ui;
+      b[2 * m + 1] = sr * ui + si * ur;
+    }
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < N; n++) {
+      double sr = 0;
+      long idx = 0;
+      for (int m = 0; m < N; m++) {
+        sr += b[2 * m] * w[2 * idx] - b[2 * m + 1] * w[2 * idx + 1];
+        idx += n; if (idx >= N) idx -= N;
+      }
+      c[n] = sr;
+    }
+    for (int i = 0; i < N; i++)
+      xi[(size_t)t * N + i] = pow(r[i], -1 * sph - q) * c[N - 1 - i] * pow(pow(M_PI, 0.5) / 4, sph);
+  }
+  free(u); free(w); free(a); free(b); free(c);
+}
+
 static int o_corr_bessel_order(int corr_type) {
   if (corr_type == O_CORR_GL) return 2;
   if (corr_type == O_CORR_LM) return 4;

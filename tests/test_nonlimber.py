@@ -1,0 +1,297 @@
+"""FKEM non-Limber integrator and the generalised FFTLog underneath (SURVEY 8f-4 second half:
+pyccl/nonlimber/_nonlimber_FKEM.py, src/ccl_fftlog.c:128-503).
+
+Pins (CPU): the oracle restatement of ccl_fftlog_ComputeXi_general against a closed-form spherical-Bessel
+transform, int dlnr r^(l+3) exp(-a r^2) j_l(k r) = sqrt(pi) k^l / (2^(l+2) a^(l+3/2)) exp(-k^2 / 4a), and against
+adaptive quadrature (scipy) for the Bessel-derivative and power-law variants FKEM uses.
+GPU: the device transform against the oracle (<= 1e-10 of the curve's scale), the batch over mu against single
+calls, and the reference's FKEM unit tests (pyccl/tests/test_cells.py:104-121,130-376) through `angular_cl`.
+Pin of FKEM itself (GPU): the reference's N5K benchmark (benchmarks/test_nonlimber.py: brute-force non-Limber C_ell
+of 10 clustering x 5 shear bins, chi^2 < 0.3 per multipole against LSST-like errors, l_limber = 'auto').  The
+reference builds its cosmology with CAMB, which is not available here; the test runs on the challenge's own
+background and P(k, z) tables shipped next to the truth (tests/golden/nonlimber_n5k.npz, tools/make_golden.py) through
+a CosmologyCalculator: worst chi^2 0.023 (gg), 4e-4 (gs), 5e-4 (ss)."""
+import numpy as np
+import pytest
+
+import oracle
+
+R = np.geomspace(1e-4, 1e3, 512)
+VARIANTS = [(2, 0.0, 0.0), (5, 0.0, 0.0), (30, 0.0, 0.0), (4, 2.0, 0.0), (4, 1.0, 0.0), (4, 0.0, -2.0), (17, 2.0, 0.0)]
+
+
+def _f(l, a=0.5):
+    return R ** (l + 3) * np.exp(-a * R * R)
+
+
+def test_oracle_general_fftlog_closed_form():
+    for l in (2, 5, 30):
+        a = 0.5
+        k, fk = oracle.fftlog_transform_general(R, _f(l, a), l, 1.01, 1, 0.0, 0.0)
+        ex = np.sqrt(np.pi) * k ** l / (2 ** (l + 2) * a ** (l + 1.5)) * np.exp(-k * k / (4 * a))
+        sel = (k > 0.05) & (k < 6)
+        assert np.max(np.abs(fk - ex)[sel]) <= 1e-12 * np.max(ex)
+
+
+def test_oracle_general_fftlog_vs_quadrature():
+    from scipy.integrate import quad
+    from scipy.special import spherical_jn
+    l, a = 4, 0.5
+    for deriv, plaw in ((2.0, 0.0), (1.0, 0.0), (0.0, -2.0)):
+        k, fk = oracle.fftlog_transform_general(R, _f(l, a), l, 1.01, 1, deriv, plaw)
+        for kk in (0.5, 1.0, 2.5):
+            i = np.argmin(np.abs(k - kk))
+            kv = k[i]
+
+            def integrand(x):
+                z = kv * x
+                if deriv == 0:
+                    j = spherical_jn(l, z)
+                elif deriv == 1:
+                    j = spherical_jn(l, z, derivative=True)
+                else:  # j'' = -2 j'/z - (1 - l(l+1)/z^2) j
+                    j = -2 / z * spherical_jn(l, z, derivative=True) - (1 - l * (l + 1) / z ** 2) * spherical_jn(l, z)
+                return x ** (l + 2) * np.exp(-a * x * x) * j * z ** plaw
+            ref = quad(integrand, 0, 12, limit=400, epsabs=0, epsrel=1e-12)[0]
+            assert abs(fk[i] / ref - 1) < 1e-10, (deriv, plaw, kv)
+
+
+@pytest.mark.gpu
+def test_device_general_fftlog_matches_oracle():
+    from ccl_b200 import lowlevel
+    for l, deriv, plaw in VARIANTS:
+        f = np.stack([_f(l), _f(l, 0.8) * (1 + 0.1 * np.sin(np.log(R)))])
+        k0, f0 = oracle.fftlog_transform_general(R, f, l, 1.01, 1, deriv, plaw)
+        k1, f1 = lowlevel.fftlog_transform_general(R, f, l, 1.01, 1, deriv, plaw)
+        assert np.max(np.abs(k1 / k0 - 1)) < 1e-12
+        assert np.max(np.abs(f1 - f0)) <= 1e-10 * np.max(np.abs(f0)), (l, deriv, plaw)
+    # non-spherical Bessel functions and an odd sample count
+    r = np.geomspace(1e-3, 1e2, 301)
+    f = r ** 2 * np.exp(-r)
+    k0, f0 = oracle.fftlog_transform_general(r, f, 1.0, 0.3, 0, 0.0, 0.0)
+    k1, f1 = lowlevel.fftlog_transform_general(r, f, 1.0, 0.3, 0, 0.0, 0.0)
+    assert np.max(np.abs(k1 / k0 - 1)) < 1e-12 and np.max(np.abs(f1 - f0)) <= 1e-10 * np.max(np.abs(f0))
+
+
+@pytest.mark.gpu
+def test_device_general_fftlog_batch_over_mu():
+    from ccl_b200 import lowlevel
+    f = np.stack([_f(3), _f(2, 0.7)])
+    mus = np.array([2., 3., 10., 57., 200.])
+    kb, fb = lowlevel.fftlog_transform_general(R, f, mus, 1.01, 1, 0.0, -2.0)
+    assert kb.shape == (5, R.size) and fb.shape == (5, 2, R.size)
+    for i, mu in enumerate(mus):
+        k1, f1 = lowlevel.fftlog_transform_general(R, f, float(mu), 1.01, 1, 0.0, -2.0)
+        assert np.array_equal(k1, kb[i]) and np.array_equal(f1, fb[i])
+        k0, f0 = oracle.fftlog_transform_general(R, f, mu, 1.01, 1, 0.0, -2.0)
+        assert np.max(np.abs(fb[i] - f0)) <= 1e-10 * np.max(np.abs(f0))
+    with pytest.raises(lowlevel.CCLB200Error):
+        lowlevel.fftlog_transform_general(R, f, 2.0, 1.01, 1, 0.5, 0.0)
+    with pytest.raises(lowlevel.CCLB200Error):
+        lowlevel.fftlog_transform_general(R, f, 2.0, 1.01, 2, 0.0, 0.0)
+
+
+# ---- the reference's FKEM unit tests (pyccl/tests/test_cells.py) ----
+@pytest.fixture(scope="module")
+def cosmo():
+    import ccl_b200 as ccl
+    return ccl.CosmologyVanillaLCDM(transfer_function='bbks')
+
+
+@pytest.mark.gpu
+def test_cells_raise_nonlimber_methods(cosmo):
+    import ccl_b200 as ccl
+    z = np.linspace(0.0, 1.0, 200)
+    lens = ccl.WeakLensingTracer(cosmo, dndz=(z, np.exp(-(((z - 0.5) / 0.1) ** 2))))
+    ells = [10, 11]
+    with pytest.raises(ValueError):
+        ccl.angular_cl(cosmo, lens, lens, ells, non_limber_integration_method="FEKM")
+    with pytest.raises(ValueError):
+        ccl.angular_cl(cosmo, lens, lens, ells, l_limber='auoto', non_limber_integration_method="FKEM")
+    cl, meta = ccl.angular_cl(cosmo, lens, lens, ells, l_limber=100, non_limber_integration_method="FKEM",
+                              return_meta=True)
+    assert meta['l_limber'] == 100 and np.all(np.isfinite(cl)) and cl.shape == (2,)
+
+
+@pytest.mark.gpu
+def test_fkem_chi_params(cosmo):
+    """above ell ~ 100 the non-Limber result agrees with Limber to 1 % with a fine chi sampling"""
+    import ccl_b200 as ccl
+    z = np.linspace(0, 4.72, 60)
+    nz = z ** 2 * np.exp(-0.5 * ((z - 1.5) / 0.7) ** 2)
+    bz = np.ones_like(z)
+    ls = np.unique(np.geomspace(2, 2000, 128).astype(int)).astype(float)
+    tracer_gal = ccl.NumberCountsTracer(cosmo, has_rsd=False, dndz=(z, nz), bias=(z, bz))
+    cl_gg = ccl.angular_cl(cosmo, tracer_gal, tracer_gal, ls, l_limber=-1)
+    cl_ggn_b, meta = ccl.angular_cl(cosmo, tracer_gal, tracer_gal, ls, l_limber=1000, fkem_chi_min=1.0, fkem_Nchi=100,
+                                    return_meta=True)
+    ell_good = ls > 100
+    assert np.all(np.fabs(cl_ggn_b / cl_gg - 1)[ell_good] < 0.01)
+    assert meta['l_limber'] >= 1000
+    # at low ell the Limber approximation is off by much more than that
+    assert np.fabs(cl_ggn_b / cl_gg - 1)[0] > 0.05
+    # 'auto' finds a transition and agrees with the fixed-l_limber result below it
+    cl_auto, meta = ccl.angular_cl(cosmo, tracer_gal, tracer_gal, ls, l_limber='auto', fkem_chi_min=1.0, fkem_Nchi=100,
+                                   return_meta=True)
+    assert 2 < meta['l_limber'] < 1000
+    n = np.count_nonzero(ls <= meta['l_limber'])
+    assert np.allclose(cl_auto[:n], cl_ggn_b[:n], rtol=1e-12)
+    assert np.all(np.fabs(cl_auto / cl_ggn_b - 1) < 0.011)
+
+
+@pytest.mark.gpu
+def test_fkem_warn_bad_params(cosmo):
+    import ccl_b200 as ccl
+    z = np.linspace(0, 2.0, 50)
+    nz = z ** 2 * np.exp(-z)
+    ells = np.array([10.0, 30.0, 100.0])
+    nc = ccl.NumberCountsTracer(cosmo, has_rsd=False, dndz=(z, nz), bias=(z, np.ones_like(z)))
+    with pytest.warns(ccl.CCLWarning, match="Nchi must be a positive integer"):
+        cl = ccl.angular_cl(cosmo, nc, nc, ells, non_limber_integration_method="FKEM", l_limber=1000, fkem_Nchi=0)
+        assert np.all(np.isfinite(cl))
+    with pytest.warns(ccl.CCLWarning, match="chi_min must be greater than zero"):
+        cl = ccl.angular_cl(cosmo, nc, nc, ells, non_limber_integration_method="FKEM", l_limber=1000,
+                            fkem_chi_min=0.0)
+        assert np.all(np.isfinite(cl))
+    with pytest.warns(ccl.CCLWarning, match="limber_max_error must be greater than zero"):
+        cl = ccl.angular_cl(cosmo, nc, nc, ells, non_limber_integration_method="FKEM", l_limber=1000,
+                            limber_max_error=0.0)
+        assert np.all(np.isfinite(cl))
+
+
+@pytest.mark.gpu
+def test_fkem_warn_mismatched_pk_types_fallback_to_limber(cosmo):
+    import ccl_b200 as ccl
+    z = np.linspace(0, 2.0, 50)
+    nz = z ** 2 * np.exp(-z)
+    ells = np.array([10.0, 30.0, 100.0])
+    nc = ccl.NumberCountsTracer(cosmo, has_rsd=False, dndz=(z, nz), bias=(z, np.ones_like(z)))
+    pka_obj = ccl.Pk2D.from_function(pkfunc=lambda k, a: a / (1.0 + k))
+    with pytest.warns(ccl.CCLWarning, match="p_of_k_a and p_of_k_a_lin must be of the same type"):
+        cl, meta = ccl.angular_cl(cosmo, nc, nc, ells, non_limber_integration_method="FKEM", l_limber=1000,
+                                  p_of_k_a=pka_obj, p_of_k_a_lin=ccl.DEFAULT_POWER_SPECTRUM, return_meta=True)
+        assert np.all(np.isfinite(cl))
+        assert meta["l_limber"] == -1
+
+
+@pytest.mark.gpu
+def test_fkem_multicomponent_tracer(cosmo):
+    import ccl_b200 as ccl
+    z = np.linspace(0.0, 2.0, 60)
+    nz = np.exp(-0.5 * ((z - 0.5) / 0.3) ** 2)
+    ells = np.array([2.0, 5.0, 10.0, 20.0])
+    nc = ccl.NumberCountsTracer(cosmo, has_rsd=True, dndz=(z, nz), bias=(z, np.ones_like(z)),
+                                mag_bias=(z, 0.5 * np.ones_like(z)))
+    kw = dict(non_limber_integration_method="FKEM", l_limber=1000, fkem_Nchi=100, fkem_chi_min=1.0)
+    assert np.all(np.isfinite(ccl.angular_cl(cosmo, nc, nc, ells, **kw)))
+    lens = ccl.WeakLensingTracer(cosmo, dndz=(z, nz))
+    assert np.all(np.isfinite(ccl.angular_cl(cosmo, nc, lens, ells, **kw)))
+
+
+@pytest.mark.gpu
+def test_fkem_decomposed_matches_direct(cosmo):
+    """linearity in the sub-tracers: density + magnification, shear + intrinsic alignments (5e-3 like the reference)"""
+    import ccl_b200 as ccl
+    z = np.linspace(0.01, 2.0, 200)
+    nz = np.exp(-((z - 1.0) ** 2) / 0.1)
+    ells = np.arange(2, 200)
+    kw = dict(l_limber=210, non_limber_integration_method="FKEM", fkem_Nchi=200, fkem_chi_min=1e-6)
+    b, m = (z, 1.5 * np.ones_like(z)), (z, 1.0 * np.ones_like(z))
+    den = ccl.NumberCountsTracer(cosmo, dndz=(z, nz), bias=b, has_rsd=False, mag_bias=None)
+    mag = ccl.NumberCountsTracer(cosmo, dndz=(z, nz), bias=None, has_rsd=False, mag_bias=m)
+    full = ccl.NumberCountsTracer(cosmo, dndz=(z, nz), bias=b, has_rsd=False, mag_bias=m)
+    dec = (ccl.angular_cl(cosmo, den, den, ells, **kw) + 2.0 * ccl.angular_cl(cosmo, den, mag, ells, **kw) +
+           ccl.angular_cl(cosmo, mag, mag, ells, **kw))
+    rel = np.abs(ccl.angular_cl(cosmo, full, full, ells, **kw) / dec - 1.0)
+    assert np.all(np.isfinite(rel)) and np.max(rel) < 5e-3
+    ia = (z, 0.5 * np.ones_like(z))
+    lens = ccl.WeakLensingTracer(cosmo, dndz=(z, nz), has_shear=True, ia_bias=None)
+    t_ia = ccl.WeakLensingTracer(cosmo, dndz=(z, nz), has_shear=False, ia_bias=ia, use_A_ia=False)
+    t_full = ccl.WeakLensingTracer(cosmo, dndz=(z, nz), has_shear=True, ia_bias=ia, use_A_ia=False)
+    dec = (ccl.angular_cl(cosmo, lens, lens, ells, **kw) + 2.0 * ccl.angular_cl(cosmo, lens, t_ia, ells, **kw) +
+           ccl.angular_cl(cosmo, t_ia, t_ia, ells, **kw))
+    rel = np.abs(ccl.angular_cl(cosmo, t_full, t_full, ells, **kw) / dec - 1.0)
+    assert np.all(np.isfinite(rel)) and np.max(rel) < 5e-3
+
+
+# ---- the reference's N5K benchmark (benchmarks/test_nonlimber.py) on the N5K challenge's own inputs ----
+N5K = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden",
+                                 "nonlimber_n5k.npz")
+B_G = np.array([1.376695, 1.451179, 1.528404, 1.607983, 1.689579, 1.772899, 1.857700, 1.943754, 2.030887, 2.118943])
+
+
+def _n5k_setup():
+    """benchmarks/test_nonlimber.py:10-176 with the CAMB cosmology replaced by a CosmologyCalculator on the
+    challenge's own background and P(k, z) tables (benchmarks/data/nonlimber/{background,pk}.npz), which is what
+    the truth C_ell were computed from."""
+    import ccl_b200 as ccl
+    from scipy.integrate import simpson
+    d = np.load(N5K)
+    zb = d["background_z"]
+    a_bg = (1. / (1 + zb))[::-1]
+    zp = d["pk_z"]
+    a_pk = (1. / (1 + zp))[::-1]
+    pk_lin, pk_nl = d["pk_pk_lin"][::-1], d["pk_pk_nl"][::-1]
+    # growth from the linear spectrum at the largest scale; rate by differentiation (only RSD would read it)
+    Dz = np.sqrt(pk_lin[:, 0] / pk_lin[-1, 0])
+    from scipy.interpolate import Akima1DInterpolator
+    D_bg = np.where(a_bg >= a_pk[0], Akima1DInterpolator(a_pk, Dz)(np.clip(a_bg, a_pk[0], 1.0)), Dz[0] * a_bg / a_pk[0])
+    f_bg = np.gradient(np.log(D_bg), np.log(a_bg))
+    cosmo = ccl.CosmologyCalculator(
+        Omega_c=0.3156 - 0.0492, Omega_b=0.0492, h=0.6727, n_s=0.9645, A_s=2.12107e-9, w0=-1.0,
+        background={'a': a_bg, 'chi': d["background_chi"][::-1], 'h_over_h0': d["background_Ez"][::-1]},
+        growth={'a': a_bg, 'growth_factor': D_bg, 'growth_rate': f_bg},
+        pk_linear={'a': a_pk, 'k': d["pk_k"], 'delta_matter:delta_matter': pk_lin},
+        pk_nonlin={'a': a_pk, 'k': d["pk_k"], 'delta_matter:delta_matter': pk_nl})
+    z_cl, z_sh = d["dNdzs_z_cl"], d["dNdzs_z_sh"]
+    t_g = [ccl.NumberCountsTracer(cosmo, has_rsd=False, dndz=(z_cl, Nz), bias=(z_cl, bg * np.ones(len(z_cl))))
+           for Nz, bg in zip(d["dNdzs_dNdz_cl"].T, B_G)]
+    t_s = [ccl.WeakLensingTracer(cosmo, dndz=(z_sh, Nz)) for Nz in d["dNdzs_dNdz_sh"].T]
+    ells = np.unique(np.geomspace(2, 2000, 128).astype(int)).astype(float)
+    assert np.allclose(d["ls"], ells)
+    arcmin2_per_sr = (60 * 60 * (180 / np.pi) ** 2)
+    nc_ints = simpson(d["dNdzs_dNdz_cl"], x=z_cl, axis=0)
+    ns_ints = simpson(d["dNdzs_dNdz_sh"], x=z_sh, axis=0)
+    nc_ints *= 40.0 / np.sum(nc_ints)
+    ns_ints *= 27.0 / np.sum(ns_ints)
+    Ngg, Nss = 1.0 / (nc_ints * arcmin2_per_sr), (0.28 ** 2) / (ns_ints * arcmin2_per_sr)
+    nmodes = list(ells[1:] ** 2 - ells[:-1] ** 2)
+    nmodes.append((ells[-1] ** 2 / ells[-2]) ** 2 - ells[-1] ** 2)
+    nmodes = np.array(nmodes) * 0.5 * 0.4
+    Ng, Ns = 10, 5
+    i_gg = [(i1, i2) for i1 in range(Ng) for i2 in range(i1, Ng)]
+    i_gs = [(i1, i2) for i1 in range(Ng) for i2 in range(Ns)]
+    i_ss = [(i1, i2) for i1 in range(Ns) for i2 in range(i1, Ns)]
+    r_gg = {p: n for n, p in enumerate(i_gg)}
+    r_ss = {p: n for n, p in enumerate(i_ss)}
+    tgg, tgs, tss = d["cls_gg"], d["cls_gs"], d["cls_ss"]
+    err = {"gg": [np.sqrt(((tgg[r_gg[(i1, i1)]] + Ngg[i1]) * (tgg[r_gg[(i2, i2)]] + Ngg[i2]) +
+                           (tgg[n] + (Ngg[i1] if i1 == i2 else 0.0)) ** 2) / nmodes) for n, (i1, i2) in enumerate(i_gg)],
+           "gs": [np.sqrt(((tgg[r_gg[(i1, i1)]] + Ngg[i1]) * (tss[r_ss[(i2, i2)]] + Nss[i2]) + tgs[n] ** 2) / nmodes)
+                  for n, (i1, i2) in enumerate(i_gs)],
+           "ss": [np.sqrt(((tss[r_ss[(i1, i1)]] + Nss[i1]) * (tss[r_ss[(i2, i2)]] + Nss[i2]) +
+                           (tss[n] + (Nss[i1] if i1 == i2 else 0.0)) ** 2) / nmodes) for n, (i1, i2) in enumerate(i_ss)]}
+    return (cosmo, ells, {"gg": t_g, "gs": t_g, "ss": t_s}, {"gg": t_g, "gs": t_s, "ss": t_s},
+            {"gg": tgg, "gs": tgs, "ss": tss}, err, {"gg": i_gg, "gs": i_gs, "ss": i_ss})
+
+
+@pytest.fixture(scope="module")
+def n5k():
+    return _n5k_setup()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cross_type,stride", [("gg", 3), ("gs", 4), ("ss", 1)])
+def test_fkem_reference_n5k_benchmark(n5k, cross_type, stride):
+    """chi^2 < 0.3 per multipole against the brute-force truth, l_limber = 'auto' (benchmarks/test_nonlimber.py:180-204);
+    every `stride`-th pair of the type"""
+    import ccl_b200 as ccl
+    cosmo, ells, tr1, tr2, truth, errors, indices = n5k
+    chi2max = 0.0
+    for n, (i1, i2) in list(enumerate(indices[cross_type]))[::stride]:
+        cls, meta = ccl.angular_cl(cosmo, tr1[cross_type][i1], tr2[cross_type][i2], ells, l_limber='auto',
+                                   non_limber_integration_method="FKEM", return_meta=True)
+        chi2 = (cls - truth[cross_type][n]) ** 2 / errors[cross_type][n] ** 2
+        chi2max = max(chi2max, chi2.max())
+        assert np.all(chi2 < 0.3), (cross_type, i1, i2, chi2.max(), meta)
+    print("N5K %s: worst chi2 %.4f" % (cross_type, chi2max))

@@ -82,3 +82,24 @@ for name in ("clustering", "ggl", "xi+", "xi-"):
 if wt:
     np.savez_compressed(os.path.join(OUT, "correlation_benchmark.npz"), **wt)
     print("correlation_benchmark.npz: %d arrays" % len(wt))
+
+
+# ---- FKEM pin: the reference's non-Limber (N5K) benchmark ----
+# benchmarks/data/nonlimber/: truth C_ell of 10 clustering x 5 shear bins from brute-force non-Limber codes
+# (benchmarks_nl_full_cl{gg,gs,ss}.npz), asserted by the reference at chi^2 < 0.3 per multipole against LSST-like
+# error bars (benchmarks/test_nonlimber.py:180-204), with the N5K inputs they were computed from: n(z)
+# (dNdzs_fullwidth.npz), P(k, z) linear and non-linear (pk.npz) and the background (background.npz).
+nl_dir = os.path.join(SRC, "nonlimber")
+if os.path.isdir(nl_dir):
+    nl = {}
+    for name, keys in (("background", ("z", "chi", "Ez")), ("pk", ("k", "z", "pk_nl", "pk_lin")),
+                       ("dNdzs_fullwidth", ("z_sh", "dNdz_sh", "z_cl", "dNdz_cl"))):
+        d = np.load(os.path.join(nl_dir, name + ".npz"))
+        for key in keys:
+            nl[name.split("_")[0] + "_" + key] = d[key]
+    for kind in ("gg", "gs", "ss"):
+        d = np.load(os.path.join(nl_dir, "benchmarks_nl_full_cl%s.npz" % kind))
+        nl["cls_" + kind] = d["cls"]
+        nl["ls"] = d["ls"]
+    np.savez_compressed(os.path.join(OUT, "nonlimber_n5k.npz"), **nl)
+    print("nonlimber_n5k.npz:", {k: v.shape for k, v in nl.items()})
