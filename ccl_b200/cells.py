@@ -1,4 +1,5 @@
-"""``angular_cl`` with the pyccl signature (pyccl/cells.py:10-175), Limber branch.
+"""``angular_cl`` with the pyccl signature (pyccl/cells.py:10-175): Limber path plus the FKEM non-Limber
+integrator below the transition multipole (nonlimber.py).
 
 The call site of the hot path: ``lib.angular_cl_vec_limber(cosmo.cosmo, clt1, clt2, psp, ell,
 integ_type, nell, status)`` (pyccl/cells.py:149-158) becomes one C-ABI call,
