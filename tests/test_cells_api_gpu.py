@@ -159,3 +159,27 @@ def test_distances_not_computed_is_error_1059():
     empty = cb.LibCosmology()           # no distances injected or computed
     cl, st = cb.angular_cls_limber(empty, ltr[:1], ltr[1:2], psp, np.array([10., 20.]), cb._lib.INTEGRATION_SPLINE)
     assert st == 1059       # the output array is left untouched, like the reference's early return
+
+
+def test_rsd_second_point_reaches_below_pk_a_range(env):
+    """The der_bessel = 2 (RSD) sub-tracer evaluates P(k, a') at chi' = (l + 3/2) / k, up to chi_max (l + 3/2) / (l + 1/2):
+    with a P(k, a) table that ends just beyond the tracer's chi_max this reaches below the table's a-range at low ell
+    and needs the growth table on the device (src/ccl_f2d.c:351-370).  The call must succeed and match the oracle."""
+    ccl, cosmo = env["ccl"], env["cosmo"]
+    a_arr = np.linspace(1. / 2.3, 1.0, 24)          # P(k, a) tabulated to z = 1.3
+    lk_arr = np.log(np.geomspace(1e-4, 50., 96))
+    pk_arr = np.array([cosmo.linear_matter_power(np.exp(lk_arr), a) for a in a_arr])
+    pk = ccl.Pk2D(a_arr=a_arr, lk_arr=lk_arr, pk_arr=np.log(pk_arr), is_logp=True)
+    z = np.linspace(0.8, 1.25, 64)                   # chi_max inside the table, chi_max * 3.5 / 2.5 outside
+    nz = np.exp(-0.5 * ((z - 1.05) / 0.06) ** 2)
+    nc = ccl.NumberCountsTracer(cosmo, has_rsd=True, dndz=(z, nz), bias=(z, np.ones_like(z)))
+    assert nc.chi_max < cosmo.comoving_radial_distance(a_arr[0]) < nc.chi_max * 3.5 / 2.5
+    ells = np.array([2., 3., 5., 10., 40., 200.])
+    for method, tol in (("spline", 1e-10), ("qag_quad", 1e-5)):
+        cl = ccl.angular_cl(cosmo, nc, nc, ells, p_of_k_a=pk, limber_integration_method=method)
+        assert np.all(np.isfinite(cl))
+        oc, op, otr = oracle_objects(cosmo, {"nc": nc}, pk=pk)
+        ref, st = oracle.angular_cl(oc, otr["nc"], otr["nc"], op, ells,
+                                    oracle.INTEG_SPLINE if method == "spline" else oracle.INTEG_QAG)
+        assert st == 0
+        assert np.max(np.abs(cl / ref - 1)) < tol, (method, np.max(np.abs(cl / ref - 1)))

@@ -1,6 +1,5 @@
 # usage: bash tools/ab.sh [lib names...]; default: the in-tree build.  A name "v1" runs the default build with
 # CCL_B200_FAST_V1=1 (round-1 kernel kept for A/B).
-python -m pytest tests -m gpu -q -x 2>&1 | tail -5
 libs="$@"; [ -z "$libs" ] && libs="libccl_b200"
 for v in $libs; do
   echo "== $v"
