@@ -58,6 +58,7 @@ SIGNATURES = {
     "ccl_b200_pk2d_new_from_arrays": (_vp, [_dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _ip]),
     "ccl_b200_f2d_free": (None, [_vp]),
     "ccl_b200_f2d_eval_multi": (None, [_vp, _dp, C.c_int, C.c_double, _vp, _dp, _ip]),
+    "ccl_b200_f2d_dlogf_dlk_eval_multi": (None, [_vp, _dp, C.c_int, C.c_double, _vp, _dp, _ip]),
     "ccl_b200_cl_tracer_t_new": (_vp, [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp,
                                        _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
     "ccl_b200_cl_tracer_t_free": (None, [_vp]),

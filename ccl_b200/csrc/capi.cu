@@ -1096,15 +1096,26 @@ void ccl_b200_f2d_free(ccl_b200_f2d* f2d) {
   delete f2d;
 }
 
+static void f2d_eval_multi(ccl_b200_f2d* f2d, const double* lk, int nk, double a, ccl_b200_cosmology* cosmo,
+                          double* out, int* status, int deriv);
 void ccl_b200_f2d_eval_multi(ccl_b200_f2d* f2d, const double* lk, int nk, double a, ccl_b200_cosmology* cosmo,
                              double* out, int* status) {
+  f2d_eval_multi(f2d, lk, nk, a, cosmo, out, status, 0);
+}
+// pk2d_der_eval_multi (pyccl/ccl_pk2d.i:58-64) -> ccl_f2d_t_dlogf_dlk_eval
+void ccl_b200_f2d_dlogf_dlk_eval_multi(ccl_b200_f2d* f2d, const double* lk, int nk, double a, ccl_b200_cosmology* cosmo,
+                                       double* out, int* status) {
+  f2d_eval_multi(f2d, lk, nk, a, cosmo, out, status, 1);
+}
+static void f2d_eval_multi(ccl_b200_f2d* f2d, const double* lk, int nk, double a, ccl_b200_cosmology* cosmo,
+                          double* out, int* status, int deriv) {
   if (*status || !f2d) return;
   std::vector<double> av(nk, a);
   const double* in[2] = {lk, av.data()};
   const size_t nn[2] = {(size_t)nk, (size_t)nk};
   const Cosmo* dcs = (cosmo && cosmo->ts.committed) ? cosmo->ts.d_cosmos : nullptr;
   run_vec(f2d->ts.device, 2, in, nn, nk, out, status, [&](const double* const* di, double* dout, int* dst) {
-    launch_eval_f2d(f2d->ts.d_psp, dcs, nk, di[0], di[1], dout, dst, 0);
+    launch_eval_f2d(f2d->ts.d_psp, dcs, nk, di[0], di[1], dout, dst, 0, deriv);
   });
   if (*status == CCL_B200_ERROR_GROWTH_INIT)
     set_err("ccl_f2d.c: ccl_f2d_t_eval(): growth factor splines have not been precomputed!");

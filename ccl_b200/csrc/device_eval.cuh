@@ -23,19 +23,6 @@ __device__ __forceinline__ double4 ldg4(const double4* p) {
 #endif
 }
 
-// The same load without allocating the line in L1 (streamed tables: with 3 CTAs per SM the Limber kernel leaves
-// ~28 KB of L1, which the reusable spline records should keep; CCLB_PK_NOALLOC selects it for the P(k,a) nodes).
-__device__ __forceinline__ double4 ldg4_stream(const double4* p) {
-  double4 r;
-  asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-  return r;
-}
-#ifdef CCLB_PK_NOALLOC
-#define CCLB_LDG4_PK ldg4_stream
-#else
-#define CCLB_LDG4_PK ldg4
-#endif
-
 // Interval i of a 1-D spline: end points (LDG.128) and coefficients (LDG.256), issued together.
 __device__ __forceinline__ Rec1 load_rec(const Spline1D& s, int i) {
   const double2 a = __ldg(s.xr + i);
@@ -137,8 +124,8 @@ __device__ __forceinline__ double bicubic_eval(const F2D& f, double x, double y,
   const int nk = f.gk.n;
   const double4* r0 = f.tab + (size_t)yi * nk + xi;
   const double4* r1 = r0 + nk;
-  const double4 c00 = CCLB_LDG4_PK(r0), c10 = CCLB_LDG4_PK(r0 + 1);  // (xmin,ymin) (xmax,ymin)
-  const double4 c01 = CCLB_LDG4_PK(r1), c11 = CCLB_LDG4_PK(r1 + 1);  // (xmin,ymax) (xmax,ymax)
+  const double4 c00 = ldg4(r0), c10 = ldg4(r0 + 1);  // (xmin,ymin) (xmax,ymin)
+  const double4 c01 = ldg4(r1), c11 = ldg4(r1 + 1);  // (xmin,ymax) (xmax,ymax)
   const double dx = ax.x1 - ax.x0, dy = ay.x1 - ay.x0;
   const double t = (x - ax.x0) * ax.inv_dx, u = (y - ay.x0) * ay.inv_dx;
   const double um = 1.0 - u;
@@ -243,6 +230,61 @@ static __device__ __noinline__ double f2d_eval(const F2D& f, double lk, double a
     } else
       gz = f.growth_factor_0;
     post *= pow(gz, (double)f.growth_exponent);
+  }
+  return post;
+}
+
+// ccl_f2d_t_dlogf_dlk_eval (src/ccl_f2d.c:375-531): d ln f / d ln k
+static __device__ __noinline__ double f2d_dlogf_dlk_eval(const F2D& f, double lk, double a, const Cosmo* cs, int& st) {
+  if (f.is_k_constant) return 0.0;
+  double inv_pk0 = 1.0;
+  if (!f.is_log) {
+    inv_pk0 = f2d_eval(f, lk, a, cs, st);
+    if (inv_pk0 == 0) return 0.0;
+    inv_pk0 = 1.0 / inv_pk0;
+  }
+  bool is_hiz = false, is_loz = false;
+  double a_ev = a;
+  if (!f.is_a_constant) {
+    is_hiz = a < f.amin;
+    is_loz = a > f.amax;
+    if (is_loz || is_hiz) {
+      if (f.extrap_linear_growth == GROWTH_NONE) { st = ST_ERR_SPLINE_EV; return nan(""); }
+      a_ev = is_loz ? f.amax : f.amin;
+    }
+  }
+  const bool is_hik = lk > f.lkmax, is_lok = lk < f.lkmin;
+  const double lk_ev = is_hik ? f.lkmax : (is_lok ? f.lkmin : lk);
+  double pre = 0.0;
+  int sp = 0;
+  if (f.is_factorizable) {
+    double fk = f.is_log ? 0. : 1., fa = f.is_log ? 0. : 1.;
+    if (f.has_fk) fk = spline_eval(f.fk, lk_ev, 1, sp);
+    if (f.has_fa) fa = spline_eval(f.fa, a_ev, 0, sp);
+    pre = f.is_log ? fk + fa : fk * fa;
+  } else {
+    if (!f.has_fka) pre = f.is_log ? 0. : 1.;
+    else if (!(lk_ev >= f.gk.x0 && lk_ev <= f.gk.xn && a_ev >= f.ga.x0 && a_ev <= f.ga.xn)) sp = ST_GSL_EDOM;
+    else pre = bicubic_eval(f, lk_ev, a_ev, 1);
+  }
+  if (sp) { st = ST_ERR_SPLINE_EV; return nan(""); }
+  double post = pre;
+  if ((is_hik && f.extrap_order_hik > 1) || (is_lok && f.extrap_order_lok > 1)) {
+    const double pd = f.is_factorizable ? spline_eval(f.fk, lk_ev, 2, sp) : bicubic_eval(f, lk_ev, a_ev, 2);
+    if (sp) { st = ST_ERR_SPLINE_EV; return nan(""); }
+    post += pd * (lk - lk_ev);
+  }
+  if (!f.is_log) {
+    post *= inv_pk0;
+    if (is_hiz) {
+      double gz;
+      if (f.extrap_linear_growth == GROWTH_CCL) {
+        if (cs == nullptr || !cs->has_growth) { st = ST_ERR_GROWTH_INIT; return nan(""); }
+        gz = growth_factor(*cs, a, st) / growth_factor(*cs, a_ev, st);
+      } else
+        gz = f.growth_factor_0;
+      post *= pow(gz, (double)f.growth_exponent);
+    }
   }
   return post;
 }

@@ -382,11 +382,11 @@ __global__ void eval_achi_kernel(const Cosmo* cs, int n, const double* chi, doub
 }
 
 __global__ void eval_f2d_kernel(const F2D* f, const Cosmo* cs, int n, const double* lk, const double* a,
-                                double* out, int* status) {
+                                double* out, int* status, int deriv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int st = 0;
-  out[i] = f2d_eval(*f, lk[i], a[i], cs, st);
+  out[i] = deriv ? f2d_dlogf_dlk_eval(*f, lk[i], a[i], cs, st) : f2d_eval(*f, lk[i], a[i], cs, st);
   if (st) atomicCAS(status, 0, st);
 }
 
@@ -410,8 +410,8 @@ void launch_eval_achi(const Cosmo* d_cs, int n, const double* d_chi, double* d_o
   if (n > 0) eval_achi_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_cs, n, d_chi, d_out, d_status);
 }
 void launch_eval_f2d(const F2D* d_f, const Cosmo* d_cs, int n, const double* d_lk, const double* d_a,
-                     double* d_out, int* d_status, cudaStream_t stream) {
-  if (n > 0) eval_f2d_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_f, d_cs, n, d_lk, d_a, d_out, d_status);
+                     double* d_out, int* d_status, cudaStream_t stream, int deriv) {
+  if (n > 0) eval_f2d_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_f, d_cs, n, d_lk, d_a, d_out, d_status, deriv);
 }
 void launch_eval_tracer_kernel(const Tracer* d_tr, int n, const double* d_chi, double* d_out,
                                cudaStream_t stream) {

@@ -267,7 +267,7 @@ double measure_fp64_peak_tflops(cudaStream_t stream);
 void launch_eval_achi(const Cosmo* d_cs, int n, const double* d_chi, double* d_out, int* d_status,
                       cudaStream_t stream);
 void launch_eval_f2d(const F2D* d_f, const Cosmo* d_cs, int n, const double* d_lk, const double* d_a,
-                     double* d_out, int* d_status, cudaStream_t stream);
+                     double* d_out, int* d_status, cudaStream_t stream, int deriv = 0);  // deriv: d ln f / d ln k
 void launch_eval_tracer_kernel(const Tracer* d_tr, int n, const double* d_chi, double* d_out,
                                cudaStream_t stream);
 void launch_eval_tracer_transfer(const Tracer* d_tr, int n, const double* d_lk, const double* d_a,

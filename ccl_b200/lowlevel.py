@@ -111,12 +111,14 @@ class LibF2D:
         self.status = st.value
         _check(st.value, "f2d_new")
 
-    def eval(self, lk, a, cosmo=None):
+    def eval(self, lk, a, cosmo=None, derivative=False):
+        """pk2d_eval_multi / pk2d_der_eval_multi (pyccl/ccl_pk2d.i:48-64): f or d ln f / d ln k at (lk[], a)."""
         k, p = darr(np.atleast_1d(lk))
         out = np.empty_like(k)
         st = C.c_int(0)
-        _lib.load().ccl_b200_f2d_eval_multi(self.h, p, len(k), float(a), cosmo.h if cosmo is not None else None,
-                                            out.ctypes.data_as(_lib._dp), C.byref(st))
+        fn = _lib.load().ccl_b200_f2d_dlogf_dlk_eval_multi if derivative else _lib.load().ccl_b200_f2d_eval_multi
+        fn(self.h, p, len(k), float(a), cosmo.h if cosmo is not None else None, out.ctypes.data_as(_lib._dp),
+           C.byref(st))
         return out, st.value
 
     def __del__(self):

@@ -101,9 +101,8 @@ class Pk2D:
         return self._psp
 
     def __call__(self, k, a, cosmo=None, *, derivative=False):
-        """P(k, a) on the device (pk2d_eval_multi, pyccl/ccl_pk2d.i:55-62)."""
-        if derivative:
-            raise NotImplementedError("dlogP/dlogk is not on the Limber path")
+        """P(k, a) or, with `derivative`, d ln P / d ln k on the device (pk2d_eval_multi / pk2d_der_eval_multi,
+        pyccl/ccl_pk2d.i:48-64; pyccl/pk2d.py:244-306)."""
         a_use = np.atleast_1d(a).astype(float)
         k_use = np.atleast_1d(k).astype(float)
         lk_use = np.log(k_use)
@@ -114,7 +113,7 @@ class Pk2D:
         psp = self._device()
         out = np.zeros([len(a_use), len(k_use)])
         for ia, aa in enumerate(a_use):
-            out[ia], status = psp.eval(lk_use, aa, dev_cosmo)
+            out[ia], status = psp.eval(lk_use, aa, dev_cosmo, derivative=derivative)
             check(status, cosmo)
         if np.ndim(k) == 0:
             out = np.squeeze(out, axis=-1)

@@ -124,6 +124,9 @@ void ccl_b200_f2d_free(ccl_b200_f2d *f2d);
  * cosmo may be NULL when no growth extrapolation is needed. */
 void ccl_b200_f2d_eval_multi(ccl_b200_f2d *f2d, const double *lk, int nk, double a, ccl_b200_cosmology *cosmo,
                              double *out, int *status);
+/* pk2d_der_eval_multi (pyccl/ccl_pk2d.i:58-64) -> ccl_f2d_t_dlogf_dlk_eval (src/ccl_f2d.c:375-531): d ln f / d ln k */
+void ccl_b200_f2d_dlogf_dlk_eval_multi(ccl_b200_f2d *f2d, const double *lk, int nk, double a,
+                                       ccl_b200_cosmology *cosmo, double *out, int *status);
 
 /* ---- ccl_cl_tracer_t (include/ccl_tracers.h:46-59, src/ccl_tracers.c:569-691) ---- */
 ccl_b200_tracer *ccl_b200_cl_tracer_t_new(ccl_b200_cosmology *cosmo, int der_bessel, int der_angles,

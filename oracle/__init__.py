@@ -69,6 +69,8 @@ def lib():
         L.o_f2d_free.argtypes = [vp]
         L.o_f2d_eval.restype = C.c_double
         L.o_f2d_eval.argtypes = [vp, C.c_double, C.c_double, vp, _ip]
+        L.o_f2d_dlogf_dlk_eval.restype = C.c_double
+        L.o_f2d_dlogf_dlk_eval.argtypes = [vp, C.c_double, C.c_double, vp, _ip]
         L.o_tracer_new.restype = vp
         L.o_tracer_new.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp,
                                    _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _ip]
@@ -240,6 +242,12 @@ class F2D:
     def __call__(self, lk, a, cosmo=None):
         st = C.c_int(0)
         v = lib().o_f2d_eval(self.h, float(lk), float(a), cosmo.h if cosmo else None, C.byref(st))
+        return v, st.value
+
+    def dlogf_dlk(self, lk, a, cosmo=None):
+        """ccl_f2d_t_dlogf_dlk_eval (src/ccl_f2d.c:375-531)."""
+        st = C.c_int(0)
+        v = lib().o_f2d_dlogf_dlk_eval(self.h, float(lk), float(a), cosmo.h if cosmo else None, C.byref(st))
         return v, st.value
 
     def __del__(self):

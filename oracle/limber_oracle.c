@@ -689,6 +689,70 @@ double o_f2d_eval(const o_f2d *f2d, double lk, double a, const o_cosmo *cosmo, i
   return fka_post;
 }
 
+/* ccl_f2d_t_dlogf_dlk_eval (src/ccl_f2d.c:375-531): d ln f / d ln k; in k-extrapolation the slope of the Taylor
+ * branch (orders > 1 add the second derivative times the distance), for non-log tables divided by f itself */
+double o_f2d_dlogf_dlk_eval(const o_f2d *f2d, double lk, double a, const o_cosmo *cosmo, int *status) {
+  if (f2d->is_k_constant) return 0;
+  double inv_pk0 = 1.;
+  if (!f2d->is_log) {
+    inv_pk0 = o_f2d_eval(f2d, lk, a, cosmo, status);
+    if (inv_pk0 == 0) return 0;
+    inv_pk0 = 1. / inv_pk0;
+  }
+  int is_hiz, is_loz;
+  double a_ev = a;
+  if (f2d->is_a_constant) { is_hiz = 0; is_loz = 0; }
+  else {
+    is_hiz = a < f2d->amin;
+    is_loz = a > f2d->amax;
+    if (is_loz || is_hiz) {
+      if (f2d->extrap_linear_growth == O_F2D_NOEXTRAPOL) { *status = O_ERR_SPLINE_EV; return NAN; }
+      a_ev = is_loz ? f2d->amax : f2d->amin;
+    }
+  }
+  double fka_pre, fka_post, lk_ev = lk;
+  const int is_hik = lk > f2d->lkmax, is_lok = lk < f2d->lkmin;
+  if (is_hik) lk_ev = f2d->lkmax;
+  else if (is_lok) lk_ev = f2d->lkmin;
+  int spstatus = 0;
+  if (f2d->is_factorizable) {
+    double fk, fa;
+    if (f2d->fk == NULL) fk = f2d->is_log ? 0 : 1;
+    else spstatus |= o_cspline_eval_e(f2d->fk, lk_ev, 1, &fk);
+    if (f2d->fa == NULL) fa = f2d->is_log ? 0 : 1;
+    else spstatus |= o_cspline_eval_e(f2d->fa, a_ev, 0, &fa);
+    fka_pre = f2d->is_log ? fk + fa : fk * fa;
+  } else {
+    if (f2d->fka == NULL) fka_pre = f2d->is_log ? 0 : 1;
+    else spstatus = o_bicubic_eval_e(f2d->fka, lk_ev, a_ev, 1, &fka_pre);
+  }
+  if (spstatus) { *status = O_ERR_SPLINE_EV; return NAN; }
+  fka_post = fka_pre;
+  if (is_hik || is_lok) {
+    const int order = is_hik ? f2d->extrap_order_hik : f2d->extrap_order_lok;
+    if (order > 1) {
+      double pd;
+      if (f2d->is_factorizable) spstatus = o_cspline_eval_e(f2d->fk, lk_ev, 2, &pd);
+      else spstatus = o_bicubic_eval_e(f2d->fka, lk_ev, a_ev, 2, &pd);
+      if (spstatus) { *status = O_ERR_SPLINE_EV; return NAN; }
+      fka_post += pd * (lk - lk_ev);
+    }
+  }
+  if (!f2d->is_log) {
+    fka_post *= inv_pk0;
+    if (is_hiz) {
+      double gz;
+      if (f2d->extrap_linear_growth == O_F2D_CCLGROWTH) {
+        if (!cosmo || !cosmo->growth) { *status = O_ERR_GROWTH_INIT; return NAN; }
+        gz = o_growth_factor(cosmo, a, status) / o_growth_factor(cosmo, a_ev, status);
+      } else
+        gz = f2d->growth_factor_0;
+      fka_post *= pow(gz, f2d->growth_exponent);
+    }
+  }
+  return fka_post;
+}
+
 /* ------------------------------------------------------------------ */
 /* ccl_cl_tracer_t (src/ccl_tracers.c:569-749)                         */
 /* ------------------------------------------------------------------ */

@@ -296,7 +296,7 @@ def test_full_size_batch_properties():
     cl2, _, _ = batch.angular_cl(colls, pairs, ells)
     assert np.array_equal(cl, cl2)
     rng = np.random.default_rng(5)
-    for ic, q in zip(rng.integers(0, n, 6), rng.integers(0, len(pairs), 6)):
+    for ic, q in zip(rng.integers(0, n, 64), rng.integers(0, len(pairs), 64)):
         t = tables[ic % nd]
         shift = 1e-3 * (ic // nd)
         redo = lambda: _oracle_all(t["bg"], t["pk"], t["subs"], t["colls"], [pairs[q]], ells, logp_shift=shift)[0][0]
