@@ -253,38 +253,65 @@ __global__ void __launch_bounds__(BW * 32) corr_bessel_kernel(CorrF1D f, CorrPro
   }
 }
 
-// ccl_tracer_corr_legendre: one thread per theta runs the upward recurrences of gsl_sf_legendre_Pl_array /
-// gsl_sf_legendre_Plm(l, 2, x) (legendre_poly.c) and the sum over l = 1..lmax-1 in the reference's order
-__global__ void corr_legendre_kernel(int lmax, const double* cl_arr, CorrProblem P) {
-  const int ith = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ith >= P.n_theta) return;
-  const double cth = cos(P.theta[ith] * PI / 180);
-  double sum = 0.0;
-  if (P.corr_type == CORR_GG) {
-    double p_ellm2 = 1.0, p_ellm1 = cth;
-    if (lmax > 1) sum += cl_arr[1] * (cth * 3);
-    for (int ell = 2; ell < lmax; ell++) {
-      const double p_ell = (cth * (2 * ell - 1) * p_ellm1 - (ell - 1) * p_ellm2) / ell;
-      p_ellm2 = p_ellm1; p_ellm1 = p_ell;
-      sum += cl_arr[ell] * (p_ell * (2 * ell + 1));
+// ccl_tracer_corr_legendre.  The upward recurrences of gsl_sf_legendre_Pl_array / gsl_sf_legendre_Plm(l, 2, x)
+// (legendre_poly.c) are sequential in l, so one thread per theta walks all multipoles; what does not depend on
+// theta -- the recurrence coefficients (2l-1)/l, (l-1)/l (or (2l-1)/(l-2), (l+1)/(l-2) for P_l^2) and the weighted
+// spectrum C_l (2l+1) (or C_l (2l+1)/(l(l+1))) -- is tabulated in parallel first (corr_legendre_tables), which takes
+// the divisions out of the 60000-step chain.  The sum runs over l = 1..lmax-1 in the reference's order.
+__global__ void corr_legendre_tables(int lmax, int corr_type, const double* cl_arr, double* ra, double* rb, double* clw) {
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l <= lmax; l += gridDim.x * blockDim.x) {
+    const double dl = (double)l;
+    if (corr_type == CORR_GG) {
+      ra[l] = l ? (2 * dl - 1) / dl : 0.0;
+      rb[l] = l ? (dl - 1) / dl : 0.0;
+      clw[l] = cl_arr[l] * (2 * dl + 1);
+    } else {
+      ra[l] = l > 2 ? (2 * dl - 1) / (dl - 2) : 0.0;
+      rb[l] = l > 2 ? (dl + 1) / (dl - 2) : 0.0;
+      clw[l] = l >= 2 ? cl_arr[l] * ((2 * dl + 1.) / ((dl + 0.) * (dl + 1.))) : 0.0;
     }
-  } else {  // CORR_GL
+  }
+}
+
+constexpr int LT = 1024;  // multipoles per shared-memory tile of the three tables
+
+// One warp per 32 thetas: the lanes load a tile of the tables together (coalesced), then each lane advances its own
+// recurrence through the tile from shared memory (all lanes read the same element: a broadcast).
+__global__ void __launch_bounds__(32) corr_legendre_kernel(int lmax, const double* ra, const double* rb,
+                                                           const double* clw, CorrProblem P) {
+  __shared__ double s_ra[LT], s_rb[LT], s_cw[LT];
+  const int lane = threadIdx.x;
+  const int ith = blockIdx.x * 32 + lane;
+  const bool live = ith < P.n_theta;
+  const double cth = live ? cos(P.theta[ith] * PI / 180) : 0.0;
+  const bool gg = P.corr_type == CORR_GG;
+  // the first terms: l = 1 for P_l (P_0 = 1, P_1 = x); l = 2, 3 for P_l^2 (P_2^2 = 3 (1-x)(1+x), P_3^2 = 5 x P_2^2)
+  double p2, p1, sum = 0.0;
+  int l0;
+  if (gg) {
+    p2 = 1.0; p1 = cth; l0 = 2;
+    if (lmax > 1) sum += clw[1] * cth;
+  } else {
     const double root_factor = sqrt(1.0 - cth) * sqrt(1.0 + cth);
     double p_mm = 1.0, fact_coeff = 1.0;
     for (int i = 1; i <= 2; i++) { p_mm *= -fact_coeff * root_factor; fact_coeff += 2.0; }
-    double p_ellm2 = p_mm, p_ellm1 = cth * 5 * p_mm;
-    for (int j = 2; j < lmax; j++) {
-      double p;
-      if (j == 2) p = p_mm;
-      else if (j == 3) p = p_ellm1;
-      else {
-        p = (cth * (2 * j - 1) * p_ellm1 - (j + 1) * p_ellm2) / (j - 2);
-        p_ellm2 = p_ellm1; p_ellm1 = p;
-      }
-      sum += cl_arr[j] * (p * ((2 * j + 1.) / ((j + 0.) * (j + 1.))));
+    p2 = p_mm; p1 = cth * 5 * p_mm; l0 = 4;
+    if (lmax > 2) sum += clw[2] * p2;
+    if (lmax > 3) sum += clw[3] * p1;
+  }
+  for (int base = l0; base < lmax; base += LT) {
+    const int n = min(LT, lmax - base);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) { s_ra[i] = ra[base + i]; s_rb[i] = rb[base + i]; s_cw[i] = clw[base + i]; }
+    __syncwarp();
+#pragma unroll 8
+    for (int i = 0; i < n; ++i) {
+      const double p = cth * s_ra[i] * p1 - s_rb[i] * p2;
+      p2 = p1; p1 = p;
+      sum += s_cw[i] * p;
     }
   }
-  P.wtheta[ith] = sum / (PI * 4);
+  if (live) P.wtheta[ith] = sum / (PI * 4);
 }
 
 // ---- generalised FFTLog: ccl_fftlog_ComputeXi_general = general_fht (src/ccl_fftlog.c:330-503), batched over mu ----
@@ -424,7 +451,7 @@ size_t correlation_work_bytes(int method, int n_ell, int n_theta, int n_ell_corr
     const size_t warps = (size_t)std::min((n_theta + BW - 1) / BW, 148 * 8) * BW;
     b += up256(warps * 4 * n_iteration * 8);
   } else {
-    b += up256(((size_t)ell_max_corr + 1) * 8);
+    b += up256(((size_t)ell_max_corr + 1) * 8) * 4;  // cl_arr, ra, rb, clw
   }
   return b;
 }
@@ -500,10 +527,15 @@ cudaError_t launch_correlation(const CorrProblem& P, cudaStream_t stream) {
     corr_bessel_kernel<<<nblk, BW * 32, 0, stream>>>(f, P, reinterpret_cast<double*>(p));
   } else {
     const int lmax = (int)P.ell_max_corr;
+    const size_t tb = up256(((size_t)lmax + 1) * 8);
     double* cl_arr = reinterpret_cast<double*>(p);
+    double* ra = reinterpret_cast<double*>(p + tb);
+    double* rb = reinterpret_cast<double*>(p + 2 * tb);
+    double* clw = reinterpret_cast<double*>(p + 3 * tb);
     corr_eval_kernel<<<(lmax + 1 + 127) / 128, 128, 0, stream>>>(f, lmax + 1, nullptr, cl_arr, P.do_taper, taper, 0);
-    // one thread per theta, spread over the SMs (the recurrence in l is sequential)
-    corr_legendre_kernel<<<(P.n_theta + 31) / 32, 32, 0, stream>>>(lmax, cl_arr, P);
+    corr_legendre_tables<<<(lmax + 1 + 127) / 128, 128, 0, stream>>>(lmax, P.corr_type, cl_arr, ra, rb, clw);
+    // neighbouring thetas share a warp: their table reads coalesce into broadcasts
+    corr_legendre_kernel<<<(P.n_theta + 31) / 32, 32, 0, stream>>>(lmax, ra, rb, clw, P);
   }
   return cudaGetLastError();
 }

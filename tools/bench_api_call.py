@@ -21,8 +21,14 @@ ell = np.arange(2, 2001).astype(float)
 t1 = time.perf_counter()
 cl = ccl.angular_cl(cosmo, lens1, lens2, ell, limber_integration_method='spline')
 t2 = time.perf_counter()
-print("setup (cosmology tables + tracers, host) %.1f ms; first angular_cl call (upload + kernels) %.1f ms" %
-      ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+print("first setup (library load + CUDA context + cosmology tables + tracers) %.1f ms; first angular_cl call "
+      "(upload + kernels) %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+t0 = time.perf_counter()
+cosmo_b = ccl.Cosmology(Omega_c=0.26, Omega_b=0.045, h=0.68, sigma8=0.81, n_s=0.96, transfer_function='bbks')
+lens_b = ccl.WeakLensingTracer(cosmo_b, dndz=(z, n))
+cl_b = ccl.angular_cl(cosmo_b, lens_b, lens_b, ell, limber_integration_method='spline')
+print("a second cosmology, parameters -> tables (device builders) -> tracer -> %d C_ell: %.1f ms" %
+      (ell.size, (time.perf_counter() - t0) * 1e3))
 for method in ("spline", "qag_quad"):
     ts = []
     for _ in range(20):
@@ -42,3 +48,31 @@ for method, m in (("spline", oracle.INTEG_SPLINE), ("qag_quad", oracle.INTEG_QAG
         ref = oracle.angular_cl(oc, otr["a"], otr["b"], op, ell, m)[0]
         ts.append(time.perf_counter() - ta)
     print("oracle %-9s on %d host threads: median %.2f ms" % (method, oracle.num_threads(), np.median(ts) * 1e3))
+
+# ---- the consumers either side of angular_cl: C_ell -> xi(theta) and the FKEM non-Limber branch ----
+theta = np.geomspace(0.01, 5.0, 30)
+for method in ("fftlog", "legendre", "bessel"):
+    ts, to = [], []
+    for _ in range(6):
+        ta = time.perf_counter()
+        xi = ccl.correlation(cosmo, ell=ell, C_ell=cl, theta=theta, type='NN', method=method)
+        ts.append(time.perf_counter() - ta)
+    for _ in range(3):
+        ta = time.perf_counter()
+        ref, st = oracle.correlation(ell, cl, theta, 'NN', method)
+        to.append(time.perf_counter() - ta)
+    print("correlation %-8s %d angles: device median %.3f ms, oracle on %d host threads %.2f ms, max |dev - oracle| / max|xi| %.1e"
+          % (method, theta.size, np.median(ts) * 1e3, oracle.num_threads(), np.median(to) * 1e3,
+             np.max(np.abs(xi - ref)) / np.max(np.abs(ref))))
+zz = np.linspace(0.01, 2.0, 200)
+nc = ccl.NumberCountsTracer(cosmo, has_rsd=False, dndz=(zz, np.exp(-((zz - 1.0) ** 2) / 0.1)), bias=(zz, np.ones_like(zz)))
+ls = np.unique(np.geomspace(2, 2000, 128).astype(int)).astype(float)
+for kw, name in ((dict(l_limber=-1), "Limber only"), (dict(l_limber=200, fkem_Nchi=400, fkem_chi_min=1e-4), "FKEM to l=200"),
+                 (dict(l_limber='auto', fkem_Nchi=400, fkem_chi_min=1e-4), "FKEM auto")):
+    ts = []
+    for _ in range(4):
+        nc._fkem_fft = None  # no reuse of cached transforms between repetitions
+        ta = time.perf_counter()
+        c, meta = ccl.angular_cl(cosmo, nc, nc, ls, return_meta=True, **kw)
+        ts.append(time.perf_counter() - ta)
+    print("angular_cl %-14s %d ells: median %.2f ms (l_limber %s)" % (name, ls.size, np.median(ts) * 1e3, meta['l_limber']))
