@@ -124,6 +124,9 @@ class PipelinedBatch:
                  # thread is latency-bound (3.9 ms per 64 cosmologies against 1.3 ms on an idle GPU)
 
     def __init__(self, ncosmo, nchunks=None, params=None):
+        import os
+        self.NSTAGE = int(os.environ.get("CCL_B200_NSTAGE", self.NSTAGE))
+        self.NCOMMIT = int(os.environ.get("CCL_B200_NCOMMIT", self.NCOMMIT))
         self.ncosmo = int(ncosmo)
         sizes = chunk_sizes(self.ncosmo, nchunks)
         offs = np.concatenate([[0], np.cumsum(sizes)])
