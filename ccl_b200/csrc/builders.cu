@@ -69,18 +69,22 @@ __global__ void bg_distance_kernel(int na, const double* __restrict__ a_grid, co
   }
 }
 
-// a(chi) on a uniform chi grid of step <= dchi: Newton iterations seeded by the previous node's root
-// and stopped when |da| < epsrel |a| (a_of_chi, src/ccl_background.c:370-410, 498-571).  The chain is
-// sequential by construction; a half-warp per cosmology spreads the 12 quadrature nodes of every
-// chi(a) evaluation over its lanes.
-__global__ void __launch_bounds__(128)
+// a(chi) on a uniform chi grid of step <= dchi: Newton iterations stopped when |da| < epsrel |a| (a_of_chi,
+// src/ccl_background.c:370-410, 498-571).  The reference walks the grid seeding every node with the previous root;
+// here one CTA per cosmology cuts the grid into ACHI_HW runs, one per half-warp: the first node of a run is seeded
+// by linear inverse interpolation of the chi(a) table, the others by the previous root as in the reference (Newton
+// converges quadratically: the accepted root does not depend on the seed beyond its last bits).  A half-warp
+// spreads the 12 quadrature nodes of every chi(a) evaluation over its lanes.
+constexpr int ACHI_HW = 16;  // half-warps (runs of consecutive chi nodes) per cosmology
+
+__global__ void __launch_bounds__(16 * ACHI_HW)
 bg_achi_kernel(int ncosmo, int na, const double* __restrict__ a_grid, const double* __restrict__ params,
                const double* __restrict__ chi, double dchi, double epsrel, int nmax, int stride,
                int* __restrict__ n_out, double* __restrict__ achi_chi, double* __restrict__ achi_a) {
-  const int sub = threadIdx.x & 15;                                  // lane within the half-warp
-  const int ic = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;       // one cosmology per half-warp
-  const unsigned hmask = 0xffffu << (threadIdx.x & 16);              // the half-warp's lanes
-  if (ic >= ncosmo) return;
+  const int sub = threadIdx.x & 15;                      // lane within the half-warp
+  const int hw = threadIdx.x >> 4;                       // run index
+  const int ic = blockIdx.x;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);  // the half-warp's lanes
   const double* p = params + (size_t)ic * CCL_B200_NPAR;
   const double* ch = chi + (size_t)ic * na;
   double* gx = achi_chi + (size_t)ic * stride;
@@ -89,7 +93,7 @@ bg_achi_kernel(int ncosmo, int na, const double* __restrict__ a_grid, const doub
   const double a0 = a_grid[na - 1], af = a_grid[0];
   int n = (int)((chif - chi0) / dchi);
   if (n > stride) n = -n;  // reported to the host: the caller's stride is too small
-  if (sub == 0) n_out[ic] = n;
+  if (threadIdx.x == 0) n_out[ic] = n;
   if (n < 5) return;
   const double dx = (chif - chi0) / (n - 1.);
   // 12-point panel with one node per lane, summed in node order by lane 0's shuffle chain so that the
@@ -102,16 +106,31 @@ bg_achi_kernel(int ncosmo, int na, const double* __restrict__ a_grid, const doub
     for (int q = 0; q < 12; ++q) s += __shfl_sync(hmask, term, q, 16);
     return half * s;
   };
-  int j = na - 1;  // a_grid[j-1] <= cur < a_grid[j], hunted downwards as chi grows
+  int j = na - 1;  // a_grid[j-1] <= cur < a_grid[j], hunted as chi grows
   auto chi_of = [&](double a) -> double {
     if (a >= 1.0) return (a > 1.0) ? -panel(1.0, a) : 0.0;
     while (j > 1 && a < a_grid[j - 1]) --j;
     while (j < na - 1 && a >= a_grid[j]) ++j;
     return ch[j] + panel(a, a_grid[j]);
   };
-  if (sub == 0) { gx[0] = chi0; ga[0] = a0; }
+  if (threadIdx.x == 0) { gx[0] = chi0; ga[0] = a0; gx[n - 1] = chif; ga[n - 1] = af; }
+  // interior nodes 1..n-2 in ACHI_HW runs
+  const int per = (n - 2 + ACHI_HW - 1) / ACHI_HW;
+  const int i_lo = 1 + hw * per, i_hi = min(i_lo + per, n - 1);
+  if (i_lo >= i_hi) return;
   double cur = a0;
-  for (int i = 1; i < n - 1; ++i) {
+  if (hw > 0) {  // seed of the run: the chi(a) table inverted linearly around chi(i_lo - 1)
+    const double t = chi0 + dx * (i_lo - 1);
+    int lo = 0, hi = na - 1;  // ch decreases with the index: ch[lo] >= t >= ch[hi]
+    while (hi > lo + 1) {
+      const int m = (hi + lo) >> 1;
+      if (ch[m] >= t) lo = m; else hi = m;
+    }
+    const double w = (ch[lo] - t) / (ch[lo] - ch[hi]);
+    cur = a_grid[lo] + w * (a_grid[hi] - a_grid[lo]);
+    j = hi;
+  }
+  for (int i = i_lo; i < i_hi; ++i) {
     const double target = chi0 + dx * i;
     double f = target - chi_of(cur);
     double df = chi_integrand(p, cur);
@@ -126,61 +145,129 @@ bg_achi_kernel(int ncosmo, int na, const double* __restrict__ a_grid, const doub
     }
     if (sub == 0) { gx[i] = target; ga[i] = cur; }
   }
-  if (sub == 0) { gx[n - 1] = chif; ga[n - 1] = af; }
 }
 
 // Linear growth: y0' = y1 / (a^3 E), y1' = 1.5 E a Omega_m(a) y0 from a_i with y0 = a_i, y1 = a_i^3 E(a_i)
 // (src/ccl_background.c:153-165, 209-284), integrated in ln a with classical RK4 at a step far below
-// the reference's RKCK tolerance (1e-6); D = y0 / y0(1), f = y1 / (a^2 E y0).  One thread per cosmology.
-__global__ void bg_growth_kernel(int ncosmo, int na, const double* __restrict__ a_grid, const double* __restrict__ params,
-                                 double a_init, double hmax, double* __restrict__ growth, double* __restrict__ fgrowth,
-                                 double* __restrict__ growth0) {
-  const int ic = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ic >= ncosmo) return;
+// the reference's RKCK tolerance (1e-6); D = y0 / y0(1), f = y1 / (a^2 E y0).
+//
+// One CTA per cosmology.  The system is linear, y' = A(ln a) y, and so is an RK4 step: the steps between two
+// a-nodes (ns = ceil(span / hmax) steps of span / ns, as a serial integration would take them) are cut into
+// segments of at most GSEG steps, every thread propagates the two basis vectors through its segments -- a 2x2
+// transfer matrix each, three evaluations of E(a) per step -- and one thread chains the matrices node by node.
+// The serial chain shrinks from ~7000 RK4 steps (2300 of them between a_init = 1e-6 and the first node) to GSEG
+// steps plus ~650 2x2 products; the result is the serial one up to the rounding of the linear combinations.
+constexpr int GSEG = 16;
+constexpr int GROWTH_THREADS = 256;
+// segments of the whole integration: at most one partial segment per node plus the full ones
+inline int growth_seg_cap(int na, double a_init, double hmax) {
+  return na + (int)(log(1.0 / a_init) / hmax / GSEG) + 8;
+}
+
+__global__ void __launch_bounds__(GROWTH_THREADS)
+bg_growth_kernel(int ncosmo, int na, const double* __restrict__ a_grid, const double* __restrict__ params, double a_init,
+                 double hmax, int seg_cap, double* __restrict__ growth, double* __restrict__ fgrowth,
+                 double* __restrict__ growth0) {
+  extern __shared__ double4 growth_sm[];
+  double4* s_M = growth_sm;                                       // [seg_cap] transfer matrix {m00, m01, m10, m11}
+  double2* s_y = reinterpret_cast<double2*>(s_M + seg_cap);       // [na] (y0, y1) at node i
+  int* s_first = reinterpret_cast<int*>(s_y + na);                // [na + 1] first segment of node i
+  const int ic = blockIdx.x;
   const double* p = params + (size_t)ic * CCL_B200_NPAR;
-  auto rhs = [&](double lna, double y0, double y1, double& d0, double& d1) {
+  const double lna_init = log(a_init);
+  // interval of node i: from the previous node (or a_init) to a_grid[i]; ns steps of h = span / ns
+  auto interval = [&](int i, double& lna0, double& h, int& ns) {
+    const double a = a_grid[i];
+    const double prev = (i > 0 && a_grid[i - 1] >= a_init) ? log(a_grid[i - 1]) : lna_init;
+    const double span = log(a) - prev;
+    lna0 = prev;
+    ns = (a >= a_init && span > 0) ? (int)ceil(span / hmax) : 0;
+    h = ns ? span / ns : 0.0;
+  };
+  for (int i = threadIdx.x; i < na; i += blockDim.x) {
+    double lna0, h;
+    int ns;
+    interval(i, lna0, h, ns);
+    s_first[i + 1] = (ns + GSEG - 1) / GSEG;
+  }
+  if (threadIdx.x == 0) s_first[0] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int i = 0; i < na; ++i) s_first[i + 1] += s_first[i];
+  __syncthreads();
+  const int nseg = s_first[na];
+  // coefficients of y' = (c0 y1, c1 y0) at ln a
+  auto coef = [&](double lna, double& c0, double& c1) {
     const double a = exp(lna);
     const double hn = h_over_h0(p, a);
     const double om = (p[P_OC] + p[P_OB]) / (a * a * a) / hn / hn;
-    d0 = a * y1 / (a * a * a * hn);
-    d1 = a * 1.5 * hn * a * om * y0;
+    c0 = a / (a * a * a * hn);
+    c1 = a * 1.5 * hn * a * om;
   };
-  double lna = log(a_init);
-  double y0 = a_init, y1 = a_init * a_init * a_init * h_over_h0(p, a_init);
+  for (int sg = threadIdx.x; sg < nseg && sg < seg_cap; sg += blockDim.x) {
+    int lo = 0, hi = na;  // node i with s_first[i] <= sg < s_first[i + 1]
+    while (hi > lo + 1) {
+      const int m = (hi + lo) >> 1;
+      if (s_first[m] > sg) hi = m; else lo = m;
+    }
+    double lna0, h;
+    int ns;
+    interval(lo, lna0, h, ns);
+    const int s0 = (sg - s_first[lo]) * GSEG, s1 = min(s0 + GSEG, ns);
+    double lna = lna0 + s0 * h;
+    double u0 = 1.0, u1 = 0.0, v0 = 0.0, v1 = 1.0;  // images of the basis vectors (1, 0) and (0, 1)
+    double ca0, ca1;
+    coef(lna, ca0, ca1);
+    for (int st = s0; st < s1; ++st) {
+      double cm0, cm1, cb0, cb1;
+      coef(lna + 0.5 * h, cm0, cm1);
+      coef(lna + h, cb0, cb1);
+      auto step = [&](double& y0, double& y1) {
+        const double k10 = ca0 * y1, k11 = ca1 * y0;
+        const double k20 = cm0 * (y1 + 0.5 * h * k11), k21 = cm1 * (y0 + 0.5 * h * k10);
+        const double k30 = cm0 * (y1 + 0.5 * h * k21), k31 = cm1 * (y0 + 0.5 * h * k20);
+        const double k40 = cb0 * (y1 + h * k31), k41 = cb1 * (y0 + h * k30);
+        y0 += h / 6.0 * (k10 + 2 * k20 + 2 * k30 + k40);
+        y1 += h / 6.0 * (k11 + 2 * k21 + 2 * k31 + k41);
+      };
+      step(u0, u1);
+      step(v0, v1);
+      lna += h;
+      ca0 = cb0; ca1 = cb1;
+    }
+    s_M[sg] = make_double4(u0, v0, u1, v1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double y0 = a_init, y1 = a_init * a_init * a_init * h_over_h0(p, a_init);
+    int sg = 0;
+    for (int i = 0; i < na; ++i) {
+      const int end = min(s_first[i + 1], seg_cap);
+      for (; sg < end; ++sg) {
+        const double4 M = s_M[sg];
+        const double n0 = M.x * y0 + M.y * y1, n1 = M.z * y0 + M.w * y1;
+        y0 = n0; y1 = n1;
+      }
+      s_y[i] = make_double2(y0, y1);
+    }
+  }
+  __syncthreads();
   double* D = growth + (size_t)ic * na;
   double* F = fgrowth + (size_t)ic * na;
-  for (int i = 0; i < na; ++i) {
+  // the a-grid ends at a = 1 (A_SPLINE_MAX is fixed to 1): normalise D(1) = 1
+  const double g0 = s_y[na - 1].x;
+  if (threadIdx.x == 0) growth0[ic] = g0;
+  for (int i = threadIdx.x; i < na; i += blockDim.x) {
     const double a = a_grid[i];
     if (a < a_init) {  // below the starting point the reference sets D = a, f = 1
       D[i] = a;
       F[i] = 1.0;
-      continue;
+    } else {
+      const double2 y = s_y[i];
+      D[i] = y.x / g0;
+      F[i] = y.y / (a * a * h_over_h0(p, a) * y.x);
     }
-    const double target = log(a);
-    const double span = target - lna;
-    if (span > 0) {
-      const int ns = (int)ceil(span / hmax);
-      const double h = span / ns;
-      for (int s = 0; s < ns; ++s) {
-        double k10, k11, k20, k21, k30, k31, k40, k41;
-        rhs(lna, y0, y1, k10, k11);
-        rhs(lna + 0.5 * h, y0 + 0.5 * h * k10, y1 + 0.5 * h * k11, k20, k21);
-        rhs(lna + 0.5 * h, y0 + 0.5 * h * k20, y1 + 0.5 * h * k21, k30, k31);
-        rhs(lna + h, y0 + h * k30, y1 + h * k31, k40, k41);
-        y0 += h / 6.0 * (k10 + 2 * k20 + 2 * k30 + k40);
-        y1 += h / 6.0 * (k11 + 2 * k21 + 2 * k31 + k41);
-        lna += h;
-      }
-      lna = target;
-    }
-    D[i] = y0;
-    F[i] = y1 / (a * a * h_over_h0(p, a) * y0);
   }
-  // the a-grid ends at a = 1 (A_SPLINE_MAX is fixed to 1): normalise D(1) = 1
-  const double g0 = D[na - 1];
-  growth0[ic] = g0;
-  for (int i = 0; i < na; ++i)
-    if (a_grid[i] >= a_init) D[i] /= g0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -954,10 +1041,15 @@ void launch_build_background(int ncosmo, int na, const double* d_a, const double
                              double* d_growth0, cudaStream_t stream) {
   if (ncosmo <= 0) return;
   bg_distance_kernel<<<ncosmo, 128, sizeof(double) * na, stream>>>(na, d_a, d_params, d_E, d_chi);
-  bg_achi_kernel<<<(ncosmo * 16 + 127) / 128, 128, 0, stream>>>(ncosmo, na, d_a, d_params, d_chi, dchi, epsrel, nmax, stride,
-                                                         d_n, d_achi_chi, d_achi_a);
-  bg_growth_kernel<<<(ncosmo + 31) / 32, 32, 0, stream>>>(ncosmo, na, d_a, d_params, a_init, 2.0e-3, d_growth,
-                                                           d_fgrowth, d_growth0);
+  bg_achi_kernel<<<ncosmo, 16 * ACHI_HW, 0, stream>>>(ncosmo, na, d_a, d_params, d_chi, dchi, epsrel, nmax, stride, d_n,
+                                                      d_achi_chi, d_achi_a);
+  const double hmax = 2.0e-3;
+  const int seg_cap = growth_seg_cap(na, a_init, hmax);
+  const size_t gsm = (size_t)seg_cap * sizeof(double4) + (size_t)na * sizeof(double2) + ((size_t)na + 1) * sizeof(int);
+  if (gsm > 48 * 1024)
+    cudaFuncSetAttribute(bg_growth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+  bg_growth_kernel<<<ncosmo, GROWTH_THREADS, gsm, stream>>>(ncosmo, na, d_a, d_params, a_init, hmax, seg_cap, d_growth,
+                                                            d_fgrowth, d_growth0);
 }
 
 }  // namespace cclb
