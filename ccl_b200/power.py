@@ -12,6 +12,9 @@ from .background import omega_x
 from .synthetic import linlog_spacing, log_spacing
 
 _GLX, _GLW = np.polynomial.legendre.leggauss(16)
+# quadrature panels per 25 e-folds of k and root tolerance of the halofit moments: the constants of
+# csrc/builders.cu (HF_PANELS, HF_ROOT_TOL), see the convergence table there
+HF_PANELS, HF_ROOT_TOL = 100, 1e-10
 
 
 def _gl_nodes(lo, hi, npanel):
@@ -187,7 +190,7 @@ def halofit_table(p, a_arr, lk_arr, logplin):
 
         def moments(R, which):
             lnkmax = max(lnkmax_t, np.log(30. / R))
-            x, w = _gl_nodes(lnkmin, lnkmax, int(400 * max(1.0, (lnkmax - lnkmin) / 25.0)))
+            x, w = _gl_nodes(lnkmin, lnkmax, int(HF_PANELS * max(1.0, (lnkmax - lnkmin) / 25.0)))
             kk = np.exp(x)
             k2 = kk * kk
             base = _plin_row_eval(spl, lk_arr, x) * kk * k2 / 2.0 / np.pi / np.pi * np.exp(-k2 * R * R)
@@ -207,7 +210,7 @@ def halofit_table(p, a_arr, lk_arr, logplin):
             flo = f(lo)
         if flo * f(hi) > 0:
             raise RuntimeError("could not solve for non-linear scale for halofit at scale factor %f" % a_arr[i])
-        lnr = brentq(f, lo, hi, xtol=1e-13, rtol=1e-13)
+        lnr = brentq(f, lo, hi, xtol=HF_ROOT_TOL, rtol=HF_ROOT_TOL)
         R = np.exp(lnr)
         rsigma[i] = R
         sigma2[i] = moments(R, 0)
