@@ -26,8 +26,6 @@
 
 namespace cclb {
 
-cudaError_t launch_limber_fast_v1(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream);
-
 namespace {
 
 #ifndef CCLB_FW
@@ -768,8 +766,6 @@ void launch_limber_group(const LimberProblem& prob, const FastPlan& plan, cudaSt
 }
 
 cudaError_t launch_limber_fast(const LimberProblem& prob, const FastPlan& plan, cudaStream_t stream) {
-  static const bool use_v1 = getenv("CCL_B200_FAST_V1") != nullptr;
-  if (use_v1) return launch_limber_fast_v1(prob, plan, stream);
   if (prob.ncosmo == 0 || prob.npair == 0 || prob.nl == 0) return cudaSuccess;
   if ((long long)prob.ncosmo * prob.nl > 0x7fffffffLL) return cudaErrorInvalidValue;
   launch_limber_group(prob, plan, stream);

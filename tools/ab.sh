@@ -1,10 +1,8 @@
-# usage: bash tools/ab.sh [lib names...]; default: the in-tree build.  A name "v1" runs the default build with
-# CCL_B200_FAST_V1=1 (round-1 kernel kept for A/B).
+# usage: bash tools/ab.sh [lib names...]; default: the in-tree build (variants: tools/build_variants.sh).
 libs="$@"; [ -z "$libs" ] && libs="libccl_b200"
 for v in $libs; do
   echo "== $v"
   lib=$PWD/ccl_b200/$v.so; extra=""
-  if [ "$v" = "v1" ]; then lib=$PWD/ccl_b200/libccl_b200.so; export CCL_B200_FAST_V1=1; else unset CCL_B200_FAST_V1; fi
   CCL_B200_LIB=$lib python bench.py --ncosmo ${NCOSMO:-512} --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --from-parameters 0 --qag-sample 0 --no-y10 2>&1 | python -c "
 import sys,json
 for ln in sys.stdin:
