@@ -696,7 +696,7 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
   double* dco = tmp + nk;  // d coefficients
   double* alpha = dco + nk;  // LDL^T factors of the natural-spline system of the ln k grid: the same
   double* gamma = alpha + nk;  // for every scale factor of the group, computed once per CTA
-  __shared__ double red[3][256];
+  __shared__ double red[3][8];   // warp partials of the three moments (blockDim = 256)
   __shared__ double glx[16], glw[16];  // lane-varying node index: shared memory, not the constant cache
   if (threadIdx.x < 16) { glx[threadIdx.x] = GL16_X[threadIdx.x]; glw[threadIdx.x] = GL16_W[threadIdx.x]; }
   const int ic = blockIdx.x;
@@ -803,17 +803,18 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
       a1 += base * (-k2 * 2.0 * R);
       a2 += base * (-2.0 * k2 + 4.0 * k2 * k2 * R * R);
     }
-    red[0][threadIdx.x] = a0; red[1][threadIdx.x] = a1; red[2][threadIdx.x] = a2;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) {
-        red[0][threadIdx.x] += red[0][threadIdx.x + o];
-        red[1][threadIdx.x] += red[1][threadIdx.x + o];
-        red[2][threadIdx.x] += red[2][threadIdx.x + o];
-      }
-      __syncthreads();
+    // warp sums by shuffles, then the eight warp partials through shared memory: two barriers per call
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
     }
-    m0 = red[0][0]; m1 = red[1][0]; m2 = red[2][0];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][w] = a0; red[1][w] = a1; red[2][w] = a2; }
+    __syncthreads();
+    m0 = 0.0; m1 = 0.0; m2 = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { m0 += red[0][q]; m1 += red[1][q]; m2 += red[2][q]; }
     __syncthreads();
   };
   // ---- sigma(R) = 1 (get_rsigma, src/ccl_halofit.c:259-315, root searched in [1e-64, 1e16] Mpc there):
@@ -871,41 +872,53 @@ halofit_kernel(int nk, const double* __restrict__ lk_grid, int na, const double*
   const double Cc = -1.0 * (m2 * R * R / sigma2 + ds * R / sigma2 - ds * ds * R * R / sigma2 / sigma2);
   if (threadIdx.x == 0) rsigma_out[oidx] = R;
   // ---- ccl_halofit_power (src/ccl_halofit.c:828-930), f_nu = 0 ----
-  const double a = a_grid[ia];
-  const double hn = h_over_h0(p, a);
-  const double om = (p[P_OC] + p[P_OB]) / (a * a * a) / hn / hn;
-  const double ode = p[P_OL] * pow(a, -3 * (1 + p[P_W0] + p[P_WA])) * exp(3 * p[P_WA] * (a - 1)) / hn / hn;
-  const double weffa = p[P_W0];
-  const double ksigma = 1.0 / R;
-  const double n1 = neff, n2 = n1 * n1, n3 = n2 * n1, n4 = n2 * n2;
-  const double an = pow(10.0, 1.5222 + 2.8553 * n1 + 2.3706 * n2 + 0.9903 * n3 + 0.2250 * n4 - 0.6038 * Cc +
-                                  0.1749 * ode * (1.0 + weffa));
-  const double bn = pow(10.0, -0.5642 + 0.5864 * n1 + 0.5716 * n2 - 1.5474 * Cc + 0.2279 * ode * (1.0 + weffa));
-  const double cn = pow(10.0, 0.3698 + 2.0404 * n1 + 0.8161 * n2 + 0.5869 * Cc);
-  const double gamman = 0.1971 - 0.0843 * n1 + 0.8460 * Cc;
-  const double alphan = fabs(6.0835 + 1.3373 * n1 - 0.1959 * n2 - 5.5274 * Cc);
-  const double betan = 2.0379 - 0.7354 * n1 + 0.3157 * n2 + 1.2490 * n3 + 0.3980 * n4 - 0.1682 * Cc;
-  const double nun = pow(10.0, 5.2105 + 3.6902 * n1);
-  double f1 = 1.0, f2 = 1.0, f3 = 1.0;
-  if (fabs(1.0 - om) > 0.01) {
-    const double f1a = pow(om, -0.0732), f2a = pow(om, -0.1423), f3a = pow(om, 0.0725);
-    const double f1b = pow(om, -0.0307), f2b = pow(om, -0.0585), f3b = pow(om, 0.0743);
-    const double fb = ode / (1.0 - om);
-    f1 = fb * f1b + (1.0 - fb) * f1a;
-    f2 = fb * f2b + (1.0 - fb) * f2a;
-    f3 = fb * f3b + (1.0 - fb) * f3a;
+  // the coefficients of the fit (eleven powers) are formed by one thread and shared; in the loop over k the powers of
+  // y = k R_sigma are exponentials of multiples of ln y = ln k + ln R_sigma, which needs no logarithm
+  __shared__ double hf[12];
+  if (threadIdx.x == 0) {
+    const double a = a_grid[ia];
+    const double hn = h_over_h0(p, a);
+    const double om = (p[P_OC] + p[P_OB]) / (a * a * a) / hn / hn;
+    const double ode = p[P_OL] * pow(a, -3 * (1 + p[P_W0] + p[P_WA])) * exp(3 * p[P_WA] * (a - 1)) / hn / hn;
+    const double weffa = p[P_W0];
+    const double n1 = neff, n2 = n1 * n1, n3 = n2 * n1, n4 = n2 * n2;
+    const double an = pow(10.0, 1.5222 + 2.8553 * n1 + 2.3706 * n2 + 0.9903 * n3 + 0.2250 * n4 - 0.6038 * Cc +
+                                    0.1749 * ode * (1.0 + weffa));
+    const double bn = pow(10.0, -0.5642 + 0.5864 * n1 + 0.5716 * n2 - 1.5474 * Cc + 0.2279 * ode * (1.0 + weffa));
+    const double cn = pow(10.0, 0.3698 + 2.0404 * n1 + 0.8161 * n2 + 0.5869 * Cc);
+    const double gamman = 0.1971 - 0.0843 * n1 + 0.8460 * Cc;
+    const double alphan = fabs(6.0835 + 1.3373 * n1 - 0.1959 * n2 - 5.5274 * Cc);
+    const double betan = 2.0379 - 0.7354 * n1 + 0.3157 * n2 + 1.2490 * n3 + 0.3980 * n4 - 0.1682 * Cc;
+    const double nun = pow(10.0, 5.2105 + 3.6902 * n1);
+    double f1 = 1.0, f2 = 1.0, f3 = 1.0;
+    if (fabs(1.0 - om) > 0.01) {
+      const double f1a = pow(om, -0.0732), f2a = pow(om, -0.1423), f3a = pow(om, 0.0725);
+      const double f1b = pow(om, -0.0307), f2b = pow(om, -0.0585), f3b = pow(om, 0.0743);
+      const double fb = ode / (1.0 - om);
+      f1 = fb * f1b + (1.0 - fb) * f1a;
+      f2 = fb * f2b + (1.0 - fb) * f2a;
+      f3 = fb * f3b + (1.0 - fb) * f3a;
+    }
+    hf[0] = an; hf[1] = bn; hf[2] = log(cn * f3); hf[3] = 3.0 - gamman; hf[4] = alphan; hf[5] = betan; hf[6] = nun;
+    hf[7] = 3.0 * f1; hf[8] = f2;
   }
-  for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-    const double k = exp(lk[i]);
-    const double delta2_norm = k * k * k / 2.0 / M_PI / M_PI;
-    const double PkL = exp(row[i]);
-    const double y = k / ksigma, y2 = y * y;
-    const double fy = y / 4.0 + y2 / 8.0;
-    const double DeltakL = PkL * delta2_norm;
-    const double DeltakQ = DeltakL * pow(1.0 + DeltakL, betan) / (1.0 + alphan * DeltakL) * exp(-fy);
-    const double DeltakHprime = an * pow(y, 3.0 * f1) / (1.0 + bn * pow(y, f2) + pow(cn * f3 * y, 3.0 - gamman));
-    const double DeltakH = DeltakHprime / (1.0 + nun / y2);
-    logpnl[oidx * nk + i] = log((DeltakQ + DeltakH) / delta2_norm);
+  __syncthreads();
+  {
+    const double an = hf[0], bn = hf[1], lcf = hf[2], e3 = hf[3], alphan = hf[4], betan = hf[5], nun = hf[6],
+                 e1 = hf[7], e2 = hf[8];
+    const double lnR = log(R), ln2pi2 = log(2.0 * M_PI * M_PI);
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+      const double lki = lk[i];
+      const double ld2 = 3.0 * lki - ln2pi2;       // ln(k^3 / (2 pi^2))
+      const double lny = lki + lnR;                // ln(k / k_sigma)
+      const double y = exp(lny), y2 = y * y;
+      const double fy = y / 4.0 + y2 / 8.0;
+      const double DeltakL = exp(row[i] + ld2);
+      const double DeltakQ = DeltakL * exp(betan * log1p(DeltakL) - fy) / (1.0 + alphan * DeltakL);
+      const double DeltakHprime = an * exp(e1 * lny) / (1.0 + bn * exp(e2 * lny) + exp(e3 * (lcf + lny)));
+      const double DeltakH = DeltakHprime / (1.0 + nun / y2);
+      logpnl[oidx * nk + i] = log(DeltakQ + DeltakH) - ld2;
+    }
   }
   }  // scale factors of the group
 }
