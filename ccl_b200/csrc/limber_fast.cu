@@ -29,13 +29,13 @@ namespace cclb {
 namespace {
 
 #ifndef CCLB_FW
-#define CCLB_FW 8
+#define CCLB_FW 5
 #endif
 #ifndef CCLB_NPL
 #define CCLB_NPL 2
 #endif
 #ifndef CCLB_MINB
-#define CCLB_MINB 3
+#define CCLB_MINB 4
 #endif
 #ifndef CCLB_TR_UNROLL
 #define CCLB_TR_UNROLL 1
