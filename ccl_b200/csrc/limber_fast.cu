@@ -519,18 +519,25 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
         const GridPair pr = gpairs[gd.pair_begin + lane];
         W.po[lane] = make_int2(pr.a * CH, pr.b * CH);
       }
+      FastEnt en;
+      en.flags = 0u;
       if (lane < min(nsub, NSG)) {
         const unsigned ent = gsubs[gd.sub_begin + lane];
         const FastTr& tr = s_tr[ent & 0xffu];
-        FastEnt en;
         en.kcr = tr.kernel.cr;
         en.pref = tr.pref[ls];
         en.acr = tr.has_fa ? tr.fa.cr : nullptr;
-        const char* self = reinterpret_cast<const char*>(&W.ents[lane]);
-        const unsigned drow = (unsigned)(reinterpret_cast<const char*>(&W.dflat[((ent >> 8) & 0xfu) * CH]) - self) >> 4;
-        en.flags = (ent & 0xffffu) | ((RSD && tr.der_bessel >= 1) ? SUB_RSD : 0u) | (drow << 16);
-        en.troff = (int)(reinterpret_cast<const char*>(&tr) - self);
-        W.ents[lane] = en;
+        en.flags = (ent & 0xffffu) | ((RSD && tr.der_bessel >= 1) ? SUB_RSD : 0u) | (tr.has_fa ? SUB_HASA : 0u);
+        en.addr = (unsigned)__cvta_generic_to_shared(&W.dflat[((ent >> 8) & 0xfu) * CH]);
+      }
+      {  // entries of the spline-grid group a NEWK entry opens: distance to the next NEWK entry (or the end)
+        const int ne = min(nsub, NSG);
+        const unsigned heads = __ballot_sync(FULL, lane < ne && (en.flags & SUB_NEWK)) | (1u << ne);
+        if (lane < ne) {
+          const unsigned later = heads >> (lane + 1);
+          en.flags |= (unsigned)__ffs(later) << 16;
+          W.ents[lane] = en;
+        }
       }
       const bool task_rsd = RSD && gd.has_rsd;
       const int nk = S.gp[gl].nk;
@@ -602,57 +609,65 @@ limber_spline_fast_kernel(const LimberProblem P, const FastPlan G) {
             // 32-byte coefficient record.  Outside a kernel's support the lookup runs on the first / last
             // interval and the term is dropped (ccl_f1d_t_eval: the end nodes count as outside,
             // src/ccl_f1d.c:137-161).
-            int ki = 0, ai = 0;
-            double kdel = 0.0, adel = 0.0;
-            bool inside = false;
+            // The list is walked group by group: the entries of a spline-grid group share one interval search in chi
+            // (done at the head of the group), each then reads its own 32-byte coefficient record and adds into the
+            // D row of its collection (absolute shared-memory address kept in the entry).
+            int ai = 0;
+            double adel = 0.0;
             const FastEnt* ep = W.ents;
-#pragma unroll TRU
-            for (int e = 0; e < nsub; ++e, ++ep) {
-              const FastEnt en = *ep;
-              const unsigned ent = en.flags;
-              if (__builtin_expect((ent & SUB_NEWK) != 0u, 0)) {
-                const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
-                double x0;
-                ki = find_interval(tr.kernel, chi, x0);
-                kdel = chi - x0;
-                inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
-              }
-              double wt = cubic(ldg4(en.kcr + ki), kdel);
-              if (en.acr != nullptr) {
-                if (__builtin_expect((ent & SUB_NEWA) != 0u, 0)) {
-                  const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
-                  const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
+            const unsigned j8 = (unsigned)j * 8u;
+            int e = 0;
+#pragma unroll 1
+            while (e < nsub) {
+              const FastEnt hd = *ep;
+              const FastTr& trk = s_tr[hd.flags & 0xffu];
+              double x0k;
+              const int ki = find_interval(trk.kernel, chi, x0k);
+              const double kdel = chi - x0k;
+              const bool inside = (chi > trk.kernel.x0) && (chi < trk.kernel.xn);
+              const int gend = e + (int)((hd.flags >> 16) & 63u);
+#pragma unroll 1
+              do {
+                const FastEnt en = *ep;
+                const unsigned ent = en.flags;
+                double wt = cubic(ldg4(en.kcr + ki), kdel);
+                if (ent & SUB_HASA) {
+                  if (__builtin_expect((ent & SUB_NEWA) != 0u, 0)) {
+                    const FastTr& tr = s_tr[ent & 0xffu];
+                    const double a_ev = fmin(fmax(a, tr.fa.x0), tr.fa.xn);
+                    double x0;
+                    ai = find_interval(tr.fa, a_ev, x0);
+                    adel = a_ev - x0;
+                  }
+                  wt *= cubic(ldg4(en.acr + ai), adel);
+                }
+                double val = inside ? wt * en.pref : 0.0;
+                if (RSD && (ent & SUB_RSD)) {
+                  const FastTr& tr = s_tr[ent & 0xffu];
+                  // w t at chi is `inside ? wt : 0`; the second point has its own support test
+                  const double l = lp1h - 0.5, lp3h = lp1h + 1.0;
+                  const double w_t = inside ? wt : 0.0;
+                  const bool inside_p = (chi_lp > tr.kernel.x0) && (chi_lp < tr.kernel.xn);
                   double x0;
-                  ai = find_interval(tr.fa, a_ev, x0);
-                  adel = a_ev - x0;
+                  const int ip = find_interval(tr.kernel, chi_lp, x0);
+                  double wt_p = cubic(ldg4(tr.kernel.cr + ip), chi_lp - x0);
+                  if (tr.has_fa) {
+                    const double a_ev = fmin(fmax(a_lp, tr.fa.x0), tr.fa.xn);
+                    const int ia = find_interval(tr.fa, a_ev, x0);
+                    wt_p *= cubic(ldg4(tr.fa.cr + ia), a_ev - x0);
+                  }
+                  if (!inside_p) wt_p = 0.0;
+                  double dd;
+                  if (tr.der_bessel == 1) dd = l * w_t / lp1h - sqell * wt_p;
+                  else dd = sqell * 2 * wt_p / lp3h - (0.25 + 2 * l) * w_t / (lp1h * lp1h);
+                  val = dd * en.pref;
                 }
-                wt *= cubic(ldg4(en.acr + ai), adel);
-              }
-              double val = inside ? wt * en.pref : 0.0;
-              if (RSD && (ent & SUB_RSD)) {
-                const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
-                // w t at chi is `inside ? wt : 0`; the second point has its own support test
-                const double l = lp1h - 0.5, lp3h = lp1h + 1.0;
-                const double w_t = inside ? wt : 0.0;
-                const bool inside_p = (chi_lp > tr.kernel.x0) && (chi_lp < tr.kernel.xn);
-                double x0;
-                const int ip = find_interval(tr.kernel, chi_lp, x0);
-                double wt_p = cubic(ldg4(tr.kernel.cr + ip), chi_lp - x0);
-                if (tr.has_fa) {
-                  const double a_ev = fmin(fmax(a_lp, tr.fa.x0), tr.fa.xn);
-                  const int ia = find_interval(tr.fa, a_ev, x0);
-                  wt_p *= cubic(ldg4(tr.fa.cr + ia), a_ev - x0);
-                }
-                if (!inside_p) wt_p = 0.0;
-                double dd;
-                if (tr.der_bessel == 1) dd = l * w_t / lp1h - sqell * wt_p;
-                else dd = sqell * 2 * wt_p / lp3h - (0.25 + 2 * l) * w_t / (lp1h * lp1h);
-                val = dd * en.pref;
-              }
-              double* dp = reinterpret_cast<double*>(const_cast<char*>(reinterpret_cast<const char*>(ep)) +
-                                                     ((ent >> 16) << 4)) + j;
-              if (!(ent & SUB_FIRST)) val += *dp;
-              *dp = val;
+                const unsigned da = en.addr + j8;
+                if (!(ent & SUB_FIRST)) val += lds_f64(da);
+                sts_f64(da, val);
+                ++ep;
+                ++e;
+              } while (e < gend);
             }
             k *= S.gp[gl].ratio;
             chi *= S.gp[gl].iratio;

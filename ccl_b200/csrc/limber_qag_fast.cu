@@ -268,7 +268,7 @@ limber_qag_fast_kernel(const LimberProblem P, const FastPlan G, double* ws, doub
         en.pref = pref * tr.pref[0];
         en.acr = tr.has_fa ? tr.fa.cr : nullptr;
         en.flags = ent & 0xfffu;
-        en.troff = (int)(reinterpret_cast<const char*>(&tr) - reinterpret_cast<const char*>(&W.ents[rank]));
+        en.addr = (unsigned)(reinterpret_cast<const char*>(&tr) - reinterpret_cast<const char*>(&W.ents[rank]));
         W.ents[rank] = en;
       }
       if (lane < ncoll) {
@@ -396,7 +396,7 @@ limber_qag_fast_kernel(const LimberProblem P, const FastPlan G, double* ws, doub
 #pragma unroll 1
                 for (int s = 0; s < cr.y; ++s, ++ep) {
                   const FastEnt en = *ep;
-                  const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + en.troff);
+                  const FastTr& tr = *reinterpret_cast<const FastTr*>(reinterpret_cast<const char*>(ep) + (int)en.addr);
                   double x0;
                   const int ki = find_interval(tr.kernel, chi, x0);
                   const bool inside = (chi > tr.kernel.x0) && (chi < tr.kernel.xn);
