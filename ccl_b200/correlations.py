@@ -10,48 +10,42 @@ from enum import Enum
 import numpy as np
 
 from . import _lib, lowlevel
-from .errors import check
+from .errors import CCLError, check
 
 __all__ = ("CorrelationMethods", "CorrelationTypes", "correlation")
 
+# name -> (user-facing string, C enum of include/ccl_correlation.h:6-12)
+_METHODS = {"FFTLOG": ("fftlog", _lib.CORR_FFTLOG), "BESSEL": ("bessel", _lib.CORR_BESSEL),
+            "LEGENDRE": ("legendre", _lib.CORR_LGNDRE)}
+_TYPES = {"NN": ("NN", _lib.CORR_GG), "NG": ("NG", _lib.CORR_GL), "GG_PLUS": ("GG+", _lib.CORR_LP),
+          "GG_MINUS": ("GG-", _lib.CORR_LM)}
 
-class CorrelationMethods(Enum):
-    """'Bessel' direct integration, 'FFTLog' fast Hankel transform, 'Legendre' brute-force sum."""
-    FFTLOG = "fftlog"
-    BESSEL = "bessel"
-    LEGENDRE = "legendre"
+#: 'bessel' direct integration, 'fftlog' fast Hankel transform, 'legendre' brute-force sum over multipoles
+CorrelationMethods = Enum("CorrelationMethods", {k: v[0] for k, v in _METHODS.items()})
+#: spin combinations: 0x0, 0x2, 2x2 (xi+), 2x2 (xi-)
+CorrelationTypes = Enum("CorrelationTypes", {k: v[0] for k, v in _TYPES.items()})
 
-
-class CorrelationTypes(Enum):
-    NN = "NN"
-    NG = "NG"
-    GG_PLUS = "GG+"
-    GG_MINUS = "GG-"
-
-
-correlation_methods = {'fftlog': _lib.CORR_FFTLOG, 'bessel': _lib.CORR_BESSEL, 'legendre': _lib.CORR_LGNDRE}
-correlation_types = {'NN': _lib.CORR_GG, 'NG': _lib.CORR_GL, 'GG+': _lib.CORR_LP, 'GG-': _lib.CORR_LM}
+correlation_methods = {label: code for label, code in _METHODS.values()}
+correlation_types = {label: code for label, code in _TYPES.values()}
 
 
 def correlation(cosmo, *, ell, C_ell, theta, type='NN', method='fftlog'):
-    """Angular correlation function at ``theta`` (degrees) from ``C_ell`` sampled at ``ell``."""
-    method = method.lower()
-    if type not in correlation_types:
+    """Angular correlation function at ``theta`` (degrees) from ``C_ell`` sampled at ``ell``; ``type`` in
+    'NN', 'NG', 'GG+', 'GG-' and ``method`` in 'fftlog', 'bessel', 'legendre' (case-insensitive)."""
+    code_m = correlation_methods.get(method.lower())
+    code_t = correlation_types.get(type)
+    if code_t is None:
         raise ValueError(f"Invalid correlation type {type}.")
-    if method not in correlation_methods.keys():
-        raise ValueError(f"Invalid correlation method {method}.")
-    if scalar := isinstance(theta, (int, float)):
-        theta = np.array([theta, ])
-    status = 0
-    if np.all(np.array(C_ell) == 0):
-        wth = np.zeros_like(theta)  # short-cut and also avoid integration errors
+    if code_m is None:
+        raise ValueError(f"Invalid correlation method {method.lower()}.")
+    is_scalar = isinstance(theta, (int, float))
+    th = np.array([theta]) if is_scalar else theta
+    if not np.any(np.asarray(C_ell)):
+        # an all-zero spectrum transforms to zero (and its power-law extrapolation has no slope to take)
+        xi = np.zeros_like(th)
     else:
         if np.shape(ell) != np.shape(C_ell):
-            from .errors import CCLError
             raise CCLError("Input shape for `larr` must match `clarr`!")  # pyccl/ccl_correlation.i:22-24
-        wth, status = lowlevel.correlation(cosmo._device(), ell, C_ell, theta, correlation_types[type],
-                                           correlation_methods[method])
-    check(status, cosmo)
-    if scalar:
-        return wth[0]
-    return wth
+        xi, status = lowlevel.correlation(cosmo._device(), ell, C_ell, th, code_t, code_m)
+        check(status, cosmo)
+    return xi[0] if is_scalar else xi
