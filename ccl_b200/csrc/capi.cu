@@ -800,6 +800,7 @@ struct ccl_b200_f3d {  // ccl_f3d_t: the planes are the P tables of a TableSet w
 };
 struct ccl_b200_tracer { TableSet ts; double chi_min, chi_max; int der_bessel, der_angles; };
 struct ccl_b200_collection { std::vector<ccl_b200_tracer*> ts; };
+struct ccl_b200_tables;
 struct ccl_b200_batch {
   ccl_b200_params params;
   TableSet ts;
@@ -821,12 +822,23 @@ struct ccl_b200_batch {
   std::vector<int> plan_key;
   unsigned long long plan_commit = ~0ull;
   cudaEvent_t plan_event = nullptr;
+  // table builders whose halofit pass this batch's next commit waits for (ccl_b200_batch_set_from_tables)
+  std::vector<const ccl_b200_tables*> table_deps;
 };
 
 struct ccl_b200_tables {
   int device = 0;
   int ncosmo = 0, na = 0, stride = 0, nk = 0, na_pk = 0, nz = 0, ntr = 0, nchi = 0;
   bool has_nl = false;
+  // halofit runs on its own stream behind the linear table and is still in flight when ccl_b200_tables_build
+  // returns: the caller plans its batch (host work) meanwhile.  Consumers of d_nl wait for ev_nl on their stream
+  // (ccl_b200_batch_set_from_tables); the kernel's failure flag is read by the commit that follows.
+  cudaStream_t s_nl = nullptr;
+  cudaEvent_t ev_nl = nullptr;
+  ~ccl_b200_tables() {
+    if (s_nl) { cudaStreamSynchronize(s_nl); cudaStreamDestroy(s_nl); }
+    if (ev_nl) cudaEventDestroy(ev_nl);
+  }
   DevBuf buf;
   double *d_par = nullptr, *d_a = nullptr, *d_E = nullptr, *d_chi = nullptr, *d_gx = nullptr, *d_ga = nullptr,
          *d_D = nullptr, *d_f = nullptr, *d_g0 = nullptr, *d_k = nullptr, *d_lk = nullptr, *d_apk = nullptr,
@@ -1835,11 +1847,14 @@ void ccl_b200_batch_reset(ccl_b200_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ts.device);
   b->ts.reset();
+  b->table_deps.clear();
 }
+
+static void check_table_deps(ccl_b200_batch* b, int* status);
 
 void ccl_b200_batch_commit(ccl_b200_batch* b, int* status) {
   if (*status || !b) return;
-  b->ts.commit(b->prep_stream, status);
+  if (b->ts.commit(b->prep_stream, status)) check_table_deps(b, status);
 }
 
 unsigned long long ccl_b200_batch_h2d_bytes(const ccl_b200_batch* b) { return b->ts.last_h2d; }
@@ -2259,8 +2274,6 @@ ccl_b200_tables* ccl_b200_tables_build(int ncosmo, const double* params, int na,
   launch_chi_at(ncosmo, na, t->d_a, t->d_chi, a_spline_min, t->d_cmax, st);
   launch_build_linpower(ncosmo, nk, t->d_k, na_pk, t->d_apk, na, t->d_a, t->d_D, t->d_par, model, log10(k_min),
                         log10(k_max), t->d_lin, t->d_s8, st);
-  if (halofit)
-    launch_build_halofit(ncosmo, nk, t->d_lk, na_pk, t->d_apk, t->d_lin, t->d_par, t->d_nl, t->d_rs, t->d_fail, st);
   if (ntr > 0) {
     cudaMemcpyAsync(t->d_z, z, (size_t)nz * 8, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(t->d_nz, nz_arr, nt * nz * 8, cudaMemcpyHostToDevice, st);
@@ -2282,6 +2295,19 @@ ccl_b200_tables* ccl_b200_tables_build(int ncosmo, const double* params, int na,
     launch_tracer_ranges(ncosmo, ntr, nz, t->d_chiz, 0, t->d_wnc, t->d_rng, st);
     launch_tracer_ranges(ncosmo, ntr, nchi, t->d_chil, 0, t->d_wl, t->d_rng + nc * nt * 4, st);
   }
+  if (halofit) {
+    cudaEvent_t ev_lin = nullptr;
+    cudaStreamCreateWithFlags(&t->s_nl, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ev_lin, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&t->ev_nl, cudaEventDisableTiming);
+    // launched after the tracer kernels so that their CTAs are dispatched first: the host waits for those (and
+    // the ranges) only, and plans the batch while halofit runs
+    cudaEventRecord(ev_lin, st);
+    cudaStreamWaitEvent(t->s_nl, ev_lin, 0);
+    launch_build_halofit(ncosmo, nk, t->d_lk, na_pk, t->d_apk, t->d_lin, t->d_par, t->d_nl, t->d_rs, t->d_fail, t->s_nl);
+    cudaEventRecord(t->ev_nl, t->s_nl);
+    cudaEventDestroy(ev_lin);
+  }
   if (!cuda_ok(cudaGetLastError(), "table builder launch", status)) { delete t; return nullptr; }
   if (!cuda_ok(cudaStreamSynchronize(st), "table builders", status)) { delete t; return nullptr; }
   // host metadata (small): sizes and end nodes
@@ -2300,8 +2326,6 @@ ccl_b200_tables* ccl_b200_tables_build(int ncosmo, const double* params, int na,
     cudaMemcpy(t->h_rng_nc.data(), t->d_rng, nc * nt * 4 * 8, cudaMemcpyDeviceToHost);
     cudaMemcpy(t->h_rng_l.data(), t->d_rng + nc * nt * 4, nc * nt * 4 * 8, cudaMemcpyDeviceToHost);
   }
-  int failed = 0;
-  cudaMemcpy(&failed, t->d_fail, 4, cudaMemcpyDeviceToHost);
   for (size_t i = 0; i < nc; ++i)
     if (t->h_nachi[i] < 5) {
       *status = CCL_B200_ERROR_MEMORY;
@@ -2309,13 +2333,22 @@ ccl_b200_tables* ccl_b200_tables_build(int ncosmo, const double* params, int na,
       delete t;
       return nullptr;
     }
-  if (failed) {
-    *status = CCL_B200_ERROR_INTEG;
-    set_err("ccl_halofit.c: could not solve for non-linear scale for halofit");
-    delete t;
-    return nullptr;
-  }
   return t;
+}
+
+// the halofit pass of a table set has finished (its consumers were ordered behind ev_nl): report its failure flag
+static void check_table_deps(ccl_b200_batch* b, int* status) {
+  for (const ccl_b200_tables* t : b->table_deps) {
+    if (!t->ev_nl) continue;
+    cudaEventSynchronize(t->ev_nl);
+    int failed = 0;
+    cudaMemcpy(&failed, t->d_fail, 4, cudaMemcpyDeviceToHost);
+    if (failed && !*status) {
+      *status = CCL_B200_ERROR_INTEG;
+      set_err("ccl_halofit.c: could not solve for non-linear scale for halofit");
+    }
+  }
+  b->table_deps.clear();
 }
 
 void ccl_b200_tables_free(ccl_b200_tables* t) {
@@ -2333,6 +2366,11 @@ void ccl_b200_batch_set_from_tables(ccl_b200_batch* b, int first, const ccl_b200
     return;
   }
   const double* pk = (t->has_nl && !use_linear) ? t->d_nl : t->d_lin;
+  if (t->ev_nl && pk == t->d_nl) {  // the halofit table may still be in the making: order this batch's streams behind it
+    cudaStreamWaitEvent(b->prep_stream, t->ev_nl, 0);
+    cudaStreamWaitEvent(b->stream, t->ev_nl, 0);
+    b->table_deps.push_back(t);
+  }
   const int gu = TableSet::quasi_uniform(t->h_a.data(), t->na);
   for (int i = 0; i < t->ncosmo; ++i) {
     CosmoPlan& p = b->ts.cosmos[first + i];

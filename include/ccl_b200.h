@@ -349,7 +349,9 @@ typedef struct ccl_b200_tables ccl_b200_tables;
  * host-in/out entries; halofit != 0 also builds the non-linear P(k); nz_arr / sz_arr / inv_norm / lens_scale
  * describe ntr redshift distributions (lens_scale[ntr], may be NULL, multiplies the lensing kernel; 0 = not built; e.g.
  * -2 for a magnification term).  The object must outlive ccl_b200_batch_commit of every batch filled
- * from it (the preparation kernels read its tables in place). */
+ * from it (the preparation kernels read its tables in place).  The halofit pass is still running on its own stream
+ * when the call returns -- the caller's batch planning overlaps it; ccl_b200_batch_set_from_tables orders the batch
+ * behind it and the following ccl_b200_batch_commit reports CCL_B200_ERROR_INTEG if sigma(R) = 1 had no root. */
 ccl_b200_tables *ccl_b200_tables_build(int ncosmo, const double *params, int na, const double *a_grid,
                                        double dchi, double root_epsrel, int root_niter, double a_growth_init,
                                        int achi_stride, double a_spline_min, int model, int halofit, int nk,
