@@ -338,13 +338,20 @@ __global__ void bicubic_deriv_kernel(const BicubicJob* jobs, int pass) {
       natural_spline_node_derivs<1>(jb.ya, na, tab + (size_t)t * 4, (size_t)nk * 4, yoff, ooff,
                                     axis_factors(jb.scratch + 4 * nk, na));
     }
-  } else {
-    if (t < na) {
-      const int yoff[2] = {0, 2}, ooff[2] = {1, 3};
-      natural_spline_node_derivs<2>(jb.xk, nk, tab + (size_t)t * nk * 4, 4, yoff, ooff,
-                                    axis_factors(jb.scratch, nk));
-    }
   }
+}
+
+// Pass 2 over the rows of ALL jobs as one index space (row r of job r / max_na): with one CTA row per job a table of
+// 50 scale factors leaves 14 of every 64 lanes idle through the whole serial sweep; here only the last warp is partial.
+__global__ void bicubic_rows_kernel(const BicubicJob* jobs, int njobs, int max_na) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (int)(r / max_na), t = (int)(r % max_na);
+  if (j >= njobs) return;
+  const BicubicJob jb = jobs[j];
+  if (t >= jb.na) return;
+  const int yoff[2] = {0, 2}, ooff[2] = {1, 3};
+  natural_spline_node_derivs<2>(jb.xk, jb.nk, reinterpret_cast<double*>(jb.tab) + (size_t)t * jb.nk * 4, 4, yoff, ooff,
+                                axis_factors(jb.scratch, jb.nk));
 }
 
 void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs, const LutJob* d_lut,
@@ -364,9 +371,10 @@ void launch_prep(const AkimaJob* d_ak, int nak, const CsplineJob* d_cs, int ncs,
   }
   if (nbc > 0) {
     bicubic_factor_kernel<<<nbc, 256, 0, stream>>>(d_bc);
-    dim3 g1((max_nk + 63) / 64, nbc), g2((max_na + 31) / 32, nbc);
+    dim3 g1((max_nk + 63) / 64, nbc);
     bicubic_deriv_kernel<<<g1, 64, 0, stream>>>(d_bc, 1);
-    bicubic_deriv_kernel<<<g2, 32, 0, stream>>>(d_bc, 2);
+    const long long nrows = (long long)nbc * max_na;
+    bicubic_rows_kernel<<<(unsigned)((nrows + 31) / 32), 32, 0, stream>>>(d_bc, nbc, max_na);
   }
 }
 
