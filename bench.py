@@ -536,7 +536,11 @@ def _main(json_out):
         d_cl2 = torch.empty((nfp, npair, nl), dtype=torch.float64, device="cuda")
         d_st2 = torch.zeros((2, nfp, npair), dtype=torch.int32, device="cuda")
         reps = []
-        for _ in range(5):   # the median of five passes: buffer allocation of the first ones is still settling
+        import gc
+        gc.collect()
+        gc.disable()         # a generation-2 collection over the harness's own objects (the 4096 Cosmology objects, the
+                             # e2e leg's chunk lists) landing inside a pass would add tens of ms to it
+        for _ in range(5):   # the median of five passes
             del fp_tabs
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -547,6 +551,7 @@ def _main(json_out):
             torch.cuda.synchronize()
             t2 = time.perf_counter()
             reps.append((t2 - t0, t0, t1, t2))
+        gc.enable()
         _, t0, t1, t2 = sorted(reps)[2]
         same = float(torch.max(torch.abs(d_cl2 - d_cl[:nfp]) / torch.clamp(torch.abs(d_cl[:nfp]), min=1e-300)).item())
         from_parameters = {"cosmologies": nfp, "cosmologies_per_s": nfp / (t2 - t0), "C_ell_per_s": nfp * npair * nl / (t2 - t0),
