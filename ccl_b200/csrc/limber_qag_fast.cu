@@ -80,7 +80,9 @@ __device__ __forceinline__ double qwarp_sum(double v) {
 __device__ __forceinline__ double q_rescale_error(double err, double result_abs, double result_asc) {
   err = fabs(err);
   if (result_asc != 0 && err != 0) {
-    const double scale = pow((200 * err / result_asc), 1.5);
+    // pow(x, 1.5) as x sqrt(x): both are correctly rounded to within an ulp, and the value only ranks intervals
+    const double x = 200 * err / result_asc;
+    const double scale = x * sqrt(x);
     err = (scale < 1) ? result_asc * scale : result_asc;
   }
   if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
