@@ -295,3 +295,19 @@ def test_fkem_reference_n5k_benchmark(n5k, cross_type, stride):
         chi2max = max(chi2max, chi2.max())
         assert np.all(chi2 < 0.3), (cross_type, i1, i2, chi2.max(), meta)
     print("N5K %s: worst chi2 %.4f" % (cross_type, chi2max))
+
+
+# ---- host helpers of the FKEM integrator (CPU) ----
+def test_fkem_host_helpers():
+    from ccl_b200 import nonlimber
+    # bessel-derivative type -> (nu, derivative order, power law): pyccl/nonlimber/_nonlimber_FKEM.py:20-43
+    assert nonlimber._general_params(0) == (1.01, 0.0, 0.0)
+    assert nonlimber._general_params(-1) == (1.01, 0.0, -2.0)
+    assert nonlimber._general_params(1) == (1.01, 1.0, 0.0)
+    assert nonlimber._general_params(2) == (1.01, 2.0, 0.0)
+    # the common k grid is the overlap of all grids, log-spaced with the largest sample count (:46-68)
+    k1 = [np.geomspace(1e-4, 10., 50), np.geomspace(2e-4, 20., 64)]
+    k2 = [np.geomspace(5e-5, 5., 40)]
+    k = nonlimber._k_common(k1, k2)
+    assert k.size == 64 and np.isclose(k[0], 2e-4) and np.isclose(k[-1], 5.0)
+    assert np.allclose(np.diff(np.log(k)), np.log(5.0 / 2e-4) / 63)
